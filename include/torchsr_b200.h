@@ -1,0 +1,190 @@
+/*
+ * torchsr_b200 C ABI — the drop-in boundary of the SRGAN/ESRGAN generator+discriminator hot path.
+ *
+ * The reference (roclark/torchsr) has no FFI: every FLOP is an ATen call made from nn.Module.forward and
+ * autograd. This header is what the Python modules in torchsr_b200/ bind with ctypes in place
+ * of those ATen calls; all pointers are raw device pointers, streams are cudaStream_t passed as void*, and
+ * every entry point returns 0 or a negative error code (message via tsr_last_error()). No torch types.
+ *
+ * Entry point                      replaces (reference file:line)
+ * -------------------------------  ---------------------------------------------------------------------------
+ * tsr_conv / tsr_prog_add_conv     aten::convolution forward and its data gradient for every nn.Conv2d and
+ *                                  nn.Linear on the path: srgan/generator.py:38,48,58  srgan/residual.py:27,64,67
+ *                                  srgan/discriminator.py:31-69  esrgan/generator.py:34-52  esrgan/residual.py:33-52
+ *                                  esrgan/discriminator.py:31-77; fused epilogues replace nn.PReLU/LeakyReLU
+ *                                  (residual.py:29,66), nn.PixelShuffle (residual.py:28), the residual adds
+ *                                  (residual.py:91, generator.py:78, esrgan/residual.py:86,129) and emit the
+ *                                  BatchNorm batch statistics (residual.py:65,68).
+ * tsr_wgrad / tsr_prog_add_wgrad   aten::convolution_backward (weight gradient) of the same layers.
+ * tsr_elt / tsr_prog_add_elt       the HBM-bound remainder: layout conversion, BatchNorm finalize / apply /
+ *                                  backward, activation backward, PixelShuffle/nearest-upsample index maps,
+ *                                  loss reductions (srgan/trainer.py:163-165,384), weight pack / grad unpack,
+ *                                  Linear weight gradient, classifier head (discriminator.py:64-69).
+ * tsr_prog_*                       a recorded launch list with pre-encoded TMA descriptors (one per module
+ *                                  call shape) replacing the per-op Python dispatch of nn.Sequential.forward.
+ */
+#ifndef TORCHSR_B200_H
+#define TORCHSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSR_MAX_TAPS 81
+
+/* out_mode */
+#define TSR_OUT_LINEAR 0
+#define TSR_OUT_SHUFFLE 1
+#define TSR_OUT_UNSHUFFLE 2
+#define TSR_OUT_GEMM_T_ATOMIC 3
+/* activations */
+#define TSR_ACT_NONE 0
+#define TSR_ACT_PRELU 1
+#define TSR_ACT_LEAKY 2
+#define TSR_ACT_RELU 3
+
+typedef struct tsr_conv_desc {
+  /* A operand: a_mode 0 = NHWC bf16 activations read through TMA im2col; 1 = row-major [M][K] bf16 matrix;
+     2 = row-major [K][M] bf16 matrix (M contiguous). */
+  const void* x;
+  const void* w;            /* packed bf16 weights, row-major [w_rows][w_ld]; rows = tap_slot*cout_pad + n */
+  int64_t N, H, W, C;       /* a_mode 0: input tensor dims (C = channels visible to the map) */
+  int64_t x_ld;             /* a_mode 0: pixel stride in elements; a_mode 1/2: row stride in elements */
+  int64_t Ho, Wo;           /* a_mode 0: traversal grid per image */
+  int64_t gemm_M, gemm_K;   /* a_mode 1/2 */
+  int64_t w_rows, w_ld;
+  int32_t a_mode;
+  int32_t stride;           /* traversal stride */
+  int32_t lower_h, lower_w; /* bounding-box lower corner (= -pad for a forward conv) */
+  int32_t upper_h, upper_w; /* bounding-box upper corner (= pad - (k-1) for a forward conv) */
+  int32_t num_taps;
+  int32_t block_k;          /* 16, 32 or 64 channels per K chunk */
+  int32_t block_n;          /* output columns per CTA: multiple of 16, <= 256 */
+  int32_t cout_pad;         /* rows per tap slot in w (multiple of block_n) */
+  int32_t a_c0;             /* first input channel used */
+  int32_t splits;           /* split-K factor (OUT_GEMM_T_ATOMIC only) */
+  uint16_t tap_off[TSR_MAX_TAPS];  /* (off_h << 8) | off_w, offsets relative to the lower corner */
+  uint16_t tap_wrow[TSR_MAX_TAPS]; /* tap slot in w */
+  /* epilogue */
+  void* out;
+  void* out_preact;
+  const float* bias;
+  const float* prelu;
+  const void* res;
+  const void* bwd_z;
+  float* dalpha_partial;
+  float* stats_partial;
+  int64_t os_n, os_h, os_w;
+  int64_t aux_n, aux_h, aux_w;
+  int32_t out_mode, out_f32, out_ch_off, aux_ch_off, n_valid, act, bwd_act, stats_ld, shuf_c;
+  float acc_scale, leaky_slope;
+} tsr_conv_desc_t;
+
+typedef struct tsr_wgrad_desc {
+  const void* x;   /* layer input, NHWC bf16 */
+  const void* dy;  /* output gradient, [pixels][dy_ld] bf16 */
+  float* out;      /* fp32 [cout_valid][num_taps][cin_pad], pre-zeroed, accumulated atomically */
+  int64_t N, H, W, C, x_ld;
+  int64_t Ho, Wo;
+  int64_t dy_ld, dy_c;     /* dY row stride and channel count visible */
+  int32_t stride, lower_h, lower_w, upper_h, upper_w;
+  int32_t num_taps;
+  int32_t chan_block;      /* 64 / 32 / 16 */
+  int32_t dy_block;        /* 64 / 32 / 16 */
+  int32_t block_n;
+  int32_t cout_valid;
+  int32_t x_c0, dy_c0;
+  int32_t splits;          /* pixel splits (0 = auto) */
+  uint16_t tap_off[TSR_MAX_TAPS];
+} tsr_wgrad_desc_t;
+
+/* Generic descriptor of the elementwise / reduction kernels; meaning of p/i/f per kind in csrc/eltwise.cu. */
+typedef struct tsr_elt_desc {
+  int32_t kind;
+  int32_t _pad;
+  void* p[8];
+  int64_t i[16];
+  float f[4];
+} tsr_elt_desc_t;
+
+enum tsr_elt_kind {
+  TSR_E_IM2ROW = 1,
+  TSR_E_GATHER_OUT = 2,
+  TSR_E_NCHW2NHWC = 3,
+  TSR_E_NHWC2NCHW = 4,
+  TSR_E_BN_FINALIZE = 5,
+  TSR_E_BN_EVAL_COEF = 6,
+  TSR_E_BN_ACT = 7,
+  TSR_E_BN_BWD_REDUCE = 8,
+  TSR_E_BN_BWD_FINALIZE = 9,
+  TSR_E_BN_BWD_APPLY = 10,
+  TSR_E_ACT_BWD = 11,
+  TSR_E_COLSUM_FINALIZE = 12,
+  TSR_E_SUM_FINALIZE = 13,
+  TSR_E_PACK_W = 14,
+  TSR_E_UNPACK_G = 15,
+  TSR_E_LINEAR_WGRAD = 16,
+  TSR_E_LOSS = 17,
+  TSR_E_ZERO = 18,
+  TSR_E_UPSAMPLE2X = 19,
+  TSR_E_UPSAMPLE2X_BWD = 20,
+  TSR_E_HEAD = 21,
+  TSR_E_HEAD_BWD = 22,
+  TSR_E_AXPBY = 23,
+  TSR_E_MAXPOOL2 = 24,
+  TSR_E_MAXPOOL2_BWD = 25,
+  TSR_E_CAST = 26,
+  TSR_E_ADAM = 27
+};
+
+/* weight pack / grad unpack index maps (TSR_E_PACK_W / TSR_E_UNPACK_G table entries) */
+enum tsr_pack_mode {
+  TSR_PK_FWD = 0,     /* dst[(kh*KW+kw)][co][ci]                       */
+  TSR_PK_T = 1,       /* dst[(kh*KW+kw)][ci][co]   (data-gradient pack) */
+  TSR_PK_ROWK = 2,    /* dst[kh][co][kw*Cin+ci]    (9x9, Cin=3 forward / its wgrad accumulator) */
+  TSR_PK_ROWN = 3,    /* dst[kh][kw*Cout+co][ci]   (9x9, Cout=3 forward / its wgrad accumulator) */
+  TSR_PK_ROWN_T = 4,  /* dst[kh][ci][kw*Cout+co]   (9x9, Cout=3 data gradient) */
+  TSR_PK_FULLK = 5,   /* dst[0][co][(kh*KW+kw)*Cin+ci]  (3x3, Cin=3 forward / its wgrad accumulator) */
+  TSR_PK_LINEAR = 6   /* dst[n][(h*Wf+w)*C+c] = src[n][c*Hf*Wf+h*Wf+w] */
+};
+
+typedef struct tsr_pack_entry {
+  const void* src;   /* pack: fp32 OIHW parameter; unpack: fp32 accumulator in packed order */
+  void* dst;         /* pack: bf16 packed; unpack: fp32 OIHW gradient */
+  int32_t mode;
+  int32_t cout, cin, kh, kw;
+  int32_t rows_pad, cols_pad; /* packed matrix: rows per tap slot, columns */
+  int32_t shuffle;   /* PixelShuffle(2) output-channel permutation: packed row r <-> co = 4*(r%(cout/4)) + r/(cout/4) */
+  int64_t block_start;  /* first CUDA block of this entry (prefix sum, 256 threads x 4 elements per block) */
+  int64_t count;        /* elements in the packed matrix */
+} tsr_pack_entry_t;
+
+typedef struct tsr_prog tsr_prog_t;
+
+int tsr_init(void);
+const char* tsr_last_error(void);
+int tsr_version(void);
+
+int tsr_conv(const tsr_conv_desc_t* d, void* stream);
+int tsr_wgrad(const tsr_wgrad_desc_t* d, void* stream);
+int tsr_elt(const tsr_elt_desc_t* d, void* stream);
+
+tsr_prog_t* tsr_prog_create(void);
+void tsr_prog_destroy(tsr_prog_t* p);
+int tsr_prog_add_conv(tsr_prog_t* p, const tsr_conv_desc_t* d);
+int tsr_prog_add_wgrad(tsr_prog_t* p, const tsr_wgrad_desc_t* d);
+int tsr_prog_add_elt(tsr_prog_t* p, const tsr_elt_desc_t* d);
+int tsr_prog_size(const tsr_prog_t* p);
+/* launches ops [first, first+count) on the stream; count < 0 means "to the end" */
+int tsr_prog_run(tsr_prog_t* p, int first, int count, void* stream);
+/* total kernels launched through this library since load (all entry points) */
+int64_t tsr_launch_count(void);
+/* reads and clears the device-side watchdog flag (0 = no kernel timed out); synchronises the stream */
+int tsr_check_watchdog(void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

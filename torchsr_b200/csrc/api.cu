@@ -1,0 +1,413 @@
+// C-ABI of libtorchsr_b200.so (see include/torchsr_b200.h): descriptor validation, TMA tensor-map encoding,
+// launch-parameter construction and the recorded-program executor. No torch dependency.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/torchsr_b200.h"
+#include "conv_params.h"
+
+namespace tsr {
+cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream);
+cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int splits, cudaStream_t stream);
+cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st);
+size_t conv_igemm_smem_bytes(const ConvParams& p);
+size_t conv_wgrad_smem_bytes(const WgradParams& p);
+}  // namespace tsr
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+int g_driver_version = 0;
+int* g_watchdog = nullptr;  // device flag
+std::mutex g_mu;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+int ensure_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_encode_tiled && g_encode_im2col && g_watchdog) return 0;
+  cudaError_t ce = cudaFree(0);
+  if (ce != cudaSuccess) return fail(-1, "CUDA runtime unavailable: %s", cudaGetErrorString(ce));
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (ce != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return fail(-2, "cuTensorMapEncodeTiled not found");
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  fn = nullptr;
+  ce = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q);
+  if (ce != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) return fail(-2, "cuTensorMapEncodeIm2col not found");
+  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+  cudaDriverGetVersion(&g_driver_version);
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail(-3, "torchsr_b200 requires an sm_100 GPU (found compute capability major %d)", major);
+  ce = cudaMalloc(&g_watchdog, sizeof(int));
+  if (ce != cudaSuccess) return fail(-1, "cudaMalloc failed: %s", cudaGetErrorString(ce));
+  cudaMemset(g_watchdog, 0, sizeof(int));
+  return 0;
+}
+
+CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 2D row-major bf16 matrix [rows][ld]; box = {box_cols, box_rows}
+int encode_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(box_cols * 2),
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(-10, "cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d base=%p", (int)r,
+                (long long)rows, (long long)cols, (long long)ld, box_cols, box_rows, base);
+  return 0;
+}
+
+// NHWC bf16 tensor, im2col mode: box = {chan, pixels}
+int encode_im2col(CUtensorMap* m, const void* base, int64_t N, int64_t H, int64_t W, int64_t C, int64_t ld, int lower_h,
+                  int lower_w, int upper_h, int upper_w, int stride, int chan, int pixels) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * W,
+                           static_cast<cuuint64_t>(ld) * 2 * W * H};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                               upper, static_cast<cuuint32_t>(chan), static_cast<cuuint32_t>(pixels), estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(chan * 2),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(-11, "cuTensorMapEncodeIm2col failed (%d): N=%lld H=%lld W=%lld C=%lld ld=%lld lo=(%d,%d) up=(%d,%d) s=%d box=%dx%d",
+                (int)r, (long long)N, (long long)H, (long long)W, (long long)C, (long long)ld, lower_h, lower_w, upper_h,
+                upper_w, stride, chan, pixels);
+  // Driver quirk for im2col maps over tensors smaller than 128 KiB on drivers <= 13.1 (descriptor bit 85 must be
+  // clear); same fix-up CUTLASS applies when it builds im2col descriptors.
+  if (g_driver_version <= 13010) {
+    const uint64_t bytes = static_cast<uint64_t>(N) * H * W * ld * 2;
+    if (bytes < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  }
+  return 0;
+}
+
+int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+struct ConvLaunch {
+  tsr::ConvParams p;
+  int tiles_n, splits;
+};
+struct WgradLaunch {
+  tsr::WgradParams p;
+  int gsets, tiles_n, splits;
+};
+
+int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
+  using namespace tsr;
+  if (int e = ensure_init()) return e;
+  ConvParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  if (d.block_k != 16 && d.block_k != 32 && d.block_k != 64) return fail(-20, "block_k must be 16/32/64");
+  if (d.block_n < 16 || d.block_n > 256 || d.block_n % 16) return fail(-20, "block_n must be a multiple of 16 in [16,256]");
+  if (d.cout_pad % d.block_n) return fail(-20, "cout_pad must be a multiple of block_n");
+  if (d.num_taps < 1 || d.num_taps > kMaxTaps) return fail(-20, "num_taps out of range");
+  if (d.a_mode == 0) {
+    if (d.C % d.block_k) return fail(-20, "C (%lld) must be a multiple of block_k (%d)", (long long)d.C, d.block_k);
+    const int64_t wo = (d.W + d.upper_w - d.lower_w - 1) / d.stride + 1;
+    const int64_t ho = (d.H + d.upper_h - d.lower_h - 1) / d.stride + 1;
+    if (wo != d.Wo || ho != d.Ho)
+      return fail(-21, "traversal grid mismatch: corners give %lldx%lld, descriptor says %lldx%lld", (long long)ho,
+                  (long long)wo, (long long)d.Ho, (long long)d.Wo);
+    if (int e = encode_im2col(&p.tmA, d.x, d.N, d.H, d.W, d.C, d.x_ld, d.lower_h, d.lower_w, d.upper_h, d.upper_w,
+                              d.stride, d.block_k, kBlockM))
+      return e;
+    p.M_total = static_cast<int>(d.N * d.Ho * d.Wo);
+    p.kc_per_tap = static_cast<int>((d.C - d.a_c0) / d.block_k);
+    p.Ho = static_cast<int>(d.Ho);
+    p.Wo = static_cast<int>(d.Wo);
+  } else if (d.a_mode == 1) {
+    if (d.gemm_K % d.block_k) return fail(-20, "gemm_K must be a multiple of block_k");
+    if (int e = encode_2d(&p.tmA, d.x, d.gemm_M, d.gemm_K, d.x_ld, d.block_k, kBlockM)) return e;
+    p.M_total = static_cast<int>(d.gemm_M);
+    p.kc_per_tap = static_cast<int>(d.gemm_K / d.block_k);
+    p.Ho = p.Wo = 1;
+  } else if (d.a_mode == 2) {
+    if (d.block_k != 64) return fail(-20, "a_mode 2 requires block_k 64");
+    if (d.gemm_K % d.block_k) return fail(-20, "gemm_K must be a multiple of block_k");
+    if (int e = encode_2d(&p.tmA, d.x, d.gemm_K, d.gemm_M, d.x_ld, 64, d.block_k)) return e;
+    p.M_total = static_cast<int>(d.gemm_M);
+    p.kc_per_tap = static_cast<int>(d.gemm_K / d.block_k);
+    p.Ho = p.Wo = 1;
+  } else {
+    return fail(-20, "bad a_mode");
+  }
+  if (int e = encode_2d(&p.tmB, d.w, d.w_rows, d.w_ld, d.w_ld, d.block_k, d.block_n)) return e;
+  p.stride = d.stride;
+  p.lower_h = d.lower_h;
+  p.lower_w = d.lower_w;
+  p.num_taps = d.a_mode == 0 ? d.num_taps : 1;
+  p.block_k = d.block_k;
+  p.block_n = d.block_n;
+  p.a_mode = d.a_mode;
+  p.a_c0 = d.a_c0;
+  p.b_rows_per_tap = d.cout_pad;
+  memcpy(p.tap_off, d.tap_off, sizeof(p.tap_off));
+  memcpy(p.tap_wrow, d.tap_wrow, sizeof(p.tap_wrow));
+  const int total_iters = p.num_taps * p.kc_per_tap;
+  int splits = d.splits > 0 ? d.splits : 1;
+  if (splits > 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC) return fail(-20, "split-K needs OUT_GEMM_T_ATOMIC");
+  if (splits > total_iters) splits = total_iters;
+  p.iters_per_split = (total_iters + splits - 1) / splits;
+  splits = (total_iters + p.iters_per_split - 1) / p.iters_per_split;
+  L->splits = splits;
+  L->tiles_n = d.cout_pad / d.block_n;
+  p.tmem_cols = pow2_cols(d.block_n);
+  const uint32_t stage_bytes = ((kBlockM * d.block_k * 2 + d.block_n * d.block_k * 2) + 1023u) & ~1023u;
+  int stages = 6;
+  while (stages > 2 && static_cast<size_t>(stages) * stage_bytes > 96 * 1024) --stages;
+  if (static_cast<size_t>(stages) * stage_bytes > 200 * 1024) return fail(-22, "tile does not fit shared memory");
+  if (stages > p.iters_per_split) stages = p.iters_per_split < 1 ? 1 : p.iters_per_split;
+  p.stages = stages;
+  EpiParams& e = p.epi;
+  e.out = d.out;
+  e.out_preact = d.out_preact;
+  e.bias = d.bias;
+  e.prelu = d.prelu;
+  e.res = d.res;
+  e.bwd_z = d.bwd_z;
+  e.dalpha_partial = d.dalpha_partial;
+  e.stats_partial = d.stats_partial;
+  e.err = g_watchdog;
+  e.os_n = d.os_n;
+  e.os_h = d.os_h;
+  e.os_w = d.os_w;
+  e.aux_n = d.aux_n;
+  e.aux_h = d.aux_h;
+  e.aux_w = d.aux_w;
+  e.out_mode = d.out_mode;
+  e.out_f32 = d.out_f32;
+  e.out_ch_off = d.out_ch_off;
+  e.aux_ch_off = d.aux_ch_off;
+  e.n_valid = d.n_valid;
+  e.act = d.act;
+  e.bwd_act = d.bwd_act;
+  e.stats_ld = d.stats_ld;
+  e.shuf_c = d.shuf_c > 0 ? d.shuf_c : 64;
+  e.acc_scale = d.acc_scale;
+  e.leaky_slope = d.leaky_slope;
+  if (!e.out) return fail(-20, "out is null");
+  if ((e.act == TSR_ACT_PRELU || e.bwd_act == TSR_ACT_PRELU) && !e.prelu) return fail(-20, "PReLU needs the slope pointer");
+  if (e.n_valid % 16) return fail(-20, "n_valid must be a multiple of 16");
+  return 0;
+}
+
+int build_wgrad(const tsr_wgrad_desc_t& d, WgradLaunch* L) {
+  using namespace tsr;
+  if (int e = ensure_init()) return e;
+  WgradParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  if (d.chan_block != 64 && d.chan_block != 32 && d.chan_block != 16) return fail(-30, "chan_block must be 16/32/64");
+  if (d.dy_block != 64 && d.dy_block != 32 && d.dy_block != 16) return fail(-30, "dy_block must be 16/32/64");
+  if (d.block_n % d.dy_block || d.block_n % 16 || d.block_n > 256) return fail(-30, "bad block_n");
+  if ((d.C - d.x_c0) % d.chan_block) return fail(-30, "C must be a multiple of chan_block");
+  if (d.num_taps < 1 || d.num_taps > kMaxTaps) return fail(-30, "num_taps out of range");
+  const int64_t wo = (d.W + d.upper_w - d.lower_w - 1) / d.stride + 1;
+  const int64_t ho = (d.H + d.upper_h - d.lower_h - 1) / d.stride + 1;
+  if (wo != d.Wo || ho != d.Ho) return fail(-31, "traversal grid mismatch in wgrad descriptor");
+  p.M_total = static_cast<int>(d.N * d.Ho * d.Wo);
+  p.Ho = static_cast<int>(d.Ho);
+  p.Wo = static_cast<int>(d.Wo);
+  p.stride = d.stride;
+  p.lower_h = d.lower_h;
+  p.lower_w = d.lower_w;
+  p.num_taps = d.num_taps;
+  p.chan_block = d.chan_block;
+  p.dy_block = d.dy_block;
+  p.blocks_per_m = 128 / d.chan_block;
+  p.cin_pad = static_cast<int>(d.C - d.x_c0);
+  p.cin_blocks = p.cin_pad / d.chan_block;
+  p.total_blocks = p.num_taps * p.cin_blocks;
+  p.block_n = d.block_n;
+  p.cout_valid = d.cout_valid;
+  p.out = d.out;
+  p.err = g_watchdog;
+  memcpy(p.tap_off, d.tap_off, sizeof(p.tap_off));
+  const int total_groups = (p.total_blocks + p.blocks_per_m - 1) / p.blocks_per_m;
+  int gpc = 512 / pow2_cols(d.block_n) * (pow2_cols(d.block_n) / d.block_n);  // groups whose accumulators fit TMEM
+  gpc = 512 / d.block_n;
+  if (gpc > total_groups) gpc = total_groups;
+  // choose pixels per stage / groups per CTA so that at least 2 stages fit in ~200 KB
+  int pix = 64;
+  auto stage_bytes = [&](int g, int px) {
+    return static_cast<size_t>(((g * p.blocks_per_m * px * d.chan_block * 2 + (d.block_n / d.dy_block) * px * d.dy_block * 2) +
+                                1023) & ~1023);
+  };
+  while (gpc > 1 && stage_bytes(gpc, pix) * 2 > 200 * 1024) --gpc;
+  if (stage_bytes(gpc, pix) * 3 > 200 * 1024) pix = 32;
+  if (stage_bytes(gpc, pix) * 2 > 200 * 1024) return fail(-32, "wgrad tile does not fit shared memory");
+  p.groups_per_cta = gpc;
+  p.pix_per_stage = pix;
+  int stages = 6;
+  while (stages > 2 && stage_bytes(gpc, pix) * stages > 200 * 1024) --stages;
+  p.tmem_cols = pow2_cols(gpc * d.block_n);
+  if (p.tmem_cols > 512) return fail(-32, "wgrad accumulators exceed TMEM");
+  L->gsets = (total_groups + gpc - 1) / gpc;
+  L->tiles_n = static_cast<int>((d.cout_valid + d.block_n - 1) / d.block_n);
+  const int total_stage_iters = (p.M_total + pix - 1) / pix;
+  int splits = d.splits;
+  if (splits <= 0) {
+    // aim for ~2 CTAs per SM overall, at least 4 pipeline iterations per CTA
+    const int base = L->gsets * L->tiles_n;
+    splits = (296 + base - 1) / base;
+    const int max_splits = total_stage_iters / 4 > 0 ? total_stage_iters / 4 : 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > total_stage_iters) splits = total_stage_iters;
+  p.stages_per_cta = (total_stage_iters + splits - 1) / splits;
+  splits = (total_stage_iters + p.stages_per_cta - 1) / p.stages_per_cta;
+  L->splits = splits;
+  if (stages > p.stages_per_cta) stages = p.stages_per_cta;
+  p.stages = stages;
+  if (int e = encode_im2col(&p.tmX, reinterpret_cast<const char*>(d.x) + static_cast<int64_t>(d.x_c0) * 2, d.N, d.H, d.W,
+                            p.cin_pad, d.x_ld, d.lower_h, d.lower_w, d.upper_h, d.upper_w, d.stride, d.chan_block, pix))
+    return e;
+  if (int e = encode_2d(&p.tmDy, reinterpret_cast<const char*>(d.dy) + static_cast<int64_t>(d.dy_c0) * 2, p.M_total,
+                        d.dy_c, d.dy_ld, d.dy_block, pix))
+    return e;
+  if (!p.out) return fail(-30, "out is null");
+  return 0;
+}
+
+}  // namespace
+
+struct tsr_prog {
+  enum Kind { CONV, WGRAD, ELT };
+  struct Op {
+    Kind kind;
+    ConvLaunch conv;
+    WgradLaunch wg;
+    tsr_elt_desc_t elt;
+  };
+  std::vector<Op> ops;
+};
+
+extern "C" {
+
+int tsr_init(void) { return ensure_init(); }
+const char* tsr_last_error(void) { return g_err.c_str(); }
+int tsr_version(void) { return 1; }
+int64_t tsr_launch_count(void) { return g_launches.load(); }
+
+int tsr_conv(const tsr_conv_desc_t* d, void* stream) {
+  ConvLaunch L;
+  if (int e = build_conv(*d, &L)) return e;
+  cudaError_t ce = tsr::launch_conv_igemm(L.p, L.tiles_n, L.splits, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return fail(-40, "conv launch failed: %s", cudaGetErrorString(ce));
+  g_launches++;
+  return 0;
+}
+
+int tsr_wgrad(const tsr_wgrad_desc_t* d, void* stream) {
+  WgradLaunch L;
+  if (int e = build_wgrad(*d, &L)) return e;
+  cudaError_t ce = tsr::launch_conv_wgrad(L.p, L.gsets, L.tiles_n, L.splits, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return fail(-40, "wgrad launch failed: %s", cudaGetErrorString(ce));
+  g_launches++;
+  return 0;
+}
+
+int tsr_elt(const tsr_elt_desc_t* d, void* stream) {
+  if (int e = ensure_init()) return e;
+  cudaError_t ce = tsr::launch_elt(*d, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return fail(-41, "elementwise kind %d launch failed: %s", d->kind, cudaGetErrorString(ce));
+  g_launches++;
+  return 0;
+}
+
+tsr_prog_t* tsr_prog_create(void) { return new tsr_prog(); }
+void tsr_prog_destroy(tsr_prog_t* p) { delete p; }
+int tsr_prog_size(const tsr_prog_t* p) { return static_cast<int>(p->ops.size()); }
+
+int tsr_prog_add_conv(tsr_prog_t* p, const tsr_conv_desc_t* d) {
+  tsr_prog::Op op;
+  op.kind = tsr_prog::CONV;
+  if (int e = build_conv(*d, &op.conv)) return e;
+  p->ops.push_back(op);
+  return static_cast<int>(p->ops.size()) - 1;
+}
+int tsr_prog_add_wgrad(tsr_prog_t* p, const tsr_wgrad_desc_t* d) {
+  tsr_prog::Op op;
+  op.kind = tsr_prog::WGRAD;
+  if (int e = build_wgrad(*d, &op.wg)) return e;
+  p->ops.push_back(op);
+  return static_cast<int>(p->ops.size()) - 1;
+}
+int tsr_prog_add_elt(tsr_prog_t* p, const tsr_elt_desc_t* d) {
+  if (int e = ensure_init()) return e;
+  tsr_prog::Op op;
+  op.kind = tsr_prog::ELT;
+  op.elt = *d;
+  p->ops.push_back(op);
+  return static_cast<int>(p->ops.size()) - 1;
+}
+
+int tsr_prog_run(tsr_prog_t* p, int first, int count, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = static_cast<int>(p->ops.size());
+  const int last = count < 0 ? n : (first + count > n ? n : first + count);
+  for (int i = first; i < last; ++i) {
+    const tsr_prog::Op& op = p->ops[i];
+    cudaError_t ce;
+    if (op.kind == tsr_prog::CONV)
+      ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st);
+    else if (op.kind == tsr_prog::WGRAD)
+      ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st);
+    else
+      ce = tsr::launch_elt(op.elt, st);
+    if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
+    g_launches++;
+  }
+  return 0;
+}
+
+int tsr_check_watchdog(void* stream) {
+  if (int e = ensure_init()) return e;
+  int v = 0;
+  cudaError_t ce = cudaMemcpyAsync(&v, g_watchdog, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return fail(-50, "watchdog read failed: %s", cudaGetErrorString(ce));
+  if (v != 0) {
+    cudaMemsetAsync(g_watchdog, 0, sizeof(int), static_cast<cudaStream_t>(stream));
+    return fail(v, "device watchdog fired: pipeline wait timed out (code %d)", v);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+// Parameter blocks shared by the host launch code and the tcgen05 implicit-GEMM kernels.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace tsr {
+
+constexpr int kMaxTaps = 81;      // 9x9
+constexpr int kBlockM = 128;      // UMMA M (TMEM lanes)
+constexpr int kConvThreads = 192; // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
+
+enum OutMode : int {
+  OUT_LINEAR = 0,     // off = n*os_n + ho*os_h + wo*os_w + col
+  OUT_SHUFFLE = 1,    // PixelShuffle(2) store: column block (i,j) of 64 -> pixel (2ho+i, 2wo+j)
+  OUT_UNSHUFFLE = 2,  // inverse: fine pixel (ho,wo) -> coarse pixel (ho/2,wo/2), column block ((ho&1)*2+(wo&1))
+  OUT_GEMM_T_ATOMIC = 3  // split-K GEMM: atomicAdd(out[col*ld + row], v) in fp32
+};
+enum Act : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_LEAKY = 2, ACT_RELU = 3 };
+
+struct EpiParams {
+  void* out;             // bf16 or fp32
+  void* out_preact;      // optional bf16 copy of the pre-activation value (same addressing as out)
+  const float* bias;     // optional, indexed by global column
+  const float* prelu;    // scalar slope (device) for ACT_PRELU / bwd_act == ACT_PRELU
+  const void* res;       // optional bf16 residual, aux addressing:  v = acc*acc_scale (+bias) + res
+  const void* bwd_z;     // optional bf16 tensor, aux addressing: v *= act'(bwd_z)
+  float* dalpha_partial; // optional [grid] partial sums of v*z*[z<0] (PReLU slope gradient)
+  float* stats_partial;  // optional [tiles_m][stats_ld][2] per-tile column sum / sum of squares of stored value
+  int* err;              // watchdog / error flag
+  long long os_n, os_h, os_w;     // out strides in elements
+  long long aux_n, aux_h, aux_w;  // aux strides in elements
+  int out_mode;
+  int out_f32;           // 1: out is fp32
+  int out_ch_off;        // added to column for out / preact
+  int aux_ch_off;
+  int n_valid;           // columns >= n_valid are not stored (multiple of 16)
+  int act;               // applied last
+  int bwd_act;           // ACT_PRELU: z holds pre-activation; ACT_LEAKY/ACT_RELU: z holds activation output
+  int stats_ld;          // total columns in stats_partial rows
+  int shuf_c;            // channels per sub-pixel block for OUT_SHUFFLE / OUT_UNSHUFFLE
+  float acc_scale;
+  float leaky_slope;
+};
+
+struct ConvParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  EpiParams epi;
+  int M_total;     // rows of the implicit GEMM (N*Ho*Wo traversal positions)
+  int Ho, Wo;      // traversal grid (per image)
+  int stride;      // traversal stride in input pixels
+  int lower_h, lower_w;
+  int num_taps;
+  int kc_per_tap;  // K chunks (of block_k) per tap
+  int block_k;     // 16 / 32 / 64 elements
+  int block_n;     // multiple of 16, <= 256
+  int a_mode;      // 0: im2col NHWC; 1: 2D tiled, K-major rows; 2: 2D tiled, MN-major (A given as [K][M])
+  int a_c0;        // first input channel
+  int b_rows_per_tap;
+  int iters_per_split;  // K iterations handled per blockIdx.z
+  int stages;
+  int tmem_cols;
+  uint16_t tap_off[kMaxTaps];   // (off_h << 8) | off_w
+  uint16_t tap_wrow[kMaxTaps];  // tap slot in the packed weight matrix
+};
+
+// Weight-gradient kernel:  dW[co][tap][ci] += sum_p X[pixel(p) + tap, ci] * dY[p, co]
+// computed as D[(block, ci), co] with the "M blocks" enumerating (tap, ci_block) pairs.
+struct WgradParams {
+  CUtensorMap tmX;   // im2col NHWC map over the layer input (MN-major operand A, chan_block channels per box)
+  CUtensorMap tmDy;  // 2D tiled map over dY [pixels, Cout] (MN-major operand B, dy_block channels per box)
+  float* out;        // fp32 [Cout][num_taps][cin_pad], accumulated with red.global.add
+  int* err;
+  int M_total;       // pixels (traversal positions == rows of dY)
+  int Ho, Wo;
+  int stride;
+  int lower_h, lower_w;
+  int num_taps;
+  int cin_blocks;      // cin_pad / chan_block
+  int chan_block;      // channels per A box: 64 (SW128), 32 (SW64), 16 (SW32)
+  int blocks_per_m;    // 128 / chan_block
+  int groups_per_cta;  // UMMA M-groups (128 rows each) accumulated by one CTA
+  int total_blocks;    // num_taps * cin_blocks
+  int block_n;         // Cout tile
+  int dy_block;        // channels per dY box: 64 / 32 / 16
+  int cin_pad;
+  int cout_valid;
+  int pix_per_stage;   // 32 or 64
+  int stages_per_cta;  // pipeline iterations per CTA (pixel range = stages_per_cta * pix_per_stage)
+  int stages;          // smem ring depth
+  int tmem_cols;
+  uint16_t tap_off[kMaxTaps];
+};
+
+}  // namespace tsr

@@ -1,0 +1,903 @@
+// HBM/L2-bound kernels of the path: layout conversion, BatchNorm (finalize / apply / backward), activation
+// backward, loss reductions, weight pack / gradient unpack, classifier head. All use 16-byte vector accesses on
+// the NHWC bf16 tensors (8 channels per thread) and warp-shuffle / shared-memory reductions.
+// Argument conventions of tsr_elt_desc_t (p[], i[], f[]) are documented at each kernel.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/torchsr_b200.h"
+#include "ptx.cuh"
+
+namespace tsr {
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  uint4 q = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(q.x, v[0], v[1]);
+  unpack_bf16x2(q.y, v[2], v[3]);
+  unpack_bf16x2(q.z, v[4], v[5]);
+  unpack_bf16x2(q.w, v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+  if (act == TSR_ACT_NONE) return z;
+  if (act == TSR_ACT_RELU) return fmaxf(z, 0.f);
+  return z > 0.f ? z : z * slope;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------- IM2ROW
+// p0 = x fp32 NCHW [B,C,H,W], p1 = E bf16 [B,H,W,Epad]
+// i: 0 B, 1 C, 2 H, 3 W, 4 KH, 5 KW, 6 ph, 7 pw, 8 sign, 9 Epad
+// E[n,h,w,(kh*KW+kw)*C+c] = x[n,c,h+sign*(kh-ph),w+sign*(kw-pw)] (0 outside), columns >= KH*KW*C are 0.
+__global__ void im2row_kernel(const float* __restrict__ x, bf16* __restrict__ E, int B, int C, int H, int W, int KH,
+                              int KW, int ph, int pw, int sign, int Epad) {
+  const int groups = Epad / 8;
+  const long long total = static_cast<long long>(B) * H * W * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    long long pix = idx / groups;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = g * 8 + j;
+      float val = 0.f;
+      if (col < KH * KW * C) {
+        const int c = col % C;
+        const int t = col / C;
+        const int kw = t % KW, kh = t / KW;
+        const int hh = h + sign * (kh - ph), ww = w + sign * (kw - pw);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + ((static_cast<long long>(n) * C + c) * H + hh) * W + ww);
+      }
+      v[j] = val;
+    }
+    st8(E + pix * Epad + g * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GATHER_OUT
+// p0 = T ([B,H,W,Tld] fp32 or bf16), p1 = out fp32 NCHW [B,C,H,W], p2 = bias fp32[C] or null
+// i: 0 B, 1 C, 2 H, 3 W, 4 KH, 5 KW, 6 ph, 7 pw, 8 sign, 9 Tld, 10 T_is_bf16
+// out[n,c,h,w] = bias[c] + sum_{kh,kw} T[n, h+sign*(kh-ph), w+sign*(kw-pw), (kh*KW+kw)*C+c]
+__global__ void gather_out_kernel(const void* __restrict__ T, float* __restrict__ out, const float* __restrict__ bias,
+                                  int B, int C, int H, int W, int KH, int KW, int ph, int pw, int sign, int Tld,
+                                  int t_bf16) {
+  const long long total = static_cast<long long>(B) * C * H * W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(idx % W);
+    const int h = static_cast<int>((idx / W) % H);
+    const int c = static_cast<int>((idx / (static_cast<long long>(W) * H)) % C);
+    const int n = static_cast<int>(idx / (static_cast<long long>(W) * H * C));
+    float acc = bias ? __ldg(bias + c) : 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const int hh = h + sign * (kh - ph);
+      if (hh < 0 || hh >= H) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ww = w + sign * (kw - pw);
+        if (ww < 0 || ww >= W) continue;
+        const long long off = ((static_cast<long long>(n) * H + hh) * W + ww) * Tld + (kh * KW + kw) * C + c;
+        acc += t_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(T)[off]) : reinterpret_cast<const float*>(T)[off];
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- layout
+// NCHW2NHWC: p0 = x fp32 NCHW, p1 = y bf16 NHWC (pixel stride ld, channel offset off); i: 0 B,1 C,2 H,3 W,4 ld,5 off
+// channels are processed in groups of 8 (C%8==0)
+__global__ void nchw2nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int B, int C, int H, int W, int ld,
+                                 int off) {
+  const int groups = C / 8;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(B) * groups * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx % hw;
+    const int g = static_cast<int>((idx / hw) % groups);
+    const int n = static_cast<int>(idx / (hw * groups));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(x + (static_cast<long long>(n) * C + g * 8 + j) * hw + p);
+    st8(y + (static_cast<long long>(n) * hw + p) * ld + off + g * 8, v);
+  }
+}
+// NHWC2NCHW: p0 = x bf16 NHWC (ld, off), p1 = y fp32 NCHW; i: 0 B,1 C,2 H,3 W,4 ld,5 off, 6 accumulate
+__global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W, int ld,
+                                 int off, int accumulate) {
+  const int groups = C / 8;
+  const long long hw = static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(B) * groups * hw;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = idx % hw;
+    const int g = static_cast<int>((idx / hw) % groups);
+    const int n = static_cast<int>(idx / (hw * groups));
+    float v[8];
+    ld8(x + (static_cast<long long>(n) * hw + p) * ld + off + g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float* dst = y + (static_cast<long long>(n) * C + g * 8 + j) * hw + p;
+      *dst = accumulate ? (*dst + v[j]) : v[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- BN finalize
+// p0 = partial [tiles][ld][2] (col sum, col sumsq), p1 = gamma, p2 = beta, p3 = running_mean, p4 = running_var,
+// p5 = num_batches_tracked (int64), p6 = coef out fp32 [4][C]: scale, shift, mean, invstd
+// i: 0 tiles, 1 C, 2 count (N*H*W), 3 update_running, 4 ld; f: 0 eps, 1 momentum
+// nn.BatchNorm2d training semantics: biased variance for normalisation, unbiased for the running estimate.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   long long* nbt, float* __restrict__ coef, int tiles, int C, long long count,
+                                   int update, int ld, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && update && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    s1 += partial[(static_cast<long long>(t) * ld + c) * 2 + 0];
+    s2 += partial[(static_cast<long long>(t) * ld + c) * 2 + 1];
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = rsqrtf(static_cast<float>(var) + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  coef[0 * C + c] = g * invstd;
+  coef[1 * C + c] = b - static_cast<float>(mean) * g * invstd;
+  coef[2 * C + c] = static_cast<float>(mean);
+  coef[3 * C + c] = invstd;
+  if (update) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+// eval-mode coefficients from running statistics: p1..p4 as above, p6 = coef; i: 1 C; f: 0 eps
+__global__ void bn_eval_coef_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                    float* coef, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(rv[c] + eps);
+  coef[0 * C + c] = gamma[c] * invstd;
+  coef[1 * C + c] = beta[c] - rm[c] * gamma[c] * invstd;
+  coef[2 * C + c] = rm[c];
+  coef[3 * C + c] = invstd;
+}
+
+// ---------------------------------------------------------------------------------------------- BN apply + act
+// p0 = x bf16 [M][x_ld], p1 = coef (scale, shift) or null (identity), p2 = y bf16 [M][y_ld], p3 = res bf16 or null,
+// p4 = prelu alpha or null
+// i: 0 M, 1 C, 2 x_ld, 3 y_ld, 4 res_ld, 5 act, 6 x_off, 7 y_off, 8 res_off; f: 0 leaky slope, 1 res_scale, 2 x_scale
+// y = act(x*scale+shift)*x_scale + res*res_scale
+__global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ coef, bf16* __restrict__ y,
+                              const bf16* __restrict__ res, const float* __restrict__ alpha, long long M, int C,
+                              int x_ld, int y_ld, int res_ld, int act, int x_off, int y_off, int res_off,
+                              float leaky, float res_scale, float x_scale) {
+  const int groups = C / 8;
+  const long long total = M * groups;
+  const float slope = act == TSR_ACT_PRELU ? __ldg(alpha) : leaky;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    const long long m = idx / groups;
+    float v[8];
+    ld8(x + m * x_ld + x_off + g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = v[j];
+      if (coef) z = z * __ldg(coef + g * 8 + j) + __ldg(coef + C + g * 8 + j);
+      v[j] = act_fwd(z, act, slope) * x_scale;
+    }
+    if (res) {
+      float r[8];
+      ld8(res + m * res_ld + res_off + g * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j] * res_scale;
+    }
+    st8(y + m * y_ld + y_off + g * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- BN backward
+// Shared column-reduction skeleton: 256 threads = (C/8 channel groups) x (256/(C/8) row lanes); each block
+// covers rows [blockIdx.x*rows_per_block, ...). Partial sums go to partial[block][C][2].
+//
+// BN_BWD_REDUCE: p0 = g bf16 (grad wrt act output) [M][g_ld], p1 = x raw bf16 [M][x_ld], p2 = coef (fwd) or null,
+// p3 = alpha or null, p4 = partial out [blocks][C][2] (sum dz, sum dz*xhat), p5 = dalpha partial [blocks] or null,
+// p6 = optional second gradient g2 bf16 added to g (same ld)
+// i: 0 M, 1 C, 2 act, 3 rows_per_block, 4 g_ld, 5 x_ld, 6 has_bn; f: 0 leaky
+// dz = g * act'(z), z = x*scale+shift (has_bn) or x; xhat = (x-mean)*invstd. For act backward without BN the
+// second sum is unused. ACT_LEAKY/RELU without BN take x = activation output (sign preserved).
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
+                                                            const float* __restrict__ coef,
+                                                            const float* __restrict__ alpha, float* __restrict__ partial,
+                                                            float* __restrict__ dalpha_partial,
+                                                            const bf16* __restrict__ g2, long long M, int C, int act,
+                                                            int rows_per_block, int g_ld, int x_ld, int has_bn,
+                                                            float leaky) {
+  extern __shared__ float sm[];
+  const int groups = C / 8;
+  const int lanes = 256 / groups;  // row lanes (groups <= 256)
+  const int g_id = threadIdx.x % groups;
+  const int r_id = threadIdx.x / groups;
+  const float slope = act == TSR_ACT_PRELU ? __ldg(alpha) : (act == TSR_ACT_RELU ? 0.f : leaky);
+  float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g_id * 8 + j;
+    sc[j] = has_bn ? __ldg(coef + c) : 1.f;
+    sh[j] = has_bn ? __ldg(coef + C + c) : 0.f;
+    mu[j] = has_bn ? __ldg(coef + 2 * C + c) : 0.f;
+    is[j] = has_bn ? __ldg(coef + 3 * C + c) : 1.f;
+  }
+  float s1[8], s2[8], da = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const long long row0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long row1 = min(M, row0 + rows_per_block);
+  if (r_id < lanes) {
+    for (long long m = row0 + r_id; m < row1; m += lanes) {
+      float gv[8], xv[8];
+      ld8(g + m * g_ld + g_id * 8, gv);
+      ld8(x + m * x_ld + g_id * 8, xv);
+      if (g2) {
+        float t[8];
+        ld8(g2 + m * g_ld + g_id * 8, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] += t[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = xv[j] * sc[j] + sh[j];
+        float dz = gv[j];
+        if (act != TSR_ACT_NONE && z <= 0.f) {
+          da += dz * z;
+          dz *= slope;
+        }
+        s1[j] += dz;
+        s2[j] += dz * (xv[j] - mu[j]) * is[j];
+      }
+    }
+  }
+  // reduce over row lanes through shared memory: sm[lane][C][2]
+  float* smp = sm;
+  if (r_id < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      smp[(r_id * C + g_id * 8 + j) * 2 + 0] = s1[j];
+      smp[(r_id * C + g_id * 8 + j) * 2 + 1] = s2[j];
+    }
+  }
+  float* sda = sm + lanes * C * 2;
+  da = warp_sum(da);
+  if ((threadIdx.x & 31) == 0) sda[threadIdx.x >> 5] = da;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      a += smp[(l * C + c) * 2 + 0];
+      b += smp[(l * C + c) * 2 + 1];
+    }
+    partial[(static_cast<long long>(blockIdx.x) * C + c) * 2 + 0] = a;
+    partial[(static_cast<long long>(blockIdx.x) * C + c) * 2 + 1] = b;
+  }
+  if (dalpha_partial && threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sda[w];
+    dalpha_partial[blockIdx.x] = t;
+  }
+}
+
+// BN_BWD_FINALIZE: p0 = partial [blocks][C][2], p1 = dalpha partial [nda] or null, p2 = coef fwd, p3 = gamma,
+// p4 = bwd coef out [3][C] (c1 = gamma*invstd, c2 = sum_dz/M, c3 = sum_dz_xhat/M), p5 = dgamma out, p6 = dbeta out,
+// p7 = dalpha out (scalar) or null
+// i: 0 blocks, 1 C, 2 M, 3 nda, 4 accumulate_dalpha
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ dalpha_partial,
+                                       const float* __restrict__ coef, const float* __restrict__ gamma,
+                                       float* __restrict__ bcoef, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ dalpha, int blocks, int C, long long M, int nda,
+                                       int acc_dalpha) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && dalpha && threadIdx.x < 32) {
+    float t = 0.f;
+    for (int i = threadIdx.x; i < nda; i += 32) t += dalpha_partial[i];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) *dalpha = acc_dalpha ? (*dalpha + t) : t;
+  }
+  if (c >= C) return;
+  float a = 0.f, b = 0.f;
+  for (int t = 0; t < blocks; ++t) {
+    a += partial[(static_cast<long long>(t) * C + c) * 2 + 0];
+    b += partial[(static_cast<long long>(t) * C + c) * 2 + 1];
+  }
+  if (dbeta) dbeta[c] = a;
+  if (dgamma) dgamma[c] = b;
+  if (bcoef) {
+    bcoef[0 * C + c] = (gamma ? gamma[c] : 1.f) * coef[3 * C + c];
+    bcoef[1 * C + c] = a / static_cast<float>(M);
+    bcoef[2 * C + c] = b / static_cast<float>(M);
+  }
+}
+
+// BN_BWD_APPLY: p0 = g bf16, p1 = x raw bf16, p2 = coef fwd or null, p3 = bwd coef or null, p4 = alpha, p5 = dx out bf16,
+// p6 = optional g2
+// i: 0 M, 1 C, 2 act, 3 g_ld, 4 x_ld, 5 dx_ld, 6 has_bn; f: 0 leaky
+// has_bn: dx = c1*(dz - c2 - xhat*c3); else dx = dz
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
+                                    const float* __restrict__ coef, const float* __restrict__ bcoef,
+                                    const float* __restrict__ alpha, bf16* __restrict__ dx,
+                                    const bf16* __restrict__ g2, long long M, int C, int act, int g_ld, int x_ld,
+                                    int dx_ld, int has_bn, float leaky) {
+  const int groups = C / 8;
+  const long long total = M * groups;
+  const float slope = act == TSR_ACT_PRELU ? __ldg(alpha) : (act == TSR_ACT_RELU ? 0.f : leaky);
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int gi = static_cast<int>(idx % groups);
+    const long long m = idx / groups;
+    float gv[8], xv[8], o[8];
+    ld8(g + m * g_ld + gi * 8, gv);
+    ld8(x + m * x_ld + gi * 8, xv);
+    if (g2) {
+      float t[8];
+      ld8(g2 + m * g_ld + gi * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] += t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = gi * 8 + j;
+      float z = xv[j], dz = gv[j];
+      if (has_bn) z = z * __ldg(coef + c) + __ldg(coef + C + c);
+      if (act != TSR_ACT_NONE && z <= 0.f) dz *= slope;
+      if (has_bn) {
+        const float xhat = (xv[j] - __ldg(coef + 2 * C + c)) * __ldg(coef + 3 * C + c);
+        dz = __ldg(bcoef + c) * (dz - __ldg(bcoef + C + c) - xhat * __ldg(bcoef + 2 * C + c));
+      }
+      o[j] = dz;
+    }
+    st8(dx + m * dx_ld + gi * 8, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- small finalizers
+// COLSUM_FINALIZE: p0 = partial [tiles][ld][2], p1 = out[C]; i: 0 tiles, 1 C, 2 ld, 3 which (0/1), 4 accumulate
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int tiles, int C,
+                                       int ld, int which, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int t = 0; t < tiles; ++t) a += partial[(static_cast<long long>(t) * ld + c) * 2 + which];
+  out[c] = accumulate ? out[c] + a : a;
+}
+// SUM_FINALIZE: p0 = partial[n], p1 = out scalar; i: 0 n, 1 accumulate; f: 0 scale
+__global__ void sum_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int accumulate,
+                                    float scale) {
+  float t = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) t += partial[i];
+  t = warp_sum(t) * scale;
+  if (threadIdx.x == 0) *out = accumulate ? (*out + t) : t;
+}
+
+// ---------------------------------------------------------------------------------------------- pack / unpack
+struct PackIdx {
+  int co, ci, kh, kw;
+  bool valid;
+};
+// maps packed coordinates (tap slot t, row r, column c) to the OIHW element
+__device__ __forceinline__ PackIdx pack_index(const tsr_pack_entry_t& e, int t, int r, int c) {
+  PackIdx o;
+  o.valid = true;
+  const int Cout = e.cout, Cin = e.cin, KH = e.kh, KW = e.kw;
+  auto unshuffle = [&](int row) {
+    if (!e.shuffle) return row;
+    const int c4 = Cout / 4;
+    return 4 * (row % c4) + row / c4;
+  };
+  switch (e.mode) {
+    case TSR_PK_FWD:
+      o.kh = t / KW; o.kw = t % KW; o.valid = r < Cout && c < Cin; o.co = unshuffle(r); o.ci = c; break;
+    case TSR_PK_T:
+      o.kh = t / KW; o.kw = t % KW; o.valid = r < Cin && c < Cout; o.ci = r; o.co = unshuffle(c); break;
+    case TSR_PK_ROWK:
+      o.kh = t; o.valid = r < Cout && c < KW * Cin; o.co = r; o.kw = c / Cin; o.ci = c % Cin; break;
+    case TSR_PK_ROWN:
+      o.kh = t; o.valid = r < KW * Cout && c < Cin; o.kw = r / Cout; o.co = r % Cout; o.ci = c; break;
+    case TSR_PK_ROWN_T:
+      o.kh = t; o.valid = r < Cin && c < KW * Cout; o.ci = r; o.kw = c / Cout; o.co = c % Cout; break;
+    case TSR_PK_FULLK: {
+      o.valid = r < Cout && c < KH * KW * Cin; o.co = r; const int tt = c / Cin; o.ci = c % Cin; o.kh = tt / KW; o.kw = tt % KW;
+      break;
+    }
+    default:
+      o.valid = false;
+  }
+  return o;
+}
+__device__ __forceinline__ int find_entry(const tsr_pack_entry_t* tab, int n, long long block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].block_start <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+// PACK_W: p0 = device table of tsr_pack_entry_t; i: 0 n_entries; grid = total blocks, 256 threads x 4 elements
+__global__ void pack_w_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
+  const int ei = find_entry(tab, n, blockIdx.x);
+  const tsr_pack_entry_t e = tab[ei];
+  const long long base = (static_cast<long long>(blockIdx.x) - e.block_start) * 1024;
+  const float* src = reinterpret_cast<const float*>(e.src);
+  bf16* dst = reinterpret_cast<bf16*>(e.dst);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i >= e.count) continue;
+    float v = 0.f;
+    if (e.mode == TSR_PK_LINEAR) {
+      // rows = out features (cout), cols = in features ordered (h, w, c); kh*kw = Hf*Wf, cin = C
+      const int K = e.cin * e.kh * e.kw;
+      const int row = static_cast<int>(i / e.cols_pad), col = static_cast<int>(i % e.cols_pad);
+      if (row < e.cout && col < K) {
+        const int c = col % e.cin, hw = col / e.cin;
+        v = src[static_cast<long long>(row) * K + static_cast<long long>(c) * e.kh * e.kw + hw];
+      }
+    } else {
+      const int c = static_cast<int>(i % e.cols_pad);
+      const long long rr = i / e.cols_pad;
+      const int r = static_cast<int>(rr % e.rows_pad);
+      const int t = static_cast<int>(rr / e.rows_pad);
+      const PackIdx o = pack_index(e, t, r, c);
+      if (o.valid) v = src[((static_cast<long long>(o.co) * e.cin + o.ci) * e.kh + o.kh) * e.kw + o.kw];
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+// UNPACK_G: same table; src = fp32 accumulator laid out [rows = cout-like][tap][cols_pad] as written by the
+// wgrad kernel, i.e. acc[(r * taps + t) * cols_pad + c]; dst = fp32 OIHW gradient (overwritten).
+// For TSR_PK_T-style entries r/c are swapped by pack_index; wgrad accumulators always use the forward-like modes
+// (FWD, ROWK, ROWN, FULLK). count = rows_pad * taps * cols_pad.
+__global__ void unpack_g_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
+  const int ei = find_entry(tab, n, blockIdx.x);
+  const tsr_pack_entry_t e = tab[ei];
+  const long long base = (static_cast<long long>(blockIdx.x) - e.block_start) * 1024;
+  const float* src = reinterpret_cast<const float*>(e.src);
+  float* dst = reinterpret_cast<float*>(e.dst);
+  const int taps = (e.mode == TSR_PK_FWD) ? e.kh * e.kw : (e.mode == TSR_PK_FULLK ? 1 : e.kh);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i >= e.count) continue;
+    const int c = static_cast<int>(i % e.cols_pad);
+    const long long rr = i / e.cols_pad;
+    const int t = static_cast<int>(rr % taps);
+    const int r = static_cast<int>(rr / taps);
+    const PackIdx o = pack_index(e, t, r, c);
+    if (o.valid) dst[((static_cast<long long>(o.co) * e.cin + o.ci) * e.kh + o.kh) * e.kw + o.kw] = src[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- Linear wgrad
+// p0 = dpre fp32 [B][Nf] (gradient wrt pre-activation of the Linear), p1 = X bf16 [B][K] in (h,w,c) order,
+// p2 = dW fp32 [Nf][K] in the parameter's (c,h,w) order, p3 = db fp32 [Nf]
+// i: 0 B, 1 Nf, 2 K, 3 C, 4 HW (K = C*HW)
+__global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ dpre, const bf16* __restrict__ X,
+                                                           float* __restrict__ dW, float* __restrict__ db, int B,
+                                                           int Nf, int K, int C, int HW) {
+  // block: 8 output features x 256*? columns; each thread one column k (param order), loops over 8 features
+  extern __shared__ float sd[];  // [8][B]
+  const int n0 = blockIdx.y * 8;
+  for (int i = threadIdx.x; i < 8 * B; i += 256) {
+    const int f = i / B, b = i % B;
+    sd[i] = (n0 + f < Nf) ? dpre[static_cast<long long>(b) * Nf + n0 + f] : 0.f;
+  }
+  __syncthreads();
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k < K) {
+    const int c = k / HW, hw = k % HW;
+    const int kp = hw * C + c;
+    float acc[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float xv = __bfloat162float(X[static_cast<long long>(b) * K + kp]);
+#pragma unroll
+      for (int f = 0; f < 8; ++f) acc[f] += sd[f * B + b] * xv;
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+      if (n0 + f < Nf) dW[static_cast<long long>(n0 + f) * K + k] = acc[f];
+  }
+  if (blockIdx.x == 0 && db && threadIdx.x < 8 && n0 + threadIdx.x < Nf) {
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += sd[threadIdx.x * B + b];
+    db[n0 + threadIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- losses
+// LOSS: p0 = a fp32, p1 = b fp32, p2 = partial out [blocks], p3 = grad out fp32 (d loss / d a) or null
+// i: 0 n, 1 kind (0 = MSE, 1 = L1); f: 0 grad scale (upstream * 1/n)
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                   float* __restrict__ partial, float* __restrict__ grad, long long n,
+                                                   int kind, float gscale) {
+  __shared__ float sw[8];
+  float acc = 0.f;
+  for (long long i = (blockIdx.x * 256ll + threadIdx.x) * 4; i < n; i += static_cast<long long>(gridDim.x) * 1024) {
+    if (i + 3 < n) {
+      const float4 x = *reinterpret_cast<const float4*>(a + i), y = *reinterpret_cast<const float4*>(b + i);
+      const float d[4] = {x.x - y.x, x.y - y.y, x.z - y.z, x.w - y.w};
+      float gq[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc += kind == 0 ? d[j] * d[j] : fabsf(d[j]);
+        gq[j] = kind == 0 ? 2.f * d[j] * gscale : (d[j] > 0.f ? gscale : (d[j] < 0.f ? -gscale : 0.f));
+      }
+      if (grad) *reinterpret_cast<float4*>(grad + i) = make_float4(gq[0], gq[1], gq[2], gq[3]);
+    } else {
+      for (long long j = i; j < n; ++j) {
+        const float d = a[j] - b[j];
+        acc += kind == 0 ? d * d : fabsf(d);
+        if (grad) grad[j] = kind == 0 ? 2.f * d * gscale : (d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f));
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sw[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- upsample (ESRGAN)
+// UPSAMPLE2X: p0 = x bf16 [B,H,W,ld_in], p1 = y bf16 [B,2H,2W,ld_out]; i: 0 B,1 H,2 W,3 C,4 ld_in,5 ld_out
+__global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C,
+                                  int ld_in, int ld_out) {
+  const int groups = C / 8;
+  const long long total = static_cast<long long>(B) * 2 * H * 2 * W * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    long long p = idx / groups;
+    const int w = static_cast<int>(p % (2 * W));
+    const int h = static_cast<int>((p / (2 * W)) % (2 * H));
+    const int n = static_cast<int>(p / (4ll * W * H));
+    const uint4 q = *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * H + h / 2) * W + w / 2) * ld_in + g * 8);
+    *reinterpret_cast<uint4*>(y + p * ld_out + g * 8) = q;
+  }
+}
+// UPSAMPLE2X_BWD: p0 = dy bf16 [B,2H,2W,ld_in], p1 = dx bf16 [B,H,W,ld_out]; i as above (H,W = coarse dims)
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int H, int W, int C,
+                                      int ld_in, int ld_out) {
+  const int groups = C / 8;
+  const long long total = static_cast<long long>(B) * H * W * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    long long p = idx / groups;
+    const int w = static_cast<int>(p % W);
+    const int h = static_cast<int>((p / W) % H);
+    const int n = static_cast<int>(p / (static_cast<long long>(W) * H));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[8];
+        ld8(dy + ((static_cast<long long>(n) * 2 * H + 2 * h + i) * 2 * W + 2 * w + j) * ld_in + g * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      }
+    st8(dx + p * ld_out + g * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- classifier head
+// HEAD: p0 = pre1 fp32 [N1][B] (transposed split-K GEMM output, no bias), p1 = b1 [N1], p2 = w2 fp32 [N1], p3 = b2 [1],
+// p4 = out fp32 [B], p5 = h1 out fp32 [B][N1] (post-LeakyReLU, saved for backward), p6 = h1 bf16 out or null
+// i: 0 B, 1 N1, 2 sigmoid; f: 0 leaky
+// discriminator.py:64-69: Linear -> LeakyReLU(0.2) -> Linear(N1,1) -> Sigmoid (SRGAN) / logits (ESRGAN)
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ pre1, const float* __restrict__ b1,
+                                                   const float* __restrict__ w2, const float* __restrict__ b2,
+                                                   float* __restrict__ out, float* __restrict__ h1, int B, int N1,
+                                                   int sigmoid, float leaky) {
+  __shared__ float sw[8];
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < N1; k += 256) {
+    float z = pre1[static_cast<long long>(k) * B + b] + b1[k];
+    z = z > 0.f ? z : z * leaky;
+    h1[static_cast<long long>(b) * N1 + k] = z;
+    acc += z * w2[k];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = b2[0];
+    for (int w = 0; w < 8; ++w) t += sw[w];
+    out[b] = sigmoid ? 1.f / (1.f + __expf(-t)) : t;
+  }
+}
+// HEAD_BWD: p0 = gout fp32 [B] (grad wrt head output), p1 = out fp32 [B] (saved output), p2 = h1 fp32 [B][N1],
+// p3 = w2 [N1], p4 = dpre1 fp32 [B][N1] out, p5 = dpre1 bf16 [Bpad][N1] out (rows >= B zero-filled by caller),
+// p6 = dw2 [N1] out, p7 = db2 [1] out
+// i: 0 B, 1 N1, 2 sigmoid; f: 0 leaky.   One block per 256 features; loops over batch.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
+                                                       const float* __restrict__ h1, const float* __restrict__ w2,
+                                                       float* __restrict__ dpre1, bf16* __restrict__ dpre1_bf,
+                                                       float* __restrict__ dw2, float* __restrict__ db2, int B, int N1,
+                                                       int sigmoid, float leaky) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  float dw = 0.f, dbs = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float dl = gout[b];
+    if (sigmoid) {
+      const float pr = out[b];
+      dl *= pr * (1.f - pr);
+    }
+    dbs += dl;
+    if (k < N1) {
+      const float h = h1[static_cast<long long>(b) * N1 + k];
+      dw += dl * h;
+      float d = dl * w2[k];
+      if (h <= 0.f) d *= leaky;
+      dpre1[static_cast<long long>(b) * N1 + k] = d;
+      if (dpre1_bf) dpre1_bf[static_cast<long long>(b) * N1 + k] = __float2bfloat16(d);
+    }
+  }
+  if (k < N1) dw2[k] = dw;
+  if (k == 0) db2[0] = dbs;
+}
+
+// ---------------------------------------------------------------------------------------------- misc
+// AXPBY (bf16): p0 = x, p1 = y or null, p2 = out; i: 0 n (multiple of 8); f: 0 a, 1 b;  out = a*x + b*y
+__global__ void axpby_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, bf16* __restrict__ out,
+                             long long n, float a, float b) {
+  for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
+    float v[8];
+    ld8(x + i, v);
+    if (y) {
+      float t[8];
+      ld8(y + i, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = a * v[j] + b * t[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= a;
+    }
+    st8(out + i, v);
+  }
+}
+// MAXPOOL2 (VGG): p0 = x bf16 [B,H,W,C], p1 = y bf16 [B,H/2,W/2,C]; i: 0 B,1 H,2 W,3 C
+__global__ void maxpool2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+  const int groups = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    long long p = idx / groups;
+    const int w = static_cast<int>(p % Wo);
+    const int h = static_cast<int>((p / Wo) % Ho);
+    const int n = static_cast<int>(p / (static_cast<long long>(Wo) * Ho));
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[8];
+        ld8(x + ((static_cast<long long>(n) * H + 2 * h + i) * W + 2 * w + j) * C + g * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], v[k]);
+      }
+    st8(y + p * C + g * 8, m);
+  }
+}
+// MAXPOOL2_BWD: p0 = x (pool input) bf16, p1 = y (pool output) bf16, p2 = dy bf16, p3 = dx out bf16; i as MAXPOOL2.
+// Gradient goes to the first element equal to the max in (0,0),(0,1),(1,0),(1,1) order (ATen's tie rule).
+__global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, const bf16* __restrict__ dy,
+                                    bf16* __restrict__ dx, int B, int H, int W, int C) {
+  const int groups = C / 8, Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * groups;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(idx % groups);
+    long long p = idx / groups;
+    const int w = static_cast<int>(p % Wo);
+    const int h = static_cast<int>((p / Wo) % Ho);
+    const int n = static_cast<int>(p / (static_cast<long long>(Wo) * Ho));
+    float m[8], d[8];
+    bool done[8];
+    ld8(y + p * C + g * 8, m);
+    ld8(dy + p * C + g * 8, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) done[k] = false;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[8], o[8];
+        const long long off = ((static_cast<long long>(n) * H + 2 * h + i) * W + 2 * w + j) * C + g * 8;
+        ld8(x + off, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool hit = !done[k] && v[k] == m[k];
+          o[k] = hit ? d[k] : 0.f;
+          done[k] = done[k] || hit;
+        }
+        st8(dx + off, o);
+      }
+  }
+}
+// CAST: p0 = src, p1 = dst; i: 0 n, 1 dir (0: fp32 -> bf16, 1: bf16 -> fp32)
+__global__ void cast_kernel(const void* __restrict__ src, void* __restrict__ dst, long long n, int dir) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (dir == 0)
+      reinterpret_cast<bf16*>(dst)[i] = __float2bfloat16(reinterpret_cast<const float*>(src)[i]);
+    else
+      reinterpret_cast<float*>(dst)[i] = __bfloat162float(reinterpret_cast<const bf16*>(src)[i]);
+  }
+}
+
+inline int grid_for(long long work_items, int block = 256, int max_blocks = 148 * 16) {
+  long long b = (work_items + block - 1) / block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
+  const int64_t* i = d.i;
+  void* const* p = d.p;
+  switch (d.kind) {
+    case TSR_E_IM2ROW:
+      im2row_kernel<<<grid_for(i[0] * i[2] * i[3] * (i[9] / 8)), 256, 0, st>>>(
+          (const float*)p[0], (bf16*)p[1], i[0], i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8], i[9]);
+      break;
+    case TSR_E_GATHER_OUT:
+      gather_out_kernel<<<grid_for(i[0] * i[1] * i[2] * i[3]), 256, 0, st>>>(p[0], (float*)p[1], (const float*)p[2], i[0],
+                                                                          i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8],
+                                                                          i[9], i[10]);
+      break;
+    case TSR_E_NCHW2NHWC:
+      nchw2nhwc_kernel<<<grid_for(i[0] * (i[1] / 8) * i[2] * i[3]), 256, 0, st>>>((const float*)p[0], (bf16*)p[1], i[0],
+                                                                               i[1], i[2], i[3], i[4], i[5]);
+      break;
+    case TSR_E_NHWC2NCHW:
+      nhwc2nchw_kernel<<<grid_for(i[0] * (i[1] / 8) * i[2] * i[3]), 256, 0, st>>>((const bf16*)p[0], (float*)p[1], i[0],
+                                                                               i[1], i[2], i[3], i[4], i[5], i[6]);
+      break;
+    case TSR_E_BN_FINALIZE:
+      bn_finalize_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[0], (const float*)p[1], (const float*)p[2],
+                                                            (float*)p[3], (float*)p[4], (long long*)p[5], (float*)p[6],
+                                                            i[0], i[1], i[2], i[3], i[4], d.f[0], d.f[1]);
+      break;
+    case TSR_E_BN_EVAL_COEF:
+      bn_eval_coef_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[1], (const float*)p[2], (const float*)p[3],
+                                                             (const float*)p[4], (float*)p[6], i[1], d.f[0]);
+      break;
+    case TSR_E_BN_ACT:
+      bn_act_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>((const bf16*)p[0], (const float*)p[1], (bf16*)p[2],
+                                                              (const bf16*)p[3], (const float*)p[4], i[0], i[1], i[2],
+                                                              i[3], i[4], i[5], i[6], i[7], i[8], d.f[0], d.f[1], d.f[2]);
+      break;
+    case TSR_E_BN_BWD_REDUCE: {
+      const int C = i[1];
+      const int lanes = 256 / (C / 8);
+      const long long blocks = (i[0] + i[3] - 1) / i[3];
+      const size_t sm = (static_cast<size_t>(lanes) * C * 2 + 8) * sizeof(float);
+      bn_bwd_reduce_kernel<<<blocks, 256, sm, st>>>((const bf16*)p[0], (const bf16*)p[1], (const float*)p[2],
+                                                    (const float*)p[3], (float*)p[4], (float*)p[5], (const bf16*)p[6],
+                                                    i[0], C, i[2], i[3], i[4], i[5], i[6], d.f[0]);
+      break;
+    }
+    case TSR_E_BN_BWD_FINALIZE:
+      bn_bwd_finalize_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[0], (const float*)p[1],
+                                                                (const float*)p[2], (const float*)p[3], (float*)p[4],
+                                                                (float*)p[5], (float*)p[6], (float*)p[7], i[0], i[1],
+                                                                i[2], i[3], i[4]);
+      break;
+    case TSR_E_BN_BWD_APPLY:
+      bn_bwd_apply_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>((const bf16*)p[0], (const bf16*)p[1],
+                                                                    (const float*)p[2], (const float*)p[3],
+                                                                    (const float*)p[4], (bf16*)p[5], (const bf16*)p[6],
+                                                                    i[0], i[1], i[2], i[3], i[4], i[5], i[6], d.f[0]);
+      break;
+    case TSR_E_COLSUM_FINALIZE:
+      colsum_finalize_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3],
+                                                                i[4]);
+      break;
+    case TSR_E_SUM_FINALIZE:
+      sum_finalize_kernel<<<1, 32, 0, st>>>((const float*)p[0], (float*)p[1], i[0], i[1], d.f[0]);
+      break;
+    case TSR_E_PACK_W:
+      pack_w_kernel<<<static_cast<unsigned>(i[1]), 256, 0, st>>>((const tsr_pack_entry_t*)p[0], i[0]);
+      break;
+    case TSR_E_UNPACK_G:
+      unpack_g_kernel<<<static_cast<unsigned>(i[1]), 256, 0, st>>>((const tsr_pack_entry_t*)p[0], i[0]);
+      break;
+    case TSR_E_LINEAR_WGRAD: {
+      dim3 grid((i[2] + 255) / 256, (i[1] + 7) / 8);
+      linear_wgrad_kernel<<<grid, 256, 8 * i[0] * sizeof(float), st>>>((const float*)p[0], (const bf16*)p[1],
+                                                                      (float*)p[2], (float*)p[3], i[0], i[1], i[2], i[3],
+                                                                      i[4]);
+      break;
+    }
+    case TSR_E_LOSS:
+      loss_kernel<<<static_cast<unsigned>(i[2]), 256, 0, st>>>((const float*)p[0], (const float*)p[1], (float*)p[2],
+                                                              (float*)p[3], i[0], i[1], d.f[0]);
+      break;
+    case TSR_E_ZERO:
+      return cudaMemsetAsync(p[0], 0, static_cast<size_t>(i[0]), st);
+    case TSR_E_UPSAMPLE2X:
+      upsample2x_kernel<<<grid_for(i[0] * 4 * i[1] * i[2] * (i[3] / 8)), 256, 0, st>>>((const bf16*)p[0], (bf16*)p[1],
+                                                                                   i[0], i[1], i[2], i[3], i[4], i[5]);
+      break;
+    case TSR_E_UPSAMPLE2X_BWD:
+      upsample2x_bwd_kernel<<<grid_for(i[0] * i[1] * i[2] * (i[3] / 8)), 256, 0, st>>>((const bf16*)p[0], (bf16*)p[1],
+                                                                                   i[0], i[1], i[2], i[3], i[4], i[5]);
+      break;
+    case TSR_E_HEAD:
+      head_kernel<<<static_cast<unsigned>(i[0]), 256, 0, st>>>((const float*)p[0], (const float*)p[1], (const float*)p[2],
+                                                              (const float*)p[3], (float*)p[4], (float*)p[5], i[0], i[1],
+                                                              i[2], d.f[0]);
+      break;
+    case TSR_E_HEAD_BWD:
+      head_bwd_kernel<<<(i[1] + 255) / 256, 256, 0, st>>>((const float*)p[0], (const float*)p[1], (const float*)p[2],
+                                                         (const float*)p[3], (float*)p[4], (bf16*)p[5], (float*)p[6],
+                                                         (float*)p[7], i[0], i[1], i[2], d.f[0]);
+      break;
+    case TSR_E_AXPBY:
+      axpby_kernel<<<grid_for(i[0] / 8), 256, 0, st>>>((const bf16*)p[0], (const bf16*)p[1], (bf16*)p[2], i[0], d.f[0],
+                                                      d.f[1]);
+      break;
+    case TSR_E_MAXPOOL2:
+      maxpool2_kernel<<<grid_for(i[0] * (i[1] / 2) * (i[2] / 2) * (i[3] / 8)), 256, 0, st>>>((const bf16*)p[0],
+                                                                                         (bf16*)p[1], i[0], i[1], i[2],
+                                                                                         i[3]);
+      break;
+    case TSR_E_MAXPOOL2_BWD:
+      maxpool2_bwd_kernel<<<grid_for(i[0] * (i[1] / 2) * (i[2] / 2) * (i[3] / 8)), 256, 0, st>>>(
+          (const bf16*)p[0], (const bf16*)p[1], (const bf16*)p[2], (bf16*)p[3], i[0], i[1], i[2], i[3]);
+      break;
+    case TSR_E_CAST:
+      cast_kernel<<<grid_for(i[0]), 256, 0, st>>>(p[0], p[1], i[0], i[1]);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace tsr
