@@ -1,0 +1,254 @@
+"""Descriptor builders over the C ABI: turns convolution geometry into tsr_conv_desc_t / tsr_wgrad_desc_t /
+tsr_elt_desc_t and records them into native programs. Pure host logic (no GPU needed to build descriptors
+until they are handed to the library)."""
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+from . import _lib as L
+from ._lib import ConvDesc, EltDesc, PackEntry, WgradDesc
+
+
+def ptr(t, offset_elems: int = 0) -> int:
+    """Device address of a torch tensor (plus an element offset) or a plain int."""
+    if t is None:
+        return 0
+    if isinstance(t, int):
+        return t
+    return t.data_ptr() + offset_elems * t.element_size()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def pick_block_k(c: int) -> int:
+    for bk in (64, 32, 16):
+        if c % bk == 0:
+            return bk
+    raise ValueError(f"channel count {c} must be a multiple of 16")
+
+
+# --------------------------------------------------------------------------------------------- geometry
+def fwd_geometry(H: int, W: int, KH: int, KW: int, ph: int, pw: int, stride: int):
+    """Bounding box and tap offsets of a forward cross-correlation (nn.Conv2d semantics)."""
+    Ho = (H + 2 * ph - KH) // stride + 1
+    Wo = (W + 2 * pw - KW) // stride + 1
+    taps = [(kh, kw, kh * KW + kw) for kh in range(KH) for kw in range(KW)]
+    return dict(lower_h=-ph, lower_w=-pw, upper_h=ph - (KH - 1), upper_w=pw - (KW - 1), Ho=Ho, Wo=Wo, stride=stride,
+                taps=taps)
+
+
+def dgrad_s1_geometry(H: int, W: int, KH: int, KW: int, ph: int, pw: int):
+    """Data gradient of a stride-1 'same' conv, as a conv over dY with transposed (unflipped) weight slots:
+    dX[h,w] = sum_{kh,kw} dY[h+ph-kh, w+pw-kw] * Wt[kh,kw]."""
+    taps = [(KH - 1 - kh, KW - 1 - kw, kh * KW + kw) for kh in range(KH) for kw in range(KW)]
+    return dict(lower_h=-(KH - 1 - ph), lower_w=-(KW - 1 - pw), upper_h=-ph, upper_w=-pw, Ho=H, Wo=W, stride=1,
+                taps=taps)
+
+
+def dgrad_s2_classes(K: int, p: int):
+    """Output-parity decomposition of the data gradient of a stride-2 conv (kernel K, padding p).
+    Returns {parity r: [(offset, k), ...]} per dimension: dX[2a+r] = sum dY[a+offset] * W[k]."""
+    out = {}
+    for r in (0, 1):
+        lst = []
+        for k in range(K):
+            if (r + p - k) % 2 == 0 and (r + p - k) >= 0:
+                lst.append(((r + p - k) // 2, k))
+        out[r] = lst
+    return out
+
+
+# --------------------------------------------------------------------------------------------- descriptors
+def _set_taps(d, taps: Sequence[Tuple[int, int, int]]):
+    d.num_taps = len(taps)
+    for i, (oh, ow, slot) in enumerate(taps):
+        assert 0 <= oh < 256 and 0 <= ow < 256
+        d.tap_off[i] = (oh << 8) | ow
+        if hasattr(d, "tap_wrow"):
+            d.tap_wrow[i] = slot
+
+
+def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n, out, os_n, os_h, os_w, n_valid,
+              block_k=None, a_c0=0, out_mode=L.OUT_LINEAR, out_f32=False, out_ch_off=0, bias=None, prelu=None,
+              act=L.ACT_NONE, out_preact=None, res=None, bwd_z=None, bwd_act=L.ACT_NONE, aux=(0, 0, 0), aux_ch_off=0,
+              dalpha_partial=None, stats_partial=None, stats_ld=0, acc_scale=1.0, leaky=0.2, shuf_c=64) -> ConvDesc:
+    d = ConvDesc()
+    d.x, d.w = ptr(x), ptr(w)
+    d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
+    d.Ho, d.Wo = geom["Ho"], geom["Wo"]
+    d.a_mode = 0
+    d.stride = geom["stride"]
+    d.lower_h, d.lower_w, d.upper_h, d.upper_w = geom["lower_h"], geom["lower_w"], geom["upper_h"], geom["upper_w"]
+    _set_taps(d, geom["taps"])
+    d.block_k = block_k or pick_block_k(C - a_c0)
+    d.block_n = block_n
+    d.cout_pad = cout_pad
+    d.w_rows, d.w_ld = n_slots * cout_pad, w_ld
+    d.a_c0 = a_c0
+    d.splits = 1
+    d.out, d.out_preact, d.bias, d.prelu = ptr(out), ptr(out_preact), ptr(bias), ptr(prelu)
+    d.res, d.bwd_z, d.dalpha_partial, d.stats_partial = ptr(res), ptr(bwd_z), ptr(dalpha_partial), ptr(stats_partial)
+    d.os_n, d.os_h, d.os_w = os_n, os_h, os_w
+    d.aux_n, d.aux_h, d.aux_w = aux
+    d.out_mode, d.out_f32, d.out_ch_off, d.aux_ch_off = out_mode, int(out_f32), out_ch_off, aux_ch_off
+    d.n_valid, d.act, d.bwd_act, d.stats_ld, d.shuf_c = n_valid, act, bwd_act, stats_ld, shuf_c
+    d.acc_scale, d.leaky_slope = acc_scale, leaky
+    return d
+
+
+def dgrad_s2_descs(*, dy, N, Hy, Wy, Cout, dy_ld, wt, Cin, cin_pad, block_n, out, Hx, Wx, out_ld, n_valid,
+                   out_f32=False, out_ch_off=0, **epi) -> List[ConvDesc]:
+    """Data gradient of a 3x3 / stride-2 / pad-1 conv as four stride-1 convs over dY, one per output-parity class
+    (rh, rw): dX[n, 2a+rh, 2b+rw, :] = sum_taps dY[n, a+oh, b+ow, :] . Wt[kh*3+kw]. `wt` is the PK_T pack
+    [9][cin_pad][Cout]; extra epilogue keywords are forwarded to conv_desc (aux strides must be the caller's)."""
+    assert Hx == 2 * Hy and Wx == 2 * Wy, "stride-2 data gradient expects even input sizes"
+    cls = dgrad_s2_classes(3, 1)
+    descs = []
+    for rh in (0, 1):
+        for rw in (0, 1):
+            taps = [(oh, ow, kh * 3 + kw) for (oh, kh) in cls[rh] for (ow, kw) in cls[rw]]
+            geom = dict(lower_h=0, lower_w=0, upper_h=0, upper_w=0, Ho=Hy, Wo=Wy, stride=1, taps=taps)
+            elem = 4 if out_f32 else 2
+            base = ptr(out) + (rh * Wx + rw) * out_ld * elem
+            descs.append(conv_desc(x=dy, N=N, H=Hy, W=Wy, C=Cout, x_ld=dy_ld, geom=geom, w=wt, cout_pad=cin_pad,
+                                   w_ld=Cout, n_slots=9, block_n=block_n, out=base, os_n=Hx * Wx * out_ld,
+                                   os_h=2 * Wx * out_ld, os_w=2 * out_ld, n_valid=n_valid, out_f32=out_f32,
+                                   out_ch_off=out_ch_off, **epi))
+    return descs
+
+
+def gemm_desc(*, a, M, K, a_ld, a_mn_major=False, w, n_rows, block_n, out, out_ld, n_valid, splits=1, bias=None,
+              act=L.ACT_NONE, atomic_t=False, out_f32=True, acc_scale=1.0, leaky=0.2) -> ConvDesc:
+    """D[M, n] = sum_k A[m,k] * Wt[n,k].  atomic_t: fp32 atomics into out[n*out_ld + m] (split-K)."""
+    d = ConvDesc()
+    d.x, d.w = ptr(a), ptr(w)
+    d.a_mode = 2 if a_mn_major else 1
+    d.gemm_M, d.gemm_K, d.x_ld = M, K, a_ld
+    d.stride = 1
+    d.num_taps = 1
+    d.block_k = 64
+    d.block_n = block_n
+    d.cout_pad = n_rows
+    d.w_rows, d.w_ld = n_rows, K
+    d.splits = splits
+    d.out, d.bias = ptr(out), ptr(bias)
+    d.out_mode = L.OUT_GEMM_T_ATOMIC if atomic_t else L.OUT_LINEAR
+    d.out_f32 = int(out_f32)
+    d.os_n = out_ld if atomic_t else 0
+    d.os_w = out_ld
+    d.n_valid, d.act = n_valid, act
+    d.acc_scale, d.leaky_slope = acc_scale, leaky
+    d.shuf_c = 64
+    return d
+
+
+def wgrad_desc(*, x, N, H, W, C, x_ld, geom, dy, dy_ld, dy_c, out, cout_valid, block_n, chan_block=None, dy_block=None,
+               x_c0=0, dy_c0=0, splits=0) -> WgradDesc:
+    d = WgradDesc()
+    d.x, d.dy, d.out = ptr(x), ptr(dy), ptr(out)
+    d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
+    d.Ho, d.Wo, d.dy_ld, d.dy_c = geom["Ho"], geom["Wo"], dy_ld, dy_c
+    d.stride = geom["stride"]
+    d.lower_h, d.lower_w, d.upper_h, d.upper_w = geom["lower_h"], geom["lower_w"], geom["upper_h"], geom["upper_w"]
+    _set_taps(d, geom["taps"])
+    d.chan_block = chan_block or pick_block_k(C - x_c0)
+    d.dy_block = dy_block or pick_block_k(dy_c)
+    d.block_n = block_n
+    d.cout_valid = cout_valid
+    d.x_c0, d.dy_c0, d.splits = x_c0, dy_c0, splits
+    return d
+
+
+def elt(kind: int, p: Iterable = (), i: Iterable = (), f: Iterable = ()) -> EltDesc:
+    d = EltDesc()
+    d.kind = kind
+    for k, v in enumerate(p):
+        d.p[k] = ptr(v)
+    for k, v in enumerate(i):
+        d.i[k] = int(v)
+    for k, v in enumerate(f):
+        d.f[k] = float(v)
+    return d
+
+
+# --------------------------------------------------------------------------------------------- programs
+class Program:
+    """A recorded launch list owned by the native library (tsr_prog_t)."""
+
+    def __init__(self):
+        self._lib = L.load()
+        self._h = self._lib.tsr_prog_create()
+        self.keep: List = []  # tensors referenced by raw pointer
+        self.marks = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.tsr_prog_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def add(self, d) -> int:
+        if isinstance(d, ConvDesc):
+            r = self._lib.tsr_prog_add_conv(self._h, C.byref(d))
+        elif isinstance(d, WgradDesc):
+            r = self._lib.tsr_prog_add_wgrad(self._h, C.byref(d))
+        else:
+            r = self._lib.tsr_prog_add_elt(self._h, C.byref(d))
+        if r < 0:
+            L.check(r)
+        return r
+
+    def mark(self, name: str):
+        self.marks[name] = len(self)
+
+    def __len__(self) -> int:
+        return int(self._lib.tsr_prog_size(self._h))
+
+    def run(self, first: int = 0, count: int = -1, stream: Optional[int] = None):
+        L.check(self._lib.tsr_prog_run(self._h, first, count, stream if stream is not None else current_stream()))
+
+
+def run_now(d, stream: Optional[int] = None):
+    """Immediate-mode launch of a single descriptor."""
+    lib = L.load()
+    st = stream if stream is not None else current_stream()
+    if isinstance(d, ConvDesc):
+        L.check(lib.tsr_conv(C.byref(d), st))
+    elif isinstance(d, WgradDesc):
+        L.check(lib.tsr_wgrad(C.byref(d), st))
+    else:
+        L.check(lib.tsr_elt(C.byref(d), st))
+
+
+def check_watchdog():
+    lib = L.load()
+    L.check(lib.tsr_check_watchdog(current_stream()))
+
+
+# --------------------------------------------------------------------------------------------- pack tables
+def pack_table(entries: List[dict], device):
+    """Builds the device table for TSR_E_PACK_W / TSR_E_UNPACK_G. Each entry: src, dst, mode, cout, cin, kh, kw,
+    rows_pad, cols_pad, shuffle, count. Returns (table tensor, n_entries, n_blocks)."""
+    import torch
+    arr = (PackEntry * len(entries))()
+    blocks = 0
+    for k, e in enumerate(entries):
+        pe = arr[k]
+        pe.src, pe.dst = ptr(e["src"]), ptr(e["dst"])
+        pe.mode = e["mode"]
+        pe.cout, pe.cin, pe.kh, pe.kw = e["cout"], e["cin"], e["kh"], e["kw"]
+        pe.rows_pad, pe.cols_pad, pe.shuffle = e["rows_pad"], e["cols_pad"], int(e.get("shuffle", 0))
+        pe.block_start = blocks
+        pe.count = e["count"]
+        blocks += (e["count"] + 1023) // 1024
+    raw = bytes(arr)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    return t, len(entries), blocks
