@@ -136,7 +136,8 @@ enum tsr_elt_kind {
   TSR_E_MAXPOOL2 = 24,
   TSR_E_MAXPOOL2_BWD = 25,
   TSR_E_CAST = 26,
-  TSR_E_ADAM = 27
+  TSR_E_ADAM = 27,
+  TSR_E_CHANSUM_NCHW = 28
 };
 
 /* weight pack / grad unpack index maps (TSR_E_PACK_W / TSR_E_UNPACK_G table entries) */

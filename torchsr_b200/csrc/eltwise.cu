@@ -647,12 +647,13 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ pre
 // HEAD_BWD: p0 = gout fp32 [B] (grad wrt head output), p1 = out fp32 [B] (saved output), p2 = h1 fp32 [B][N1],
 // p3 = w2 [N1], p4 = dpre1 fp32 [B][N1] out, p5 = dpre1 bf16 [Bpad][N1] out (rows >= B zero-filled by caller),
 // p6 = dw2 [N1] out, p7 = db2 [1] out
-// i: 0 B, 1 N1, 2 sigmoid; f: 0 leaky.   One block per 256 features; loops over batch.
+// i: 0 B, 1 N1, 2 sigmoid, 3 row stride of dpre1_bf in elements (0 = N1); f: 0 leaky.
+// One block per 256 features; loops over batch.
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
                                                        const float* __restrict__ h1, const float* __restrict__ w2,
                                                        float* __restrict__ dpre1, bf16* __restrict__ dpre1_bf,
                                                        float* __restrict__ dw2, float* __restrict__ db2, int B, int N1,
-                                                       int sigmoid, float leaky) {
+                                                       int sigmoid, int ld_bf, float leaky) {
   const int k = blockIdx.x * 256 + threadIdx.x;
   float dw = 0.f, dbs = 0.f;
   for (int b = 0; b < B; ++b) {
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       float d = dl * w2[k];
       if (h <= 0.f) d *= leaky;
       dpre1[static_cast<long long>(b) * N1 + k] = d;
-      if (dpre1_bf) dpre1_bf[static_cast<long long>(b) * N1 + k] = __float2bfloat16(d);
+      if (dpre1_bf) dpre1_bf[static_cast<long long>(b) * ld_bf + k] = __float2bfloat16(d);
     }
   }
   if (k < N1) dw2[k] = dw;
@@ -765,6 +766,31 @@ __global__ void cast_kernel(const void* __restrict__ src, void* __restrict__ dst
       reinterpret_cast<bf16*>(dst)[i] = __float2bfloat16(reinterpret_cast<const float*>(src)[i]);
     else
       reinterpret_cast<float*>(dst)[i] = __bfloat162float(reinterpret_cast<const bf16*>(src)[i]);
+  }
+}
+
+// CHANSUM_NCHW: p0 = x fp32 [B][C][HW], p1 = partial out [splits][C][2] (slot 0 = sum); i: 0 B, 1 C, 2 HW, 3 splits
+// grid (C, splits): split s of channel c covers a contiguous slice of the B*HW elements of that channel.
+__global__ void __launch_bounds__(256) chansum_nchw_kernel(const float* __restrict__ x, float* __restrict__ partial, int B,
+                                                           int C, long long HW, int splits) {
+  __shared__ float sw[8];
+  const int c = blockIdx.x, s = blockIdx.y;
+  const long long total = static_cast<long long>(B) * HW;
+  const long long per = (total + splits - 1) / splits;
+  const long long lo = s * per, hi = min(total, lo + per);
+  float acc = 0.f;
+  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+    const long long b = i / HW, r = i - b * HW;
+    acc += __ldg(x + (b * C + c) * HW + r);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += sw[w];
+    partial[(static_cast<long long>(s) * C + c) * 2 + 0] = t;
+    partial[(static_cast<long long>(s) * C + c) * 2 + 1] = 0.f;
   }
 }
 
@@ -876,7 +902,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
     case TSR_E_HEAD_BWD:
       head_bwd_kernel<<<(i[1] + 255) / 256, 256, 0, st>>>((const float*)p[0], (const float*)p[1], (const float*)p[2],
                                                          (const float*)p[3], (float*)p[4], (bf16*)p[5], (float*)p[6],
-                                                         (float*)p[7], i[0], i[1], i[2], d.f[0]);
+                                                         (float*)p[7], i[0], i[1], i[2], i[3] > 0 ? i[3] : i[1], d.f[0]);
       break;
     case TSR_E_AXPBY:
       axpby_kernel<<<grid_for(i[0] / 8), 256, 0, st>>>((const bf16*)p[0], (const bf16*)p[1], (bf16*)p[2], i[0], d.f[0],
@@ -894,6 +920,11 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
     case TSR_E_CAST:
       cast_kernel<<<grid_for(i[0]), 256, 0, st>>>(p[0], p[1], i[0], i[1]);
       break;
+    case TSR_E_CHANSUM_NCHW: {
+      dim3 grid(static_cast<unsigned>(i[1]), static_cast<unsigned>(i[3]));
+      chansum_nchw_kernel<<<grid, 256, 0, st>>>((const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3]);
+      break;
+    }
     default:
       return cudaErrorInvalidValue;
   }

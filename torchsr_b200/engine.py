@@ -1,0 +1,540 @@
+"""Plan compiler of the B200 path: turns one nn.Module call (generator or discriminator, at one input shape)
+into recorded native launch lists (ops.Program) over pre-allocated NHWC bf16 workspaces, and binds them to autograd.
+
+Replaces the per-op ATen dispatch of the reference's forward() methods and autograd graph
+(torchsr/srgan/generator.py:60-81, discriminator.py:71-88, the esrgan twins). Layout decisions:
+
+* activations: NHWC bf16, one buffer per tensor that backward needs (raw conv outputs, activations, pre-activations);
+* parameters stay fp32 OIHW torch Parameters (the state_dict contract); bf16 packed copies ([tap][Cout][Cin] for
+  forward, [tap][Cin][Cout] for the data gradient) live in one arena per module and are re-packed by ONE kernel
+  whenever a parameter's version counter moved (i.e. after optimizer.step / load_state_dict);
+* weight gradients: fp32 atomically-accumulated arena in packed order -> ONE unpack kernel -> flat fp32 gradient in
+  parameters() order -> handed to autograd as views of a clone.
+"""
+from typing import Callable, Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+NUM_SMS = 148
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class Act:
+    """A [B, H, W, C] NHWC view: tensor + geometry (ld = pixel stride in elements, c0 = first channel)."""
+    __slots__ = ("t", "B", "H", "W", "C", "ld", "c0", "hook")
+
+    def __init__(self, t, B, H, W, C, ld=None, c0=0):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.ld = ld if ld is not None else C
+        self.c0 = c0
+        # Set by the producer of this activation when its own activation backward (and PixelShuffle inverse) can be
+        # fused into the epilogue of the data-gradient conv that computes d/d(this): dict(bwd_z=Act, bwd_act=int,
+        # prelu=Tensor, unshuffle_to=Act, dalpha_partial=Tensor).
+        self.hook = None
+
+    @property
+    def M(self) -> int:
+        return self.B * self.H * self.W
+
+    def strides(self):
+        return (self.H * self.W * self.ld, self.W * self.ld, self.ld)
+
+
+# ------------------------------------------------------------------------------------------------ parameter store
+class ConvRec:
+    """Packing / gradient bookkeeping of one nn.Conv2d.
+    kind: 'std'   KxK conv, Cin multiple of 16: implicit GEMM over the NHWC input (TMA im2col)
+          'fullk' Cin == 3: the input is expanded by the im2row kernel to K*K*3 (padded) columns, then a 1-tap GEMM
+          'rown'  9x9, Cout == 3 (SRGAN conv3): 9 vertical taps with N' = kw*3+co columns, horizontal taps summed by
+                  the gather kernel
+    """
+
+    def __init__(self, name: str, conv: nn.Conv2d, kind: str = "std", shuffle: bool = False, need_dgrad: bool = True):
+        self.name, self.conv, self.kind, self.shuffle, self.need_dgrad = name, conv, kind, shuffle, need_dgrad
+        self.weight, self.bias = conv.weight, conv.bias
+        self.cout, self.cin, self.k, _ = conv.weight.shape
+        self.stride = conv.stride[0]
+        self.pad = conv.padding[0]
+        k = self.k
+        if kind == "std":
+            assert self.cin % 16 == 0
+            self.cout_pad = _round_up(self.cout, 16)
+            self.block_n = self.cout_pad if self.cout_pad <= 128 else 128
+            assert self.cout_pad % self.block_n == 0
+            self.slots, self.cols = k * k, self.cin
+            self.fwd_mode, self.t_mode = L.PK_FWD, L.PK_T
+            self.t_rows, self.t_cols = self.cin, _round_up(self.cout, 16)
+            self.acc_rows, self.acc_taps, self.acc_cols = self.cout_pad, k * k, self.cin
+        elif kind == "fullk":
+            self.epad = _round_up(k * k * self.cin, 32)
+            self.cout_pad = self.cout
+            self.block_n = min(self.cout, 128)
+            self.slots, self.cols = 1, self.epad
+            self.fwd_mode, self.t_mode = L.PK_FULLK, L.PK_T
+            self.t_rows, self.t_cols = _round_up(k * k * self.cin, 32), self.cout   # [k*k*cin (padded)][cout]
+            self.acc_rows, self.acc_taps, self.acc_cols = self.cout, 1, self.epad
+        elif kind == "rown":
+            self.npad = _round_up(k * self.cout, 32)     # 27 -> 32 columns (kw*cout + co)
+            self.cout_pad = self.npad
+            self.block_n = self.npad
+            self.slots, self.cols = k, self.cin
+            self.fwd_mode, self.t_mode = L.PK_ROWN, L.PK_ROWN_T
+            self.t_rows, self.t_cols = self.cin, self.npad
+            self.acc_rows, self.acc_taps, self.acc_cols = self.npad, k, self.cin
+        else:
+            raise ValueError(kind)
+        self.w_fwd = self.w_t = self.acc = self.bias_packed = None
+
+
+class LinearRec:
+    """nn.Linear applied to a flattened NHWC feature map [B][Hf*Wf*C] (weight columns permuted from (c,h,w))."""
+
+    def __init__(self, name: str, lin: nn.Linear, C: int, Hf: int, Wf: int):
+        self.name, self.lin, self.C, self.Hf, self.Wf = name, lin, C, Hf, Wf
+        self.weight, self.bias = lin.weight, lin.bias
+        self.nout, self.K = lin.weight.shape
+        assert self.K == C * Hf * Wf
+        self.nout_pad = _round_up(self.nout, 128)
+        self.w_fwd = None
+
+
+class ParamStore:
+    """Everything derived from one module's parameters: packed bf16 weights, wgrad accumulators, flat gradient."""
+
+    def __init__(self, module: nn.Module, convs: List[ConvRec], linears: List[LinearRec], device):
+        self.module, self.convs, self.linears, self.device = module, convs, linears, device
+        self.params = [p for _, p in module.named_parameters()]
+        self.offsets: Dict[int, int] = {}
+        off = 0
+        for p in self.params:
+            self.offsets[id(p)] = off
+            off += _round_up(p.numel(), 4)          # keep every slice 16-byte aligned
+        self.total = off
+        self.flat_grad = torch.zeros(max(off, 4), dtype=F32, device=device)
+        # ---- arenas: bf16 packed operands, fp32 weight-gradient accumulators (packed order)
+        w_elems, acc_elems = 0, 0
+        for r in convs:
+            r._fwd_off, w_elems = w_elems, w_elems + _round_up(r.slots * r.cout_pad * r.cols, 128)
+            if r.need_dgrad:
+                r._t_off, w_elems = w_elems, w_elems + _round_up(self._t_slots(r) * r.t_rows * r.t_cols, 128)
+            r._acc_off, acc_elems = acc_elems, acc_elems + _round_up(r.acc_rows * r.acc_taps * r.acc_cols, 64)
+        for r in linears:
+            r._fwd_off, w_elems = w_elems, w_elems + _round_up(r.nout_pad * r.K, 128)
+        self.w_arena = torch.zeros(max(w_elems, 128), dtype=BF16, device=device)
+        self.acc_arena = torch.zeros(max(acc_elems, 64), dtype=F32, device=device)
+        self._version = None
+        self._build_tables()
+
+    # T-pack slot counts differ per kind
+    @staticmethod
+    def _t_slots(r: ConvRec) -> int:
+        return {"std": r.k * r.k, "fullk": 1, "rown": r.k}[r.kind]
+
+    def _build_tables(self):
+        pack, unpack = [], []
+        self.bias_perm: List[ConvRec] = []
+        for r in self.convs:
+            n_fwd = r.slots * r.cout_pad * r.cols
+            r.w_fwd = self.w_arena[r._fwd_off:r._fwd_off + n_fwd]
+            pack.append(dict(src=r.weight, dst=r.w_fwd, mode=r.fwd_mode, cout=r.cout, cin=r.cin, kh=r.k, kw=r.k,
+                             rows_pad=r.cout_pad, cols_pad=r.cols, shuffle=r.shuffle, count=n_fwd))
+            if r.need_dgrad:
+                if r.kind == "fullk":
+                    # [k*k*cin][cout] == PK_T with rows_pad = cin: rows t*cin+ci; the padded tail rows stay zero
+                    n_t = r.k * r.k * r.cin * r.t_cols
+                    r.w_t = self.w_arena[r._t_off:r._t_off + r.t_rows * r.t_cols]
+                    pack.append(dict(src=r.weight, dst=r.w_t, mode=L.PK_T, cout=r.cout, cin=r.cin, kh=r.k, kw=r.k,
+                                     rows_pad=r.cin, cols_pad=r.t_cols, shuffle=0, count=n_t))
+                else:
+                    n_t = self._t_slots(r) * r.t_rows * r.t_cols
+                    r.w_t = self.w_arena[r._t_off:r._t_off + n_t]
+                    pack.append(dict(src=r.weight, dst=r.w_t, mode=r.t_mode, cout=r.cout, cin=r.cin, kh=r.k, kw=r.k,
+                                     rows_pad=r.t_rows, cols_pad=r.t_cols, shuffle=r.shuffle, count=n_t))
+            n_acc = r.acc_rows * r.acc_taps * r.acc_cols
+            r.acc = self.acc_arena[r._acc_off:r._acc_off + n_acc]
+            unpack.append(dict(src=r.acc, dst=self.grad_slice(r.weight), mode=r.fwd_mode, cout=r.cout, cin=r.cin, kh=r.k,
+                               kw=r.k, rows_pad=r.acc_rows, cols_pad=r.acc_cols, shuffle=r.shuffle, count=n_acc))
+            if r.shuffle and r.bias is not None:
+                r.bias_packed = torch.zeros(r.cout_pad, dtype=F32, device=self.device)
+                r.bias_grad_packed = torch.zeros(r.cout_pad, dtype=F32, device=self.device)
+                self.bias_perm.append(r)
+        for r in self.linears:
+            n = r.nout_pad * r.K
+            r.w_fwd = self.w_arena[r._fwd_off:r._fwd_off + n]
+            pack.append(dict(src=r.weight, dst=r.w_fwd, mode=L.PK_LINEAR, cout=r.nout, cin=r.C, kh=r.Hf, kw=r.Wf,
+                             rows_pad=r.nout_pad, cols_pad=r.K, shuffle=0, count=n))
+        self._pack_tab, self._pack_n, self._pack_blocks = ops.pack_table(pack, self.device)
+        self._unpack_tab, self._unpack_n, self._unpack_blocks = ops.pack_table(unpack, self.device)
+        self._pack_desc = ops.elt(L.E_PACK_W, p=[self._pack_tab], i=[self._pack_n, self._pack_blocks])
+        self.unpack_desc = ops.elt(L.E_UNPACK_G, p=[self._unpack_tab], i=[self._unpack_n, self._unpack_blocks])
+        self._watched = [r.weight for r in self.convs] + [r.weight for r in self.linears] + \
+                        [r.bias for r in self.bias_perm]
+
+    def grad_slice(self, p: torch.Tensor) -> torch.Tensor:
+        o = self.offsets[id(p)]
+        return self.flat_grad[o:o + p.numel()]
+
+    def ensure_packed(self):
+        """Re-packs the bf16 operand copies if any watched parameter changed since the last pack (one kernel)."""
+        ver = 0
+        for p in self._watched:
+            ver += p._version
+        if ver == self._version:
+            return
+        ops.run_now(self._pack_desc)
+        for r in self.bias_perm:   # PixelShuffle layers consume the bias in packed-column order
+            c4 = r.cout // 4
+            r.bias_packed.view(4, c4).copy_(r.bias.detach().view(c4, 4).t())
+        self._version = ver
+
+    def grads_from_flat(self, flat: torch.Tensor, want: List[bool]) -> List[Optional[torch.Tensor]]:
+        out = []
+        for p, w in zip(self.params, want):
+            if not w:
+                out.append(None)
+                continue
+            o = self.offsets[id(p)]
+            out.append(flat[o:o + p.numel()].view(p.shape))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ plan
+class Plan:
+    """One instance = the workspaces + recorded programs of one module call at one input shape and mode.
+    A net definition fills it through the emit_* helpers; backward is emitted by replaying the tape in reverse."""
+
+    def __init__(self, store: ParamStore, B: int, H: int, W: int, training: bool):
+        self.store, self.B, self.H, self.W, self.training = store, B, H, W, training
+        self.device = store.device
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.fwd = ops.Program()
+        self.tape: List[Callable] = []
+        self.bwd: Dict[tuple, ops.Program] = {}
+        self.busy = False
+        self.slots: Dict[str, Act] = {}     # side-channel gradients between tape entries (skip connections)
+        self.has_bn = False
+        self.post_backward: List[Callable] = []
+        self.input_fn = self.output_fn = self.ingest_fn = self.grad_input_fn = None
+        self.last_g: Dict[tuple, Optional[Act]] = {}
+
+    # ---- buffers
+    def buf(self, name: str, numel: int, dtype=BF16, zero: bool = False) -> torch.Tensor:
+        if name in self.bufs:
+            t = self.bufs[name]
+            assert t.numel() >= numel and t.dtype == dtype, name
+            return t
+        t = (torch.zeros if zero else torch.empty)(max(int(numel), 8), dtype=dtype, device=self.device)
+        self.bufs[name] = t
+        return t
+
+    def act(self, name: str, B, H, W, C, dtype=BF16, zero=False) -> Act:
+        return Act(self.buf(name, B * H * W * C, dtype, zero), B, H, W, C)
+
+    # ---- forward emitters
+    def conv(self, prog, x: Act, w: torch.Tensor, w_cols: int, n_slots: int, geom: dict, cout_pad: int, block_n: int,
+             out: torch.Tensor, out_strides, n_valid: int, **kw):
+        d = ops.conv_desc(x=ops.ptr(x.t, x.c0) if x.c0 else x.t, N=x.B, H=x.H, W=x.W, C=x.C, x_ld=x.ld, geom=geom, w=w,
+                          cout_pad=cout_pad, w_ld=w_cols, n_slots=n_slots, block_n=block_n, out=out,
+                          os_n=out_strides[0], os_h=out_strides[1], os_w=out_strides[2], n_valid=n_valid, **kw)
+        prog.add(d)
+        return d
+
+    def conv_fwd(self, prog, rec: ConvRec, x: Act, out: Act, *, stats=None, act=L.ACT_NONE, prelu=None, preact=None,
+                 res: Optional[Act] = None, out_f32=False, shuffle_out=False):
+        """Forward of a 'std' conv (any stride) into `out` (OUT_LINEAR or PixelShuffle store)."""
+        geom = ops.fwd_geometry(x.H, x.W, rec.k, rec.k, rec.pad, rec.pad, rec.stride)
+        bias = None
+        if rec.bias is not None:
+            bias = rec.bias_packed if rec.shuffle else rec.bias
+        kw = dict(bias=bias, act=act, prelu=prelu, out_preact=preact, out_f32=out_f32)
+        if stats is not None:
+            kw.update(stats_partial=stats, stats_ld=rec.cout_pad)
+        if res is not None:
+            kw.update(res=res.t, aux=res.strides())
+        if shuffle_out:
+            kw.update(out_mode=L.OUT_SHUFFLE, shuf_c=rec.cout // 4)
+        return self.conv(prog, x, rec.w_fwd, rec.cols, rec.slots, geom, rec.cout_pad, rec.block_n, out.t, out.strides(),
+                         rec.cout_pad, **kw)
+
+    def stats_buf(self, name: str, M: int, cout_pad: int) -> torch.Tensor:
+        return self.buf(name, ((M + 127) // 128) * cout_pad * 2, F32)
+
+    def bn_coef(self, prog, name: str, bn: nn.BatchNorm2d, stats: Optional[torch.Tensor], M: int, ld: int):
+        """Per-channel (scale, shift, mean, invstd): from the conv epilogue's batch statistics in training mode
+        (also updates running_mean / running_var / num_batches_tracked), from the running estimates in eval mode."""
+        C = bn.num_features
+        coef = self.buf(name, 4 * C, F32)
+        if self.training:
+            tiles = (M + 127) // 128
+            prog.add(ops.elt(L.E_BN_FINALIZE, p=[stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                 bn.num_batches_tracked, coef],
+                             i=[tiles, C, M, 1, ld], f=[bn.eps, bn.momentum]))
+        else:
+            prog.add(ops.elt(L.E_BN_EVAL_COEF, p=[None, bn.weight, bn.bias, bn.running_mean, bn.running_var, None, coef],
+                             i=[0, C], f=[bn.eps]))
+        return coef
+
+    def bn_act(self, prog, x: Act, coef, y: Act, act=L.ACT_NONE, alpha=None, res: Optional[Act] = None,
+               leaky=0.2, res_scale=1.0, x_scale=1.0):
+        prog.add(ops.elt(L.E_BN_ACT, p=[x.t, coef, y.t, res.t if res is not None else None, alpha],
+                         i=[x.M, x.C, x.ld, y.ld, res.ld if res is not None else 0, act, x.c0, y.c0,
+                            res.c0 if res is not None else 0],
+                         f=[leaky, res_scale, x_scale]))
+
+    # ---- backward emitters
+    def norm_act_bwd(self, prog, name: str, g: Act, x: Act, *, coef=None, bn: Optional[nn.BatchNorm2d] = None,
+                     act=L.ACT_NONE, alpha: Optional[torch.Tensor] = None, g2: Optional[Act] = None,
+                     bias_grad: Optional[torch.Tensor] = None, want_w=True, leaky=0.2) -> Act:
+        """Backward of y = act(BN(x)) (bn given) or y = act(x) (bn None) for upstream gradient g (+ g2):
+        column reduction -> finalize (dgamma/dbeta/dalpha or bias gradient) -> apply. Returns d/dx as a new Act."""
+        M, C = x.M, x.C
+        assert g.ld == C and x.ld == C and (g2 is None or g2.ld == C)
+        has_bn = 1 if bn is not None else 0
+        rpb = max(32, -(-M // (4 * NUM_SMS)))
+        blocks = -(-M // rpb)
+        dx = self.act(name + ".dx", x.B, x.H, x.W, C)
+        need_reduce = has_bn or (want_w and (alpha is not None or bias_grad is not None))
+        store = self.store
+        if need_reduce:
+            partial = self.buf(name + ".bpart", blocks * C * 2, F32)
+            dap = self.buf(name + ".dap", blocks, F32) if act == L.ACT_PRELU else None
+            prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, x.t, coef, alpha if act == L.ACT_PRELU else None, partial, dap,
+                                                   g2.t if g2 is not None else None],
+                             i=[M, C, act, rpb, C, C, has_bn], f=[leaky]))
+            bcoef = self.buf(name + ".bcoef", 3 * C, F32) if has_bn else None
+            dgamma = store.grad_slice(bn.weight) if has_bn and want_w else None
+            dbeta = store.grad_slice(bn.bias) if has_bn and want_w else (bias_grad if want_w else None)
+            dalpha = store.grad_slice(alpha) if (act == L.ACT_PRELU and want_w) else None
+            prog.add(ops.elt(L.E_BN_BWD_FINALIZE, p=[partial, dap, coef, bn.weight if has_bn else None, bcoef, dgamma,
+                                                     dbeta, dalpha],
+                             i=[blocks, C, M, blocks if dap is not None else 0, 0]))
+        else:
+            bcoef = None
+        prog.add(ops.elt(L.E_BN_BWD_APPLY, p=[g.t, x.t, coef, bcoef, alpha if act == L.ACT_PRELU else None, dx.t,
+                                              g2.t if g2 is not None else None],
+                         i=[M, C, act, C, C, C, has_bn], f=[leaky]))
+        return dx
+
+    def conv_dgrad(self, prog, name: str, rec: ConvRec, dy: Act, x_like: Act, *, res: Optional[Act] = None,
+                   out_f32: bool = False) -> Act:
+        """Gradient w.r.t. the input `x_like` of conv `rec` from dY, as an implicit-GEMM conv over dY with the
+        transposed weight pack. Fused epilogue: + res (residual branch gradient) and, when the producer of x_like
+        left a hook, * act'(pre-activation) with the PixelShuffle inverse folded into the store.
+        Returns the Act holding the result (the hook's un-shuffled target when one was used)."""
+        assert rec.need_dgrad
+        kw = {}
+        if res is not None:
+            kw.update(res=res.t, aux=res.strides(), aux_ch_off=res.c0)
+        hook = x_like.hook
+        if hook is not None:
+            assert res is None
+            z = hook["bwd_z"]
+            kw.update(bwd_z=z.t, bwd_act=hook["bwd_act"], prelu=hook.get("prelu"),
+                      dalpha_partial=hook.get("dalpha_partial"), aux=z.strides())
+        if rec.kind == "std":
+            n_out, n_slots = rec.t_rows, rec.k * rec.k
+            geom = ops.dgrad_s1_geometry(dy.H, dy.W, rec.k, rec.k, rec.pad, rec.pad)
+        elif rec.kind == "rown":
+            n_out, n_slots = rec.t_rows, rec.k
+            geom = ops.dgrad_s1_geometry(dy.H, dy.W, rec.k, 1, rec.pad, 0)
+        else:  # fullk: plain GEMM back to the im2row columns
+            n_out, n_slots = rec.t_rows, 1
+            geom = ops.fwd_geometry(dy.H, dy.W, 1, 1, 0, 0, 1)
+        block_n = next(b for b in (128, 96, 64, 160, 192, 32, 16) if n_out % b == 0 and b <= n_out)
+        dx = self.act(name + ".dgrad", x_like.B, x_like.H, x_like.W, n_out, F32 if out_f32 else BF16) \
+            if (hook is None or hook.get("unshuffle_to") is None) else None
+        if hook is not None and hook.get("unshuffle_to") is not None:
+            target = hook["unshuffle_to"]
+            kw.update(out_mode=L.OUT_UNSHUFFLE, shuf_c=n_out)
+        else:
+            target = dx
+        if rec.stride == 1:
+            self.conv(prog, dy, rec.w_t, rec.t_cols, n_slots, geom, n_out, block_n, target.t, target.strides(), n_out,
+                      out_ch_off=target.c0, out_f32=out_f32, **kw)
+        else:
+            assert rec.stride == 2 and rec.k == 3 and rec.pad == 1 and not kw and rec.kind == "std"
+            for d in ops.dgrad_s2_descs(dy=dy.t, N=dy.B, Hy=dy.H, Wy=dy.W, Cout=dy.C, dy_ld=dy.ld, wt=rec.w_t,
+                                        Cin=n_out, cin_pad=n_out, block_n=block_n, out=target.t, Hx=x_like.H,
+                                        Wx=x_like.W, out_ld=target.ld, n_valid=n_out):
+                prog.add(d)
+        return target
+
+    def colsum(self, prog, name: str, g: Act, out_vec: torch.Tensor):
+        """out_vec[c] = sum over rows of g[:, c] (bias gradients)."""
+        M, C = g.M, g.C
+        rpb = max(32, -(-M // (4 * NUM_SMS)))
+        blocks = -(-M // rpb)
+        partial = self.buf(name + ".cspart", blocks * C * 2, F32)
+        prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, g.t, None, None, partial, None, None],
+                         i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2]))
+        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[partial, out_vec], i=[blocks, C, C, 0, 0]))
+
+    def conv_wgrad(self, prog, rec: ConvRec, x: Act, dy: Act, geom: Optional[dict] = None, cout_valid=None):
+        geom = geom or ops.fwd_geometry(x.H, x.W, rec.k, rec.k, rec.pad, rec.pad, rec.stride)
+        block_n = dy.C if dy.C <= 128 else 128
+        d = ops.wgrad_desc(x=x.t, N=x.B, H=x.H, W=x.W, C=x.C + x.c0, x_ld=x.ld, geom=geom, dy=dy.t, dy_ld=dy.ld,
+                           dy_c=dy.C, out=rec.acc, cout_valid=cout_valid or rec.acc_rows, block_n=block_n, x_c0=x.c0,
+                           dy_c0=dy.c0)
+        prog.add(d)
+
+    # ---- execution (set by the net definition: input_fn, output_fn, ingest_fn, grad_input_fn, post_backward)
+    def run_forward(self, x: torch.Tensor) -> torch.Tensor:
+        self.input_fn(x)
+        self.fwd.run()
+        return self.output_fn()
+
+    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool):
+        if not self.training and self.has_bn:
+            raise NotImplementedError("torchsr_b200: backward through eval-mode BatchNorm is not implemented; call "
+                                      ".train() for gradient computation (the reference trainers do)")
+        seed = self.ingest_fn(gout)
+        prog = self.backward_program(want_x, want_w, seed)
+        prog.run()
+        gx = self.grad_input_fn() if want_x else None
+        flat = None
+        if want_w:
+            for fn in self.post_backward:
+                fn()
+            flat = self.store.flat_grad.clone()
+        return gx, flat
+
+    # ---- programs
+    def backward_program(self, want_x: bool, want_w: bool, seed: Act) -> "ops.Program":
+        key = (want_x, want_w)
+        if key not in self.bwd:
+            prog = ops.Program()
+            if want_w:
+                prog.add(ops.elt(L.E_ZERO, p=[self.store.acc_arena], i=[self.store.acc_arena.numel() * 4]))
+            g = seed
+            self.slots.clear()
+            for fn in reversed(self.tape):
+                g = fn(prog, g, want_x, want_w)
+            self.last_g[key] = g
+            if want_w:
+                prog.add(self.store.unpack_desc)
+            self.bwd[key] = prog
+        self.cur_g = self.last_g[key]
+        return self.bwd[key]
+
+
+class _Lease:
+    """Returns a plan to its pool when the autograd node that holds it dies (backward done or graph dropped)."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+
+    def release(self):
+        if self.plan is not None:
+            self.plan.busy = False
+            self.plan = None
+
+    def __del__(self):
+        self.release()
+
+
+# ------------------------------------------------------------------------------------------------ module base
+class B200Module(nn.Module):
+    """Base of the drop-in modules: owns the ParamStore and the plan pool, binds plans to autograd.
+
+    Subclasses create the same nn.Conv2d / nn.BatchNorm2d / nn.PReLU / nn.Linear children, in the same order and
+    under the same attribute names, as the reference classes (so default init consumes the RNG identically and
+    state_dict() keys/shapes match), and implement `_records()` and `_define(plan)`."""
+
+    def __init__(self):
+        super().__init__()
+        object.__setattr__(self, "_tsr", dict(store=None, plans={}))
+
+    # -- to be provided by subclasses
+    def _records(self):
+        raise NotImplementedError
+
+    def _define(self, plan: Plan, x_shape):
+        """Emit the forward program and the backward tape. Must set plan.run_input / plan.run_output callables and
+        plan.bwd_seed / plan.run_grad_input / plan.run_grad_output."""
+        raise NotImplementedError
+
+    # -- invalidation: .to()/.cuda()/.float() move or recreate parameter storage
+    def _apply(self, fn, *a, **kw):
+        r = super()._apply(fn, *a, **kw)
+        st = self.__dict__.get("_tsr")
+        if st is not None:
+            st["store"], st["plans"] = None, {}
+        return r
+
+    def _store(self) -> ParamStore:
+        st = self._tsr
+        p0 = next(self.parameters())
+        if st["store"] is None or st["store"].params[0].data_ptr() != p0.data_ptr() or st["store"].device != p0.device:
+            if p0.device.type != "cuda" and not ops.DRY:
+                raise L.TorchSRB200Error(
+                    f"{type(self).__name__} runs only on a CUDA sm_100 device (parameters are on '{p0.device}'); "
+                    "there is no CPU fallback for this path")
+            convs, linears = self._records()
+            st["store"] = ParamStore(self, convs, linears, p0.device)
+            st["plans"] = {}
+        return st["store"]
+
+    def _acquire(self, shape, training: bool) -> Plan:
+        store = self._store()
+        key = (tuple(shape), bool(training))
+        pool = self._tsr["plans"].setdefault(key, [])
+        for pl in pool:
+            if not pl.busy:
+                pl.busy = True
+                return pl
+        pl = Plan(store, shape[0], shape[2], shape[3], training)
+        self._define(pl, shape)
+        pl.busy = True
+        pool.append(pl)
+        return pl
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4:
+            raise RuntimeError(f"expected a 4-D NCHW tensor, got shape {tuple(x.shape)}")
+        store = self._store()
+        if x.device != store.device:
+            raise RuntimeError(f"input is on {x.device} but the module is on {store.device}")
+        x = x.contiguous()
+        if x.dtype != F32:
+            x = x.float()
+        needs_graph = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in store.params))
+        return _PlanFn.apply(self, needs_graph, x, *store.params)
+
+
+class _PlanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module: B200Module, needs_graph: bool, x: torch.Tensor, *params):
+        plan = module._acquire(x.shape, module.training)
+        store = plan.store
+        store.ensure_packed()
+        out = plan.run_forward(x)
+        if needs_graph:
+            ctx.lease = _Lease(plan)
+            ctx.module = module
+        else:
+            plan.busy = False
+        return out
+
+    @staticmethod
+    def backward(ctx, gout: torch.Tensor):
+        lease = ctx.lease
+        plan = lease.plan
+        if plan is None:
+            raise RuntimeError("torchsr_b200: backward through the same module call twice is not supported "
+                               "(activations live in a pooled workspace)")
+        want_x = ctx.needs_input_grad[2]
+        want = list(ctx.needs_input_grad[3:])
+        want_w = any(want)
+        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w)
+        grads = plan.store.grads_from_flat(flat, want) if want_w else [None] * len(want)
+        lease.release()
+        return (None, None, gx, *grads)

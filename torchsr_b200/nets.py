@@ -1,0 +1,359 @@
+"""Network definitions: how each reference module graph is laid out as native launch lists.
+
+Each ``define_*`` function fills a Plan (engine.py): it emits the forward program in the reference's layer order and
+pushes one backward closure per stage on the plan's tape. Reference graphs restated here:
+  SRGAN generator      torchsr/srgan/generator.py:33-81, residual.py:16-92
+  SRGAN discriminator  torchsr/srgan/discriminator.py:27-88
+  ESRGAN discriminator torchsr/esrgan/discriminator.py:27-95 (same stage structure, 10 convs, logits)
+"""
+from typing import Dict, List
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .engine import BF16, F32, Act, ConvRec, LinearRec, Plan, _round_up
+
+CHANSUM_SPLITS = 64
+
+
+def _recs(plan: Plan) -> Dict[str, ConvRec]:
+    return {r.name: r for r in plan.store.convs}
+
+
+def _geom1(H, W):
+    return ops.fwd_geometry(H, W, 1, 1, 0, 0, 1)
+
+
+# ------------------------------------------------------------------------------------------------ SRGAN generator
+def srgan_generator_records(m) -> List[ConvRec]:
+    recs = [ConvRec("conv1.0", m.conv1[0], "fullk", need_dgrad=False)]
+    for i, blk in enumerate(m.blocks):
+        recs.append(ConvRec(f"blocks.{i}.conv1", blk.conv1))
+        recs.append(ConvRec(f"blocks.{i}.conv2", blk.conv2))
+    recs.append(ConvRec("conv2.0", m.conv2[0]))
+    for j, layer in enumerate(m.conv_layers):
+        recs.append(ConvRec(f"conv_layers.{j}.conv", layer.conv, shuffle=True))
+    recs.append(ConvRec("conv3", m.conv3, "rown"))
+    return recs
+
+
+def residual_block_stage(plan: Plan, prog, name: str, blk, ra: ConvRec, rb: ConvRec, x: Act) -> Act:
+    """conv-BN-PReLU-conv-BN + x (torchsr/srgan/residual.py:86-91)."""
+    B, H, W, C, M = x.B, x.H, x.W, x.C, x.M
+    tr = plan.training
+    plan.has_bn = True
+    raw1 = plan.act(name + ".raw1", B, H, W, C)
+    s1 = plan.stats_buf(name + ".s1", M, C) if tr else None
+    plan.conv_fwd(prog, ra, x, raw1, stats=s1)
+    coef1 = plan.bn_coef(prog, name + ".coef1", blk.bn1, s1, M, C)
+    a1 = plan.act(name + ".a1", B, H, W, C)
+    alpha = blk.prelu.weight
+    plan.bn_act(prog, raw1, coef1, a1, act=L.ACT_PRELU, alpha=alpha)
+    raw2 = plan.act(name + ".raw2", B, H, W, C)
+    s2 = plan.stats_buf(name + ".s2", M, C) if tr else None
+    plan.conv_fwd(prog, rb, a1, raw2, stats=s2)
+    coef2 = plan.bn_coef(prog, name + ".coef2", blk.bn2, s2, M, C)
+    y = plan.act(name + ".y", B, H, W, C)
+    plan.bn_act(prog, raw2, coef2, y, act=L.ACT_NONE, res=x)
+
+    def bwd(bp, g, want_x, want_w):
+        d2 = plan.norm_act_bwd(bp, name + ".bn2", g, raw2, coef=coef2, bn=blk.bn2, act=L.ACT_NONE, want_w=want_w)
+        if want_w:
+            plan.conv_wgrad(bp, rb, a1, d2)
+        da1 = plan.conv_dgrad(bp, name + ".c2", rb, d2, a1)
+        d1 = plan.norm_act_bwd(bp, name + ".bn1", da1, raw1, coef=coef1, bn=blk.bn1, act=L.ACT_PRELU, alpha=alpha,
+                               want_w=want_w)
+        if want_w:
+            plan.conv_wgrad(bp, ra, x, d1)
+        return plan.conv_dgrad(bp, name + ".c1", ra, d1, x, res=g)
+
+    plan.tape.append(bwd)
+    return y
+
+
+def subpixel_stage(plan: Plan, prog, name: str, layer, rec: ConvRec, x: Act, consumer_block_n: int = 64) -> Act:
+    """PReLU(PixelShuffle2(conv(x)+b)) with the shuffle folded into the conv store (residual.py:45-47)."""
+    B, H, W, C = x.B, x.H, x.W, rec.cout // 4
+    store = plan.store
+    out = plan.act(name + ".out", B, 2 * H, 2 * W, C)
+    pre = plan.act(name + ".pre", B, 2 * H, 2 * W, C)
+    alpha = layer.prelu.weight
+    plan.conv_fwd(prog, rec, x, out, act=L.ACT_PRELU, prelu=alpha, preact=pre.t, shuffle_out=True)
+    dconv = plan.act(name + ".dconv", B, H, W, rec.cout)
+    n_dap = (out.M + 127) // 128
+    dap = plan.buf(name + ".dap", n_dap, F32)
+    out.hook = dict(bwd_z=pre, bwd_act=L.ACT_PRELU, prelu=alpha, unshuffle_to=dconv, dalpha_partial=dap)
+
+    def bwd(bp, g, want_x, want_w):
+        assert g is dconv, "the consumer of a sub-pixel stage must honour its gradient hook"
+        if want_w:
+            bp.add(ops.elt(L.E_SUM_FINALIZE, p=[dap, store.grad_slice(alpha)], i=[n_dap, 0], f=[1.0]))
+            plan.colsum(bp, name + ".db", g, rec.bias_grad_packed)
+            plan.conv_wgrad(bp, rec, x, g)
+        return plan.conv_dgrad(bp, name, rec, g, x)
+
+    def unpermute_bias_grad():
+        c4 = rec.cout // 4
+        store.grad_slice(rec.bias).view(c4, 4).copy_(rec.bias_grad_packed.view(4, c4).t())
+
+    plan.tape.append(bwd)
+    plan.post_backward.append(unpermute_bias_grad)
+    return out
+
+
+def define_srgan_generator(m, plan: Plan, shape):
+    B, cin, H, W = shape
+    if cin != 3:
+        raise RuntimeError(f"Generator expects 3 input channels, got {cin}")
+    R = _recs(plan)
+    store, fwd = plan.store, plan.fwd
+    r1 = R["conv1.0"]
+    alpha1 = m.conv1[1].weight
+    E1 = plan.act("E1", B, H, W, r1.epad)
+    c1 = plan.act("c1", B, H, W, 64)
+    c1_pre = plan.act("c1.pre", B, H, W, 64)
+    g1 = _geom1(H, W)
+    plan.conv(fwd, E1, r1.w_fwd, r1.cols, 1, g1, r1.cout_pad, r1.block_n, c1.t, c1.strides(), r1.cout_pad, bias=r1.bias,
+              act=L.ACT_PRELU, prelu=alpha1, out_preact=c1_pre.t)
+
+    def bwd_conv1(bp, g, want_x, want_w):
+        if want_w:
+            d = plan.norm_act_bwd(bp, "c1", g, c1_pre, act=L.ACT_PRELU, alpha=alpha1, g2=plan.slots["skip"],
+                                  bias_grad=store.grad_slice(r1.bias), want_w=True)
+            plan.conv_wgrad(bp, r1, E1, d, geom=g1)
+        return None
+
+    plan.tape.append(bwd_conv1)
+
+    x = c1
+    for i, blk in enumerate(m.blocks):
+        x = residual_block_stage(plan, fwd, f"blocks.{i}", blk, R[f"blocks.{i}.conv1"], R[f"blocks.{i}.conv2"], x)
+
+    rc2, bn2 = R["conv2.0"], m.conv2[1]
+    plan.has_bn = True
+    xt = x
+    raw = plan.act("conv2.raw", B, H, W, 64)
+    st = plan.stats_buf("conv2.s", raw.M, 64) if plan.training else None
+    plan.conv_fwd(fwd, rc2, xt, raw, stats=st)
+    coef = plan.bn_coef(fwd, "conv2.coef", bn2, st, raw.M, 64)
+    s = plan.act("trunk", B, H, W, 64)
+    plan.bn_act(fwd, raw, coef, s, act=L.ACT_NONE, res=c1)
+
+    def bwd_conv2(bp, g, want_x, want_w):
+        plan.slots["skip"] = g          # out = conv1 + conv2 (generator.py:79): the same gradient reaches conv1
+        d = plan.norm_act_bwd(bp, "conv2.bn", g, raw, coef=coef, bn=bn2, act=L.ACT_NONE, want_w=want_w)
+        if want_w:
+            plan.conv_wgrad(bp, rc2, xt, d)
+        return plan.conv_dgrad(bp, "conv2", rc2, d, xt)
+
+    plan.tape.append(bwd_conv2)
+
+    u = s
+    for j, layer in enumerate(m.conv_layers):
+        u = subpixel_stage(plan, fwd, f"conv_layers.{j}", layer, R[f"conv_layers.{j}.conv"], u)
+
+    r3 = R["conv3"]
+    Hf, Wf = u.H, u.W
+    T = plan.act("T", B, Hf, Wf, r3.npad, F32)
+    geom3 = ops.fwd_geometry(Hf, Wf, r3.k, 1, r3.pad, 0, 1)
+    plan.conv(fwd, u, r3.w_fwd, r3.cols, r3.k, geom3, r3.npad, r3.npad, T.t, T.strides(), r3.npad, out_f32=True)
+    E3 = plan.act("E3", B, Hf, Wf, r3.npad)
+    cs = plan.buf("conv3.cs", CHANSUM_SPLITS * r3.cout * 2, F32)
+    u_last = u
+
+    def input_fn(x_nchw):
+        ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E1.t], i=[B, 3, H, W, r1.k, r1.k, r1.pad, r1.pad, 1, r1.epad]))
+
+    def output_fn():
+        out = torch.empty(B, r3.cout, Hf, Wf, dtype=F32, device=plan.device)
+        ops.run_now(ops.elt(L.E_GATHER_OUT, p=[T.t, out, r3.bias], i=[B, r3.cout, Hf, Wf, 1, r3.k, 0, r3.pad, 1, r3.npad, 0]))
+        return out
+
+    def ingest_fn(gout):
+        # dOut (NCHW fp32) -> row-expanded E3[n,h,w,kw*3+co] = dOut[n,co,h,w-(kw-4)], shared by conv3's dgrad and wgrad
+        ops.run_now(ops.elt(L.E_IM2ROW, p=[gout, E3.t], i=[B, r3.cout, Hf, Wf, 1, r3.k, 0, r3.pad, -1, r3.npad]))
+        ops.run_now(ops.elt(L.E_CHANSUM_NCHW, p=[gout, cs], i=[B, r3.cout, Hf * Wf, CHANSUM_SPLITS]))
+        return E3
+
+    def bwd_conv3(bp, g, want_x, want_w):
+        if want_w:
+            bp.add(ops.elt(L.E_COLSUM_FINALIZE, p=[cs, store.grad_slice(r3.bias)], i=[CHANSUM_SPLITS, r3.cout, r3.cout, 0, 0]))
+            plan.conv_wgrad(bp, r3, u_last, E3, geom=geom3, cout_valid=r3.k * r3.cout)
+        return plan.conv_dgrad(bp, "conv3", r3, E3, u_last)
+
+    plan.tape.append(bwd_conv3)
+
+    def grad_input_fn():
+        raise NotImplementedError("torchsr_b200: the gradient w.r.t. the generator's low-resolution input is not "
+                                  "implemented (the reference training loops never request it)")
+
+    plan.input_fn, plan.output_fn, plan.ingest_fn, plan.grad_input_fn = input_fn, output_fn, ingest_fn, grad_input_fn
+
+
+# ------------------------------------------------------------------------------------------------ standalone blocks
+class _IdentityRec:
+    """Looks like the transposed pack of a 1x1 identity conv: lets conv_dgrad run a block's gradient hook (activation
+    backward + PixelShuffle inverse) when no real consumer conv exists to fuse it into."""
+    kind, need_dgrad, stride, k, pad = "fullk", True, 1, 1, 0
+
+    def __init__(self, plan: Plan, C: int):
+        self.t_rows = self.t_cols = C
+        self.w_t = plan.buf("identity", C * C, BF16)
+        self.w_t.view(C, C).copy_(torch.eye(C, dtype=BF16, device=plan.device))
+
+
+def define_standalone(m, plan: Plan, shape, stage_fn):
+    """A building block called on its own (e.g. ResidualBlock()(x)): NCHW fp32 <-> NHWC bf16 conversion kernels at
+    both ends, the block's stage in between."""
+    B, C, H, W = shape
+    if C % 16:
+        raise RuntimeError(f"{type(m).__name__} needs a channel count that is a multiple of 16, got {C}")
+    xin = plan.act("in", B, H, W, C)
+    y = stage_fn(xin)
+    gy = plan.act("gy", y.B, y.H, y.W, y.C)
+    if y.hook is not None:
+        ident = _IdentityRec(plan, y.C)
+        plan.tape.append(lambda bp, g, want_x, want_w: plan.conv_dgrad(bp, "hook", ident, g, y))
+
+    def input_fn(x):
+        ops.run_now(ops.elt(L.E_NCHW2NHWC, p=[x, xin.t], i=[B, C, H, W, C, 0]))
+
+    def output_fn():
+        out = torch.empty(B, y.C, y.H, y.W, dtype=F32, device=plan.device)
+        ops.run_now(ops.elt(L.E_NHWC2NCHW, p=[y.t, out], i=[B, y.C, y.H, y.W, y.ld, y.c0, 0]))
+        return out
+
+    def ingest_fn(gout):
+        ops.run_now(ops.elt(L.E_NCHW2NHWC, p=[gout, gy.t], i=[B, y.C, y.H, y.W, y.C, 0]))
+        return gy
+
+    def grad_input_fn():
+        g = plan.cur_g
+        gx = torch.empty(B, C, H, W, dtype=F32, device=plan.device)
+        ops.run_now(ops.elt(L.E_NHWC2NCHW, p=[g.t, gx], i=[B, C, H, W, g.ld, g.c0, 0]))
+        return gx
+
+    plan.input_fn, plan.output_fn, plan.ingest_fn, plan.grad_input_fn = input_fn, output_fn, ingest_fn, grad_input_fn
+
+
+# ------------------------------------------------------------------------------------------------ discriminators
+def discriminator_records(m, conv_idx):
+    recs = [ConvRec("features.0", m.features[0], "fullk", need_dgrad=True)]
+    for k in conv_idx[1:]:
+        recs.append(ConvRec(f"features.{k}", m.features[k]))
+    return recs
+
+
+def discriminator_linears(m, image_size: int):
+    fm = image_size // (2 ** (sum(1 for c in m.features if isinstance(c, torch.nn.Conv2d) and c.stride[0] == 2)))
+    return [LinearRec("classifier.0", m.classifier[0], 512, fm, fm)]
+
+
+def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
+    """3x3 conv + LeakyReLU, then (conv, BN, LeakyReLU) stages with strides from the module, flatten, Linear,
+    LeakyReLU, Linear (+ Sigmoid for SRGAN)."""
+    B, cin, H, W = shape
+    if cin != 3 or H != m.image_size or W != m.image_size:
+        raise RuntimeError(f"Discriminator(image_size={m.image_size}) expects [N,3,{m.image_size},{m.image_size}] "
+                           f"inputs, got {tuple(shape)}")
+    R = _recs(plan)
+    store, fwd = plan.store, plan.fwd
+    r0 = R["features.0"]
+    E0 = plan.act("E0", B, H, W, r0.epad)
+    f0 = plan.act("f0", B, H, W, r0.cout)
+    g1 = _geom1(H, W)
+    plan.conv(fwd, E0, r0.w_fwd, r0.cols, 1, g1, r0.cout_pad, r0.block_n, f0.t, f0.strides(), r0.cout_pad, bias=r0.bias,
+              act=L.ACT_LEAKY)
+
+    def bwd_f0(bp, g, want_x, want_w):
+        if not (want_x or want_w):
+            return None
+        d = plan.norm_act_bwd(bp, "f0", g, f0, act=L.ACT_LEAKY, bias_grad=store.grad_slice(r0.bias), want_w=want_w)
+        if want_w:
+            plan.conv_wgrad(bp, r0, E0, d, geom=g1)
+        if want_x:
+            return plan.conv_dgrad(bp, "f0", r0, d, E0, out_f32=True)   # d/dE0, fp32 [M][epad]
+        return None
+
+    plan.tape.append(bwd_f0)
+
+    prev = f0
+    plan.has_bn = True
+    for k in conv_idx[1:]:
+        rk, bn = R[f"features.{k}"], m.features[k + 1]
+        Ho = (prev.H + 2 * rk.pad - rk.k) // rk.stride + 1
+        Wo = (prev.W + 2 * rk.pad - rk.k) // rk.stride + 1
+        raw = plan.act(f"f{k}.raw", B, Ho, Wo, rk.cout)
+        st = plan.stats_buf(f"f{k}.s", raw.M, rk.cout_pad) if plan.training else None
+        plan.conv_fwd(fwd, rk, prev, raw, stats=st)
+        coef = plan.bn_coef(fwd, f"f{k}.coef", bn, st, raw.M, rk.cout_pad)
+        a = plan.act(f"f{k}.act", B, Ho, Wo, rk.cout)
+        plan.bn_act(fwd, raw, coef, a, act=L.ACT_LEAKY)
+
+        def bwd(bp, g, want_x, want_w, rk=rk, bn=bn, raw=raw, coef=coef, xin=prev, k=k):
+            d = plan.norm_act_bwd(bp, f"f{k}", g, raw, coef=coef, bn=bn, act=L.ACT_LEAKY, want_w=want_w)
+            if want_w:
+                plan.conv_wgrad(bp, rk, xin, d)
+            return plan.conv_dgrad(bp, f"f{k}", rk, d, xin)
+
+        plan.tape.append(bwd)
+        prev = a
+
+    l1 = plan.store.linears[0]
+    lin2 = m.classifier[2]
+    N1, K = l1.nout, l1.K
+    assert prev.M // B * prev.C == K
+    Bpad = _round_up(B, 16)
+    pre1t = plan.buf("pre1t", l1.nout_pad * B, F32)
+    fwd.add(ops.elt(L.E_ZERO, p=[pre1t], i=[l1.nout_pad * B * 4]))
+    tiles_n = l1.nout_pad // 128
+    k_iters = K // 64
+    splits = max(1, min(k_iters, (2 * 148) // tiles_n))
+    fwd.add(ops.gemm_desc(a=prev.t, M=B, K=K, a_ld=K, w=l1.w_fwd, n_rows=l1.nout_pad, block_n=128, out=pre1t, out_ld=B,
+                          n_valid=l1.nout_pad, splits=splits, atomic_t=True))
+    out_b = plan.buf("out", B, F32)
+    h1 = plan.buf("h1", B * N1, F32)
+    fwd.add(ops.elt(L.E_HEAD, p=[pre1t, l1.bias, lin2.weight, lin2.bias, out_b, h1], i=[B, N1, int(sigmoid)], f=[0.2]))
+    gbuf = plan.buf("gout", B, F32)
+    flat_act = prev
+
+    def bwd_head(bp, g, want_x, want_w):
+        dpre1 = plan.buf("dpre1", B * N1, F32)
+        dpre1_bf = plan.buf("dpre1_bf", Bpad * l1.nout_pad, BF16, zero=True)
+        dw2 = store.grad_slice(lin2.weight) if want_w else plan.buf("dw2.scratch", N1, F32)
+        db2 = store.grad_slice(lin2.bias) if want_w else plan.buf("db2.scratch", 4, F32)
+        bp.add(ops.elt(L.E_HEAD_BWD, p=[gbuf, out_b, h1, lin2.weight, dpre1, dpre1_bf, dw2, db2],
+                       i=[B, N1, int(sigmoid), l1.nout_pad], f=[0.2]))
+        if want_w:
+            bp.add(ops.elt(L.E_LINEAR_WGRAD, p=[dpre1, flat_act.t, store.grad_slice(l1.weight), store.grad_slice(l1.bias)],
+                           i=[B, N1, K, l1.C, l1.Hf * l1.Wf]))
+        dflat32 = plan.buf("dflat32", Bpad * K, F32)
+        bp.add(ops.elt(L.E_ZERO, p=[dflat32], i=[Bpad * K * 4]))
+        bn_ = next(b for b in (128, 64, 32, 16) if Bpad % b == 0)
+        # dX^T[(h,w,c)][b] = sum_n Wp[n][(h,w,c)] * dpre1[b][n]: the packed weight is the MN-major A operand as stored
+        bp.add(ops.gemm_desc(a=l1.w_fwd, M=K, K=l1.nout_pad, a_ld=K, a_mn_major=True, w=dpre1_bf, n_rows=Bpad,
+                             block_n=bn_, out=dflat32, out_ld=K, n_valid=Bpad, atomic_t=True))
+        dflat = plan.act("dflat", B, flat_act.H, flat_act.W, flat_act.C)
+        bp.add(ops.elt(L.E_CAST, p=[dflat32, dflat.t], i=[B * K, 0]))
+        return dflat
+
+    plan.tape.append(bwd_head)
+
+    def input_fn(x_nchw):
+        ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E0.t], i=[B, 3, H, W, r0.k, r0.k, r0.pad, r0.pad, 1, r0.epad]))
+
+    def output_fn():
+        return out_b[:B].clone().view(B, 1)
+
+    def ingest_fn(gout):
+        gbuf[:B].copy_(gout.reshape(-1))
+        return None
+
+    def grad_input_fn():
+        dE0 = plan.cur_g
+        gx = torch.empty(B, 3, H, W, dtype=F32, device=plan.device)
+        ops.run_now(ops.elt(L.E_GATHER_OUT, p=[dE0.t, gx, None], i=[B, 3, H, W, r0.k, r0.k, r0.pad, r0.pad, -1, dE0.ld, 0]))
+        return gx
+
+    plan.input_fn, plan.output_fn, plan.ingest_fn, plan.grad_input_fn = input_fn, output_fn, ingest_fn, grad_input_fn

@@ -2,10 +2,18 @@
 tsr_elt_desc_t and records them into native programs. Pure host logic (no GPU needed to build descriptors
 until they are handed to the library)."""
 import ctypes as C
+import os
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 from . import _lib as L
 from ._lib import ConvDesc, EltDesc, PackEntry, WgradDesc
+
+
+DRY = bool(int(os.environ.get("TSR_DRY", "0")))   # build and validate descriptors without a GPU (host-logic tests)
+
+# Address ranges of every tensor handed to a descriptor: the extent checks below refuse a descriptor whose kernel
+# would touch memory outside the tensor it points into (an out-of-bounds access is a device fault, not an exception).
+_RANGES: dict = {}
 
 
 def ptr(t, offset_elems: int = 0) -> int:
@@ -14,11 +22,47 @@ def ptr(t, offset_elems: int = 0) -> int:
         return 0
     if isinstance(t, int):
         return t
-    return t.data_ptr() + offset_elems * t.element_size()
+    base = t.data_ptr()
+    try:
+        nbytes = t.untyped_storage().nbytes() - t.storage_offset() * t.element_size()
+    except Exception:  # noqa: BLE001
+        nbytes = t.numel() * t.element_size()
+    if nbytes > _RANGES.get(base, 0):
+        _RANGES[base] = nbytes
+    return base + offset_elems * t.element_size()
+
+
+class ExtentError(ValueError):
+    pass
+
+
+def _room(addr: int) -> int:
+    """Bytes available from `addr` to the end of the registered tensor containing it (-1 if unknown)."""
+    best = -1
+    for base, n in _RANGES.items():
+        if base <= addr < base + n:
+            best = max(best, base + n - addr)
+    return best
+
+
+def _need(what: str, addr: int, nbytes: int):
+    if addr == 0 or nbytes <= 0:
+        return
+    room = _room(addr)
+    if room < 0:
+        raise ExtentError(f"{what}: address {addr:#x} is not inside any tensor known to torchsr_b200.ops")
+    if nbytes > room:
+        raise ExtentError(f"{what}: kernel would touch {nbytes} bytes but only {room} remain in the tensor")
+
+
+def forget_ranges():
+    _RANGES.clear()
 
 
 def current_stream() -> int:
     import torch
+    if DRY:
+        return 0
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -177,15 +221,163 @@ def elt(kind: int, p: Iterable = (), i: Iterable = (), f: Iterable = ()) -> EltD
     return d
 
 
+# --------------------------------------------------------------------------------------------- extent checks
+def validate_conv(d: ConvDesc):
+    esz = 4 if d.out_f32 else 2
+    if d.a_mode == 0:
+        M = d.N * d.Ho * d.Wo
+        _need("conv x", d.x, ((d.N * d.H * d.W - 1) * d.x_ld + d.C) * 2)
+        last = (d.N - 1) * d.os_n + (d.Ho - 1) * d.os_h + (d.Wo - 1) * d.os_w
+        aux_last = (d.N - 1) * d.aux_n + (d.Ho - 1) * d.aux_h + (d.Wo - 1) * d.aux_w
+        if d.out_mode == L.OUT_SHUFFLE:
+            last = (d.N - 1) * d.os_n + (2 * d.Ho - 1) * d.os_h + (2 * d.Wo - 1) * d.os_w
+            span = d.shuf_c
+        elif d.out_mode == L.OUT_UNSHUFFLE:
+            last = (d.N - 1) * d.os_n + ((d.Ho - 1) // 2) * d.os_h + ((d.Wo - 1) // 2) * d.os_w + 3 * d.shuf_c
+            span = d.n_valid
+        else:
+            span = d.n_valid
+        _need("conv out", d.out, (last + d.out_ch_off + span) * esz)
+        if d.out_preact:
+            _need("conv out_preact", d.out_preact, (last + d.out_ch_off + span) * 2)
+        for name, p in (("res", d.res), ("bwd_z", d.bwd_z)):
+            if p:
+                _need("conv " + name, p, (aux_last + d.aux_ch_off + d.n_valid) * 2)
+    else:
+        M = d.gemm_M
+        rows, cols = (d.gemm_M, d.gemm_K) if d.a_mode == 1 else (d.gemm_K, d.gemm_M)
+        _need("gemm a", d.x, ((rows - 1) * d.x_ld + cols) * 2)
+        if d.out_mode == L.OUT_GEMM_T_ATOMIC:
+            _need("gemm out^T", d.out, ((d.n_valid - 1) * d.os_n + M) * 4)
+        else:
+            _need("gemm out", d.out, ((M - 1) * d.os_w + d.out_ch_off + d.n_valid) * esz)
+    _need("conv w", d.w, d.w_rows * d.w_ld * 2)
+    if d.bias:
+        _need("conv bias", d.bias, d.cout_pad * 4)
+    tiles_m = (M + 127) // 128
+    if d.stats_partial:
+        if d.stats_ld < d.cout_pad:
+            raise ExtentError("conv stats_ld smaller than cout_pad")
+        _need("conv stats_partial", d.stats_partial, tiles_m * d.stats_ld * 2 * 4)
+    if d.dalpha_partial:
+        _need("conv dalpha_partial", d.dalpha_partial, tiles_m * (d.cout_pad // d.block_n) * 4)
+    if d.n_valid % 16 or d.n_valid > d.cout_pad:
+        raise ExtentError("conv n_valid must be a multiple of 16 and <= cout_pad")
+    for off in (d.out_ch_off, d.aux_ch_off):
+        if off % 8:
+            raise ExtentError("channel offsets must be multiples of 8 (16-byte vector accesses)")
+    if d.out_mode != L.OUT_GEMM_T_ATOMIC:
+        q = 4 if d.out_f32 else 8
+        for st in ((d.os_n, d.os_h, d.os_w) if d.a_mode == 0 else (d.os_w,)):
+            if st % q:
+                raise ExtentError("output strides must keep 16-byte alignment")
+        if d.res or d.bwd_z:
+            for st in ((d.aux_n, d.aux_h, d.aux_w) if d.a_mode == 0 else (d.aux_w,)):
+                if st % 8:
+                    raise ExtentError("aux strides must keep 16-byte alignment")
+
+
+def validate_wgrad(d: WgradDesc):
+    M = d.N * d.Ho * d.Wo
+    _need("wgrad x", d.x, ((d.N * d.H * d.W - 1) * d.x_ld + d.C) * 2)
+    _need("wgrad dy", d.dy, ((M - 1) * d.dy_ld + d.dy_c0 + d.dy_c) * 2)
+    _need("wgrad out", d.out, d.cout_valid * d.num_taps * (d.C - d.x_c0) * 4)
+    if d.cout_valid > d.dy_c:
+        raise ExtentError("wgrad cout_valid exceeds the dY channels visible")
+
+
+def _elt_extents(d: EltDesc):
+    """(pointer index, bytes) pairs the kernel of this kind touches; conservative for the kinds used by the plans."""
+    i, k = d.i, d.kind
+    if k == L.E_IM2ROW:
+        return [(0, i[0] * i[1] * i[2] * i[3] * 4), (1, i[0] * i[2] * i[3] * i[9] * 2)]
+    if k == L.E_GATHER_OUT:
+        return [(0, i[0] * i[2] * i[3] * i[9] * (2 if i[10] else 4)), (1, i[0] * i[1] * i[2] * i[3] * 4), (2, i[1] * 4)]
+    if k == L.E_NCHW2NHWC:
+        return [(0, i[0] * i[1] * i[2] * i[3] * 4), (1, ((i[0] * i[2] * i[3] - 1) * i[4] + i[5] + i[1]) * 2)]
+    if k == L.E_NHWC2NCHW:
+        return [(0, ((i[0] * i[2] * i[3] - 1) * i[4] + i[5] + i[1]) * 2), (1, i[0] * i[1] * i[2] * i[3] * 4)]
+    if k == L.E_BN_FINALIZE:
+        C = i[1]
+        return [(0, i[0] * i[4] * 8), (1, C * 4), (2, C * 4), (3, C * 4), (4, C * 4), (5, 8), (6, 4 * C * 4)]
+    if k == L.E_BN_EVAL_COEF:
+        C = i[1]
+        return [(1, C * 4), (2, C * 4), (3, C * 4), (4, C * 4), (6, 4 * C * 4)]
+    if k == L.E_BN_ACT:
+        M, C = i[0], i[1]
+        return [(0, ((M - 1) * i[2] + i[6] + C) * 2), (1, 2 * C * 4), (2, ((M - 1) * i[3] + i[7] + C) * 2),
+                (3, ((M - 1) * i[4] + i[8] + C) * 2), (4, 4)]
+    if k == L.E_BN_BWD_REDUCE:
+        M, C = i[0], i[1]
+        blocks = (M + i[3] - 1) // i[3]
+        return [(0, ((M - 1) * i[4] + C) * 2), (1, ((M - 1) * i[5] + C) * 2), (2, 4 * C * 4 if i[6] else 0), (3, 4),
+                (4, blocks * C * 8), (5, blocks * 4), (6, ((M - 1) * i[4] + C) * 2)]
+    if k == L.E_BN_BWD_FINALIZE:
+        C = i[1]
+        return [(0, i[0] * C * 8), (1, i[3] * 4), (2, 4 * C * 4), (3, C * 4), (4, 3 * C * 4), (5, C * 4), (6, C * 4), (7, 4)]
+    if k == L.E_BN_BWD_APPLY:
+        M, C = i[0], i[1]
+        return [(0, ((M - 1) * i[3] + C) * 2), (1, ((M - 1) * i[4] + C) * 2), (2, 4 * C * 4 if i[6] else 0),
+                (3, 3 * C * 4 if i[6] else 0), (4, 4), (5, ((M - 1) * i[5] + C) * 2), (6, ((M - 1) * i[3] + C) * 2)]
+    if k == L.E_COLSUM_FINALIZE:
+        return [(0, i[0] * i[2] * 8), (1, i[1] * 4)]
+    if k == L.E_SUM_FINALIZE:
+        return [(0, i[0] * 4), (1, 4)]
+    if k == L.E_LINEAR_WGRAD:
+        return [(0, i[0] * i[1] * 4), (1, i[0] * i[2] * 2), (2, i[1] * i[2] * 4), (3, i[1] * 4)]
+    if k == L.E_LOSS:
+        return [(0, i[0] * 4), (1, i[0] * 4), (2, i[2] * 4), (3, i[0] * 4)]
+    if k == L.E_ZERO:
+        return [(0, i[0])]
+    if k == L.E_UPSAMPLE2X:
+        return [(0, ((i[0] * i[1] * i[2] - 1) * i[4] + i[3]) * 2), (1, ((4 * i[0] * i[1] * i[2] - 1) * i[5] + i[3]) * 2)]
+    if k == L.E_UPSAMPLE2X_BWD:
+        return [(0, ((4 * i[0] * i[1] * i[2] - 1) * i[4] + i[3]) * 2), (1, ((i[0] * i[1] * i[2] - 1) * i[5] + i[3]) * 2)]
+    if k == L.E_HEAD:
+        B, N1 = i[0], i[1]
+        return [(0, N1 * B * 4), (1, N1 * 4), (2, N1 * 4), (3, 4), (4, B * 4), (5, B * N1 * 4)]
+    if k == L.E_HEAD_BWD:
+        B, N1 = i[0], i[1]
+        ld = i[3] if i[3] > 0 else N1
+        return [(0, B * 4), (1, B * 4), (2, B * N1 * 4), (3, N1 * 4), (4, B * N1 * 4), (5, ((B - 1) * ld + N1) * 2),
+                (6, N1 * 4), (7, 4)]
+    if k == L.E_AXPBY:
+        return [(0, i[0] * 2), (1, i[0] * 2), (2, i[0] * 2)]
+    if k == L.E_CAST:
+        return [(0, i[0] * (4 if i[1] == 0 else 2)), (1, i[0] * (2 if i[1] == 0 else 4))]
+    if k == L.E_CHANSUM_NCHW:
+        return [(0, i[0] * i[1] * i[2] * 4), (1, i[3] * i[1] * 8)]
+    return []
+
+
+def validate_elt(d: EltDesc):
+    for idx, nbytes in _elt_extents(d):
+        if d.p[idx]:
+            _need(f"elt kind {d.kind} p[{idx}]", d.p[idx], int(nbytes))
+
+
+def validate(d):
+    if isinstance(d, ConvDesc):
+        validate_conv(d)
+    elif isinstance(d, WgradDesc):
+        validate_wgrad(d)
+    else:
+        validate_elt(d)
+
+
 # --------------------------------------------------------------------------------------------- programs
 class Program:
     """A recorded launch list owned by the native library (tsr_prog_t)."""
 
     def __init__(self):
-        self._lib = L.load()
-        self._h = self._lib.tsr_prog_create()
         self.keep: List = []  # tensors referenced by raw pointer
         self.marks = {}
+        self.descs: List = []  # kept for introspection (tests, launch accounting)
+        if DRY:
+            self._lib, self._h = None, None
+            return
+        self._lib = L.load()
+        self._h = self._lib.tsr_prog_create()
 
     def __del__(self):
         try:
@@ -196,6 +388,10 @@ class Program:
             pass
 
     def add(self, d) -> int:
+        validate(d)
+        self.descs.append(d)
+        if DRY:
+            return len(self.descs) - 1
         if isinstance(d, ConvDesc):
             r = self._lib.tsr_prog_add_conv(self._h, C.byref(d))
         elif isinstance(d, WgradDesc):
@@ -210,14 +406,19 @@ class Program:
         self.marks[name] = len(self)
 
     def __len__(self) -> int:
-        return int(self._lib.tsr_prog_size(self._h))
+        return len(self.descs)
 
     def run(self, first: int = 0, count: int = -1, stream: Optional[int] = None):
+        if DRY:
+            return
         L.check(self._lib.tsr_prog_run(self._h, first, count, stream if stream is not None else current_stream()))
 
 
 def run_now(d, stream: Optional[int] = None):
     """Immediate-mode launch of a single descriptor."""
+    validate(d)
+    if DRY:
+        return
     lib = L.load()
     st = stream if stream is not None else current_stream()
     if isinstance(d, ConvDesc):
@@ -229,6 +430,8 @@ def run_now(d, stream: Optional[int] = None):
 
 
 def check_watchdog():
+    if DRY:
+        return
     lib = L.load()
     L.check(lib.tsr_check_watchdog(current_stream()))
 
