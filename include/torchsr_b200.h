@@ -74,18 +74,19 @@ typedef struct tsr_conv_desc {
   const float* prelu;
   const void* res;
   const void* bwd_z;
-  float* dalpha_partial;
-  float* stats_partial;
+  float* dalpha_partial;    /* one float accumulated atomically: PReLU slope gradient (pre-zeroed) */
+  float* stats_partial;     /* [stats_ld][2] column sum / sum of squares, accumulated atomically (pre-zeroed) */
   int64_t os_n, os_h, os_w;
   int64_t aux_n, aux_h, aux_w;
   int32_t out_mode, out_f32, out_ch_off, aux_ch_off, n_valid, act, bwd_act, stats_ld, shuf_c;
   float acc_scale, leaky_slope;
+  int64_t* trace;           /* optional debug: per-CTA clock64 stamps [grid][40] (null in production) */
 } tsr_conv_desc_t;
 
 typedef struct tsr_wgrad_desc {
   const void* x;   /* layer input, NHWC bf16 */
   const void* dy;  /* output gradient, [pixels][dy_ld] bf16 */
-  float* out;      /* fp32 [cout_valid][num_taps][cin_pad], pre-zeroed, accumulated atomically */
+  float* out;      /* fp32 [num_taps][cin_pad][cout_valid], pre-zeroed, accumulated with vector reductions */
   int64_t N, H, W, C, x_ld;
   int64_t Ho, Wo;
   int64_t dy_ld, dy_c;     /* dY row stride and channel count visible */
@@ -94,7 +95,7 @@ typedef struct tsr_wgrad_desc {
   int32_t chan_block;      /* 64 / 32 / 16 */
   int32_t dy_block;        /* 64 / 32 / 16 */
   int32_t block_n;
-  int32_t cout_valid;
+  int32_t cout_valid;      /* accumulator row width = padded output-channel count (multiple of 16) */
   int32_t x_c0, dy_c0;
   int32_t splits;          /* pixel splits (0 = auto) */
   uint16_t tap_off[TSR_MAX_TAPS];
@@ -104,9 +105,9 @@ typedef struct tsr_wgrad_desc {
 typedef struct tsr_elt_desc {
   int32_t kind;
   int32_t _pad;
-  void* p[8];
+  void* p[12];
   int64_t i[16];
-  float f[4];
+  float f[8];
 } tsr_elt_desc_t;
 
 enum tsr_elt_kind {

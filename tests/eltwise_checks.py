@@ -58,7 +58,8 @@ def check_gather_out(B=2, C=3, H=8, W=10, KW=9, seed=2):
 
 
 def check_bn_train(M=1000, C=64, act=L.ACT_PRELU, residual=True, seed=3):
-    """stats (torch-side partials) -> BN_FINALIZE -> BN_ACT, then the three backward kernels, against autograd."""
+    """column sums (as the conv epilogue leaves them) -> fused BN_ACT, then BN_BWD_REDUCE + BN_BWD_APPLY, against
+    autograd through F.batch_norm / prelu / leaky_relu."""
     g = torch.Generator().manual_seed(seed)
     x = bf16_round(torch.randn(M, C, generator=g) * 1.5 + 0.3)
     res = bf16_round(torch.randn(M, C, generator=g)) if residual else None
@@ -68,57 +69,76 @@ def check_bn_train(M=1000, C=64, act=L.ACT_PRELU, residual=True, seed=3):
     gout = bf16_round(torch.randn(M, C, generator=g))
     rm, rv = torch.zeros(C), torch.ones(C)
     # ---- device
-    tiles = 4
-    chunks = x.chunk(tiles, 0)
-    partial = torch.stack([torch.stack([c.sum(0), (c * c).sum(0)], -1) for c in chunks]).to(DEV)  # [tiles][C][2]
-    coef = torch.empty(4, C, device=DEV)
+    stats = torch.stack([x.sum(0), (x * x).sum(0)], -1).contiguous().to(DEV)     # [C][2]
+    coef = torch.full((4, C), float("nan"), device=DEV)
     rm_d, rv_d = rm.to(DEV), rv.to(DEV)
     nbt = torch.zeros((), dtype=torch.int64, device=DEV)
     gam_d, bet_d, alp_d = gamma.to(DEV), beta.to(DEV), alpha.to(DEV)
-    ops.run_now(ops.elt(L.E_BN_FINALIZE, p=[partial, gam_d, bet_d, rm_d, rv_d, nbt, coef], i=[tiles, C, M, 1, C],
-                        f=[1e-5, 0.1]))
     x_d = x.to(torch.bfloat16).to(DEV)
     res_d = res.to(torch.bfloat16).to(DEV) if residual else None
     y_d = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
-    ops.run_now(ops.elt(L.E_BN_ACT, p=[x_d, coef, y_d, res_d, alp_d], i=[M, C, C, C, C, act, 0, 0, 0],
-                        f=[0.2, 1.0, 1.0]))
+    ops.run_now(ops.elt(L.E_BN_ACT, p=[x_d, stats, y_d, res_d, alp_d, gam_d, bet_d, rm_d, rv_d, nbt, coef],
+                        i=[M, C, C, C, C, act, 0, 0, 0, 1, M], f=[0.2, 1.0, 1.0, 1e-5, 0.1]))
+    # eval-mode twin of the same layer (running statistics as just updated)
+    y_eval = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.run_now(ops.elt(L.E_BN_ACT, p=[x_d, None, y_eval, res_d, alp_d, gam_d, bet_d, rm_d, rv_d, None, None],
+                        i=[M, C, C, C, C, act, 0, 0, 0, 2, M], f=[0.2, 1.0, 1.0, 1e-5, 0.1]))
     # backward
     g_d = gout.to(torch.bfloat16).to(DEV)
-    rows_per_block = 128
-    blocks = (M + rows_per_block - 1) // rows_per_block
-    bpart = torch.full((blocks, C, 2), float("nan"), device=DEV)
-    dap = torch.full((blocks,), float("nan"), device=DEV)
-    ops.run_now(ops.elt(L.E_BN_BWD_REDUCE, p=[g_d, x_d, coef, alp_d, bpart, dap, None],
-                        i=[M, C, act, rows_per_block, C, C, 1], f=[0.2]))
-    bcoef = torch.empty(3, C, device=DEV)
+    sums = torch.zeros(C, 2, device=DEV)
+    dacc = torch.zeros(1, device=DEV)
+    ops.run_now(ops.elt(L.E_BN_BWD_REDUCE, p=[g_d, x_d, coef, alp_d, sums, dacc, None],
+                        i=[M, C, act, 128, C, C, 1], f=[0.2]))
     dgamma, dbeta, dalpha = torch.empty(C, device=DEV), torch.empty(C, device=DEV), torch.zeros(1, device=DEV)
-    ops.run_now(ops.elt(L.E_BN_BWD_FINALIZE, p=[bpart, dap, coef, gam_d, bcoef, dgamma, dbeta, dalpha],
-                        i=[blocks, C, M, blocks, 0]))
     dx_d = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
-    ops.run_now(ops.elt(L.E_BN_BWD_APPLY, p=[g_d, x_d, coef, bcoef, alp_d, dx_d, None], i=[M, C, act, C, C, C, 1],
-                        f=[0.2]))
+    ops.run_now(ops.elt(L.E_BN_BWD_APPLY, p=[g_d, x_d, coef, sums, alp_d, dx_d, None, gam_d, dgamma, dbeta, dalpha, dacc],
+                        i=[M, C, act, C, C, C, 1], f=[0.2]))
     sync_check()
     # ---- reference
     xr = x.clone().requires_grad_(True)
     gr, br, ar = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True), alpha.clone().requires_grad_(True)
     rm_r, rv_r = rm.clone(), rv.clone()
+
+    def act_fn(z):
+        if act == L.ACT_PRELU:
+            return F.prelu(z, ar)
+        if act == L.ACT_LEAKY:
+            return F.leaky_relu(z, 0.2)
+        return z
+
     z = F.batch_norm(xr, rm_r, rv_r, gr, br, training=True, momentum=0.1, eps=1e-5)
-    if act == L.ACT_PRELU:
-        a = F.prelu(z, ar)
-    elif act == L.ACT_LEAKY:
-        a = F.leaky_relu(z, 0.2)
-    else:
-        a = z
+    a = act_fn(z)
     y = a + res if residual else a
     y.backward(gout)
+    ye = act_fn(F.batch_norm(x, rm_r, rv_r, gamma, beta, training=False, eps=1e-5))
+    ye = ye + res if residual else ye
     r = {
-        "y": rel_l2(y_d.float(), y), "running_mean": rel_l2(rm_d, rm_r), "running_var": rel_l2(rv_d, rv_r),
-        "nbt": float(abs(int(nbt.item()) - 1)),
+        "y": rel_l2(y_d.float(), y), "y_eval": rel_l2(y_eval.float(), ye), "running_mean": rel_l2(rm_d, rm_r),
+        "running_var": rel_l2(rv_d, rv_r), "nbt": float(abs(int(nbt.item()) - 1)),
         "dx": rel_l2(dx_d.float(), xr.grad), "dgamma": rel_l2(dgamma, gr.grad), "dbeta": rel_l2(dbeta, br.grad),
     }
     if act == L.ACT_PRELU:
         r["dalpha"] = rel_l2(dalpha, ar.grad)
     return r
+
+
+def check_act_bwd_bias(M=700, C=64, seed=9):
+    """Activation-only backward (no BatchNorm): dx = g * leaky'(y), bias gradient = column sums of dx."""
+    g = torch.Generator().manual_seed(seed)
+    pre = torch.randn(M, C, generator=g)
+    yv = bf16_round(F.leaky_relu(pre, 0.2))
+    gout = bf16_round(torch.randn(M, C, generator=g))
+    y_d, g_d = yv.to(torch.bfloat16).to(DEV), gout.to(torch.bfloat16).to(DEV)
+    sums = torch.zeros(C, 2, device=DEV)
+    ops.run_now(ops.elt(L.E_BN_BWD_REDUCE, p=[g_d, y_d, None, None, sums, None, None], i=[M, C, L.ACT_LEAKY, 64, C, C, 0],
+                        f=[0.2]))
+    dx = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    db = torch.full((C,), float("nan"), device=DEV)
+    ops.run_now(ops.elt(L.E_BN_BWD_APPLY, p=[g_d, y_d, None, sums, None, dx, None, None, None, db, None, None],
+                        i=[M, C, L.ACT_LEAKY, C, C, C, 0], f=[0.2]))
+    sync_check()
+    ref = gout * torch.where(yv > 0, torch.ones_like(yv), torch.full_like(yv, 0.2))
+    return {"dx": rel_l2(dx.float(), ref), "dbias": rel_l2(db, ref.sum(0))}
 
 
 def check_pack_unpack(seed=4):
@@ -164,20 +184,20 @@ def check_pack_unpack(seed=4):
     r["rown_t"] = rel_l2(d_rownt.float().view(9, 64, 32), bf16_round(ref))
     ref = wl.view(24, 8, 6).permute(0, 2, 1).reshape(24, 48)        # (c,hw) -> (hw,c)
     r["linear"] = rel_l2(d_lin.float().view(24, 48), bf16_round(ref))
-    # unpack round trip: accumulator [rows][taps][cols_pad] fp32 -> OIHW
-    acc = torch.randn(64, 9, 32, generator=g)
+    # unpack round trip: accumulator [taps][cols_pad (ci)][rows_pad (co-like)] fp32 -> OIHW
+    acc = torch.randn(9, 32, 64, generator=g)
     dst = torch.full((64, 32, 3, 3), float("nan"), device=DEV)
     ent2 = [dict(src=acc.to(DEV), dst=dst, mode=L.PK_FWD, cout=64, cin=32, kh=3, kw=3, rows_pad=64, cols_pad=32,
                  shuffle=0, count=acc.numel())]
-    acc2 = torch.randn(32, 9, 64, generator=g)      # ROWN: rows = kw*3+co (27 valid), taps = kh, cols = ci
+    acc2 = torch.randn(9, 64, 32, generator=g)      # ROWN: [kh][ci][kw*3+co (27 valid)]
     dst2 = torch.full((3, 64, 9, 9), float("nan"), device=DEV)
     ent2.append(dict(src=acc2.to(DEV), dst=dst2, mode=L.PK_ROWN, cout=3, cin=64, kh=9, kw=9, rows_pad=32, cols_pad=64,
                      shuffle=0, count=acc2.numel()))
     tab2, n2, blocks2 = ops.pack_table(ent2, DEV)
     ops.run_now(ops.elt(L.E_UNPACK_G, p=[tab2], i=[n2, blocks2]))
     sync_check()
-    r["unpack_fwd"] = rel_l2(dst, acc.view(64, 3, 3, 32).permute(0, 3, 1, 2))
-    r["unpack_rown"] = rel_l2(dst2, acc2[:27].view(9, 3, 9, 64).permute(1, 3, 2, 0))  # [kw][co][kh][ci] -> [co][ci][kh][kw]
+    r["unpack_fwd"] = rel_l2(dst, acc.view(3, 3, 32, 64).permute(3, 2, 0, 1))
+    r["unpack_rown"] = rel_l2(dst2, acc2[:, :, :27].reshape(9, 64, 9, 3).permute(3, 1, 0, 2))  # [kh][ci][kw][co] -> OIHW
     return r
 
 
@@ -226,12 +246,10 @@ def check_linear_wgrad(B=16, Nf=40, C=16, HW=6, seed=7):
     g = torch.Generator().manual_seed(seed)
     K = C * HW
     dpre = torch.randn(B, Nf, generator=g)
-    x_hwc = bf16_round(torch.randn(B, HW, C, generator=g))        # device layout (h,w,c)
+    x_chw = torch.randn(B, K, generator=g)                        # already in the parameter's (c,h,w) order, fp32
     dW, db = torch.full((Nf, K), float("nan"), device=DEV), torch.empty(Nf, device=DEV)
-    ops.run_now(ops.elt(L.E_LINEAR_WGRAD, p=[dpre.to(DEV), x_hwc.to(torch.bfloat16).to(DEV).view(B, K), dW, db],
-                        i=[B, Nf, K, C, HW]))
+    ops.run_now(ops.elt(L.E_LINEAR_WGRAD, p=[dpre.to(DEV), x_chw.to(DEV), dW, db], i=[B, Nf, K]))
     sync_check()
-    x_chw = x_hwc.permute(0, 2, 1).reshape(B, K)                  # parameter order (c,h,w)
     return {"dW": rel_l2(dW, dpre.t() @ x_chw), "db": rel_l2(db, dpre.sum(0))}
 
 

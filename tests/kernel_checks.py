@@ -149,8 +149,7 @@ def check_conv_fwd(B=2, H=24, W=24, Cin=64, Cout=64, k=3, stride=1, block_n=None
         os_n, os_h, os_w = Ho * Wo * Cout, Wo * Cout, Cout
         bias_dev = b.to(DEV) if bias else None
     alpha_dev = alpha.to(DEV)
-    tiles_m = (B * Ho * Wo + 127) // 128
-    stats_buf = torch.full((tiles_m, Cout, 2), float("nan"), device=DEV) if stats else None
+    stats_buf = torch.zeros(Cout, 2, device=DEV) if stats else None   # accumulated with atomics by the epilogue
     d = ops.conv_desc(x=x_dev, N=B, H=H, W=W, C=Cin, x_ld=Cin, geom=geom, w=w_dev, cout_pad=Cout, w_ld=Cin,
                       n_slots=k * k, block_n=block_n, out=out, os_n=os_n, os_h=os_h, os_w=os_w, n_valid=Cout,
                       out_mode=L.OUT_SHUFFLE if shuffle else L.OUT_LINEAR, out_f32=out_f32, bias=bias_dev,
@@ -173,7 +172,7 @@ def check_conv_fwd(B=2, H=24, W=24, Cin=64, Cout=64, k=3, stride=1, block_n=None
     if r["out"] > 1e-2:
         print("   mismatch:", describe_mismatch(out.float(), ref.permute(0, 2, 3, 1)), flush=True)
     if stats:
-        tot = stats_buf.sum(0).cpu()
+        tot = stats_buf.cpu()
         r["sum"] = rel_l2(tot[:, 0], pre.sum((0, 2, 3)))
         r["sumsq"] = rel_l2(tot[:, 1], (pre * pre).sum((0, 2, 3)))
     return r
@@ -223,7 +222,7 @@ def check_wgrad(B=2, H=24, W=24, Cin=64, Cout=64, k=3, stride=1, seed=6, block_n
     x = bf16_round(torch.randn(B, Cin, H, W, generator=g))
     dy = bf16_round(torch.randn(B, Cout, Ho, Wo, generator=g))
     x_dev, dy_dev = nhwc_bf16(x), nhwc_bf16(dy)
-    acc = torch.zeros(Cout, k * k, Cin, device=DEV)
+    acc = torch.zeros(k * k, Cin, Cout, device=DEV)   # [tap][ci][co], accumulated with vector reductions
     d = ops.wgrad_desc(x=x_dev, N=B, H=H, W=W, C=Cin, x_ld=Cin, geom=geom, dy=dy_dev, dy_ld=Cout, dy_c=Cout, out=acc,
                        cout_valid=Cout, block_n=block_n or min(Cout, 128))
     ops.run_now(d)
@@ -231,5 +230,5 @@ def check_wgrad(B=2, H=24, W=24, Cin=64, Cout=64, k=3, stride=1, seed=6, block_n
     xr = x.clone().requires_grad_(False)
     wz = torch.zeros(Cout, Cin, k, k, requires_grad=True)
     F.conv2d(xr, wz, None, stride=stride, padding=pad).backward(dy)
-    ref = wz.grad.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin)
+    ref = wz.grad.permute(2, 3, 1, 0).reshape(k * k, Cin, Cout)
     return {"out": rel_l2(acc, ref)}

@@ -25,6 +25,7 @@ CHECKS = [
     ("bn_prelu_res", lambda: E.check_bn_train()),
     ("bn_leaky_c512", lambda: E.check_bn_train(M=600, C=512, act=L.ACT_LEAKY, residual=False)),
     ("bn_none", lambda: E.check_bn_train(M=333, C=64, act=L.ACT_NONE, residual=False)),
+    ("act_bwd_bias", lambda: E.check_act_bwd_bias()),
     ("pack_unpack", lambda: E.check_pack_unpack()),
     ("loss_mse", lambda: E.check_loss(kind=0)),
     ("loss_l1", lambda: E.check_loss(kind=1)),

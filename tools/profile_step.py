@@ -1,0 +1,54 @@
+"""GPU timeline of the training step with torch.profiler (CUPTI): per-kernel totals and busy fraction.
+Usage: python tools/profile_step.py [batch]"""
+import os
+import sys
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TORCHSR_VGG_WEIGHTS", "random")
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+from torchsr_b200.srgan.trainer import SRGANTrainer  # noqa: E402
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    novgg = len(sys.argv) > 2 and sys.argv[2] == "novgg"
+    torch.manual_seed(0)
+    targs = Namespace(disable_amp=False, batch_size=B, epochs=8, pretrain_epochs=1, gan_checkpoint=None,
+                      psnr_checkpoint=None, skip_image_save=True, local_rank=0, rank=-1, world_size=1)
+    tr = SRGANTrainer(torch.device("cuda"), targs, [], [], 0, 0, False)
+    if novgg:
+        tr.vgg_loss = lambda a, b: torch.nn.functional.mse_loss(a, b)
+    lr, hr = torch.rand(B, 3, 24, 24, device="cuda"), torch.rand(B, 3, 96, 96, device="cuda")
+    for s in range(5):
+        tr._gan_loop(lr, hr, s)
+    torch.cuda.synchronize()
+    steps = 3
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        for s in range(steps):
+            tr._gan_loop(lr, hr, s)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    agg = {}
+    t0, t1, busy = None, None, 0.0
+    for e in evs:
+        name = e.name[:70]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += e.device_time
+        s_, e_ = e.time_range.start, e.time_range.end
+        t0 = s_ if t0 is None else min(t0, s_)
+        t1 = e_ if t1 is None else max(t1, e_)
+        busy += e.device_time
+    span = (t1 - t0)
+    print(f"batch {B}: {steps} steps, GPU span {span / steps / 1e3:.3f} ms/step, kernel-busy {busy / steps / 1e3:.3f} ms/step, "
+          f"{len(evs) / steps:.0f} GPU activities/step")
+    for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+        print(f"{t / steps:9.1f} us/step {n / steps:6.1f} x {t / n:8.2f} us  {name}")
+
+
+if __name__ == "__main__":
+    main()

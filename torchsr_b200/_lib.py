@@ -40,6 +40,7 @@ class ConvDesc(C.Structure):
         ("n_valid", C.c_int32), ("act", C.c_int32), ("bwd_act", C.c_int32), ("stats_ld", C.c_int32),
         ("shuf_c", C.c_int32),
         ("acc_scale", C.c_float), ("leaky_slope", C.c_float),
+        ("trace", C.c_void_p),
     ]
 
 
@@ -57,8 +58,8 @@ class WgradDesc(C.Structure):
 
 
 class EltDesc(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("p", C.c_void_p * 8), ("i", C.c_int64 * 16),
-                ("f", C.c_float * 4)]
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("p", C.c_void_p * 12), ("i", C.c_int64 * 16),
+                ("f", C.c_float * 8)]
 
 
 class PackEntry(C.Structure):

@@ -6,7 +6,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -194,6 +196,14 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   if (static_cast<size_t>(stages) * stage_bytes > 200 * 1024) return fail(-22, "tile does not fit shared memory");
   if (stages > p.iters_per_split) stages = p.iters_per_split < 1 ? 1 : p.iters_per_split;
   p.stages = stages;
+  p.a_bytes = kBlockM * d.block_k * 2;
+  p.b_bytes = static_cast<uint32_t>(d.block_n) * d.block_k * 2;
+  p.stage_bytes = stage_bytes;
+  p.ksteps = d.block_k / 16;
+  p.sbo_bytes = 8 * d.block_k * 2;
+  p.layout_type = d.block_k == 64 ? 2u : (d.block_k == 32 ? 4u : 6u);
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((d.a_mode == 2 ? 1u : 0u) << 15) |
+            (static_cast<uint32_t>(d.block_n >> 3) << 17) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
   EpiParams& e = p.epi;
   e.out = d.out;
   e.out_preact = d.out_preact;
@@ -204,6 +214,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   e.dalpha_partial = d.dalpha_partial;
   e.stats_partial = d.stats_partial;
   e.err = g_watchdog;
+  e.trace = reinterpret_cast<long long*>(d.trace);
   e.os_n = d.os_n;
   e.os_h = d.os_h;
   e.os_w = d.os_w;
@@ -235,6 +246,7 @@ int build_wgrad(const tsr_wgrad_desc_t& d, WgradLaunch* L) {
   if (d.chan_block != 64 && d.chan_block != 32 && d.chan_block != 16) return fail(-30, "chan_block must be 16/32/64");
   if (d.dy_block != 64 && d.dy_block != 32 && d.dy_block != 16) return fail(-30, "dy_block must be 16/32/64");
   if (d.block_n % d.dy_block || d.block_n % 16 || d.block_n > 256) return fail(-30, "bad block_n");
+  if (d.cout_valid % 16) return fail(-30, "cout_valid (accumulator row width) must be a multiple of 16");
   if ((d.C - d.x_c0) % d.chan_block) return fail(-30, "C must be a multiple of chan_block");
   if (d.num_taps < 1 || d.num_taps > kMaxTaps) return fail(-30, "num_taps out of range");
   const int64_t wo = (d.W + d.upper_w - d.lower_w - 1) / d.stride + 1;
@@ -259,9 +271,15 @@ int build_wgrad(const tsr_wgrad_desc_t& d, WgradLaunch* L) {
   p.err = g_watchdog;
   memcpy(p.tap_off, d.tap_off, sizeof(p.tap_off));
   const int total_groups = (p.total_blocks + p.blocks_per_m - 1) / p.blocks_per_m;
-  int gpc = 512 / pow2_cols(d.block_n) * (pow2_cols(d.block_n) / d.block_n);  // groups whose accumulators fit TMEM
-  gpc = 512 / d.block_n;
+  int gpc = 512 / d.block_n;  // groups whose accumulators fit the 512 TMEM columns
   if (gpc > total_groups) gpc = total_groups;
+  {
+    // fewer groups per CTA = more CTAs (each re-reads the dY tile): shrink until the grid can cover the 148 SMs
+    const int tiles_n0 = static_cast<int>((d.cout_valid + d.block_n - 1) / d.block_n);
+    const int iters64 = (p.M_total + 63) / 64;
+    const int max_splits0 = iters64 / 4 > 0 ? iters64 / 4 : 1;
+    while (gpc > 1 && ((total_groups + gpc - 1) / gpc) * tiles_n0 * max_splits0 < 148) gpc = (gpc + 1) / 2;
+  }
   // choose pixels per stage / groups per CTA so that at least 2 stages fit in ~200 KB
   int pix = 64;
   auto stage_bytes = [&](int g, int px) {
@@ -316,7 +334,38 @@ struct tsr_prog {
     tsr_elt_desc_t elt;
   };
   std::vector<Op> ops;
+  // one instantiated CUDA graph per executed [first, last) range: every pointer in a program is fixed, so a range is
+  // captured once and replayed with a single cudaGraphLaunch
+  std::map<std::pair<int, int>, cudaGraphExec_t> graphs;
 };
+
+namespace {
+cudaStream_t g_capture_stream = nullptr;
+int g_use_graphs = -1;
+
+bool use_graphs() {
+  if (g_use_graphs < 0) {
+    const char* e = getenv("TSR_GRAPHS");
+    g_use_graphs = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_use_graphs == 1;
+}
+
+int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
+  for (int i = first; i < last; ++i) {
+    const tsr_prog::Op& op = p->ops[i];
+    cudaError_t ce;
+    if (op.kind == tsr_prog::CONV)
+      ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st);
+    else if (op.kind == tsr_prog::WGRAD)
+      ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st);
+    else
+      ce = tsr::launch_elt(op.elt, st);
+    if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
+  }
+  return 0;
+}
+}  // namespace
 
 extern "C" {
 
@@ -352,7 +401,10 @@ int tsr_elt(const tsr_elt_desc_t* d, void* stream) {
 }
 
 tsr_prog_t* tsr_prog_create(void) { return new tsr_prog(); }
-void tsr_prog_destroy(tsr_prog_t* p) { delete p; }
+void tsr_prog_destroy(tsr_prog_t* p) {
+  for (auto& kv : p->graphs) cudaGraphExecDestroy(kv.second);
+  delete p;
+}
 int tsr_prog_size(const tsr_prog_t* p) { return static_cast<int>(p->ops.size()); }
 
 int tsr_prog_add_conv(tsr_prog_t* p, const tsr_conv_desc_t* d) {
@@ -382,18 +434,44 @@ int tsr_prog_run(tsr_prog_t* p, int first, int count, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = static_cast<int>(p->ops.size());
   const int last = count < 0 ? n : (first + count > n ? n : first + count);
-  for (int i = first; i < last; ++i) {
-    const tsr_prog::Op& op = p->ops[i];
-    cudaError_t ce;
-    if (op.kind == tsr_prog::CONV)
-      ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st);
-    else if (op.kind == tsr_prog::WGRAD)
-      ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st);
-    else
-      ce = tsr::launch_elt(op.elt, st);
-    if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
-    g_launches++;
+  if (last <= first) return 0;
+  if (!use_graphs() || last - first < 4) {
+    if (int e = launch_range(p, first, last, st)) return e;
+    g_launches += last - first;
+    return 0;
   }
+  const auto key = std::make_pair(first, last);
+  auto it = p->graphs.find(key);
+  if (it == p->graphs.end()) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_capture_stream) {
+      cudaError_t ce = cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking);
+      if (ce != cudaSuccess) return fail(-43, "capture stream: %s", cudaGetErrorString(ce));
+    }
+    // first execution of this range: run it eagerly once (sets the kernels' function attributes outside capture and
+    // keeps first-run behaviour identical), then capture it for every later call
+    if (int e = launch_range(p, first, last, st)) return e;
+    g_launches += last - first;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) return fail(-43, "begin capture: %s", cudaGetErrorString(ce));
+    const int e = launch_range(p, first, last, g_capture_stream);
+    ce = cudaStreamEndCapture(g_capture_stream, &graph);
+    if (e) {
+      if (graph) cudaGraphDestroy(graph);
+      return e;
+    }
+    if (ce != cudaSuccess) return fail(-43, "end capture: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(-43, "graph instantiate: %s", cudaGetErrorString(ce));
+    p->graphs[key] = exec;
+    return 0;
+  }
+  cudaError_t ce = cudaGraphLaunch(it->second, st);
+  if (ce != cudaSuccess) return fail(-44, "graph launch failed: %s", cudaGetErrorString(ce));
+  g_launches += last - first;
   return 0;
 }
 

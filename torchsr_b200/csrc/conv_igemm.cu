@@ -93,6 +93,133 @@ __device__ __forceinline__ void store_f32x16(void* base, long long off, const fl
 
 }  // namespace
 
+// Warp 0 (all lanes run the loop so that every value stays warp-uniform; one elected lane issues): keeps the smem
+// ring full. All per-iteration state is carried incrementally (no divisions).
+template <int A_MODE>
+__device__ __forceinline__ void producer_loop(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t tiles,
+                                              int m0, int tile_n, int it_begin, int it_end, long long* trace) {
+  int w0 = 0, h0 = 0, n0 = 0;
+  if (A_MODE == 0) {
+    const int hw = p.Ho * p.Wo;
+    n0 = m0 / hw;
+    const int rem = m0 - n0 * hw;
+    const int ho = rem / p.Wo;
+    const int wo = rem - ho * p.Wo;
+    h0 = ho * p.stride + p.lower_h;
+    w0 = wo * p.stride + p.lower_w;
+  }
+  const int stages = p.stages;
+  const uint32_t stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, tx = p.a_bytes + p.b_bytes;
+  const int kc_per_tap = p.kc_per_tap, block_k = p.block_k;
+  const int b_row0 = tile_n * p.block_n;
+  int tap = 0, kc = it_begin;
+  if (A_MODE == 0) {
+    tap = it_begin / kc_per_tap;
+    kc = it_begin - tap * kc_per_tap;
+  }
+  int s = 0;
+  uint32_t ph = 1;  // parity to wait for on the empty barrier (first pass over the ring passes immediately)
+  uint32_t dst = tiles;
+  for (int it = it_begin; it < it_end; ++it) {
+    if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) break;
+    const uint32_t full = bar_full + 8 * s;
+    if (A_MODE == 0) {
+      const uint32_t off = p.tap_off[tap];
+      const int brow = p.tap_wrow[tap] * p.b_rows_per_tap + b_row0;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full, tx);
+        tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
+        tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, brow);
+      }
+      if (++kc == kc_per_tap) {
+        kc = 0;
+        ++tap;
+      }
+    } else if (A_MODE == 1) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full, tx);
+        tma_load_2d(dst, &p.tmA, full, kc * block_k, m0);
+        tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+      }
+      ++kc;
+    } else {
+      // MN-major A: two [block_k rows (K)] x [64 M-elements] boxes
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full, tx);
+        tma_load_2d(dst, &p.tmA, full, m0, kc * block_k);
+        tma_load_2d(dst + block_k * 128, &p.tmA, full, m0 + 64, kc * block_k);
+        tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+      }
+      ++kc;
+    }
+    __syncwarp();
+    if (trace && it - it_begin < 16 && (threadIdx.x & 31) == 0) trace[8 + it - it_begin] = clock64();
+    dst += stage_bytes;
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1;
+      dst = tiles;
+    }
+  }
+}
+
+// Warp 1 (all lanes loop, one elected lane issues): the UMMAs of every stage, slot recycling with tcgen05.commit.
+template <int A_MODE>
+__device__ __forceinline__ void mma_loop(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tmem,
+                                         uint32_t tiles, uint32_t tmem_base, int n_iters, long long* trace) {
+  const int stages = p.stages;
+  const uint32_t ksteps = p.ksteps, idesc = p.idesc;
+  const uint32_t stage16 = p.stage_bytes >> 4, a16 = p.a_bytes >> 4;
+  // descriptor high words are loop invariant; the low word's start-address field advances in 16-byte units
+  uint64_t a0, b0;
+  uint32_t a_kadv;
+  if (A_MODE == 2) {
+    a0 = make_smem_desc(tiles, p.block_k * 128, 1024, 2);
+    a_kadv = 2048 >> 4;
+  } else {
+    a0 = make_smem_desc(tiles, 16, p.sbo_bytes, p.layout_type);
+    a_kadv = 32 >> 4;
+  }
+  b0 = make_smem_desc(tiles, 16, p.sbo_bytes, p.layout_type);
+  const uint32_t a_hi = static_cast<uint32_t>(a0 >> 32), b_hi = static_cast<uint32_t>(b0 >> 32);
+  const uint32_t a_lo0 = static_cast<uint32_t>(a0), b_lo0 = static_cast<uint32_t>(b0) + a16;
+  int s = 0;
+  uint32_t ph = 0, soff = 0, acc = 0;
+  bool ok = true;
+  for (int it = 0; it < n_iters; ++it) {
+    if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) {
+      ok = false;
+      break;
+    }
+    tc_fence_after();
+    if (trace && it < 16 && (threadIdx.x & 31) == 0) trace[24 + it] = clock64();
+    if (elect_one()) {
+      uint32_t a_lo = a_lo0 + soff, b_lo = b_lo0 + soff;
+      uint32_t acc_k = acc;
+      for (uint32_t k = 0; k < ksteps; ++k) {
+        umma_bf16(tmem_base, (static_cast<uint64_t>(a_hi) << 32) | a_lo, (static_cast<uint64_t>(b_hi) << 32) | b_lo,
+                  idesc, acc_k);
+        acc_k = 1;
+        a_lo += a_kadv;
+        b_lo += 2;
+      }
+      umma_commit(bar_empty + 8 * s);
+    }
+    __syncwarp();
+    acc = 1;
+    soff += stage16;
+    if (++s == stages) {
+      s = 0;
+      ph ^= 1;
+      soff = 0;
+    }
+  }
+  if (ok && elect_one()) umma_commit(bar_tmem);
+  __syncwarp();
+  if (trace && (threadIdx.x & 31) == 0) trace[4] = clock64();
+}
+
+template <int A_MODE>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -102,12 +229,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const int lane = threadIdx.x & 31;
   const int tile_m = blockIdx.x;
   const int tile_n = blockIdx.y;
-  const int split = blockIdx.z;
 
-  const int stages = p.stages;
-  const uint32_t a_bytes = kBlockM * p.block_k * 2;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * p.block_k * 2;
-  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
   const uint32_t bar_full = smem_base;                 // 8 x u64
   const uint32_t bar_empty = smem_base + 64;           // 8 x u64
   const uint32_t bar_tmem = smem_base + 128;           // u64
@@ -116,13 +238,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   float* scratch = reinterpret_cast<float*>(smem_gen + kScratchOff);
   const uint32_t tiles = smem_base + kHeaderBytes;
 
+  long long* trace = p.epi.trace ? p.epi.trace + 40ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
+                                 : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
   const int total_iters = p.num_taps * p.kc_per_tap;
-  const int it_begin = split * p.iters_per_split;
+  const int it_begin = blockIdx.z * p.iters_per_split;
   const int it_end = min(total_iters, it_begin + p.iters_per_split);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    const int stages = p.stages;
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -138,150 +264,106 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
 
   const int m0 = tile_m * kBlockM;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      int w0 = 0, h0 = 0, n0 = 0;
-      if (p.a_mode == 0) {
-        const int hw = p.Ho * p.Wo;
-        n0 = m0 / hw;
-        const int rem = m0 - n0 * hw;
-        const int ho = rem / p.Wo;
-        const int wo = rem - ho * p.Wo;
-        h0 = ho * p.stride + p.lower_h;
-        w0 = wo * p.stride + p.lower_w;
-      }
-      int idx = 0;
-      for (int it = it_begin; it < it_end; ++it, ++idx) {
-        const int s = idx % stages;
-        const uint32_t ph = (idx / stages) & 1;
-        if (!mbar_wait(bar_empty + 8 * s, ph ^ 1, p.epi.err, 1)) break;
-        const int tap = it / p.kc_per_tap;
-        const int kc = it - tap * p.kc_per_tap;
-        const uint32_t a_dst = tiles + s * stage_bytes;
-        const uint32_t b_dst = a_dst + a_bytes;
-        const uint32_t full = bar_full + 8 * s;
-        mbar_arrive_expect_tx(full, a_bytes + b_bytes);
-        if (p.a_mode == 0) {
-          const uint16_t off = p.tap_off[tap];
-          tma_load_im2col_4d(a_dst, &p.tmA, full, p.a_c0 + kc * p.block_k, w0, h0, n0, off & 0xFF, off >> 8);
-        } else if (p.a_mode == 1) {
-          tma_load_2d(a_dst, &p.tmA, full, it * p.block_k, m0);
-        } else {
-          // MN-major A: two [block_k rows (K)] x [64 M-elements] boxes
-          tma_load_2d(a_dst, &p.tmA, full, m0, it * p.block_k);
-          tma_load_2d(a_dst + p.block_k * 128, &p.tmA, full, m0 + 64, it * p.block_k);
-        }
-        tma_load_2d(b_dst, &p.tmB, full, (p.a_mode == 0 ? kc : it) * p.block_k,
-                    p.tap_wrow[tap] * p.b_rows_per_tap + tile_n * p.block_n);
-      }
-    }
+    producer_loop<A_MODE>(p, bar_full, bar_empty, tiles, m0, tile_n, it_begin, it_end, trace);
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      const int row_bytes = p.block_k * 2;
-      const uint32_t lt = layout_type_for_row_bytes(row_bytes);
-      const uint32_t sbo = 8 * row_bytes;
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, p.a_mode == 2 ? 1 : 0, 0);
-      int idx = 0;
-      bool ok = true;
-      for (int it = it_begin; it < it_end; ++it, ++idx) {
-        const int s = idx % stages;
-        const uint32_t ph = (idx / stages) & 1;
-        if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) {
-          ok = false;
-          break;
-        }
-        tc_fence_after();
-        const uint32_t a_src = tiles + s * stage_bytes;
-        const uint32_t b_src = a_src + a_bytes;
-        const int ksteps = p.block_k / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          uint64_t adesc;
-          if (p.a_mode == 2)
-            adesc = make_smem_desc(a_src + k * 2048, /*LBO: next 64 M-elements*/ p.block_k * 128, 1024, 2);
-          else
-            adesc = make_smem_desc(a_src + k * 32, 16, sbo, lt);
-          const uint64_t bdesc = make_smem_desc(b_src + k * 32, 16, sbo, lt);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (idx > 0 || k > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_empty + 8 * s);
-      }
-      if (ok) umma_commit(bar_tmem);
-    }
+    mma_loop<A_MODE>(p, bar_full, bar_empty, bar_tmem, tiles, tmem_base, it_end - it_begin, trace);
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the 16-column chunks.
     const EpiParams& e = p.epi;
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool valid = m < p.M_total;
     int n = 0, ho = 0, wo = 0;
-    if (p.a_mode == 0) {
+    long long out_base, aux_base;
+    if (A_MODE == 0) {
       const int hw = p.Ho * p.Wo;
       n = m / hw;
       const int rem = m - n * hw;
       ho = rem / p.Wo;
       wo = rem - ho * p.Wo;
-    }
-    long long out_base = 0, aux_base = 0;
-    if (e.out_mode == OUT_LINEAR) {
       out_base = n * e.os_n + ho * e.os_h + wo * e.os_w + e.out_ch_off;
-    } else if (e.out_mode == OUT_UNSHUFFLE) {
-      out_base = n * e.os_n + (ho >> 1) * e.os_h + (wo >> 1) * e.os_w + ((ho & 1) * 2 + (wo & 1)) * e.shuf_c +
-                 e.out_ch_off;
-    }
-    aux_base = n * e.aux_n + ho * e.aux_h + wo * e.aux_w + e.aux_ch_off;
-    if (p.a_mode != 0) {
+      if (e.out_mode == OUT_UNSHUFFLE)
+        out_base = n * e.os_n + (ho >> 1) * e.os_h + (wo >> 1) * e.os_w + ((ho & 1) * 2 + (wo & 1)) * e.shuf_c +
+                   e.out_ch_off;
+      else if (e.out_mode == OUT_SHUFFLE)
+        out_base = n * e.os_n + (2 * ho) * e.os_h + (2 * wo) * e.os_w + e.out_ch_off;
+      aux_base = n * e.aux_n + ho * e.aux_h + wo * e.aux_w + e.aux_ch_off;
+    } else {
       out_base = static_cast<long long>(m) * e.os_w + e.out_ch_off;
       aux_base = static_cast<long long>(m) * e.aux_w + e.aux_ch_off;
     }
-
+    const int out_mode = e.out_mode, act = e.act, bwd_act = e.bwd_act, n_valid = e.n_valid, shuf_c = e.shuf_c;
+    const float acc_scale = e.acc_scale, leaky = e.leaky_slope;
+    const float* bias = e.bias;
+    const void* bwd_z = e.bwd_z;
+    const void* res = e.res;
+    void* out = e.out;
+    void* out_preact = e.out_preact;
+    const bool want_stats = e.stats_partial != nullptr;
+    const bool out_f32 = e.out_f32 != 0;
     const float alpha = (e.prelu != nullptr) ? __ldg(e.prelu) : 0.f;
+    const float bslope = (bwd_act == ACT_PRELU) ? alpha : (bwd_act == ACT_LEAKY ? leaky : 0.f);
     float dalpha = 0.f;
+    const int chunks = p.block_n >> 4;
+    const int ch_begin = half ? (chunks + 1) >> 1 : 0;
+    const int ch_end = half ? chunks : (chunks + 1) >> 1;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int colbase = tile_n * p.block_n;
     const bool ok = mbar_wait(bar_tmem, 0, e.err, 3);
     tc_fence_after();
-    const int chunks = p.block_n / 16;
+    if (trace && threadIdx.x == 64) trace[5] = clock64();
     if (ok) {
-      for (int ch = 0; ch < chunks; ++ch) {
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
         uint32_t r[16];
-        tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ch * 16, r);
+        tmem_ld16(taddr + ch * 16, r);
         tmem_ld_wait();
-        const int col0 = tile_n * p.block_n + ch * 16;
+        if (trace && threadIdx.x == 64 && ch < 4) trace[32 + 2 * ch] = clock64();
+        const int col0 = colbase + ch * 16;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * e.acc_scale;
-        const bool st = valid && col0 < e.n_valid;
-        if (e.bias != nullptr) {
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * acc_scale;
+        const bool st = valid && col0 < n_valid;
+        if (bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(e.bias + col0 + i);
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            v[4 * i] += b4.x;
+            v[4 * i + 1] += b4.y;
+            v[4 * i + 2] += b4.z;
+            v[4 * i + 3] += b4.w;
+          }
         }
-        if (e.bwd_z != nullptr && st) {
+        if (bwd_z != nullptr && st) {
           float z[16];
-          load_bf16x16(e.bwd_z, aux_base + col0, z);
-          const float slope = (e.bwd_act == ACT_PRELU) ? alpha : (e.bwd_act == ACT_LEAKY ? e.leaky_slope : 0.f);
+          load_bf16x16(bwd_z, aux_base + col0, z);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             if (z[i] <= 0.f) {
               dalpha += v[i] * z[i];
-              v[i] *= slope;
+              v[i] *= bslope;
             }
           }
         }
-        if (e.res != nullptr && st) {
+        if (res != nullptr && st) {
           float z[16];
-          load_bf16x16(e.res, aux_base + col0, z);
+          load_bf16x16(res, aux_base + col0, z);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += z[i];
         }
-        if (!valid) {
+        if (want_stats) {
+          if (!valid) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-        }
-        if (e.stats_partial != nullptr) {
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
           float sq[16], s1, s2;
 #pragma unroll
           for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
@@ -293,67 +375,61 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             scratch[(q * 256 + c) * 2 + 1] = s2;
           }
         }
-        long long off;
-        if (e.out_mode == OUT_SHUFFLE) {
-          const int blk = col0 / e.shuf_c;
-          off = n * e.os_n + (2 * ho + (blk >> 1)) * e.os_h + (2 * wo + (blk & 1)) * e.os_w + (col0 - blk * e.shuf_c) +
-                e.out_ch_off;
-        } else {
-          off = out_base + col0;
-        }
         if (st) {
-          if (e.out_mode == OUT_GEMM_T_ATOMIC) {
-            float* o = reinterpret_cast<float*>(e.out);
+          long long off = out_base + col0;
+          if (out_mode == OUT_SHUFFLE) {
+            const int blk = col0 / shuf_c;
+            off = out_base + (blk >> 1) * e.os_h + (blk & 1) * e.os_w + (col0 - blk * shuf_c);
+          }
+          if (out_mode == OUT_GEMM_T_ATOMIC) {
+            float* o = reinterpret_cast<float*>(out);
 #pragma unroll
             for (int i = 0; i < 16; ++i) atomicAdd(o + static_cast<long long>(col0 + i) * e.os_n + m, v[i]);
           } else {
-            if (e.out_preact != nullptr) store_bf16x16(e.out_preact, off, v);
-            if (e.act == ACT_PRELU) {
+            if (out_preact != nullptr) store_bf16x16(out_preact, off, v);
+            if (act == ACT_PRELU || act == ACT_LEAKY) {
+              const float sl = act == ACT_PRELU ? alpha : leaky;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * alpha;
-            } else if (e.act == ACT_LEAKY) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * e.leaky_slope;
-            } else if (e.act == ACT_RELU) {
+              for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+            } else if (act == ACT_RELU) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (e.out_f32)
-              store_f32x16(e.out, off, v);
+            if (out_f32)
+              store_f32x16(out, off, v);
             else
-              store_bf16x16(e.out, off, v);
+              store_bf16x16(out, off, v);
           }
         }
+        if (trace && threadIdx.x == 64 && ch < 4) trace[33 + 2 * ch] = clock64();
       }
     }
-    // cross-warp reductions of the epilogue side products
-    if (e.stats_partial != nullptr || e.dalpha_partial != nullptr) {
+    // cross-warp reductions of the epilogue side products -> one red.global.add per column / per CTA
+    if (want_stats || e.dalpha_partial != nullptr) {
       if (e.dalpha_partial != nullptr) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dalpha += __shfl_xor_sync(0xffffffffu, dalpha, o);
-        if (lane == 0) scratch[4 * 256 * 2 + q] = dalpha;
+        if (lane == 0) scratch[4 * 256 * 2 + (warp - 2)] = dalpha;
       }
-      named_bar_sync(1, 128);
-      const int t = threadIdx.x - 64;  // 0..127
-      if (e.stats_partial != nullptr && ok) {
-        for (int c = t; c < p.block_n; c += 128) {
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            s1 += scratch[(w * 256 + c) * 2 + 0];
-            s2 += scratch[(w * 256 + c) * 2 + 1];
-          }
-          float* dst = e.stats_partial + (static_cast<long long>(tile_m) * e.stats_ld + tile_n * p.block_n + c) * 2;
-          dst[0] = s1;
-          dst[1] = s2;
+      named_bar_sync(1, kConvThreads - 64);
+      const int t = threadIdx.x - 64;  // 0..255
+      if (want_stats && ok) {
+        // thread t -> (column t>>1, statistic t&1) for block_n <= 128; two passes for wider tiles
+        for (int idx = t; idx < p.block_n * 2; idx += kConvThreads - 64) {
+          const int c = idx >> 1, w = idx & 1;
+          const float sum = scratch[(0 * 256 + c) * 2 + w] + scratch[(1 * 256 + c) * 2 + w] +
+                            scratch[(2 * 256 + c) * 2 + w] + scratch[(3 * 256 + c) * 2 + w];
+          atomicAdd(e.stats_partial + (colbase + c) * 2 + w, sum);
         }
       }
       if (e.dalpha_partial != nullptr && t == 0) {
-        const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        e.dalpha_partial[cta] =
-            scratch[4 * 256 * 2 + 0] + scratch[4 * 256 * 2 + 1] + scratch[4 * 256 * 2 + 2] + scratch[4 * 256 * 2 + 3];
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += scratch[4 * 256 * 2 + w];
+        atomicAdd(e.dalpha_partial, tot);
       }
     }
+    if (trace && threadIdx.x == 64) trace[6] = clock64();
   }
 
   tc_fence_before();
@@ -362,26 +438,33 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (trace && threadIdx.x == 0) trace[7] = clock64();
 }
 
 size_t conv_igemm_smem_bytes(const ConvParams& p) {
-  const uint32_t a_bytes = kBlockM * p.block_k * 2;
-  const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * p.block_k * 2;
-  const uint32_t stage_bytes = (a_bytes + b_bytes + 1023u) & ~1023u;
-  return 1024 + kHeaderBytes + static_cast<size_t>(p.stages) * stage_bytes;
+  return 1024 + kHeaderBytes + static_cast<size_t>(p.stages) * p.stage_bytes;
 }
 
-cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream) {
+template <int A_MODE>
+static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e =
+        cudaFuncSetAttribute(conv_igemm_kernel<A_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  conv_igemm_kernel<A_MODE><<<grid, kConvThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream) {
   const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
   dim3 grid(tiles_m, tiles_n, splits);
-  conv_igemm_kernel<<<grid, kConvThreads, conv_igemm_smem_bytes(p), stream>>>(p);
-  return cudaGetLastError();
+  const size_t smem = conv_igemm_smem_bytes(p);
+  if (p.a_mode == 0) return launch_mode<0>(p, grid, smem, stream);
+  if (p.a_mode == 1) return launch_mode<1>(p, grid, smem, stream);
+  return launch_mode<2>(p, grid, smem, stream);
 }
 
 }  // namespace tsr

@@ -7,7 +7,8 @@ namespace tsr {
 
 constexpr int kMaxTaps = 81;      // 9x9
 constexpr int kBlockM = 128;      // UMMA M (TMEM lanes)
-constexpr int kConvThreads = 192; // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
+constexpr int kConvThreads = 320; // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogue (2 per TMEM lane quadrant)
+constexpr int kWgradThreads = 192; // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
 
 enum OutMode : int {
   OUT_LINEAR = 0,     // off = n*os_n + ho*os_h + wo*os_w + col
@@ -25,8 +26,10 @@ struct EpiParams {
   const void* res;       // optional bf16 residual, aux addressing:  v = acc*acc_scale (+bias) + res
   const void* bwd_z;     // optional bf16 tensor, aux addressing: v *= act'(bwd_z)
   float* dalpha_partial; // optional [grid] partial sums of v*z*[z<0] (PReLU slope gradient)
-  float* stats_partial;  // optional [tiles_m][stats_ld][2] per-tile column sum / sum of squares of stored value
+  float* stats_partial;  // optional [stats_ld][2]: per-column sum / sum of squares of the stored value, accumulated
+                         // with red.global.add (the caller zeroes it before the launch)
   int* err;              // watchdog / error flag
+  long long* trace;      // optional per-CTA clock64 stamps [grid][8]
   long long os_n, os_h, os_w;     // out strides in elements
   long long aux_n, aux_h, aux_w;  // aux strides in elements
   int out_mode;
@@ -60,6 +63,12 @@ struct ConvParams {
   int iters_per_split;  // K iterations handled per blockIdx.z
   int stages;
   int tmem_cols;
+  // derived on the host so that the single-thread producer / MMA loops stay short
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  uint32_t ksteps;      // block_k / 16
+  uint32_t sbo_bytes;   // 8 rows of the K-major tiles
+  uint32_t layout_type; // UMMA swizzle code of the K-major tiles
+  uint32_t idesc;
   uint16_t tap_off[kMaxTaps];   // (off_h << 8) | off_w
   uint16_t tap_wrow[kMaxTaps];  // tap slot in the packed weight matrix
 };

@@ -5,8 +5,8 @@
 // Both operands are NHWC (channel-contiguous), i.e. MN-major for this GEMM. X tiles arrive through TMA im2col
 // (pix_per_stage pixels x chan_block channels per (tap, ci-block) "M block"), dY tiles through tiled TMA.
 // blocks_per_m M blocks are stacked into one UMMA M=128 operand; groups_per_cta such groups share every dY
-// tile and own block_n TMEM columns each. Partial sums over the pixel split are reduced with fp32
-// red.global.add into a zero-initialised [Cout][tap][Cin] buffer (lanes = consecutive ci -> coalesced).
+// tile and own block_n TMEM columns each. Partial sums over the pixel split are reduced with 16-byte fp32 vector
+// reductions (red.global.add.v4.f32) into a zero-initialised [tap][Cin][Cout_pad] buffer.
 //
 // Reference behaviour being replaced: autograd's convolution_backward (weight part) for every nn.Conv2d on
 // the path, e.g. torchsr/srgan/residual.py:64,67.
@@ -19,7 +19,11 @@ namespace {
 constexpr int kWgHeader = 1024;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -79,63 +83,109 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
 
   if (warp == 0) {
     if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (incremental pixel coordinates)
       const int hw = p.Ho * p.Wo;
+      int n0 = pix_begin / hw;
+      int rem = pix_begin - n0 * hw;
+      int ho = rem / p.Wo;
+      int wo = rem - ho * p.Wo;
+      // (tap, channel-block) of this CTA's first block; later blocks advance incrementally
+      const int tap0 = first_block / p.cin_blocks;
+      const int cib0 = first_block - tap0 * p.cin_blocks;
+      const uint32_t tx = cta_blocks * blkA + nb * blkB;
+      const int dy_col0 = tile_n * p.block_n;
+      int s = 0;
+      uint32_t ph = 1, dst = tiles;
+      int pix0 = pix_begin;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
-        if (!mbar_wait(bar_empty + 8 * s, ph ^ 1, p.err, 11)) break;
-        const int pix0 = pix_begin + it * p.pix_per_stage;
-        const int n0 = pix0 / hw;
-        const int rem = pix0 - n0 * hw;
-        const int ho = rem / p.Wo;
-        const int wo = rem - ho * p.Wo;
+        if (!mbar_wait(bar_empty + 8 * s, ph, p.err, 11)) break;
         const int h0 = ho * p.stride + p.lower_h;
         const int w0 = wo * p.stride + p.lower_w;
-        const uint32_t a_dst = tiles + s * stage_bytes;
-        const uint32_t b_dst = a_dst + a_region;
         const uint32_t full = bar_full + 8 * s;
-        mbar_arrive_expect_tx(full, cta_blocks * blkA + nb * blkB);
+        mbar_arrive_expect_tx(full, tx);
+        int tap = tap0, cib = cib0;
+        uint32_t a_dst = dst;
         for (int j = 0; j < cta_blocks; ++j) {
-          const int blk = first_block + j;
-          const int tap = blk / p.cin_blocks;
-          const int cib = blk - tap * p.cin_blocks;
-          const uint16_t off = p.tap_off[tap];
-          tma_load_im2col_4d(a_dst + j * blkA, &p.tmX, full, cib * p.chan_block, w0, h0, n0, off & 0xFF, off >> 8);
+          const uint32_t off = p.tap_off[tap];
+          tma_load_im2col_4d(a_dst, &p.tmX, full, cib * p.chan_block, w0, h0, n0, off & 0xFF, off >> 8);
+          a_dst += blkA;
+          if (++cib == p.cin_blocks) {
+            cib = 0;
+            ++tap;
+          }
         }
-        for (int j = 0; j < nb; ++j)
-          tma_load_2d(b_dst + j * blkB, &p.tmDy, full, tile_n * p.block_n + j * p.dy_block, pix0);
+        uint32_t b_dst = dst + a_region;
+        for (int j = 0; j < nb; ++j) {
+          tma_load_2d(b_dst, &p.tmDy, full, dy_col0 + j * p.dy_block, pix0);
+          b_dst += blkB;
+        }
+        // advance the pixel cursor by pix_per_stage positions (W, then H, then N)
+        pix0 += p.pix_per_stage;
+        wo += p.pix_per_stage;
+        while (wo >= p.Wo) {
+          wo -= p.Wo;
+          if (++ho == p.Ho) {
+            ho = 0;
+            ++n0;
+          }
+        }
+        dst += stage_bytes;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+          dst = tiles;
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
       const uint32_t ltA = layout_type_for_row_bytes(rowA);
       const uint32_t ltB = layout_type_for_row_bytes(rowB);
       const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1);
+      const uint64_t a0 = make_smem_desc(tiles, blkA, 8 * rowA, ltA);
+      const uint64_t b0 = make_smem_desc(tiles + a_region, blkB, 8 * rowB, ltB);
+      const uint32_t a_hi = static_cast<uint32_t>(a0 >> 32), b_hi = static_cast<uint32_t>(b0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(a0), b_lo0 = static_cast<uint32_t>(b0);
+      const uint32_t stage16 = stage_bytes >> 4, group16 = (p.blocks_per_m * blkA) >> 4;
+      const uint32_t ka16 = (16 * rowA) >> 4, kb16 = (16 * rowB) >> 4;
+      const int ksteps = p.pix_per_stage / 16;
+      int s = 0;
+      uint32_t ph = 0, soff = 0;
       bool ok = true;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
         if (!mbar_wait(bar_full + 8 * s, ph, p.err, 12)) {
           ok = false;
           break;
         }
         tc_fence_after();
-        const uint32_t a_src = tiles + s * stage_bytes;
-        const uint32_t b_src = a_src + a_region;
-        const int ksteps = p.pix_per_stage / 16;
+        const uint32_t acc = it > 0 ? 1u : 0u;
+        uint32_t a_lo_g = a_lo0 + soff;
+        uint32_t tm = tmem_base;
         for (int g = 0; g < cta_groups; ++g) {
+          uint32_t a_lo = a_lo_g, b_lo = b_lo0 + soff;
           for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc =
-                make_smem_desc(a_src + g * p.blocks_per_m * blkA + k * 16 * rowA, blkA, 8 * rowA, ltA);
-            const uint64_t bdesc = make_smem_desc(b_src + k * 16 * rowB, blkB, 8 * rowB, ltB);
-            umma_bf16(tmem_base + g * p.block_n, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tm, (static_cast<uint64_t>(a_hi) << 32) | a_lo, (static_cast<uint64_t>(b_hi) << 32) | b_lo, idesc,
+                      (k > 0) ? 1u : acc);
+            a_lo += ka16;
+            b_lo += kb16;
           }
+          a_lo_g += group16;
+          tm += p.block_n;
         }
         umma_commit(bar_empty + 8 * s);
+        soff += stage16;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+          soff = 0;
+        }
       }
       if (ok) umma_commit(bar_tmem);
     }
   } else {
+    // -------------------------------------------------------------- epilogue: TMEM -> red.global.add.v4.f32
+    // out[(tap * cin_pad + ci) * ld_out + co]: a thread owns one (tap, ci) row, its 16-column chunks are contiguous
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int blk_in_group = row / p.chan_block;
@@ -144,25 +194,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_wgrad_kernel(const __gri
     tc_fence_after();
     if (ok) {
       const int chunks = p.block_n / 16;
+      const int ld_out = p.cout_valid;   // padded output-channel count of the accumulator (multiple of 16)
       for (int g = 0; g < cta_groups; ++g) {
         const int blk = first_block + g * p.blocks_per_m + blk_in_group;
         const bool row_ok = blk < p.total_blocks && blk < first_block + cta_blocks;
         const int tap = blk / p.cin_blocks;
         const int cib = blk - tap * p.cin_blocks;
         const int ci = cib * p.chan_block + ci_in_blk;
+        float* orow = p.out + (static_cast<long long>(tap) * p.cin_pad + ci) * ld_out + tile_n * p.block_n;
         for (int ch = 0; ch < chunks; ++ch) {
           uint32_t r[16];
           tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n + ch * 16, r);
           tmem_ld_wait();
-          const int col0 = tile_n * p.block_n + ch * 16;
-          if (row_ok) {
+          if (row_ok && tile_n * p.block_n + ch * 16 < ld_out) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int co = col0 + i;
-              if (co < p.cout_valid)
-                atomicAdd(p.out + (static_cast<long long>(co) * p.num_taps + tap) * p.cin_pad + ci,
-                          __uint_as_float(r[i]));
-            }
+            for (int i = 0; i < 16; i += 4)
+              red_add_v4(orow + ch * 16 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
+                         __uint_as_float(r[i + 3]));
           }
         }
       }
@@ -193,7 +241,7 @@ cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int 
     attr_set = true;
   }
   dim3 grid(gsets, tiles_n, splits);
-  conv_wgrad_kernel<<<grid, kConvThreads, conv_wgrad_smem_bytes(p), stream>>>(p);
+  conv_wgrad_kernel<<<grid, kWgradThreads, conv_wgrad_smem_bytes(p), stream>>>(p);
   return cudaGetLastError();
 }
 

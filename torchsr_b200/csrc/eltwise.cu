@@ -142,98 +142,110 @@ __global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, float* __restrict__
   }
 }
 
-// ---------------------------------------------------------------------------------------------- BN finalize
-// p0 = partial [tiles][ld][2] (col sum, col sumsq), p1 = gamma, p2 = beta, p3 = running_mean, p4 = running_var,
-// p5 = num_batches_tracked (int64), p6 = coef out fp32 [4][C]: scale, shift, mean, invstd
-// i: 0 tiles, 1 C, 2 count (N*H*W), 3 update_running, 4 ld; f: 0 eps, 1 momentum
-// nn.BatchNorm2d training semantics: biased variance for normalisation, unbiased for the running estimate.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean, float* running_var,
-                                   long long* nbt, float* __restrict__ coef, int tiles, int C, long long count,
-                                   int update, int ld, float eps, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && update && nbt) *nbt += 1;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    s1 += partial[(static_cast<long long>(t) * ld + c) * 2 + 0];
-    s2 += partial[(static_cast<long long>(t) * ld + c) * 2 + 1];
-  }
-  const double mean = s1 / count;
-  double var = s2 / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float invstd = rsqrtf(static_cast<float>(var) + eps);
-  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-  coef[0 * C + c] = g * invstd;
-  coef[1 * C + c] = b - static_cast<float>(mean) * g * invstd;
-  coef[2 * C + c] = static_cast<float>(mean);
-  coef[3 * C + c] = invstd;
-  if (update) {
-    const double unbiased = count > 1 ? var * count / (count - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
-  }
-}
-// eval-mode coefficients from running statistics: p1..p4 as above, p6 = coef; i: 1 C; f: 0 eps
-__global__ void bn_eval_coef_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
-                                    float* coef, int C, float eps) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float invstd = rsqrtf(rv[c] + eps);
-  coef[0 * C + c] = gamma[c] * invstd;
-  coef[1 * C + c] = beta[c] - rm[c] * gamma[c] * invstd;
-  coef[2 * C + c] = rm[c];
-  coef[3 * C + c] = invstd;
-}
+// ---------------------------------------------------------------------------------------------- BN + activation
+// BN_ACT: y = act(norm(x)) * x_scale + res * res_scale, the per-channel (scale, shift) being derived on the fly:
+//   mode 0: identity (no normalisation)
+//   mode 1: training-mode nn.BatchNorm2d from the conv epilogue's column sums p1 = stats [C][2] (sum, sum of squares):
+//           biased variance for the normalisation; block 0 also writes coef_out (scale, shift, mean, invstd) for
+//           backward and updates running_mean / running_var (momentum, UNBIASED variance) and num_batches_tracked
+//   mode 2: eval-mode BatchNorm from running_mean / running_var
+// p0 = x bf16 [M][x_ld], p1 = stats, p2 = y bf16 [M][y_ld], p3 = res bf16 or null, p4 = prelu alpha or null, p5 = gamma,
+// p6 = beta, p7 = running_mean, p8 = running_var, p9 = num_batches_tracked (int64), p10 = coef_out fp32 [4][C] or null
+// i: 0 M, 1 C, 2 x_ld, 3 y_ld, 4 res_ld, 5 act, 6 x_off, 7 y_off, 8 res_off, 9 mode, 10 count (rows behind stats)
+// f: 0 leaky slope, 1 res_scale, 2 x_scale, 3 eps, 4 momentum
+struct BnActArgs {
+  const bf16* x;
+  const float* stats;
+  bf16* y;
+  const bf16* res;
+  const float* alpha;
+  const float* gamma;
+  const float* beta;
+  float* rm;
+  float* rv;
+  long long* nbt;
+  float* coef;
+  long long M, count;
+  int C, x_ld, y_ld, res_ld, act, x_off, y_off, res_off, mode;
+  float leaky, res_scale, x_scale, eps, momentum;
+};
 
-// ---------------------------------------------------------------------------------------------- BN apply + act
-// p0 = x bf16 [M][x_ld], p1 = coef (scale, shift) or null (identity), p2 = y bf16 [M][y_ld], p3 = res bf16 or null,
-// p4 = prelu alpha or null
-// i: 0 M, 1 C, 2 x_ld, 3 y_ld, 4 res_ld, 5 act, 6 x_off, 7 y_off, 8 res_off; f: 0 leaky slope, 1 res_scale, 2 x_scale
-// y = act(x*scale+shift)*x_scale + res*res_scale
-__global__ void bn_act_kernel(const bf16* __restrict__ x, const float* __restrict__ coef, bf16* __restrict__ y,
-                              const bf16* __restrict__ res, const float* __restrict__ alpha, long long M, int C,
-                              int x_ld, int y_ld, int res_ld, int act, int x_off, int y_off, int res_off,
-                              float leaky, float res_scale, float x_scale) {
-  const int groups = C / 8;
-  const long long total = M * groups;
-  const float slope = act == TSR_ACT_PRELU ? __ldg(alpha) : leaky;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % groups);
+__global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
+  const int groups = a.C / 8;
+  const long long total = a.M * groups;
+  const float slope = a.act == TSR_ACT_PRELU ? __ldg(a.alpha) : a.leaky;
+  const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
+  const int g = static_cast<int>(idx0 % groups);  // constant per thread: the grid stride is a multiple of `groups`
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    float mean = 0.f, var = 1.f, gm = 1.f, bt = 0.f;
+    if (a.mode != 0) {
+      gm = a.gamma ? __ldg(a.gamma + c) : 1.f;
+      bt = a.beta ? __ldg(a.beta + c) : 0.f;
+    }
+    if (a.mode == 1) {
+      const float inv_n = 1.f / static_cast<float>(a.count);
+      mean = __ldg(a.stats + 2 * c) * inv_n;
+      var = fmaxf(__ldg(a.stats + 2 * c + 1) * inv_n - mean * mean, 0.f);
+    } else if (a.mode == 2) {
+      mean = a.rm[c];
+      var = a.rv[c];
+    }
+    if (a.mode == 0) {
+      sc[j] = 1.f;
+      sh[j] = 0.f;
+    } else {
+      const float invstd = rsqrtf(var + a.eps);
+      sc[j] = gm * invstd;
+      sh[j] = bt - mean * sc[j];
+      if (blockIdx.x == 0 && threadIdx.x < groups) {
+        if (a.coef) {
+          a.coef[0 * a.C + c] = sc[j];
+          a.coef[1 * a.C + c] = sh[j];
+          a.coef[2 * a.C + c] = mean;
+          a.coef[3 * a.C + c] = invstd;
+        }
+        if (a.mode == 1 && a.rm) {
+          const float n = static_cast<float>(a.count);
+          const float unbiased = a.count > 1 ? var * n / (n - 1.f) : var;
+          a.rm[c] = (1.f - a.momentum) * a.rm[c] + a.momentum * mean;
+          a.rv[c] = (1.f - a.momentum) * a.rv[c] + a.momentum * unbiased;
+        }
+      }
+    }
+  }
+  if (a.mode == 1 && a.nbt && blockIdx.x == 0 && threadIdx.x == 0) *a.nbt += 1;
+  for (long long idx = idx0; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
     const long long m = idx / groups;
     float v[8];
-    ld8(x + m * x_ld + x_off + g * 8, v);
+    ld8(a.x + m * a.x_ld + a.x_off + g * 8, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float z = v[j];
-      if (coef) z = z * __ldg(coef + g * 8 + j) + __ldg(coef + C + g * 8 + j);
-      v[j] = act_fwd(z, act, slope) * x_scale;
-    }
-    if (res) {
+    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j] * sc[j] + sh[j], a.act, slope) * a.x_scale;
+    if (a.res) {
       float r[8];
-      ld8(res + m * res_ld + res_off + g * 8, r);
+      ld8(a.res + m * a.res_ld + a.res_off + g * 8, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j] * res_scale;
+      for (int j = 0; j < 8; ++j) v[j] += r[j] * a.res_scale;
     }
-    st8(y + m * y_ld + y_off + g * 8, v);
+    st8(a.y + m * a.y_ld + a.y_off + g * 8, v);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- BN backward
-// Shared column-reduction skeleton: 256 threads = (C/8 channel groups) x (256/(C/8) row lanes); each block
-// covers rows [blockIdx.x*rows_per_block, ...). Partial sums go to partial[block][C][2].
-//
-// BN_BWD_REDUCE: p0 = g bf16 (grad wrt act output) [M][g_ld], p1 = x raw bf16 [M][x_ld], p2 = coef (fwd) or null,
-// p3 = alpha or null, p4 = partial out [blocks][C][2] (sum dz, sum dz*xhat), p5 = dalpha partial [blocks] or null,
-// p6 = optional second gradient g2 bf16 added to g (same ld)
+// BN_BWD_REDUCE: column sums of dz and dz*xhat over all rows, accumulated with red.global.add into sums [C][2]
+// (zeroed by the caller), plus the PReLU slope gradient into a scalar.
+// p0 = g bf16 (grad wrt act output) [M][g_ld], p1 = x raw bf16 [M][x_ld], p2 = coef (fwd: scale, shift, mean, invstd)
+// or null, p3 = alpha or null, p4 = sums [C][2], p5 = dalpha accumulator (scalar) or null, p6 = optional second
+// gradient g2 bf16 added to g (same ld)
 // i: 0 M, 1 C, 2 act, 3 rows_per_block, 4 g_ld, 5 x_ld, 6 has_bn; f: 0 leaky
-// dz = g * act'(z), z = x*scale+shift (has_bn) or x; xhat = (x-mean)*invstd. For act backward without BN the
-// second sum is unused. ACT_LEAKY/RELU without BN take x = activation output (sign preserved).
+// dz = g * act'(z), z = x*scale+shift (has_bn) or x; xhat = (x-mean)*invstd. ACT_LEAKY/RELU without BN take
+// x = activation output (sign preserved).
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
                                                             const float* __restrict__ coef,
-                                                            const float* __restrict__ alpha, float* __restrict__ partial,
-                                                            float* __restrict__ dalpha_partial,
+                                                            const float* __restrict__ alpha, float* __restrict__ sums,
+                                                            float* __restrict__ dalpha_acc,
                                                             const bf16* __restrict__ g2, long long M, int C, int act,
                                                             int rows_per_block, int g_ld, int x_ld, int has_bn,
                                                             float leaky) {
@@ -281,8 +293,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
       }
     }
   }
-  // reduce over row lanes through shared memory: sm[lane][C][2]
-  float* smp = sm;
+  float* smp = sm;  // [lane][C][2]
   if (r_id < lanes) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -294,91 +305,93 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
   da = warp_sum(da);
   if ((threadIdx.x & 31) == 0) sda[threadIdx.x >> 5] = da;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float a = 0.f, b = 0.f;
-    for (int l = 0; l < lanes; ++l) {
-      a += smp[(l * C + c) * 2 + 0];
-      b += smp[(l * C + c) * 2 + 1];
-    }
-    partial[(static_cast<long long>(blockIdx.x) * C + c) * 2 + 0] = a;
-    partial[(static_cast<long long>(blockIdx.x) * C + c) * 2 + 1] = b;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float a = 0.f;
+    for (int l = 0; l < lanes; ++l) a += smp[l * C * 2 + i];
+    atomicAdd(sums + i, a);
   }
-  if (dalpha_partial && threadIdx.x == 0) {
+  if (dalpha_acc && threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += sda[w];
-    dalpha_partial[blockIdx.x] = t;
+    atomicAdd(dalpha_acc, t);
   }
 }
 
-// BN_BWD_FINALIZE: p0 = partial [blocks][C][2], p1 = dalpha partial [nda] or null, p2 = coef fwd, p3 = gamma,
-// p4 = bwd coef out [3][C] (c1 = gamma*invstd, c2 = sum_dz/M, c3 = sum_dz_xhat/M), p5 = dgamma out, p6 = dbeta out,
-// p7 = dalpha out (scalar) or null
-// i: 0 blocks, 1 C, 2 M, 3 nda, 4 accumulate_dalpha
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ dalpha_partial,
-                                       const float* __restrict__ coef, const float* __restrict__ gamma,
-                                       float* __restrict__ bcoef, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                       float* __restrict__ dalpha, int blocks, int C, long long M, int nda,
-                                       int acc_dalpha) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0 && dalpha && threadIdx.x < 32) {
-    float t = 0.f;
-    for (int i = threadIdx.x; i < nda; i += 32) t += dalpha_partial[i];
-    t = warp_sum(t);
-    if (threadIdx.x == 0) *dalpha = acc_dalpha ? (*dalpha + t) : t;
-  }
-  if (c >= C) return;
-  float a = 0.f, b = 0.f;
-  for (int t = 0; t < blocks; ++t) {
-    a += partial[(static_cast<long long>(t) * C + c) * 2 + 0];
-    b += partial[(static_cast<long long>(t) * C + c) * 2 + 1];
-  }
-  if (dbeta) dbeta[c] = a;
-  if (dgamma) dgamma[c] = b;
-  if (bcoef) {
-    bcoef[0 * C + c] = (gamma ? gamma[c] : 1.f) * coef[3 * C + c];
-    bcoef[1 * C + c] = a / static_cast<float>(M);
-    bcoef[2 * C + c] = b / static_cast<float>(M);
-  }
-}
-
-// BN_BWD_APPLY: p0 = g bf16, p1 = x raw bf16, p2 = coef fwd or null, p3 = bwd coef or null, p4 = alpha, p5 = dx out bf16,
-// p6 = optional g2
+// BN_BWD_APPLY: dx from g (+g2), the raw conv output x, the forward coefficients and the column sums.
+// p0 = g bf16, p1 = x raw bf16, p2 = coef fwd or null, p3 = sums [C][2] or null, p4 = alpha, p5 = dx out bf16,
+// p6 = optional g2, p7 = gamma or null, p8 = dgamma out [C] or null, p9 = dbeta / bias-gradient out [C] or null,
+// p10 = dalpha out (scalar) or null, p11 = dalpha accumulator (scalar) or null
 // i: 0 M, 1 C, 2 act, 3 g_ld, 4 x_ld, 5 dx_ld, 6 has_bn; f: 0 leaky
-// has_bn: dx = c1*(dz - c2 - xhat*c3); else dx = dz
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
-                                    const float* __restrict__ coef, const float* __restrict__ bcoef,
-                                    const float* __restrict__ alpha, bf16* __restrict__ dx,
-                                    const bf16* __restrict__ g2, long long M, int C, int act, int g_ld, int x_ld,
-                                    int dx_ld, int has_bn, float leaky) {
+// has_bn: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); else dx = dz.  Block 0 publishes the parameter
+// gradients (dgamma = sum dz*xhat, dbeta = sum dz, dalpha).
+struct BnBwdApplyArgs {
+  const bf16* g;
+  const bf16* x;
+  const float* coef;
+  const float* sums;
+  const float* alpha;
+  bf16* dx;
+  const bf16* g2;
+  const float* gamma;
+  float* dgamma;
+  float* dbeta;
+  float* dalpha;
+  const float* dalpha_acc;
+  long long M;
+  int C, act, g_ld, x_ld, dx_ld, has_bn;
+  float leaky;
+};
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs a) {
+  const int C = a.C;
   const int groups = C / 8;
-  const long long total = M * groups;
-  const float slope = act == TSR_ACT_PRELU ? __ldg(alpha) : (act == TSR_ACT_RELU ? 0.f : leaky);
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int gi = static_cast<int>(idx % groups);
+  const long long total = a.M * groups;
+  const float slope = a.act == TSR_ACT_PRELU ? __ldg(a.alpha) : (a.act == TSR_ACT_RELU ? 0.f : a.leaky);
+  const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
+  const int gi = static_cast<int>(idx0 % groups);
+  float sc[8], sh[8], mu[8], is[8], c1[8], c2[8], c3[8];
+  const float inv_m = 1.f / static_cast<float>(a.M);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = gi * 8 + j;
+    sc[j] = a.has_bn ? __ldg(a.coef + c) : 1.f;
+    sh[j] = a.has_bn ? __ldg(a.coef + C + c) : 0.f;
+    mu[j] = a.has_bn ? __ldg(a.coef + 2 * C + c) : 0.f;
+    is[j] = a.has_bn ? __ldg(a.coef + 3 * C + c) : 1.f;
+    const float s1 = a.sums ? __ldg(a.sums + 2 * c) : 0.f;
+    const float s2 = a.sums ? __ldg(a.sums + 2 * c + 1) : 0.f;
+    c1[j] = (a.gamma ? __ldg(a.gamma + c) : 1.f) * is[j];
+    c2[j] = s1 * inv_m;
+    c3[j] = s2 * inv_m;
+    if (blockIdx.x == 0 && threadIdx.x < groups) {
+      if (a.dbeta) a.dbeta[c] = s1;
+      if (a.dgamma) a.dgamma[c] = s2;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.dalpha) *a.dalpha = *a.dalpha_acc;
+  for (long long idx = idx0; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
     const long long m = idx / groups;
     float gv[8], xv[8], o[8];
-    ld8(g + m * g_ld + gi * 8, gv);
-    ld8(x + m * x_ld + gi * 8, xv);
-    if (g2) {
+    ld8(a.g + m * a.g_ld + gi * 8, gv);
+    ld8(a.x + m * a.x_ld + gi * 8, xv);
+    if (a.g2) {
       float t[8];
-      ld8(g2 + m * g_ld + gi * 8, t);
+      ld8(a.g2 + m * a.g_ld + gi * 8, t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] += t[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = gi * 8 + j;
-      float z = xv[j], dz = gv[j];
-      if (has_bn) z = z * __ldg(coef + c) + __ldg(coef + C + c);
-      if (act != TSR_ACT_NONE && z <= 0.f) dz *= slope;
-      if (has_bn) {
-        const float xhat = (xv[j] - __ldg(coef + 2 * C + c)) * __ldg(coef + 3 * C + c);
-        dz = __ldg(bcoef + c) * (dz - __ldg(bcoef + C + c) - xhat * __ldg(bcoef + 2 * C + c));
+      const float z = xv[j] * sc[j] + sh[j];
+      float dz = gv[j];
+      if (a.act != TSR_ACT_NONE && z <= 0.f) dz *= slope;
+      if (a.has_bn) {
+        const float xhat = (xv[j] - mu[j]) * is[j];
+        dz = c1[j] * (dz - c2[j] - xhat * c3[j]);
       }
       o[j] = dz;
     }
-    st8(dx + m * dx_ld + gi * 8, o);
+    st8(a.dx + m * a.dx_ld + gi * 8, o);
   }
 }
 
@@ -475,8 +488,9 @@ __global__ void pack_w_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
     dst[i] = __float2bfloat16(v);
   }
 }
-// UNPACK_G: same table; src = fp32 accumulator laid out [rows = cout-like][tap][cols_pad] as written by the
-// wgrad kernel, i.e. acc[(r * taps + t) * cols_pad + c]; dst = fp32 OIHW gradient (overwritten).
+// UNPACK_G: same table; src = fp32 accumulator laid out [tap][cols_pad][rows_pad] as written by the wgrad kernel
+// (rows = the dY columns, contiguous, so that its epilogue can use 16-byte vector reductions), i.e.
+// acc[(t * cols_pad + c) * rows_pad + r]; dst = fp32 OIHW gradient (overwritten).
 // For TSR_PK_T-style entries r/c are swapped by pack_index; wgrad accumulators always use the forward-like modes
 // (FWD, ROWK, ROWN, FULLK). count = rows_pad * taps * cols_pad.
 __global__ void unpack_g_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
@@ -490,47 +504,47 @@ __global__ void unpack_g_kernel(const tsr_pack_entry_t* __restrict__ tab, int n)
   for (int k = 0; k < 4; ++k) {
     const long long i = base + k * 256 + threadIdx.x;
     if (i >= e.count) continue;
-    const int c = static_cast<int>(i % e.cols_pad);
-    const long long rr = i / e.cols_pad;
-    const int t = static_cast<int>(rr % taps);
-    const int r = static_cast<int>(rr / taps);
+    const int r = static_cast<int>(i % e.rows_pad);
+    const long long rr = i / e.rows_pad;
+    const int c = static_cast<int>(rr % e.cols_pad);
+    const int t = static_cast<int>(rr / e.cols_pad);
+    (void)taps;
     const PackIdx o = pack_index(e, t, r, c);
     if (o.valid) dst[((static_cast<long long>(o.co) * e.cin + o.ci) * e.kh + o.kh) * e.kw + o.kw] = src[i];
   }
 }
 
 // ---------------------------------------------------------------------------------------------- Linear wgrad
-// p0 = dpre fp32 [B][Nf] (gradient wrt pre-activation of the Linear), p1 = X bf16 [B][K] in (h,w,c) order,
-// p2 = dW fp32 [Nf][K] in the parameter's (c,h,w) order, p3 = db fp32 [Nf]
-// i: 0 B, 1 Nf, 2 K, 3 C, 4 HW (K = C*HW)
-__global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ dpre, const bf16* __restrict__ X,
+// p0 = dpre fp32 [B][Nf] (gradient wrt pre-activation of the Linear), p1 = X fp32 [B][K] in the parameter's (c,h,w)
+// column order (the NHWC2NCHW kernel produces it), p2 = dW fp32 [Nf][K], p3 = db fp32 [Nf]
+// i: 0 B, 1 Nf, 2 K
+// Block = 256 consecutive columns x 16 output features: every global access is coalesced; HBM-bound on the dW write.
+constexpr int kLwF = 16;
+__global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ X,
                                                            float* __restrict__ dW, float* __restrict__ db, int B,
-                                                           int Nf, int K, int C, int HW) {
-  // block: 8 output features x 256*? columns; each thread one column k (param order), loops over 8 features
-  extern __shared__ float sd[];  // [8][B]
-  const int n0 = blockIdx.y * 8;
-  for (int i = threadIdx.x; i < 8 * B; i += 256) {
+                                                           int Nf, int K) {
+  extern __shared__ float sd[];  // [kLwF][B]
+  const int n0 = blockIdx.y * kLwF;
+  for (int i = threadIdx.x; i < kLwF * B; i += 256) {
     const int f = i / B, b = i % B;
     sd[i] = (n0 + f < Nf) ? dpre[static_cast<long long>(b) * Nf + n0 + f] : 0.f;
   }
   __syncthreads();
   const int k = blockIdx.x * 256 + threadIdx.x;
   if (k < K) {
-    const int c = k / HW, hw = k % HW;
-    const int kp = hw * C + c;
-    float acc[8];
+    float acc[kLwF];
 #pragma unroll
-    for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+    for (int f = 0; f < kLwF; ++f) acc[f] = 0.f;
     for (int b = 0; b < B; ++b) {
-      const float xv = __bfloat162float(X[static_cast<long long>(b) * K + kp]);
+      const float xv = __ldg(X + static_cast<long long>(b) * K + k);
 #pragma unroll
-      for (int f = 0; f < 8; ++f) acc[f] += sd[f * B + b] * xv;
+      for (int f = 0; f < kLwF; ++f) acc[f] += sd[f * B + b] * xv;
     }
 #pragma unroll
-    for (int f = 0; f < 8; ++f)
+    for (int f = 0; f < kLwF; ++f)
       if (n0 + f < Nf) dW[static_cast<long long>(n0 + f) * K + k] = acc[f];
   }
-  if (blockIdx.x == 0 && db && threadIdx.x < 8 && n0 + threadIdx.x < Nf) {
+  if (blockIdx.x == 0 && db && threadIdx.x < kLwF && n0 + threadIdx.x < Nf) {
     float t = 0.f;
     for (int b = 0; b < B; ++b) t += sd[threadIdx.x * B + b];
     db[n0 + threadIdx.x] = t;
@@ -824,20 +838,17 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
       nhwc2nchw_kernel<<<grid_for(i[0] * (i[1] / 8) * i[2] * i[3]), 256, 0, st>>>((const bf16*)p[0], (float*)p[1], i[0],
                                                                                i[1], i[2], i[3], i[4], i[5], i[6]);
       break;
-    case TSR_E_BN_FINALIZE:
-      bn_finalize_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[0], (const float*)p[1], (const float*)p[2],
-                                                            (float*)p[3], (float*)p[4], (long long*)p[5], (float*)p[6],
-                                                            i[0], i[1], i[2], i[3], i[4], d.f[0], d.f[1]);
+    case TSR_E_BN_ACT: {
+      BnActArgs a;
+      a.x = (const bf16*)p[0]; a.stats = (const float*)p[1]; a.y = (bf16*)p[2]; a.res = (const bf16*)p[3];
+      a.alpha = (const float*)p[4]; a.gamma = (const float*)p[5]; a.beta = (const float*)p[6]; a.rm = (float*)p[7];
+      a.rv = (float*)p[8]; a.nbt = (long long*)p[9]; a.coef = (float*)p[10];
+      a.M = i[0]; a.C = i[1]; a.x_ld = i[2]; a.y_ld = i[3]; a.res_ld = i[4]; a.act = i[5]; a.x_off = i[6];
+      a.y_off = i[7]; a.res_off = i[8]; a.mode = i[9]; a.count = i[10];
+      a.leaky = d.f[0]; a.res_scale = d.f[1]; a.x_scale = d.f[2]; a.eps = d.f[3]; a.momentum = d.f[4];
+      bn_act_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>(a);
       break;
-    case TSR_E_BN_EVAL_COEF:
-      bn_eval_coef_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[1], (const float*)p[2], (const float*)p[3],
-                                                             (const float*)p[4], (float*)p[6], i[1], d.f[0]);
-      break;
-    case TSR_E_BN_ACT:
-      bn_act_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>((const bf16*)p[0], (const float*)p[1], (bf16*)p[2],
-                                                              (const bf16*)p[3], (const float*)p[4], i[0], i[1], i[2],
-                                                              i[3], i[4], i[5], i[6], i[7], i[8], d.f[0], d.f[1], d.f[2]);
-      break;
+    }
     case TSR_E_BN_BWD_REDUCE: {
       const int C = i[1];
       const int lanes = 256 / (C / 8);
@@ -848,18 +859,16 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
                                                     i[0], C, i[2], i[3], i[4], i[5], i[6], d.f[0]);
       break;
     }
-    case TSR_E_BN_BWD_FINALIZE:
-      bn_bwd_finalize_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[0], (const float*)p[1],
-                                                                (const float*)p[2], (const float*)p[3], (float*)p[4],
-                                                                (float*)p[5], (float*)p[6], (float*)p[7], i[0], i[1],
-                                                                i[2], i[3], i[4]);
+    case TSR_E_BN_BWD_APPLY: {
+      BnBwdApplyArgs a;
+      a.g = (const bf16*)p[0]; a.x = (const bf16*)p[1]; a.coef = (const float*)p[2]; a.sums = (const float*)p[3];
+      a.alpha = (const float*)p[4]; a.dx = (bf16*)p[5]; a.g2 = (const bf16*)p[6]; a.gamma = (const float*)p[7];
+      a.dgamma = (float*)p[8]; a.dbeta = (float*)p[9]; a.dalpha = (float*)p[10]; a.dalpha_acc = (const float*)p[11];
+      a.M = i[0]; a.C = i[1]; a.act = i[2]; a.g_ld = i[3]; a.x_ld = i[4]; a.dx_ld = i[5]; a.has_bn = i[6];
+      a.leaky = d.f[0];
+      bn_bwd_apply_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>(a);
       break;
-    case TSR_E_BN_BWD_APPLY:
-      bn_bwd_apply_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>((const bf16*)p[0], (const bf16*)p[1],
-                                                                    (const float*)p[2], (const float*)p[3],
-                                                                    (const float*)p[4], (bf16*)p[5], (const bf16*)p[6],
-                                                                    i[0], i[1], i[2], i[3], i[4], i[5], i[6], d.f[0]);
-      break;
+    }
     case TSR_E_COLSUM_FINALIZE:
       colsum_finalize_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3],
                                                                 i[4]);
@@ -874,10 +883,9 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
       unpack_g_kernel<<<static_cast<unsigned>(i[1]), 256, 0, st>>>((const tsr_pack_entry_t*)p[0], i[0]);
       break;
     case TSR_E_LINEAR_WGRAD: {
-      dim3 grid((i[2] + 255) / 256, (i[1] + 7) / 8);
-      linear_wgrad_kernel<<<grid, 256, 8 * i[0] * sizeof(float), st>>>((const float*)p[0], (const bf16*)p[1],
-                                                                      (float*)p[2], (float*)p[3], i[0], i[1], i[2], i[3],
-                                                                      i[4]);
+      dim3 grid((i[2] + 255) / 256, (i[1] + kLwF - 1) / kLwF);
+      linear_wgrad_kernel<<<grid, 256, kLwF * i[0] * sizeof(float), st>>>((const float*)p[0], (const float*)p[1],
+                                                                         (float*)p[2], (float*)p[3], i[0], i[1], i[2]);
       break;
     }
     case TSR_E_LOSS:

@@ -148,6 +148,17 @@ __device__ __forceinline__ uint32_t layout_type_for_row_bytes(int row_bytes) {
   return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
 }
 
+// One lane of a converged warp (the same lane every time); the others get false.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -1,0 +1,96 @@
+"""Data-parallel plumbing: one process per GPU, gradients averaged with NCCL over NVLink.
+
+Replaces the DistributedDataParallel wrappers of the reference (torchsr/srgan/trainer.py:143-157, torchsr.py:257-258):
+  * attach(): parameters (and buffers) are broadcast from rank 0 once - mandatory, ranks are seeded differently
+    (torchsr.py:152-153);
+  * every backward of an attached module all-reduces its flat fp32 gradient in buckets, each launched asynchronously
+    as soon as the backward launch list has produced it, so the transfer of the discriminator's 75 MB classifier
+    gradient (produced first) overlaps the whole convolutional backward;
+  * BatchNorm statistics stay local to each rank (the reference uses no SyncBatchNorm); with broadcast_buffers=True
+    rank 0's running statistics are re-broadcast before each training forward, as DDP does for the generator.
+"""
+import contextlib
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+class DataParallelState:
+    def __init__(self, group=None, broadcast_buffers: bool = True):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.broadcast_buffers = broadcast_buffers
+        self.pending: List = []
+
+    def allreduce_async(self, t: torch.Tensor):
+        """Average `t` over the ranks, asynchronously w.r.t. the current stream."""
+        if self.world == 1:
+            return
+        backend = dist.get_backend(self.group)
+        if backend == "nccl":
+            self.pending.append((dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
+        else:   # gloo has no AVG
+            self.pending.append((dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True), t))
+
+    def wait(self):
+        for work, t in self.pending:
+            work.wait()
+            if t is not None:
+                t.div_(self.world)
+        self.pending.clear()
+
+
+def bucket_slices(total: int, early_from: Optional[int], max_elems: int = 32 * 1024 * 1024) -> List[Tuple[int, int]]:
+    """Splits the flat gradient [0, total) into buckets: the tail [early_from, total) first (it is produced first in
+    backward), then the head; each piece capped at max_elems elements so that one bucket is at most 128 MB."""
+    out: List[Tuple[int, int]] = []
+
+    def split(lo, hi):
+        while lo < hi:
+            step = min(max_elems, hi - lo)
+            out.append((lo, lo + step))
+            lo += step
+
+    if early_from is not None and 0 < early_from < total:
+        split(early_from, total)
+        split(0, early_from)
+    else:
+        split(0, total)
+    return out
+
+
+def attach(module, group=None, broadcast_buffers: bool = True) -> DataParallelState:
+    """Makes `module` (a torchsr_b200 drop-in module) data parallel over the default process group."""
+    if not dist.is_initialized():
+        raise RuntimeError("torchsr_b200.dist.attach needs an initialised torch.distributed process group")
+    state = DataParallelState(group, broadcast_buffers)
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    module._tsr["ddp"] = state
+    return state
+
+
+def sync_buffers(module):
+    """DDP's broadcast_buffers=True behaviour: rank 0's buffers win before a training forward."""
+    state = module._tsr.get("ddp")
+    if state is None or not state.broadcast_buffers or state.world == 1:
+        return
+    with torch.no_grad():
+        for b in module.buffers():
+            dist.broadcast(b, src=0, group=state.group)
+
+
+@contextlib.contextmanager
+def frozen(module):
+    """Runs a block with the module's parameters not requiring grad: its backward then produces only the gradient
+    w.r.t. the input (the discriminator inside the generator step, reference trainer.py:456)."""
+    params = [p for p in module.parameters() if p.requires_grad]
+    for p in params:
+        p.requires_grad_(False)
+    try:
+        yield module
+    finally:
+        for p in params:
+            p.requires_grad_(True)

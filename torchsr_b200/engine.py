@@ -22,6 +22,7 @@ from . import ops
 BF16 = torch.bfloat16
 F32 = torch.float32
 NUM_SMS = 148
+ZERO_ARENA_FLOATS = 64 * 1024
 
 
 def _round_up(v: int, m: int) -> int:
@@ -222,6 +223,13 @@ class Plan:
         self.busy = False
         self.slots: Dict[str, Act] = {}     # side-channel gradients between tape entries (skip connections)
         self.has_bn = False
+        # fp32 scratch that kernels accumulate into with red.global.add: zeroed by ONE memset at the head of the
+        # forward (BatchNorm column sums) / backward (BN-backward column sums, PReLU slope gradients) program
+        self._zarena = {"fwd": torch.zeros(ZERO_ARENA_FLOATS, dtype=F32, device=self.device),
+                        "bwd": torch.zeros(ZERO_ARENA_FLOATS, dtype=F32, device=self.device)}
+        self._zused = {"fwd": 0, "bwd": 0}
+        self._znamed: Dict[str, torch.Tensor] = {}
+        self.fwd.add(ops.elt(L.E_ZERO, p=[self._zarena["fwd"]], i=[ZERO_ARENA_FLOATS * 4]))
         self.post_backward: List[Callable] = []
         self.input_fn = self.output_fn = self.ingest_fn = self.grad_input_fn = None
         self.last_g: Dict[tuple, Optional[Act]] = {}
@@ -235,6 +243,17 @@ class Plan:
         t = (torch.zeros if zero else torch.empty)(max(int(numel), 8), dtype=dtype, device=self.device)
         self.bufs[name] = t
         return t
+
+    def zbuf(self, which: str, name: str, numel: int) -> torch.Tensor:
+        """`numel` floats inside the forward / backward zero arena (stable across program rebuilds)."""
+        key = which + ":" + name
+        if key not in self._znamed:
+            n = _round_up(numel, 4)
+            if self._zused[which] + n > ZERO_ARENA_FLOATS:
+                raise RuntimeError("torchsr_b200: zero arena exhausted")
+            self._znamed[key] = self._zarena[which][self._zused[which]:self._zused[which] + n]
+            self._zused[which] += n
+        return self._znamed[key]
 
     def act(self, name: str, B, H, W, C, dtype=BF16, zero=False) -> Act:
         return Act(self.buf(name, B * H * W * C, dtype, zero), B, H, W, C)
@@ -262,65 +281,73 @@ class Plan:
             kw.update(res=res.t, aux=res.strides())
         if shuffle_out:
             kw.update(out_mode=L.OUT_SHUFFLE, shuf_c=rec.cout // 4)
-        return self.conv(prog, x, rec.w_fwd, rec.cols, rec.slots, geom, rec.cout_pad, rec.block_n, out.t, out.strides(),
+        block_n = self.pick_block_n(x.B * geom["Ho"] * geom["Wo"], rec.cout_pad, rec.block_n)
+        return self.conv(prog, x, rec.w_fwd, rec.cols, rec.slots, geom, rec.cout_pad, block_n, out.t, out.strides(),
                          rec.cout_pad, **kw)
 
+    @staticmethod
+    def pick_block_n(M: int, n_total: int, block_n: int) -> int:
+        """Halve the N tile while the grid cannot cover the SMs: these layers are bound by per-SM L2->smem bandwidth
+        and per-CTA latency, so more, narrower CTAs win even though the A tile is then fetched once per N tile."""
+        tiles_m = (M + 127) // 128
+        while block_n >= 64 and block_n % 32 == 0 and tiles_m * (n_total // block_n) * 2 <= NUM_SMS + 20:
+            block_n //= 2
+        return block_n
+
     def stats_buf(self, name: str, M: int, cout_pad: int) -> torch.Tensor:
-        return self.buf(name, ((M + 127) // 128) * cout_pad * 2, F32)
+        return self.zbuf("fwd", name, cout_pad * 2)
 
-    def bn_coef(self, prog, name: str, bn: nn.BatchNorm2d, stats: Optional[torch.Tensor], M: int, ld: int):
-        """Per-channel (scale, shift, mean, invstd): from the conv epilogue's batch statistics in training mode
-        (also updates running_mean / running_var / num_batches_tracked), from the running estimates in eval mode."""
-        C = bn.num_features
-        coef = self.buf(name, 4 * C, F32)
-        if self.training:
-            tiles = (M + 127) // 128
-            prog.add(ops.elt(L.E_BN_FINALIZE, p=[stats, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                                 bn.num_batches_tracked, coef],
-                             i=[tiles, C, M, 1, ld], f=[bn.eps, bn.momentum]))
-        else:
-            prog.add(ops.elt(L.E_BN_EVAL_COEF, p=[None, bn.weight, bn.bias, bn.running_mean, bn.running_var, None, coef],
-                             i=[0, C], f=[bn.eps]))
-        return coef
-
-    def bn_act(self, prog, x: Act, coef, y: Act, act=L.ACT_NONE, alpha=None, res: Optional[Act] = None,
+    def bn_act(self, prog, name: str, x: Act, y: Act, *, bn: Optional[nn.BatchNorm2d] = None,
+               stats: Optional[torch.Tensor] = None, act=L.ACT_NONE, alpha=None, res: Optional[Act] = None,
                leaky=0.2, res_scale=1.0, x_scale=1.0):
-        prog.add(ops.elt(L.E_BN_ACT, p=[x.t, coef, y.t, res.t if res is not None else None, alpha],
-                         i=[x.M, x.C, x.ld, y.ld, res.ld if res is not None else 0, act, x.c0, y.c0,
-                            res.c0 if res is not None else 0],
-                         f=[leaky, res_scale, x_scale]))
+        """y = act(BN(x)) + res in one pass. Training mode: the batch statistics come from the conv epilogue's column
+        sums (`stats`); the same launch publishes (scale, shift, mean, invstd) for backward and updates running_mean /
+        running_var / num_batches_tracked. Eval mode: running statistics. Returns the coefficient buffer (or None)."""
+        C = x.C
+        coef = None
+        if bn is None:
+            mode, p_bn = 0, [None] * 6
+            eps = mom = 0.0
+        else:
+            coef = self.buf(name + ".coef", 4 * C, F32)
+            mode = 1 if self.training else 2
+            p_bn = [bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, coef]
+            eps, mom = bn.eps, (bn.momentum if bn.momentum is not None else 0.1)
+        prog.add(ops.elt(L.E_BN_ACT, p=[x.t, stats if mode == 1 else None, y.t, res.t if res is not None else None,
+                                        alpha] + p_bn,
+                         i=[x.M, C, x.ld, y.ld, res.ld if res is not None else 0, act, x.c0, y.c0,
+                            res.c0 if res is not None else 0, mode, x.M],
+                         f=[leaky, res_scale, x_scale, eps, mom]))
+        return coef
 
     # ---- backward emitters
     def norm_act_bwd(self, prog, name: str, g: Act, x: Act, *, coef=None, bn: Optional[nn.BatchNorm2d] = None,
                      act=L.ACT_NONE, alpha: Optional[torch.Tensor] = None, g2: Optional[Act] = None,
                      bias_grad: Optional[torch.Tensor] = None, want_w=True, leaky=0.2) -> Act:
         """Backward of y = act(BN(x)) (bn given) or y = act(x) (bn None) for upstream gradient g (+ g2):
-        column reduction -> finalize (dgamma/dbeta/dalpha or bias gradient) -> apply. Returns d/dx as a new Act."""
+        column reduction (atomics into the zero arena) -> apply, whose block 0 also publishes dgamma / dbeta (or the
+        bias gradient) / dalpha into the flat gradient. Returns d/dx as a new Act."""
         M, C = x.M, x.C
         assert g.ld == C and x.ld == C and (g2 is None or g2.ld == C)
         has_bn = 1 if bn is not None else 0
-        rpb = max(32, -(-M // (4 * NUM_SMS)))
-        blocks = -(-M // rpb)
+        rpb = max(32, -(-M // (2 * NUM_SMS)))
         dx = self.act(name + ".dx", x.B, x.H, x.W, C)
-        need_reduce = has_bn or (want_w and (alpha is not None or bias_grad is not None))
+        prelu = act == L.ACT_PRELU
+        need_reduce = has_bn or (want_w and (prelu or bias_grad is not None))
         store = self.store
+        sums = dacc = None
         if need_reduce:
-            partial = self.buf(name + ".bpart", blocks * C * 2, F32)
-            dap = self.buf(name + ".dap", blocks, F32) if act == L.ACT_PRELU else None
-            prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, x.t, coef, alpha if act == L.ACT_PRELU else None, partial, dap,
+            sums = self.zbuf("bwd", name + ".sums", 2 * C)
+            dacc = self.zbuf("bwd", name + ".dalpha", 1) if prelu else None
+            prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, x.t, coef, alpha if prelu else None, sums, dacc,
                                                    g2.t if g2 is not None else None],
                              i=[M, C, act, rpb, C, C, has_bn], f=[leaky]))
-            bcoef = self.buf(name + ".bcoef", 3 * C, F32) if has_bn else None
-            dgamma = store.grad_slice(bn.weight) if has_bn and want_w else None
-            dbeta = store.grad_slice(bn.bias) if has_bn and want_w else (bias_grad if want_w else None)
-            dalpha = store.grad_slice(alpha) if (act == L.ACT_PRELU and want_w) else None
-            prog.add(ops.elt(L.E_BN_BWD_FINALIZE, p=[partial, dap, coef, bn.weight if has_bn else None, bcoef, dgamma,
-                                                     dbeta, dalpha],
-                             i=[blocks, C, M, blocks if dap is not None else 0, 0]))
-        else:
-            bcoef = None
-        prog.add(ops.elt(L.E_BN_BWD_APPLY, p=[g.t, x.t, coef, bcoef, alpha if act == L.ACT_PRELU else None, dx.t,
-                                              g2.t if g2 is not None else None],
+        dgamma = store.grad_slice(bn.weight) if has_bn and want_w else None
+        dbeta = (store.grad_slice(bn.bias) if has_bn else bias_grad) if want_w else None
+        dalpha = store.grad_slice(alpha) if (prelu and want_w) else None
+        prog.add(ops.elt(L.E_BN_BWD_APPLY, p=[g.t, x.t, coef, sums, alpha if prelu else None, dx.t,
+                                              g2.t if g2 is not None else None, bn.weight if has_bn else None, dgamma,
+                                              dbeta, dalpha, dacc],
                          i=[M, C, act, C, C, C, has_bn], f=[leaky]))
         return dx
 
@@ -350,6 +377,8 @@ class Plan:
             n_out, n_slots = rec.t_rows, 1
             geom = ops.fwd_geometry(dy.H, dy.W, 1, 1, 0, 0, 1)
         block_n = next(b for b in (128, 96, 64, 160, 192, 32, 16) if n_out % b == 0 and b <= n_out)
+        if rec.stride == 1:
+            block_n = self.pick_block_n(dy.M, n_out, block_n)
         dx = self.act(name + ".dgrad", x_like.B, x_like.H, x_like.W, n_out, F32 if out_f32 else BF16) \
             if (hook is None or hook.get("unshuffle_to") is None) else None
         if hook is not None and hook.get("unshuffle_to") is not None:
@@ -371,19 +400,18 @@ class Plan:
     def colsum(self, prog, name: str, g: Act, out_vec: torch.Tensor):
         """out_vec[c] = sum over rows of g[:, c] (bias gradients)."""
         M, C = g.M, g.C
-        rpb = max(32, -(-M // (4 * NUM_SMS)))
-        blocks = -(-M // rpb)
-        partial = self.buf(name + ".cspart", blocks * C * 2, F32)
-        prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, g.t, None, None, partial, None, None],
+        rpb = max(32, -(-M // (2 * NUM_SMS)))
+        sums = self.zbuf("bwd", name + ".cs", 2 * C)
+        prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, g.t, None, None, sums, None, None],
                          i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2]))
-        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[partial, out_vec], i=[blocks, C, C, 0, 0]))
+        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0]))
 
-    def conv_wgrad(self, prog, rec: ConvRec, x: Act, dy: Act, geom: Optional[dict] = None, cout_valid=None):
+    def conv_wgrad(self, prog, rec: ConvRec, x: Act, dy: Act, geom: Optional[dict] = None):
         geom = geom or ops.fwd_geometry(x.H, x.W, rec.k, rec.k, rec.pad, rec.pad, rec.stride)
         block_n = dy.C if dy.C <= 128 else 128
+        assert dy.C == rec.acc_rows, (rec.name, dy.C, rec.acc_rows)
         d = ops.wgrad_desc(x=x.t, N=x.B, H=x.H, W=x.W, C=x.C + x.c0, x_ld=x.ld, geom=geom, dy=dy.t, dy_ld=dy.ld,
-                           dy_c=dy.C, out=rec.acc, cout_valid=cout_valid or rec.acc_rows, block_n=block_n, x_c0=x.c0,
-                           dy_c0=dy.c0)
+                           dy_c=dy.C, out=rec.acc, cout_valid=rec.acc_rows, block_n=block_n, x_c0=x.c0, dy_c0=dy.c0)
         prog.add(d)
 
     # ---- execution (set by the net definition: input_fn, output_fn, ingest_fn, grad_input_fn, post_backward)
@@ -392,19 +420,45 @@ class Plan:
         self.fwd.run()
         return self.output_fn()
 
-    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool):
+    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None):
         if not self.training and self.has_bn:
             raise NotImplementedError("torchsr_b200: backward through eval-mode BatchNorm is not implemented; call "
                                       ".train() for gradient computation (the reference trainers do)")
         seed = self.ingest_fn(gout)
         prog = self.backward_program(want_x, want_w, seed)
-        prog.run()
-        gx = self.grad_input_fn() if want_x else None
         flat = None
-        if want_w:
+        store = self.store
+        early = prog.marks.get("early_grads")
+        if want_w and ddp is not None and ddp.world > 1:
+            # bucketed all-reduce launched from inside backward: the tail of the flat gradient (the classifier of a
+            # discriminator) is complete after the first few launches and travels while the conv stack runs
+            from .dist import bucket_slices
+            flat = torch.empty_like(store.flat_grad)
+            early_from = self.early_from if early is not None else None
+            buckets = bucket_slices(store.total, early_from)
+            done = 0
+            if early is not None:
+                prog.run(0, early)
+                done = early
+                for lo, hi in buckets:
+                    if lo >= early_from:
+                        flat[lo:hi].copy_(store.flat_grad[lo:hi])
+                        ddp.allreduce_async(flat[lo:hi])
+            prog.run(done, -1)
             for fn in self.post_backward:
                 fn()
-            flat = self.store.flat_grad.clone()
+            for lo, hi in buckets:
+                if early is None or lo < early_from:
+                    flat[lo:hi].copy_(store.flat_grad[lo:hi])
+                    ddp.allreduce_async(flat[lo:hi])
+            ddp.wait()
+        else:
+            prog.run()
+            if want_w:
+                for fn in self.post_backward:
+                    fn()
+                flat = store.flat_grad.clone()
+        gx = self.grad_input_fn() if want_x else None
         return gx, flat
 
     # ---- programs
@@ -412,6 +466,7 @@ class Plan:
         key = (want_x, want_w)
         if key not in self.bwd:
             prog = ops.Program()
+            prog.add(ops.elt(L.E_ZERO, p=[self._zarena["bwd"]], i=[ZERO_ARENA_FLOATS * 4]))
             if want_w:
                 prog.add(ops.elt(L.E_ZERO, p=[self.store.acc_arena], i=[self.store.acc_arena.numel() * 4]))
             g = seed
@@ -467,7 +522,8 @@ class B200Module(nn.Module):
         r = super()._apply(fn, *a, **kw)
         st = self.__dict__.get("_tsr")
         if st is not None:
-            st["store"], st["plans"] = None, {}
+            st["store"] = None
+            st["plans"] = {}
         return r
 
     def _store(self) -> ParamStore:
@@ -516,6 +572,9 @@ class _PlanFn(torch.autograd.Function):
         plan = module._acquire(x.shape, module.training)
         store = plan.store
         store.ensure_packed()
+        if module.training and module._tsr.get("ddp") is not None:
+            from .dist import sync_buffers
+            sync_buffers(module)
         out = plan.run_forward(x)
         if needs_graph:
             ctx.lease = _Lease(plan)
@@ -534,7 +593,7 @@ class _PlanFn(torch.autograd.Function):
         want_x = ctx.needs_input_grad[2]
         want = list(ctx.needs_input_grad[3:])
         want_w = any(want)
-        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w)
+        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ctx.module._tsr.get("ddp"))
         grads = plan.store.grads_from_flat(flat, want) if want_w else [None] * len(want)
         lease.release()
         return (None, None, gx, *grads)

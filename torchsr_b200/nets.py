@@ -46,16 +46,14 @@ def residual_block_stage(plan: Plan, prog, name: str, blk, ra: ConvRec, rb: Conv
     raw1 = plan.act(name + ".raw1", B, H, W, C)
     s1 = plan.stats_buf(name + ".s1", M, C) if tr else None
     plan.conv_fwd(prog, ra, x, raw1, stats=s1)
-    coef1 = plan.bn_coef(prog, name + ".coef1", blk.bn1, s1, M, C)
     a1 = plan.act(name + ".a1", B, H, W, C)
     alpha = blk.prelu.weight
-    plan.bn_act(prog, raw1, coef1, a1, act=L.ACT_PRELU, alpha=alpha)
+    coef1 = plan.bn_act(prog, name + ".bn1", raw1, a1, bn=blk.bn1, stats=s1, act=L.ACT_PRELU, alpha=alpha)
     raw2 = plan.act(name + ".raw2", B, H, W, C)
     s2 = plan.stats_buf(name + ".s2", M, C) if tr else None
     plan.conv_fwd(prog, rb, a1, raw2, stats=s2)
-    coef2 = plan.bn_coef(prog, name + ".coef2", blk.bn2, s2, M, C)
     y = plan.act(name + ".y", B, H, W, C)
-    plan.bn_act(prog, raw2, coef2, y, act=L.ACT_NONE, res=x)
+    coef2 = plan.bn_act(prog, name + ".bn2", raw2, y, bn=blk.bn2, stats=s2, act=L.ACT_NONE, res=x)
 
     def bwd(bp, g, want_x, want_w):
         d2 = plan.norm_act_bwd(bp, name + ".bn2", g, raw2, coef=coef2, bn=blk.bn2, act=L.ACT_NONE, want_w=want_w)
@@ -81,14 +79,13 @@ def subpixel_stage(plan: Plan, prog, name: str, layer, rec: ConvRec, x: Act, con
     alpha = layer.prelu.weight
     plan.conv_fwd(prog, rec, x, out, act=L.ACT_PRELU, prelu=alpha, preact=pre.t, shuffle_out=True)
     dconv = plan.act(name + ".dconv", B, H, W, rec.cout)
-    n_dap = (out.M + 127) // 128
-    dap = plan.buf(name + ".dap", n_dap, F32)
+    dap = plan.zbuf("bwd", name + ".dalpha", 1)     # accumulated by the consumer's dgrad epilogue (one red per CTA)
     out.hook = dict(bwd_z=pre, bwd_act=L.ACT_PRELU, prelu=alpha, unshuffle_to=dconv, dalpha_partial=dap)
 
     def bwd(bp, g, want_x, want_w):
         assert g is dconv, "the consumer of a sub-pixel stage must honour its gradient hook"
         if want_w:
-            bp.add(ops.elt(L.E_SUM_FINALIZE, p=[dap, store.grad_slice(alpha)], i=[n_dap, 0], f=[1.0]))
+            bp.add(ops.elt(L.E_SUM_FINALIZE, p=[dap, store.grad_slice(alpha)], i=[1, 0], f=[1.0]))
             plan.colsum(bp, name + ".db", g, rec.bias_grad_packed)
             plan.conv_wgrad(bp, rec, x, g)
         return plan.conv_dgrad(bp, name, rec, g, x)
@@ -136,9 +133,8 @@ def define_srgan_generator(m, plan: Plan, shape):
     raw = plan.act("conv2.raw", B, H, W, 64)
     st = plan.stats_buf("conv2.s", raw.M, 64) if plan.training else None
     plan.conv_fwd(fwd, rc2, xt, raw, stats=st)
-    coef = plan.bn_coef(fwd, "conv2.coef", bn2, st, raw.M, 64)
     s = plan.act("trunk", B, H, W, 64)
-    plan.bn_act(fwd, raw, coef, s, act=L.ACT_NONE, res=c1)
+    coef = plan.bn_act(fwd, "conv2.bn", raw, s, bn=bn2, stats=st, act=L.ACT_NONE, res=c1)
 
     def bwd_conv2(bp, g, want_x, want_w):
         plan.slots["skip"] = g          # out = conv1 + conv2 (generator.py:79): the same gradient reaches conv1
@@ -179,7 +175,7 @@ def define_srgan_generator(m, plan: Plan, shape):
     def bwd_conv3(bp, g, want_x, want_w):
         if want_w:
             bp.add(ops.elt(L.E_COLSUM_FINALIZE, p=[cs, store.grad_slice(r3.bias)], i=[CHANSUM_SPLITS, r3.cout, r3.cout, 0, 0]))
-            plan.conv_wgrad(bp, r3, u_last, E3, geom=geom3, cout_valid=r3.k * r3.cout)
+            plan.conv_wgrad(bp, r3, u_last, E3, geom=geom3)
         return plan.conv_dgrad(bp, "conv3", r3, E3, u_last)
 
     plan.tape.append(bwd_conv3)
@@ -287,9 +283,8 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
         raw = plan.act(f"f{k}.raw", B, Ho, Wo, rk.cout)
         st = plan.stats_buf(f"f{k}.s", raw.M, rk.cout_pad) if plan.training else None
         plan.conv_fwd(fwd, rk, prev, raw, stats=st)
-        coef = plan.bn_coef(fwd, f"f{k}.coef", bn, st, raw.M, rk.cout_pad)
         a = plan.act(f"f{k}.act", B, Ho, Wo, rk.cout)
-        plan.bn_act(fwd, raw, coef, a, act=L.ACT_LEAKY)
+        coef = plan.bn_act(fwd, f"f{k}.bn", raw, a, bn=bn, stats=st, act=L.ACT_LEAKY)
 
         def bwd(bp, g, want_x, want_w, rk=rk, bn=bn, raw=raw, coef=coef, xin=prev, k=k):
             d = plan.norm_act_bwd(bp, f"f{k}", g, raw, coef=coef, bn=bn, act=L.ACT_LEAKY, want_w=want_w)
@@ -326,8 +321,12 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
         bp.add(ops.elt(L.E_HEAD_BWD, p=[gbuf, out_b, h1, lin2.weight, dpre1, dpre1_bf, dw2, db2],
                        i=[B, N1, int(sigmoid), l1.nout_pad], f=[0.2]))
         if want_w:
-            bp.add(ops.elt(L.E_LINEAR_WGRAD, p=[dpre1, flat_act.t, store.grad_slice(l1.weight), store.grad_slice(l1.bias)],
-                           i=[B, N1, K, l1.C, l1.Hf * l1.Wf]))
+            xchw = plan.buf("flat_chw", B * K, F32)     # features in the parameter's (c,h,w) column order
+            bp.add(ops.elt(L.E_NHWC2NCHW, p=[flat_act.t, xchw], i=[B, l1.C, l1.Hf, l1.Wf, flat_act.ld, flat_act.c0, 0]))
+            bp.add(ops.elt(L.E_LINEAR_WGRAD, p=[dpre1, xchw, store.grad_slice(l1.weight), store.grad_slice(l1.bias)],
+                           i=[B, N1, K]))
+            bp.mark("early_grads")     # everything from classifier.0.weight to the end of the flat gradient is final
+            plan.early_from = store.offsets[id(l1.weight)]
         dflat32 = plan.buf("dflat32", Bpad * K, F32)
         bp.add(ops.elt(L.E_ZERO, p=[dflat32], i=[Bpad * K * 4]))
         bn_ = next(b for b in (128, 64, 32, 16) if Bpad % b == 0)

@@ -254,13 +254,12 @@ def validate_conv(d: ConvDesc):
     _need("conv w", d.w, d.w_rows * d.w_ld * 2)
     if d.bias:
         _need("conv bias", d.bias, d.cout_pad * 4)
-    tiles_m = (M + 127) // 128
     if d.stats_partial:
         if d.stats_ld < d.cout_pad:
             raise ExtentError("conv stats_ld smaller than cout_pad")
-        _need("conv stats_partial", d.stats_partial, tiles_m * d.stats_ld * 2 * 4)
+        _need("conv stats_partial", d.stats_partial, d.stats_ld * 2 * 4)
     if d.dalpha_partial:
-        _need("conv dalpha_partial", d.dalpha_partial, tiles_m * (d.cout_pad // d.block_n) * 4)
+        _need("conv dalpha_partial", d.dalpha_partial, 4)
     if d.n_valid % 16 or d.n_valid > d.cout_pad:
         raise ExtentError("conv n_valid must be a multiple of 16 and <= cout_pad")
     for off in (d.out_ch_off, d.aux_ch_off):
@@ -282,8 +281,8 @@ def validate_wgrad(d: WgradDesc):
     _need("wgrad x", d.x, ((d.N * d.H * d.W - 1) * d.x_ld + d.C) * 2)
     _need("wgrad dy", d.dy, ((M - 1) * d.dy_ld + d.dy_c0 + d.dy_c) * 2)
     _need("wgrad out", d.out, d.cout_valid * d.num_taps * (d.C - d.x_c0) * 4)
-    if d.cout_valid > d.dy_c:
-        raise ExtentError("wgrad cout_valid exceeds the dY channels visible")
+    if d.cout_valid % 16:
+        raise ExtentError("wgrad cout_valid (accumulator row width) must be a multiple of 16")
 
 
 def _elt_extents(d: EltDesc):
@@ -297,34 +296,32 @@ def _elt_extents(d: EltDesc):
         return [(0, i[0] * i[1] * i[2] * i[3] * 4), (1, ((i[0] * i[2] * i[3] - 1) * i[4] + i[5] + i[1]) * 2)]
     if k == L.E_NHWC2NCHW:
         return [(0, ((i[0] * i[2] * i[3] - 1) * i[4] + i[5] + i[1]) * 2), (1, i[0] * i[1] * i[2] * i[3] * 4)]
-    if k == L.E_BN_FINALIZE:
-        C = i[1]
-        return [(0, i[0] * i[4] * 8), (1, C * 4), (2, C * 4), (3, C * 4), (4, C * 4), (5, 8), (6, 4 * C * 4)]
-    if k == L.E_BN_EVAL_COEF:
-        C = i[1]
-        return [(1, C * 4), (2, C * 4), (3, C * 4), (4, C * 4), (6, 4 * C * 4)]
+    if k in (L.E_BN_FINALIZE, L.E_BN_EVAL_COEF, L.E_BN_BWD_FINALIZE):
+        raise ExtentError("kernel kind retired: the finalize steps are fused into BN_ACT / BN_BWD_APPLY")
     if k == L.E_BN_ACT:
         M, C = i[0], i[1]
+        if 256 % (C // 8) or C % 8:
+            raise ExtentError("BN_ACT needs C/8 to divide 256")
         return [(0, ((M - 1) * i[2] + i[6] + C) * 2), (1, 2 * C * 4), (2, ((M - 1) * i[3] + i[7] + C) * 2),
-                (3, ((M - 1) * i[4] + i[8] + C) * 2), (4, 4)]
+                (3, ((M - 1) * i[4] + i[8] + C) * 2), (4, 4), (5, C * 4), (6, C * 4), (7, C * 4), (8, C * 4), (9, 8),
+                (10, 4 * C * 4)]
     if k == L.E_BN_BWD_REDUCE:
         M, C = i[0], i[1]
-        blocks = (M + i[3] - 1) // i[3]
         return [(0, ((M - 1) * i[4] + C) * 2), (1, ((M - 1) * i[5] + C) * 2), (2, 4 * C * 4 if i[6] else 0), (3, 4),
-                (4, blocks * C * 8), (5, blocks * 4), (6, ((M - 1) * i[4] + C) * 2)]
-    if k == L.E_BN_BWD_FINALIZE:
-        C = i[1]
-        return [(0, i[0] * C * 8), (1, i[3] * 4), (2, 4 * C * 4), (3, C * 4), (4, 3 * C * 4), (5, C * 4), (6, C * 4), (7, 4)]
+                (4, C * 8), (5, 4), (6, ((M - 1) * i[4] + C) * 2)]
     if k == L.E_BN_BWD_APPLY:
         M, C = i[0], i[1]
+        if 256 % (C // 8) or C % 8:
+            raise ExtentError("BN_BWD_APPLY needs C/8 to divide 256")
         return [(0, ((M - 1) * i[3] + C) * 2), (1, ((M - 1) * i[4] + C) * 2), (2, 4 * C * 4 if i[6] else 0),
-                (3, 3 * C * 4 if i[6] else 0), (4, 4), (5, ((M - 1) * i[5] + C) * 2), (6, ((M - 1) * i[3] + C) * 2)]
+                (3, C * 8), (4, 4), (5, ((M - 1) * i[5] + C) * 2), (6, ((M - 1) * i[3] + C) * 2), (7, C * 4),
+                (8, C * 4), (9, C * 4), (10, 4), (11, 4)]
     if k == L.E_COLSUM_FINALIZE:
         return [(0, i[0] * i[2] * 8), (1, i[1] * 4)]
     if k == L.E_SUM_FINALIZE:
         return [(0, i[0] * 4), (1, 4)]
     if k == L.E_LINEAR_WGRAD:
-        return [(0, i[0] * i[1] * 4), (1, i[0] * i[2] * 2), (2, i[1] * i[2] * 4), (3, i[1] * 4)]
+        return [(0, i[0] * i[1] * 4), (1, i[0] * i[2] * 4), (2, i[1] * i[2] * 4), (3, i[1] * 4)]
     if k == L.E_LOSS:
         return [(0, i[0] * 4), (1, i[0] * 4), (2, i[2] * 4), (3, i[0] * 4)]
     if k == L.E_ZERO:

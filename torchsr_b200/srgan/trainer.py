@@ -1,0 +1,216 @@
+"""SRGAN training loop - mirror of the hot parts of torchsr/srgan/trainer.py.
+
+Same class name, constructor signature, attribute and method names as the reference's SRGANTrainer for the parts
+that sit on the hot path: model/loss/optimizer construction (reference :136-196), the pretrain step (:376-388), the
+GAN step `_gan_loop` (:416-469), evaluation `_test` (:260-343) and the checkpoint format (:254-258, :321-327).
+Differences, all math-identical:
+  * the generator step runs the discriminator with its parameters frozen, so the weight gradients the reference
+    computes, all-reduces and then discards at the next `discriminator.zero_grad()` are never computed;
+  * data-parallel gradient averaging is done by torchsr_b200.dist (bucketed NCCL all-reduce of the flat gradient
+    launched from inside backward) instead of torch DDP wrappers; BatchNorm statistics stay local to each GPU, as
+    in the reference (no SyncBatchNorm).
+"""
+import os
+import time
+from argparse import Namespace
+from math import log10
+from typing import Optional
+
+import torch
+from torch import Tensor, nn, optim
+
+from .. import dist as tdist
+from .discriminator import Discriminator
+from .generator import Generator
+from .loss import VGGLoss
+
+
+class SRGANTrainer:
+    def __init__(self, device, args: Namespace, train_loader, test_loader, train_len: int, test_len: int,
+                 distributed: bool = False) -> None:
+        self.amp = not args.disable_amp
+        self.batch_size = args.batch_size
+        self.best_psnr = -1.0
+        self.device = torch.device(device)
+        self.distributed = distributed
+        self.epochs = args.epochs
+        self.gan_checkpoint = args.gan_checkpoint
+        self.local_rank = args.local_rank
+        self.pre_epochs = args.pretrain_epochs
+        self.psnr_checkpoint = args.psnr_checkpoint
+        self.save_image = not args.skip_image_save
+        self.test_loader, self.test_len = test_loader, test_len
+        self.train_loader, self.train_len = train_loader, train_len
+        self.world_size = args.world_size
+        self.main_process = args.rank in [-1, 0]
+        if self.device.type == 'cuda' and args.local_rank is not None and args.local_rank >= 0:
+            torch.cuda.set_device(args.local_rank)
+            self.device = torch.device('cuda', args.local_rank)
+        if self.save_image and self.main_process and not os.path.exists('output'):
+            os.makedirs('output')
+        self._initialize_trainer()
+        self._create_test_image()
+
+    # ------------------------------------------------------------------ construction (reference :136-205)
+    def _initialize_models(self) -> None:
+        self.generator = Generator().to(self.device)
+        self.discriminator = Discriminator().to(self.device)
+        if self.distributed:
+            # reference :143-157 wraps both in DistributedDataParallel; here: broadcast from rank 0 once, then the
+            # modules all-reduce their own flat gradients (torchsr_b200/dist.py)
+            tdist.attach(self.generator, broadcast_buffers=True)
+            tdist.attach(self.discriminator, broadcast_buffers=False)
+
+    def _initialize_loss(self) -> None:
+        self.mse_loss = nn.MSELoss().to(self.device)
+        self.bce_loss = nn.BCELoss().to(self.device)
+        self.vgg_loss = VGGLoss().to(self.device)
+
+    def _initialize_optimizers(self) -> None:
+        fused = self.device.type == 'cuda'
+        mk = lambda params: optim.Adam(params, lr=0.0001, betas=(0.9, 0.999), fused=fused)  # noqa: E731
+        self.psnr_optimizer = mk(self.generator.parameters())
+        self.disc_optimizer = mk(self.discriminator.parameters())
+        self.gen_optimizer = mk(self.generator.parameters())
+        step = max(1, self.epochs // 8)   # reference :188 divides by zero for --epochs < 8
+        self.disc_scheduler = optim.lr_scheduler.StepLR(self.disc_optimizer, step_size=step, gamma=0.6)
+        self.gen_scheduler = optim.lr_scheduler.StepLR(self.gen_optimizer, step_size=step, gamma=0.6)
+
+    def _initialize_trainer(self) -> None:
+        self._initialize_models()
+        self._initialize_loss()
+        self._initialize_optimizers()
+
+    def _create_test_image(self) -> None:
+        self.test_image = None
+        path = 'media/waterfalls-low-res.png'
+        if self.save_image and os.path.exists(path):
+            from PIL import Image
+            from torchvision.transforms import ToTensor
+            self.test_image = ToTensor()(Image.open(path).convert('RGB')).unsqueeze(0).to(self.device)
+
+    def _log(self, statement: str) -> None:
+        if self.main_process:
+            print(statement)
+
+    # ------------------------------------------------------------------ steps
+    def _pretrain_step(self, low_res: Tensor, high_res: Tensor) -> Tensor:
+        """One PSNR-phase step (reference :376-388): G forward, MSE, backward, Adam. The reference wraps this in fp16
+        autocast + GradScaler; the kernels here compute in bf16 with fp32 accumulation, which needs no loss scaling."""
+        low_res = low_res.to(self.device, non_blocking=True)
+        high_res = high_res.to(self.device, non_blocking=True)
+        self.psnr_optimizer.zero_grad()
+        super_res = self.generator(low_res)
+        loss = self.mse_loss(super_res, high_res)
+        loss.backward()
+        self.psnr_optimizer.step()
+        return loss.detach()
+
+    def _gan_loop(self, low_res: Tensor, high_res: Tensor, step: int) -> Tensor:
+        """One GAN step, statement for statement the reference's `_gan_loop` (:435-469)."""
+        low_res = low_res.to(self.device, non_blocking=True)
+        high_res = high_res.to(self.device, non_blocking=True)
+        batch_size = low_res.size(0)
+        real_label = torch.full((batch_size, 1), 1, dtype=low_res.dtype, device=self.device)
+        fake_label = torch.full((batch_size, 1), 0, dtype=low_res.dtype, device=self.device)
+
+        self.discriminator.zero_grad()
+        super_res = self.generator(low_res)
+        disc_loss_real = self.bce_loss(self.discriminator(high_res), real_label)
+        disc_loss_fake = self.bce_loss(self.discriminator(super_res.detach()), fake_label)
+        disc_loss = disc_loss_real + disc_loss_fake
+        disc_loss.backward()
+        self.disc_optimizer.step()
+
+        self.generator.zero_grad()
+        content_loss = self.vgg_loss(super_res, high_res.detach())
+        with tdist.frozen(self.discriminator):
+            adversarial_loss = self.bce_loss(self.discriminator(super_res), real_label)
+        gen_loss = content_loss + 0.001 * adversarial_loss
+        gen_loss.backward()
+        self.gen_optimizer.step()
+        return gen_loss.detach()
+
+    # ------------------------------------------------------------------ evaluation / checkpoints
+    def _model_state(self, epoch: int, phase: str) -> dict:
+        return {"epoch": epoch, "phase": phase, "state": self.generator.state_dict()}
+
+    def _test(self, epoch: int, phase: str, step: int) -> float:
+        """Eval-mode, no-grad pass over the test loader: PSNR = 10 log10(1 / mse) per batch (reference :282-303)."""
+        self.generator.eval()
+        psnr, n = 0.0, 0
+        with torch.no_grad():
+            for low_res, _, high_res in self.test_loader:
+                super_res = self.generator(low_res.to(self.device))
+                psnr += 10 * log10(1 / ((super_res - high_res.to(self.device)) ** 2).mean().item())
+                n += 1
+        psnr = psnr / max(n, 1)
+        self._log(f'PSNR: {round(psnr, 3)}')
+        if self.main_process:
+            if psnr > self.best_psnr:
+                self.best_psnr = psnr
+                torch.save(self._model_state(epoch, phase), f'{phase}-best.pth')
+            torch.save(self._model_state(epoch, phase), f'{phase}-latest.pth')
+            if self.save_image and self.test_image is not None:
+                from torchvision import utils
+                utils.save_image(self.generator(self.test_image), f'output/SR_epoch{epoch}.png', padding=5)
+        self.generator.train()
+        return psnr
+
+    def _load_checkpoint(self, path: Optional[str]):
+        if path and os.path.exists(path):
+            return torch.load(path, map_location=self.device)
+        return None
+
+    def _restore(self, *paths) -> bool:
+        for p in paths:
+            ck = self._load_checkpoint(p)
+            if ck is not None:
+                state = ck["state"] if "state" in ck else ck
+                state = {k[len('module.'):] if k.startswith('module.') else k: v for k, v in state.items()}
+                self.generator.load_state_dict(state)
+                return True
+        return False
+
+    def _pretrain(self) -> None:
+        self.best_psnr = -1.0
+        self._restore(self.psnr_checkpoint, 'srgan-psnr-latest.pth')
+        step = 0
+        for epoch in range(1, self.pre_epochs + 1):
+            self._log(f'Starting epoch {epoch} out of {self.pre_epochs}')
+            t0 = time.time()
+            seen = 0
+            for low_res, high_res in self.train_loader:
+                self._pretrain_step(low_res, high_res)
+                seen += low_res.size(0)
+                step += 1
+            if self.device.type == 'cuda':
+                torch.cuda.synchronize()
+            self._log(f'Throughput: {round(seen * max(self.world_size, 1) / (time.time() - t0), 3)} images/sec')
+            self._test(epoch, 'srgan-psnr', step)
+
+    def _gan_train(self) -> None:
+        self.best_psnr = -1.0
+        if not self._restore(self.gan_checkpoint, 'srgan-gan-latest.pth'):
+            self._restore('srgan-psnr-latest.pth')
+        step = 0
+        for epoch in range(1, self.epochs + 1):
+            self._log(f'Starting epoch {epoch} out of {self.epochs}')
+            t0 = time.time()
+            seen = 0
+            for low_res, high_res in self.train_loader:
+                self._gan_loop(low_res, high_res, step)
+                seen += low_res.size(0)
+                step += 1
+            self.disc_scheduler.step()
+            self.gen_scheduler.step()
+            if self.device.type == 'cuda':
+                torch.cuda.synchronize()
+            self._log(f'Throughput: {round(seen * max(self.world_size, 1) / (time.time() - t0), 3)} images/sec')
+            self._test(epoch, 'srgan-gan', step)
+
+    def train(self) -> None:
+        self._pretrain()
+        if self.device.type == 'cuda':
+            torch.cuda.empty_cache()
+        self._gan_train()
