@@ -80,6 +80,11 @@ typedef struct tsr_conv_desc {
   int64_t aux_n, aux_h, aux_w;
   int32_t out_mode, out_f32, out_ch_off, aux_ch_off, n_valid, act, bwd_act, stats_ld, shuf_c;
   float acc_scale, leaky_slope;
+  /* v = (acc + bias) * acc_scale + res * res_scale + res2 * res2_scale; res / res2 share the aux strides and only
+     touch columns < res_cols (0 = all) */
+  const void* res2;
+  float res_scale, res2_scale;
+  int32_t res_cols, _pad0;
   int64_t* trace;           /* optional debug: per-CTA clock64 stamps [grid][40] (null in production) */
 } tsr_conv_desc_t;
 

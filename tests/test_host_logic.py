@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports what include/torchsr_b200.h declares,
+descriptor geometry, extent validation, plan construction in dry mode, gradient bucketing, loud failure on CPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from torchsr_b200 import _lib, build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "torchsr_b200.h")).read()
+    declared = set(re.findall(r"\b(tsr_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(_lib.EXPORTS) <= declared
+    assert lib.tsr_version() >= 1
+
+
+def test_ctypes_structs_match_header_sizes():
+    """sizeof of the ctypes mirrors equals what a C compiler computes for the header's structs."""
+    from torchsr_b200 import _lib
+    src = '#include <stdio.h>\n#include "torchsr_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(tsr_conv_desc_t),' \
+          ' sizeof(tsr_wgrad_desc_t), sizeof(tsr_elt_desc_t), sizeof(tsr_pack_entry_t));return 0;}\n'
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.WgradDesc), ctypes.sizeof(_lib.EltDesc),
+                     ctypes.sizeof(_lib.PackEntry)]
+
+
+def test_geometry_helpers():
+    from torchsr_b200 import ops
+    g = ops.fwd_geometry(96, 96, 3, 3, 1, 1, 2)
+    assert (g["Ho"], g["Wo"], g["lower_h"], g["upper_h"]) == (48, 48, -1, -1)
+    g = ops.fwd_geometry(24, 24, 9, 9, 4, 4, 1)
+    assert len(g["taps"]) == 81 and g["lower_w"] == -4 and g["upper_w"] == -4
+    g = ops.dgrad_s1_geometry(24, 24, 3, 3, 1, 1)
+    assert g["taps"][0] == (2, 2, 0) and g["taps"][-1] == (0, 0, 8)
+    cls = ops.dgrad_s2_classes(3, 1)
+    assert cls[0] == [(0, 1)] and sorted(cls[1]) == [(0, 2), (1, 0)]
+    # every (input row, kernel row) pair of a stride-2 conv appears in exactly one parity class
+    for hx in range(8):
+        r, a = hx % 2, hx // 2
+        pairs = {(a + off, k) for off, k in cls[r]}
+        want = {(hy, k) for hy in range(-1, 6) for k in range(3) if 2 * hy - 1 + k == hx}
+        assert pairs == want
+
+
+def test_extent_validation_rejects_out_of_bounds():
+    from torchsr_b200 import _lib as L
+    from torchsr_b200 import ops
+    x = torch.zeros(2 * 8 * 8 * 64, dtype=torch.bfloat16)
+    w = torch.zeros(9 * 64 * 64, dtype=torch.bfloat16)
+    out = torch.zeros(2 * 8 * 8 * 64 - 8, dtype=torch.bfloat16)      # 8 elements too small
+    geom = ops.fwd_geometry(8, 8, 3, 3, 1, 1, 1)
+    d = ops.conv_desc(x=x, N=2, H=8, W=8, C=64, x_ld=64, geom=geom, w=w, cout_pad=64, w_ld=64, n_slots=9, block_n=64,
+                      out=out, os_n=8 * 8 * 64, os_h=8 * 64, os_w=64, n_valid=64)
+    with pytest.raises(ops.ExtentError):
+        ops.validate(d)
+    ok = torch.zeros(2 * 8 * 8 * 64, dtype=torch.bfloat16)
+    d.out = ops.ptr(ok)
+    ops.validate(d)
+    e = ops.elt(L.E_CAST, p=[torch.zeros(10), torch.zeros(4, dtype=torch.bfloat16)], i=[10, 0])
+    with pytest.raises(ops.ExtentError):
+        ops.validate(e)
+
+
+def test_modules_fail_loudly_without_cuda():
+    from torchsr_b200 import _lib as L
+    from torchsr_b200.srgan.generator import Generator
+    with pytest.raises(L.TorchSRB200Error):
+        Generator()(torch.rand(1, 3, 8, 8))
+
+
+DRY_SCRIPT = r"""
+import os, sys
+os.environ["TSR_DRY"] = "1"
+sys.path.insert(0, %r)
+import torch
+from torchsr_b200.srgan.generator import Generator
+from torchsr_b200.srgan.discriminator import Discriminator
+from torchsr_b200.esrgan.discriminator import Discriminator as ED
+from torchsr_b200.esrgan.generator import Generator as EG
+from torchsr_b200.srgan.residual import ResidualBlock, SubpixelConvolutionLayer
+for mod, shape, need_x in [(Generator(), (2, 3, 24, 24), False), (Discriminator(), (2, 3, 96, 96), True),
+                           (ED(), (1, 3, 128, 128), True), (EG(num_rrdb_blocks=2), (1, 3, 16, 16), False),
+                           (ResidualBlock(), (2, 64, 8, 8), True), (SubpixelConvolutionLayer(), (2, 64, 8, 8), True)]:
+    x = torch.rand(*shape, requires_grad=need_x)
+    y = mod(x)
+    y.sum().backward()
+    assert all(p.grad is not None and p.grad.shape == p.shape for p in mod.parameters()), type(mod)
+    if need_x:
+        assert x.grad.shape == x.shape
+    mod.eval()
+    with torch.no_grad():
+        mod(x.detach())
+    plans = mod._tsr["plans"]
+    assert len(plans) == 2, plans.keys()
+    for key, pool in plans.items():
+        assert len(pool) == 1 and not pool[0].busy
+print("DRY_OK")
+"""
+
+
+def test_plans_build_and_validate_in_dry_mode():
+    """Builds the forward and backward launch lists of every module on the CPU (descriptors are validated for extents
+    and alignment, nothing is launched)."""
+    out = subprocess.run([sys.executable, "-c", DRY_SCRIPT % ROOT], capture_output=True, text=True, timeout=600)
+    assert "DRY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_bucket_slices_cover_flat_gradient_once():
+    from torchsr_b200.dist import bucket_slices
+    for total, early, cap in [(1000, 600, 300), (1000, None, 400), (23_563_652, 4_689_000, 8 * 1024 * 1024), (10, 0, 4)]:
+        sl = bucket_slices(total, early, cap)
+        covered = sorted(sl)
+        assert covered[0][0] == 0 and covered[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        assert all(hi - lo <= cap for lo, hi in sl)
+        if early:
+            assert sl[0][0] == early      # the tail (produced first in backward) is sent first

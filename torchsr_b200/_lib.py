@@ -40,6 +40,8 @@ class ConvDesc(C.Structure):
         ("n_valid", C.c_int32), ("act", C.c_int32), ("bwd_act", C.c_int32), ("stats_ld", C.c_int32),
         ("shuf_c", C.c_int32),
         ("acc_scale", C.c_float), ("leaky_slope", C.c_float),
+        ("res2", C.c_void_p), ("res_scale", C.c_float), ("res2_scale", C.c_float), ("res_cols", C.c_int32),
+        ("_pad0", C.c_int32),
         ("trace", C.c_void_p),
     ]
 

@@ -232,6 +232,10 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   e.shuf_c = d.shuf_c > 0 ? d.shuf_c : 64;
   e.acc_scale = d.acc_scale;
   e.leaky_slope = d.leaky_slope;
+  e.res2 = d.res2;
+  e.res_scale = d.res_scale;
+  e.res2_scale = d.res2_scale;
+  e.res_cols = d.res_cols > 0 ? d.res_cols : (1 << 30);
   if (!e.out) return fail(-20, "out is null");
   if ((e.act == TSR_ACT_PRELU || e.bwd_act == TSR_ACT_PRELU) && !e.prelu) return fail(-20, "PReLU needs the slope pointer");
   if (e.n_valid % 16) return fail(-20, "n_valid must be a multiple of 16");

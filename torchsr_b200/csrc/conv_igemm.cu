@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int col0 = colbase + ch * 16;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * acc_scale;
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         const bool st = valid && col0 < n_valid;
         if (bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(bias + col0);
@@ -342,6 +342,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             v[4 * i + 3] += b4.w;
           }
         }
+        if (acc_scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= acc_scale;
+        }
         if (bwd_z != nullptr && st) {
           float z[16];
           load_bf16x16(bwd_z, aux_base + col0, z);
@@ -353,11 +357,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
           }
         }
-        if (res != nullptr && st) {
+        if (res != nullptr && st && col0 < e.res_cols) {
           float z[16];
           load_bf16x16(res, aux_base + col0, z);
+          const float rs = e.res_scale;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += z[i];
+          for (int i = 0; i < 16; ++i) v[i] += z[i] * rs;
+          if (e.res2 != nullptr) {
+            load_bf16x16(e.res2, aux_base + col0, z);
+            const float rs2 = e.res2_scale;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += z[i] * rs2;
+          }
         }
         if (want_stats) {
           if (!valid) {

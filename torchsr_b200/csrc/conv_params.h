@@ -23,7 +23,8 @@ struct EpiParams {
   void* out_preact;      // optional bf16 copy of the pre-activation value (same addressing as out)
   const float* bias;     // optional, indexed by global column
   const float* prelu;    // scalar slope (device) for ACT_PRELU / bwd_act == ACT_PRELU
-  const void* res;       // optional bf16 residual, aux addressing:  v = acc*acc_scale (+bias) + res
+  const void* res;       // optional bf16 residual, aux addressing:  v = (acc+bias)*acc_scale + res*res_scale + res2*res2_scale
+  const void* res2;      // optional second residual (same addressing)
   const void* bwd_z;     // optional bf16 tensor, aux addressing: v *= act'(bwd_z)
   float* dalpha_partial; // optional [grid] partial sums of v*z*[z<0] (PReLU slope gradient)
   float* stats_partial;  // optional [stats_ld][2]: per-column sum / sum of squares of the stored value, accumulated
@@ -43,6 +44,8 @@ struct EpiParams {
   int shuf_c;            // channels per sub-pixel block for OUT_SHUFFLE / OUT_UNSHUFFLE
   float acc_scale;
   float leaky_slope;
+  float res_scale, res2_scale;
+  int res_cols;          // residuals only touch columns < res_cols
 };
 
 struct ConvParams {

@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
 // p0 = g bf16 (grad wrt act output) [M][g_ld], p1 = x raw bf16 [M][x_ld], p2 = coef (fwd: scale, shift, mean, invstd)
 // or null, p3 = alpha or null, p4 = sums [C][2], p5 = dalpha accumulator (scalar) or null, p6 = optional second
 // gradient g2 bf16 added to g (same ld)
-// i: 0 M, 1 C, 2 act, 3 rows_per_block, 4 g_ld, 5 x_ld, 6 has_bn; f: 0 leaky
+// i: 0 M, 1 C, 2 act, 3 rows_per_block, 4 g_ld, 5 x_ld, 6 has_bn; f: 0 leaky, 1 gscale (0 = 1: scales g (+g2) on load)
 // dz = g * act'(z), z = x*scale+shift (has_bn) or x; xhat = (x-mean)*invstd. ACT_LEAKY/RELU without BN take
 // x = activation output (sign preserved).
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x,
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
                                                             float* __restrict__ dalpha_acc,
                                                             const bf16* __restrict__ g2, long long M, int C, int act,
                                                             int rows_per_block, int g_ld, int x_ld, int has_bn,
-                                                            float leaky) {
+                                                            float leaky, float gscale) {
   extern __shared__ float sm[];
   const int groups = C / 8;
   const int lanes = 256 / groups;  // row lanes (groups <= 256)
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float z = xv[j] * sc[j] + sh[j];
-        float dz = gv[j];
+        float dz = gv[j] * gscale;
         if (act != TSR_ACT_NONE && z <= 0.f) {
           da += dz * z;
           dz *= slope;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
 // p0 = g bf16, p1 = x raw bf16, p2 = coef fwd or null, p3 = sums [C][2] or null, p4 = alpha, p5 = dx out bf16,
 // p6 = optional g2, p7 = gamma or null, p8 = dgamma out [C] or null, p9 = dbeta / bias-gradient out [C] or null,
 // p10 = dalpha out (scalar) or null, p11 = dalpha accumulator (scalar) or null
-// i: 0 M, 1 C, 2 act, 3 g_ld, 4 x_ld, 5 dx_ld, 6 has_bn; f: 0 leaky
+// i: 0 M, 1 C, 2 act, 3 g_ld, 4 x_ld, 5 dx_ld, 6 has_bn; f: 0 leaky, 1 gscale (0 = 1)
 // has_bn: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); else dx = dz.  Block 0 publishes the parameter
 // gradients (dgamma = sum dz*xhat, dbeta = sum dz, dalpha).
 struct BnBwdApplyArgs {
@@ -339,7 +339,7 @@ struct BnBwdApplyArgs {
   const float* dalpha_acc;
   long long M;
   int C, act, g_ld, x_ld, dx_ld, has_bn;
-  float leaky;
+  float leaky, gscale;
 };
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs a) {
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float z = xv[j] * sc[j] + sh[j];
-      float dz = gv[j];
+      float dz = gv[j] * a.gscale;
       if (a.act != TSR_ACT_NONE && z <= 0.f) dz *= slope;
       if (a.has_bn) {
         const float xhat = (xv[j] - mu[j]) * is[j];
@@ -856,7 +856,8 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
       const size_t sm = (static_cast<size_t>(lanes) * C * 2 + 8) * sizeof(float);
       bn_bwd_reduce_kernel<<<blocks, 256, sm, st>>>((const bf16*)p[0], (const bf16*)p[1], (const float*)p[2],
                                                     (const float*)p[3], (float*)p[4], (float*)p[5], (const bf16*)p[6],
-                                                    i[0], C, i[2], i[3], i[4], i[5], i[6], d.f[0]);
+                                                    i[0], C, i[2], i[3], i[4], i[5], i[6], d.f[0],
+                                                    d.f[1] != 0.f ? d.f[1] : 1.f);
       break;
     }
     case TSR_E_BN_BWD_APPLY: {
@@ -866,6 +867,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
       a.dgamma = (float*)p[8]; a.dbeta = (float*)p[9]; a.dalpha = (float*)p[10]; a.dalpha_acc = (const float*)p[11];
       a.M = i[0]; a.C = i[1]; a.act = i[2]; a.g_ld = i[3]; a.x_ld = i[4]; a.dx_ld = i[5]; a.has_bn = i[6];
       a.leaky = d.f[0];
+      a.gscale = d.f[1] != 0.f ? d.f[1] : 1.f;
       bn_bwd_apply_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>(a);
       break;
     }

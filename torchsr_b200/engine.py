@@ -268,17 +268,23 @@ class Plan:
         return d
 
     def conv_fwd(self, prog, rec: ConvRec, x: Act, out: Act, *, stats=None, act=L.ACT_NONE, prelu=None, preact=None,
-                 res: Optional[Act] = None, out_f32=False, shuffle_out=False):
-        """Forward of a 'std' conv (any stride) into `out` (OUT_LINEAR or PixelShuffle store)."""
+                 res: Optional[Act] = None, res2: Optional[Act] = None, res_scale=1.0, res2_scale=1.0, acc_scale=1.0,
+                 out_f32=False, shuffle_out=False, use_bias=True):
+        """Forward of a 'std' conv (any stride) into `out` (OUT_LINEAR or PixelShuffle store), with the fused epilogue
+        v = (acc + bias) * acc_scale + res * res_scale + res2 * res2_scale, optional activation, optional statistics.
+        `x` / `out` / `res` may be channel slices of wider NHWC buffers (ld, c0)."""
         geom = ops.fwd_geometry(x.H, x.W, rec.k, rec.k, rec.pad, rec.pad, rec.stride)
         bias = None
-        if rec.bias is not None:
+        if rec.bias is not None and use_bias:
             bias = rec.bias_packed if rec.shuffle else rec.bias
-        kw = dict(bias=bias, act=act, prelu=prelu, out_preact=preact, out_f32=out_f32)
+        kw = dict(bias=bias, act=act, prelu=prelu, out_preact=preact, out_f32=out_f32, acc_scale=acc_scale,
+                  out_ch_off=out.c0)
         if stats is not None:
             kw.update(stats_partial=stats, stats_ld=rec.cout_pad)
         if res is not None:
-            kw.update(res=res.t, aux=res.strides())
+            assert res2 is None or (res2.ld == res.ld and res2.c0 == res.c0)
+            kw.update(res=res.t, aux=res.strides(), aux_ch_off=res.c0, res_scale=res_scale,
+                      res2=res2.t if res2 is not None else None, res2_scale=res2_scale)
         if shuffle_out:
             kw.update(out_mode=L.OUT_SHUFFLE, shuf_c=rec.cout // 4)
         block_n = self.pick_block_n(x.B * geom["Ho"] * geom["Wo"], rec.cout_pad, rec.block_n)
@@ -323,44 +329,50 @@ class Plan:
     # ---- backward emitters
     def norm_act_bwd(self, prog, name: str, g: Act, x: Act, *, coef=None, bn: Optional[nn.BatchNorm2d] = None,
                      act=L.ACT_NONE, alpha: Optional[torch.Tensor] = None, g2: Optional[Act] = None,
-                     bias_grad: Optional[torch.Tensor] = None, want_w=True, leaky=0.2) -> Act:
-        """Backward of y = act(BN(x)) (bn given) or y = act(x) (bn None) for upstream gradient g (+ g2):
+                     bias_grad: Optional[torch.Tensor] = None, want_w=True, leaky=0.2, gscale=1.0) -> Act:
+        """Backward of y = act(BN(x)) (bn given) or y = act(x) (bn None) for upstream gradient gscale * (g + g2):
         column reduction (atomics into the zero arena) -> apply, whose block 0 also publishes dgamma / dbeta (or the
-        bias gradient) / dalpha into the flat gradient. Returns d/dx as a new Act."""
+        bias gradient) / dalpha into the flat gradient. g / x may be channel slices (ld, c0). Returns d/dx (dense)."""
         M, C = x.M, x.C
-        assert g.ld == C and x.ld == C and (g2 is None or g2.ld == C)
+        assert g.C == C and (g2 is None or (g2.ld == g.ld and g2.C == C))
         has_bn = 1 if bn is not None else 0
         rpb = max(32, -(-M // (2 * NUM_SMS)))
         dx = self.act(name + ".dx", x.B, x.H, x.W, C)
         prelu = act == L.ACT_PRELU
         need_reduce = has_bn or (want_w and (prelu or bias_grad is not None))
         store = self.store
+        gp = ops.ptr(g.t, g.c0)
+        xp = ops.ptr(x.t, x.c0)
+        g2p = ops.ptr(g2.t, g2.c0) if g2 is not None else None
         sums = dacc = None
         if need_reduce:
             sums = self.zbuf("bwd", name + ".sums", 2 * C)
             dacc = self.zbuf("bwd", name + ".dalpha", 1) if prelu else None
-            prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, x.t, coef, alpha if prelu else None, sums, dacc,
-                                                   g2.t if g2 is not None else None],
-                             i=[M, C, act, rpb, C, C, has_bn], f=[leaky]))
+            prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[gp, xp, coef, alpha if prelu else None, sums, dacc, g2p],
+                             i=[M, C, act, rpb, g.ld, x.ld, has_bn], f=[leaky, gscale]))
         dgamma = store.grad_slice(bn.weight) if has_bn and want_w else None
         dbeta = (store.grad_slice(bn.bias) if has_bn else bias_grad) if want_w else None
         dalpha = store.grad_slice(alpha) if (prelu and want_w) else None
-        prog.add(ops.elt(L.E_BN_BWD_APPLY, p=[g.t, x.t, coef, sums, alpha if prelu else None, dx.t,
-                                              g2.t if g2 is not None else None, bn.weight if has_bn else None, dgamma,
-                                              dbeta, dalpha, dacc],
-                         i=[M, C, act, C, C, C, has_bn], f=[leaky]))
+        prog.add(ops.elt(L.E_BN_BWD_APPLY, p=[gp, xp, coef, sums, alpha if prelu else None, dx.t, g2p,
+                                              bn.weight if has_bn else None, dgamma, dbeta, dalpha, dacc],
+                         i=[M, C, act, g.ld, x.ld, C, has_bn], f=[leaky, gscale]))
         return dx
 
     def conv_dgrad(self, prog, name: str, rec: ConvRec, dy: Act, x_like: Act, *, res: Optional[Act] = None,
-                   out_f32: bool = False) -> Act:
+                   out_f32: bool = False, out: Optional[Act] = None, res2: Optional[Act] = None, res_scale=1.0,
+                   res2_scale=1.0, res_cols=0, acc_scale=1.0) -> Act:
         """Gradient w.r.t. the input `x_like` of conv `rec` from dY, as an implicit-GEMM conv over dY with the
         transposed weight pack. Fused epilogue: + res (residual branch gradient) and, when the producer of x_like
         left a hook, * act'(pre-activation) with the PixelShuffle inverse folded into the store.
         Returns the Act holding the result (the hook's un-shuffled target when one was used)."""
         assert rec.need_dgrad
         kw = {}
+        if acc_scale != 1.0:
+            kw.update(acc_scale=acc_scale)
         if res is not None:
-            kw.update(res=res.t, aux=res.strides(), aux_ch_off=res.c0)
+            assert res2 is None or (res2.ld == res.ld and res2.c0 == res.c0)
+            kw.update(res=res.t, aux=res.strides(), aux_ch_off=res.c0, res_scale=res_scale, res_cols=res_cols,
+                      res2=res2.t if res2 is not None else None, res2_scale=res2_scale)
         hook = x_like.hook
         if hook is not None:
             assert res is None
@@ -379,8 +391,9 @@ class Plan:
         block_n = next(b for b in (128, 96, 64, 160, 192, 32, 16) if n_out % b == 0 and b <= n_out)
         if rec.stride == 1:
             block_n = self.pick_block_n(dy.M, n_out, block_n)
-        dx = self.act(name + ".dgrad", x_like.B, x_like.H, x_like.W, n_out, F32 if out_f32 else BF16) \
-            if (hook is None or hook.get("unshuffle_to") is None) else None
+        dx = out
+        if dx is None and (hook is None or hook.get("unshuffle_to") is None):
+            dx = self.act(name + ".dgrad", x_like.B, x_like.H, x_like.W, n_out, F32 if out_f32 else BF16)
         if hook is not None and hook.get("unshuffle_to") is not None:
             target = hook["unshuffle_to"]
             kw.update(out_mode=L.OUT_UNSHUFFLE, shuf_c=n_out)
@@ -403,6 +416,16 @@ class Plan:
         rpb = max(32, -(-M // (2 * NUM_SMS)))
         sums = self.zbuf("bwd", name + ".cs", 2 * C)
         prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, g.t, None, None, sums, None, None],
+                         i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2]))
+        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0]))
+
+    def colsum_strided(self, prog, name: str, g: Act, out_vec: torch.Tensor):
+        """colsum for a channel slice of a wider buffer."""
+        M, C = g.M, g.C
+        rpb = max(32, -(-M // (2 * NUM_SMS)))
+        sums = self.zbuf("bwd", name + ".cs", 2 * C)
+        gp = ops.ptr(g.t, g.c0)
+        prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[gp, gp, None, None, sums, None, None],
                          i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2]))
         prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0]))
 

@@ -356,3 +356,196 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
         return gx
 
     plan.input_fn, plan.output_fn, plan.ingest_fn, plan.grad_input_fn = input_fn, output_fn, ingest_fn, grad_input_fn
+
+
+# ------------------------------------------------------------------------------------------------ ESRGAN generator
+RDB_NAMES = ("RDB1", "RDB2", "RDB3")
+
+
+def esrgan_generator_records(m) -> List[ConvRec]:
+    recs = [ConvRec("conv1", m.conv1, "fullk", need_dgrad=False)]
+    for b, blk in enumerate(m.blocks):
+        for r in RDB_NAMES:
+            rdb = getattr(blk, r)
+            for k in range(1, 5):
+                recs.append(ConvRec(f"blocks.{b}.{r}.conv{k}.0", getattr(rdb, f"conv{k}")[0]))
+            recs.append(ConvRec(f"blocks.{b}.{r}.conv5", rdb.conv5))
+    recs += [ConvRec("conv2", m.conv2), ConvRec("upsample1", m.upsample1), ConvRec("upsample2", m.upsample2),
+             ConvRec("conv3.0", m.conv3[0]), ConvRec("conv4", m.conv4)]
+    return recs
+
+
+def define_esrgan_generator(m, plan: Plan, shape):
+    """torchsr/esrgan/generator.py:54-81 and residual.py:81-86,124-129.
+
+    Dense blocks are zero-copy: every RDB owns one [B,H,W,192] NHWC buffer `cat`; conv_k reads the channel prefix
+    [0, 64+32(k-1)) and writes its 32 channels right behind it, conv5 reads all 192 and writes (conv5+b)*0.2 + x into
+    the first 64 channels of the NEXT block's buffer (for the third RDB of an RRDB the outer `*0.2 + x` is folded
+    into the same epilogue: (conv5+b)*0.04 + 0.2*x_rdb3 + x_rrdb). Backward mirrors this with [B,H,W,192] gradient
+    buffers that the data-gradient convs accumulate into in place."""
+    B, cin, H, W = shape
+    if cin != 3:
+        raise RuntimeError(f"Generator expects 3 input channels, got {cin}")
+    R = _recs(plan)
+    store, fwd = plan.store, plan.fwd
+    C, G, CT = 64, 32, 192
+    n_rrdb = len(m.blocks)
+    n_rdb = 3 * n_rrdb
+
+    def cat_buf(j):
+        return plan.buf(f"cat{j}", B * H * W * CT, BF16)
+
+    def sl(t, c, c0=0, h=H, w=W):
+        return Act(t, B, h, w, c, ld=CT, c0=c0)
+
+    # ---- conv1 (3 -> 64, no activation) straight into the first dense buffer
+    r1 = R["conv1"]
+    E1 = plan.act("E1", B, H, W, r1.epad)
+    g1 = _geom1(H, W)
+    c1 = sl(cat_buf(0), C)
+    plan.conv(fwd, E1, r1.w_fwd, r1.cols, 1, g1, r1.cout_pad, r1.block_n, c1.t, c1.strides(), r1.cout_pad, bias=r1.bias)
+
+    def bwd_conv1(bp, g, want_x, want_w):
+        if want_w:
+            d = plan.norm_act_bwd(bp, "conv1", g, g, act=L.ACT_NONE, g2=plan.slots["skip"],
+                                  bias_grad=store.grad_slice(r1.bias), want_w=True)
+            plan.conv_wgrad(bp, r1, E1, d, geom=g1)
+        return None
+
+    plan.tape.append(bwd_conv1)
+
+    # ---- 23 x 3 dense blocks
+    NG = 5   # ring of gradient buffers: an RRDB's incoming gradient must outlive its three RDB backward passes
+
+    def gbuf(i):
+        return plan.buf(f"dcat{i % NG}", B * H * W * CT, BF16)
+
+    for j in range(n_rdb):
+        b, r = divmod(j, 3)
+        name = f"blocks.{b}.{RDB_NAMES[r]}"
+        cat, nxt = cat_buf(j), cat_buf(j + 1)
+        rk = [R[f"{name}.conv{k}.0"] for k in range(1, 5)]
+        r5 = R[f"{name}.conv5"]
+        for k in range(1, 5):
+            plan.conv_fwd(fwd, rk[k - 1], sl(cat, C + G * (k - 1)), sl(cat, G, C + G * (k - 1)), act=L.ACT_LEAKY)
+        x_rdb = sl(cat, C)
+        if r == 2:
+            x_rrdb = sl(cat_buf(j - 2), C)
+            plan.conv_fwd(fwd, r5, sl(cat, CT), sl(nxt, C), acc_scale=0.04, res=x_rdb, res_scale=0.2, res2=x_rrdb,
+                          res2_scale=1.0)
+        else:
+            plan.conv_fwd(fwd, r5, sl(cat, CT), sl(nxt, C), acc_scale=0.2, res=x_rdb)
+
+        def bwd(bp, g, want_x, want_w, j=j, r=r, name=name, cat=cat, rk=rk, r5=r5):
+            # g: gradient w.r.t. this RDB's output (first 64 channels of a 192-wide buffer). For the third RDB of an
+            # RRDB it is the RRDB-level gradient: the block output was 0.2 * rdb3_out + x_rrdb.
+            outer = 0.2 if r == 2 else 1.0
+            if r == 2:
+                plan.slots[f"rrdb{j // 3}"] = g
+            dcat = gbuf(n_rdb - j)
+            d5 = plan.norm_act_bwd(bp, name + ".c5", g, g, act=L.ACT_NONE, gscale=0.2 * outer,
+                                   bias_grad=store.grad_slice(r5.bias), want_w=want_w)
+            if want_w:
+                plan.conv_wgrad(bp, r5, sl(cat, CT), d5)
+            plan.conv_dgrad(bp, name + ".c5", r5, d5, sl(cat, CT), out=sl(dcat, CT), res=sl(g.t, C), res_scale=outer,
+                            res_cols=C)
+            for k in range(4, 0, -1):
+                ck = C + G * (k - 1)
+                dk = plan.norm_act_bwd(bp, f"{name}.c{k}", sl(dcat, G, ck), sl(cat, G, ck), act=L.ACT_LEAKY,
+                                       bias_grad=store.grad_slice(rk[k - 1].bias), want_w=want_w)
+                if want_w:
+                    plan.conv_wgrad(bp, rk[k - 1], sl(cat, ck), dk)
+                last = k == 1 and r == 0
+                plan.conv_dgrad(bp, f"{name}.c{k}", rk[k - 1], dk, sl(cat, ck), out=sl(dcat, ck), res=sl(dcat, ck),
+                                res2=sl(plan.slots[f"rrdb{j // 3}"].t, ck) if last else None)
+            return sl(dcat, C)
+
+        plan.tape.append(bwd)
+
+    trunk = sl(cat_buf(n_rdb), C)
+
+    # ---- conv2 + skip, two nearest-x2 upsample stages, conv3 + LeakyReLU, conv4
+    r2 = R["conv2"]
+    s = plan.act("trunk", B, H, W, C)
+    plan.conv_fwd(fwd, r2, trunk, s, res=c1)
+
+    def bwd_conv2(bp, g, want_x, want_w):
+        # g: gradient w.r.t. s = conv1 + conv2(trunk), living in a 192-wide buffer; it also reaches conv1
+        plan.slots["skip"] = g
+        if want_w:
+            plan.colsum_strided(bp, "conv2.db", g, store.grad_slice(r2.bias))
+            plan.conv_wgrad(bp, r2, trunk, g)          # dY may be a channel slice (row stride 192)
+        return plan.conv_dgrad(bp, "conv2", r2, g, trunk, out=sl(gbuf(0), C))
+
+    plan.tape.append(bwd_conv2)
+
+    prev, h, w = s, H, W
+    for name in ("upsample1", "upsample2"):
+        rec = R[name]
+        up = plan.act(name + ".in", B, 2 * h, 2 * w, C)
+        fwd.add(ops.elt(L.E_UPSAMPLE2X, p=[prev.t, up.t], i=[B, h, w, C, prev.ld, C]))
+        out = plan.act(name + ".out", B, 2 * h, 2 * w, C)
+        plan.conv_fwd(fwd, rec, up, out, act=L.ACT_LEAKY)
+        first = name == "upsample1"
+
+        def bwd_up(bp, g, want_x, want_w, rec=rec, up=up, out=out, h=h, w=w, name=name, first=first):
+            d = plan.norm_act_bwd(bp, name, g, out, act=L.ACT_LEAKY, bias_grad=store.grad_slice(rec.bias), want_w=want_w)
+            if want_w:
+                plan.conv_wgrad(bp, rec, up, d)
+            gup = plan.conv_dgrad(bp, name, rec, d, up)
+            # gradient of nearest-neighbour x2: 2x2 sums; the first stage writes into a 192-wide buffer because the
+            # dense-block backward (and the skip into conv1) address their gradients that way
+            tgt = Act(plan.buf("s.grad", B * h * w * CT, BF16), B, h, w, C, ld=CT) if first else \
+                plan.act(name + ".gin", B, h, w, C)
+            bp.add(ops.elt(L.E_UPSAMPLE2X_BWD, p=[gup.t, tgt.t], i=[B, h, w, C, C, tgt.ld]))
+            return tgt
+
+        plan.tape.append(bwd_up)
+        prev, h, w = out, 2 * h, 2 * w
+
+    r3 = R["conv3.0"]
+    u3 = plan.act("conv3.out", B, h, w, C)
+    u2 = prev
+    plan.conv_fwd(fwd, r3, u2, u3, act=L.ACT_LEAKY)
+
+    def bwd_conv3(bp, g, want_x, want_w):
+        d = plan.norm_act_bwd(bp, "conv3", g, u3, act=L.ACT_LEAKY, bias_grad=store.grad_slice(r3.bias), want_w=want_w)
+        if want_w:
+            plan.conv_wgrad(bp, r3, u2, d)
+        return plan.conv_dgrad(bp, "conv3", r3, d, u2)
+
+    plan.tape.append(bwd_conv3)
+
+    r4 = R["conv4"]
+    Hf, Wf = h, w
+    T = plan.act("T", B, Hf, Wf, r4.cout_pad, F32)
+    plan.conv_fwd(fwd, r4, u3, T, out_f32=True, use_bias=False)     # bias (3 values) is added by the gather kernel
+    E4 = plan.act("E4", B, Hf, Wf, r4.cout_pad)
+    cs = plan.buf("conv4.cs", CHANSUM_SPLITS * r4.cout * 2, F32)
+
+    def bwd_conv4(bp, g, want_x, want_w):
+        if want_w:
+            bp.add(ops.elt(L.E_COLSUM_FINALIZE, p=[cs, store.grad_slice(r4.bias)], i=[CHANSUM_SPLITS, r4.cout, r4.cout, 0, 0]))
+            plan.conv_wgrad(bp, r4, u3, E4)
+        return plan.conv_dgrad(bp, "conv4", r4, E4, u3)
+
+    plan.tape.append(bwd_conv4)
+
+    def input_fn(x_nchw):
+        ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E1.t], i=[B, 3, H, W, r1.k, r1.k, r1.pad, r1.pad, 1, r1.epad]))
+
+    def output_fn():
+        out = torch.empty(B, r4.cout, Hf, Wf, dtype=F32, device=plan.device)
+        ops.run_now(ops.elt(L.E_GATHER_OUT, p=[T.t, out, r4.bias], i=[B, r4.cout, Hf, Wf, 1, 1, 0, 0, 1, r4.cout_pad, 0]))
+        return out
+
+    def ingest_fn(gout):
+        ops.run_now(ops.elt(L.E_IM2ROW, p=[gout, E4.t], i=[B, r4.cout, Hf, Wf, 1, 1, 0, 0, 1, r4.cout_pad]))
+        ops.run_now(ops.elt(L.E_CHANSUM_NCHW, p=[gout, cs], i=[B, r4.cout, Hf * Wf, CHANSUM_SPLITS]))
+        return E4
+
+    def grad_input_fn():
+        raise NotImplementedError("torchsr_b200: the gradient w.r.t. the generator's low-resolution input is not "
+                                  "implemented (the reference training loops never request it)")
+
+    plan.input_fn, plan.output_fn, plan.ingest_fn, plan.grad_input_fn = input_fn, output_fn, ingest_fn, grad_input_fn

@@ -121,7 +121,8 @@ def _set_taps(d, taps: Sequence[Tuple[int, int, int]]):
 def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n, out, os_n, os_h, os_w, n_valid,
               block_k=None, a_c0=0, out_mode=L.OUT_LINEAR, out_f32=False, out_ch_off=0, bias=None, prelu=None,
               act=L.ACT_NONE, out_preact=None, res=None, bwd_z=None, bwd_act=L.ACT_NONE, aux=(0, 0, 0), aux_ch_off=0,
-              dalpha_partial=None, stats_partial=None, stats_ld=0, acc_scale=1.0, leaky=0.2, shuf_c=64) -> ConvDesc:
+              dalpha_partial=None, stats_partial=None, stats_ld=0, acc_scale=1.0, leaky=0.2, shuf_c=64, res2=None,
+              res_scale=1.0, res2_scale=1.0, res_cols=0) -> ConvDesc:
     d = ConvDesc()
     d.x, d.w = ptr(x), ptr(w)
     d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
@@ -143,6 +144,7 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     d.out_mode, d.out_f32, d.out_ch_off, d.aux_ch_off = out_mode, int(out_f32), out_ch_off, aux_ch_off
     d.n_valid, d.act, d.bwd_act, d.stats_ld, d.shuf_c = n_valid, act, bwd_act, stats_ld, shuf_c
     d.acc_scale, d.leaky_slope = acc_scale, leaky
+    d.res2, d.res_scale, d.res2_scale, d.res_cols = ptr(res2), res_scale, res2_scale, res_cols
     return d
 
 
@@ -188,6 +190,7 @@ def gemm_desc(*, a, M, K, a_ld, a_mn_major=False, w, n_rows, block_n, out, out_l
     d.os_w = out_ld
     d.n_valid, d.act = n_valid, act
     d.acc_scale, d.leaky_slope = acc_scale, leaky
+    d.res_scale = d.res2_scale = 1.0
     d.shuf_c = 64
     return d
 
@@ -240,9 +243,10 @@ def validate_conv(d: ConvDesc):
         _need("conv out", d.out, (last + d.out_ch_off + span) * esz)
         if d.out_preact:
             _need("conv out_preact", d.out_preact, (last + d.out_ch_off + span) * 2)
-        for name, p in (("res", d.res), ("bwd_z", d.bwd_z)):
+        rc = min(d.n_valid, d.res_cols) if d.res_cols > 0 else d.n_valid
+        for name, p, cols in (("res", d.res, rc), ("res2", d.res2, rc), ("bwd_z", d.bwd_z, d.n_valid)):
             if p:
-                _need("conv " + name, p, (aux_last + d.aux_ch_off + d.n_valid) * 2)
+                _need("conv " + name, p, (aux_last + d.aux_ch_off + cols) * 2)
     else:
         M = d.gemm_M
         rows, cols = (d.gemm_M, d.gemm_K) if d.a_mode == 1 else (d.gemm_K, d.gemm_M)

@@ -26,6 +26,8 @@ from .loss import VGGLoss
 
 
 class SRGANTrainer:
+    PREFIX = 'srgan'
+
     def __init__(self, device, args: Namespace, train_loader, test_loader, train_len: int, test_len: int,
                  distributed: bool = False) -> None:
         self.amp = not args.disable_amp
@@ -174,7 +176,7 @@ class SRGANTrainer:
 
     def _pretrain(self) -> None:
         self.best_psnr = -1.0
-        self._restore(self.psnr_checkpoint, 'srgan-psnr-latest.pth')
+        self._restore(self.psnr_checkpoint, f'{self.PREFIX}-psnr-latest.pth')
         step = 0
         for epoch in range(1, self.pre_epochs + 1):
             self._log(f'Starting epoch {epoch} out of {self.pre_epochs}')
@@ -187,12 +189,12 @@ class SRGANTrainer:
             if self.device.type == 'cuda':
                 torch.cuda.synchronize()
             self._log(f'Throughput: {round(seen * max(self.world_size, 1) / (time.time() - t0), 3)} images/sec')
-            self._test(epoch, 'srgan-psnr', step)
+            self._test(epoch, f'{self.PREFIX}-psnr', step)
 
     def _gan_train(self) -> None:
         self.best_psnr = -1.0
-        if not self._restore(self.gan_checkpoint, 'srgan-gan-latest.pth'):
-            self._restore('srgan-psnr-latest.pth')
+        if not self._restore(self.gan_checkpoint, f'{self.PREFIX}-gan-latest.pth'):
+            self._restore(f'{self.PREFIX}-psnr-latest.pth')
         step = 0
         for epoch in range(1, self.epochs + 1):
             self._log(f'Starting epoch {epoch} out of {self.epochs}')
@@ -207,7 +209,7 @@ class SRGANTrainer:
             if self.device.type == 'cuda':
                 torch.cuda.synchronize()
             self._log(f'Throughput: {round(seen * max(self.world_size, 1) / (time.time() - t0), 3)} images/sec')
-            self._test(epoch, 'srgan-gan', step)
+            self._test(epoch, f'{self.PREFIX}-gan', step)
 
     def train(self) -> None:
         self._pretrain()
