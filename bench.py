@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="crops per GPU per step (configs[1]: 16; configs[2]: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-vgg", action="store_true", help="MSE content loss instead of VGG (NOT the headline config)")
+    ap.add_argument("--eager", action="store_true", help="call _gan_loop eagerly instead of trainer.graph_step")
     return ap.parse_args()
 
 
@@ -225,15 +226,23 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), L.launch_count() - l0
 
+    # public step API: trainer.graph_step replays the whole _gan_loop as one CUDA graph (same arithmetic as the eager
+    # call, see srgan/trainer.py); --eager times the plain Python call instead
+    step_fn = trainer._gan_loop if (args.eager or distributed) else trainer.graph_step
     for s in range(max(args.warmup, 3)):
-        trainer._gan_loop(lr_d, hr_d, s)
+        step_fn(lr_d, hr_d, s)
+    # kernels of ours per step (graph replays do not pass through the library's launch counter)
+    l0 = L.launch_count()
+    trainer._gan_loop(lr_d, hr_d, 0)
+    launches_per_step = L.launch_count() - l0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, launches = timed(lambda s: trainer._gan_loop(lr_d, hr_d, s), args.steps)
+    ms, _ = timed(lambda s: step_fn(lr_d, hr_d, s), args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
     # end to end: pinned host batch -> H2D inside the step, loss read back to the host every step
-    ms_e2e, _ = timed(lambda s: trainer._gan_loop(lr_h, hr_h, s).item(), args.steps)
+    ms_e2e, _ = timed(lambda s: step_fn(lr_h, hr_h, s).item(), args.steps)
     crops = args.batch * world * args.steps
     value = crops / (ms * 1e-3)
     e2e = crops / (ms_e2e * 1e-3)
@@ -253,6 +262,8 @@ def run_b200(args):
                                (args.batch, "replaced by MSE (--no-vgg)" if args.no_vgg else
                                 "executed by PyTorch/cuDNN under bf16 autocast (not one of this repo's kernels)"),
                    "parallelism": f"dp{world}", "global_batch": args.batch * world,
+                   "step_api": "SRGANTrainer._gan_loop (eager)" if (args.eager or distributed) else
+                               "SRGANTrainer.graph_step (whole step replayed as one CUDA graph)",
                    "l2": "per-step working set (fp32 weights + Adam state + activations, > 0.5 GB) exceeds the 126 MB "
                          "L2; no explicit flush between steps"},
         "e2e": {"value": e2e, "unit": "crops/s", "ms_per_step": ms_e2e / args.steps,

@@ -44,6 +44,26 @@ def main():
         t1 = e_ if t1 is None else max(t1, e_)
         busy += e.device_time
     span = (t1 - t0)
+    # union of busy intervals (kernels overlapping on different streams / graph branches count once)
+    iv = sorted((e.time_range.start, e.time_range.end) for e in evs)
+    union, cur_s, cur_e = 0.0, None, None
+    for s_, e_ in iv:
+        if cur_e is None or s_ > cur_e:
+            if cur_e is not None:
+                union += cur_e - cur_s
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    union += (cur_e - cur_s) if cur_e is not None else 0.0
+    print(f"union-busy {union / steps / 1e3:.3f} ms/step (sum of durations {busy / steps / 1e3:.3f})")
+    cpu_ops = {}
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CPU and e.name.startswith("aten::"):
+            a = cpu_ops.setdefault(e.name, [0, 0.0])
+            a[0] += 1
+            a[1] += e.cpu_time
+    print("top aten ops on the CPU (count/step, us/step):",
+          [(k, round(v[0] / steps, 1), round(v[1] / steps)) for k, v in sorted(cpu_ops.items(), key=lambda kv: -kv[1][1])[:14]])
     print(f"batch {B}: {steps} steps, GPU span {span / steps / 1e3:.3f} ms/step, kernel-busy {busy / steps / 1e3:.3f} ms/step, "
           f"{len(evs) / steps:.0f} GPU activities/step")
     for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:

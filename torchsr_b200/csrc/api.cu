@@ -355,18 +355,64 @@ bool use_graphs() {
   return g_use_graphs == 1;
 }
 
+cudaStream_t g_side_stream = nullptr;
+cudaEvent_t g_fork_event = nullptr, g_join_event = nullptr;
+int g_use_side = -1;
+
+bool use_side_stream() {
+  if (g_use_side < 0) {
+    const char* e = getenv("TSR_WGRAD_BRANCH");
+    g_use_side = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_use_side == 1;
+}
+
+// Weight-gradient GEMMs only feed the final unpack, so they run on a side stream forked off the main chain right
+// after the kernel that produced their dY (a parallel branch once the range is captured into a CUDA graph) and
+// are joined before the first non-wgrad op that follows the last of them in program order is NOT required: the
+// join happens once, before the op that consumes the accumulators (the unpack kernel / the end of the range).
 int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
+  bool side = use_side_stream();
+  if (side && !g_side_stream) {
+    if (cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming) != cudaSuccess)
+      return fail(-45, "side stream setup failed");
+  }
+  bool forked = false;
+  auto join = [&]() -> cudaError_t {
+    if (!forked) return cudaSuccess;
+    forked = false;
+    cudaError_t e = cudaEventRecord(g_join_event, g_side_stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamWaitEvent(st, g_join_event, 0);
+  };
   for (int i = first; i < last; ++i) {
     const tsr_prog::Op& op = p->ops[i];
     cudaError_t ce;
-    if (op.kind == tsr_prog::CONV)
-      ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st);
-    else if (op.kind == tsr_prog::WGRAD)
+    if (op.kind == tsr_prog::WGRAD && side) {
+      ce = cudaEventRecord(g_fork_event, st);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(g_side_stream, g_fork_event, 0);
+      if (ce == cudaSuccess)
+        ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, g_side_stream);
+      forked = true;
+    } else if (op.kind == tsr_prog::WGRAD) {
       ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st);
-    else
-      ce = tsr::launch_elt(op.elt, st);
+    } else {
+      // the unpack kernel reads every accumulator: join the branch first
+      if (op.kind == tsr_prog::ELT && op.elt.kind == TSR_E_UNPACK_G) {
+        ce = join();
+        if (ce != cudaSuccess) return fail(-45, "join failed: %s", cudaGetErrorString(ce));
+      }
+      if (op.kind == tsr_prog::CONV)
+        ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st);
+      else
+        ce = tsr::launch_elt(op.elt, st);
+    }
     if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
   }
+  cudaError_t ce = join();
+  if (ce != cudaSuccess) return fail(-45, "join failed: %s", cudaGetErrorString(ce));
   return 0;
 }
 }  // namespace
@@ -439,7 +485,11 @@ int tsr_prog_run(tsr_prog_t* p, int first, int count, void* stream) {
   const int n = static_cast<int>(p->ops.size());
   const int last = count < 0 ? n : (first + count > n ? n : first + count);
   if (last <= first) return 0;
-  if (!use_graphs() || last - first < 4) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (!use_graphs() || last - first < 4 || cap != cudaStreamCaptureStatusNone) {
+    // plain launches; when the caller's stream is itself being captured (a whole training step recorded into one
+    // CUDA graph) the kernels, the memsets and the wgrad branch become nodes of the caller's graph
     if (int e = launch_range(p, first, last, st)) return e;
     g_launches += last - first;
     return 0;

@@ -120,7 +120,6 @@ class ParamStore:
             self.offsets[id(p)] = off
             off += _round_up(p.numel(), 4)          # keep every slice 16-byte aligned
         self.total = off
-        self.flat_grad = torch.zeros(max(off, 4), dtype=F32, device=device)
         # ---- arenas: bf16 packed operands, fp32 weight-gradient accumulators (packed order)
         w_elems, acc_elems = 0, 0
         for r in convs:
@@ -131,7 +130,7 @@ class ParamStore:
         for r in linears:
             r._fwd_off, w_elems = w_elems, w_elems + _round_up(r.nout_pad * r.K, 128)
         self.w_arena = torch.zeros(max(w_elems, 128), dtype=BF16, device=device)
-        self.acc_arena = torch.zeros(max(acc_elems, 64), dtype=F32, device=device)
+        self.acc_elems = max(acc_elems, 64)
         self._version = None
         self._build_tables()
 
@@ -141,7 +140,7 @@ class ParamStore:
         return {"std": r.k * r.k, "fullk": 1, "rown": r.k}[r.kind]
 
     def _build_tables(self):
-        pack, unpack = [], []
+        pack = []
         self.bias_perm: List[ConvRec] = []
         for r in self.convs:
             n_fwd = r.slots * r.cout_pad * r.cols
@@ -160,13 +159,8 @@ class ParamStore:
                     r.w_t = self.w_arena[r._t_off:r._t_off + n_t]
                     pack.append(dict(src=r.weight, dst=r.w_t, mode=r.t_mode, cout=r.cout, cin=r.cin, kh=r.k, kw=r.k,
                                      rows_pad=r.t_rows, cols_pad=r.t_cols, shuffle=r.shuffle, count=n_t))
-            n_acc = r.acc_rows * r.acc_taps * r.acc_cols
-            r.acc = self.acc_arena[r._acc_off:r._acc_off + n_acc]
-            unpack.append(dict(src=r.acc, dst=self.grad_slice(r.weight), mode=r.fwd_mode, cout=r.cout, cin=r.cin, kh=r.k,
-                               kw=r.k, rows_pad=r.acc_rows, cols_pad=r.acc_cols, shuffle=r.shuffle, count=n_acc))
             if r.shuffle and r.bias is not None:
                 r.bias_packed = torch.zeros(r.cout_pad, dtype=F32, device=self.device)
-                r.bias_grad_packed = torch.zeros(r.cout_pad, dtype=F32, device=self.device)
                 self.bias_perm.append(r)
         for r in self.linears:
             n = r.nout_pad * r.K
@@ -174,15 +168,9 @@ class ParamStore:
             pack.append(dict(src=r.weight, dst=r.w_fwd, mode=L.PK_LINEAR, cout=r.nout, cin=r.C, kh=r.Hf, kw=r.Wf,
                              rows_pad=r.nout_pad, cols_pad=r.K, shuffle=0, count=n))
         self._pack_tab, self._pack_n, self._pack_blocks = ops.pack_table(pack, self.device)
-        self._unpack_tab, self._unpack_n, self._unpack_blocks = ops.pack_table(unpack, self.device)
         self._pack_desc = ops.elt(L.E_PACK_W, p=[self._pack_tab], i=[self._pack_n, self._pack_blocks])
-        self.unpack_desc = ops.elt(L.E_UNPACK_G, p=[self._unpack_tab], i=[self._unpack_n, self._unpack_blocks])
         self._watched = [r.weight for r in self.convs] + [r.weight for r in self.linears] + \
                         [r.bias for r in self.bias_perm]
-
-    def grad_slice(self, p: torch.Tensor) -> torch.Tensor:
-        o = self.offsets[id(p)]
-        return self.flat_grad[o:o + p.numel()]
 
     def ensure_packed(self):
         """Re-packs the bf16 operand copies if any watched parameter changed since the last pack (one kernel)."""
@@ -208,6 +196,47 @@ class ParamStore:
         return out
 
 
+class GradBuffers:
+    """Per-plan-instance gradient storage: the fp32 weight-gradient accumulators (packed order), the flat fp32 gradient
+    in parameters() order and the unpack table between them. Owned by the plan instance (not the module) so that
+    the backward passes of two outstanding calls of one module - D(real) and D(fake) - may run concurrently on two
+    streams. Allocated on the first backward that wants weight gradients."""
+
+    def __init__(self, store: ParamStore):
+        self.store = store
+        self.flat = None
+
+    def _ensure(self):
+        if self.flat is not None:
+            return
+        st = self.store
+        self.flat = torch.zeros(max(st.total, 4), dtype=F32, device=st.device)
+        self.acc_arena = torch.zeros(st.acc_elems, dtype=F32, device=st.device)
+        self._bgp: Dict[str, torch.Tensor] = {}
+        unpack = []
+        for r in st.convs:
+            n_acc = r.acc_rows * r.acc_taps * r.acc_cols
+            unpack.append(dict(src=self.acc(r), dst=self.grad_slice(r.weight), mode=r.fwd_mode, cout=r.cout, cin=r.cin,
+                               kh=r.k, kw=r.k, rows_pad=r.acc_rows, cols_pad=r.acc_cols, shuffle=r.shuffle, count=n_acc))
+        self._tab, n, blocks = ops.pack_table(unpack, st.device)
+        self.unpack_desc = ops.elt(L.E_UNPACK_G, p=[self._tab], i=[n, blocks])
+
+    def grad_slice(self, p: torch.Tensor) -> torch.Tensor:
+        self._ensure()
+        o = self.store.offsets[id(p)]
+        return self.flat[o:o + p.numel()]
+
+    def acc(self, r: ConvRec) -> torch.Tensor:
+        self._ensure()
+        return self.acc_arena[r._acc_off:r._acc_off + r.acc_rows * r.acc_taps * r.acc_cols]
+
+    def bias_grad_packed(self, r: ConvRec) -> torch.Tensor:
+        self._ensure()
+        if r.name not in self._bgp:
+            self._bgp[r.name] = torch.zeros(r.cout_pad, dtype=F32, device=self.store.device)
+        return self._bgp[r.name]
+
+
 # ------------------------------------------------------------------------------------------------ plan
 class Plan:
     """One instance = the workspaces + recorded programs of one module call at one input shape and mode.
@@ -216,6 +245,7 @@ class Plan:
     def __init__(self, store: ParamStore, B: int, H: int, W: int, training: bool):
         self.store, self.B, self.H, self.W, self.training = store, B, H, W, training
         self.device = store.device
+        self.grads = GradBuffers(store)
         self.bufs: Dict[str, torch.Tensor] = {}
         self.fwd = ops.Program()
         self.tape: List[Callable] = []
@@ -340,7 +370,7 @@ class Plan:
         dx = self.act(name + ".dx", x.B, x.H, x.W, C)
         prelu = act == L.ACT_PRELU
         need_reduce = has_bn or (want_w and (prelu or bias_grad is not None))
-        store = self.store
+        store = self.grads
         gp = ops.ptr(g.t, g.c0)
         xp = ops.ptr(x.t, x.c0)
         g2p = ops.ptr(g2.t, g2.c0) if g2 is not None else None
@@ -434,7 +464,7 @@ class Plan:
         block_n = dy.C if dy.C <= 128 else 128
         assert dy.C == rec.acc_rows, (rec.name, dy.C, rec.acc_rows)
         d = ops.wgrad_desc(x=x.t, N=x.B, H=x.H, W=x.W, C=x.C + x.c0, x_ld=x.ld, geom=geom, dy=dy.t, dy_ld=dy.ld,
-                           dy_c=dy.C, out=rec.acc, cout_valid=rec.acc_rows, block_n=block_n, x_c0=x.c0, dy_c0=dy.c0)
+                           dy_c=dy.C, out=self.grads.acc(rec), cout_valid=rec.acc_rows, block_n=block_n, x_c0=x.c0, dy_c0=dy.c0)
         prog.add(d)
 
     # ---- execution (set by the net definition: input_fn, output_fn, ingest_fn, grad_input_fn, post_backward)
@@ -443,7 +473,7 @@ class Plan:
         self.fwd.run()
         return self.output_fn()
 
-    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None):
+    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None, alias: bool = False):
         if not self.training and self.has_bn:
             raise NotImplementedError("torchsr_b200: backward through eval-mode BatchNorm is not implemented; call "
                                       ".train() for gradient computation (the reference trainers do)")
@@ -451,12 +481,13 @@ class Plan:
         prog = self.backward_program(want_x, want_w, seed)
         flat = None
         store = self.store
+        gb = self.grads
         early = prog.marks.get("early_grads")
         if want_w and ddp is not None and ddp.world > 1:
             # bucketed all-reduce launched from inside backward: the tail of the flat gradient (the classifier of a
             # discriminator) is complete after the first few launches and travels while the conv stack runs
             from .dist import bucket_slices
-            flat = torch.empty_like(store.flat_grad)
+            flat = torch.empty_like(gb.flat)
             early_from = self.early_from if early is not None else None
             buckets = bucket_slices(store.total, early_from)
             done = 0
@@ -465,14 +496,14 @@ class Plan:
                 done = early
                 for lo, hi in buckets:
                     if lo >= early_from:
-                        flat[lo:hi].copy_(store.flat_grad[lo:hi])
+                        flat[lo:hi].copy_(gb.flat[lo:hi])
                         ddp.allreduce_async(flat[lo:hi])
             prog.run(done, -1)
             for fn in self.post_backward:
                 fn()
             for lo, hi in buckets:
                 if early is None or lo < early_from:
-                    flat[lo:hi].copy_(store.flat_grad[lo:hi])
+                    flat[lo:hi].copy_(gb.flat[lo:hi])
                     ddp.allreduce_async(flat[lo:hi])
             ddp.wait()
         else:
@@ -480,7 +511,9 @@ class Plan:
             if want_w:
                 for fn in self.post_backward:
                     fn()
-                flat = store.flat_grad.clone()
+                # alias mode (set by the trainers, which zero the gradients before every backward): hand out views
+                # of this plan's flat buffer instead of a copy; valid until this plan instance runs backward again
+                flat = gb.flat if alias else gb.flat.clone()
         gx = self.grad_input_fn() if want_x else None
         return gx, flat
 
@@ -491,14 +524,15 @@ class Plan:
             prog = ops.Program()
             prog.add(ops.elt(L.E_ZERO, p=[self._zarena["bwd"]], i=[ZERO_ARENA_FLOATS * 4]))
             if want_w:
-                prog.add(ops.elt(L.E_ZERO, p=[self.store.acc_arena], i=[self.store.acc_arena.numel() * 4]))
+                self.grads._ensure()
+                prog.add(ops.elt(L.E_ZERO, p=[self.grads.acc_arena], i=[self.grads.acc_arena.numel() * 4]))
             g = seed
             self.slots.clear()
             for fn in reversed(self.tape):
                 g = fn(prog, g, want_x, want_w)
             self.last_g[key] = g
             if want_w:
-                prog.add(self.store.unpack_desc)
+                prog.add(self.grads.unpack_desc)
             self.bwd[key] = prog
         self.cur_g = self.last_g[key]
         return self.bwd[key]
@@ -616,7 +650,8 @@ class _PlanFn(torch.autograd.Function):
         want_x = ctx.needs_input_grad[2]
         want = list(ctx.needs_input_grad[3:])
         want_w = any(want)
-        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ctx.module._tsr.get("ddp"))
+        st = ctx.module._tsr
+        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, st.get("ddp"), st.get("alias_grads", False))
         grads = plan.store.grads_from_flat(flat, want) if want_w else [None] * len(want)
         lease.release()
         return (None, None, gx, *grads)

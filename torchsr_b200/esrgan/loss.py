@@ -47,6 +47,19 @@ class VGGLoss(nn.Module):
             object.__setattr__(self, "_bf16", f.eval())
         return self._bf16
 
+    def target_features(self, target: Tensor) -> Tensor:
+        """Features of the (constant) target image; lets a trainer compute them early, on another stream."""
+        with torch.no_grad():
+            if target.is_cuda:
+                return self._features_bf16()(target.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
+            return self.features(target)
+
+    def from_features(self, source: Tensor, target_features: Tensor) -> Tensor:
+        if source.is_cuda:
+            fs = self._features_bf16()(source.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
+            return torch.nn.functional.l1_loss(fs.float(), target_features.float())
+        return torch.nn.functional.l1_loss(self.features(source), target_features)
+
     def forward(self, source: Tensor, target: Tensor) -> Tensor:
         if source.is_cuda:
             f = self._features_bf16()

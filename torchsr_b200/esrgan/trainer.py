@@ -22,6 +22,7 @@ class ESRGANTrainer(SRGANTrainer):
     def _initialize_models(self) -> None:
         self.generator = Generator().to(self.device)
         self.discriminator = Discriminator().to(self.device)
+        self._configure_modules()
         if self.distributed:
             tdist.attach(self.generator, broadcast_buffers=True)
             tdist.attach(self.discriminator, broadcast_buffers=False)

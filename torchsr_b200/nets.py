@@ -73,7 +73,7 @@ def residual_block_stage(plan: Plan, prog, name: str, blk, ra: ConvRec, rb: Conv
 def subpixel_stage(plan: Plan, prog, name: str, layer, rec: ConvRec, x: Act, consumer_block_n: int = 64) -> Act:
     """PReLU(PixelShuffle2(conv(x)+b)) with the shuffle folded into the conv store (residual.py:45-47)."""
     B, H, W, C = x.B, x.H, x.W, rec.cout // 4
-    store = plan.store
+    store = plan.grads
     out = plan.act(name + ".out", B, 2 * H, 2 * W, C)
     pre = plan.act(name + ".pre", B, 2 * H, 2 * W, C)
     alpha = layer.prelu.weight
@@ -86,13 +86,13 @@ def subpixel_stage(plan: Plan, prog, name: str, layer, rec: ConvRec, x: Act, con
         assert g is dconv, "the consumer of a sub-pixel stage must honour its gradient hook"
         if want_w:
             bp.add(ops.elt(L.E_SUM_FINALIZE, p=[dap, store.grad_slice(alpha)], i=[1, 0], f=[1.0]))
-            plan.colsum(bp, name + ".db", g, rec.bias_grad_packed)
+            plan.colsum(bp, name + ".db", g, store.bias_grad_packed(rec))
             plan.conv_wgrad(bp, rec, x, g)
         return plan.conv_dgrad(bp, name, rec, g, x)
 
     def unpermute_bias_grad():
         c4 = rec.cout // 4
-        store.grad_slice(rec.bias).view(c4, 4).copy_(rec.bias_grad_packed.view(4, c4).t())
+        store.grad_slice(rec.bias).view(c4, 4).copy_(store.bias_grad_packed(rec).view(4, c4).t())
 
     plan.tape.append(bwd)
     plan.post_backward.append(unpermute_bias_grad)
@@ -104,7 +104,7 @@ def define_srgan_generator(m, plan: Plan, shape):
     if cin != 3:
         raise RuntimeError(f"Generator expects 3 input channels, got {cin}")
     R = _recs(plan)
-    store, fwd = plan.store, plan.fwd
+    store, fwd = plan.grads, plan.fwd
     r1 = R["conv1.0"]
     alpha1 = m.conv1[1].weight
     E1 = plan.act("E1", B, H, W, r1.epad)
@@ -254,7 +254,7 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
         raise RuntimeError(f"Discriminator(image_size={m.image_size}) expects [N,3,{m.image_size},{m.image_size}] "
                            f"inputs, got {tuple(shape)}")
     R = _recs(plan)
-    store, fwd = plan.store, plan.fwd
+    store, fwd = plan.grads, plan.fwd
     r0 = R["features.0"]
     E0 = plan.act("E0", B, H, W, r0.epad)
     f0 = plan.act("f0", B, H, W, r0.cout)
@@ -326,7 +326,7 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
             bp.add(ops.elt(L.E_LINEAR_WGRAD, p=[dpre1, xchw, store.grad_slice(l1.weight), store.grad_slice(l1.bias)],
                            i=[B, N1, K]))
             bp.mark("early_grads")     # everything from classifier.0.weight to the end of the flat gradient is final
-            plan.early_from = store.offsets[id(l1.weight)]
+            plan.early_from = plan.store.offsets[id(l1.weight)]
         dflat32 = plan.buf("dflat32", Bpad * K, F32)
         bp.add(ops.elt(L.E_ZERO, p=[dflat32], i=[Bpad * K * 4]))
         bn_ = next(b for b in (128, 64, 32, 16) if Bpad % b == 0)
@@ -387,7 +387,7 @@ def define_esrgan_generator(m, plan: Plan, shape):
     if cin != 3:
         raise RuntimeError(f"Generator expects 3 input channels, got {cin}")
     R = _recs(plan)
-    store, fwd = plan.store, plan.fwd
+    store, fwd = plan.grads, plan.fwd
     C, G, CT = 64, 32, 192
     n_rrdb = len(m.blocks)
     n_rdb = 3 * n_rrdb

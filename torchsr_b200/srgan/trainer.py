@@ -54,9 +54,18 @@ class SRGANTrainer:
         self._create_test_image()
 
     # ------------------------------------------------------------------ construction (reference :136-205)
+    def _configure_modules(self) -> None:
+        """Trainer-owned execution settings of the drop-in modules: gradients are handed to autograd as views of the
+        plan's flat buffer (no copy) - valid here because every backward is preceded by zero_grad() - and a second
+        CUDA stream carries the work that depends only on the real batch."""
+        for m in (self.generator, self.discriminator):
+            m._tsr["alias_grads"] = not self.distributed
+        self._side = torch.cuda.Stream(device=self.device) if self.device.type == 'cuda' else None
+
     def _initialize_models(self) -> None:
         self.generator = Generator().to(self.device)
         self.discriminator = Discriminator().to(self.device)
+        self._configure_modules()
         if self.distributed:
             # reference :143-157 wraps both in DistributedDataParallel; here: broadcast from rank 0 once, then the
             # modules all-reduce their own flat gradients (torchsr_b200/dist.py)
@@ -69,8 +78,11 @@ class SRGANTrainer:
         self.vgg_loss = VGGLoss().to(self.device)
 
     def _initialize_optimizers(self) -> None:
-        fused = self.device.type == 'cuda'
-        mk = lambda params: optim.Adam(params, lr=0.0001, betas=(0.9, 0.999), fused=fused)  # noqa: E731
+        cuda = self.device.type == 'cuda'
+        # fused multi-tensor Adam; capturable + tensor lr so that a whole training step can be replayed as one CUDA
+        # graph (graph_step) while StepLR keeps working (schedulers fill_() a tensor learning rate in place)
+        mk = lambda params: optim.Adam(params, lr=torch.tensor(0.0001, device=self.device) if cuda else 0.0001,  # noqa: E731
+                                       betas=(0.9, 0.999), fused=cuda, capturable=cuda)
         self.psnr_optimizer = mk(self.generator.parameters())
         self.disc_optimizer = mk(self.discriminator.parameters())
         self.gen_optimizer = mk(self.generator.parameters())
@@ -116,22 +128,79 @@ class SRGANTrainer:
         real_label = torch.full((batch_size, 1), 1, dtype=low_res.dtype, device=self.device)
         fake_label = torch.full((batch_size, 1), 0, dtype=low_res.dtype, device=self.device)
 
+        cur, side = torch.cuda.current_stream(self.device), self._side
         self.discriminator.zero_grad()
+        # stream B: what depends only on the real batch - D(real) forward (and, in backward, its gradients) and the
+        # VGG features of the target - runs beside the generator forward on stream A. Same arithmetic as the
+        # reference's sequential statements (:444-448); D(fake) still follows D(real), so the BatchNorm running
+        # statistics are updated in the reference's order.
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            p_real = self.discriminator(high_res)
+            done_real = side.record_event()
+            hr_feats = self.vgg_loss.target_features(high_res) if hasattr(self.vgg_loss, 'target_features') else None
         super_res = self.generator(low_res)
-        disc_loss_real = self.bce_loss(self.discriminator(high_res), real_label)
-        disc_loss_fake = self.bce_loss(self.discriminator(super_res.detach()), fake_label)
+        cur.wait_event(done_real)
+        p_fake = self.discriminator(super_res.detach())
+        cur.wait_stream(side)
+        p_real.record_stream(cur)
+        disc_loss_real = self.bce_loss(p_real, real_label)
+        disc_loss_fake = self.bce_loss(p_fake, fake_label)
         disc_loss = disc_loss_real + disc_loss_fake
         disc_loss.backward()
         self.disc_optimizer.step()
 
         self.generator.zero_grad()
-        content_loss = self.vgg_loss(super_res, high_res.detach())
+        # generator step: VGG(super_res) on stream B beside D(super_res) on stream A (:455-457)
+        side.wait_stream(cur)
+        super_res.record_stream(side)
+        with torch.cuda.stream(side):
+            if hr_feats is not None:
+                content_loss = self.vgg_loss.from_features(super_res, hr_feats)
+            else:
+                content_loss = self.vgg_loss(super_res, high_res.detach())
         with tdist.frozen(self.discriminator):
             adversarial_loss = self.bce_loss(self.discriminator(super_res), real_label)
+        cur.wait_stream(side)
+        content_loss.record_stream(cur)
         gen_loss = content_loss + 0.001 * adversarial_loss
         gen_loss.backward()
         self.gen_optimizer.step()
         return gen_loss.detach()
+
+    # ------------------------------------------------------------------ whole-step CUDA graph
+    def graph_step(self, low_res: Tensor, high_res: Tensor, step: int = 0, kind: str = 'gan') -> Tensor:
+        """`_gan_loop` (kind='gan') or `_pretrain_step` (kind='psnr') replayed as ONE CUDA graph: the first call for a
+        batch shape warms up eagerly, captures the whole step (module launch lists, losses, backward, Adam) and every
+        later call copies the batch into static input buffers and replays. Results are identical to the eager step; the
+        returned loss tensor is a static buffer that the next call overwrites."""
+        key = (kind, tuple(low_res.shape), tuple(high_res.shape))
+        g = self._graphs.get(key) if hasattr(self, '_graphs') else None
+        if g is None:
+            if not hasattr(self, '_graphs'):
+                self._graphs = {}
+            fn = (lambda a, b: self._gan_loop(a, b, step)) if kind == 'gan' else self._pretrain_step
+            s_lr = torch.empty(low_res.shape, dtype=torch.float32, device=self.device)
+            s_hr = torch.empty(high_res.shape, dtype=torch.float32, device=self.device)
+            s_lr.copy_(low_res, non_blocking=True)
+            s_hr.copy_(high_res, non_blocking=True)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(3):          # warm-up: builds plans, captures the per-module launch lists, sizes pools
+                    fn(s_lr, s_hr)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss = fn(s_lr, s_hr)
+            g = self._graphs[key] = (graph, s_lr, s_hr, loss)
+            return loss
+        graph, s_lr, s_hr, loss = g
+        s_lr.copy_(low_res, non_blocking=True)
+        s_hr.copy_(high_res, non_blocking=True)
+        graph.replay()
+        return loss
 
     # ------------------------------------------------------------------ evaluation / checkpoints
     def _model_state(self, epoch: int, phase: str) -> dict:
