@@ -228,7 +228,7 @@ def run_b200(args):
 
     # public step API: trainer.graph_step replays the whole _gan_loop as one CUDA graph (same arithmetic as the eager
     # call, see srgan/trainer.py); --eager times the plain Python call instead
-    step_fn = trainer._gan_loop if (args.eager or distributed) else trainer.graph_step
+    step_fn = trainer._gan_loop if args.eager else trainer.graph_step
     for s in range(max(args.warmup, 3)):
         step_fn(lr_d, hr_d, s)
     # kernels of ours per step (graph replays do not pass through the library's launch counter)
@@ -262,7 +262,7 @@ def run_b200(args):
                                (args.batch, "replaced by MSE (--no-vgg)" if args.no_vgg else
                                 "executed by PyTorch/cuDNN under bf16 autocast (not one of this repo's kernels)"),
                    "parallelism": f"dp{world}", "global_batch": args.batch * world,
-                   "step_api": "SRGANTrainer._gan_loop (eager)" if (args.eager or distributed) else
+                   "step_api": "SRGANTrainer._gan_loop (eager)" if args.eager else
                                "SRGANTrainer.graph_step (whole step replayed as one CUDA graph)",
                    "l2": "per-step working set (fp32 weights + Adam state + activations, > 0.5 GB) exceeds the 126 MB "
                          "L2; no explicit flush between steps"},

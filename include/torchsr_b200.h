@@ -84,7 +84,17 @@ typedef struct tsr_conv_desc {
      touch columns < res_cols (0 = all) */
   const void* res2;
   float res_scale, res2_scale;
-  int32_t res_cols, _pad0;
+  int32_t res_cols;
+  int32_t w_static;         /* 1: `w` is not written by any kernel launched before this one on the stream since the
+                               last full dependency (real, pre-packed weights): its tiles may be fetched before a
+                               programmatically-launched kernel waits for its predecessor */
+  /* fused BatchNorm / activation backward reduction (data-gradient convs, see csrc/conv_params.h): v is the gradient
+     w.r.t. act(BN(x)); the epilogue stores dz = v * act'(x*scale+shift) and accumulates per column sum(dz), sum(dz*x)
+     into stats_partial and the PReLU slope gradient into dalpha_partial. bnr_x uses the aux strides. */
+  const void* bnr_x;
+  const float* bnr_coef;    /* [4][bnr_c] forward coefficients (scale, shift, mean, invstd) or null (z = x) */
+  const float* bnr_prelu;
+  int32_t bnr_act, bnr_c;
   int64_t* trace;           /* optional debug: per-CTA clock64 stamps [grid][40] (null in production) */
 } tsr_conv_desc_t;
 

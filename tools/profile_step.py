@@ -23,13 +23,14 @@ def main():
     if novgg:
         tr.vgg_loss = lambda a, b: torch.nn.functional.mse_loss(a, b)
     lr, hr = torch.rand(B, 3, 24, 24, device="cuda"), torch.rand(B, 3, 96, 96, device="cuda")
+    step_fn = tr._gan_loop if os.environ.get("EAGER") else tr.graph_step
     for s in range(5):
-        tr._gan_loop(lr, hr, s)
+        step_fn(lr, hr, s)
     torch.cuda.synchronize()
     steps = 3
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         for s in range(steps):
-            tr._gan_loop(lr, hr, s)
+            step_fn(lr, hr, s)
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     agg = {}
@@ -66,8 +67,24 @@ def main():
           [(k, round(v[0] / steps, 1), round(v[1] / steps)) for k, v in sorted(cpu_ops.items(), key=lambda kv: -kv[1][1])[:14]])
     print(f"batch {B}: {steps} steps, GPU span {span / steps / 1e3:.3f} ms/step, kernel-busy {busy / steps / 1e3:.3f} ms/step, "
           f"{len(evs) / steps:.0f} GPU activities/step")
-    for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
-        print(f"{t / steps:9.1f} us/step {n / steps:6.1f} x {t / n:8.2f} us  {name}")
+    dump = os.environ.get("TIMELINE")
+    if dump:
+        # last step only: start (us since the step's first activity), duration, stream id, name
+        kev = [k for k in prof.profiler.kineto_results.events() if k.device_type() == torch.autograd.DeviceType.CUDA]
+        kev.sort(key=lambda k: k.start_ns())
+        last = kev[len(kev) * (steps - 1) // steps:]
+        z = last[0].start_ns()
+        with open(dump, "w") as f:
+            for k in last:
+                f.write(f"{(k.start_ns() - z) / 1e3:.1f},{k.duration_ns() / 1e3:.1f},{k.device_resource_id()},{k.name()[:90]}\n")
+    durs = {}
+    for e in evs:
+        durs.setdefault(e.name[:70], []).append(e.device_time)
+    for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("TOP", "40"))]:
+        d = sorted(durs[name])
+        q = lambda f: d[min(len(d) - 1, int(f * len(d)))]  # noqa: E731
+        print(f"{t / steps:9.1f} us/step {n / steps:6.1f} x {t / n:8.2f} us  [min {d[0]:.1f} p25 {q(.25):.1f} p50 {q(.5):.1f} "
+              f"p75 {q(.75):.1f} max {d[-1]:.1f}]  {name[:60]}")
 
 
 if __name__ == "__main__":

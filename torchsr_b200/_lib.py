@@ -41,7 +41,9 @@ class ConvDesc(C.Structure):
         ("shuf_c", C.c_int32),
         ("acc_scale", C.c_float), ("leaky_slope", C.c_float),
         ("res2", C.c_void_p), ("res_scale", C.c_float), ("res2_scale", C.c_float), ("res_cols", C.c_int32),
-        ("_pad0", C.c_int32),
+        ("w_static", C.c_int32),
+        ("bnr_x", C.c_void_p), ("bnr_coef", C.c_void_p), ("bnr_prelu", C.c_void_p), ("bnr_act", C.c_int32),
+        ("bnr_c", C.c_int32),
         ("trace", C.c_void_p),
     ]
 

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libtorchsr_b200.so")
 SOURCES = ["api.cu", "conv_igemm.cu", "conv_wgrad.cu", "eltwise.cu"]
-HEADERS = ["ptx.cuh", "conv_params.h", os.path.join("..", "..", "include", "torchsr_b200.h")]
+HEADERS = ["ptx.cuh", "conv_params.h", "launch.h", os.path.join("..", "..", "include", "torchsr_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -17,9 +17,9 @@
 #include "conv_params.h"
 
 namespace tsr {
-cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream);
-cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int splits, cudaStream_t stream);
-cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st);
+cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream, bool pdl);
+cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int splits, cudaStream_t stream, bool pdl);
+cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl);
 size_t conv_igemm_smem_bytes(const ConvParams& p);
 size_t conv_wgrad_smem_bytes(const WgradParams& p);
 }  // namespace tsr
@@ -178,6 +178,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   p.block_n = d.block_n;
   p.a_mode = d.a_mode;
   p.a_c0 = d.a_c0;
+  p.w_static = d.w_static;
   p.b_rows_per_tap = d.cout_pad;
   memcpy(p.tap_off, d.tap_off, sizeof(p.tap_off));
   memcpy(p.tap_wrow, d.tap_wrow, sizeof(p.tap_wrow));
@@ -236,6 +237,14 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   e.res_scale = d.res_scale;
   e.res2_scale = d.res2_scale;
   e.res_cols = d.res_cols > 0 ? d.res_cols : (1 << 30);
+  e.bnr_x = d.bnr_x;
+  e.bnr_coef = d.bnr_coef;
+  e.bnr_prelu = d.bnr_prelu;
+  e.bnr_act = d.bnr_act;
+  e.bnr_c = d.bnr_c;
+  if (e.bnr_x && !e.stats_partial) return fail(-20, "the fused BatchNorm-backward reduction needs stats_partial");
+  if (e.bnr_x && e.bnr_act == TSR_ACT_PRELU && !e.bnr_prelu) return fail(-20, "bnr PReLU needs the slope pointer");
+  if (e.bnr_x && e.bwd_z) return fail(-20, "bnr_x and bwd_z are mutually exclusive");
   if (!e.out) return fail(-20, "out is null");
   if ((e.act == TSR_ACT_PRELU || e.bwd_act == TSR_ACT_PRELU) && !e.prelu) return fail(-20, "PReLU needs the slope pointer");
   if (e.n_valid % 16) return fail(-20, "n_valid must be a multiple of 16");
@@ -367,12 +376,25 @@ bool use_side_stream() {
   return g_use_side == 1;
 }
 
+int g_use_pdl = -1;
+bool use_pdl() {
+  if (g_use_pdl < 0) {
+    const char* e = getenv("TSR_PDL");
+    g_use_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_use_pdl == 1;
+}
+
 // Weight-gradient GEMMs only feed the final unpack, so they run on a side stream forked off the main chain right
-// after the kernel that produced their dY (a parallel branch once the range is captured into a CUDA graph) and
-// are joined before the first non-wgrad op that follows the last of them in program order is NOT required: the
-// join happens once, before the op that consumes the accumulators (the unpack kernel / the end of the range).
+// after the kernel that produced their dY (a parallel branch once the range is captured into a CUDA graph); the
+// branch is joined once, before the op that consumes the accumulators (the unpack kernel / the end of the range).
+//
+// Programmatic dependent launch: a kernel on the main chain is launched with the PDL attribute when the operation
+// right before it on that stream is another kernel of this range (not a memset, not the join of the side branch):
+// its CTAs are then staged while the predecessor drains, and in a captured graph the edge becomes programmatic.
 int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
   bool side = use_side_stream();
+  const bool pdl_on = use_pdl();
   if (side && !g_side_stream) {
     if (cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming) != cudaSuccess ||
@@ -380,9 +402,11 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
       return fail(-45, "side stream setup failed");
   }
   bool forked = false;
+  bool chain = false;   // previous op on `st` was one of our kernels
   auto join = [&]() -> cudaError_t {
     if (!forked) return cudaSuccess;
     forked = false;
+    chain = false;
     cudaError_t e = cudaEventRecord(g_join_event, g_side_stream);
     if (e != cudaSuccess) return e;
     return cudaStreamWaitEvent(st, g_join_event, 0);
@@ -394,20 +418,24 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
       ce = cudaEventRecord(g_fork_event, st);
       if (ce == cudaSuccess) ce = cudaStreamWaitEvent(g_side_stream, g_fork_event, 0);
       if (ce == cudaSuccess)
-        ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, g_side_stream);
+        ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, g_side_stream, false);
       forked = true;
     } else if (op.kind == tsr_prog::WGRAD) {
-      ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st);
+      ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st, pdl_on && chain);
+      chain = true;
     } else {
       // the unpack kernel reads every accumulator: join the branch first
       if (op.kind == tsr_prog::ELT && op.elt.kind == TSR_E_UNPACK_G) {
         ce = join();
         if (ce != cudaSuccess) return fail(-45, "join failed: %s", cudaGetErrorString(ce));
       }
-      if (op.kind == tsr_prog::CONV)
-        ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st);
-      else
-        ce = tsr::launch_elt(op.elt, st);
+      if (op.kind == tsr_prog::CONV) {
+        ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st, pdl_on && chain);
+        chain = true;
+      } else {
+        ce = tsr::launch_elt(op.elt, st, pdl_on && chain);
+        chain = op.elt.kind != TSR_E_ZERO;
+      }
     }
     if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
   }
@@ -427,7 +455,7 @@ int64_t tsr_launch_count(void) { return g_launches.load(); }
 int tsr_conv(const tsr_conv_desc_t* d, void* stream) {
   ConvLaunch L;
   if (int e = build_conv(*d, &L)) return e;
-  cudaError_t ce = tsr::launch_conv_igemm(L.p, L.tiles_n, L.splits, static_cast<cudaStream_t>(stream));
+  cudaError_t ce = tsr::launch_conv_igemm(L.p, L.tiles_n, L.splits, static_cast<cudaStream_t>(stream), false);
   if (ce != cudaSuccess) return fail(-40, "conv launch failed: %s", cudaGetErrorString(ce));
   g_launches++;
   return 0;
@@ -436,7 +464,7 @@ int tsr_conv(const tsr_conv_desc_t* d, void* stream) {
 int tsr_wgrad(const tsr_wgrad_desc_t* d, void* stream) {
   WgradLaunch L;
   if (int e = build_wgrad(*d, &L)) return e;
-  cudaError_t ce = tsr::launch_conv_wgrad(L.p, L.gsets, L.tiles_n, L.splits, static_cast<cudaStream_t>(stream));
+  cudaError_t ce = tsr::launch_conv_wgrad(L.p, L.gsets, L.tiles_n, L.splits, static_cast<cudaStream_t>(stream), false);
   if (ce != cudaSuccess) return fail(-40, "wgrad launch failed: %s", cudaGetErrorString(ce));
   g_launches++;
   return 0;
@@ -444,7 +472,7 @@ int tsr_wgrad(const tsr_wgrad_desc_t* d, void* stream) {
 
 int tsr_elt(const tsr_elt_desc_t* d, void* stream) {
   if (int e = ensure_init()) return e;
-  cudaError_t ce = tsr::launch_elt(*d, static_cast<cudaStream_t>(stream));
+  cudaError_t ce = tsr::launch_elt(*d, static_cast<cudaStream_t>(stream), false);
   if (ce != cudaSuccess) return fail(-41, "elementwise kind %d launch failed: %s", d->kind, cudaGetErrorString(ce));
   g_launches++;
   return 0;

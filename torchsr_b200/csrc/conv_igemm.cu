@@ -13,14 +13,16 @@
 // Reference behaviour being replaced: every nn.Conv2d / nn.Linear call on the SRGAN/ESRGAN path
 // (torchsr/srgan/generator.py:38-58, residual.py:27,64,67, discriminator.py:31-69 and the esrgan twins).
 #include "conv_params.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace tsr {
 
 namespace {
 
-constexpr int kHeaderBytes = 10240;  // barriers + epilogue scratch, tiles start here (1024-aligned)
+constexpr int kHeaderBytes = 13312;  // barriers + epilogue scratch, tiles start here (1024-aligned)
 constexpr int kScratchOff = 1024;    // float scratch[4 warps][256 cols][2]
+constexpr int kColVecOff = 9216 + 64; // float colvec[3][256]: bias, BatchNorm scale, shift of this CTA's columns
 
 __device__ __forceinline__ void butterfly16(float (&v)[16], int lane, float& out) {
   // Sum each of the 16 per-lane values across the 32 lanes of the warp with 16 shuffles.
@@ -117,19 +119,40 @@ __device__ __forceinline__ void producer_loop(const ConvParams& p, uint32_t bar_
     tap = it_begin / kc_per_tap;
     kc = it_begin - tap * kc_per_tap;
   }
+  // Weight tiles of the first ring pass do not depend on the previous kernel of the stream (w_static): arm the
+  // barriers and fetch them before the programmatic-launch wait, so only the activation loads follow it.
+  const int pre = p.w_static ? min(stages, it_end - it_begin) : 0;
+  if (elect_one()) {
+    uint32_t d = tiles + a_bytes;
+    for (int j = 0; j < pre; ++j) {
+      const int it = it_begin + j;
+      int ktap = 0, kkc = it;
+      if (A_MODE == 0) {
+        ktap = it / kc_per_tap;
+        kkc = it - ktap * kc_per_tap;
+      }
+      const int brow = (A_MODE == 0 ? p.tap_wrow[ktap] * p.b_rows_per_tap : 0) + b_row0;
+      mbar_arrive_expect_tx(bar_full + 8 * j, tx);
+      tma_load_2d(d, &p.tmB, bar_full + 8 * j, kkc * block_k, brow);
+      d += stage_bytes;
+    }
+  }
+  __syncwarp();
+  pdl_sync();
   int s = 0;
   uint32_t ph = 1;  // parity to wait for on the empty barrier (first pass over the ring passes immediately)
   uint32_t dst = tiles;
   for (int it = it_begin; it < it_end; ++it) {
     if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) break;
     const uint32_t full = bar_full + 8 * s;
+    const bool fresh = it - it_begin >= pre;   // barrier not armed / weights not fetched yet
     if (A_MODE == 0) {
       const uint32_t off = p.tap_off[tap];
       const int brow = p.tap_wrow[tap] * p.b_rows_per_tap + b_row0;
       if (elect_one()) {
-        mbar_arrive_expect_tx(full, tx);
+        if (fresh) mbar_arrive_expect_tx(full, tx);
         tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
-        tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, brow);
+        if (fresh) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, brow);
       }
       if (++kc == kc_per_tap) {
         kc = 0;
@@ -137,18 +160,18 @@ __device__ __forceinline__ void producer_loop(const ConvParams& p, uint32_t bar_
       }
     } else if (A_MODE == 1) {
       if (elect_one()) {
-        mbar_arrive_expect_tx(full, tx);
+        if (fresh) mbar_arrive_expect_tx(full, tx);
         tma_load_2d(dst, &p.tmA, full, kc * block_k, m0);
-        tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+        if (fresh) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
       }
       ++kc;
     } else {
       // MN-major A: two [block_k rows (K)] x [64 M-elements] boxes
       if (elect_one()) {
-        mbar_arrive_expect_tx(full, tx);
+        if (fresh) mbar_arrive_expect_tx(full, tx);
         tma_load_2d(dst, &p.tmA, full, m0, kc * block_k);
         tma_load_2d(dst + block_k * 128, &p.tmA, full, m0 + 64, kc * block_k);
-        tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+        if (fresh) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
       }
       ++kc;
     }
@@ -220,7 +243,7 @@ __device__ __forceinline__ void mma_loop(const ConvParams& p, uint32_t bar_full,
 }
 
 template <int A_MODE>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -269,10 +292,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const int m0 = tile_m * kBlockM;
 
   if (warp == 0) {
-    producer_loop<A_MODE>(p, bar_full, bar_empty, tiles, m0, tile_n, it_begin, it_end, trace);
+    producer_loop<A_MODE>(p, bar_full, bar_empty, tiles, m0, tile_n, it_begin, it_end, trace);   // calls pdl_sync()
   } else if (warp == 1) {
+    pdl_sync();
     mma_loop<A_MODE>(p, bar_full, bar_empty, bar_tmem, tiles, tmem_base, it_end - it_begin, trace);
   } else {
+    pdl_sync();   // the epilogue reads residuals / statistics buffers written by earlier kernels of the stream
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the 16-column chunks.
     const EpiParams& e = p.epi;
@@ -311,12 +336,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const bool out_f32 = e.out_f32 != 0;
     const float alpha = (e.prelu != nullptr) ? __ldg(e.prelu) : 0.f;
     const float bslope = (bwd_act == ACT_PRELU) ? alpha : (bwd_act == ACT_LEAKY ? leaky : 0.f);
+    const void* bnr_x = e.bnr_x;
+    const int bnr_act = e.bnr_act;
+    const float bnr_slope = (bnr_act == ACT_PRELU) ? __ldg(e.bnr_prelu) : (bnr_act == ACT_LEAKY ? leaky : 0.f);
     float dalpha = 0.f;
     const int chunks = p.block_n >> 4;
     const int ch_begin = half ? (chunks + 1) >> 1 : 0;
     const int ch_end = half ? chunks : (chunks + 1) >> 1;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const int colbase = tile_n * p.block_n;
+    // The auxiliary operands of the epilogue (residuals, activation-backward tensor, raw BatchNorm input) do not
+    // depend on the accumulator: pull this thread's rows into L1 while the main loop runs, so that the dependent
+    // global loads of the chunk loop below hit L1 instead of paying an L2 / HBM round trip per chunk.
+    if (valid && out_mode != OUT_GEMM_T_ATOMIC) {
+      const int c_lo = colbase + ch_begin * 16, c_hi = min(colbase + ch_end * 16, n_valid);
+      const void* aux_ptrs[4] = {res, e.res2, bwd_z, bnr_x};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        if (aux_ptrs[a] == nullptr) continue;
+        if (a < 2 && c_lo >= e.res_cols) continue;
+        const char* row = reinterpret_cast<const char*>(aux_ptrs[a]) + (aux_base + c_lo) * 2;
+        for (int b = 0; b < (c_hi - c_lo) * 2; b += 64) prefetch_l1(row + b);
+      }
+    }
+    // per-column vectors of this CTA's tile -> shared memory, once (the chunk loop reads them as broadcasts)
+    float* s_bias = reinterpret_cast<float*>(smem_gen + kColVecOff);
+    float* s_sc = s_bias + 256;
+    float* s_sh = s_sc + 256;
+    {
+      const int et = threadIdx.x - 64;
+      if (et < p.block_n) {
+        const int c = colbase + et;
+        s_bias[et] = bias != nullptr ? __ldg(bias + c) : 0.f;
+        const bool hc = bnr_x != nullptr && e.bnr_coef != nullptr && c < e.bnr_c;
+        s_sc[et] = hc ? __ldg(e.bnr_coef + c) : 1.f;
+        s_sh[et] = hc ? __ldg(e.bnr_coef + e.bnr_c + c) : 0.f;
+      }
+      named_bar_sync(1, kConvThreads - 64);
+    }
     const bool ok = mbar_wait(bar_tmem, 0, e.err, 3);
     tc_fence_after();
     if (trace && threadIdx.x == 64) trace[5] = clock64();
@@ -332,10 +389,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         const bool st = valid && col0 < n_valid;
         if (bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(bias + col0);
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 16);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 b4 = __ldg(bp + i);
+            const float4 b4 = bp[i];
             v[4 * i] += b4.x;
             v[4 * i + 1] += b4.y;
             v[4 * i + 2] += b4.z;
@@ -370,6 +427,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             for (int i = 0; i < 16; ++i) v[i] += z[i] * rs2;
           }
         }
+        float xr[16];
+        if (bnr_x != nullptr) {
+          if (st) {
+            load_bf16x16(bnr_x, aux_base + col0, xr);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xr[i] = 0.f;
+          }
+          if (bnr_act != ACT_NONE) {
+            const float* sc = s_sc + ch * 16;
+            const float* sh = s_sh + ch * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float z = xr[i] * sc[i] + sh[i];
+              if (z <= 0.f) {
+                dalpha += v[i] * z;
+                v[i] *= bnr_slope;
+              }
+            }
+          }
+        }
         if (want_stats) {
           if (!valid) {
 #pragma unroll
@@ -377,7 +455,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
           }
           float sq[16], s1, s2;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+          for (int i = 0; i < 16; ++i) sq[i] = v[i] * (bnr_x != nullptr ? xr[i] : v[i]);
           butterfly16(v, lane, s1);
           butterfly16(sq, lane, s2);
           if ((lane & 1) == 0) {
@@ -457,7 +535,7 @@ size_t conv_igemm_smem_bytes(const ConvParams& p) {
 }
 
 template <int A_MODE>
-static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -465,17 +543,17 @@ static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cuda
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_igemm_kernel<A_MODE><<<grid, kConvThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaError_t e = launch_k(conv_igemm_kernel<A_MODE>, grid, dim3(kConvThreads), smem, stream, pdl, p);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream) {
+cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream, bool pdl) {
   const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
   dim3 grid(tiles_m, tiles_n, splits);
   const size_t smem = conv_igemm_smem_bytes(p);
-  if (p.a_mode == 0) return launch_mode<0>(p, grid, smem, stream);
-  if (p.a_mode == 1) return launch_mode<1>(p, grid, smem, stream);
-  return launch_mode<2>(p, grid, smem, stream);
+  if (p.a_mode == 0) return launch_mode<0>(p, grid, smem, stream, pdl);
+  if (p.a_mode == 1) return launch_mode<1>(p, grid, smem, stream, pdl);
+  return launch_mode<2>(p, grid, smem, stream, pdl);
 }
 
 }  // namespace tsr

@@ -46,6 +46,15 @@ struct EpiParams {
   float leaky_slope;
   float res_scale, res2_scale;
   int res_cols;          // residuals only touch columns < res_cols
+  // Fused BatchNorm / activation backward reduction (data-gradient convs): the value v computed so far is the gradient
+  // w.r.t. y = act(BN(x)); with z = x*scale+shift (scale/shift from bnr_coef, identity when null) the epilogue turns
+  // it into dz = v * act'(z), stores dz, and accumulates per column sum(dz) and sum(dz*x) into stats_partial (and
+  // sum(v*z*[z<=0]) into dalpha_partial) - the reductions bn_bwd_reduce_kernel would otherwise make in a second pass.
+  const void* bnr_x;     // bf16 raw conv output x of the BatchNorm being differentiated (aux addressing), or null
+  const float* bnr_coef; // [4][bnr_c]: scale, shift, mean, invstd (forward coefficients) or null
+  const float* bnr_prelu;
+  int bnr_act;
+  int bnr_c;
 };
 
 struct ConvParams {
@@ -66,6 +75,7 @@ struct ConvParams {
   int iters_per_split;  // K iterations handled per blockIdx.z
   int stages;
   int tmem_cols;
+  int w_static;    // the B operand is not written by any kernel of the enclosing stream segment (real weights)
   // derived on the host so that the single-thread producer / MMA loops stay short
   uint32_t a_bytes, b_bytes, stage_bytes;
   uint32_t ksteps;      // block_k / 16

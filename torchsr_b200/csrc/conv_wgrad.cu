@@ -11,6 +11,7 @@
 // Reference behaviour being replaced: autograd's convolution_backward (weight part) for every nn.Conv2d on
 // the path, e.g. torchsr/srgan/residual.py:64,67.
 #include "conv_params.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace tsr {
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_wgrad_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
+  pdl_sync();   // both operands (layer input, dY) come from earlier kernels of the stream
   const int pix_begin = split * p.stages_per_cta * p.pix_per_stage;
   int n_iters = p.stages_per_cta;
   {
@@ -233,7 +235,7 @@ size_t conv_wgrad_smem_bytes(const WgradParams& p) {
   return 1024 + kWgHeader + static_cast<size_t>(p.stages) * stage_bytes;
 }
 
-cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int splits, cudaStream_t stream) {
+cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int splits, cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -241,8 +243,8 @@ cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int 
     attr_set = true;
   }
   dim3 grid(gsets, tiles_n, splits);
-  conv_wgrad_kernel<<<grid, kWgradThreads, conv_wgrad_smem_bytes(p), stream>>>(p);
-  return cudaGetLastError();
+  cudaError_t e = launch_k(conv_wgrad_kernel, grid, dim3(kWgradThreads), conv_wgrad_smem_bytes(p), stream, pdl, p);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace tsr

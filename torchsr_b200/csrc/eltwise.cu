@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include "../../include/torchsr_b200.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace tsr {
@@ -46,6 +47,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // E[n,h,w,(kh*KW+kw)*C+c] = x[n,c,h+sign*(kh-ph),w+sign*(kw-pw)] (0 outside), columns >= KH*KW*C are 0.
 __global__ void im2row_kernel(const float* __restrict__ x, bf16* __restrict__ E, int B, int C, int H, int W, int KH,
                               int KW, int ph, int pw, int sign, int Epad) {
+  pdl_sync();
   const int groups = Epad / 8;
   const long long total = static_cast<long long>(B) * H * W * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -80,6 +82,7 @@ __global__ void im2row_kernel(const float* __restrict__ x, bf16* __restrict__ E,
 __global__ void gather_out_kernel(const void* __restrict__ T, float* __restrict__ out, const float* __restrict__ bias,
                                   int B, int C, int H, int W, int KH, int KW, int ph, int pw, int sign, int Tld,
                                   int t_bf16) {
+  pdl_sync();
   const long long total = static_cast<long long>(B) * C * H * W;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -107,6 +110,7 @@ __global__ void gather_out_kernel(const void* __restrict__ T, float* __restrict_
 // channels are processed in groups of 8 (C%8==0)
 __global__ void nchw2nhwc_kernel(const float* __restrict__ x, bf16* __restrict__ y, int B, int C, int H, int W, int ld,
                                  int off) {
+  pdl_sync();
   const int groups = C / 8;
   const long long hw = static_cast<long long>(H) * W;
   const long long total = static_cast<long long>(B) * groups * hw;
@@ -124,6 +128,7 @@ __global__ void nchw2nhwc_kernel(const float* __restrict__ x, bf16* __restrict__
 // NHWC2NCHW: p0 = x bf16 NHWC (ld, off), p1 = y fp32 NCHW; i: 0 B,1 C,2 H,3 W,4 ld,5 off, 6 accumulate
 __global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W, int ld,
                                  int off, int accumulate) {
+  pdl_sync();
   const int groups = C / 8;
   const long long hw = static_cast<long long>(H) * W;
   const long long total = static_cast<long long>(B) * groups * hw;
@@ -170,42 +175,42 @@ struct BnActArgs {
   float leaky, res_scale, x_scale, eps, momentum;
 };
 
+constexpr int kMaxBnC = 512;   // widest BatchNorm on the path (discriminator 512 channels)
+
+__device__ __forceinline__ void lds8(const float* s, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// The per-channel coefficients are derived ONCE per block into shared memory (one or two channels per thread);
+// the row loop then costs two 16-byte loads and one store per 8 channels. Two rows are in flight per thread.
 __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
-  const int groups = a.C / 8;
-  const long long total = a.M * groups;
-  const float slope = a.act == TSR_ACT_PRELU ? __ldg(a.alpha) : a.leaky;
-  const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
-  const int g = static_cast<int>(idx0 % groups);  // constant per thread: the grid stride is a multiple of `groups`
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = g * 8 + j;
-    float mean = 0.f, var = 1.f, gm = 1.f, bt = 0.f;
+  __shared__ __align__(16) float s_sc[kMaxBnC], s_sh[kMaxBnC];
+  pdl_sync();
+  const int C = a.C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float sc = 1.f, sh = 0.f;
     if (a.mode != 0) {
-      gm = a.gamma ? __ldg(a.gamma + c) : 1.f;
-      bt = a.beta ? __ldg(a.beta + c) : 0.f;
-    }
-    if (a.mode == 1) {
-      const float inv_n = 1.f / static_cast<float>(a.count);
-      mean = __ldg(a.stats + 2 * c) * inv_n;
-      var = fmaxf(__ldg(a.stats + 2 * c + 1) * inv_n - mean * mean, 0.f);
-    } else if (a.mode == 2) {
-      mean = a.rm[c];
-      var = a.rv[c];
-    }
-    if (a.mode == 0) {
-      sc[j] = 1.f;
-      sh[j] = 0.f;
-    } else {
+      const float gm = a.gamma ? __ldg(a.gamma + c) : 1.f;
+      const float bt = a.beta ? __ldg(a.beta + c) : 0.f;
+      float mean, var;
+      if (a.mode == 1) {
+        const float inv_n = 1.f / static_cast<float>(a.count);
+        mean = a.stats[2 * c] * inv_n;
+        var = fmaxf(a.stats[2 * c + 1] * inv_n - mean * mean, 0.f);
+      } else {
+        mean = a.rm[c];
+        var = a.rv[c];
+      }
       const float invstd = rsqrtf(var + a.eps);
-      sc[j] = gm * invstd;
-      sh[j] = bt - mean * sc[j];
-      if (blockIdx.x == 0 && threadIdx.x < groups) {
+      sc = gm * invstd;
+      sh = bt - mean * sc;
+      if (blockIdx.x == 0) {
         if (a.coef) {
-          a.coef[0 * a.C + c] = sc[j];
-          a.coef[1 * a.C + c] = sh[j];
-          a.coef[2 * a.C + c] = mean;
-          a.coef[3 * a.C + c] = invstd;
+          a.coef[0 * C + c] = sc;
+          a.coef[1 * C + c] = sh;
+          a.coef[2 * C + c] = mean;
+          a.coef[3 * C + c] = invstd;
         }
         if (a.mode == 1 && a.rm) {
           const float n = static_cast<float>(a.count);
@@ -215,21 +220,47 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
         }
       }
     }
+    s_sc[c] = sc;
+    s_sh[c] = sh;
   }
   if (a.mode == 1 && a.nbt && blockIdx.x == 0 && threadIdx.x == 0) *a.nbt += 1;
-  for (long long idx = idx0; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
-    const long long m = idx / groups;
-    float v[8];
-    ld8(a.x + m * a.x_ld + a.x_off + g * 8, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = act_fwd(v[j] * sc[j] + sh[j], a.act, slope) * a.x_scale;
-    if (a.res) {
-      float r[8];
-      ld8(a.res + m * a.res_ld + a.res_off + g * 8, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += r[j] * a.res_scale;
+  __syncthreads();
+  const int groups = C >> 3;
+  const long long total = a.M * groups;
+  const float slope = a.act == TSR_ACT_PRELU ? __ldg(a.alpha) : a.leaky;
+  const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  const int g = static_cast<int>(idx0 % groups);  // constant per thread: the grid stride is a multiple of `groups`
+  float sc[8], sh[8];
+  lds8(s_sc + g * 8, sc);
+  lds8(s_sh + g * 8, sh);
+  const bf16* xp = a.x + a.x_off + g * 8;
+  const bf16* rp = a.res ? a.res + a.res_off + g * 8 : nullptr;
+  bf16* yp = a.y + a.y_off + g * 8;
+  for (long long idx = idx0; idx < total; idx += 2 * stride) {
+    const long long m0 = idx / groups, m1 = (idx + stride) / groups;
+    const bool two = idx + stride < total;
+    float v0[8], v1[8], r0[8], r1[8];
+    ld8(xp + m0 * a.x_ld, v0);
+    if (two) ld8(xp + m1 * a.x_ld, v1);
+    if (rp) {
+      ld8(rp + m0 * a.res_ld, r0);
+      if (two) ld8(rp + m1 * a.res_ld, r1);
     }
-    st8(a.y + m * a.y_ld + a.y_off + g * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v0[j] = act_fwd(v0[j] * sc[j] + sh[j], a.act, slope) * a.x_scale;
+      v1[j] = act_fwd(v1[j] * sc[j] + sh[j], a.act, slope) * a.x_scale;
+    }
+    if (rp) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v0[j] += r0[j] * a.res_scale;
+        v1[j] += r1[j] * a.res_scale;
+      }
+    }
+    st8(yp + m0 * a.y_ld, v0);
+    if (two) st8(yp + m1 * a.y_ld, v1);
   }
 }
 
@@ -249,21 +280,26 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const bf16* __restri
                                                             const bf16* __restrict__ g2, long long M, int C, int act,
                                                             int rows_per_block, int g_ld, int x_ld, int has_bn,
                                                             float leaky, float gscale) {
+  pdl_sync();
   extern __shared__ float sm[];
+  __shared__ __align__(16) float s_co[4][kMaxBnC];
   const int groups = C / 8;
   const int lanes = 256 / groups;  // row lanes (groups <= 256)
   const int g_id = threadIdx.x % groups;
   const int r_id = threadIdx.x / groups;
   const float slope = act == TSR_ACT_PRELU ? __ldg(alpha) : (act == TSR_ACT_RELU ? 0.f : leaky);
-  float sc[8], sh[8], mu[8], is[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = g_id * 8 + j;
-    sc[j] = has_bn ? __ldg(coef + c) : 1.f;
-    sh[j] = has_bn ? __ldg(coef + C + c) : 0.f;
-    mu[j] = has_bn ? __ldg(coef + 2 * C + c) : 0.f;
-    is[j] = has_bn ? __ldg(coef + 3 * C + c) : 1.f;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    s_co[0][c] = has_bn ? coef[c] : 1.f;
+    s_co[1][c] = has_bn ? coef[C + c] : 0.f;
+    s_co[2][c] = has_bn ? coef[2 * C + c] : 0.f;
+    s_co[3][c] = has_bn ? coef[3 * C + c] : 1.f;
   }
+  __syncthreads();
+  float sc[8], sh[8], mu[8], is[8];
+  lds8(s_co[0] + g_id * 8, sc);
+  lds8(s_co[1] + g_id * 8, sh);
+  lds8(s_co[2] + g_id * 8, mu);
+  lds8(s_co[3] + g_id * 8, is);
   float s1[8], s2[8], da = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
@@ -338,60 +374,98 @@ struct BnBwdApplyArgs {
   float* dalpha;
   const float* dalpha_acc;
   long long M;
-  int C, act, g_ld, x_ld, dx_ld, has_bn;
+  int C, act, g_ld, x_ld, dx_ld, has_bn, raw_sums, pre_act;
   float leaky, gscale;
 };
 
+// i[7] raw_sums: sums[c][1] holds sum(dz * x) over the RAW conv output x (as accumulated by a data-gradient conv
+// epilogue, conv_igemm.cu "fused BatchNorm-backward reduction") instead of sum(dz * xhat);
+// i[8] pre_act: g already is dz (the activation derivative was applied by that epilogue).
+// Per channel the whole backward collapses to dx = A*dz + Bx*x + Cc (derived once per block into shared memory).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs a) {
+  __shared__ __align__(16) float s_co[5][kMaxBnC];   // sc, sh, A, Bx, Cc
+  pdl_sync();
   const int C = a.C;
-  const int groups = C / 8;
-  const long long total = a.M * groups;
-  const float slope = a.act == TSR_ACT_PRELU ? __ldg(a.alpha) : (a.act == TSR_ACT_RELU ? 0.f : a.leaky);
-  const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
-  const int gi = static_cast<int>(idx0 % groups);
-  float sc[8], sh[8], mu[8], is[8], c1[8], c2[8], c3[8];
   const float inv_m = 1.f / static_cast<float>(a.M);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = gi * 8 + j;
-    sc[j] = a.has_bn ? __ldg(a.coef + c) : 1.f;
-    sh[j] = a.has_bn ? __ldg(a.coef + C + c) : 0.f;
-    mu[j] = a.has_bn ? __ldg(a.coef + 2 * C + c) : 0.f;
-    is[j] = a.has_bn ? __ldg(a.coef + 3 * C + c) : 1.f;
-    const float s1 = a.sums ? __ldg(a.sums + 2 * c) : 0.f;
-    const float s2 = a.sums ? __ldg(a.sums + 2 * c + 1) : 0.f;
-    c1[j] = (a.gamma ? __ldg(a.gamma + c) : 1.f) * is[j];
-    c2[j] = s1 * inv_m;
-    c3[j] = s2 * inv_m;
-    if (blockIdx.x == 0 && threadIdx.x < groups) {
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float sc = 1.f, sh = 0.f, mu = 0.f, is = 1.f;
+    if (a.has_bn) {
+      sc = a.coef[c];
+      sh = a.coef[C + c];
+      mu = a.coef[2 * C + c];
+      is = a.coef[3 * C + c];
+    }
+    const float s1 = a.sums ? a.sums[2 * c] : 0.f;
+    float s2 = a.sums ? a.sums[2 * c + 1] : 0.f;
+    if (a.raw_sums) s2 = is * (s2 - mu * s1);
+    const float A = (a.gamma ? __ldg(a.gamma + c) : 1.f) * is;
+    const float c2 = s1 * inv_m, c3 = s2 * inv_m;
+    s_co[0][c] = sc;
+    s_co[1][c] = sh;
+    s_co[2][c] = A;
+    s_co[3][c] = -A * c3 * is;
+    s_co[4][c] = -A * (c2 - mu * is * c3);
+    if (blockIdx.x == 0) {
       if (a.dbeta) a.dbeta[c] = s1;
       if (a.dgamma) a.dgamma[c] = s2;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.dalpha) *a.dalpha = *a.dalpha_acc;
-  for (long long idx = idx0; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
-    const long long m = idx / groups;
-    float gv[8], xv[8], o[8];
-    ld8(a.g + m * a.g_ld + gi * 8, gv);
-    ld8(a.x + m * a.x_ld + gi * 8, xv);
-    if (a.g2) {
-      float t[8];
-      ld8(a.g2 + m * a.g_ld + gi * 8, t);
+  __syncthreads();
+  const int groups = C >> 3;
+  const long long total = a.M * groups;
+  const float slope = a.act == TSR_ACT_PRELU ? __ldg(a.alpha) : (a.act == TSR_ACT_RELU ? 0.f : a.leaky);
+  const bool mask = a.act != TSR_ACT_NONE && !a.pre_act;
+  const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * 256;
+  const int gi = static_cast<int>(idx0 % groups);
+  float sc[8], sh[8], cA[8], cB[8], cC[8];
+  lds8(s_co[0] + gi * 8, sc);
+  lds8(s_co[1] + gi * 8, sh);
+  lds8(s_co[2] + gi * 8, cA);
+  lds8(s_co[3] + gi * 8, cB);
+  lds8(s_co[4] + gi * 8, cC);
+  const bf16* gp = a.g + gi * 8;
+  const bf16* g2p = a.g2 ? a.g2 + gi * 8 : nullptr;
+  const bf16* xp = a.x + gi * 8;
+  bf16* op = a.dx + gi * 8;
+  const bool need_x = a.has_bn || mask;
+  for (long long idx = idx0; idx < total; idx += 2 * stride) {
+    const long long m0 = idx / groups, m1 = (idx + stride) / groups;
+    const bool two = idx + stride < total;
+    float g0[8], g1[8], x0[8], x1[8];
+    ld8(gp + m0 * a.g_ld, g0);
+    if (two) ld8(gp + m1 * a.g_ld, g1);
+    if (need_x) {
+      ld8(xp + m0 * a.x_ld, x0);
+      if (two) ld8(xp + m1 * a.x_ld, x1);
+    }
+    if (g2p) {
+      float t0[8], t1[8];
+      ld8(g2p + m0 * a.g_ld, t0);
+      if (two) ld8(g2p + m1 * a.g_ld, t1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gv[j] += t[j];
+      for (int j = 0; j < 8; ++j) {
+        g0[j] += t0[j];
+        g1[j] += t1[j];
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = xv[j] * sc[j] + sh[j];
-      float dz = gv[j] * a.gscale;
-      if (a.act != TSR_ACT_NONE && z <= 0.f) dz *= slope;
-      if (a.has_bn) {
-        const float xhat = (xv[j] - mu[j]) * is[j];
-        dz = c1[j] * (dz - c2[j] - xhat * c3[j]);
+      float d0 = g0[j] * a.gscale, d1 = g1[j] * a.gscale;
+      if (mask) {
+        if (x0[j] * sc[j] + sh[j] <= 0.f) d0 *= slope;
+        if (x1[j] * sc[j] + sh[j] <= 0.f) d1 *= slope;
       }
-      o[j] = dz;
+      if (a.has_bn) {
+        d0 = cA[j] * d0 + cB[j] * x0[j] + cC[j];
+        d1 = cA[j] * d1 + cB[j] * x1[j] + cC[j];
+      }
+      g0[j] = d0;
+      g1[j] = d1;
     }
-    st8(a.dx + m * a.dx_ld + gi * 8, o);
+    st8(op + m0 * a.dx_ld, g0);
+    if (two) st8(op + m1 * a.dx_ld, g1);
   }
 }
 
@@ -399,6 +473,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs 
 // COLSUM_FINALIZE: p0 = partial [tiles][ld][2], p1 = out[C]; i: 0 tiles, 1 C, 2 ld, 3 which (0/1), 4 accumulate
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int tiles, int C,
                                        int ld, int which, int accumulate) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f;
@@ -408,6 +483,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, float*
 // SUM_FINALIZE: p0 = partial[n], p1 = out scalar; i: 0 n, 1 accumulate; f: 0 scale
 __global__ void sum_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int accumulate,
                                     float scale) {
+  pdl_sync();
   float t = 0.f;
   for (int i = threadIdx.x; i < n; i += 32) t += partial[i];
   t = warp_sum(t) * scale;
@@ -459,6 +535,7 @@ __device__ __forceinline__ int find_entry(const tsr_pack_entry_t* tab, int n, lo
 }
 // PACK_W: p0 = device table of tsr_pack_entry_t; i: 0 n_entries; grid = total blocks, 256 threads x 4 elements
 __global__ void pack_w_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
+  pdl_sync();
   const int ei = find_entry(tab, n, blockIdx.x);
   const tsr_pack_entry_t e = tab[ei];
   const long long base = (static_cast<long long>(blockIdx.x) - e.block_start) * 1024;
@@ -494,6 +571,7 @@ __global__ void pack_w_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
 // For TSR_PK_T-style entries r/c are swapped by pack_index; wgrad accumulators always use the forward-like modes
 // (FWD, ROWK, ROWN, FULLK). count = rows_pad * taps * cols_pad.
 __global__ void unpack_g_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
+  pdl_sync();
   const int ei = find_entry(tab, n, blockIdx.x);
   const tsr_pack_entry_t e = tab[ei];
   const long long base = (static_cast<long long>(blockIdx.x) - e.block_start) * 1024;
@@ -523,6 +601,7 @@ constexpr int kLwF = 16;
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ X,
                                                            float* __restrict__ dW, float* __restrict__ db, int B,
                                                            int Nf, int K) {
+  pdl_sync();
   extern __shared__ float sd[];  // [kLwF][B]
   const int n0 = blockIdx.y * kLwF;
   for (int i = threadIdx.x; i < kLwF * B; i += 256) {
@@ -557,6 +636,7 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const float* __restri
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                    float* __restrict__ partial, float* __restrict__ grad, long long n,
                                                    int kind, float gscale) {
+  pdl_sync();
   __shared__ float sw[8];
   float acc = 0.f;
   for (long long i = (blockIdx.x * 256ll + threadIdx.x) * 4; i < n; i += static_cast<long long>(gridDim.x) * 1024) {
@@ -592,6 +672,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ a, 
 // UPSAMPLE2X: p0 = x bf16 [B,H,W,ld_in], p1 = y bf16 [B,2H,2W,ld_out]; i: 0 B,1 H,2 W,3 C,4 ld_in,5 ld_out
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C,
                                   int ld_in, int ld_out) {
+  pdl_sync();
   const int groups = C / 8;
   const long long total = static_cast<long long>(B) * 2 * H * 2 * W * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -608,6 +689,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__
 // UPSAMPLE2X_BWD: p0 = dy bf16 [B,2H,2W,ld_in], p1 = dx bf16 [B,H,W,ld_out]; i as above (H,W = coarse dims)
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int H, int W, int C,
                                       int ld_in, int ld_out) {
+  pdl_sync();
   const int groups = C / 8;
   const long long total = static_cast<long long>(B) * H * W * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -640,6 +722,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ pre
                                                    const float* __restrict__ w2, const float* __restrict__ b2,
                                                    float* __restrict__ out, float* __restrict__ h1, int B, int N1,
                                                    int sigmoid, float leaky) {
+  pdl_sync();
   __shared__ float sw[8];
   const int b = blockIdx.x;
   float acc = 0.f;
@@ -668,6 +751,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        float* __restrict__ dpre1, bf16* __restrict__ dpre1_bf,
                                                        float* __restrict__ dw2, float* __restrict__ db2, int B, int N1,
                                                        int sigmoid, int ld_bf, float leaky) {
+  pdl_sync();
   const int k = blockIdx.x * 256 + threadIdx.x;
   float dw = 0.f, dbs = 0.f;
   for (int b = 0; b < B; ++b) {
@@ -694,6 +778,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 // AXPBY (bf16): p0 = x, p1 = y or null, p2 = out; i: 0 n (multiple of 8); f: 0 a, 1 b;  out = a*x + b*y
 __global__ void axpby_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, bf16* __restrict__ out,
                              long long n, float a, float b) {
+  pdl_sync();
   for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) * 8; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x * 8) {
     float v[8];
@@ -712,6 +797,7 @@ __global__ void axpby_kernel(const bf16* __restrict__ x, const bf16* __restrict_
 }
 // MAXPOOL2 (VGG): p0 = x bf16 [B,H,W,C], p1 = y bf16 [B,H/2,W/2,C]; i: 0 B,1 H,2 W,3 C
 __global__ void maxpool2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C) {
+  pdl_sync();
   const int groups = C / 8, Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -740,6 +826,7 @@ __global__ void maxpool2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
 // Gradient goes to the first element equal to the max in (0,0),(0,1),(1,0),(1,1) order (ATen's tie rule).
 __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, const bf16* __restrict__ dy,
                                     bf16* __restrict__ dx, int B, int H, int W, int C) {
+  pdl_sync();
   const int groups = C / 8, Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * groups;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -774,6 +861,7 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
 }
 // CAST: p0 = src, p1 = dst; i: 0 n, 1 dir (0: fp32 -> bf16, 1: bf16 -> fp32)
 __global__ void cast_kernel(const void* __restrict__ src, void* __restrict__ dst, long long n, int dir) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     if (dir == 0)
@@ -787,6 +875,7 @@ __global__ void cast_kernel(const void* __restrict__ src, void* __restrict__ dst
 // grid (C, splits): split s of channel c covers a contiguous slice of the B*HW elements of that channel.
 __global__ void __launch_bounds__(256) chansum_nchw_kernel(const float* __restrict__ x, float* __restrict__ partial, int B,
                                                            int C, long long HW, int splits) {
+  pdl_sync();
   __shared__ float sw[8];
   const int c = blockIdx.x, s = blockIdx.y;
   const long long total = static_cast<long long>(B) * HW;
@@ -817,25 +906,26 @@ inline int grid_for(long long work_items, int block = 256, int max_blocks = 148 
 
 }  // namespace
 
-cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
+cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
+  cudaError_t ce = cudaSuccess;
   const int64_t* i = d.i;
   void* const* p = d.p;
   switch (d.kind) {
     case TSR_E_IM2ROW:
-      im2row_kernel<<<grid_for(i[0] * i[2] * i[3] * (i[9] / 8)), 256, 0, st>>>(
+      ce = launch_k(im2row_kernel, dim3(grid_for(i[0] * i[2] * i[3] * (i[9] / 8))), dim3(256), 0, st, pdl, 
           (const float*)p[0], (bf16*)p[1], i[0], i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8], i[9]);
       break;
     case TSR_E_GATHER_OUT:
-      gather_out_kernel<<<grid_for(i[0] * i[1] * i[2] * i[3]), 256, 0, st>>>(p[0], (float*)p[1], (const float*)p[2], i[0],
+      ce = launch_k(gather_out_kernel, dim3(grid_for(i[0] * i[1] * i[2] * i[3])), dim3(256), 0, st, pdl, p[0], (float*)p[1], (const float*)p[2], i[0],
                                                                           i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8],
                                                                           i[9], i[10]);
       break;
     case TSR_E_NCHW2NHWC:
-      nchw2nhwc_kernel<<<grid_for(i[0] * (i[1] / 8) * i[2] * i[3]), 256, 0, st>>>((const float*)p[0], (bf16*)p[1], i[0],
+      ce = launch_k(nchw2nhwc_kernel, dim3(grid_for(i[0] * (i[1] / 8) * i[2] * i[3])), dim3(256), 0, st, pdl, (const float*)p[0], (bf16*)p[1], i[0],
                                                                                i[1], i[2], i[3], i[4], i[5]);
       break;
     case TSR_E_NHWC2NCHW:
-      nhwc2nchw_kernel<<<grid_for(i[0] * (i[1] / 8) * i[2] * i[3]), 256, 0, st>>>((const bf16*)p[0], (float*)p[1], i[0],
+      ce = launch_k(nhwc2nchw_kernel, dim3(grid_for(i[0] * (i[1] / 8) * i[2] * i[3])), dim3(256), 0, st, pdl, (const bf16*)p[0], (float*)p[1], i[0],
                                                                                i[1], i[2], i[3], i[4], i[5], i[6]);
       break;
     case TSR_E_BN_ACT: {
@@ -846,15 +936,17 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
       a.M = i[0]; a.C = i[1]; a.x_ld = i[2]; a.y_ld = i[3]; a.res_ld = i[4]; a.act = i[5]; a.x_off = i[6];
       a.y_off = i[7]; a.res_off = i[8]; a.mode = i[9]; a.count = i[10];
       a.leaky = d.f[0]; a.res_scale = d.f[1]; a.x_scale = d.f[2]; a.eps = d.f[3]; a.momentum = d.f[4];
-      bn_act_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>(a);
+      if (a.C > kMaxBnC) return cudaErrorInvalidValue;
+      ce = launch_k(bn_act_kernel, dim3(grid_for(i[0] * (i[1] / 8))), dim3(256), 0, st, pdl, a);
       break;
     }
     case TSR_E_BN_BWD_REDUCE: {
       const int C = i[1];
+      if (C > kMaxBnC) return cudaErrorInvalidValue;
       const int lanes = 256 / (C / 8);
       const long long blocks = (i[0] + i[3] - 1) / i[3];
       const size_t sm = (static_cast<size_t>(lanes) * C * 2 + 8) * sizeof(float);
-      bn_bwd_reduce_kernel<<<blocks, 256, sm, st>>>((const bf16*)p[0], (const bf16*)p[1], (const float*)p[2],
+      ce = launch_k(bn_bwd_reduce_kernel, dim3(blocks), dim3(256), sm, st, pdl, (const bf16*)p[0], (const bf16*)p[1], (const float*)p[2],
                                                     (const float*)p[3], (float*)p[4], (float*)p[5], (const bf16*)p[6],
                                                     i[0], C, i[2], i[3], i[4], i[5], i[6], d.f[0],
                                                     d.f[1] != 0.f ? d.f[1] : 1.f);
@@ -866,79 +958,81 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st) {
       a.alpha = (const float*)p[4]; a.dx = (bf16*)p[5]; a.g2 = (const bf16*)p[6]; a.gamma = (const float*)p[7];
       a.dgamma = (float*)p[8]; a.dbeta = (float*)p[9]; a.dalpha = (float*)p[10]; a.dalpha_acc = (const float*)p[11];
       a.M = i[0]; a.C = i[1]; a.act = i[2]; a.g_ld = i[3]; a.x_ld = i[4]; a.dx_ld = i[5]; a.has_bn = i[6];
+      a.raw_sums = i[7]; a.pre_act = i[8];
+      if (a.C > kMaxBnC) return cudaErrorInvalidValue;
       a.leaky = d.f[0];
       a.gscale = d.f[1] != 0.f ? d.f[1] : 1.f;
-      bn_bwd_apply_kernel<<<grid_for(i[0] * (i[1] / 8)), 256, 0, st>>>(a);
+      ce = launch_k(bn_bwd_apply_kernel, dim3(grid_for(i[0] * (i[1] / 8))), dim3(256), 0, st, pdl, a);
       break;
     }
     case TSR_E_COLSUM_FINALIZE:
-      colsum_finalize_kernel<<<(i[1] + 127) / 128, 128, 0, st>>>((const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3],
+      ce = launch_k(colsum_finalize_kernel, dim3((i[1] + 127) / 128), dim3(128), 0, st, pdl, (const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3],
                                                                 i[4]);
       break;
     case TSR_E_SUM_FINALIZE:
-      sum_finalize_kernel<<<1, 32, 0, st>>>((const float*)p[0], (float*)p[1], i[0], i[1], d.f[0]);
+      ce = launch_k(sum_finalize_kernel, dim3(1), dim3(32), 0, st, pdl, (const float*)p[0], (float*)p[1], i[0], i[1], d.f[0]);
       break;
     case TSR_E_PACK_W:
-      pack_w_kernel<<<static_cast<unsigned>(i[1]), 256, 0, st>>>((const tsr_pack_entry_t*)p[0], i[0]);
+      ce = launch_k(pack_w_kernel, dim3(static_cast<unsigned>(i[1])), dim3(256), 0, st, pdl, (const tsr_pack_entry_t*)p[0], i[0]);
       break;
     case TSR_E_UNPACK_G:
-      unpack_g_kernel<<<static_cast<unsigned>(i[1]), 256, 0, st>>>((const tsr_pack_entry_t*)p[0], i[0]);
+      ce = launch_k(unpack_g_kernel, dim3(static_cast<unsigned>(i[1])), dim3(256), 0, st, pdl, (const tsr_pack_entry_t*)p[0], i[0]);
       break;
     case TSR_E_LINEAR_WGRAD: {
       dim3 grid((i[2] + 255) / 256, (i[1] + kLwF - 1) / kLwF);
-      linear_wgrad_kernel<<<grid, 256, kLwF * i[0] * sizeof(float), st>>>((const float*)p[0], (const float*)p[1],
+      ce = launch_k(linear_wgrad_kernel, dim3(grid), dim3(256), kLwF * i[0] * sizeof(float), st, pdl, (const float*)p[0], (const float*)p[1],
                                                                          (float*)p[2], (float*)p[3], i[0], i[1], i[2]);
       break;
     }
     case TSR_E_LOSS:
-      loss_kernel<<<static_cast<unsigned>(i[2]), 256, 0, st>>>((const float*)p[0], (const float*)p[1], (float*)p[2],
+      ce = launch_k(loss_kernel, dim3(static_cast<unsigned>(i[2])), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (float*)p[2],
                                                               (float*)p[3], i[0], i[1], d.f[0]);
       break;
     case TSR_E_ZERO:
       return cudaMemsetAsync(p[0], 0, static_cast<size_t>(i[0]), st);
     case TSR_E_UPSAMPLE2X:
-      upsample2x_kernel<<<grid_for(i[0] * 4 * i[1] * i[2] * (i[3] / 8)), 256, 0, st>>>((const bf16*)p[0], (bf16*)p[1],
+      ce = launch_k(upsample2x_kernel, dim3(grid_for(i[0] * 4 * i[1] * i[2] * (i[3] / 8))), dim3(256), 0, st, pdl, (const bf16*)p[0], (bf16*)p[1],
                                                                                    i[0], i[1], i[2], i[3], i[4], i[5]);
       break;
     case TSR_E_UPSAMPLE2X_BWD:
-      upsample2x_bwd_kernel<<<grid_for(i[0] * i[1] * i[2] * (i[3] / 8)), 256, 0, st>>>((const bf16*)p[0], (bf16*)p[1],
+      ce = launch_k(upsample2x_bwd_kernel, dim3(grid_for(i[0] * i[1] * i[2] * (i[3] / 8))), dim3(256), 0, st, pdl, (const bf16*)p[0], (bf16*)p[1],
                                                                                    i[0], i[1], i[2], i[3], i[4], i[5]);
       break;
     case TSR_E_HEAD:
-      head_kernel<<<static_cast<unsigned>(i[0]), 256, 0, st>>>((const float*)p[0], (const float*)p[1], (const float*)p[2],
+      ce = launch_k(head_kernel, dim3(static_cast<unsigned>(i[0])), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (const float*)p[2],
                                                               (const float*)p[3], (float*)p[4], (float*)p[5], i[0], i[1],
                                                               i[2], d.f[0]);
       break;
     case TSR_E_HEAD_BWD:
-      head_bwd_kernel<<<(i[1] + 255) / 256, 256, 0, st>>>((const float*)p[0], (const float*)p[1], (const float*)p[2],
+      ce = launch_k(head_bwd_kernel, dim3((i[1] + 255) / 256), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (const float*)p[2],
                                                          (const float*)p[3], (float*)p[4], (bf16*)p[5], (float*)p[6],
                                                          (float*)p[7], i[0], i[1], i[2], i[3] > 0 ? i[3] : i[1], d.f[0]);
       break;
     case TSR_E_AXPBY:
-      axpby_kernel<<<grid_for(i[0] / 8), 256, 0, st>>>((const bf16*)p[0], (const bf16*)p[1], (bf16*)p[2], i[0], d.f[0],
+      ce = launch_k(axpby_kernel, dim3(grid_for(i[0] / 8)), dim3(256), 0, st, pdl, (const bf16*)p[0], (const bf16*)p[1], (bf16*)p[2], i[0], d.f[0],
                                                       d.f[1]);
       break;
     case TSR_E_MAXPOOL2:
-      maxpool2_kernel<<<grid_for(i[0] * (i[1] / 2) * (i[2] / 2) * (i[3] / 8)), 256, 0, st>>>((const bf16*)p[0],
+      ce = launch_k(maxpool2_kernel, dim3(grid_for(i[0] * (i[1] / 2) * (i[2] / 2) * (i[3] / 8))), dim3(256), 0, st, pdl, (const bf16*)p[0],
                                                                                          (bf16*)p[1], i[0], i[1], i[2],
                                                                                          i[3]);
       break;
     case TSR_E_MAXPOOL2_BWD:
-      maxpool2_bwd_kernel<<<grid_for(i[0] * (i[1] / 2) * (i[2] / 2) * (i[3] / 8)), 256, 0, st>>>(
+      ce = launch_k(maxpool2_bwd_kernel, dim3(grid_for(i[0] * (i[1] / 2) * (i[2] / 2) * (i[3] / 8))), dim3(256), 0, st, pdl, 
           (const bf16*)p[0], (const bf16*)p[1], (const bf16*)p[2], (bf16*)p[3], i[0], i[1], i[2], i[3]);
       break;
     case TSR_E_CAST:
-      cast_kernel<<<grid_for(i[0]), 256, 0, st>>>(p[0], p[1], i[0], i[1]);
+      ce = launch_k(cast_kernel, dim3(grid_for(i[0])), dim3(256), 0, st, pdl, p[0], p[1], i[0], i[1]);
       break;
     case TSR_E_CHANSUM_NCHW: {
       dim3 grid(static_cast<unsigned>(i[1]), static_cast<unsigned>(i[3]));
-      chansum_nchw_kernel<<<grid, 256, 0, st>>>((const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3]);
+      ce = launch_k(chansum_nchw_kernel, dim3(grid), dim3(256), 0, st, pdl, (const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3]);
       break;
     }
     default:
       return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
+  return ce != cudaSuccess ? ce : cudaGetLastError();
 }
 
 }  // namespace tsr

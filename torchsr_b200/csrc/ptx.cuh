@@ -159,6 +159,27 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the library may be launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch.h):
+// its CTAs then become resident while the previous kernel of the stream is still running. pdl_wait() returns once
+// that kernel has completed and its writes are visible (no-op for a plain launch); everything before it (barrier
+// init, TMEM allocation, tensor-map prefetch, loads of data no kernel of the chain writes) overlaps the previous
+// kernel's tail. Every thread calls it before touching dependent global memory and before exiting, so completion of
+// kernel N implies completion of kernels < N. pdl_trigger() lets the NEXT kernel's CTAs be scheduled; it is issued
+// after the wait so that at most one successor is staged at a time.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+// Pulls the 128-byte line holding `p` into L1 (no register destination, no ordering): used by the epilogue warps to
+// fetch their residual / statistics operands while the main loop is still running.
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // ------------------------------------------------------------------ misc
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

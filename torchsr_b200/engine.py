@@ -11,6 +11,7 @@ Replaces the per-op ATen dispatch of the reference's forward() methods and autog
 * weight gradients: fp32 atomically-accumulated arena in packed order -> ONE unpack kernel -> flat fp32 gradient in
   parameters() order -> handed to autograd as views of a clone.
 """
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -22,6 +23,8 @@ from . import ops
 BF16 = torch.bfloat16
 F32 = torch.float32
 NUM_SMS = 148
+# fold BatchNorm-backward column reductions into the epilogue of the data-gradient conv that produces the gradient
+FUSE_BN_REDUCE = os.environ.get("TSR_FUSE_BN_REDUCE", "1") != "0"
 ZERO_ARENA_FLOATS = 64 * 1024
 
 
@@ -290,11 +293,14 @@ class Plan:
 
     # ---- forward emitters
     def conv(self, prog, x: Act, w: torch.Tensor, w_cols: int, n_slots: int, geom: dict, cout_pad: int, block_n: int,
-             out: torch.Tensor, out_strides, n_valid: int, **kw):
+             out: torch.Tensor, out_strides, n_valid: int, defer_tag=None, **kw):
         d = ops.conv_desc(x=ops.ptr(x.t, x.c0) if x.c0 else x.t, N=x.B, H=x.H, W=x.W, C=x.C, x_ld=x.ld, geom=geom, w=w,
                           cout_pad=cout_pad, w_ld=w_cols, n_slots=n_slots, block_n=block_n, out=out,
                           os_n=out_strides[0], os_h=out_strides[1], os_w=out_strides[2], n_valid=n_valid, **kw)
-        prog.add(d)
+        if defer_tag is not None:
+            prog.defer([d], defer_tag)
+        else:
+            prog.add(d)
         return d
 
     def conv_fwd(self, prog, rec: ConvRec, x: Act, out: Act, *, stats=None, act=L.ACT_NONE, prelu=None, preact=None,
@@ -375,18 +381,66 @@ class Plan:
         xp = ops.ptr(x.t, x.c0)
         g2p = ops.ptr(g2.t, g2.c0) if g2 is not None else None
         sums = dacc = None
+        fused = 0
         if need_reduce:
             sums = self.zbuf("bwd", name + ".sums", 2 * C)
             dacc = self.zbuf("bwd", name + ".dalpha", 1) if prelu else None
-            prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[gp, xp, coef, alpha if prelu else None, sums, dacc, g2p],
-                             i=[M, C, act, rpb, g.ld, x.ld, has_bn], f=[leaky, gscale]))
+            # The data-gradient conv that produced g may still be held by the program (conv_dgrad defers it): fold
+            # the column reductions into its epilogue instead of a separate pass over g and x. The conv then stores
+            # dz = g * act'(z) in place of g - legal because nothing else reads g when an activation is involved
+            # (with act == NONE the stored value is unchanged, e.g. the skip gradient of a residual block).
+            held = prog.take_deferred(g) if (FUSE_BN_REDUCE and g2 is None and gscale == 1.0 and leaky == 0.2) else None
+            if held is not None and self._fuse_bn_reduce(held, x, coef if has_bn else None, act,
+                                                         alpha if prelu else None, sums, dacc):
+                fused = 1
+            if held is not None:
+                for d in held:
+                    prog.add(d)
+            if not fused:
+                prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[gp, xp, coef, alpha if prelu else None, sums, dacc, g2p],
+                                 i=[M, C, act, rpb, g.ld, x.ld, has_bn], f=[leaky, gscale]))
         dgamma = store.grad_slice(bn.weight) if has_bn and want_w else None
         dbeta = (store.grad_slice(bn.bias) if has_bn else bias_grad) if want_w else None
         dalpha = store.grad_slice(alpha) if (prelu and want_w) else None
         prog.add(ops.elt(L.E_BN_BWD_APPLY, p=[gp, xp, coef, sums, alpha if prelu else None, dx.t, g2p,
                                               bn.weight if has_bn else None, dgamma, dbeta, dalpha, dacc],
-                         i=[M, C, act, g.ld, x.ld, C, has_bn], f=[leaky, gscale]))
+                         i=[M, C, act, g.ld, x.ld, C, has_bn, fused, fused], f=[leaky, gscale]))
         return dx
+
+    @staticmethod
+    def _fuse_bn_reduce(descs, x: Act, coef, act, alpha, sums, dacc) -> bool:
+        """Patches the held data-gradient conv descriptor(s) (one, or the four output-parity classes of a stride-2
+        layer) so that their epilogues accumulate sum(dz), sum(dz*x) into `sums`. Returns False (descriptors left
+        untouched) when the epilogue's aux addressing is already bound to a tensor of a different geometry."""
+        xs = x.strides()
+        for d in descs:
+            cls = getattr(d, "_parity", None)
+            want = xs if cls is None else (xs[0], 2 * xs[1], 2 * xs[2])
+            if d.n_valid != x.C or d.stats_partial or d.dalpha_partial or d.bwd_z or d.out_f32 or \
+                    d.out_mode != L.OUT_LINEAR:
+                return False
+            if d.res and ((d.aux_n, d.aux_h, d.aux_w) != want or d.aux_ch_off != x.c0 or cls is not None):
+                return False
+        for d in descs:
+            cls = getattr(d, "_parity", None)
+            base = ops.ptr(x.t)
+            if cls is None:
+                d.aux_n, d.aux_h, d.aux_w = xs
+                d.aux_ch_off = x.c0
+            else:
+                rh, rw = cls
+                d.aux_n, d.aux_h, d.aux_w = xs[0], 2 * xs[1], 2 * xs[2]
+                d.aux_ch_off = 0
+                base += ((rh * x.W + rw) * x.ld + x.c0) * 2
+            d.bnr_x = base
+            d.bnr_coef = ops.ptr(coef)
+            d.bnr_prelu = ops.ptr(alpha)
+            d.bnr_act = act
+            d.bnr_c = x.C
+            d.stats_partial = ops.ptr(sums)
+            d.stats_ld = x.C
+            d.dalpha_partial = ops.ptr(dacc)
+        return True
 
     def conv_dgrad(self, prog, name: str, rec: ConvRec, dy: Act, x_like: Act, *, res: Optional[Act] = None,
                    out_f32: bool = False, out: Optional[Act] = None, res2: Optional[Act] = None, res_scale=1.0,
@@ -429,15 +483,21 @@ class Plan:
             kw.update(out_mode=L.OUT_UNSHUFFLE, shuf_c=n_out)
         else:
             target = dx
+        # held back until the next emission: a following norm_act_bwd may fold its reductions into this epilogue
+        deferrable = hook is None and not out_f32
         if rec.stride == 1:
             self.conv(prog, dy, rec.w_t, rec.t_cols, n_slots, geom, n_out, block_n, target.t, target.strides(), n_out,
-                      out_ch_off=target.c0, out_f32=out_f32, **kw)
+                      out_ch_off=target.c0, out_f32=out_f32, defer_tag=target if deferrable else None, **kw)
         else:
             assert rec.stride == 2 and rec.k == 3 and rec.pad == 1 and not kw and rec.kind == "std"
-            for d in ops.dgrad_s2_descs(dy=dy.t, N=dy.B, Hy=dy.H, Wy=dy.W, Cout=dy.C, dy_ld=dy.ld, wt=rec.w_t,
-                                        Cin=n_out, cin_pad=n_out, block_n=block_n, out=target.t, Hx=x_like.H,
-                                        Wx=x_like.W, out_ld=target.ld, n_valid=n_out):
-                prog.add(d)
+            descs = ops.dgrad_s2_descs(dy=dy.t, N=dy.B, Hy=dy.H, Wy=dy.W, Cout=dy.C, dy_ld=dy.ld, wt=rec.w_t,
+                                       Cin=n_out, cin_pad=n_out, block_n=block_n, out=target.t, Hx=x_like.H,
+                                       Wx=x_like.W, out_ld=target.ld, n_valid=n_out)
+            if deferrable and target.c0 == 0:
+                prog.defer(descs, target)
+            else:
+                for d in descs:
+                    prog.add(d)
         return target
 
     def colsum(self, prog, name: str, g: Act, out_vec: torch.Tensor):
@@ -533,6 +593,7 @@ class Plan:
             self.last_g[key] = g
             if want_w:
                 prog.add(self.grads.unpack_desc)
+            prog.flush()
             self.bwd[key] = prog
         self.cur_g = self.last_g[key]
         return self.bwd[key]

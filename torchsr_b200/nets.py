@@ -306,7 +306,7 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
     k_iters = K // 64
     splits = max(1, min(k_iters, (2 * 148) // tiles_n))
     fwd.add(ops.gemm_desc(a=prev.t, M=B, K=K, a_ld=K, w=l1.w_fwd, n_rows=l1.nout_pad, block_n=128, out=pre1t, out_ld=B,
-                          n_valid=l1.nout_pad, splits=splits, atomic_t=True))
+                          n_valid=l1.nout_pad, splits=splits, atomic_t=True, w_static=True))
     out_b = plan.buf("out", B, F32)
     h1 = plan.buf("h1", B * N1, F32)
     fwd.add(ops.elt(L.E_HEAD, p=[pre1t, l1.bias, lin2.weight, lin2.bias, out_b, h1], i=[B, N1, int(sigmoid)], f=[0.2]))

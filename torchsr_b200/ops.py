@@ -122,7 +122,8 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
               block_k=None, a_c0=0, out_mode=L.OUT_LINEAR, out_f32=False, out_ch_off=0, bias=None, prelu=None,
               act=L.ACT_NONE, out_preact=None, res=None, bwd_z=None, bwd_act=L.ACT_NONE, aux=(0, 0, 0), aux_ch_off=0,
               dalpha_partial=None, stats_partial=None, stats_ld=0, acc_scale=1.0, leaky=0.2, shuf_c=64, res2=None,
-              res_scale=1.0, res2_scale=1.0, res_cols=0) -> ConvDesc:
+              res_scale=1.0, res2_scale=1.0, res_cols=0, w_static=True, bnr_x=None, bnr_coef=None, bnr_prelu=None,
+              bnr_act=L.ACT_NONE, bnr_c=0) -> ConvDesc:
     d = ConvDesc()
     d.x, d.w = ptr(x), ptr(w)
     d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
@@ -145,6 +146,8 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     d.n_valid, d.act, d.bwd_act, d.stats_ld, d.shuf_c = n_valid, act, bwd_act, stats_ld, shuf_c
     d.acc_scale, d.leaky_slope = acc_scale, leaky
     d.res2, d.res_scale, d.res2_scale, d.res_cols = ptr(res2), res_scale, res2_scale, res_cols
+    d.w_static = int(w_static)
+    d.bnr_x, d.bnr_coef, d.bnr_prelu, d.bnr_act, d.bnr_c = ptr(bnr_x), ptr(bnr_coef), ptr(bnr_prelu), bnr_act, bnr_c
     return d
 
 
@@ -162,15 +165,17 @@ def dgrad_s2_descs(*, dy, N, Hy, Wy, Cout, dy_ld, wt, Cin, cin_pad, block_n, out
             geom = dict(lower_h=0, lower_w=0, upper_h=0, upper_w=0, Ho=Hy, Wo=Wy, stride=1, taps=taps)
             elem = 4 if out_f32 else 2
             base = ptr(out) + (rh * Wx + rw) * out_ld * elem
-            descs.append(conv_desc(x=dy, N=N, H=Hy, W=Wy, C=Cout, x_ld=dy_ld, geom=geom, w=wt, cout_pad=cin_pad,
-                                   w_ld=Cout, n_slots=9, block_n=block_n, out=base, os_n=Hx * Wx * out_ld,
-                                   os_h=2 * Wx * out_ld, os_w=2 * out_ld, n_valid=n_valid, out_f32=out_f32,
-                                   out_ch_off=out_ch_off, **epi))
+            d = conv_desc(x=dy, N=N, H=Hy, W=Wy, C=Cout, x_ld=dy_ld, geom=geom, w=wt, cout_pad=cin_pad,
+                          w_ld=Cout, n_slots=9, block_n=block_n, out=base, os_n=Hx * Wx * out_ld,
+                          os_h=2 * Wx * out_ld, os_w=2 * out_ld, n_valid=n_valid, out_f32=out_f32,
+                          out_ch_off=out_ch_off, **epi)
+            d._parity = (rh, rw)
+            descs.append(d)
     return descs
 
 
 def gemm_desc(*, a, M, K, a_ld, a_mn_major=False, w, n_rows, block_n, out, out_ld, n_valid, splits=1, bias=None,
-              act=L.ACT_NONE, atomic_t=False, out_f32=True, acc_scale=1.0, leaky=0.2) -> ConvDesc:
+              act=L.ACT_NONE, atomic_t=False, out_f32=True, acc_scale=1.0, leaky=0.2, w_static=False) -> ConvDesc:
     """D[M, n] = sum_k A[m,k] * Wt[n,k].  atomic_t: fp32 atomics into out[n*out_ld + m] (split-K)."""
     d = ConvDesc()
     d.x, d.w = ptr(a), ptr(w)
@@ -192,6 +197,7 @@ def gemm_desc(*, a, M, K, a_ld, a_mn_major=False, w, n_rows, block_n, out, out_l
     d.acc_scale, d.leaky_slope = acc_scale, leaky
     d.res_scale = d.res2_scale = 1.0
     d.shuf_c = 64
+    d.w_static = int(w_static)
     return d
 
 
@@ -244,7 +250,8 @@ def validate_conv(d: ConvDesc):
         if d.out_preact:
             _need("conv out_preact", d.out_preact, (last + d.out_ch_off + span) * 2)
         rc = min(d.n_valid, d.res_cols) if d.res_cols > 0 else d.n_valid
-        for name, p, cols in (("res", d.res, rc), ("res2", d.res2, rc), ("bwd_z", d.bwd_z, d.n_valid)):
+        for name, p, cols in (("res", d.res, rc), ("res2", d.res2, rc), ("bwd_z", d.bwd_z, d.n_valid),
+                              ("bnr_x", d.bnr_x, d.n_valid)):
             if p:
                 _need("conv " + name, p, (aux_last + d.aux_ch_off + cols) * 2)
     else:
@@ -264,6 +271,13 @@ def validate_conv(d: ConvDesc):
         _need("conv stats_partial", d.stats_partial, d.stats_ld * 2 * 4)
     if d.dalpha_partial:
         _need("conv dalpha_partial", d.dalpha_partial, 4)
+    if d.bnr_x:
+        if not d.stats_partial or d.bwd_z or d.out_mode != L.OUT_LINEAR:
+            raise ExtentError("bnr_x needs stats_partial, no bwd_z hook and a linear store")
+        if d.bnr_coef:
+            if d.bnr_c < d.n_valid:
+                raise ExtentError("bnr_c smaller than the stored column count")
+            _need("conv bnr_coef", d.bnr_coef, 4 * d.bnr_c * 4)
     if d.n_valid % 16 or d.n_valid > d.cout_pad:
         raise ExtentError("conv n_valid must be a multiple of 16 and <= cout_pad")
     for off in (d.out_ch_off, d.aux_ch_off):
@@ -274,7 +288,7 @@ def validate_conv(d: ConvDesc):
         for st in ((d.os_n, d.os_h, d.os_w) if d.a_mode == 0 else (d.os_w,)):
             if st % q:
                 raise ExtentError("output strides must keep 16-byte alignment")
-        if d.res or d.bwd_z:
+        if d.res or d.bwd_z or d.bnr_x:
             for st in ((d.aux_n, d.aux_h, d.aux_w) if d.a_mode == 0 else (d.aux_w,)):
                 if st % 8:
                     raise ExtentError("aux strides must keep 16-byte alignment")
@@ -388,7 +402,31 @@ class Program:
         except Exception:
             pass
 
+    # Deferred emission: a data-gradient conv may be held back until the next emission so that a BatchNorm-backward
+    # stage that consumes its output can first fold its column reductions into the conv's epilogue (engine.py
+    # norm_act_bwd). Any other emission, run(), mark() or len() flushes the held descriptors unchanged.
+    _deferred = None
+
+    def defer(self, descs: List, tag):
+        self.flush()
+        self._deferred = (list(descs), tag)
+
+    def take_deferred(self, tag):
+        """Returns and removes the held descriptors if they were deferred under `tag` (identity), else None."""
+        if self._deferred is not None and self._deferred[1] is tag:
+            descs = self._deferred[0]
+            self._deferred = None
+            return descs
+        return None
+
+    def flush(self):
+        if self._deferred is not None:
+            descs, self._deferred = self._deferred[0], None
+            for d in descs:
+                self.add(d)
+
     def add(self, d) -> int:
+        self.flush()
         validate(d)
         self.descs.append(d)
         if DRY:
@@ -407,9 +445,11 @@ class Program:
         self.marks[name] = len(self)
 
     def __len__(self) -> int:
+        self.flush()
         return len(self.descs)
 
     def run(self, first: int = 0, count: int = -1, stream: Optional[int] = None):
+        self.flush()
         if DRY:
             return
         L.check(self._lib.tsr_prog_run(self._h, first, count, stream if stream is not None else current_stream()))
