@@ -187,3 +187,53 @@ def test_gan_step_matches_oracle_step():
         agree += int((torch.sign(du) == torch.sign(dr)).sum())
         total += du.numel()
     assert agree / total >= 0.85, agree / total
+
+
+def test_packed_weights_follow_fused_optimizer_and_graph_replay():
+    """torch.optim.Adam(fused=True) does not bump Tensor._version: the bf16 operand copies must still be re-packed
+    after every optimizer step - eagerly and inside a replayed whole-step CUDA graph (regression: stale packs)."""
+    MC, SG, SD, EG, ED = _mods()
+    torch.manual_seed(11)
+    G = SG().cuda()
+    x = torch.rand(2, 3, 24, 24, device="cuda")
+    opt = torch.optim.Adam(G.parameters(), lr=torch.tensor(1e-2, device="cuda"), fused=True, capturable=True)
+
+    def step():
+        opt.zero_grad()
+        y = G(x)
+        y.square().mean().backward()
+        opt.step()
+        return y
+
+    def fresh_forward():
+        # an independent module instance holding the current weights packs them from scratch
+        H = SG().cuda()
+        H.load_state_dict(G.state_dict())
+        with torch.no_grad():
+            return H(x)
+
+    y0 = step().detach().clone()
+    y1 = step().detach().clone()          # must see the weights of the first update
+    assert MC.rel_l2(y1, y0) > 1e-2, "the optimizer step did not reach the kernels (stale packed weights)"
+    with torch.no_grad():
+        now = G(x)
+    assert MC.rel_l2(now, fresh_forward()) <= 2e-3
+    # whole step captured into a CUDA graph and replayed
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = step()
+    outs = []
+    for _ in range(3):
+        graph.replay()
+        outs.append(out.detach().clone())
+    torch.cuda.synchronize()
+    assert MC.rel_l2(outs[2], outs[0]) > 1e-3, "replays do not see updated weights"
+    with torch.no_grad():
+        now = G(x)
+    assert MC.rel_l2(now, fresh_forward()) <= 2e-3

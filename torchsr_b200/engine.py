@@ -12,6 +12,7 @@ Replaces the per-op ATen dispatch of the reference's forward() methods and autog
   parameters() order -> handed to autograd as views of a clone.
 """
 import os
+import weakref
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -54,6 +55,34 @@ class Act:
 
 
 # ------------------------------------------------------------------------------------------------ parameter store
+# Fused optimizers (torch.optim.Adam(fused=True), which the trainers use) update parameters through
+# torch._fused_adam_, which does NOT bump Tensor._version - so the version counters alone cannot tell that the bf16
+# operand copies went stale. Every ParamStore is therefore also marked dirty by a global optimizer-step hook whenever
+# an optimizer that owns one of its parameters has stepped (also while a CUDA graph is being captured: the re-pack
+# kernel of the next forward is then part of the graph).
+_LIVE_STORES = weakref.WeakSet()
+_HOOK_INSTALLED = False
+
+
+def _optimizer_step_hook(optimizer, args, kwargs):
+    ids = getattr(optimizer, "_tsr_param_ids", None)
+    n = sum(len(g["params"]) for g in optimizer.param_groups)
+    if ids is None or ids[0] != n:
+        ids = (n, {id(p) for g in optimizer.param_groups for p in g["params"]})
+        optimizer._tsr_param_ids = ids
+    for st in list(_LIVE_STORES):
+        if not st.dirty and any(id(p) in ids[1] for p in st._watched):
+            st.dirty = True
+
+
+def _install_optimizer_hook():
+    global _HOOK_INSTALLED
+    if not _HOOK_INSTALLED:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+        register_optimizer_step_post_hook(_optimizer_step_hook)
+        _HOOK_INSTALLED = True
+
+
 class ConvRec:
     """Packing / gradient bookkeeping of one nn.Conv2d.
     kind: 'std'   KxK conv, Cin multiple of 16: implicit GEMM over the NHWC input (TMA im2col)
@@ -135,7 +164,10 @@ class ParamStore:
         self.w_arena = torch.zeros(max(w_elems, 128), dtype=BF16, device=device)
         self.acc_elems = max(acc_elems, 64)
         self._version = None
+        self.dirty = True
         self._build_tables()
+        _LIVE_STORES.add(self)
+        _install_optimizer_hook()
 
     # T-pack slot counts differ per kind
     @staticmethod
@@ -180,13 +212,14 @@ class ParamStore:
         ver = 0
         for p in self._watched:
             ver += p._version
-        if ver == self._version:
+        if ver == self._version and not self.dirty:
             return
         ops.run_now(self._pack_desc)
         for r in self.bias_perm:   # PixelShuffle layers consume the bias in packed-column order
             c4 = r.cout // 4
             r.bias_packed.view(4, c4).copy_(r.bias.detach().view(c4, 4).t())
         self._version = ver
+        self.dirty = False
 
     def grads_from_flat(self, flat: torch.Tensor, want: List[bool]) -> List[Optional[torch.Tensor]]:
         out = []

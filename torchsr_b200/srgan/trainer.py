@@ -60,7 +60,11 @@ class SRGANTrainer:
         CUDA stream carries the work that depends only on the real batch."""
         for m in (self.generator, self.discriminator):
             m._tsr["alias_grads"] = not self.distributed
-        self._side = torch.cuda.Stream(device=self.device) if self.device.type == 'cuda' else None
+        cuda = self.device.type == 'cuda'
+        # stream B shares the critical path (D(real)), stream V only carries the VGG content branch: lowest priority
+        self._side = torch.cuda.Stream(device=self.device, priority=-1) if cuda else None
+        self._vgg_stream = torch.cuda.Stream(device=self.device, priority=0) if cuda else None
+        self._capture_stream = torch.cuda.Stream(device=self.device, priority=-1) if cuda else None
 
     def _initialize_models(self) -> None:
         self.generator = Generator().to(self.device)
@@ -128,43 +132,61 @@ class SRGANTrainer:
         real_label = torch.full((batch_size, 1), 1, dtype=low_res.dtype, device=self.device)
         fake_label = torch.full((batch_size, 1), 0, dtype=low_res.dtype, device=self.device)
 
-        cur, side = torch.cuda.current_stream(self.device), self._side
+        cur, side, vs = torch.cuda.current_stream(self.device), self._side, self._vgg_stream
+        split_vgg = hasattr(self.vgg_loss, 'from_features')
         self.discriminator.zero_grad()
-        # stream B: what depends only on the real batch - D(real) forward (and, in backward, its gradients) and the
-        # VGG features of the target - runs beside the generator forward on stream A. Same arithmetic as the
-        # reference's sequential statements (:444-448); D(fake) still follows D(real), so the BatchNorm running
-        # statistics are updated in the reference's order.
+        # Three dependency chains, same arithmetic as the reference's sequential statements (:444-468):
+        #   stream A (current): G forward -> D(fake) -> discriminator step -> D(super_res) -> G backward -> Adam
+        #   stream B (side):    D(real) forward (and, in backward, its gradients); D(fake) still follows D(real), so
+        #                       the BatchNorm running statistics are updated in the reference's order
+        #   stream V (low priority): everything of the VGG content loss - target features, features of super_res and
+        #                       the gradient of the content loss w.r.t. super_res. None of it depends on the
+        #                       discriminator, so it fills idle SMs during the discriminator step instead of sitting
+        #                       on the critical path of the generator step.
         side.wait_stream(cur)
+        vs.wait_stream(cur)
         with torch.cuda.stream(side):
             p_real = self.discriminator(high_res)
             done_real = side.record_event()
-            hr_feats = self.vgg_loss.target_features(high_res) if hasattr(self.vgg_loss, 'target_features') else None
+        if split_vgg:
+            with torch.cuda.stream(vs):
+                hr_feats = self.vgg_loss.target_features(high_res)
         super_res = self.generator(low_res)
+        if split_vgg:
+            vs.wait_stream(cur)
+            super_res.record_stream(vs)
+            with torch.cuda.stream(vs):
+                # d(content)/d(super_res) through a detached leaf; added to the adversarial gradient below, which is
+                # exactly what autograd does at the super_res node for gen_loss = content + 0.001 * adversarial
+                sr_leaf = super_res.detach().requires_grad_(True)
+                content_loss = self.vgg_loss.from_features(sr_leaf, hr_feats)
+                (g_content,) = torch.autograd.grad(content_loss, sr_leaf)
+                content_loss = content_loss.detach()
+                done_content = vs.record_event()
         cur.wait_event(done_real)
         p_fake = self.discriminator(super_res.detach())
-        cur.wait_stream(side)
         p_real.record_stream(cur)
         disc_loss_real = self.bce_loss(p_real, real_label)
         disc_loss_fake = self.bce_loss(p_fake, fake_label)
         disc_loss = disc_loss_real + disc_loss_fake
         disc_loss.backward()
+        cur.wait_stream(side)      # D(real)'s backward ran on stream B
         self.disc_optimizer.step()
 
         self.generator.zero_grad()
-        # generator step: VGG(super_res) on stream B beside D(super_res) on stream A (:455-457)
-        side.wait_stream(cur)
-        super_res.record_stream(side)
-        with torch.cuda.stream(side):
-            if hr_feats is not None:
-                content_loss = self.vgg_loss.from_features(super_res, hr_feats)
-            else:
-                content_loss = self.vgg_loss(super_res, high_res.detach())
         with tdist.frozen(self.discriminator):
             adversarial_loss = self.bce_loss(self.discriminator(super_res), real_label)
-        cur.wait_stream(side)
-        content_loss.record_stream(cur)
-        gen_loss = content_loss + 0.001 * adversarial_loss
-        gen_loss.backward()
+        if split_vgg:
+            (g_adv,) = torch.autograd.grad(0.001 * adversarial_loss, super_res)
+            cur.wait_event(done_content)
+            g_content.record_stream(cur)
+            content_loss.record_stream(cur)
+            super_res.backward(g_content + g_adv)
+            gen_loss = content_loss + 0.001 * adversarial_loss.detach()
+        else:
+            content_loss = self.vgg_loss(super_res, high_res.detach())
+            gen_loss = content_loss + 0.001 * adversarial_loss
+            gen_loss.backward()
         self.gen_optimizer.step()
         return gen_loss.detach()
 
@@ -192,7 +214,7 @@ class SRGANTrainer:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._capture_stream):     # high-priority capture stream (chain A)
                 loss = fn(s_lr, s_hr)
             g = self._graphs[key] = (graph, s_lr, s_hr, loss)
             return loss
