@@ -246,9 +246,17 @@ def run_b200(args):
     crops = args.batch * world * args.steps
     value = crops / (ms * 1e-3)
     e2e = crops / (ms_e2e * 1e-3)
-    if rank != 0:
+    def leave():
+        # captured NCCL work is still referenced by the step graph: synchronise, meet the other ranks, and leave
+        # without tearing the communicator down underneath it
+        sys.stdout.flush()
         if distributed:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
     pk = peaks()
     ach = value * GFLOP_PER_CROP_GD / 1e3 / world     # TFLOP/s per GPU on the G+D algorithmic FLOPs
@@ -285,8 +293,7 @@ def run_b200(args):
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
-    if distributed:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():

@@ -364,8 +364,15 @@ bool use_graphs() {
   return g_use_graphs == 1;
 }
 
-cudaStream_t g_side_stream = nullptr;
-cudaEvent_t g_fork_event = nullptr, g_join_event = nullptr;
+// Side branches for the weight-gradient GEMMs: per caller stream (two module backward passes captured on two
+// streams must not serialise on one branch) a small pool of non-blocking streams used round-robin.
+constexpr int kSideStreams = 2;
+struct SideBranch {
+  cudaStream_t s[kSideStreams] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kSideStreams] = {nullptr, nullptr};
+};
+std::map<cudaStream_t, SideBranch> g_side;
+std::mutex g_side_mu;   // not g_mu: tsr_prog_run holds g_mu while it captures a range
 int g_use_side = -1;
 
 bool use_side_stream() {
@@ -374,6 +381,24 @@ bool use_side_stream() {
     g_use_side = (e && e[0] == '0') ? 0 : 1;
   }
   return g_use_side == 1;
+}
+
+SideBranch* side_for(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  auto it = g_side.find(st);
+  if (it != g_side.end()) return &it->second;
+  SideBranch b;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = greatest priority
+  const char* e = getenv("TSR_WGRAD_PRIO");
+  const int prio = e ? atoi(e) : hi;
+  for (int k = 0; k < kSideStreams; ++k) {
+    if (cudaStreamCreateWithPriority(&b.s[k], cudaStreamNonBlocking, prio) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b.join[k], cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
+  }
+  if (cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  return &(g_side[st] = b);
 }
 
 int g_use_pdl = -1;
@@ -393,49 +418,55 @@ bool use_pdl() {
 // right before it on that stream is another kernel of this range (not a memset, not the join of the side branch):
 // its CTAs are then staged while the predecessor drains, and in a captured graph the edge becomes programmatic.
 int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
-  bool side = use_side_stream();
+  const bool side = use_side_stream();
   const bool pdl_on = use_pdl();
-  if (side && !g_side_stream) {
-    if (cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g_fork_event, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g_join_event, cudaEventDisableTiming) != cudaSuccess)
-      return fail(-45, "side stream setup failed");
+  SideBranch* sb = nullptr;
+  if (side) {
+    sb = side_for(st);
+    if (!sb) return fail(-45, "side stream setup failed");
   }
-  bool forked = false;
+  bool used[kSideStreams] = {false, false};
+  int next_side = 0;
   bool chain = false;   // previous op on `st` was one of our kernels
   auto join = [&]() -> cudaError_t {
-    if (!forked) return cudaSuccess;
-    forked = false;
-    chain = false;
-    cudaError_t e = cudaEventRecord(g_join_event, g_side_stream);
-    if (e != cudaSuccess) return e;
-    return cudaStreamWaitEvent(st, g_join_event, 0);
+    for (int k = 0; k < kSideStreams; ++k) {
+      if (!used[k]) continue;
+      used[k] = false;
+      chain = false;
+      cudaError_t e = cudaEventRecord(sb->join[k], sb->s[k]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, sb->join[k], 0);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
   };
   for (int i = first; i < last; ++i) {
     const tsr_prog::Op& op = p->ops[i];
     cudaError_t ce;
     if (op.kind == tsr_prog::WGRAD && side) {
-      ce = cudaEventRecord(g_fork_event, st);
-      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(g_side_stream, g_fork_event, 0);
+      const int k = next_side;
+      next_side = (next_side + 1) % kSideStreams;
+      ce = cudaEventRecord(sb->fork, st);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sb->s[k], sb->fork, 0);
       if (ce == cudaSuccess)
-        ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, g_side_stream, false);
-      forked = true;
+        ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, sb->s[k], false);
+      used[k] = true;
     } else if (op.kind == tsr_prog::WGRAD) {
       ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st, pdl_on && chain);
       chain = true;
     } else {
-      // the unpack kernel reads every accumulator: join the branch first
+      // the unpack kernel reads every accumulator: join the branches first
       if (op.kind == tsr_prog::ELT && op.elt.kind == TSR_E_UNPACK_G) {
         ce = join();
         if (ce != cudaSuccess) return fail(-45, "join failed: %s", cudaGetErrorString(ce));
       }
       if (op.kind == tsr_prog::CONV) {
         ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st, pdl_on && chain);
-        chain = true;
       } else {
         ce = tsr::launch_elt(op.elt, st, pdl_on && chain);
-        chain = op.elt.kind != TSR_E_ZERO;
       }
+      // an unaligned TSR_E_ZERO falls back to a memset node, which ends the programmatic chain
+      chain = !(op.kind == tsr_prog::ELT && op.elt.kind == TSR_E_ZERO &&
+                ((reinterpret_cast<uintptr_t>(op.elt.p[0]) & 15) || (op.elt.i[0] & 15)));
     }
     if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
   }

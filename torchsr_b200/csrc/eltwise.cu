@@ -535,12 +535,33 @@ __device__ __forceinline__ int find_entry(const tsr_pack_entry_t* tab, int n, lo
 }
 // PACK_W: p0 = device table of tsr_pack_entry_t; i: 0 n_entries; grid = total blocks, 256 threads x 4 elements
 __global__ void pack_w_kernel(const tsr_pack_entry_t* __restrict__ tab, int n) {
+  __shared__ float tile[32][65];
   pdl_sync();
   const int ei = find_entry(tab, n, blockIdx.x);
   const tsr_pack_entry_t e = tab[ei];
   const long long base = (static_cast<long long>(blockIdx.x) - e.block_start) * 1024;
   const float* src = reinterpret_cast<const float*>(e.src);
   bf16* dst = reinterpret_cast<bf16*>(e.dst);
+  if (e.mode == TSR_PK_LINEAR && e.shuffle == 1) {
+    // tiled permutation (shuffle == 1 marks the tiled block mapping, see ops.pack_table): one block = one output row
+    // x 32 channels x all HW positions. The source run [c0*HW, (c0+32)*HW) of the row is contiguous (coalesced reads),
+    // the destination is HW segments of 32 consecutive bf16 (64-byte stores).
+    const int HW = e.kh * e.kw, Cc = e.cin, K = Cc * HW;
+    const int chunks = (Cc + 31) / 32;
+    const long long b = static_cast<long long>(blockIdx.x) - e.block_start;
+    const int row = static_cast<int>(b / chunks), c0 = static_cast<int>(b % chunks) * 32;
+    if (row >= e.cout) return;
+    const int nc = min(32, Cc - c0);
+    const float* s0 = src + static_cast<long long>(row) * K + static_cast<long long>(c0) * HW;
+    for (int i = threadIdx.x; i < nc * HW; i += 256) tile[i / HW][i % HW] = s0[i];
+    __syncthreads();
+    bf16* d0 = dst + static_cast<long long>(row) * e.cols_pad + c0;
+    for (int i = threadIdx.x; i < nc * HW; i += 256) {
+      const int hw = i / nc, c = i % nc;
+      d0[static_cast<long long>(hw) * Cc + c] = __float2bfloat16(tile[c][hw]);
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const long long i = base + k * 256 + threadIdx.x;
@@ -859,6 +880,14 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
       }
   }
 }
+// ZERO: p0 = dst (16-byte aligned); i: 0 bytes (multiple of 16)
+__global__ void zero_kernel(uint4* __restrict__ dst, long long n16) {
+  pdl_sync();
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = z;
+}
 // CAST: p0 = src, p1 = dst; i: 0 n, 1 dir (0: fp32 -> bf16, 1: bf16 -> fp32)
 __global__ void cast_kernel(const void* __restrict__ src, void* __restrict__ dst, long long n, int dir) {
   pdl_sync();
@@ -988,8 +1017,12 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       ce = launch_k(loss_kernel, dim3(static_cast<unsigned>(i[2])), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (float*)p[2],
                                                               (float*)p[3], i[0], i[1], d.f[0]);
       break;
-    case TSR_E_ZERO:
-      return cudaMemsetAsync(p[0], 0, static_cast<size_t>(i[0]), st);
+    case TSR_E_ZERO: {
+      // a kernel (not a memset node): stays inside programmatic-launch chains and graph branches of kernel nodes
+      if ((reinterpret_cast<uintptr_t>(p[0]) & 15) || (i[0] & 15)) return cudaMemsetAsync(p[0], 0, static_cast<size_t>(i[0]), st);
+      ce = launch_k(zero_kernel, dim3(grid_for(i[0] / 16, 256, 148 * 8)), dim3(256), 0, st, pdl, (uint4*)p[0], i[0] / 16);
+      break;
+    }
     case TSR_E_UPSAMPLE2X:
       ce = launch_k(upsample2x_kernel, dim3(grid_for(i[0] * 4 * i[1] * i[2] * (i[3] / 8))), dim3(256), 0, st, pdl, (const bf16*)p[0], (bf16*)p[1],
                                                                                    i[0], i[1], i[2], i[3], i[4], i[5]);

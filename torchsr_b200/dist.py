@@ -60,6 +60,13 @@ def bucket_slices(total: int, early_from: Optional[int], max_elems: int = 32 * 1
     return out
 
 
+def allreduce_flat(flat: torch.Tensor, state: "DataParallelState", early_from: Optional[int] = None):
+    """Averages a flat gradient over the ranks in place: bucketed, every bucket launched asynchronously, one wait."""
+    for lo, hi in bucket_slices(flat.numel(), early_from):
+        state.allreduce_async(flat[lo:hi])
+    state.wait()
+
+
 def attach(module, group=None, broadcast_buffers: bool = True) -> DataParallelState:
     """Makes `module` (a torchsr_b200 drop-in module) data parallel over the default process group."""
     if not dist.is_initialized():

@@ -566,7 +566,10 @@ class Plan:
         self.fwd.run()
         return self.output_fn()
 
-    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None, alias: bool = False):
+    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None, alias: bool = False,
+                     defer_comm: bool = False):
+        """defer_comm: no all-reduce here and the plan's own flat buffer is returned - the caller sums the gradients of
+        several outstanding calls of the module first (see _PlanFn.backward, 'merge_pending_grads')."""
         if not self.training and self.has_bn:
             raise NotImplementedError("torchsr_b200: backward through eval-mode BatchNorm is not implemented; call "
                                       ".train() for gradient computation (the reference trainers do)")
@@ -576,7 +579,7 @@ class Plan:
         store = self.store
         gb = self.grads
         early = prog.marks.get("early_grads")
-        if want_w and ddp is not None and ddp.world > 1:
+        if want_w and ddp is not None and ddp.world > 1 and not defer_comm:
             # bucketed all-reduce launched from inside backward: the tail of the flat gradient (the classifier of a
             # discriminator) is complete after the first few launches and travels while the conv stack runs
             from .dist import bucket_slices
@@ -606,7 +609,7 @@ class Plan:
                     fn()
                 # alias mode (set by the trainers, which zero the gradients before every backward): hand out views
                 # of this plan's flat buffer instead of a copy; valid until this plan instance runs backward again
-                flat = gb.flat if alias else gb.flat.clone()
+                flat = gb.flat if (alias or defer_comm) else gb.flat.clone()
         gx = self.grad_input_fn() if want_x else None
         return gx, flat
 
@@ -633,13 +636,19 @@ class Plan:
 
 
 class _Lease:
-    """Returns a plan to its pool when the autograd node that holds it dies (backward done or graph dropped)."""
+    """Returns a plan to its pool when the autograd node that holds it dies (backward done or graph dropped).
+    `pending` (optional) is the module's set of outstanding calls whose backward will produce weight gradients."""
 
-    def __init__(self, plan: Plan):
+    def __init__(self, plan: Plan, pending: Optional[set] = None):
         self.plan = plan
+        self.pending = pending
+        if pending is not None:
+            pending.add(id(plan))
 
     def release(self):
         if self.plan is not None:
+            if self.pending is not None:
+                self.pending.discard(id(self.plan))
             self.plan.busy = False
             self.plan = None
 
@@ -728,7 +737,8 @@ class _PlanFn(torch.autograd.Function):
             sync_buffers(module)
         out = plan.run_forward(x)
         if needs_graph:
-            ctx.lease = _Lease(plan)
+            wants_w = any(p.requires_grad for p in store.params)
+            ctx.lease = _Lease(plan, module._tsr.setdefault("pending", set()) if wants_w else None)
             ctx.module = module
         else:
             plan.busy = False
@@ -745,7 +755,28 @@ class _PlanFn(torch.autograd.Function):
         want = list(ctx.needs_input_grad[3:])
         want_w = any(want)
         st = ctx.module._tsr
-        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, st.get("ddp"), st.get("alias_grads", False))
-        grads = plan.store.grads_from_flat(flat, want) if want_w else [None] * len(want)
+        ddp = st.get("ddp")
+        merge = want_w and st.get("merge_pending_grads", False)
+        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ddp, st.get("alias_grads", False),
+                                     defer_comm=merge)
+        if merge:
+            # Several calls of the module feed one loss (D(real) and D(fake), trainer.py): every backward but the last
+            # parks its flat gradient; the last one sums them with ONE kernel per parked call, all-reduces the sum once
+            # and returns it (the others return no parameter gradients, which autograd treats as zero).
+            cur = torch.cuda.current_stream(flat.device)
+            others = st["pending"] - {id(plan)}
+            if others:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                st.setdefault("parked", []).append((flat, ev))
+                flat = None
+            else:
+                for other, ev in st.pop("parked", []):
+                    cur.wait_event(ev)
+                    flat.add_(other)
+                if ddp is not None and ddp.world > 1:
+                    from .dist import allreduce_flat
+                    allreduce_flat(flat, ddp)
+        grads = plan.store.grads_from_flat(flat, want) if (want_w and flat is not None) else [None] * len(want)
         lease.release()
         return (None, None, gx, *grads)

@@ -492,7 +492,12 @@ def pack_table(entries: List[dict], device):
         pe.rows_pad, pe.cols_pad, pe.shuffle = e["rows_pad"], e["cols_pad"], int(e.get("shuffle", 0))
         pe.block_start = blocks
         pe.count = e["count"]
-        blocks += (e["count"] + 1023) // 1024
+        if e["mode"] == L.PK_LINEAR and e["kh"] * e["kw"] <= 64 and e["cols_pad"] == e["cin"] * e["kh"] * e["kw"]:
+            # tiled permutation: one block per (output row, 32-channel chunk); flagged through `shuffle`
+            pe.shuffle = 1
+            blocks += e["rows_pad"] * ((e["cin"] + 31) // 32)
+        else:
+            blocks += (e["count"] + 1023) // 1024
     raw = bytes(arr)
     t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
     return t, len(entries), blocks

@@ -60,11 +60,15 @@ class SRGANTrainer:
         CUDA stream carries the work that depends only on the real batch."""
         for m in (self.generator, self.discriminator):
             m._tsr["alias_grads"] = not self.distributed
+        # D(real) and D(fake) feed one loss: their weight gradients are summed by the last of the two backward passes
+        # (one add instead of one per parameter) and all-reduced once instead of twice
+        self.discriminator._tsr["merge_pending_grads"] = True
         cuda = self.device.type == 'cuda'
         # stream B shares the critical path (D(real)), stream V only carries the VGG content branch: lowest priority
-        self._side = torch.cuda.Stream(device=self.device, priority=-1) if cuda else None
-        self._vgg_stream = torch.cuda.Stream(device=self.device, priority=0) if cuda else None
-        self._capture_stream = torch.cuda.Stream(device=self.device, priority=-1) if cuda else None
+        prio = lambda name, default: int(os.environ.get(name, default))  # noqa: E731
+        self._side = torch.cuda.Stream(device=self.device, priority=prio("TSR_PRIO_SIDE", -1)) if cuda else None
+        self._vgg_stream = torch.cuda.Stream(device=self.device, priority=prio("TSR_PRIO_VGG", -1)) if cuda else None
+        self._capture_stream = torch.cuda.Stream(device=self.device, priority=prio("TSR_PRIO_MAIN", -1)) if cuda else None
 
     def _initialize_models(self) -> None:
         self.generator = Generator().to(self.device)
@@ -139,7 +143,7 @@ class SRGANTrainer:
         #   stream A (current): G forward -> D(fake) -> discriminator step -> D(super_res) -> G backward -> Adam
         #   stream B (side):    D(real) forward (and, in backward, its gradients); D(fake) still follows D(real), so
         #                       the BatchNorm running statistics are updated in the reference's order
-        #   stream V (low priority): everything of the VGG content loss - target features, features of super_res and
+        #   stream V: everything of the VGG content loss - target features, features of super_res and
         #                       the gradient of the content loss w.r.t. super_res. None of it depends on the
         #                       discriminator, so it fills idle SMs during the discriminator step instead of sitting
         #                       on the critical path of the generator step.
