@@ -268,7 +268,8 @@ def run_b200(args):
         "config": {"workload": "SRGAN G+D _gan_loop (BASELINE configs[1]), batch %d per GPU of 96x96 HR / 24x24 LR "
                                "crops, random-init weights, VGG19 loss %s" %
                                (args.batch, "replaced by MSE (--no-vgg)" if args.no_vgg else
-                                "executed by PyTorch/cuDNN under bf16 autocast (not one of this repo's kernels)"),
+                                ("on this repo's kernels (nets.define_vgg)" if os.environ.get("TORCHSR_VGG_IMPL", "b200") != "torch"
+                                 else "executed by PyTorch/cuDNN under bf16 (TORCHSR_VGG_IMPL=torch)")),
                    "parallelism": f"dp{world}", "global_batch": args.batch * world,
                    "step_api": "SRGANTrainer._gan_loop (eager)" if args.eager else
                                "SRGANTrainer.graph_step (whole step replayed as one CUDA graph)",
@@ -281,7 +282,7 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
                      "frac": ach / pk["sustained"], "traffic": None,
                      "what": "whole step: crops/s x 21.73 GFLOP/crop (G+D algorithmic minimum, SURVEY 8d) per GPU vs the "
-                             f"{pk['source']} sustained bf16 peak; with the VGG19 FLOPs (+21.50/crop, executed by PyTorch) "
+                             f"{pk['source']} sustained bf16 peak; with the VGG19 FLOPs (+21.50/crop) "
                              f"the step sustains {value * (GFLOP_PER_CROP_GD + GFLOP_PER_CROP_VGG) / 1e3 / world:.1f} TFLOP/s",
                      "dominant_kernel": kern},
     }

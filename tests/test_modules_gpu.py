@@ -237,3 +237,36 @@ def test_packed_weights_follow_fused_optimizer_and_graph_replay():
     with torch.no_grad():
         now = G(x)
     assert MC.rel_l2(now, fresh_forward()) <= 2e-3
+
+
+def test_vgg_content_loss_vs_torch_fp32():
+    """VGG19 perceptual loss on this repo's kernels (bf16, fused ReLU, max-pool kernels, data gradients only) against
+    the same torchvision network in fp32 on the CPU: loss value, features and the gradient w.r.t. the image."""
+    import os
+    import module_checks as MC
+    os.environ["TORCHSR_VGG_WEIGHTS"] = "random"
+    from torchsr_b200.srgan.loss import VGGLoss
+    torch.manual_seed(12)
+    x, t = torch.rand(2, 3, 96, 96), torch.rand(2, 3, 96, 96)
+    ref_mod = VGGLoss()
+    xr = x.clone().requires_grad_(True)
+    ref = ref_mod(xr, t)
+    ref.backward()
+    mod = VGGLoss().cuda()           # seeded initialisation: identical weights
+    xg = x.cuda().requires_grad_(True)
+    got = mod(xg, t.cuda())
+    got.backward()
+    torch.cuda.synchronize()
+    feats = mod.target_features(x.cuda())
+    with torch.no_grad():
+        ref_feats = ref_mod.features(x)
+    errs = {"loss": abs(float(got) - float(ref)) / abs(float(ref)), "features": MC.rel_l2(feats, ref_feats),
+            "dx": MC.rel_l2(xg.grad, xr.grad)}
+    print("vgg", errs)
+    assert errs["features"] <= 3e-2 and errs["loss"] <= 3e-2, errs
+    # The image gradient passes 16 ReLU masks and the sign() of the L1 loss in bf16: PyTorch's own bf16 path (cuDNN,
+    # TORCHSR_VGG_IMPL=torch) measures rel-L2 0.416 / cosine 0.913 against fp32 on these inputs, this path 0.410 / 0.916
+    # (tools/diag_vgg.py); the per-kernel arithmetic is pinned to 1e-4 in test_kernels_gpu.py.
+    cos = float(torch.nn.functional.cosine_similarity(xg.grad.flatten().cpu(), xr.grad.flatten(), dim=0))
+    assert errs["dx"] <= 0.5 and cos >= 0.88, (errs, cos)
+    assert any(p._version >= 0 for p in mod.parameters()) and mod._b200 is not None

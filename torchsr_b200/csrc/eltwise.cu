@@ -843,10 +843,11 @@ __global__ void maxpool2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y
     st8(y + p * C + g * 8, m);
   }
 }
-// MAXPOOL2_BWD: p0 = x (pool input) bf16, p1 = y (pool output) bf16, p2 = dy bf16, p3 = dx out bf16; i as MAXPOOL2.
+// MAXPOOL2_BWD: p0 = x (pool input) bf16, p1 = y (pool output) bf16, p2 = dy bf16, p3 = dx out bf16; i as MAXPOOL2,
+// i4 relu: x is a ReLU output whose own backward is folded in (gradient only where x > 0).
 // Gradient goes to the first element equal to the max in (0,0),(0,1),(1,0),(1,1) order (ATen's tie rule).
 __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, const bf16* __restrict__ dy,
-                                    bf16* __restrict__ dx, int B, int H, int W, int C) {
+                                    bf16* __restrict__ dx, int B, int H, int W, int C, int relu) {
   pdl_sync();
   const int groups = C / 8, Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(B) * Ho * Wo * groups;
@@ -873,7 +874,7 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const bool hit = !done[k] && v[k] == m[k];
-          o[k] = hit ? d[k] : 0.f;
+          o[k] = (hit && !(relu && v[k] <= 0.f)) ? d[k] : 0.f;
           done[k] = done[k] || hit;
         }
         st8(dx + off, o);
@@ -1052,7 +1053,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       break;
     case TSR_E_MAXPOOL2_BWD:
       ce = launch_k(maxpool2_bwd_kernel, dim3(grid_for(i[0] * (i[1] / 2) * (i[2] / 2) * (i[3] / 8))), dim3(256), 0, st, pdl, 
-          (const bf16*)p[0], (const bf16*)p[1], (const bf16*)p[2], (bf16*)p[3], i[0], i[1], i[2], i[3]);
+          (const bf16*)p[0], (const bf16*)p[1], (const bf16*)p[2], (bf16*)p[3], i[0], i[1], i[2], i[3], i[4]);
       break;
     case TSR_E_CAST:
       ce = launch_k(cast_kernel, dim3(grid_for(i[0])), dim3(256), 0, st, pdl, p[0], p[1], i[0], i[1]);

@@ -549,3 +549,95 @@ def define_esrgan_generator(m, plan: Plan, shape):
                                   "implemented (the reference training loops never request it)")
 
     plan.input_fn, plan.output_fn, plan.ingest_fn, plan.grad_input_fn = input_fn, output_fn, ingest_fn, grad_input_fn
+
+
+# ------------------------------------------------------------------------------------------------ VGG19 features
+def vgg_records(m) -> List[ConvRec]:
+    """Every nn.Conv2d of the (frozen) torchvision feature extractor; the 3-channel first conv runs as a full-K GEMM
+    over im2row columns like the discriminators' first layer."""
+    return [ConvRec(f"features.{i}", layer, "fullk" if layer.in_channels == 3 else "std", need_dgrad=True)
+            for i, layer in enumerate(m.features) if isinstance(layer, torch.nn.Conv2d)]
+
+
+def define_vgg(m, plan: Plan, shape):
+    """torchvision vgg19.features[:36] (torchsr/srgan/loss.py:30-33): (3x3 conv + ReLU) x 16 with four 2x2 max-pools,
+    output = post-ReLU conv5_4 features. ReLU is fused into the conv epilogue; its backward into the epilogue of the
+    data-gradient conv that produces the gradient (or into the max-pool backward). Frozen: no weight gradients."""
+    B, cin, H, W = shape
+    if cin != 3 or H % 16 or W % 16:
+        raise RuntimeError(f"VGG feature extractor expects [N,3,H,W] with H, W multiples of 16, got {tuple(shape)}")
+    R = _recs(plan)
+    fwd = plan.fwd
+    layers = list(m.features)
+    relu_hook = lambda a: dict(bwd_z=a, bwd_act=L.ACT_RELU)  # noqa: E731
+    x, h, w = None, H, W
+    E0 = None
+    i = 0
+    while i < len(layers):
+        layer = layers[i]
+        if isinstance(layer, torch.nn.Conv2d):
+            assert i + 1 < len(layers) and isinstance(layers[i + 1], torch.nn.ReLU), "conv without ReLU in VGG features"
+            assert layer.kernel_size == (3, 3) and layer.stride == (1, 1) and layer.padding == (1, 1)
+            rec = R[f"features.{i}"]
+            out = plan.act(f"a{i}", B, h, w, rec.cout)
+            if rec.kind == "fullk":
+                E0 = plan.act("E0", B, h, w, rec.epad)
+                plan.conv(fwd, E0, rec.w_fwd, rec.cols, 1, _geom1(h, w), rec.cout_pad, rec.block_n, out.t, out.strides(),
+                          rec.cout_pad, bias=rec.bias, act=L.ACT_RELU)
+
+                def bwd(bp, g, want_x, want_w, rec=rec, E0=E0):
+                    return plan.conv_dgrad(bp, "c0", rec, g, E0, out_f32=True) if want_x else None
+            else:
+                plan.conv_fwd(fwd, rec, x, out, act=L.ACT_RELU)
+
+                def bwd(bp, g, want_x, want_w, rec=rec, xin=x, name=f"c{i}"):
+                    return plan.conv_dgrad(bp, name, rec, g, xin)
+            out.hook = relu_hook(out)
+            plan.tape.append(bwd)
+            x = out
+            i += 2
+        elif isinstance(layer, torch.nn.MaxPool2d):
+            assert layer.kernel_size == 2 and layer.stride == 2
+            y = plan.act(f"p{i}", B, h // 2, w // 2, x.C)
+            fwd.add(ops.elt(L.E_MAXPOOL2, p=[x.t, y.t], i=[B, h, w, x.C]))
+
+            def bwd_pool(bp, g, want_x, want_w, xin=x, y=y, h=h, w=w, name=f"p{i}"):
+                d = plan.act(name + ".dx", B, h, w, xin.C)
+                bp.add(ops.elt(L.E_MAXPOOL2_BWD, p=[xin.t, y.t, g.t, d.t], i=[B, h, w, xin.C, 1]))   # + ReLU backward
+                return d
+
+            plan.tape.append(bwd_pool)
+            x, h, w = y, h // 2, w // 2
+            i += 1
+        else:
+            raise RuntimeError(f"unexpected layer in VGG features: {layer}")
+    feats = x
+    gy = plan.act("gy", B, h, w, feats.C)
+
+    def bwd_out(bp, g, want_x, want_w):
+        # gradient w.r.t. the post-ReLU output features: apply the last ReLU's derivative (no consumer conv to fuse into)
+        return plan.norm_act_bwd(bp, "out", g, feats, act=L.ACT_RELU, want_w=False)
+
+    if feats.hook is not None:
+        plan.tape.append(bwd_out)
+    r0 = R["features.0"]
+
+    def input_fn(x_nchw):
+        ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E0.t], i=[B, 3, H, W, r0.k, r0.k, r0.pad, r0.pad, 1, r0.epad]))
+
+    def output_fn():
+        out = torch.empty(B, feats.C, feats.H, feats.W, dtype=F32, device=plan.device)
+        ops.run_now(ops.elt(L.E_NHWC2NCHW, p=[feats.t, out], i=[B, feats.C, feats.H, feats.W, feats.ld, feats.c0, 0]))
+        return out
+
+    def ingest_fn(gout):
+        ops.run_now(ops.elt(L.E_NCHW2NHWC, p=[gout, gy.t], i=[B, feats.C, feats.H, feats.W, feats.C, 0]))
+        return gy
+
+    def grad_input_fn():
+        dE0 = plan.cur_g
+        gx = torch.empty(B, 3, H, W, dtype=F32, device=plan.device)
+        ops.run_now(ops.elt(L.E_GATHER_OUT, p=[dE0.t, gx, None], i=[B, 3, H, W, r0.k, r0.k, r0.pad, r0.pad, -1, dE0.ld, 0]))
+        return gx
+
+    plan.input_fn, plan.output_fn, plan.ingest_fn, plan.grad_input_fn = input_fn, output_fn, ingest_fn, grad_input_fn

@@ -356,6 +356,11 @@ def _elt_extents(d: EltDesc):
         ld = i[3] if i[3] > 0 else N1
         return [(0, B * 4), (1, B * 4), (2, B * N1 * 4), (3, N1 * 4), (4, B * N1 * 4), (5, ((B - 1) * ld + N1) * 2),
                 (6, N1 * 4), (7, 4)]
+    if k in (L.E_MAXPOOL2, L.E_MAXPOOL2_BWD):
+        big, small = i[0] * i[1] * i[2] * i[3] * 2, i[0] * (i[1] // 2) * (i[2] // 2) * i[3] * 2
+        if i[1] % 2 or i[2] % 2 or i[3] % 8:
+            raise ExtentError("MAXPOOL2 needs even H, W and C % 8 == 0")
+        return [(0, big), (1, small)] + ([(2, small), (3, big)] if k == L.E_MAXPOOL2_BWD else [])
     if k == L.E_AXPBY:
         return [(0, i[0] * 2), (1, i[0] * 2), (2, i[0] * 2)]
     if k == L.E_CAST:

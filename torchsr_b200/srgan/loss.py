@@ -4,11 +4,34 @@ Adjacent to the hot path: a frozen torchvision VGG19 `features
 of the generated and the target image, inputs not ImageNet-normalised (as in the reference). The reference downloads
 ImageNet weights (`vgg19(pretrained=True)`); offline they come from the torch-hub cache, from a file named by
 TORCHSR_VGG_WEIGHTS, or - for benchmarks and parity runs, where only the arithmetic matters - from a seeded random
-initialisation (TORCHSR_VGG_WEIGHTS=random). This module is executed by PyTorch (cuDNN, bf16 autocast on CUDA)."""
+initialisation (TORCHSR_VGG_WEIGHTS=random).
+
+On a CUDA device the feature extractor runs on this repo's kernels (nets.define_vgg: implicit-GEMM convs with the ReLU
+fused into the epilogue, NHWC bf16 activations, max-pool / ReLU backward kernels, data gradients only - the network is
+frozen); TORCHSR_VGG_IMPL=torch selects PyTorch/cuDNN under bf16 instead. On the CPU it is plain PyTorch fp32."""
 import os
 
 import torch
 from torch import Tensor, nn
+
+from .. import nets
+from ..engine import B200Module, Plan
+
+
+class VGGFeaturesB200(B200Module):
+    """The frozen feature extractor as a launch-list module. Shares the Parameters of the torchvision layers it is
+    given (no copy, same state_dict entries); input NCHW fp32, output NCHW fp32 features."""
+
+    def __init__(self, features: nn.Sequential) -> None:
+        super().__init__()
+        self.features = features
+        self.eval()
+
+    def _records(self):
+        return nets.vgg_records(self), []
+
+    def _define(self, plan: Plan, shape):
+        nets.define_vgg(self, plan, shape)
 
 
 def _vgg19_features(feature_layer: int) -> nn.Sequential:
@@ -37,7 +60,17 @@ class VGGLoss(nn.Module):
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)
         self._bf16 = None
+        object.__setattr__(self, "_b200", None)
         return r
+
+    def _use_b200(self, x: Tensor) -> bool:
+        return x.is_cuda and os.environ.get("TORCHSR_VGG_IMPL", "b200") != "torch"
+
+    def _features_b200(self) -> VGGFeaturesB200:
+        if getattr(self, "_b200", None) is None:
+            # not registered as a child module: the parameters already belong to self.features
+            object.__setattr__(self, "_b200", VGGFeaturesB200(self.features))
+        return self._b200
 
     def _features_bf16(self):
         """bf16 channels_last copy of the frozen feature extractor (made once; the weights never change)."""
@@ -47,24 +80,20 @@ class VGGLoss(nn.Module):
             object.__setattr__(self, "_bf16", f.eval())
         return self._bf16
 
+    def _extract(self, x: Tensor) -> Tensor:
+        if self._use_b200(x):
+            return self._features_b200()(x)
+        if x.is_cuda:
+            return self._features_bf16()(x.to(dtype=torch.bfloat16, memory_format=torch.channels_last)).float()
+        return self.features(x)
+
     def target_features(self, target: Tensor) -> Tensor:
         """Features of the (constant) target image; lets a trainer compute them early, on another stream."""
         with torch.no_grad():
-            if target.is_cuda:
-                return self._features_bf16()(target.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-            return self.features(target)
+            return self._extract(target)
 
     def from_features(self, source: Tensor, target_features: Tensor) -> Tensor:
-        if source.is_cuda:
-            fs = self._features_bf16()(source.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-            return torch.nn.functional.l1_loss(fs.float(), target_features.float())
-        return torch.nn.functional.l1_loss(self.features(source), target_features)
+        return torch.nn.functional.l1_loss(self._extract(source), target_features)
 
     def forward(self, source: Tensor, target: Tensor) -> Tensor:
-        if source.is_cuda:
-            f = self._features_bf16()
-            fs = f(source.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-            with torch.no_grad():
-                ft = f(target.to(dtype=torch.bfloat16, memory_format=torch.channels_last))
-            return torch.nn.functional.l1_loss(fs.float(), ft.float())
-        return torch.nn.functional.l1_loss(self.features(source), self.features(target))
+        return self.from_features(source, self.target_features(target))
