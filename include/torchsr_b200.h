@@ -95,6 +95,11 @@ typedef struct tsr_conv_desc {
   const float* bnr_coef;    /* [4][bnr_c] forward coefficients (scale, shift, mean, invstd) or null (z = x) */
   const float* bnr_prelu;
   int32_t bnr_act, bnr_c;
+  /* split-K with in-kernel finalize (splits > 1 and out_mode != TSR_OUT_GEMM_T_ATOMIC): fp32 workspace [M][ws_ld] and
+     one int per output tile, both all-zero between launches (the kernel leaves them zeroed) */
+  float* ws;
+  int32_t* tile_counters;
+  int32_t ws_ld, _pad1;
   int64_t* trace;           /* optional debug: per-CTA clock64 stamps [grid][40] (null in production) */
 } tsr_conv_desc_t;
 
@@ -177,6 +182,30 @@ typedef struct tsr_pack_entry {
   int64_t block_start;  /* first CUDA block of this entry (prefix sum, 256 threads x 4 elements per block) */
   int64_t count;        /* elements in the packed matrix */
 } tsr_pack_entry_t;
+
+/* TSR_E_ADAM table entry: one parameter tensor of a torch.optim.Adam-equivalent step (no weight decay, no amsgrad)
+   that also refreshes the bf16 operand copies the conv / GEMM kernels read (csrc/eltwise.cu adam_pack_kernel). */
+enum tsr_adam_mode {
+  TSR_AD_PLAIN = 0,   /* update only (1-D parameters, convs whose packs the pack kernel still makes)       */
+  TSR_AD_CONV = 1,    /* OIHW conv weight: + dst_fwd[(t*rows_fwd + co')*cols_fwd + ci], dst_t[(t*rows_t + ci)*cols_t + co'] */
+  TSR_AD_LINEAR = 2   /* Linear weight [n][c*HW+hw]: + dst_fwd[n*K + hw*C + c] (NHWC column order)          */
+};
+typedef struct tsr_adam_entry {
+  float* p;           /* parameter (fp32, updated in place) */
+  const float* g;     /* gradient */
+  float* m;           /* exp_avg */
+  float* v;           /* exp_avg_sq */
+  void* dst_fwd;      /* bf16 forward pack or null */
+  void* dst_t;        /* bf16 data-gradient pack or null */
+  int64_t numel;
+  int64_t block_start; /* first CUDA block of this entry */
+  int32_t mode;
+  int32_t cout, cin, kk;        /* CONV: OIHW dims (kk = kh*kw); LINEAR: cout = rows, cin = C, kk = HW */
+  int32_t rows_fwd, cols_fwd;   /* CONV: rows per tap slot / columns of the forward pack */
+  int32_t rows_t, cols_t;       /* CONV: same for the transposed pack */
+  int32_t shuffle;              /* PixelShuffle output-channel permutation (as tsr_pack_entry) */
+  int32_t _pad;
+} tsr_adam_entry_t;
 
 typedef struct tsr_prog tsr_prog_t;
 

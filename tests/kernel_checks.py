@@ -120,7 +120,7 @@ def check_gemm_mn_major(M=192, N=32, K=128, seed=2):
 
 # ------------------------------------------------------------------------------------------------ conv forward
 def check_conv_fwd(B=2, H=24, W=24, Cin=64, Cout=64, k=3, stride=1, block_n=None, bias=False, act=L.ACT_NONE,
-                   stats=False, shuffle=False, residual=False, seed=3, out_f32=True):
+                   stats=False, shuffle=False, residual=False, seed=3, out_f32=True, splits=1, repeat=1):
     g = torch.Generator().manual_seed(seed)
     pad = k // 2
     x = bf16_round(torch.randn(B, Cin, H, W, generator=g))
@@ -156,8 +156,19 @@ def check_conv_fwd(B=2, H=24, W=24, Cin=64, Cout=64, k=3, stride=1, block_n=None
                       prelu=alpha_dev if act == L.ACT_PRELU else None, act=act, res=res_dev,
                       aux=(Ho * Wo * Cout, Wo * Cout, Cout), stats_partial=stats_buf, stats_ld=Cout,
                       shuf_c=Cout // 4 if shuffle else 64)
-    ops.run_now(d)
+    if splits > 1:
+        # split-K with in-kernel finalize: zeroed fp32 workspace + tile counters, which the kernel leaves zeroed
+        M = B * Ho * Wo
+        ws = torch.zeros((M + 127) // 128 * 128, Cout, device=DEV)
+        cnt = torch.zeros(((M + 127) // 128) * (Cout // block_n), dtype=torch.int32, device=DEV)
+        d.splits, d.ws, d.tile_counters, d.ws_ld = splits, ops.ptr(ws), ops.ptr(cnt), Cout
+    for rep in range(repeat):     # repeated launches must give the same result (self-cleaning workspace)
+        if stats and rep:
+            stats_buf.zero_()
+        ops.run_now(d)
     sync_check()
+    if splits > 1:
+        assert float(ws.abs().max()) == 0.0 and int(cnt.abs().max()) == 0, "split-K workspace not left zeroed"
     ref = F.conv2d(x, w, b, stride=stride, padding=pad)
     pre = ref.clone()
     if residual:

@@ -52,6 +52,10 @@ CHECKS = [
     ("conv3x3_c16", lambda: K.check_conv_fwd(Cin=16, Cout=64)),
     ("conv3x3_128_256", lambda: K.check_conv_fwd(Cin=128, Cout=256, H=12, W=12)),
     ("conv3x3_512", lambda: K.check_conv_fwd(Cin=512, Cout=512, H=6, W=6)),
+    ("conv3x3_splitk", lambda: K.check_conv_fwd(Cin=256, Cout=256, H=12, W=12, splits=6, bias=True, act=L.ACT_LEAKY,
+                                                stats=True, repeat=2)),
+    ("conv3x3_splitk_odd", lambda: K.check_conv_fwd(B=3, H=13, W=10, Cin=128, Cout=64, splits=4, residual=True,
+                                                    out_f32=False, repeat=2)),
     ("conv3x3_s2", lambda: K.check_conv_fwd(stride=2)),
     ("conv3x3_s2_128", lambda: K.check_conv_fwd(Cin=128, Cout=128, H=12, W=12, stride=2, stats=True)),
     ("conv9x9_64", lambda: K.check_conv_fwd(k=9, Cout=32, H=12, W=12)),

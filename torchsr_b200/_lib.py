@@ -44,6 +44,7 @@ class ConvDesc(C.Structure):
         ("w_static", C.c_int32),
         ("bnr_x", C.c_void_p), ("bnr_coef", C.c_void_p), ("bnr_prelu", C.c_void_p), ("bnr_act", C.c_int32),
         ("bnr_c", C.c_int32),
+        ("ws", C.c_void_p), ("tile_counters", C.c_void_p), ("ws_ld", C.c_int32), ("_pad1", C.c_int32),
         ("trace", C.c_void_p),
     ]
 
@@ -72,6 +73,19 @@ class PackEntry(C.Structure):
         ("cout", C.c_int32), ("cin", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("rows_pad", C.c_int32), ("cols_pad", C.c_int32), ("shuffle", C.c_int32),
         ("block_start", C.c_int64), ("count", C.c_int64),
+    ]
+
+
+AD_PLAIN, AD_CONV, AD_LINEAR = 0, 1, 2
+
+
+class AdamEntry(C.Structure):
+    _fields_ = [
+        ("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+        ("dst_fwd", C.c_void_p), ("dst_t", C.c_void_p), ("numel", C.c_int64), ("block_start", C.c_int64),
+        ("mode", C.c_int32), ("cout", C.c_int32), ("cin", C.c_int32), ("kk", C.c_int32),
+        ("rows_fwd", C.c_int32), ("cols_fwd", C.c_int32), ("rows_t", C.c_int32), ("cols_t", C.c_int32),
+        ("shuffle", C.c_int32), ("_pad", C.c_int32),
     ]
 
 

@@ -184,7 +184,8 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   memcpy(p.tap_wrow, d.tap_wrow, sizeof(p.tap_wrow));
   const int total_iters = p.num_taps * p.kc_per_tap;
   int splits = d.splits > 0 ? d.splits : 1;
-  if (splits > 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC) return fail(-20, "split-K needs OUT_GEMM_T_ATOMIC");
+  if (splits > 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && (!d.ws || !d.tile_counters || d.ws_ld < d.cout_pad))
+    return fail(-20, "split-K needs OUT_GEMM_T_ATOMIC or a reduction workspace (ws, tile_counters, ws_ld >= cout_pad)");
   if (splits > total_iters) splits = total_iters;
   p.iters_per_split = (total_iters + splits - 1) / splits;
   splits = (total_iters + p.iters_per_split - 1) / p.iters_per_split;
@@ -237,6 +238,9 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   e.res_scale = d.res_scale;
   e.res2_scale = d.res2_scale;
   e.res_cols = d.res_cols > 0 ? d.res_cols : (1 << 30);
+  e.ws = d.ws;
+  e.tile_counters = d.tile_counters;
+  e.ws_ld = d.ws_ld;
   e.bnr_x = d.bnr_x;
   e.bnr_coef = d.bnr_coef;
   e.bnr_prelu = d.bnr_prelu;

@@ -377,16 +377,68 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     const bool ok = mbar_wait(bar_tmem, 0, e.err, 3);
     tc_fence_after();
     if (trace && threadIdx.x == 64) trace[5] = clock64();
-    if (ok) {
+    // ---- split-K: reduce the partial tiles through the fp32 workspace, the last CTA of the tile finalizes
+    const bool split_ws = gridDim.z > 1 && out_mode != OUT_GEMM_T_ATOMIC;
+    bool finalize = ok;
+    if (split_ws) {
+      float* wrow = e.ws + static_cast<long long>(m) * e.ws_ld + colbase;
+      if (ok) {
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);     // .sync.aligned: every lane of the warp, valid row or not
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + ch * 16 + i), "r"(r[i]),
+                           "r"(r[i + 1]), "r"(r[i + 2]), "r"(r[i + 3])
+                           : "memory");
+          }
+        }
+      }
+      // release: the CTA's reductions are ordered before the counter bump by the barrier + one cumulative fence
+      named_bar_sync(1, kConvThreads - 64);
+      int* flag = reinterpret_cast<int*>(smem_gen + 144);
+      if (threadIdx.x == 64) {
+        __threadfence();
+        int* cnt = e.tile_counters + blockIdx.y * gridDim.x + blockIdx.x;
+        const int old = atomicAdd(cnt, 1);
+        const int last = old == static_cast<int>(gridDim.z) - 1;
+        if (last) *cnt = 0;
+        __threadfence();
+        *flag = last;
+      }
+      named_bar_sync(1, kConvThreads - 64);
+      finalize = ok && (*reinterpret_cast<volatile int*>(flag) != 0);
+    }
+    if (finalize) {
       for (int ch = ch_begin; ch < ch_end; ++ch) {
-        uint32_t r[16];
-        tmem_ld16(taddr + ch * 16, r);
-        tmem_ld_wait();
-        if (trace && threadIdx.x == 64 && ch < 4) trace[32 + 2 * ch] = clock64();
         const int col0 = colbase + ch * 16;
         float v[16];
+        if (split_ws) {
+          // sums of all splits, read from L2 (every line is read once per launch and L1 starts each launch empty);
+          // all loads of the chunk are issued before the zeroing stores - a store to an address waits for the
+          // load of that address, so interleaving them would serialise on the L2 latency
+          float4* wp = reinterpret_cast<float4*>(e.ws + static_cast<long long>(m) * e.ws_ld + col0);
+          float4 q[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 4; ++i) q[i] = valid ? __ldcg(wp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[4 * i] = q[i].x; v[4 * i + 1] = q[i].y; v[4 * i + 2] = q[i].z; v[4 * i + 3] = q[i].w;
+          }
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) __stcg(wp + i, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        } else {
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        if (trace && threadIdx.x == 64 && ch < 4) trace[32 + 2 * ch] = clock64();
         const bool st = valid && col0 < n_valid;
         if (bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 16);
@@ -502,7 +554,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
       }
       named_bar_sync(1, kConvThreads - 64);
       const int t = threadIdx.x - 64;  // 0..255
-      if (want_stats && ok) {
+      if (want_stats && finalize) {
         // thread t -> (column t>>1, statistic t&1) for block_n <= 128; two passes for wider tiles
         for (int idx = t; idx < p.block_n * 2; idx += kConvThreads - 64) {
           const int c = idx >> 1, w = idx & 1;
@@ -511,7 +563,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
           atomicAdd(e.stats_partial + (colbase + c) * 2 + w, sum);
         }
       }
-      if (e.dalpha_partial != nullptr && t == 0) {
+      if (e.dalpha_partial != nullptr && t == 0 && finalize) {
         float tot = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) tot += scratch[4 * 256 * 2 + w];

@@ -50,6 +50,12 @@ struct EpiParams {
   // w.r.t. y = act(BN(x)); with z = x*scale+shift (scale/shift from bnr_coef, identity when null) the epilogue turns
   // it into dz = v * act'(z), stores dz, and accumulates per column sum(dz) and sum(dz*x) into stats_partial (and
   // sum(v*z*[z<=0]) into dalpha_partial) - the reductions bn_bwd_reduce_kernel would otherwise make in a second pass.
+  // Split-K with in-kernel finalize (gridDim.z > 1, out_mode != OUT_GEMM_T_ATOMIC): every split adds its partial
+  // tile into `ws` (fp32 [M][ws_ld], all zero between launches) with vector reductions and bumps the tile's counter;
+  // the CTA that arrives last reads the sums back, re-zeroes them (and the counter) and runs the normal epilogue.
+  float* ws;
+  int* tile_counters;    // [tiles_m * tiles_n], zero between launches
+  int ws_ld;
   const void* bnr_x;     // bf16 raw conv output x of the BatchNorm being differentiated (aux addressing), or null
   const float* bnr_coef; // [4][bnr_c]: scale, shift, mean, invstd (forward coefficients) or null
   const float* bnr_prelu;

@@ -613,6 +613,123 @@ __global__ void unpack_g_kernel(const tsr_pack_entry_t* __restrict__ tab, int n)
   }
 }
 
+// ---------------------------------------------------------------------------------------------- Adam + pack
+// ADAM: p0 = device table of tsr_adam_entry_t, p1 = lr (device float, or null -> f[0]), p2 = step (device float: number
+// of steps taken so far, incremented by the kernel), p3 = int block counter (zero between launches)
+// i: 0 n_entries, 1 total blocks; f: 0 lr (when p1 is null), 1 beta1, 2 beta2, 3 eps, 4 1-beta1, 5 1-beta2
+// torch.optim.Adam semantics (torch/optim/_functional / fused kernel): exp_avg = lerp(exp_avg, g, 1-b1);
+// exp_avg_sq = b2*exp_avg_sq + (1-b2)*g*g; p -= (lr / (1-b1^t)) * exp_avg / (sqrt(exp_avg_sq)/sqrt(1-b2^t) + eps).
+// The same pass writes the bf16 operand copies of the updated weights in the layouts the conv kernels read, so no
+// separate pack pass over the parameters is needed after an optimizer step.
+struct AdamCoef {
+  float w1, b2, omb2, step_size, inv_bc2_sqrt, eps;
+};
+__device__ __forceinline__ float adam_update(float& p, float g, float& m, float& v, const AdamCoef& c) {
+  m = m + c.w1 * (g - m);
+  v = c.b2 * v + c.omb2 * g * g;
+  const float denom = sqrtf(v) * c.inv_bc2_sqrt + c.eps;
+  p = p - c.step_size * (m / denom);
+  return p;
+}
+__device__ __forceinline__ int find_adam_entry(const tsr_adam_entry_t* tab, int n, long long block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab[mid].block_start <= block) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(256) adam_pack_kernel(const tsr_adam_entry_t* __restrict__ tab, int n,
+                                                        const float* __restrict__ lr_ptr, float lr_val, float beta1,
+                                                        float beta2, float eps, float one_minus_b1, float one_minus_b2,
+                                                        float* step_ptr, int* counter) {
+  __shared__ float tile[32][65];
+  pdl_sync();
+  const tsr_adam_entry_t e = tab[find_adam_entry(tab, n, blockIdx.x)];
+  const float t = *reinterpret_cast<volatile float*>(step_ptr) + 1.f;
+  const float lr = lr_ptr ? *lr_ptr : lr_val;
+  AdamCoef c;
+  c.w1 = one_minus_b1;      // 1 - beta computed in double on the host (1.f - 0.999f loses 1e-5 relative)
+  c.b2 = beta2;
+  c.omb2 = one_minus_b2;
+  c.step_size = lr / (1.f - powf(beta1, t));
+  c.inv_bc2_sqrt = 1.f / sqrtf(1.f - powf(beta2, t));
+  c.eps = eps;
+  const long long b = static_cast<long long>(blockIdx.x) - e.block_start;
+  if (e.mode == TSR_AD_PLAIN) {
+    const long long i0 = b * 1024 + threadIdx.x * 4;
+    if (i0 + 3 < e.numel && ((reinterpret_cast<uintptr_t>(e.p) | reinterpret_cast<uintptr_t>(e.g)) & 15) == 0) {
+      float4 P = *reinterpret_cast<float4*>(e.p + i0), M = *reinterpret_cast<float4*>(e.m + i0),
+             V = *reinterpret_cast<float4*>(e.v + i0);
+      const float4 G = *reinterpret_cast<const float4*>(e.g + i0);
+      adam_update(P.x, G.x, M.x, V.x, c);
+      adam_update(P.y, G.y, M.y, V.y, c);
+      adam_update(P.z, G.z, M.z, V.z, c);
+      adam_update(P.w, G.w, M.w, V.w, c);
+      *reinterpret_cast<float4*>(e.p + i0) = P;
+      *reinterpret_cast<float4*>(e.m + i0) = M;
+      *reinterpret_cast<float4*>(e.v + i0) = V;
+    } else {
+      for (long long i = i0; i < i0 + 4 && i < static_cast<long long>(e.numel); ++i) adam_update(e.p[i], e.g[i], e.m[i], e.v[i], c);
+    }
+  } else if (e.mode == TSR_AD_CONV) {
+    // one thread = one (co, ci) pair = kk consecutive OIHW elements; lanes walk ci, so the forward pack
+    // ([tap][co'][ci]) gets contiguous 64-byte stores per tap
+    const long long pair = b * 256 + threadIdx.x;
+    if (pair < static_cast<long long>(e.cout) * e.cin) {
+      const int co = static_cast<int>(pair / e.cin), ci = static_cast<int>(pair - static_cast<long long>(co) * e.cin);
+      int cop = co;
+      if (e.shuffle) {
+        const int c4 = e.cout / 4;
+        cop = (co & 3) * c4 + (co >> 2);   // inverse of co = 4*(r % c4) + r / c4
+      }
+      const long long base = pair * e.kk;
+      bf16* df = reinterpret_cast<bf16*>(e.dst_fwd);
+      bf16* dt = reinterpret_cast<bf16*>(e.dst_t);
+      for (int k = 0; k < e.kk; ++k) {
+        float P = e.p[base + k], M = e.m[base + k], V = e.v[base + k];
+        adam_update(P, e.g[base + k], M, V, c);
+        e.p[base + k] = P;
+        e.m[base + k] = M;
+        e.v[base + k] = V;
+        const bf16 h = __float2bfloat16(P);
+        if (df) df[(static_cast<long long>(k) * e.rows_fwd + cop) * e.cols_fwd + ci] = h;
+        if (dt) dt[(static_cast<long long>(k) * e.rows_t + ci) * e.cols_t + cop] = h;
+      }
+    }
+  } else {
+    // LINEAR: one block = one output row x 32 channels x all HW positions (contiguous in the parameter)
+    const int HW = e.kk, Cc = e.cin, K = Cc * HW;
+    const int chunks = (Cc + 31) / 32;
+    const int row = static_cast<int>(b / chunks), c0 = static_cast<int>(b % chunks) * 32;
+    const int nc = min(32, Cc - c0);
+    const long long off = static_cast<long long>(row) * K + static_cast<long long>(c0) * HW;
+    for (int i = threadIdx.x; i < nc * HW; i += 256) {
+      float P = e.p[off + i], M = e.m[off + i], V = e.v[off + i];
+      adam_update(P, e.g[off + i], M, V, c);
+      e.p[off + i] = P;
+      e.m[off + i] = M;
+      e.v[off + i] = V;
+      tile[i / HW][i % HW] = P;
+    }
+    __syncthreads();
+    bf16* d0 = reinterpret_cast<bf16*>(e.dst_fwd) + static_cast<long long>(row) * K + c0;
+    for (int i = threadIdx.x; i < nc * HW; i += 256) {
+      const int hw = i / nc, cc = i % nc;
+      d0[static_cast<long long>(hw) * Cc + cc] = __float2bfloat16(tile[cc][hw]);
+    }
+  }
+  // the block that finishes last advances the step counter (every block read it at its start)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(counter, 1) == static_cast<int>(gridDim.x) - 1) {
+      *counter = 0;
+      *step_ptr = t;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- Linear wgrad
 // p0 = dpre fp32 [B][Nf] (gradient wrt pre-activation of the Linear), p1 = X fp32 [B][K] in the parameter's (c,h,w)
 // column order (the NHWC2NCHW kernel produces it), p2 = dW fp32 [Nf][K], p3 = db fp32 [Nf]
@@ -1007,6 +1124,11 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       break;
     case TSR_E_UNPACK_G:
       ce = launch_k(unpack_g_kernel, dim3(static_cast<unsigned>(i[1])), dim3(256), 0, st, pdl, (const tsr_pack_entry_t*)p[0], i[0]);
+      break;
+    case TSR_E_ADAM:
+      ce = launch_k(adam_pack_kernel, dim3(static_cast<unsigned>(i[1])), dim3(256), 0, st, pdl,
+                    (const tsr_adam_entry_t*)p[0], i[0], (const float*)p[1], d.f[0], d.f[1], d.f[2], d.f[3], d.f[4], d.f[5],
+                    (float*)p[2], (int*)p[3]);
       break;
     case TSR_E_LINEAR_WGRAD: {
       dim3 grid((i[2] + 255) / 256, (i[1] + kLwF - 1) / kLwF);

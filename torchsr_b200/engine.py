@@ -26,6 +26,10 @@ F32 = torch.float32
 NUM_SMS = 148
 # fold BatchNorm-backward column reductions into the epilogue of the data-gradient conv that produces the gradient
 FUSE_BN_REDUCE = os.environ.get("TSR_FUSE_BN_REDUCE", "1") != "0"
+# convs with at least this many K iterations (taps x channel chunks) and an under-filled grid split K. Off by default
+# (0): measured on B200 the last-CTA finalize (dependent L2 reads of the fp32 partial sums) costs more than the shorter
+# main loop saves for every layer of this workload (profiles/r01_splitk_experiment.md); the mode stays parity-tested.
+SPLIT_K_MIN_ITERS = int(os.environ.get("TSR_SPLITK_MIN_ITERS", "0"))
 ZERO_ARENA_FLOATS = 64 * 1024
 
 
@@ -165,6 +169,7 @@ class ParamStore:
         self.acc_elems = max(acc_elems, 64)
         self._version = None
         self.dirty = True
+        self.opt_fresh = False
         self._build_tables()
         _LIVE_STORES.add(self)
         _install_optimizer_hook()
@@ -204,6 +209,15 @@ class ParamStore:
                              rows_pad=r.nout_pad, cols_pad=r.K, shuffle=0, count=n))
         self._pack_tab, self._pack_n, self._pack_blocks = ops.pack_table(pack, self.device)
         self._pack_desc = ops.elt(L.E_PACK_W, p=[self._pack_tab], i=[self._pack_n, self._pack_blocks])
+        # the packs torchsr_b200.optim.FusedAdam does not write itself (first / last layers with 3 channels)
+        std_dsts = {r.w_fwd.data_ptr() for r in self.convs if r.kind == "std"} | \
+                   {r.w_t.data_ptr() for r in self.convs if r.kind == "std" and r.need_dgrad} | \
+                   {r.w_fwd.data_ptr() for r in self.linears if r.Hf * r.Wf <= 64}
+        special = [e for e in pack if e["dst"].data_ptr() not in std_dsts]
+        self._pack_special_desc = None
+        if special:
+            self._sp_tab, n, blocks = ops.pack_table(special, self.device)
+            self._pack_special_desc = ops.elt(L.E_PACK_W, p=[self._sp_tab], i=[n, blocks])
         self._watched = [r.weight for r in self.convs] + [r.weight for r in self.linears] + \
                         [r.bias for r in self.bias_perm]
 
@@ -214,7 +228,13 @@ class ParamStore:
             ver += p._version
         if ver == self._version and not self.dirty:
             return
-        ops.run_now(self._pack_desc)
+        if ver == self._version and self.opt_fresh:
+            # stepped by torchsr_b200.optim.FusedAdam only: it rewrote the 'std' conv and Linear packs itself
+            if self._pack_special_desc is not None:
+                ops.run_now(self._pack_special_desc)
+        else:
+            ops.run_now(self._pack_desc)
+        self.opt_fresh = False
         for r in self.bias_perm:   # PixelShuffle layers consume the bias in packed-column order
             c4 = r.cout // 4
             r.bias_packed.view(4, c4).copy_(r.bias.detach().view(c4, 4).t())
@@ -356,9 +376,26 @@ class Plan:
                       res2=res2.t if res2 is not None else None, res2_scale=res2_scale)
         if shuffle_out:
             kw.update(out_mode=L.OUT_SHUFFLE, shuf_c=rec.cout // 4)
-        block_n = self.pick_block_n(x.B * geom["Ho"] * geom["Wo"], rec.cout_pad, rec.block_n)
+        tiles = self.pick_tiles(x.B * geom["Ho"] * geom["Wo"], rec.cout_pad, rec.block_n,
+                                len(geom["taps"]) * ((x.C) // ops.pick_block_k(x.C)))
+        block_n = tiles.pop("block_n")
         return self.conv(prog, x, rec.w_fwd, rec.cols, rec.slots, geom, rec.cout_pad, block_n, out.t, out.strides(),
-                         rec.cout_pad, **kw)
+                         rec.cout_pad, **kw, **tiles)
+
+    def pick_tiles(self, M: int, n_total: int, block_n: int, total_iters: int) -> dict:
+        """Tile shape / split-K choice for a conv whose grid would leave most SMs idle. Deep layers (many K iterations,
+        few output tiles) split K across CTAs - every split re-reads only its slice of the activations, the partial
+        tiles meet in an fp32 workspace and the last CTA runs the epilogue (conv_igemm.cu). Shallow layers halve the N
+        tile instead (pick_block_n). Returns the extra conv_desc keywords."""
+        tiles_m = (M + 127) // 128
+        ctas = tiles_m * (n_total // block_n)
+        if SPLIT_K_MIN_ITERS > 0 and total_iters >= SPLIT_K_MIN_ITERS and ctas * 2 <= NUM_SMS + 20:
+            splits = max(1, min(total_iters // 4, (2 * NUM_SMS) // ctas))
+            if splits > 1:
+                ws = self.buf(f"splitk.ws.{M}x{n_total}", _round_up(M, 128) * n_total, F32, zero=True)
+                cnt = self.buf(f"splitk.cnt.{tiles_m}x{n_total // block_n}", ctas, torch.int32, zero=True)
+                return dict(block_n=block_n, splits=splits, ws=ws, tile_counters=cnt, ws_ld=n_total)
+        return dict(block_n=self.pick_block_n(M, n_total, block_n))
 
     @staticmethod
     def pick_block_n(M: int, n_total: int, block_n: int) -> int:
@@ -506,7 +543,11 @@ class Plan:
             n_out, n_slots = rec.t_rows, 1
             geom = ops.fwd_geometry(dy.H, dy.W, 1, 1, 0, 0, 1)
         block_n = next(b for b in (128, 96, 64, 160, 192, 32, 16) if n_out % b == 0 and b <= n_out)
-        if rec.stride == 1:
+        if rec.stride == 1 and rec.kind != "fullk":
+            tiles = self.pick_tiles(dy.M, n_out, block_n, len(geom["taps"]) * (dy.C // ops.pick_block_k(dy.C)))
+            block_n = tiles.pop("block_n")
+            kw.update(tiles)
+        elif rec.stride == 1:
             block_n = self.pick_block_n(dy.M, n_out, block_n)
         dx = out
         if dx is None and (hook is None or hook.get("unshuffle_to") is None):

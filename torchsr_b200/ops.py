@@ -123,7 +123,7 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
               act=L.ACT_NONE, out_preact=None, res=None, bwd_z=None, bwd_act=L.ACT_NONE, aux=(0, 0, 0), aux_ch_off=0,
               dalpha_partial=None, stats_partial=None, stats_ld=0, acc_scale=1.0, leaky=0.2, shuf_c=64, res2=None,
               res_scale=1.0, res2_scale=1.0, res_cols=0, w_static=True, bnr_x=None, bnr_coef=None, bnr_prelu=None,
-              bnr_act=L.ACT_NONE, bnr_c=0) -> ConvDesc:
+              bnr_act=L.ACT_NONE, bnr_c=0, splits=1, ws=None, tile_counters=None, ws_ld=0) -> ConvDesc:
     d = ConvDesc()
     d.x, d.w = ptr(x), ptr(w)
     d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
@@ -137,7 +137,8 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     d.cout_pad = cout_pad
     d.w_rows, d.w_ld = n_slots * cout_pad, w_ld
     d.a_c0 = a_c0
-    d.splits = 1
+    d.splits = splits
+    d.ws, d.tile_counters, d.ws_ld = ptr(ws), ptr(tile_counters), ws_ld
     d.out, d.out_preact, d.bias, d.prelu = ptr(out), ptr(out_preact), ptr(bias), ptr(prelu)
     d.res, d.bwd_z, d.dalpha_partial, d.stats_partial = ptr(res), ptr(bwd_z), ptr(dalpha_partial), ptr(stats_partial)
     d.os_n, d.os_h, d.os_w = os_n, os_h, os_w
@@ -271,6 +272,12 @@ def validate_conv(d: ConvDesc):
         _need("conv stats_partial", d.stats_partial, d.stats_ld * 2 * 4)
     if d.dalpha_partial:
         _need("conv dalpha_partial", d.dalpha_partial, 4)
+    if d.a_mode == 0 and d.splits > 1:
+        tiles = ((d.N * d.Ho * d.Wo + 127) // 128) * (d.cout_pad // d.block_n)
+        if not d.ws or not d.tile_counters or d.ws_ld < d.cout_pad or d.ws_ld % 4:
+            raise ExtentError("split-K conv needs ws / tile_counters and ws_ld >= cout_pad (multiple of 4)")
+        _need("conv ws", d.ws, d.N * d.Ho * d.Wo * d.ws_ld * 4)
+        _need("conv tile_counters", d.tile_counters, tiles * 4)
     if d.bnr_x:
         if not d.stats_partial or d.bwd_z or d.out_mode != L.OUT_LINEAR:
             raise ExtentError("bnr_x needs stats_partial, no bwd_z hook and a linear store")

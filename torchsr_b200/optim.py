@@ -1,0 +1,130 @@
+"""Adam on this repo's kernels: one launch per parameter group updates every parameter, its
+exp_avg / exp_avg_sq state AND the bf16 operand copies the conv / GEMM kernels read (csrc/eltwise.cu
+adam_pack_kernel), replacing torch's multi-tensor Adam launches plus the separate re-pack pass over the weights.
+
+Same update rule, defaults and param_group keys as torch.optim.Adam (reference torchsr/srgan/trainer.py:171-185:
+lr 1e-4, betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad), so lr schedulers (StepLR) work unchanged; a tensor
+learning rate and the device-side step counter make a step capturable in a CUDA graph. There is no CPU path."""
+from typing import Dict, List
+
+import torch
+
+from . import _lib as L
+from . import engine, ops
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or eps < 0.0:
+            raise ValueError("invalid Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._tables: Dict[int, dict] = {}
+
+    # ---- per-group device state
+    def _group_state(self, gi: int, group) -> dict:
+        st = self._tables.get(gi)
+        params = [p for p in group["params"] if p.grad is not None]
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params) + \
+            tuple(id(s) for s in self._stores_of(params))
+        if st is not None and st["key"] == key:
+            return st
+        dev = params[0].device
+        if dev.type != "cuda" and not ops.DRY:
+            raise L.TorchSRB200Error("torchsr_b200.optim.FusedAdam runs only on CUDA parameters (no CPU fallback)")
+        old = st
+        st = dict(key=key, params=params)
+        # optimizer state lives in two flat arenas; self.state[p] exposes per-parameter views (state_dict compatible)
+        if old is not None and [id(p) for p in old["params"]] == [id(p) for p in params]:
+            st.update(m=old["m"], v=old["v"], step=old["step"], counter=old["counter"], offs=old["offs"])
+        else:
+            offs, tot = [], 0
+            for p in params:
+                offs.append(tot)
+                tot += (p.numel() + 3) // 4 * 4
+            st.update(m=torch.zeros(tot, dtype=torch.float32, device=dev), v=torch.zeros(tot, dtype=torch.float32, device=dev),
+                      step=torch.zeros(1, dtype=torch.float32, device=dev),
+                      counter=torch.zeros(1, dtype=torch.int32, device=dev), offs=offs)
+            for p, o in zip(params, offs):
+                s = self.state[p]
+                s["step"] = st["step"]
+                s["exp_avg"] = st["m"][o:o + p.numel()].view(p.shape)
+                s["exp_avg_sq"] = st["v"][o:o + p.numel()].view(p.shape)
+        # table
+        recs = self._recs_of(params)
+        arr = (L.AdamEntry * len(params))()
+        blocks = 0
+        stores = set()
+        for k, (p, o) in enumerate(zip(params, st["offs"])):
+            e = arr[k]
+            if not p.is_contiguous() or not p.grad.is_contiguous() or p.dtype != torch.float32:
+                raise L.TorchSRB200Error("FusedAdam needs contiguous fp32 parameters and gradients")
+            e.p, e.g = ops.ptr(p.detach()), ops.ptr(p.grad)
+            e.m, e.v = ops.ptr(st["m"], o), ops.ptr(st["v"], o)
+            e.numel = p.numel()
+            e.block_start = blocks
+            rec, store = recs.get(id(p), (None, None))
+            if isinstance(rec, engine.ConvRec) and rec.kind == "std" and rec.w_fwd is not None:
+                e.mode = L.AD_CONV
+                e.cout, e.cin, e.kk = rec.cout, rec.cin, rec.k * rec.k
+                e.dst_fwd, e.rows_fwd, e.cols_fwd = ops.ptr(rec.w_fwd), rec.cout_pad, rec.cols
+                if rec.need_dgrad:
+                    e.dst_t, e.rows_t, e.cols_t = ops.ptr(rec.w_t), rec.t_rows, rec.t_cols
+                e.shuffle = int(rec.shuffle)
+                blocks += (rec.cout * rec.cin + 255) // 256
+                stores.add(store)
+            elif isinstance(rec, engine.LinearRec) and rec.Hf * rec.Wf <= 64 and rec.w_fwd is not None:
+                e.mode = L.AD_LINEAR
+                e.cout, e.cin, e.kk = rec.nout, rec.C, rec.Hf * rec.Wf
+                e.dst_fwd = ops.ptr(rec.w_fwd)
+                blocks += rec.nout * ((rec.C + 31) // 32)
+                stores.add(store)
+            else:
+                e.mode = L.AD_PLAIN
+                blocks += (p.numel() + 1023) // 1024
+                if store is not None:
+                    stores.add(store)
+        # pinned staging + async copy: legal while a CUDA graph is being captured (the host buffer is kept alive)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        if dev.type == "cuda":
+            host = host.pin_memory()
+        st["table_host"] = host
+        st["table"] = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
+        st["table"].copy_(host, non_blocking=True)
+        st["n"], st["blocks"], st["stores"] = len(params), blocks, stores
+        self._tables[gi] = st
+        return st
+
+    @staticmethod
+    def _stores_of(params) -> List:
+        ids = {id(p) for p in params}
+        return [s for s in list(engine._LIVE_STORES) if any(id(q) in ids for q in s.params)]
+
+    def _recs_of(self, params) -> dict:
+        out = {}
+        for store in self._stores_of(params):
+            for r in store.convs:
+                out[id(r.weight)] = (r, store)
+            for r in store.linears:
+                out[id(r.weight)] = (r, store)
+            for q in store.params:
+                out.setdefault(id(q), (None, store))
+        return out
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            if not any(p.grad is not None for p in group["params"]):
+                continue
+            st = self._group_state(gi, group)
+            lr = group["lr"]
+            lr_t = lr if (isinstance(lr, torch.Tensor) and lr.is_cuda) else None
+            b1, b2 = group["betas"]
+            ops.run_now(ops.elt(L.E_ADAM, p=[st["table"], lr_t, st["step"], st["counter"]], i=[st["n"], st["blocks"]],
+                                f=[0.0 if lr_t is not None else float(lr), b1, b2, group["eps"], 1.0 - b1, 1.0 - b2]))
+            for store in st["stores"]:
+                store.opt_fresh = True     # its 'std' conv / Linear packs were just rewritten by the kernel
+        return loss

@@ -59,10 +59,11 @@ class SRGANTrainer:
         plan's flat buffer (no copy) - valid here because every backward is preceded by zero_grad() - and a second
         CUDA stream carries the work that depends only on the real batch."""
         for m in (self.generator, self.discriminator):
-            m._tsr["alias_grads"] = not self.distributed
-        # D(real) and D(fake) feed one loss: their weight gradients are summed by the last of the two backward passes
-        # (one add instead of one per parameter) and all-reduced once instead of twice
-        self.discriminator._tsr["merge_pending_grads"] = True
+            # gradients are handed to autograd as views of the plan's flat buffer (stable addresses, no copy); calls of
+            # one module that feed one loss - D(real) and D(fake) - are summed by the last of their backward passes
+            # (one add instead of one per parameter) and all-reduced in place once
+            m._tsr["alias_grads"] = True
+            m._tsr["merge_pending_grads"] = True
         cuda = self.device.type == 'cuda'
         # stream B shares the critical path (D(real)), stream V only carries the VGG content branch: lowest priority
         prio = lambda name, default: int(os.environ.get(name, default))  # noqa: E731
@@ -87,10 +88,16 @@ class SRGANTrainer:
 
     def _initialize_optimizers(self) -> None:
         cuda = self.device.type == 'cuda'
-        # fused multi-tensor Adam; capturable + tensor lr so that a whole training step can be replayed as one CUDA
-        # graph (graph_step) while StepLR keeps working (schedulers fill_() a tensor learning rate in place)
-        mk = lambda params: optim.Adam(params, lr=torch.tensor(0.0001, device=self.device) if cuda else 0.0001,  # noqa: E731
-                                       betas=(0.9, 0.999), fused=cuda, capturable=cuda)
+        # Adam on this repo's kernels (optim.FusedAdam: one launch updates parameters, state and the packed bf16 weight
+        # copies); tensor lr + device-side step counter so that a whole training step can be replayed as one CUDA graph
+        # (graph_step) while StepLR keeps working (schedulers fill_() a tensor learning rate in place).
+        # TSR_OPTIM=torch selects torch.optim.Adam(fused=True, capturable=True) instead.
+        if cuda and os.environ.get("TSR_OPTIM", "b200") != "torch":
+            from ..optim import FusedAdam
+            mk = lambda params: FusedAdam(params, lr=torch.tensor(0.0001, device=self.device), betas=(0.9, 0.999))  # noqa: E731
+        else:
+            mk = lambda params: optim.Adam(params, lr=torch.tensor(0.0001, device=self.device) if cuda else 0.0001,  # noqa: E731
+                                           betas=(0.9, 0.999), fused=cuda, capturable=cuda)
         self.psnr_optimizer = mk(self.generator.parameters())
         self.disc_optimizer = mk(self.discriminator.parameters())
         self.gen_optimizer = mk(self.generator.parameters())
