@@ -621,6 +621,7 @@ __global__ void unpack_g_kernel(const tsr_pack_entry_t* __restrict__ tab, int n)
 // exp_avg_sq = b2*exp_avg_sq + (1-b2)*g*g; p -= (lr / (1-b1^t)) * exp_avg / (sqrt(exp_avg_sq)/sqrt(1-b2^t) + eps).
 // The same pass writes the bf16 operand copies of the updated weights in the layouts the conv kernels read, so no
 // separate pack pass over the parameters is needed after an optimizer step.
+constexpr int kAdamTiles = 4;   // LINEAR mode: tiles per block
 struct AdamCoef {
   float w1, b2, omb2, step_size, inv_bc2_sqrt, eps;
 };
@@ -686,37 +687,100 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(const tsr_adam_entry_t* 
       const long long base = pair * e.kk;
       bf16* df = reinterpret_cast<bf16*>(e.dst_fwd);
       bf16* dt = reinterpret_cast<bf16*>(e.dst_t);
-      for (int k = 0; k < e.kk; ++k) {
-        float P = e.p[base + k], M = e.m[base + k], V = e.v[base + k];
-        adam_update(P, e.g[base + k], M, V, c);
-        e.p[base + k] = P;
-        e.m[base + k] = M;
-        e.v[base + k] = V;
-        const bf16 h = __float2bfloat16(P);
-        if (df) df[(static_cast<long long>(k) * e.rows_fwd + cop) * e.cols_fwd + ci] = h;
-        if (dt) dt[(static_cast<long long>(k) * e.rows_t + ci) * e.cols_t + cop] = h;
+      if (e.kk == 9) {
+        // 3x3: all 36 loads in flight before the first dependent instruction
+        float P[9], G[9], M[9], V[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          P[k] = e.p[base + k];
+          G[k] = e.g[base + k];
+          M[k] = e.m[base + k];
+          V[k] = e.v[base + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          adam_update(P[k], G[k], M[k], V[k], c);
+          e.p[base + k] = P[k];
+          e.m[base + k] = M[k];
+          e.v[base + k] = V[k];
+          const bf16 h = __float2bfloat16(P[k]);
+          if (df) df[(static_cast<long long>(k) * e.rows_fwd + cop) * e.cols_fwd + ci] = h;
+          if (dt) dt[(static_cast<long long>(k) * e.rows_t + ci) * e.cols_t + cop] = h;
+        }
+      } else {
+        for (int k = 0; k < e.kk; ++k) {
+          float P = e.p[base + k], M = e.m[base + k], V = e.v[base + k];
+          adam_update(P, e.g[base + k], M, V, c);
+          e.p[base + k] = P;
+          e.m[base + k] = M;
+          e.v[base + k] = V;
+          const bf16 h = __float2bfloat16(P);
+          if (df) df[(static_cast<long long>(k) * e.rows_fwd + cop) * e.cols_fwd + ci] = h;
+          if (dt) dt[(static_cast<long long>(k) * e.rows_t + ci) * e.cols_t + cop] = h;
+        }
       }
     }
   } else {
-    // LINEAR: one block = one output row x 32 channels x all HW positions (contiguous in the parameter)
+    // LINEAR: one tile = one output row x 32 channels x all HW positions (a contiguous run of the parameter); a block
+    // walks kAdamTiles consecutive tiles of a row so that the per-block prologue is amortised
     const int HW = e.kk, Cc = e.cin, K = Cc * HW;
     const int chunks = (Cc + 31) / 32;
-    const int row = static_cast<int>(b / chunks), c0 = static_cast<int>(b % chunks) * 32;
-    const int nc = min(32, Cc - c0);
-    const long long off = static_cast<long long>(row) * K + static_cast<long long>(c0) * HW;
-    for (int i = threadIdx.x; i < nc * HW; i += 256) {
-      float P = e.p[off + i], M = e.m[off + i], V = e.v[off + i];
-      adam_update(P, e.g[off + i], M, V, c);
-      e.p[off + i] = P;
-      e.m[off + i] = M;
-      e.v[off + i] = V;
-      tile[i / HW][i % HW] = P;
-    }
-    __syncthreads();
-    bf16* d0 = reinterpret_cast<bf16*>(e.dst_fwd) + static_cast<long long>(row) * K + c0;
-    for (int i = threadIdx.x; i < nc * HW; i += 256) {
-      const int hw = i / nc, cc = i % nc;
-      d0[static_cast<long long>(hw) * Cc + cc] = __float2bfloat16(tile[cc][hw]);
+    const int groups = (chunks + kAdamTiles - 1) / kAdamTiles;
+    const int row = static_cast<int>(b / groups);
+    const int ch0 = static_cast<int>(b % groups) * kAdamTiles;
+    for (int ch = ch0; ch < min(ch0 + kAdamTiles, chunks); ++ch) {
+      const int c0 = ch * 32;
+      const int nc = min(32, Cc - c0);
+      const int cnt = nc * HW;
+      const long long off = static_cast<long long>(row) * K + static_cast<long long>(c0) * HW;
+      const bool vec = (cnt & 3) == 0 && (off & 3) == 0 &&
+                       ((reinterpret_cast<uintptr_t>(e.p) | reinterpret_cast<uintptr_t>(e.g) |
+                         reinterpret_cast<uintptr_t>(e.m) | reinterpret_cast<uintptr_t>(e.v)) & 15) == 0;
+      if (vec) {
+        for (int q = threadIdx.x; q < cnt / 4; q += 256) {
+          float4 P = *reinterpret_cast<float4*>(e.p + off + 4 * q), M = *reinterpret_cast<float4*>(e.m + off + 4 * q),
+                 V = *reinterpret_cast<float4*>(e.v + off + 4 * q);
+          const float4 G = *reinterpret_cast<const float4*>(e.g + off + 4 * q);
+          adam_update(P.x, G.x, M.x, V.x, c);
+          adam_update(P.y, G.y, M.y, V.y, c);
+          adam_update(P.z, G.z, M.z, V.z, c);
+          adam_update(P.w, G.w, M.w, V.w, c);
+          *reinterpret_cast<float4*>(e.p + off + 4 * q) = P;
+          *reinterpret_cast<float4*>(e.m + off + 4 * q) = M;
+          *reinterpret_cast<float4*>(e.v + off + 4 * q) = V;
+          const float pv[4] = {P.x, P.y, P.z, P.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = 4 * q + j;
+            tile[i / HW][i % HW] = pv[j];
+          }
+        }
+      } else {
+        for (int i = threadIdx.x; i < cnt; i += 256) {
+          float P = e.p[off + i], M = e.m[off + i], V = e.v[off + i];
+          adam_update(P, e.g[off + i], M, V, c);
+          e.p[off + i] = P;
+          e.m[off + i] = M;
+          e.v[off + i] = V;
+          tile[i / HW][i % HW] = P;
+        }
+      }
+      __syncthreads();
+      bf16* d0 = reinterpret_cast<bf16*>(e.dst_fwd) + static_cast<long long>(row) * K + c0;
+      if ((nc & 1) == 0) {
+        // two channels per thread: 4-byte stores, 64 bytes contiguous per (hw, 32-channel chunk)
+        const int half = nc >> 1;
+        for (int i = threadIdx.x; i < half * HW; i += 256) {
+          const int hw = i / half, cc = (i % half) * 2;
+          *reinterpret_cast<uint32_t*>(d0 + static_cast<long long>(hw) * Cc + cc) = pack_bf16x2(tile[cc][hw], tile[cc + 1][hw]);
+        }
+      } else {
+        for (int i = threadIdx.x; i < cnt; i += 256) {
+          const int hw = i / nc, cc = i % nc;
+          d0[static_cast<long long>(hw) * Cc + cc] = __float2bfloat16(tile[cc][hw]);
+        }
+      }
+      __syncthreads();
     }
   }
   // the block that finishes last advances the step counter (every block read it at its start)

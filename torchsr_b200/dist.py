@@ -60,10 +60,14 @@ def bucket_slices(total: int, early_from: Optional[int], max_elems: int = 32 * 1
     return out
 
 
-def allreduce_flat(flat: torch.Tensor, state: "DataParallelState", early_from: Optional[int] = None):
-    """Averages a flat gradient over the ranks in place: bucketed, every bucket launched asynchronously, one wait."""
-    for lo, hi in bucket_slices(flat.numel(), early_from):
+def allreduce_async_flat(flat: torch.Tensor, state: "DataParallelState"):
+    """Launches the in-place averaging of a flat gradient (slice) over the ranks, bucketed; state.wait() completes it."""
+    for lo, hi in bucket_slices(flat.numel(), None):
         state.allreduce_async(flat[lo:hi])
+
+
+def allreduce_flat(flat: torch.Tensor, state: "DataParallelState"):
+    allreduce_async_flat(flat, state)
     state.wait()
 
 

@@ -608,9 +608,11 @@ class Plan:
         return self.output_fn()
 
     def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None, alias: bool = False,
-                     defer_comm: bool = False):
+                     defer_comm: bool = False, early_cb=None):
         """defer_comm: no all-reduce here and the plan's own flat buffer is returned - the caller sums the gradients of
-        several outstanding calls of the module first (see _PlanFn.backward, 'merge_pending_grads')."""
+        several outstanding calls of the module first (see _PlanFn.backward, 'merge_pending_grads'). early_cb(offset)
+        is called once the tail [offset, total) of the flat gradient is final (the classifier of a discriminator,
+        produced by the first launches of backward), so that the caller can start its exchange early."""
         if not self.training and self.has_bn:
             raise NotImplementedError("torchsr_b200: backward through eval-mode BatchNorm is not implemented; call "
                                       ".train() for gradient computation (the reference trainers do)")
@@ -644,7 +646,12 @@ class Plan:
                     ddp.allreduce_async(flat[lo:hi])
             ddp.wait()
         else:
-            prog.run()
+            if want_w and early is not None and early_cb is not None:
+                prog.run(0, early)
+                early_cb(self.early_from)
+                prog.run(early, -1)
+            else:
+                prog.run()
             if want_w:
                 for fn in self.post_backward:
                     fn()
@@ -798,26 +805,54 @@ class _PlanFn(torch.autograd.Function):
         st = ctx.module._tsr
         ddp = st.get("ddp")
         merge = want_w and st.get("merge_pending_grads", False)
-        gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ddp, st.get("alias_grads", False),
-                                     defer_comm=merge)
-        if merge:
+        if not merge:
+            gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ddp, st.get("alias_grads", False))
+        else:
             # Several calls of the module feed one loss (D(real) and D(fake), trainer.py): every backward but the last
-            # parks its flat gradient; the last one sums them with ONE kernel per parked call, all-reduces the sum once
-            # and returns it (the others return no parameter gradients, which autograd treats as zero).
-            cur = torch.cuda.current_stream(flat.device)
+            # parks its flat gradient; the last one adds the parked ones to its own (one kernel per parked call and
+            # slice), all-reduces the sum once and returns it - the others return no parameter gradients, which
+            # autograd treats as zero. The tail of the flat gradient that is final early (early_cb) is summed and sent
+            # as soon as every call has produced it, so its transfer overlaps the convolutional backward.
+            from .dist import allreduce_async_flat
+            dist_on = ddp is not None and ddp.world > 1
+            cur = torch.cuda.current_stream(gout.device)
             others = st["pending"] - {id(plan)}
+            parked = st.setdefault("parked", [])
+            info = {}
+
+            def early_cb(offset):
+                info["offset"] = offset
+                if others:
+                    info["ev_early"] = torch.cuda.Event()
+                    info["ev_early"].record(cur)
+                elif all(p.get("offset") == offset for p in parked):
+                    mine = plan.grads.flat
+                    for p in parked:
+                        cur.wait_event(p["ev_early"])
+                        mine[offset:].add_(p["flat"][offset:])
+                    if dist_on:
+                        allreduce_async_flat(mine[offset:], ddp)
+                    info["early_done"] = offset
+
+            gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ddp, True, defer_comm=True,
+                                         early_cb=early_cb)
             if others:
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                st.setdefault("parked", []).append((flat, ev))
+                info["flat"] = flat
+                info["ev_done"] = torch.cuda.Event()
+                info["ev_done"].record(cur)
+                parked.append(info)
                 flat = None
             else:
-                for other, ev in st.pop("parked", []):
-                    cur.wait_event(ev)
-                    flat.add_(other)
-                if ddp is not None and ddp.world > 1:
-                    from .dist import allreduce_flat
-                    allreduce_flat(flat, ddp)
+                head = info.get("early_done")      # [head, total) was already summed (and sent)
+                for p in st.pop("parked", []):
+                    cur.wait_event(p["ev_done"])
+                    if head is None:
+                        flat.add_(p["flat"])
+                    else:
+                        flat[:head].add_(p["flat"][:head])
+                if dist_on:
+                    allreduce_async_flat(flat if head is None else flat[:head], ddp)
+                    ddp.wait()
         grads = plan.store.grads_from_flat(flat, want) if (want_w and flat is not None) else [None] * len(want)
         lease.release()
         return (None, None, gx, *grads)

@@ -13,6 +13,9 @@ from . import _lib as L
 from . import engine, ops
 
 
+ADAM_TILES = 4     # kAdamTiles in csrc/eltwise.cu
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or eps < 0.0:
@@ -76,7 +79,7 @@ class FusedAdam(torch.optim.Optimizer):
                 e.mode = L.AD_LINEAR
                 e.cout, e.cin, e.kk = rec.nout, rec.C, rec.Hf * rec.Wf
                 e.dst_fwd = ops.ptr(rec.w_fwd)
-                blocks += rec.nout * ((rec.C + 31) // 32)
+                blocks += rec.nout * (((rec.C + 31) // 32 + ADAM_TILES - 1) // ADAM_TILES)
                 stores.add(store)
             else:
                 e.mode = L.AD_PLAIN
