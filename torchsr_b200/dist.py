@@ -84,13 +84,19 @@ def attach(module, group=None, broadcast_buffers: bool = True) -> DataParallelSt
 
 
 def sync_buffers(module):
-    """DDP's broadcast_buffers=True behaviour: rank 0's buffers win before a training forward."""
+    """DDP's broadcast_buffers=True behaviour: rank 0's buffers win before a training forward. The buffers are
+    coalesced per dtype into one flat tensor (one broadcast per dtype instead of one per buffer), as DDP does."""
     state = module._tsr.get("ddp")
     if state is None or not state.broadcast_buffers or state.world == 1:
         return
     with torch.no_grad():
+        groups = {}
         for b in module.buffers():
-            dist.broadcast(b, src=0, group=state.group)
+            groups.setdefault(b.dtype, []).append(b)
+        for bufs in groups.values():
+            flat = torch.cat([b.reshape(-1) for b in bufs])
+            dist.broadcast(flat, src=0, group=state.group)
+            torch._foreach_copy_(bufs, [c.view(b.shape) for b, c in zip(bufs, flat.split([b.numel() for b in bufs]))])
 
 
 @contextlib.contextmanager
