@@ -180,6 +180,63 @@ def trunk_conv_roofline(batch, pk):
             "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "bound": "tensor"}
 
 
+# algorithmic GFLOP per crop executed by conv_igemm_kernel in one step (forward + data-gradient convs and the Linear
+# GEMMs; weight gradients run in conv_wgrad_kernel): G 2.5553 + 2.5374, D 3 x 1.7683 forward + 1.7365 (real) + 1.7365
+# (fake) + 1.7683 (super-res pass, full data gradient), VGG19 3 x 7.166
+CONV_IGEMM_GFLOP_PER_CROP_GD = 15.639
+CONV_IGEMM_GFLOP_PER_CROP_VGG = 21.50
+
+
+def conv_kernel_roofline(trainer, lr_d, hr_d, batch, pk, vgg_ours):
+    """The dominant kernel (conv_igemm_kernel: ~52 % of the step's launch time in profiles/r01b_ncu_launches_step.csv)
+    over ALL of its launches in one training step: every distinct conv / GEMM descriptor of the programs a step
+    executes is replayed 20x back to back (CUDA events on the launching stream) and weighted by how often the step
+    runs it; achieved = algorithmic FLOPs of those launches / summed launch time."""
+    import torch
+    from torchsr_b200 import _lib as L
+    from torchsr_b200 import ops
+    counts = {}
+    orig = ops.Program.run
+
+    def counting(self, first=0, count=-1, stream=None):
+        if first == 0:
+            counts[id(self)] = (self, counts.get(id(self), (self, 0))[1] + 1)
+        return orig(self, first, count, stream)
+
+    ops.Program.run = counting
+    try:
+        trainer._gan_loop(lr_d, hr_d, 0)
+        torch.cuda.synchronize()
+    finally:
+        ops.Program.run = orig
+    cache, total_us, launches, reps = {}, 0.0, 0, 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for prog, c in counts.values():
+        for d in prog.descs:
+            if not isinstance(d, L.ConvDesc):
+                continue
+            key = bytes(d)
+            if key not in cache:
+                p2 = ops.Program()
+                for _ in range(reps):
+                    p2.add(d)
+                p2.run()
+                p2.run()
+                e0.record()
+                p2.run()
+                p2.run()
+                e1.record()
+                torch.cuda.synchronize()
+                cache[key] = e0.elapsed_time(e1) * 1e3 / (2 * reps)
+            total_us += cache[key] * c
+            launches += c
+    gflop = (CONV_IGEMM_GFLOP_PER_CROP_GD + (CONV_IGEMM_GFLOP_PER_CROP_VGG if vgg_ours else 0.0)) * batch
+    ach = gflop * 1e9 / (total_us * 1e-6) / 1e12
+    return {"kernel": "conv_igemm_kernel, all %d launches of one step (%d distinct descriptors)" % (launches, len(cache)),
+            "us_per_step": total_us, "us_per_launch": total_us / max(launches, 1), "gflop_per_step": gflop,
+            "achieved": ach, "peak": pk["burst"], "unit": "TFLOP/s", "frac": ach / pk["burst"], "bound": "tensor"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -261,6 +318,14 @@ def run_b200(args):
     pk = peaks()
     ach = value * GFLOP_PER_CROP_GD / 1e3 / world     # TFLOP/s per GPU on the G+D algorithmic FLOPs
     kern = trunk_conv_roofline(args.batch, pk)
+    vgg_ours = not args.no_vgg and os.environ.get("TORCHSR_VGG_IMPL", "b200") != "torch"
+    if distributed:
+        dom = {"note": "measured at N=1 only (replaying a step on rank 0 alone would leave its collectives unmatched)"}
+    else:
+        try:
+            dom = conv_kernel_roofline(trainer, lr_d, hr_d, args.batch, pk, vgg_ours)
+        except Exception as exc:  # noqa: BLE001
+            dom = {"error": repr(exc)}
     line = {
         "metric": "SRGAN GAN training crops/sec (96x96 HR)", "value": value, "unit": "crops/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -284,7 +349,9 @@ def run_b200(args):
                      "what": "whole step: crops/s x 21.73 GFLOP/crop (G+D algorithmic minimum, SURVEY 8d) per GPU vs the "
                              f"{pk['source']} sustained bf16 peak; with the VGG19 FLOPs (+21.50/crop) "
                              f"the step sustains {value * (GFLOP_PER_CROP_GD + GFLOP_PER_CROP_VGG) / 1e3 / world:.1f} TFLOP/s",
-                     "dominant_kernel": kern},
+                     "dominant_kernel": dom, "trunk_conv_only": kern,
+                     "ncu": "profiles/r01b_ncu_full_conv_igemm_summary.csv (dram bytes, tensor-pipe activity, L2->SM "
+                            "bytes per launch), profiles/r01b_ncu_launches_step.csv (every launch of one step)"},
     }
     if not args.no_cpu_baseline and world == 1:
         cps, spstep, threads = cpu_port_crops_per_sec(args.batch, 3, 1, not args.no_vgg)
