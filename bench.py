@@ -213,13 +213,19 @@ def conv_kernel_roofline(trainer, lr_d, hr_d, batch, pk, vgg_ours):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for prog, c in counts.values():
         for d in prog.descs:
-            if not isinstance(d, L.ConvDesc):
+            if isinstance(d, ops.ConvGroupDesc):        # four parity-class convs in one launch
+                key = b"".join(bytes(m) for m in d.members)
+            elif isinstance(d, L.ConvDesc):
+                key = bytes(d)
+            else:
                 continue
-            key = bytes(d)
             if key not in cache:
                 p2 = ops.Program()
                 for _ in range(reps):
-                    p2.add(d)
+                    if isinstance(d, ops.ConvGroupDesc):
+                        p2.add_group(d.members)
+                    else:
+                        p2.add(d)
                 p2.run()
                 p2.run()
                 e0.record()

@@ -220,6 +220,9 @@ int tsr_elt(const tsr_elt_desc_t* d, void* stream);
 tsr_prog_t* tsr_prog_create(void);
 void tsr_prog_destroy(tsr_prog_t* p);
 int tsr_prog_add_conv(tsr_prog_t* p, const tsr_conv_desc_t* d);
+/* n (<= 4) independent unsplit im2col convs executed by ONE launch (the output-parity classes of a stride-2 data
+   gradient); counts as one op of the program */
+int tsr_prog_add_conv_group(tsr_prog_t* p, const tsr_conv_desc_t* descs, int n);
 int tsr_prog_add_wgrad(tsr_prog_t* p, const tsr_wgrad_desc_t* d);
 int tsr_prog_add_elt(tsr_prog_t* p, const tsr_elt_desc_t* d);
 int tsr_prog_size(const tsr_prog_t* p);

@@ -207,7 +207,7 @@ def check_dgrad_s1(B=2, H=24, W=24, Cin=64, Cout=64, k=3, seed=4):
     return {"out": rel_l2(out.permute(0, 3, 1, 2), ref)}
 
 
-def check_dgrad_s2(B=2, H=24, W=24, Cin=64, Cout=64, seed=5):
+def check_dgrad_s2(B=2, H=24, W=24, Cin=64, Cout=64, seed=5, grouped=False):
     """Stride-2 3x3 pad-1 conv: dX assembled from 4 output-parity classes (H, W = input dims, even)."""
     g = torch.Generator().manual_seed(seed)
     k, pad = 3, 1
@@ -216,9 +216,22 @@ def check_dgrad_s2(B=2, H=24, W=24, Cin=64, Cout=64, seed=5):
     w = bf16_round(torch.randn(Cout, Cin, k, k, generator=g) / (Cout * k * k) ** 0.5)
     dy_dev, wt_dev = nhwc_bf16(dy), pack_t(w)
     out = torch.full((B, H, W, Cin), float("nan"), device=DEV)
-    for d in ops.dgrad_s2_descs(dy=dy_dev, N=B, Hy=Hy, Wy=Wy, Cout=Cout, dy_ld=Cout, wt=wt_dev, Cin=Cin, cin_pad=Cin,
-                                block_n=min(Cin, 128), out=out, Hx=H, Wx=W, out_ld=Cin, n_valid=Cin, out_f32=True):
-        ops.run_now(d)
+    descs = ops.dgrad_s2_descs(dy=dy_dev, N=B, Hy=Hy, Wy=Wy, Cout=Cout, dy_ld=Cout, wt=wt_dev, Cin=Cin, cin_pad=Cin,
+                               block_n=min(Cin, 128), out=out, Hx=H, Wx=W, out_ld=Cin, n_valid=Cin, out_f32=True)
+    if grouped:
+        # the four parity classes as ONE grouped launch inside a recorded program (twice: plain launch, then the
+        # captured graph of the range)
+        prog = ops.Program()
+        prog.add(ops.elt(L.E_ZERO, p=[out], i=[out.numel() * 4]))
+        prog.add_group(descs)
+        prog.add(ops.elt(L.E_CAST, p=[out, torch.empty(out.numel(), device=DEV, dtype=torch.bfloat16)], i=[out.numel(), 0]))
+        prog.add(ops.elt(L.E_CAST, p=[out, torch.empty(out.numel(), device=DEV, dtype=torch.bfloat16)], i=[out.numel(), 0]))
+        prog.run()
+        prog.run()
+        prog.run()
+    else:
+        for d in descs:
+            ops.run_now(d)
     sync_check()
     ref = F.conv_transpose2d(dy, w, stride=2, padding=pad, output_padding=1)
     return {"out": rel_l2(out.permute(0, 3, 1, 2), ref)}

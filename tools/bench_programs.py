@@ -11,6 +11,7 @@ import torch  # noqa: E402
 
 from torchsr_b200 import _lib as L  # noqa: E402
 from torchsr_b200 import dist as tdist  # noqa: E402
+from torchsr_b200 import ops as ops_mod  # noqa: E402
 from torchsr_b200.srgan.discriminator import Discriminator  # noqa: E402
 from torchsr_b200.srgan.generator import Generator  # noqa: E402
 
@@ -33,7 +34,9 @@ def time_prog(prog, reps=20):
 def describe(prog):
     c = Counter()
     for d in prog.descs:
-        if isinstance(d, L.ConvDesc):
+        if isinstance(d, ops_mod.ConvGroupDesc):
+            c["conv_group"] += 1
+        elif isinstance(d, L.ConvDesc):
             c["conv"] += 1
         elif isinstance(d, L.WgradDesc):
             c["wgrad"] += 1
@@ -69,6 +72,8 @@ def main():
 
 
 def op_name(d):
+    if isinstance(d, ops_mod.ConvGroupDesc):
+        return "group[" + " | ".join(op_name(m) for m in d.members) + "]"
     if isinstance(d, L.ConvDesc):
         if d.a_mode == 0:
             return (f"conv M={d.N * d.Ho * d.Wo} N={d.cout_pad} K={d.num_taps}x{d.C - d.a_c0} bn={d.block_n} s={d.stride} "
@@ -103,7 +108,10 @@ def per_op():
                     if nm not in seen:
                         p2 = ops.Program()
                         for _ in range(40):
-                            p2.add(d)
+                            if isinstance(d, ops_mod.ConvGroupDesc):
+                                p2.add_group(d.members)
+                            else:
+                                p2.add(d)
                         seen[nm] = [time_prog(p2, 5) / 40, 0]
                     seen[nm][1] += 1
                     tot += seen[nm][0]

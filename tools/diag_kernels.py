@@ -63,6 +63,7 @@ CHECKS = [
     ("dgrad_s1_256_128", lambda: K.check_dgrad_s1(Cin=128, Cout=256, H=12, W=12)),
     ("dgrad_s2", lambda: K.check_dgrad_s2()),
     ("dgrad_s2_512", lambda: K.check_dgrad_s2(Cin=512, Cout=512, H=12, W=12)),
+    ("dgrad_s2_grouped", lambda: K.check_dgrad_s2(B=3, H=12, W=20, Cin=128, Cout=64, grouped=True)),
     ("wgrad_64", lambda: K.check_wgrad()),
     ("wgrad_64_b16", lambda: K.check_wgrad(B=16)),
     ("wgrad_odd", lambda: K.check_wgrad(B=3, H=13, W=10)),

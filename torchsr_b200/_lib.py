@@ -91,7 +91,7 @@ class AdamEntry(C.Structure):
 
 EXPORTS = [
     "tsr_init", "tsr_last_error", "tsr_version", "tsr_conv", "tsr_wgrad", "tsr_elt", "tsr_prog_create",
-    "tsr_prog_destroy", "tsr_prog_add_conv", "tsr_prog_add_wgrad", "tsr_prog_add_elt", "tsr_prog_size",
+    "tsr_prog_destroy", "tsr_prog_add_conv", "tsr_prog_add_conv_group", "tsr_prog_add_wgrad", "tsr_prog_add_elt", "tsr_prog_size",
     "tsr_prog_run", "tsr_launch_count", "tsr_check_watchdog",
 ]
 
@@ -122,6 +122,7 @@ def load():
     lib.tsr_elt.argtypes = [C.POINTER(EltDesc), C.c_void_p]
     lib.tsr_prog_add_conv.argtypes = [C.c_void_p, C.POINTER(ConvDesc)]
     lib.tsr_prog_add_wgrad.argtypes = [C.c_void_p, C.POINTER(WgradDesc)]
+    lib.tsr_prog_add_conv_group.argtypes = [C.c_void_p, C.POINTER(ConvDesc), C.c_int]
     lib.tsr_prog_add_elt.argtypes = [C.c_void_p, C.POINTER(EltDesc)]
     lib.tsr_prog_size.argtypes = [C.c_void_p]
     lib.tsr_prog_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]

@@ -18,6 +18,7 @@
 
 namespace tsr {
 cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream, bool pdl);
+cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bool pdl);
 cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int splits, cudaStream_t stream, bool pdl);
 cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl);
 size_t conv_igemm_smem_bytes(const ConvParams& p);
@@ -343,13 +344,19 @@ int build_wgrad(const tsr_wgrad_desc_t& d, WgradLaunch* L) {
 }  // namespace
 
 struct tsr_prog {
-  enum Kind { CONV, WGRAD, ELT };
+  enum Kind { CONV, WGRAD, ELT, CONV_GROUP };
   struct Op {
     Kind kind;
     ConvLaunch conv;
     WgradLaunch wg;
     tsr_elt_desc_t elt;
+    int group = -1;       // CONV_GROUP: index into groups
   };
+  struct Group {
+    tsr::ConvGroup g;
+    int n;
+  };
+  std::vector<Group> groups;
   std::vector<Op> ops;
   // one instantiated CUDA graph per executed [first, last) range: every pointer in a program is fixed, so a range is
   // captured once and replayed with a single cudaGraphLaunch
@@ -465,6 +472,8 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
       }
       if (op.kind == tsr_prog::CONV) {
         ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st, pdl_on && chain);
+      } else if (op.kind == tsr_prog::CONV_GROUP) {
+        ce = tsr::launch_conv_group(p->groups[op.group].g, p->groups[op.group].n, st, pdl_on && chain);
       } else {
         ce = tsr::launch_elt(op.elt, st, pdl_on && chain);
       }
@@ -524,6 +533,25 @@ int tsr_prog_add_conv(tsr_prog_t* p, const tsr_conv_desc_t* d) {
   tsr_prog::Op op;
   op.kind = tsr_prog::CONV;
   if (int e = build_conv(*d, &op.conv)) return e;
+  p->ops.push_back(op);
+  return static_cast<int>(p->ops.size()) - 1;
+}
+int tsr_prog_add_conv_group(tsr_prog_t* p, const tsr_conv_desc_t* descs, int n) {
+  if (n < 1 || n > tsr::kMaxGroup) return fail(-20, "a conv group holds 1..%d members", tsr::kMaxGroup);
+  tsr_prog::Group grp;
+  memset(&grp.g, 0, sizeof(grp.g));
+  grp.n = n;
+  for (int k = 0; k < n; ++k) {
+    ConvLaunch L;
+    if (int e = build_conv(descs[k], &L)) return e;
+    if (L.p.a_mode != 0 || L.splits != 1) return fail(-20, "conv group members must be unsplit im2col convs");
+    grp.g.p[k] = L.p;
+    grp.g.tiles_n[k] = L.tiles_n;
+  }
+  p->groups.push_back(grp);
+  tsr_prog::Op op;
+  op.kind = tsr_prog::CONV_GROUP;
+  op.group = static_cast<int>(p->groups.size()) - 1;
   p->ops.push_back(op);
   return static_cast<int>(p->ops.size()) - 1;
 }

@@ -242,8 +242,9 @@ __device__ __forceinline__ void mma_loop(const ConvParams& p, uint32_t bar_full,
   if (trace && (threadIdx.x & 31) == 0) trace[4] = clock64();
 }
 
+// One CTA = one output tile (tile_m, tile_n) of conv `p`, K range = split `zsplit` of `nsplits`.
 template <int A_MODE>
-__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+__device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit, const int nsplits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -261,11 +262,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
   float* scratch = reinterpret_cast<float*>(smem_gen + kScratchOff);
   const uint32_t tiles = smem_base + kHeaderBytes;
 
-  long long* trace = p.epi.trace ? p.epi.trace + 40ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
+  long long* trace = p.epi.trace ? p.epi.trace + 40ll * ((zsplit * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
                                  : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = clock64();
   const int total_iters = p.num_taps * p.kc_per_tap;
-  const int it_begin = blockIdx.z * p.iters_per_split;
+  const int it_begin = zsplit * p.iters_per_split;
   const int it_end = min(total_iters, it_begin + p.iters_per_split);
 
   if (warp == 0 && lane == 0) {
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
     tc_fence_after();
     if (trace && threadIdx.x == 64) trace[5] = clock64();
     // ---- split-K: reduce the partial tiles through the fp32 workspace, the last CTA of the tile finalizes
-    const bool split_ws = gridDim.z > 1 && out_mode != OUT_GEMM_T_ATOMIC;
+    const bool split_ws = nsplits > 1 && out_mode != OUT_GEMM_T_ATOMIC;
     bool finalize = ok;
     if (split_ws) {
       float* wrow = e.ws + static_cast<long long>(m) * e.ws_ld + colbase;
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
         __threadfence();
         int* cnt = e.tile_counters + blockIdx.y * gridDim.x + blockIdx.x;
         const int old = atomicAdd(cnt, 1);
-        const int last = old == static_cast<int>(gridDim.z) - 1;
+        const int last = old == nsplits - 1;
         if (last) *cnt = 0;
         __threadfence();
         *flag = last;
@@ -582,6 +583,19 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
   if (trace && threadIdx.x == 0) trace[7] = clock64();
 }
 
+template <int A_MODE>
+__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  conv_body<A_MODE>(p, blockIdx.z, gridDim.z);
+}
+
+// Up to four independent im2col convs of the same tile grid in ONE launch (blockIdx.z selects the member): the four
+// output-parity classes of a stride-2 data gradient, which would otherwise be four latency-bound launches in a row.
+__global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_group_kernel(const __grid_constant__ ConvGroup g) {
+  const ConvParams& p = g.p[blockIdx.z];
+  if (static_cast<int>(blockIdx.x) * kBlockM >= p.M_total || static_cast<int>(blockIdx.y) >= g.tiles_n[blockIdx.z]) return;
+  conv_body<0>(p, 0, 1);
+}
+
 size_t conv_igemm_smem_bytes(const ConvParams& p) {
   return 1024 + kHeaderBytes + static_cast<size_t>(p.stages) * p.stage_bytes;
 }
@@ -596,6 +610,24 @@ static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cuda
     attr_set = true;
   }
   cudaError_t e = launch_k(conv_igemm_kernel<A_MODE>, grid, dim3(kConvThreads), smem, stream, pdl, p);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bool pdl) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int tiles_m = 0, tiles_n = 0;
+  size_t smem = 0;
+  for (int k = 0; k < n; ++k) {
+    tiles_m = max(tiles_m, (g.p[k].M_total + kBlockM - 1) / kBlockM);
+    tiles_n = max(tiles_n, g.tiles_n[k]);
+    smem = max(smem, conv_igemm_smem_bytes(g.p[k]));
+  }
+  cudaError_t e = launch_k(conv_igemm_group_kernel, dim3(tiles_m, tiles_n, n), dim3(kConvThreads), smem, stream, pdl, g);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -92,6 +92,12 @@ struct ConvParams {
   uint16_t tap_wrow[kMaxTaps];  // tap slot in the packed weight matrix
 };
 
+constexpr int kMaxGroup = 4;
+struct ConvGroup {
+  ConvParams p[kMaxGroup];
+  int tiles_n[kMaxGroup];
+};
+
 // Weight-gradient kernel:  dW[co][tap][ci] += sum_p X[pixel(p) + tap, ci] * dY[p, co]
 // computed as D[(block, ci), co] with the "M blocks" enumerating (tap, ci_block) pairs.
 struct WgradParams {

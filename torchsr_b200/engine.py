@@ -464,8 +464,10 @@ class Plan:
                                                          alpha if prelu else None, sums, dacc):
                 fused = 1
             if held is not None:
-                for d in held:
-                    prog.add(d)
+                if len(held) > 1:
+                    prog.add_group(held)
+                else:
+                    prog.add(held[0])
             if not fused:
                 prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[gp, xp, coef, alpha if prelu else None, sums, dacc, g2p],
                                  i=[M, C, act, rpb, g.ld, x.ld, has_bn], f=[leaky, gscale]))
@@ -568,10 +570,9 @@ class Plan:
                                        Cin=n_out, cin_pad=n_out, block_n=block_n, out=target.t, Hx=x_like.H,
                                        Wx=x_like.W, out_ld=target.ld, n_valid=n_out)
             if deferrable and target.c0 == 0:
-                prog.defer(descs, target)
+                prog.defer(descs, target, group=True)     # one launch for the four parity classes
             else:
-                for d in descs:
-                    prog.add(d)
+                prog.add_group(descs)
         return target
 
     def colsum(self, prog, name: str, g: Act, out_vec: torch.Tensor):

@@ -393,6 +393,16 @@ def validate(d):
 
 
 # --------------------------------------------------------------------------------------------- programs
+GROUP_LAUNCH = os.environ.get("TSR_GROUP_LAUNCH", "1") != "0"
+
+
+class ConvGroupDesc:
+    """Introspection record of a grouped launch (Program.descs): the member descriptors."""
+
+    def __init__(self, members: List):
+        self.members = list(members)
+
+
 class Program:
     """A recorded launch list owned by the native library (tsr_prog_t)."""
 
@@ -419,9 +429,31 @@ class Program:
     # norm_act_bwd). Any other emission, run(), mark() or len() flushes the held descriptors unchanged.
     _deferred = None
 
-    def defer(self, descs: List, tag):
+    def defer(self, descs: List, tag, group: bool = False):
+        """group: the held descriptors are independent convs of one tile grid (stride-2 data-gradient parity classes)
+        and are emitted as ONE grouped launch."""
         self.flush()
         self._deferred = (list(descs), tag)
+        self._deferred_group = group
+
+    def add_group(self, descs: List) -> int:
+        """Up to four unsplit im2col convs in one launch (tsr_prog_add_conv_group)."""
+        self.flush()
+        for d in descs:
+            validate(d)
+        if len(descs) == 1 or not GROUP_LAUNCH:
+            r = -1
+            for d in descs:
+                r = self.add(d)
+            return r
+        self.descs.append(ConvGroupDesc(descs))
+        if DRY:
+            return len(self.descs) - 1
+        arr = (ConvDesc * len(descs))(*descs)
+        r = self._lib.tsr_prog_add_conv_group(self._h, arr, len(descs))
+        if r < 0:
+            L.check(r)
+        return r
 
     def take_deferred(self, tag):
         """Returns and removes the held descriptors if they were deferred under `tag` (identity), else None."""
@@ -434,8 +466,11 @@ class Program:
     def flush(self):
         if self._deferred is not None:
             descs, self._deferred = self._deferred[0], None
-            for d in descs:
-                self.add(d)
+            if getattr(self, "_deferred_group", False) and len(descs) > 1:
+                self.add_group(descs)
+            else:
+                for d in descs:
+                    self.add(d)
 
     def add(self, d) -> int:
         self.flush()
