@@ -124,7 +124,8 @@ typedef struct tsr_wgrad_desc {
 /* Generic descriptor of the elementwise / reduction kernels; meaning of p/i/f per kind in csrc/eltwise.cu. */
 typedef struct tsr_elt_desc {
   int32_t kind;
-  int32_t _pad;
+  int32_t side;    /* 1: inside a program this op only feeds gradient outputs - run it on the weight-gradient side
+                      branch (consecutive side ops share one branch and keep their order) */
   void* p[12];
   int64_t i[16];
   float f[8];

@@ -63,7 +63,7 @@ class WgradDesc(C.Structure):
 
 
 class EltDesc(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("p", C.c_void_p * 12), ("i", C.c_int64 * 16),
+    _fields_ = [("kind", C.c_int32), ("side", C.c_int32), ("p", C.c_void_p * 12), ("i", C.c_int64 * 16),
                 ("f", C.c_float * 8)]
 
 

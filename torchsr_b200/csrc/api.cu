@@ -450,18 +450,31 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
     }
     return cudaSuccess;
   };
+  bool prev_side_elt = false;   // consecutive side ELT ops stay on one branch, in order
   for (int i = first; i < last; ++i) {
     const tsr_prog::Op& op = p->ops[i];
     cudaError_t ce;
-    if (op.kind == tsr_prog::WGRAD && side) {
-      const int k = next_side;
-      next_side = (next_side + 1) % kSideStreams;
-      ce = cudaEventRecord(sb->fork, st);
-      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sb->s[k], sb->fork, 0);
+    const bool side_elt = side && op.kind == tsr_prog::ELT && op.elt.side != 0;
+    if ((op.kind == tsr_prog::WGRAD && side) || side_elt) {
+      int k = next_side;
+      if (side_elt && prev_side_elt) {
+        k = (next_side + kSideStreams - 1) % kSideStreams;   // same branch as the previous side op
+        ce = cudaSuccess;
+      } else {
+        next_side = (next_side + 1) % kSideStreams;
+        ce = cudaEventRecord(sb->fork, st);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sb->s[k], sb->fork, 0);
+      }
       if (ce == cudaSuccess)
-        ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, sb->s[k], false);
+        ce = side_elt ? tsr::launch_elt(op.elt, sb->s[k], false)
+                      : tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, sb->s[k], false);
       used[k] = true;
-    } else if (op.kind == tsr_prog::WGRAD) {
+      prev_side_elt = side_elt;
+      if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
+      continue;
+    }
+    prev_side_elt = false;
+    if (op.kind == tsr_prog::WGRAD) {
       ce = tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, st, pdl_on && chain);
       chain = true;
     } else {

@@ -75,6 +75,50 @@ __global__ void im2row_kernel(const float* __restrict__ x, bf16* __restrict__ E,
   }
 }
 
+// Fast path for the 3-channel 3x3 first layers of the discriminators and VGG: one thread per pixel gathers its 27 taps
+// once and writes the whole 64-byte row; the generic kernel above spends most of its time on per-element index
+// arithmetic.
+template <int KH, int KW, int C>
+__global__ void __launch_bounds__(256) im2row_small_kernel(const float* __restrict__ x, bf16* __restrict__ E, int B, int H,
+                                                           int W, int ph, int pw, int sign) {
+  static_assert(KH * KW * C <= 32, "row must fit 32 columns");
+  pdl_sync();
+  const long long total = static_cast<long long>(B) * H * W;
+  const long long hw = static_cast<long long>(H) * W;
+  for (long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; pix < total;
+       pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const long long n = pix / hw;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    // fully unrolled: all KH*KW*C loads are independent and in flight together
+#pragma unroll
+    for (int kh = 0; kh < KH; ++kh) {
+      const int hh = h + sign * (kh - ph);
+#pragma unroll
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ww = w + sign * (kw - pw);
+        const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          v[(kh * KW + kw) * C + c] = in ? __ldg(x + (n * C + c) * hw + static_cast<long long>(hh) * W + ww) : 0.f;
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(E + pix * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * q], v[8 * q + 1]);
+      o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+      o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+      o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      dst[q] = o;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- GATHER_OUT
 // p0 = T ([B,H,W,Tld] fp32 or bf16), p1 = out fp32 NCHW [B,C,H,W], p2 = bias fp32[C] or null
 // i: 0 B, 1 C, 2 H, 3 W, 4 KH, 5 KW, 6 ph, 7 pw, 8 sign, 9 Tld, 10 T_is_bf16
@@ -1123,6 +1167,16 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
   void* const* p = d.p;
   switch (d.kind) {
     case TSR_E_IM2ROW:
+      if (i[9] == 32 && i[1] == 3 && i[4] == 3 && i[5] == 3) {      // 3-channel 3x3 first layers (D, VGG)
+        ce = launch_k(im2row_small_kernel<3, 3, 3>, dim3(grid_for(i[0] * i[2] * i[3])), dim3(256), 0, st, pdl,
+                      (const float*)p[0], (bf16*)p[1], i[0], i[2], i[3], i[6], i[7], i[8]);
+        break;
+      }
+      if (i[9] == 32 && i[1] == 3 && i[4] == 1 && i[5] == 9) {      // row expansion of dOut for the 9x9 Cout=3 conv
+        ce = launch_k(im2row_small_kernel<1, 9, 3>, dim3(grid_for(i[0] * i[2] * i[3])), dim3(256), 0, st, pdl,
+                      (const float*)p[0], (bf16*)p[1], i[0], i[2], i[3], i[6], i[7], i[8]);
+        break;
+      }
       ce = launch_k(im2row_kernel, dim3(grid_for(i[0] * i[2] * i[3] * (i[9] / 8))), dim3(256), 0, st, pdl, 
           (const float*)p[0], (bf16*)p[1], i[0], i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8], i[9]);
       break;

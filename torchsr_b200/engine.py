@@ -835,8 +835,10 @@ class _PlanFn(torch.autograd.Function):
                         allreduce_async_flat(mine[offset:], ddp)
                     info["early_done"] = offset
 
+            # single GPU: nothing to send early - the whole backward runs as one range (the classifier's weight
+            # gradient then overlaps the convolutional backward on the side branch)
             gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ddp, True, defer_comm=True,
-                                         early_cb=early_cb)
+                                         early_cb=early_cb if dist_on else None)
             if others:
                 info["flat"] = flat
                 info["ev_done"] = torch.cuda.Event()

@@ -322,9 +322,11 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
                        i=[B, N1, int(sigmoid), l1.nout_pad], f=[0.2]))
         if want_w:
             xchw = plan.buf("flat_chw", B * K, F32)     # features in the parameter's (c,h,w) column order
-            bp.add(ops.elt(L.E_NHWC2NCHW, p=[flat_act.t, xchw], i=[B, l1.C, l1.Hf, l1.Wf, flat_act.ld, flat_act.c0, 0]))
+            # both only feed gradient outputs: they run on the weight-gradient side branch (joined at the range end)
+            bp.add(ops.elt(L.E_NHWC2NCHW, p=[flat_act.t, xchw], i=[B, l1.C, l1.Hf, l1.Wf, flat_act.ld, flat_act.c0, 0],
+                           side=True))
             bp.add(ops.elt(L.E_LINEAR_WGRAD, p=[dpre1, xchw, store.grad_slice(l1.weight), store.grad_slice(l1.bias)],
-                           i=[B, N1, K]))
+                           i=[B, N1, K], side=True))
             bp.mark("early_grads")     # everything from classifier.0.weight to the end of the flat gradient is final
             plan.early_from = plan.store.offsets[id(l1.weight)]
         dflat32 = plan.buf("dflat32", Bpad * K, F32)

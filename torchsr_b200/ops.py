@@ -219,9 +219,10 @@ def wgrad_desc(*, x, N, H, W, C, x_ld, geom, dy, dy_ld, dy_c, out, cout_valid, b
     return d
 
 
-def elt(kind: int, p: Iterable = (), i: Iterable = (), f: Iterable = ()) -> EltDesc:
+def elt(kind: int, p: Iterable = (), i: Iterable = (), f: Iterable = (), side: bool = False) -> EltDesc:
     d = EltDesc()
     d.kind = kind
+    d.side = int(side)
     for k, v in enumerate(p):
         d.p[k] = ptr(v)
     for k, v in enumerate(i):
