@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 pytestmark = pytest.mark.gpu
 
 BF16_OUT = {"y", "y_eval", "dx", "dpre1_bf", "nhwc", "nchw", "E"}     # result keys stored in bf16 by the kernel
-BF16_CHECKS = {"conv3x3_bf16out", "conv3x3_splitk_odd"}
+BF16_CHECKS = {"conv3x3_bf16out", "conv3x3_splitk_odd", "conv3x3_persistent_n256"}
 
 
 def _checks():

@@ -56,6 +56,12 @@ CHECKS = [
                                                 stats=True, repeat=2)),
     ("conv3x3_splitk_odd", lambda: K.check_conv_fwd(B=3, H=13, W=10, Cin=128, Cout=64, splits=4, residual=True,
                                                     out_f32=False, repeat=2)),
+    # persistent weight-stationary mode (>= 2 M tiles per CTA): resident weights, two accumulator stages
+    ("conv3x3_persistent", lambda: K.check_conv_fwd(B=18, H=48, W=48, bias=True, act=L.ACT_PRELU, stats=True)),
+    ("conv3x3_persistent_n256", lambda: K.check_conv_fwd(B=4, H=72, W=72, Cout=256, block_n=128, bias=True, shuffle=True,
+                                                         out_f32=False)),
+    ("conv3x3_persistent_odd", lambda: K.check_conv_fwd(B=21, H=45, W=43, Cin=32, Cout=32, residual=True)),
+    ("conv3x3_persistent_s2", lambda: K.check_conv_fwd(B=20, H=96, W=96, stride=2, stats=True)),
     ("conv3x3_s2", lambda: K.check_conv_fwd(stride=2)),
     ("conv3x3_s2_128", lambda: K.check_conv_fwd(Cin=128, Cout=128, H=12, W=12, stride=2, stats=True)),
     ("conv9x9_64", lambda: K.check_conv_fwd(k=9, Cout=32, H=12, W=12)),

@@ -17,6 +17,9 @@ NVCC_FLAGS = [
 ]
 
 
+NVCC_FLAGS += [f for f in os.environ.get("TSR_NVCC_EXTRA", "").split() if f]
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

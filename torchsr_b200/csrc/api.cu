@@ -131,7 +131,16 @@ struct WgradLaunch {
   int gsets, tiles_n, splits;
 };
 
-int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
+int g_use_persistent = -1;
+bool use_persistent() {
+  if (g_use_persistent < 0) {
+    const char* e = getenv("TSR_CONV_PERSISTENT");
+    g_use_persistent = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_use_persistent == 1;
+}
+
+int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = true) {
   using namespace tsr;
   if (int e = ensure_init()) return e;
   ConvParams& p = L->p;
@@ -192,12 +201,36 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L) {
   splits = (total_iters + p.iters_per_split - 1) / p.iters_per_split;
   L->splits = splits;
   L->tiles_n = d.cout_pad / d.block_n;
-  p.tmem_cols = pow2_cols(d.block_n);
-  const uint32_t stage_bytes = ((kBlockM * d.block_k * 2 + d.block_n * d.block_k * 2) + 1023u) & ~1023u;
+  p.acc_cols = pow2_cols(d.block_n);
+  p.tmem_cols = p.acc_cols;
+  uint32_t stage_bytes = ((kBlockM * d.block_k * 2 + d.block_n * d.block_k * 2) + 1023u) & ~1023u;
   int stages = 6;
   while (stages > 2 && static_cast<size_t>(stages) * stage_bytes > 96 * 1024) --stages;
   if (static_cast<size_t>(stages) * stage_bytes > 200 * 1024) return fail(-22, "tile does not fit shared memory");
   if (stages > p.iters_per_split) stages = p.iters_per_split < 1 ? 1 : p.iters_per_split;
+  // Persistent weight-stationary mode: many M tiles per CTA, the weights of the N tile resident in shared memory
+  // (they are re-fetched by every CTA otherwise: half of the L2->SM traffic of the large-M layers), two accumulator
+  // stages. Chosen when the resident weights fit and every CTA gets at least two tiles.
+  p.persistent = 0;
+  p.b_res_bytes = 0;
+  {
+    const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
+    const int n_ctas = L->tiles_n > 0 ? (148 / L->tiles_n > 0 ? 148 / L->tiles_n : 1) : 148;
+    const uint32_t a_bytes = kBlockM * d.block_k * 2, b_bytes = static_cast<uint32_t>(d.block_n) * d.block_k * 2;
+    const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
+    const size_t budget = 227 * 1024 - 1024 - 13312 - 1024;
+    if (use_persistent() && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && allow_persistent &&
+        b_res % 1024 == 0 && a_bytes % 1024 == 0 && b_res + 3 * static_cast<size_t>(a_bytes) <= budget &&
+        tiles_m >= 2 * n_ctas && 2 * p.acc_cols <= 512) {
+      int st = static_cast<int>((budget - b_res) / a_bytes);
+      if (st > 8) st = 8;
+      p.persistent = n_ctas;
+      p.b_res_bytes = static_cast<uint32_t>(b_res);
+      p.tmem_cols = 2 * p.acc_cols;
+      stage_bytes = a_bytes;
+      stages = st;
+    }
+  }
   p.stages = stages;
   p.a_bytes = kBlockM * d.block_k * 2;
   p.b_bytes = static_cast<uint32_t>(d.block_n) * d.block_k * 2;
@@ -556,7 +589,7 @@ int tsr_prog_add_conv_group(tsr_prog_t* p, const tsr_conv_desc_t* descs, int n) 
   grp.n = n;
   for (int k = 0; k < n; ++k) {
     ConvLaunch L;
-    if (int e = build_conv(descs[k], &L)) return e;
+    if (int e = build_conv(descs[k], &L, false)) return e;
     if (L.p.a_mode != 0 || L.splits != 1) return fail(-20, "conv group members must be unsplit im2col convs");
     grp.g.p[k] = L.p;
     grp.g.tiles_n[k] = L.tiles_n;

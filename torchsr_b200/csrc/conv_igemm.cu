@@ -95,155 +95,210 @@ __device__ __forceinline__ void store_f32x16(void* base, long long off, const fl
 
 }  // namespace
 
+// Shared-memory barrier block (offsets from the 1024-aligned base): full[8] @0, empty[8] @64, acc_full[2] @128,
+// acc_empty[2] @144, b_full @160, TMEM slot @168, split-K flag @172.
+//
+// Persistent mode (p.persistent): gridDim.x CTAs walk the M tiles (tile_m = blockIdx.x, += gridDim.x). The whole weight
+// operand of the CTA's N tile (num_taps * kc_per_tap K-chunks) is fetched ONCE into a resident region and only the
+// activation tiles stream through the ring; two TMEM accumulator stages let the epilogue of tile j overlap the main
+// loop of tile j+1. In the non-persistent mode gridDim.x == tiles_m, every CTA runs exactly one tile and both
+// operands stream through the ring (weights of the first ring pass are fetched before the PDL wait when w_static).
+
 // Warp 0 (all lanes run the loop so that every value stays warp-uniform; one elected lane issues): keeps the smem
-// ring full. All per-iteration state is carried incrementally (no divisions).
-template <int A_MODE>
-__device__ __forceinline__ void producer_loop(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t tiles,
-                                              int m0, int tile_n, int it_begin, int it_end, long long* trace) {
-  int w0 = 0, h0 = 0, n0 = 0;
-  if (A_MODE == 0) {
-    const int hw = p.Ho * p.Wo;
-    n0 = m0 / hw;
-    const int rem = m0 - n0 * hw;
-    const int ho = rem / p.Wo;
-    const int wo = rem - ho * p.Wo;
-    h0 = ho * p.stride + p.lower_h;
-    w0 = wo * p.stride + p.lower_w;
-  }
+// ring full. All per-iteration state is carried incrementally (no divisions inside the K loop).
+template <int A_MODE, bool PERS>
+__device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_b,
+                                              uint32_t b_res, uint32_t ring, int tile_n, int it_begin, int it_end,
+                                              int tiles_m, long long* trace) {
+  constexpr bool pers = PERS;
   const int stages = p.stages;
-  const uint32_t stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, tx = p.a_bytes + p.b_bytes;
+  const uint32_t stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+  const uint32_t tx = pers ? a_bytes : a_bytes + b_bytes;
   const int kc_per_tap = p.kc_per_tap, block_k = p.block_k;
   const int b_row0 = tile_n * p.block_n;
-  int tap = 0, kc = it_begin;
-  if (A_MODE == 0) {
-    tap = it_begin / kc_per_tap;
-    kc = it_begin - tap * kc_per_tap;
-  }
-  // Weight tiles of the first ring pass do not depend on the previous kernel of the stream (w_static): arm the
-  // barriers and fetch them before the programmatic-launch wait, so only the activation loads follow it.
-  const int pre = p.w_static ? min(stages, it_end - it_begin) : 0;
-  if (elect_one()) {
-    uint32_t d = tiles + a_bytes;
-    for (int j = 0; j < pre; ++j) {
-      const int it = it_begin + j;
-      int ktap = 0, kkc = it;
-      if (A_MODE == 0) {
-        ktap = it / kc_per_tap;
-        kkc = it - ktap * kc_per_tap;
+  int pre = 0;
+  auto load_resident_b = [&]() {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bar_b, static_cast<uint32_t>(it_end - it_begin) * b_bytes);
+      uint32_t d = b_res;
+      int ktap = 0, kkc = 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        const int brow = (A_MODE == 0 ? p.tap_wrow[ktap] * p.b_rows_per_tap : 0) + b_row0;
+        tma_load_2d(d, &p.tmB, bar_b, kkc * block_k, brow);
+        d += b_bytes;
+        if (++kkc == kc_per_tap && A_MODE == 0) {
+          kkc = 0;
+          ++ktap;
+        }
       }
-      const int brow = (A_MODE == 0 ? p.tap_wrow[ktap] * p.b_rows_per_tap : 0) + b_row0;
-      mbar_arrive_expect_tx(bar_full + 8 * j, tx);
-      tma_load_2d(d, &p.tmB, bar_full + 8 * j, kkc * block_k, brow);
-      d += stage_bytes;
-    }
-  }
-  __syncwarp();
-  pdl_sync();
-  int s = 0;
-  uint32_t ph = 1;  // parity to wait for on the empty barrier (first pass over the ring passes immediately)
-  uint32_t dst = tiles;
-  for (int it = it_begin; it < it_end; ++it) {
-    if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) break;
-    const uint32_t full = bar_full + 8 * s;
-    const bool fresh = it - it_begin >= pre;   // barrier not armed / weights not fetched yet
-    if (A_MODE == 0) {
-      const uint32_t off = p.tap_off[tap];
-      const int brow = p.tap_wrow[tap] * p.b_rows_per_tap + b_row0;
-      if (elect_one()) {
-        if (fresh) mbar_arrive_expect_tx(full, tx);
-        tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
-        if (fresh) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, brow);
-      }
-      if (++kc == kc_per_tap) {
-        kc = 0;
-        ++tap;
-      }
-    } else if (A_MODE == 1) {
-      if (elect_one()) {
-        if (fresh) mbar_arrive_expect_tx(full, tx);
-        tma_load_2d(dst, &p.tmA, full, kc * block_k, m0);
-        if (fresh) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
-      }
-      ++kc;
-    } else {
-      // MN-major A: two [block_k rows (K)] x [64 M-elements] boxes
-      if (elect_one()) {
-        if (fresh) mbar_arrive_expect_tx(full, tx);
-        tma_load_2d(dst, &p.tmA, full, m0, kc * block_k);
-        tma_load_2d(dst + block_k * 128, &p.tmA, full, m0 + 64, kc * block_k);
-        if (fresh) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
-      }
-      ++kc;
     }
     __syncwarp();
-    if (trace && it - it_begin < 16 && (threadIdx.x & 31) == 0) trace[8 + it - it_begin] = clock64();
-    dst += stage_bytes;
-    if (++s == stages) {
-      s = 0;
-      ph ^= 1;
-      dst = tiles;
+  };
+  if (pers) {
+    if (p.w_static) load_resident_b();
+  } else {
+    // Weight tiles of the first ring pass do not depend on the previous kernel of the stream (w_static): arm the
+    // barriers and fetch them before the programmatic-launch wait, so only the activation loads follow it.
+    pre = p.w_static ? min(stages, it_end - it_begin) : 0;
+    if (elect_one()) {
+      uint32_t d = ring + a_bytes;
+      for (int j = 0; j < pre; ++j) {
+        const int it = it_begin + j;
+        int ktap = 0, kkc = it;
+        if (A_MODE == 0) {
+          ktap = it / kc_per_tap;
+          kkc = it - ktap * kc_per_tap;
+        }
+        const int brow = (A_MODE == 0 ? p.tap_wrow[ktap] * p.b_rows_per_tap : 0) + b_row0;
+        mbar_arrive_expect_tx(bar_full + 8 * j, tx);
+        tma_load_2d(d, &p.tmB, bar_full + 8 * j, kkc * block_k, brow);
+        d += stage_bytes;
+      }
     }
+    __syncwarp();
+  }
+  pdl_sync();
+  if (pers && !p.w_static) load_resident_b();
+  int s = 0;
+  uint32_t ph = 1;  // parity to wait for on the empty barrier (first pass over the ring passes immediately)
+  uint32_t dst = ring;
+  bool first_tile = true;
+  for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x) {
+    const int m0 = tile_m * kBlockM;
+    int w0 = 0, h0 = 0, n0 = 0;
+    if (A_MODE == 0) {
+      const int hw = p.Ho * p.Wo;
+      n0 = m0 / hw;
+      const int rem = m0 - n0 * hw;
+      const int ho = rem / p.Wo;
+      const int wo = rem - ho * p.Wo;
+      h0 = ho * p.stride + p.lower_h;
+      w0 = wo * p.stride + p.lower_w;
+    }
+    int tap = 0, kc = it_begin;
+    if (A_MODE == 0) {
+      tap = it_begin / kc_per_tap;
+      kc = it_begin - tap * kc_per_tap;
+    }
+    for (int it = it_begin; it < it_end; ++it) {
+      if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
+      const uint32_t full = bar_full + 8 * s;
+      // arm the barrier unless the pre-issue above already did; weights go through the ring only when not resident
+      const bool arm = !(first_tile && it - it_begin < pre);
+      const bool load_b = arm && !pers;
+      if (A_MODE == 0) {
+        const uint32_t off = p.tap_off[tap];
+        const int brow = p.tap_wrow[tap] * p.b_rows_per_tap + b_row0;
+        if (elect_one()) {
+          if (arm) mbar_arrive_expect_tx(full, tx);
+          tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
+          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, brow);
+        }
+        if (++kc == kc_per_tap) {
+          kc = 0;
+          ++tap;
+        }
+      } else if (A_MODE == 1) {
+        if (elect_one()) {
+          if (arm) mbar_arrive_expect_tx(full, tx);
+          tma_load_2d(dst, &p.tmA, full, kc * block_k, m0);
+          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+        }
+        ++kc;
+      } else {
+        // MN-major A: two [block_k rows (K)] x [64 M-elements] boxes
+        if (elect_one()) {
+          if (arm) mbar_arrive_expect_tx(full, tx);
+          tma_load_2d(dst, &p.tmA, full, m0, kc * block_k);
+          tma_load_2d(dst + block_k * 128, &p.tmA, full, m0 + 64, kc * block_k);
+          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+        }
+        ++kc;
+      }
+      __syncwarp();
+      if (trace && first_tile && it - it_begin < 16 && (threadIdx.x & 31) == 0) trace[8 + it - it_begin] = clock64();
+      dst += stage_bytes;
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+        dst = ring;
+      }
+    }
+    first_tile = false;
+    if (!PERS) break;     // one tile per CTA: lets the compiler drop the loop-carried state
   }
 }
 
 // Warp 1 (all lanes loop, one elected lane issues): the UMMAs of every stage, slot recycling with tcgen05.commit.
-template <int A_MODE>
-__device__ __forceinline__ void mma_loop(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_tmem,
-                                         uint32_t tiles, uint32_t tmem_base, int n_iters, long long* trace) {
+template <int A_MODE, bool PERS>
+__device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_acc_full,
+                                         uint32_t bar_acc_empty, uint32_t bar_b, uint32_t b_res, uint32_t ring,
+                                         uint32_t tmem_base, int n_iters, int tiles_m, long long* trace) {
+  constexpr bool pers = PERS;
   const int stages = p.stages;
   const uint32_t ksteps = p.ksteps, idesc = p.idesc;
-  const uint32_t stage16 = p.stage_bytes >> 4, a16 = p.a_bytes >> 4;
+  const uint32_t stage16 = p.stage_bytes >> 4, a16 = p.a_bytes >> 4, b16 = p.b_bytes >> 4;
   // descriptor high words are loop invariant; the low word's start-address field advances in 16-byte units
   uint64_t a0, b0;
   uint32_t a_kadv;
   if (A_MODE == 2) {
-    a0 = make_smem_desc(tiles, p.block_k * 128, 1024, 2);
+    a0 = make_smem_desc(ring, p.block_k * 128, 1024, 2);
     a_kadv = 2048 >> 4;
   } else {
-    a0 = make_smem_desc(tiles, 16, p.sbo_bytes, p.layout_type);
+    a0 = make_smem_desc(ring, 16, p.sbo_bytes, p.layout_type);
     a_kadv = 32 >> 4;
   }
-  b0 = make_smem_desc(tiles, 16, p.sbo_bytes, p.layout_type);
+  b0 = make_smem_desc(pers ? b_res : ring, 16, p.sbo_bytes, p.layout_type);
   const uint32_t a_hi = static_cast<uint32_t>(a0 >> 32), b_hi = static_cast<uint32_t>(b0 >> 32);
-  const uint32_t a_lo0 = static_cast<uint32_t>(a0), b_lo0 = static_cast<uint32_t>(b0) + a16;
-  int s = 0;
-  uint32_t ph = 0, soff = 0, acc = 0;
-  bool ok = true;
-  for (int it = 0; it < n_iters; ++it) {
-    if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) {
-      ok = false;
-      break;
-    }
+  const uint32_t a_lo0 = static_cast<uint32_t>(a0), b_lo0 = static_cast<uint32_t>(b0) + (pers ? 0u : a16);
+  if (pers) {
+    if (!mbar_wait(bar_b, 0, p.epi.err, 4)) return;
     tc_fence_after();
-    if (trace && it < 16 && (threadIdx.x & 31) == 0) trace[24 + it] = clock64();
-    if (elect_one()) {
-      uint32_t a_lo = a_lo0 + soff, b_lo = b_lo0 + soff;
-      uint32_t acc_k = acc;
-      for (uint32_t k = 0; k < ksteps; ++k) {
-        umma_bf16(tmem_base, (static_cast<uint64_t>(a_hi) << 32) | a_lo, (static_cast<uint64_t>(b_hi) << 32) | b_lo,
-                  idesc, acc_k);
-        acc_k = 1;
-        a_lo += a_kadv;
-        b_lo += 2;
-      }
-      umma_commit(bar_empty + 8 * s);
-    }
-    __syncwarp();
-    acc = 1;
-    soff += stage16;
-    if (++s == stages) {
-      s = 0;
-      ph ^= 1;
-      soff = 0;
-    }
   }
-  if (ok && elect_one()) umma_commit(bar_tmem);
-  __syncwarp();
-  if (trace && (threadIdx.x & 31) == 0) trace[4] = clock64();
+  int s = 0, j = 0;
+  uint32_t ph = 0, soff = 0;
+  for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++j) {
+    const int as = j & 1;
+    // the epilogue must have drained this accumulator stage (first use of a stage passes immediately)
+    if (!mbar_wait(bar_acc_empty + 8 * as, ((j >> 1) & 1) ^ 1, p.epi.err, 5)) return;
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * p.acc_cols;
+    uint32_t acc = 0, boff = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) return;
+      tc_fence_after();
+      if (trace && j == 0 && it < 16 && (threadIdx.x & 31) == 0) trace[24 + it] = clock64();
+      if (elect_one()) {
+        uint32_t a_lo = a_lo0 + soff, b_lo = b_lo0 + (pers ? boff : soff);
+        uint32_t acc_k = acc;
+        for (uint32_t k = 0; k < ksteps; ++k) {
+          umma_bf16(d_tmem, (static_cast<uint64_t>(a_hi) << 32) | a_lo, (static_cast<uint64_t>(b_hi) << 32) | b_lo,
+                    idesc, acc_k);
+          acc_k = 1;
+          a_lo += a_kadv;
+          b_lo += 2;
+        }
+        umma_commit(bar_empty + 8 * s);
+      }
+      __syncwarp();
+      acc = 1;
+      boff += b16;
+      soff += stage16;
+      if (++s == stages) {
+        s = 0;
+        ph ^= 1;
+        soff = 0;
+      }
+    }
+    if (elect_one()) umma_commit(bar_acc_full + 8 * as);
+    __syncwarp();
+    if (trace && j == 0 && (threadIdx.x & 31) == 0) trace[4] = clock64();
+    if (!PERS) break;
+  }
 }
 
 // One CTA = one output tile (tile_m, tile_n) of conv `p`, K range = split `zsplit` of `nsplits`.
-template <int A_MODE>
+template <int A_MODE, bool PERS>
 __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit, const int nsplits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -251,16 +306,19 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x;
   const int tile_n = blockIdx.y;
 
   const uint32_t bar_full = smem_base;                 // 8 x u64
   const uint32_t bar_empty = smem_base + 64;           // 8 x u64
-  const uint32_t bar_tmem = smem_base + 128;           // u64
-  const uint32_t tmem_slot = smem_base + 136;          // u32
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 136);
+  const uint32_t bar_acc_full = smem_base + 128;       // 2 x u64
+  const uint32_t bar_acc_empty = smem_base + 144;      // 2 x u64
+  const uint32_t bar_b = smem_base + 160;              // u64 (resident weights)
+  const uint32_t tmem_slot = smem_base + 168;          // u32
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 168);
   float* scratch = reinterpret_cast<float*>(smem_gen + kScratchOff);
-  const uint32_t tiles = smem_base + kHeaderBytes;
+  const uint32_t b_res = smem_base + kHeaderBytes;     // resident weights (persistent mode) ...
+  const uint32_t ring = b_res + p.b_res_bytes;         // ... then the operand ring
+  const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
 
   long long* trace = p.epi.trace ? p.epi.trace + 40ll * ((zsplit * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
                                  : nullptr;
@@ -277,7 +335,11 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_tmem, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_acc_full + 8 * a, 1);
+      mbar_init(bar_acc_empty + 8 * a, kConvThreads / 32 - 2);   // one arrival per epilogue warp
+    }
+    mbar_init(bar_b, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -290,13 +352,12 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
   const uint32_t tmem_base = *tmem_slot_gen;
   if (trace && threadIdx.x == 0) trace[1] = clock64();
 
-  const int m0 = tile_m * kBlockM;
-
   if (warp == 0) {
-    producer_loop<A_MODE>(p, bar_full, bar_empty, tiles, m0, tile_n, it_begin, it_end, trace);   // calls pdl_sync()
+    producer_role<A_MODE, PERS>(p, bar_full, bar_empty, bar_b, b_res, ring, tile_n, it_begin, it_end, tiles_m, trace);  // pdl_sync() inside
   } else if (warp == 1) {
     pdl_sync();
-    mma_loop<A_MODE>(p, bar_full, bar_empty, bar_tmem, tiles, tmem_base, it_end - it_begin, trace);
+    mma_role<A_MODE, PERS>(p, bar_full, bar_empty, bar_acc_full, bar_acc_empty, bar_b, b_res, ring, tmem_base,
+                     it_end - it_begin, tiles_m, trace);
   } else {
     pdl_sync();   // the epilogue reads residuals / statistics buffers written by earlier kernels of the stream
     // ------------------------------------------------------------------ epilogue (warps 2..9)
@@ -304,6 +365,43 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
     const EpiParams& e = p.epi;
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    const int out_mode = e.out_mode, act = e.act, bwd_act = e.bwd_act, n_valid = e.n_valid, shuf_c = e.shuf_c;
+    const float acc_scale = e.acc_scale, leaky = e.leaky_slope;
+    const float* bias = e.bias;
+    const void* bwd_z = e.bwd_z;
+    const void* res = e.res;
+    void* out = e.out;
+    void* out_preact = e.out_preact;
+    const bool want_stats = e.stats_partial != nullptr;
+    const bool out_f32 = e.out_f32 != 0;
+    const float alpha = (e.prelu != nullptr) ? __ldg(e.prelu) : 0.f;
+    const float bslope = (bwd_act == ACT_PRELU) ? alpha : (bwd_act == ACT_LEAKY ? leaky : 0.f);
+    const void* bnr_x = e.bnr_x;
+    const int bnr_act = e.bnr_act;
+    const float bnr_slope = (bnr_act == ACT_PRELU) ? __ldg(e.bnr_prelu) : (bnr_act == ACT_LEAKY ? leaky : 0.f);
+    const int chunks = p.block_n >> 4;
+    const int ch_begin = half ? (chunks + 1) >> 1 : 0;
+    const int ch_end = half ? chunks : (chunks + 1) >> 1;
+    const int colbase = tile_n * p.block_n;
+    // per-column vectors of this CTA's N tile -> shared memory, once (the chunk loop reads them as broadcasts)
+    float* s_bias = reinterpret_cast<float*>(smem_gen + kColVecOff);
+    float* s_sc = s_bias + 256;
+    float* s_sh = s_sc + 256;
+    {
+      const int et = threadIdx.x - 64;
+      if (et < p.block_n) {
+        const int c = colbase + et;
+        s_bias[et] = bias != nullptr ? __ldg(bias + c) : 0.f;
+        const bool hc = bnr_x != nullptr && e.bnr_coef != nullptr && c < e.bnr_c;
+        s_sc[et] = hc ? __ldg(e.bnr_coef + c) : 1.f;
+        s_sh[et] = hc ? __ldg(e.bnr_coef + e.bnr_c + c) : 0.f;
+      }
+      named_bar_sync(1, kConvThreads - 64);
+    }
+    int j = 0;
+    for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++j) {
+    const int m0 = tile_m * kBlockM;
+    const int as = j & 1;          // accumulator stage of this tile
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const bool valid = m < p.M_total;
@@ -326,26 +424,8 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       out_base = static_cast<long long>(m) * e.os_w + e.out_ch_off;
       aux_base = static_cast<long long>(m) * e.aux_w + e.aux_ch_off;
     }
-    const int out_mode = e.out_mode, act = e.act, bwd_act = e.bwd_act, n_valid = e.n_valid, shuf_c = e.shuf_c;
-    const float acc_scale = e.acc_scale, leaky = e.leaky_slope;
-    const float* bias = e.bias;
-    const void* bwd_z = e.bwd_z;
-    const void* res = e.res;
-    void* out = e.out;
-    void* out_preact = e.out_preact;
-    const bool want_stats = e.stats_partial != nullptr;
-    const bool out_f32 = e.out_f32 != 0;
-    const float alpha = (e.prelu != nullptr) ? __ldg(e.prelu) : 0.f;
-    const float bslope = (bwd_act == ACT_PRELU) ? alpha : (bwd_act == ACT_LEAKY ? leaky : 0.f);
-    const void* bnr_x = e.bnr_x;
-    const int bnr_act = e.bnr_act;
-    const float bnr_slope = (bnr_act == ACT_PRELU) ? __ldg(e.bnr_prelu) : (bnr_act == ACT_LEAKY ? leaky : 0.f);
     float dalpha = 0.f;
-    const int chunks = p.block_n >> 4;
-    const int ch_begin = half ? (chunks + 1) >> 1 : 0;
-    const int ch_end = half ? chunks : (chunks + 1) >> 1;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int colbase = tile_n * p.block_n;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * p.acc_cols;
     // The auxiliary operands of the epilogue (residuals, activation-backward tensor, raw BatchNorm input) do not
     // depend on the accumulator: pull this thread's rows into L1 while the main loop runs, so that the dependent
     // global loads of the chunk loop below hit L1 instead of paying an L2 / HBM round trip per chunk.
@@ -356,28 +436,13 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       for (int a = 0; a < 4; ++a) {
         if (aux_ptrs[a] == nullptr) continue;
         if (a < 2 && c_lo >= e.res_cols) continue;
-        const char* row = reinterpret_cast<const char*>(aux_ptrs[a]) + (aux_base + c_lo) * 2;
-        for (int b = 0; b < (c_hi - c_lo) * 2; b += 64) prefetch_l1(row + b);
+        const char* rowp = reinterpret_cast<const char*>(aux_ptrs[a]) + (aux_base + c_lo) * 2;
+        for (int b = 0; b < (c_hi - c_lo) * 2; b += 64) prefetch_l1(rowp + b);
       }
     }
-    // per-column vectors of this CTA's tile -> shared memory, once (the chunk loop reads them as broadcasts)
-    float* s_bias = reinterpret_cast<float*>(smem_gen + kColVecOff);
-    float* s_sc = s_bias + 256;
-    float* s_sh = s_sc + 256;
-    {
-      const int et = threadIdx.x - 64;
-      if (et < p.block_n) {
-        const int c = colbase + et;
-        s_bias[et] = bias != nullptr ? __ldg(bias + c) : 0.f;
-        const bool hc = bnr_x != nullptr && e.bnr_coef != nullptr && c < e.bnr_c;
-        s_sc[et] = hc ? __ldg(e.bnr_coef + c) : 1.f;
-        s_sh[et] = hc ? __ldg(e.bnr_coef + e.bnr_c + c) : 0.f;
-      }
-      named_bar_sync(1, kConvThreads - 64);
-    }
-    const bool ok = mbar_wait(bar_tmem, 0, e.err, 3);
+    const bool ok = mbar_wait(bar_acc_full + 8 * as, (j >> 1) & 1, e.err, 3);
     tc_fence_after();
-    if (trace && threadIdx.x == 64) trace[5] = clock64();
+    if (trace && j == 0 && threadIdx.x == 64) trace[5] = clock64();
     // ---- split-K: reduce the partial tiles through the fp32 workspace, the last CTA of the tile finalizes
     const bool split_ws = nsplits > 1 && out_mode != OUT_GEMM_T_ATOMIC;
     bool finalize = ok;
@@ -399,10 +464,10 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       }
       // release: the CTA's reductions are ordered before the counter bump by the barrier + one cumulative fence
       named_bar_sync(1, kConvThreads - 64);
-      int* flag = reinterpret_cast<int*>(smem_gen + 144);
+      int* flag = reinterpret_cast<int*>(smem_gen + 172);
       if (threadIdx.x == 64) {
         __threadfence();
-        int* cnt = e.tile_counters + blockIdx.y * gridDim.x + blockIdx.x;
+        int* cnt = e.tile_counters + blockIdx.y * tiles_m + tile_m;
         const int old = atomicAdd(cnt, 1);
         const int last = old == nsplits - 1;
         if (last) *cnt = 0;
@@ -546,7 +611,11 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         if (trace && threadIdx.x == 64 && ch < 4) trace[33 + 2 * ch] = clock64();
       }
     }
-    // cross-warp reductions of the epilogue side products -> one red.global.add per column / per CTA
+    // every tcgen05.ld of this tile has completed (tmem_ld_wait above): hand the accumulator stage back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+    // cross-warp reductions of the epilogue side products -> one red.global.add per column / per tile
     if (want_stats || e.dalpha_partial != nullptr) {
       if (e.dalpha_partial != nullptr) {
 #pragma unroll
@@ -570,8 +639,12 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         for (int w = 0; w < 8; ++w) tot += scratch[4 * 256 * 2 + w];
         atomicAdd(e.dalpha_partial, tot);
       }
+      // the scratch slots are reused by the next tile of a persistent CTA
+      if (tile_m + static_cast<int>(gridDim.x) < tiles_m) named_bar_sync(1, kConvThreads - 64);
     }
-    if (trace && threadIdx.x == 64) trace[6] = clock64();
+    if (trace && j == 0 && threadIdx.x == 64) trace[6] = clock64();
+    if (!PERS) break;
+    }  // tile loop
   }
 
   tc_fence_before();
@@ -585,7 +658,12 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
 
 template <int A_MODE>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  conv_body<A_MODE>(p, blockIdx.z, gridDim.z);
+  conv_body<A_MODE, false>(p, blockIdx.z, gridDim.z);
+}
+
+// Persistent weight-stationary variant (im2col convs only): see the comment above producer_role.
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_persistent_kernel(const __grid_constant__ ConvParams p) {
+  conv_body<0, true>(p, 0, 1);
 }
 
 // Up to four independent im2col convs of the same tile grid in ONE launch (blockIdx.z selects the member): the four
@@ -593,11 +671,11 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __gri
 __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_group_kernel(const __grid_constant__ ConvGroup g) {
   const ConvParams& p = g.p[blockIdx.z];
   if (static_cast<int>(blockIdx.x) * kBlockM >= p.M_total || static_cast<int>(blockIdx.y) >= g.tiles_n[blockIdx.z]) return;
-  conv_body<0>(p, 0, 1);
+  conv_body<0, false>(p, 0, 1);
 }
 
 size_t conv_igemm_smem_bytes(const ConvParams& p) {
-  return 1024 + kHeaderBytes + static_cast<size_t>(p.stages) * p.stage_bytes;
+  return 1024 + kHeaderBytes + p.b_res_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
 }
 
 template <int A_MODE>
@@ -633,8 +711,19 @@ cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bo
 
 cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream, bool pdl) {
   const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
-  dim3 grid(tiles_m, tiles_n, splits);
+  dim3 grid(p.persistent ? min(tiles_m, p.persistent) : tiles_m, tiles_n, splits);
   const size_t smem = conv_igemm_smem_bytes(p);
+  if (p.persistent) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e =
+          cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    cudaError_t e = launch_k(conv_igemm_persistent_kernel, grid, dim3(kConvThreads), smem, stream, pdl, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   if (p.a_mode == 0) return launch_mode<0>(p, grid, smem, stream, pdl);
   if (p.a_mode == 1) return launch_mode<1>(p, grid, smem, stream, pdl);
   return launch_mode<2>(p, grid, smem, stream, pdl);

@@ -81,6 +81,10 @@ struct ConvParams {
   int iters_per_split;  // K iterations handled per blockIdx.z
   int stages;
   int tmem_cols;
+  int persistent;  // 0: one CTA per output tile; > 0: that many CTAs (per N tile) walk the M tiles with the weights
+                   // of their N tile resident in shared memory (see conv_igemm.cu)
+  uint32_t b_res_bytes;  // bytes of the resident weight region (0 when not persistent)
+  uint32_t acc_cols;     // TMEM columns per accumulator stage
   int w_static;    // the B operand is not written by any kernel of the enclosing stream segment (real weights)
   // derived on the host so that the single-thread producer / MMA loops stay short
   uint32_t a_bytes, b_bytes, stage_bytes;

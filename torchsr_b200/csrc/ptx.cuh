@@ -170,8 +170,13 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() {
+#ifdef TSR_PDL_EARLY
+  pdl_trigger();   // experiment: lets the successor be staged before this kernel's own dependency has resolved
+  pdl_wait();
+#else
   pdl_wait();
   pdl_trigger();
+#endif
 }
 
 // Pulls the 128-byte line holding `p` into L1 (no register destination, no ordering): used by the epilogue warps to
