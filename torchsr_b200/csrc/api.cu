@@ -140,6 +140,17 @@ bool use_persistent() {
   return g_use_persistent == 1;
 }
 
+// persistent mode needs at least this many M tiles per CTA (x10); TSR_PERSIST_MIN_TILES_X10 overrides
+int persistent_min_tiles_x10() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TSR_PERSIST_MIN_TILES_X10");
+    v = e ? atoi(e) : 20;
+    if (v < 10) v = 10;
+  }
+  return v;
+}
+
 int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = true) {
   using namespace tsr;
   if (int e = ensure_init()) return e;
@@ -221,7 +232,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
     const size_t budget = 227 * 1024 - 1024 - 13312 - 1024;
     if (use_persistent() && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && allow_persistent &&
         b_res % 1024 == 0 && a_bytes % 1024 == 0 && b_res + 3 * static_cast<size_t>(a_bytes) <= budget &&
-        tiles_m >= 2 * n_ctas && 2 * p.acc_cols <= 512) {
+        10 * tiles_m >= persistent_min_tiles_x10() * n_ctas && 2 * p.acc_cols <= 512) {
       int st = static_cast<int>((budget - b_res) / a_bytes);
       if (st > 8) st = 8;
       p.persistent = n_ctas;
