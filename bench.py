@@ -188,7 +188,7 @@ CONV_IGEMM_GFLOP_PER_CROP_VGG = 21.50
 
 
 def conv_kernel_roofline(trainer, lr_d, hr_d, batch, pk, vgg_ours):
-    """The dominant kernel (conv_igemm_kernel: ~52 % of the step's launch time in profiles/r01b_ncu_launches_step.csv)
+    """The dominant kernel (conv_igemm_kernel: ~49 % of the step's launch time with its persistent / grouped variants, profiles/r01c_ncu_launches_step.csv)
     over ALL of its launches in one training step: every distinct conv / GEMM descriptor of the programs a step
     executes is replayed 20x back to back (CUDA events on the launching stream) and weighted by how often the step
     runs it; achieved = algorithmic FLOPs of those launches / summed launch time."""
@@ -356,8 +356,9 @@ def run_b200(args):
                              f"{pk['source']} sustained bf16 peak; with the VGG19 FLOPs (+21.50/crop) "
                              f"the step sustains {value * (GFLOP_PER_CROP_GD + GFLOP_PER_CROP_VGG) / 1e3 / world:.1f} TFLOP/s",
                      "dominant_kernel": dom, "trunk_conv_only": kern,
-                     "ncu": "profiles/r01b_ncu_full_conv_igemm_summary.csv (dram bytes, tensor-pipe activity, L2->SM "
-                            "bytes per launch), profiles/r01b_ncu_launches_step.csv (every launch of one step)"},
+                     "ncu": "profiles/r01c_ncu_full_conv_igemm_summary.csv, r01c_ncu_full_conv_persistent_summary.csv (dram "
+                            "bytes, tensor-pipe activity, L2->SM bytes per launch), r01c_ncu_launches_step.csv (every "
+                            "launch of one step)"},
     }
     if not args.no_cpu_baseline and world == 1:
         cps, spstep, threads = cpu_port_crops_per_sec(args.batch, 3, 1, not args.no_vgg)
