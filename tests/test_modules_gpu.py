@@ -304,3 +304,29 @@ def test_fused_adam_matches_torch_adam_and_keeps_packs_fresh():
         A.eval(), H.eval()
         with torch.no_grad():
             assert MC.rel_l2(A(x), H(x)) <= 1e-6
+
+
+def test_esrgan_trainer_steps_eager_and_graph():
+    """ESRGANTrainer (relativistic GAN step, torchsr/esrgan/trainer.py:418-484) end to end on the B200 path: pretrain
+    step, eager GAN steps and the same step replayed as a CUDA graph - finite losses, both networks updated, and the
+    replayed step continues the eager trajectory (same loss scale)."""
+    import os
+    from argparse import Namespace
+    os.environ["TORCHSR_VGG_WEIGHTS"] = "random"
+    from torchsr_b200.esrgan.trainer import ESRGANTrainer
+    torch.manual_seed(21)
+    args = Namespace(disable_amp=False, batch_size=2, epochs=8, pretrain_epochs=1, gan_checkpoint=None,
+                     psnr_checkpoint=None, skip_image_save=True, local_rank=0, rank=-1, world_size=1)
+    tr = ESRGANTrainer(torch.device("cuda"), args, [], [], 0, 0, False)
+    lr, hr = torch.rand(2, 3, 32, 32, device="cuda"), torch.rand(2, 3, 128, 128, device="cuda")
+    g0 = {k: v.detach().clone() for k, v in tr.generator.state_dict().items()}
+    d0 = {k: v.detach().clone() for k, v in tr.discriminator.state_dict().items()}
+    l_pre = float(tr._pretrain_step(lr, hr))
+    losses = [float(tr._gan_loop(lr, hr, s)) for s in range(2)]
+    losses += [float(tr.graph_step(lr, hr, s)) for s in range(3)]
+    torch.cuda.synchronize()
+    assert all(l == l and abs(l) < 1e3 for l in [l_pre] + losses), (l_pre, losses)
+    assert max(losses) <= 3 * min(losses) + 1e-3, losses
+    moved_g = sum(int(not torch.equal(v, g0[k])) for k, v in tr.generator.state_dict().items())
+    moved_d = sum(int(not torch.equal(v, d0[k])) for k, v in tr.discriminator.state_dict().items() if "num_batches" not in k)
+    assert moved_g >= len(g0) - 2 and moved_d >= len(d0) // 2, (moved_g, len(g0), moved_d, len(d0))

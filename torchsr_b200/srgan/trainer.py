@@ -203,10 +203,11 @@ class SRGANTrainer:
 
     # ------------------------------------------------------------------ whole-step CUDA graph
     def graph_step(self, low_res: Tensor, high_res: Tensor, step: int = 0, kind: str = 'gan') -> Tensor:
-        """`_gan_loop` (kind='gan') or `_pretrain_step` (kind='psnr') replayed as ONE CUDA graph: the first call for a
-        batch shape warms up eagerly, captures the whole step (module launch lists, losses, backward, Adam) and every
-        later call copies the batch into static input buffers and replays. Results are identical to the eager step; the
-        returned loss tensor is a static buffer that the next call overwrites."""
+        """`_gan_loop` (kind='gan') or `_pretrain_step` (kind='psnr') replayed as ONE CUDA graph. The first call for a
+        batch shape runs the step eagerly (that IS the step for this batch: builds plans, launch lists and optimizer
+        tables, sizes the plan pools) and then records the same step into a graph without executing it; every later
+        call copies the batch into static input buffers and replays. Results are identical to the eager step; from
+        the second call on the returned loss tensor is a static buffer that the next call overwrites."""
         key = (kind, tuple(low_res.shape), tuple(high_res.shape))
         g = self._graphs.get(key) if hasattr(self, '_graphs') else None
         if g is None:
@@ -217,18 +218,13 @@ class SRGANTrainer:
             s_hr = torch.empty(high_res.shape, dtype=torch.float32, device=self.device)
             s_lr.copy_(low_res, non_blocking=True)
             s_hr.copy_(high_res, non_blocking=True)
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                for _ in range(3):          # warm-up: builds plans, captures the per-module launch lists, sizes pools
-                    fn(s_lr, s_hr)
-            torch.cuda.current_stream(self.device).wait_stream(side)
+            first_loss = fn(s_lr, s_hr).clone()
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=self._capture_stream):     # high-priority capture stream (chain A)
+            with torch.cuda.graph(graph, stream=self._capture_stream):     # capture only: nothing executes here
                 loss = fn(s_lr, s_hr)
-            g = self._graphs[key] = (graph, s_lr, s_hr, loss)
-            return loss
+            self._graphs[key] = (graph, s_lr, s_hr, loss)
+            return first_loss
         graph, s_lr, s_hr, loss = g
         s_lr.copy_(low_res, non_blocking=True)
         s_hr.copy_(high_res, non_blocking=True)
