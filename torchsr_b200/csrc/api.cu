@@ -140,6 +140,14 @@ bool use_persistent() {
   return g_use_persistent == 1;
 }
 
+// Halo mode is correct (parity-tested) but off by default: with the main loop this cheap the large-M convs turn out to
+// be bound by their epilogue (tcgen05.ld + scattered 32-byte stores per tile), so it does not pay yet
+// (profiles/r01c_halo_mode.md). TSR_CONV_HALO=1 enables it; read at descriptor-build time so tests can switch it.
+bool use_halo() {
+  const char* e = getenv("TSR_CONV_HALO");
+  return e && e[0] == '1' && use_persistent();
+}
+
 // persistent mode needs at least this many M tiles per CTA (x10); TSR_PERSIST_MIN_TILES_X10 overrides
 int persistent_min_tiles_x10() {
   static int v = -1;
@@ -242,6 +250,61 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
       stages = st;
     }
   }
+  // Halo mode on top of the persistent kernel (see conv_params.h): 3x3 / stride 1 / "same" convs on 64-channel chunks.
+  p.halo = 0;
+  if (use_halo() && allow_persistent && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC &&
+      d.stride == 1 && d.num_taps == 9 && d.lower_h == -1 && d.lower_w == -1 && d.Ho == d.H && d.Wo == d.W &&
+      d.block_k == 64 && (d.C - d.a_c0) % 64 == 0 && d.W >= 16 && d.W + 2 <= 128 && 2 * p.acc_cols <= 512) {
+    bool taps_ok = true;
+    for (int t = 0; t < 9; ++t) taps_ok = taps_ok && (d.tap_off[t] >> 8) <= 2 && (d.tap_off[t] & 0xFF) <= 2;
+    const int pw = static_cast<int>(d.W) + 2;
+    int th = 128 / pw;
+    if (th > d.H) th = static_cast<int>(d.H);
+    const uint32_t b_bytes = static_cast<uint32_t>(d.block_n) * 64 * 2;
+    const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
+    const uint32_t patch_tx = static_cast<uint32_t>((th + 2) * pw * 128);
+    const uint32_t patch_alloc = (static_cast<uint32_t>((128 + 2 * pw + 2) * 128) + 1023u) & ~1023u;
+    const size_t budget = 227 * 1024 - 1024 - 13312 - 1024;
+    if (taps_ok && th >= 1 && b_res % 1024 == 0 && b_res + 2 * static_cast<size_t>(patch_alloc) <= budget) {
+      const int tiles_per_img = static_cast<int>((d.H + th - 1) / th);
+      const int tiles = tiles_per_img * static_cast<int>(d.N);
+      const int n_ctas = 148 / L->tiles_n > 0 ? 148 / L->tiles_n : 1;
+      int st = static_cast<int>((budget - b_res) / patch_alloc);
+      if (st > 4) st = 4;
+      // the tiled map replaces the im2col map: box {64 channels, W+2 positions, th+2 rows, 1 image}
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.C), static_cast<cuuint64_t>(d.W), static_cast<cuuint64_t>(d.H),
+                            static_cast<cuuint64_t>(d.N)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.x_ld) * 2, static_cast<cuuint64_t>(d.x_ld) * 2 * d.W,
+                               static_cast<cuuint64_t>(d.x_ld) * 2 * d.W * d.H};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pw), static_cast<cuuint32_t>(th + 2), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = g_encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.x), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(-12, "cuTensorMapEncodeTiled (halo patch) failed (%d)", (int)r);
+      p.halo = 1;
+      p.halo_th = th;
+      p.halo_pw = pw;
+      p.halo_tiles_per_img = tiles_per_img;
+      p.halo_H = static_cast<int>(d.H);
+      p.halo_W = static_cast<int>(d.W);
+      p.persistent = tiles < n_ctas ? tiles : n_ctas;
+      p.b_res_bytes = static_cast<uint32_t>(b_res);
+      p.tmem_cols = 2 * p.acc_cols;
+      stage_bytes = patch_alloc;
+      stages = st;
+      p.stages = stages;
+      p.a_bytes = patch_tx;
+      p.b_bytes = b_bytes;
+      p.stage_bytes = stage_bytes;
+      p.ksteps = 4;
+      p.sbo_bytes = 8 * 64 * 2;
+      p.layout_type = 2u;
+      p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(d.block_n >> 3) << 17) |
+                (static_cast<uint32_t>(kBlockM >> 4) << 24);
+      goto epilogue_params;
+    }
+  }
   p.stages = stages;
   p.a_bytes = kBlockM * d.block_k * 2;
   p.b_bytes = static_cast<uint32_t>(d.block_n) * d.block_k * 2;
@@ -251,6 +314,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   p.layout_type = d.block_k == 64 ? 2u : (d.block_k == 32 ? 4u : 6u);
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((d.a_mode == 2 ? 1u : 0u) << 15) |
             (static_cast<uint32_t>(d.block_n >> 3) << 17) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
+epilogue_params:
   EpiParams& e = p.epi;
   e.out = d.out;
   e.out_preact = d.out_preact;

@@ -164,6 +164,27 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
   uint32_t dst = ring;
   bool first_tile = true;
   for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x) {
+    if (PERS && p.halo) {
+      // one tiled load per 64-channel chunk: the (halo_th + 2) x halo_pw input patch of this tile, origin (-1, -1)
+      const int n_img = tile_m / p.halo_tiles_per_img;
+      const int hrow0 = (tile_m - n_img * p.halo_tiles_per_img) * p.halo_th - 1;
+      for (int kc = 0; kc < kc_per_tap; ++kc) {
+        if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
+        const uint32_t full = bar_full + 8 * s;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full, p.a_bytes);
+          tma_load_tile_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, -1, hrow0, n_img);
+        }
+        __syncwarp();
+        dst += stage_bytes;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+          dst = ring;
+        }
+      }
+      continue;
+    }
     const int m0 = tile_m * kBlockM;
     int w0 = 0, h0 = 0, n0 = 0;
     if (A_MODE == 0) {
@@ -264,6 +285,45 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * p.acc_cols;
     uint32_t acc = 0, boff = 0;
+    if (PERS && p.halo) {
+      // per 64-channel chunk (one ring stage = one patch): nine taps = nine operand windows into the same patch
+      const int kc_per_tap = p.kc_per_tap;
+      for (int kc = 0; kc < kc_per_tap; ++kc) {
+        if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) return;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t stage_addr = ring + static_cast<uint32_t>(s) * p.stage_bytes;
+          for (int t = 0; t < p.num_taps; ++t) {
+            const uint32_t off = p.tap_off[t];
+            const uint32_t a_addr = stage_addr + ((off >> 8) * p.halo_pw + (off & 0xFF)) * 128u;
+            // The window starts (a_addr / 128) % 8 rows into a 1024-byte swizzle atom. The tensor core derives the
+            // 128B-swizzle phase from the absolute shared-memory address (as TMA did when it wrote the patch), so the
+            // descriptor only needs the shifted start address; its base-offset field stays 0 (measured: setting it
+            // to (addr >> 7) & 7 gives wrong results).
+            uint32_t a_lo = (a_lo0 & ~0x3FFFu) | ((a_addr >> 4) & 0x3FFFu);
+            const uint32_t a_hi_t = a_hi;
+            uint32_t b_lo = b_lo0 + static_cast<uint32_t>(t * kc_per_tap + kc) * b16;
+            for (uint32_t k = 0; k < ksteps; ++k) {
+              umma_bf16(d_tmem, (static_cast<uint64_t>(a_hi_t) << 32) | a_lo, (static_cast<uint64_t>(b_hi) << 32) | b_lo,
+                        idesc, acc);
+              acc = 1;
+              a_lo += a_kadv;
+              b_lo += 2;
+            }
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        __syncwarp();
+        acc = 1;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit(bar_acc_full + 8 * as);
+      __syncwarp();
+      continue;
+    }
     for (int it = 0; it < n_iters; ++it) {
       if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) return;
       tc_fence_after();
@@ -318,7 +378,8 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
   float* scratch = reinterpret_cast<float*>(smem_gen + kScratchOff);
   const uint32_t b_res = smem_base + kHeaderBytes;     // resident weights (persistent mode) ...
   const uint32_t ring = b_res + p.b_res_bytes;         // ... then the operand ring
-  const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
+  const int tiles_m = (PERS && p.halo) ? p.halo_tiles_per_img * (p.M_total / (p.halo_H * p.halo_W))
+                                       : (p.M_total + kBlockM - 1) / kBlockM;
 
   long long* trace = p.epi.trace ? p.epi.trace + 40ll * ((zsplit * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
                                  : nullptr;
@@ -403,16 +464,26 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
     const int m0 = tile_m * kBlockM;
     const int as = j & 1;          // accumulator stage of this tile
     const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool valid = m < p.M_total;
+    int m = m0 + row;
+    bool valid = m < p.M_total;
     int n = 0, ho = 0, wo = 0;
     long long out_base, aux_base;
     if (A_MODE == 0) {
-      const int hw = p.Ho * p.Wo;
-      n = m / hw;
-      const int rem = m - n * hw;
-      ho = rem / p.Wo;
-      wo = rem - ho * p.Wo;
+      if (PERS && p.halo) {
+        // accumulator row -> (output row of the tile, position incl. the two discarded halo positions)
+        n = tile_m / p.halo_tiles_per_img;
+        const int orow = row / p.halo_pw;
+        wo = row - orow * p.halo_pw;
+        ho = (tile_m - n * p.halo_tiles_per_img) * p.halo_th + orow;
+        valid = wo < p.halo_W && orow < p.halo_th && ho < p.halo_H;
+        m = (n * p.halo_H + ho) * p.halo_W + wo;
+      } else {
+        const int hw = p.Ho * p.Wo;
+        n = m / hw;
+        const int rem = m - n * hw;
+        ho = rem / p.Wo;
+        wo = rem - ho * p.Wo;
+      }
       out_base = n * e.os_n + ho * e.os_h + wo * e.os_w + e.out_ch_off;
       if (e.out_mode == OUT_UNSHUFFLE)
         out_base = n * e.os_n + (ho >> 1) * e.os_h + (wo >> 1) * e.os_w + ((ho & 1) * 2 + (wo & 1)) * e.shuf_c +
@@ -711,7 +782,7 @@ cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bo
 
 cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream, bool pdl) {
   const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
-  dim3 grid(p.persistent ? min(tiles_m, p.persistent) : tiles_m, tiles_n, splits);
+  dim3 grid(p.persistent ? (p.halo ? p.persistent : min(tiles_m, p.persistent)) : tiles_m, tiles_n, splits);
   const size_t smem = conv_igemm_smem_bytes(p);
   if (p.persistent) {
     static bool attr_set = false;

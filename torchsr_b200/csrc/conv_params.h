@@ -85,6 +85,15 @@ struct ConvParams {
                    // of their N tile resident in shared memory (see conv_igemm.cu)
   uint32_t b_res_bytes;  // bytes of the resident weight region (0 when not persistent)
   uint32_t acc_cols;     // TMEM columns per accumulator stage
+  // Halo mode (persistent kernel only; 3x3 stride-1 "same" convs): an M tile is halo_th output rows x halo_pw = W+2
+  // positions of ONE image; per 64-channel chunk ONE tiled TMA load fetches the (halo_th+2) x halo_pw input patch
+  // (zero-filled outside the image) and the nine taps are nine UMMA operands that start (dy*halo_pw + dx) rows into
+  // that patch - instead of nine im2col loads of 128 separate 128-byte rows each. Outputs at the two halo positions of
+  // every row are computed and discarded. tmA then holds the tiled map.
+  int halo;              // 0 / 1
+  int halo_th, halo_pw;  // output rows per tile, positions per row
+  int halo_tiles_per_img;
+  int halo_H, halo_W;    // image size (output == input size)
   int w_static;    // the B operand is not written by any kernel of the enclosing stream segment (real weights)
   // derived on the host so that the single-thread producer / MMA loops stay short
   uint32_t a_bytes, b_bytes, stage_bytes;

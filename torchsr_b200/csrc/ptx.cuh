@@ -69,6 +69,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint3
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Tiled 4-D load on an NHWC tensor map {C, W, H, N}: the whole box starting at (c, w, h, n); coordinates may be
+// negative / run past the tensor (the TMA unit zero-fills out-of-bounds elements and still delivers the full box).
+__device__ __forceinline__ void tma_load_tile_4d(uint32_t dst, const void* map, uint32_t bar, int c, int w, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
 // im2col-mode load on an NHWC tensor map {C, W, H, N}: `pixelsPerColumn` pixels starting at (w, h, n),
 // walking W then H then N inside the map's bounding box, each shifted by the filter offsets (off_w, off_h).
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* map, uint32_t bar, int c, int w, int h,
