@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_header_sizes():
     """sizeof of the ctypes mirrors equals what a C compiler computes for the header's structs."""
     from torchsr_b200 import _lib
-    src = '#include <stdio.h>\n#include "torchsr_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(tsr_conv_desc_t),' \
-          ' sizeof(tsr_wgrad_desc_t), sizeof(tsr_elt_desc_t), sizeof(tsr_pack_entry_t));return 0;}\n'
+    src = '#include <stdio.h>\n#include "torchsr_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(tsr_conv_desc_t),' \
+          ' sizeof(tsr_wgrad_desc_t), sizeof(tsr_elt_desc_t), sizeof(tsr_pack_entry_t), sizeof(tsr_adam_entry_t));return 0;}\n'
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -38,7 +38,7 @@ def test_ctypes_structs_match_header_sizes():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.WgradDesc), ctypes.sizeof(_lib.EltDesc),
-                     ctypes.sizeof(_lib.PackEntry)]
+                     ctypes.sizeof(_lib.PackEntry), ctypes.sizeof(_lib.AdamEntry)]
 
 
 def test_geometry_helpers():
