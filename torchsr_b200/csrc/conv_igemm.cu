@@ -574,6 +574,12 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          if (PERS && p.halo && !valid) {
+            // halo / padding rows of the tile were computed from whatever the patch buffer held: keep their
+            // (possibly non-finite) values out of the side reductions below
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
         }
         if (trace && threadIdx.x == 64 && ch < 4) trace[32 + 2 * ch] = clock64();
         const bool st = valid && col0 < n_valid;
