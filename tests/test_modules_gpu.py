@@ -330,3 +330,87 @@ def test_esrgan_trainer_steps_eager_and_graph():
     moved_g = sum(int(not torch.equal(v, g0[k])) for k, v in tr.generator.state_dict().items())
     moved_d = sum(int(not torch.equal(v, d0[k])) for k, v in tr.discriminator.state_dict().items() if "num_batches" not in k)
     assert moved_g >= len(g0) - 2 and moved_d >= len(d0) // 2, (moved_g, len(g0), moved_d, len(d0))
+
+
+def _trainer(kind, batch):
+    import os
+    from argparse import Namespace
+    os.environ["TORCHSR_VGG_WEIGHTS"] = "random"     # seeded (1234) random VGG19: the oracle builds the same one
+    args = Namespace(disable_amp=False, batch_size=batch, epochs=8, pretrain_epochs=1, gan_checkpoint=None,
+                     psnr_checkpoint=None, skip_image_save=True, local_rank=0, rank=-1, world_size=1)
+    if kind == "srgan":
+        from torchsr_b200.srgan.trainer import SRGANTrainer as T
+    else:
+        from torchsr_b200.esrgan.trainer import ESRGANTrainer as T
+    return T(torch.device("cuda"), args, [], [], 0, 0, False)
+
+
+def _cpu_state(module):
+    return {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}
+
+
+def _update_agreement(new_sd, old_sd, oracle_sd, min_numel=64):
+    """Adam's first step moves every weight by ~lr * sign(grad): fraction of weights moved in the oracle's direction."""
+    agree, total = 0, 0
+    for k, v in oracle_sd.items():
+        if not v.requires_grad or v.numel() < min_numel:
+            continue
+        du = (new_sd[k].cpu() - old_sd[k]).flatten()
+        dr = (v.detach() - old_sd[k]).flatten()
+        agree += int((torch.sign(du) == torch.sign(dr)).sum())
+        total += du.numel()
+    return agree / max(total, 1)
+
+
+@pytest.mark.parametrize("kind", ["srgan", "esrgan"])
+def test_pretrain_step_matches_oracle(kind):
+    """PSNR-phase step (srgan/trainer.py:376-388 MSE; esrgan/trainer.py:378-390 L1) through `_pretrain_step` on the
+    B200 against the oracle step pinned by tests/golden/*_pretrain_step.npz: same loss, same update direction."""
+    import step_oracle as S
+    torch.manual_seed(31)
+    tr = _trainer(kind, 2)
+    g_sd = _cpu_state(tr.generator)
+    s = 24 if kind == "srgan" else 32
+    lr, hr = torch.rand(2, 3, s, s), torch.rand(2, 3, 4 * s, 4 * s)
+    loss = float(tr._pretrain_step(lr.cuda(), hr.cuda()))
+    o = (S.OracleSRGAN if kind == "srgan" else S.OracleESRGAN)(g_sd, {}, None)
+    ref = o.pretrain_step(lr, hr)
+    assert abs(loss - ref) <= 2e-2 * abs(ref) + 1e-4, (loss, ref)
+    frac = _update_agreement(tr.generator.state_dict(), g_sd, o.g)
+    assert frac >= 0.85, frac
+
+
+def test_esrgan_gan_step_matches_oracle_step():
+    """One ESRGANTrainer._gan_loop (relativistic GAN step, esrgan/trainer.py:435-484) on the B200, WITH the VGG19
+    perceptual loss on this repo's kernels, against the oracle step (pinned by tests/golden/esrgan_gan_step.npz):
+    generator loss within 5 % (23 RRDB blocks + 16 VGG convs of bf16 roundings) and the same Adam update direction
+    for both networks."""
+    import step_oracle as S
+    torch.manual_seed(41)
+    tr = _trainer("esrgan", 2)
+    g_sd, d_sd = _cpu_state(tr.generator), _cpu_state(tr.discriminator)
+    lr, hr = torch.rand(2, 3, 32, 32), torch.rand(2, 3, 128, 128)
+    gen_loss = float(tr._gan_loop(lr.cuda(), hr.cuda(), 0))
+    o = S.OracleESRGAN(g_sd, d_sd, S.vgg19_features(1234))
+    _, ref = o.gan_step(lr, hr)
+    assert abs(gen_loss - ref) <= 5e-2 * abs(ref) + 1e-4, (gen_loss, ref)
+    fg = _update_agreement(tr.generator.state_dict(), g_sd, o.g)
+    fd = _update_agreement(tr.discriminator.state_dict(), d_sd, o.d)
+    assert fg >= 0.8 and fd >= 0.8, (fg, fd)
+
+
+def test_srgan_gan_step_with_vgg_matches_oracle_step():
+    """The headline step exactly as bench.py runs it (VGG19 loss on this repo's kernels, seeded random VGG weights on
+    both sides) against the oracle step pinned by tests/golden/srgan_gan_step.npz."""
+    import step_oracle as S
+    torch.manual_seed(51)
+    tr = _trainer("srgan", 4)
+    g_sd, d_sd = _cpu_state(tr.generator), _cpu_state(tr.discriminator)
+    lr, hr = torch.rand(4, 3, 24, 24), torch.rand(4, 3, 96, 96)
+    gen_loss = float(tr._gan_loop(lr.cuda(), hr.cuda(), 0))
+    o = S.OracleSRGAN(g_sd, d_sd, S.vgg19_features(1234))
+    _, ref = o.gan_step(lr, hr)
+    assert abs(gen_loss - ref) <= 5e-2 * abs(ref) + 1e-4, (gen_loss, ref)
+    fg = _update_agreement(tr.generator.state_dict(), g_sd, o.g)
+    fd = _update_agreement(tr.discriminator.state_dict(), d_sd, o.d)
+    assert fg >= 0.8 and fd >= 0.8, (fg, fd)

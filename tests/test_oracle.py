@@ -47,6 +47,42 @@ def test_oracle_gan_step_reproduces_reference_trainer():
         assert digest_close(digest(o.d[k].float()), ref, rtol=2e-4, atol=1e-6), (k, digest(o.d[k].float()), ref)
 
 
+def test_oracle_esrgan_gan_step_reproduces_reference_trainer():
+    """One full ESRGANTrainer._gan_loop (relativistic GAN, 23 RRDB blocks): post-step parameters and BatchNorm buffers
+    of the oracle step equal the reference trainer's."""
+    torch.set_num_threads(8)
+    meta, arr = load_fixture("esrgan_gan_step")
+    from torchsr_b200.esrgan.discriminator import Discriminator
+    from torchsr_b200.esrgan.generator import Generator
+    g_sd = synth_state_dict(Generator().state_dict(), 21)
+    d_sd = synth_state_dict(Discriminator().state_dict(), 22)
+    o = S.OracleESRGAN(g_sd, d_sd, S.vgg19_features(1234))
+    o.gan_step(arr["low_res"], arr["high_res"])
+    for k, ref in meta["g_after"].items():
+        assert digest_close(digest(o.g[k].float()), ref, rtol=2e-4, atol=1e-6), (k, digest(o.g[k].float()), ref)
+    for k, ref in meta["d_after"].items():
+        assert digest_close(digest(o.d[k].float()), ref, rtol=2e-4, atol=1e-6), (k, digest(o.d[k].float()), ref)
+
+
+@pytest.mark.parametrize("kind", ["srgan", "esrgan"])
+def test_oracle_pretrain_steps_reproduce_reference(kind):
+    """Two PSNR-phase steps (srgan/trainer.py:376-388 MSE, esrgan/trainer.py:378-390 L1): losses and post-step
+    generator state equal the reference trainer's own modules / optimizer driven through the same statements."""
+    torch.set_num_threads(8)
+    meta, arr = load_fixture(f"{kind}_pretrain_step")
+    if kind == "srgan":
+        from torchsr_b200.srgan.generator import Generator
+        o = S.OracleSRGAN(synth_state_dict(Generator().state_dict(), 31), {}, None)
+    else:
+        from torchsr_b200.esrgan.generator import Generator
+        o = S.OracleESRGAN(synth_state_dict(Generator().state_dict(), 41), {}, None)
+    losses = [o.pretrain_step(arr["low_res"], arr["high_res"]) for _ in range(2)]
+    for a, b in zip(losses, meta["losses"]):
+        assert abs(a - b) <= 1e-4 * abs(b), (losses, meta["losses"])
+    for k, ref in meta["g_after"].items():
+        assert digest_close(digest(o.g[k].float()), ref, rtol=2e-4, atol=1e-6), (k, digest(o.g[k].float()), ref)
+
+
 def test_state_dict_contract_matches_reference_shapes():
     """Keys, shapes and dtypes of the drop-in modules equal the reference's (recorded in the fixtures)."""
     from torchsr_b200.esrgan.discriminator import Discriminator as ED
