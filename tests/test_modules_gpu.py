@@ -414,3 +414,79 @@ def test_srgan_gan_step_with_vgg_matches_oracle_step():
     fg = _update_agreement(tr.generator.state_dict(), g_sd, o.g)
     fd = _update_agreement(tr.discriminator.state_dict(), d_sd, o.d)
     assert fg >= 0.8 and fd >= 0.8, (fg, fd)
+
+
+def _write_png(path, h, w, seed):
+    """Smooth synthetic RGB image (low-frequency noise), written as PNG."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.Generator(np.random.PCG64(seed))
+    small = torch.from_numpy(rng.uniform(0, 1, (1, 3, h // 8 + 2, w // 8 + 2)).astype("float32"))
+    img = torch.nn.functional.interpolate(small, size=(h, w), mode="bicubic", align_corners=False).clamp(0, 1)
+    arr = (img[0].permute(1, 2, 0).numpy() * 255 + 0.5).astype("uint8")
+    Image.fromarray(arr).save(path)
+
+
+def _read_png(path):
+    from PIL import Image
+    from torchvision.transforms import ToTensor
+    return ToTensor()(Image.open(path).convert("RGB")).unsqueeze(0)
+
+
+def test_cli_train_then_test_end_to_end(tmp_path, monkeypatch):
+    """`torchsr train` (1 pretrain + 2 GAN epochs on a tiny synthetic image folder, whole-step CUDA graphs in the epoch
+    loops) writes the reference's checkpoint files ({"epoch","phase","state"}, torchsr/srgan/trainer.py:305-343);
+    `torchsr test` then loads `srgan-gan-best.pth` and writes `upres-<image>` at x4 (torchsr/test.py:22-63). The image
+    is compared with the oracle generator run on the same checkpoint."""
+    import os
+    import torchsr_oracle as O
+    from torchsr_b200 import torchsr as cli
+    monkeypatch.setenv("TORCHSR_VGG_WEIGHTS", "random")
+    monkeypatch.chdir(tmp_path)
+    data = tmp_path / "data"
+    data.mkdir()
+    for i in range(12):
+        _write_png(str(data / f"img{i:02d}.png"), 128, 160, 100 + i)
+    torch.manual_seed(61)
+    cli.main(["train", "--train-dir", str(data), "--batch-size", "2", "--epochs", "2", "--pretrain-epochs", "1",
+              "--data-workers", "0", "--skip-image-save", "--model", "srgan"])
+    for name in ["srgan-psnr-best.pth", "srgan-psnr-latest.pth", "srgan-gan-best.pth", "srgan-gan-latest.pth"]:
+        ck = torch.load(str(tmp_path / name), map_location="cpu")
+        assert set(ck) == {"epoch", "phase", "state"} and ck["phase"] == name.rsplit("-", 1)[0], (name, ck.keys())
+        assert all(torch.isfinite(v.float()).all() for v in ck["state"].values()), name
+    _write_png(str(tmp_path / "lowres.png"), 48, 64, 7)
+    cli.main(["test", "lowres.png", "--model", "srgan"])
+    ours = _read_png(str(tmp_path / "upres-lowres.png"))
+    assert ours.shape == (1, 3, 192, 256)
+    state = {k: v.float() if v.is_floating_point() else v
+             for k, v in torch.load(str(tmp_path / "srgan-gan-best.pth"), map_location="cpu")["state"].items()}
+    with torch.no_grad():
+        ref = O.srgan_generator(state, _read_png(str(tmp_path / "lowres.png")), False).clamp(0, 1)
+    ref8 = (ref * 255 + 0.5).floor() / 255          # torchvision.utils.save_image quantisation
+    assert O.psnr(ours, ref8) >= 30.0, O.psnr(ours, ref8)
+
+
+def test_c1_fixture_shape_inference_psnr_both_bn_modes():
+    """BASELINE configs[0] shape: one 320x480 image -> 1280x1920 through `test.upscale` with trained-like synthetic
+    weights, in eval mode (this repo's default) and in the reference's train-mode-BatchNorm behaviour (torchsr/test.py
+    never calls eval()). Output PSNR against a x4 bicubic target agrees with the oracle within
+    0.05 dB (north star)."""
+    import torchsr_oracle as O
+    from golden_util import synth_input, synth_state_dict
+    from torchsr_b200.srgan.generator import Generator
+    from torchsr_b200.test import upscale
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    G = Generator()
+    sd = synth_state_dict(G.state_dict(), 71)
+    G.load_state_dict(sd)
+    G = G.cuda()
+    x = synth_input((1, 3, 320, 480), 72)
+    target = torch.nn.functional.interpolate(x, scale_factor=4, mode="bicubic").clamp(0, 1)
+    for train_mode in (False, True):
+        y = upscale(G, x.cuda(), train_mode=train_mode).float().cpu()
+        with torch.no_grad():
+            ref = O.srgan_generator(sd, x, train_mode)
+        assert y.shape == (1, 3, 1280, 1920)
+        assert float((y - ref).norm() / ref.norm()) <= 3e-2, train_mode
+        p_ours, p_ref = O.psnr(y.clamp(0, 1), target), O.psnr(ref.clamp(0, 1), target)
+        assert abs(p_ours - p_ref) <= 0.05, (train_mode, p_ours, p_ref)

@@ -231,6 +231,14 @@ class SRGANTrainer:
         graph.replay()
         return loss
 
+    def _train_step(self, kind: str, low_res: Tensor, high_res: Tensor, step: int) -> Tensor:
+        """The step the epoch loops call: the whole-step CUDA graph for full batches on a GPU (TORCHSR_GRAPH_STEP=0
+        selects the eager call), the eager step for a ragged batch."""
+        if (self.device.type == 'cuda' and low_res.size(0) == self.batch_size
+                and os.environ.get('TORCHSR_GRAPH_STEP', '1') != '0'):
+            return self.graph_step(low_res, high_res, step, kind)
+        return self._gan_loop(low_res, high_res, step) if kind == 'gan' else self._pretrain_step(low_res, high_res)
+
     # ------------------------------------------------------------------ evaluation / checkpoints
     def _model_state(self, epoch: int, phase: str) -> dict:
         return {"epoch": epoch, "phase": phase, "state": self.generator.state_dict()}
@@ -281,7 +289,7 @@ class SRGANTrainer:
             t0 = time.time()
             seen = 0
             for low_res, high_res in self.train_loader:
-                self._pretrain_step(low_res, high_res)
+                self._train_step('psnr', low_res, high_res, step)
                 seen += low_res.size(0)
                 step += 1
             if self.device.type == 'cuda':
@@ -299,7 +307,7 @@ class SRGANTrainer:
             t0 = time.time()
             seen = 0
             for low_res, high_res in self.train_loader:
-                self._gan_loop(low_res, high_res, step)
+                self._train_step('gan', low_res, high_res, step)
                 seen += low_res.size(0)
                 step += 1
             self.disc_scheduler.step()
