@@ -208,6 +208,10 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   p.a_mode = d.a_mode;
   p.a_c0 = d.a_c0;
   p.w_static = d.w_static;
+  {
+    const char* dbg = getenv("TSR_CONV_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   p.b_rows_per_tap = d.cout_pad;
   memcpy(p.tap_off, d.tap_off, sizeof(p.tap_off));
   memcpy(p.tap_wrow, d.tap_wrow, sizeof(p.tap_wrow));

@@ -106,7 +106,7 @@ __device__ __forceinline__ void store_f32x16(void* base, long long off, const fl
 
 // Warp 0 (all lanes run the loop so that every value stays warp-uniform; one elected lane issues): keeps the smem
 // ring full. All per-iteration state is carried incrementally (no divisions inside the K loop).
-template <int A_MODE, bool PERS>
+template <int A_MODE, bool PERS, bool FAST>
 __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_b,
                                               uint32_t b_res, uint32_t ring, int tile_n, int it_begin, int it_end,
                                               int tiles_m, long long* trace) {
@@ -159,6 +159,7 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
   }
   pdl_sync();
   if (pers && !p.w_static) load_resident_b();
+  const bool leader = elect_one();   // the same lane every time; hoisted out of the FAST loop
   int s = 0;
   uint32_t ph = 1;  // parity to wait for on the empty barrier (first pass over the ring passes immediately)
   uint32_t dst = ring;
@@ -172,8 +173,12 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
         if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
         const uint32_t full = bar_full + 8 * s;
         if (elect_one()) {
-          mbar_arrive_expect_tx(full, p.a_bytes);
-          tma_load_tile_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, -1, hrow0, n_img);
+          if (p.debug & 4) {
+            mbar_arrive(full);      // attribution run: no activation traffic, the MMAs read whatever the stage holds
+          } else {
+            mbar_arrive_expect_tx(full, p.a_bytes);
+            tma_load_tile_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, -1, hrow0, n_img);
+          }
         }
         __syncwarp();
         dst += stage_bytes;
@@ -201,6 +206,39 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
       tap = it_begin / kc_per_tap;
       kc = it_begin - tap * kc_per_tap;
     }
+    if constexpr (FAST) {
+      // Lean im2col loop (production path: 64-channel K chunks, no trace / attribution hooks). The K-iteration rate of
+      // the small-N layers is set by the instruction latency of this single warp, not by TMA or the tensor core
+      // (tools/trace_conv.py: with loads and UMMAs removed the loop still took ~500 clk per iteration), so everything
+      // that is not the wait, the arm and the two loads is hoisted out of it.
+      const uint32_t b_tap_rows = static_cast<uint32_t>(p.b_rows_per_tap);
+      int n_pre = first_tile ? pre : 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
+        if (leader) {
+          const uint32_t full = bar_full + 8 * s;
+          const uint32_t off = p.tap_off[tap];
+          if (PERS || n_pre <= 0) mbar_arrive_expect_tx(full, tx);
+          tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
+          if (!PERS && n_pre <= 0)
+            tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, p.tap_wrow[tap] * b_tap_rows + b_row0);
+        }
+        --n_pre;
+        if (++kc == kc_per_tap) {
+          kc = 0;
+          ++tap;
+        }
+        dst += stage_bytes;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+          dst = ring;
+        }
+      }
+      first_tile = false;
+      if (!PERS) break;
+      continue;
+    }
     for (int it = it_begin; it < it_end; ++it) {
       if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
       const uint32_t full = bar_full + 8 * s;
@@ -211,9 +249,13 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
         const uint32_t off = p.tap_off[tap];
         const int brow = p.tap_wrow[tap] * p.b_rows_per_tap + b_row0;
         if (elect_one()) {
-          if (arm) mbar_arrive_expect_tx(full, tx);
-          tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
-          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, brow);
+          if (PERS && (p.debug & 4)) {
+            mbar_arrive(full);      // attribution run (see the halo branch)
+          } else {
+            if (arm) mbar_arrive_expect_tx(full, tx);
+            tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
+            if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, brow);
+          }
         }
         if (++kc == kc_per_tap) {
           kc = 0;
@@ -251,7 +293,7 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
 }
 
 // Warp 1 (all lanes loop, one elected lane issues): the UMMAs of every stage, slot recycling with tcgen05.commit.
-template <int A_MODE, bool PERS>
+template <int A_MODE, bool PERS, bool FAST>
 __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_acc_full,
                                          uint32_t bar_acc_empty, uint32_t bar_b, uint32_t b_res, uint32_t ring,
                                          uint32_t tmem_base, int n_iters, int tiles_m, long long* trace) {
@@ -276,6 +318,7 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
     if (!mbar_wait(bar_b, 0, p.epi.err, 4)) return;
     tc_fence_after();
   }
+  const bool leader = elect_one();
   int s = 0, j = 0;
   uint32_t ph = 0, soff = 0;
   for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++j) {
@@ -304,6 +347,7 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
             const uint32_t a_hi_t = a_hi;
             uint32_t b_lo = b_lo0 + static_cast<uint32_t>(t * kc_per_tap + kc) * b16;
             for (uint32_t k = 0; k < ksteps; ++k) {
+              if (!(p.debug & 8))
               umma_bf16(d_tmem, (static_cast<uint64_t>(a_hi_t) << 32) | a_lo, (static_cast<uint64_t>(b_hi) << 32) | b_lo,
                         idesc, acc);
               acc = 1;
@@ -324,6 +368,28 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
       __syncwarp();
       continue;
     }
+    if constexpr (FAST) {
+      // Lean loop (64-element K chunks): one asm block issues the four UMMAs of the stage and the commit.
+      const uint64_t a_desc0 = (static_cast<uint64_t>(a_hi) << 32) | a_lo0;
+      const uint64_t b_desc0 = (static_cast<uint64_t>(b_hi) << 32) | b_lo0;
+      for (int it = 0; it < n_iters; ++it) {
+        if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) return;
+        tc_fence_after();
+        if (leader)
+          umma_bf16_x4_commit(d_tmem, a_desc0 + soff, b_desc0 + (pers ? boff : soff), idesc, acc, bar_empty + 8 * s);
+        acc = 1;
+        boff += b16;
+        soff += stage16;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+          soff = 0;
+        }
+      }
+      if (leader) umma_commit(bar_acc_full + 8 * as);
+      if (!PERS) break;
+      continue;
+    }
     for (int it = 0; it < n_iters; ++it) {
       if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) return;
       tc_fence_after();
@@ -332,6 +398,7 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
         uint32_t a_lo = a_lo0 + soff, b_lo = b_lo0 + (pers ? boff : soff);
         uint32_t acc_k = acc;
         for (uint32_t k = 0; k < ksteps; ++k) {
+          if (!(PERS && (p.debug & 8)))
           umma_bf16(d_tmem, (static_cast<uint64_t>(a_hi) << 32) | a_lo, (static_cast<uint64_t>(b_hi) << 32) | b_lo,
                     idesc, acc_k);
           acc_k = 1;
@@ -358,7 +425,9 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
 }
 
 // One CTA = one output tile (tile_m, tile_n) of conv `p`, K range = split `zsplit` of `nsplits`.
-template <int A_MODE, bool PERS>
+// FAST: production instantiation for im2col convs on 64-channel K chunks - no trace stamps, no attribution hooks,
+// lean producer / MMA loops. The host selects it whenever the descriptor allows (launch_conv_igemm).
+template <int A_MODE, bool PERS, bool FAST = false>
 __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit, const int nsplits) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -381,8 +450,9 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
   const int tiles_m = (PERS && p.halo) ? p.halo_tiles_per_img * (p.M_total / (p.halo_H * p.halo_W))
                                        : (p.M_total + kBlockM - 1) / kBlockM;
 
-  long long* trace = p.epi.trace ? p.epi.trace + 40ll * ((zsplit * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
-                                 : nullptr;
+  long long* trace = (!FAST && p.epi.trace)
+                         ? p.epi.trace + 40ll * ((zsplit * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x)
+                         : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = clock64();
   const int total_iters = p.num_taps * p.kc_per_tap;
   const int it_begin = zsplit * p.iters_per_split;
@@ -414,10 +484,10 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
   if (trace && threadIdx.x == 0) trace[1] = clock64();
 
   if (warp == 0) {
-    producer_role<A_MODE, PERS>(p, bar_full, bar_empty, bar_b, b_res, ring, tile_n, it_begin, it_end, tiles_m, trace);  // pdl_sync() inside
+    producer_role<A_MODE, PERS, FAST>(p, bar_full, bar_empty, bar_b, b_res, ring, tile_n, it_begin, it_end, tiles_m, trace);  // pdl_sync() inside
   } else if (warp == 1) {
     pdl_sync();
-    mma_role<A_MODE, PERS>(p, bar_full, bar_empty, bar_acc_full, bar_acc_empty, bar_b, b_res, ring, tmem_base,
+    mma_role<A_MODE, PERS, FAST>(p, bar_full, bar_empty, bar_acc_full, bar_acc_empty, bar_b, b_res, ring, tmem_base,
                      it_end - it_begin, tiles_m, trace);
   } else {
     pdl_sync();   // the epilogue reads residuals / statistics buffers written by earlier kernels of the stream
@@ -548,6 +618,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       named_bar_sync(1, kConvThreads - 64);
       finalize = ok && (*reinterpret_cast<volatile int*>(flag) != 0);
     }
+    if (!FAST && (p.debug & 1)) finalize = false;
     if (finalize) {
       for (int ch = ch_begin; ch < ch_end; ++ch) {
         const int col0 = colbase + ch * 16;
@@ -582,7 +653,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           }
         }
         if (trace && threadIdx.x == 64 && ch < 4) trace[32 + 2 * ch] = clock64();
-        const bool st = valid && col0 < n_valid;
+        const bool st = valid && col0 < n_valid && (FAST || !(p.debug & 2));
         if (bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 16);
 #pragma unroll
@@ -733,77 +804,84 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
   if (trace && threadIdx.x == 0) trace[7] = clock64();
 }
 
-template <int A_MODE>
+template <int A_MODE, bool FAST = false>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  conv_body<A_MODE, false>(p, blockIdx.z, gridDim.z);
+  conv_body<A_MODE, false, FAST>(p, blockIdx.z, gridDim.z);
 }
 
 // Persistent weight-stationary variant (im2col convs only): see the comment above producer_role.
+template <bool FAST>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_persistent_kernel(const __grid_constant__ ConvParams p) {
-  conv_body<0, true>(p, 0, 1);
+  conv_body<0, true, FAST>(p, 0, 1);
+}
+
+// FAST instantiations need 64-channel K chunks and run without trace stamps / attribution hooks.
+static bool fast_ok(const ConvParams& p) {
+  return p.a_mode == 0 && p.block_k == 64 && p.epi.trace == nullptr && p.debug == 0;
 }
 
 // Up to four independent im2col convs of the same tile grid in ONE launch (blockIdx.z selects the member): the four
 // output-parity classes of a stride-2 data gradient, which would otherwise be four latency-bound launches in a row.
+template <bool FAST>
 __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_group_kernel(const __grid_constant__ ConvGroup g) {
   const ConvParams& p = g.p[blockIdx.z];
   if (static_cast<int>(blockIdx.x) * kBlockM >= p.M_total || static_cast<int>(blockIdx.y) >= g.tiles_n[blockIdx.z]) return;
-  conv_body<0, false>(p, 0, 1);
+  conv_body<0, false, FAST>(p, 0, 1);
 }
 
 size_t conv_igemm_smem_bytes(const ConvParams& p) {
   return 1024 + kHeaderBytes + p.b_res_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
 }
 
-template <int A_MODE>
-static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t stream, bool pdl) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(conv_igemm_kernel<A_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+// One launch path for every instantiation: raises the dynamic shared-memory limit of `kernel` once, then launches.
+template <typename Kernel, typename Params>
+static cudaError_t launch_conv_kernel(Kernel kernel, bool* attr_set, dim3 grid, size_t smem, cudaStream_t stream, bool pdl,
+                                      const Params& params) {
+  if (!*attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    *attr_set = true;
   }
-  cudaError_t e = launch_k(conv_igemm_kernel<A_MODE>, grid, dim3(kConvThreads), smem, stream, pdl, p);
+  cudaError_t e = launch_k(kernel, grid, dim3(kConvThreads), smem, stream, pdl, params);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bool pdl) {
+template <int A_MODE, bool FAST>
+static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  return launch_conv_kernel(conv_igemm_kernel<A_MODE, FAST>, &attr_set, grid, smem, stream, pdl, p);
+}
+
+cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bool pdl) {
   int tiles_m = 0, tiles_n = 0;
   size_t smem = 0;
+  bool fast = true;
   for (int k = 0; k < n; ++k) {
     tiles_m = max(tiles_m, (g.p[k].M_total + kBlockM - 1) / kBlockM);
     tiles_n = max(tiles_n, g.tiles_n[k]);
     smem = max(smem, conv_igemm_smem_bytes(g.p[k]));
+    fast = fast && fast_ok(g.p[k]);
   }
-  cudaError_t e = launch_k(conv_igemm_group_kernel, dim3(tiles_m, tiles_n, n), dim3(kConvThreads), smem, stream, pdl, g);
-  return e != cudaSuccess ? e : cudaGetLastError();
+  const dim3 grid(tiles_m, tiles_n, n);
+  static bool attr_fast = false, attr_slow = false;
+  if (fast) return launch_conv_kernel(conv_igemm_group_kernel<true>, &attr_fast, grid, smem, stream, pdl, g);
+  return launch_conv_kernel(conv_igemm_group_kernel<false>, &attr_slow, grid, smem, stream, pdl, g);
 }
 
 cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cudaStream_t stream, bool pdl) {
   const int tiles_m = (p.M_total + kBlockM - 1) / kBlockM;
   dim3 grid(p.persistent ? (p.halo ? p.persistent : min(tiles_m, p.persistent)) : tiles_m, tiles_n, splits);
   const size_t smem = conv_igemm_smem_bytes(p);
+  const bool fast = fast_ok(p);
   if (p.persistent) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e =
-          cudaFuncSetAttribute(conv_igemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    cudaError_t e = launch_k(conv_igemm_persistent_kernel, grid, dim3(kConvThreads), smem, stream, pdl, p);
-    return e != cudaSuccess ? e : cudaGetLastError();
+    static bool attr_fast = false, attr_slow = false;
+    if (fast) return launch_conv_kernel(conv_igemm_persistent_kernel<true>, &attr_fast, grid, smem, stream, pdl, p);
+    return launch_conv_kernel(conv_igemm_persistent_kernel<false>, &attr_slow, grid, smem, stream, pdl, p);
   }
-  if (p.a_mode == 0) return launch_mode<0>(p, grid, smem, stream, pdl);
-  if (p.a_mode == 1) return launch_mode<1>(p, grid, smem, stream, pdl);
-  return launch_mode<2>(p, grid, smem, stream, pdl);
+  if (p.a_mode == 0)
+    return fast ? launch_mode<0, true>(p, grid, smem, stream, pdl) : launch_mode<0, false>(p, grid, smem, stream, pdl);
+  if (p.a_mode == 1) return launch_mode<1, false>(p, grid, smem, stream, pdl);
+  return launch_mode<2, false>(p, grid, smem, stream, pdl);
 }
 
 }  // namespace tsr

@@ -95,6 +95,9 @@ struct ConvParams {
   int halo_tiles_per_img;
   int halo_H, halo_W;    // image size (output == input size)
   int w_static;    // the B operand is not written by any kernel of the enclosing stream segment (real weights)
+  int debug;       // attribution experiments only (TSR_CONV_DEBUG bits, tools/trace_conv.py), 0 in production: 1 = the
+                   // epilogue skips the accumulator read-out and the stores, 2 = it computes but does not store,
+                   // 4 = (persistent kernel) no activation TMA loads, 8 = (persistent kernel) no UMMAs issued.
   // derived on the host so that the single-thread producer / MMA loops stay short
   uint32_t a_bytes, b_bytes, stage_bytes;
   uint32_t ksteps;      // block_k / 16

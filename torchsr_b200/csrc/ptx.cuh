@@ -113,6 +113,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The four K=16 steps of one 64-element K chunk (K-major bf16 operands: the start-address field of both shared-memory
+// descriptors advances by 32 bytes = 2 units per step) followed by the commit that recycles the ring stage: one asm
+// block, so the single issuing thread spends as few instructions as possible per K iteration.
+__device__ __forceinline__ void umma_bf16_x4_commit(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %4, %4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %6, %7, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %8, %9, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %10, %11, %3, t;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(bar), "l"(adesc + 2), "l"(bdesc + 2),
+        "l"(adesc + 4), "l"(bdesc + 4), "l"(adesc + 6), "l"(bdesc + 6)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
