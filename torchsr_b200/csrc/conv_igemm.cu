@@ -209,30 +209,46 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
     if constexpr (FAST) {
       // Lean im2col loop (production path: 64-channel K chunks, no trace / attribution hooks). The K-iteration rate of
       // the small-N layers is set by the instruction latency of this single warp, not by TMA or the tensor core
-      // (tools/trace_conv.py: with loads and UMMAs removed the loop still took ~500 clk per iteration), so everything
-      // that is not the wait, the arm and the two loads is hoisted out of it.
-      const uint32_t b_tap_rows = static_cast<uint32_t>(p.b_rows_per_tap);
+      // (tools/trace_conv.py: with loads and UMMAs removed the loop still took ~500 clk per iteration). So: loop
+      // invariants are pinned in registers, every operand of iteration i+1 (barrier addresses, destination, channel
+      // coordinate, filter offsets) is prepared before the wait of iteration i+1, and the body is wait-arm-load.
+      const uint32_t kcpt = in_reg(static_cast<uint32_t>(kc_per_tap)), nst = in_reg(static_cast<uint32_t>(stages));
+      const uint32_t sbytes = in_reg(stage_bytes), txr = in_reg(tx), abytes = in_reg(a_bytes);
+      const uint32_t b_tap_rows = in_reg(static_cast<uint32_t>(p.b_rows_per_tap));
+      const int c_first = static_cast<int>(in_reg(static_cast<uint32_t>(p.a_c0)));
       int n_pre = first_tile ? pre : 0;
+      uint32_t ukc = static_cast<uint32_t>(kc);
+      int cA = c_first + kc * 64, cB = kc * 64;
+      uint32_t offs = p.tap_off[tap];
+      int brow = static_cast<int>(p.tap_wrow[tap] * b_tap_rows) + b_row0;
+      uint32_t full = bar_full + 8 * s, empty = bar_empty + 8 * s;
       for (int it = it_begin; it < it_end; ++it) {
-        if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
+        if (!mbar_wait(empty, ph, p.epi.err, 1)) return;
         if (leader) {
-          const uint32_t full = bar_full + 8 * s;
-          const uint32_t off = p.tap_off[tap];
-          if (PERS || n_pre <= 0) mbar_arrive_expect_tx(full, tx);
-          tma_load_im2col_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, w0, h0, n0, off & 0xFF, off >> 8);
-          if (!PERS && n_pre <= 0)
-            tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, p.tap_wrow[tap] * b_tap_rows + b_row0);
+          if (PERS || n_pre <= 0) mbar_arrive_expect_tx(full, txr);
+          tma_load_im2col_4d(dst, &p.tmA, full, cA, w0, h0, n0, offs & 0xFF, offs >> 8);
+          if (!PERS && n_pre <= 0) tma_load_2d(dst + abytes, &p.tmB, full, cB, brow);
         }
         --n_pre;
-        if (++kc == kc_per_tap) {
-          kc = 0;
+        cA += 64;
+        cB += 64;
+        if (++ukc == kcpt) {
+          ukc = 0;
+          cA = c_first;
+          cB = 0;
           ++tap;
+          offs = p.tap_off[tap < kMaxTaps ? tap : kMaxTaps - 1];
+          brow = static_cast<int>(p.tap_wrow[tap < kMaxTaps ? tap : kMaxTaps - 1] * b_tap_rows) + b_row0;
         }
-        dst += stage_bytes;
-        if (++s == stages) {
+        dst += sbytes;
+        full += 8;
+        empty += 8;
+        if (static_cast<uint32_t>(++s) == nst) {
           s = 0;
           ph ^= 1;
           dst = ring;
+          full = bar_full;
+          empty = bar_empty;
         }
       }
       first_tile = false;
@@ -369,21 +385,32 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
       continue;
     }
     if constexpr (FAST) {
-      // Lean loop (64-element K chunks): one asm block issues the four UMMAs of the stage and the commit.
+      // Lean loop (64-element K chunks): one asm block issues the four UMMAs of the stage and the commit; descriptors
+      // and barrier addresses of the next stage are advanced before its wait, loop invariants are pinned in registers.
+      const uint32_t nst = in_reg(static_cast<uint32_t>(stages)), st16 = in_reg(stage16), b16r = in_reg(b16);
+      const uint32_t idesc_r = in_reg(idesc);
       const uint64_t a_desc0 = (static_cast<uint64_t>(a_hi) << 32) | a_lo0;
       const uint64_t b_desc0 = (static_cast<uint64_t>(b_hi) << 32) | b_lo0;
+      uint64_t ad = a_desc0 + soff, bd = pers ? b_desc0 : b_desc0 + soff;
+      uint32_t full = bar_full + 8 * s, empty = bar_empty + 8 * s;
       for (int it = 0; it < n_iters; ++it) {
-        if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) return;
+        if (!mbar_wait(full, ph, p.epi.err, 2)) return;
         tc_fence_after();
-        if (leader)
-          umma_bf16_x4_commit(d_tmem, a_desc0 + soff, b_desc0 + (pers ? boff : soff), idesc, acc, bar_empty + 8 * s);
+        if (leader) umma_bf16_x4_commit(d_tmem, ad, bd, idesc_r, acc, empty);
         acc = 1;
-        boff += b16;
-        soff += stage16;
-        if (++s == stages) {
+        ad += st16;
+        bd += pers ? b16r : st16;
+        soff += st16;
+        full += 8;
+        empty += 8;
+        if (static_cast<uint32_t>(++s) == nst) {
           s = 0;
           ph ^= 1;
           soff = 0;
+          ad = a_desc0;
+          if (!pers) bd = b_desc0;
+          full = bar_full;
+          empty = bar_empty;
         }
       }
       if (leader) umma_commit(bar_acc_full + 8 * as);

@@ -212,6 +212,11 @@ __device__ __forceinline__ void prefetch_l1(const void* p) {
 }
 
 // ------------------------------------------------------------------ misc
+// Pins a loop-invariant kernel parameter in a register: ptxas otherwise re-loads it from the constant bank inside the
+// loop (LDC/LDCU, ~35 clk each, in the dependency chain of the single-warp producer / MMA loops).
+// (A warp shuffle is the cheapest operation whose result ptxas cannot trace back to the constant bank; call it
+// with the whole warp converged.)
+__device__ __forceinline__ uint32_t in_reg(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
