@@ -23,6 +23,15 @@ SHAPES = {
     "trunk   64->64  @24": (16, 24, 24, 64, 64, 32, True, L.ACT_NONE),
     "trunk64 64->64  @24": (16, 24, 24, 64, 64, 64, True, L.ACT_NONE),
     "infer   64->64 @512": (1, 512, 512, 64, 64, 64, False, L.ACT_PRELU),
+    "inferup 64->256@512": (1, 512, 512, 64, 256, 128, False, L.ACT_PRELU),
+    "vgg2_1  64->128 @48": (16, 48, 48, 64, 128, 128, False, L.ACT_RELU),
+    "n256 up2 64->256@48": (16, 48, 48, 64, 256, 256, False, L.ACT_PRELU),
+    "n256 inferup    @512": (1, 512, 512, 64, 256, 256, False, L.ACT_PRELU),
+    "n256 vgg3_2     @24": (16, 24, 24, 256, 256, 256, False, L.ACT_RELU),
+    "n256 vgg4 512  @12": (16, 12, 12, 512, 512, 256, False, L.ACT_RELU),
+    "n128 vgg4 512  @12": (16, 12, 12, 512, 512, 128, False, L.ACT_RELU),
+    "n64  vgg4 512  @12": (16, 12, 12, 512, 512, 64, False, L.ACT_RELU),
+    "vgg2_2n 128->128@48": (16, 48, 48, 128, 128, 64, False, L.ACT_RELU),
 }
 
 
@@ -84,13 +93,16 @@ def main():
         for halo in ("0", "1"):
             os.environ["TSR_CONV_HALO"] = halo
             row = []
-            for dbg in ("0", "2", "1", "5", "9", "13"):
+            for dbg in (("0",) if os.environ.get("TRACE_CONV_QUICK") else ("0", "2", "1", "5", "9", "13")):
                 os.environ["TSR_CONV_DEBUG"] = dbg
                 row.append(time_it(shape))
             os.environ["TSR_CONV_DEBUG"] = "0"
+            if os.environ.get("TRACE_CONV_QUICK"):
+                print(f"{name} bn={shape[5]:3d} halo={halo}: {row[0]:7.2f} us ({gflop / row[0]:6.1f} TF/s)")
+                continue
             tr = trace_it(shape)
             chunks = " ".join(f"[{int(a)}->{int(b)}]" for a, b in tr["chunks"])
-            print(f"{name} bn={shape[5]:3d} halo={halo}: {row[0]:7.2f} us ({gflop / row[0] * 1e-3:6.1f} TF/s) | no-store "
+            print(f"{name} bn={shape[5]:3d} halo={halo}: {row[0]:7.2f} us ({gflop / row[0] * 1e-3 * 1e3:6.1f} TF/s) | no-store "
                   f"{row[1]:7.2f} | no-epi {row[2]:7.2f} | no-epi,no-TMA {row[3]:7.2f} | no-epi,no-MMA {row[4]:7.2f} | "
                   f"sync only {row[5]:7.2f} | ctas {tr['ctas']} setup {int(tr['setup'])} "
                   f"acc_full {int(tr['acc_full'])} chunks(ld->st) {chunks} epi_done {int(tr['epi_done'])} exit {int(tr['exit'])}")

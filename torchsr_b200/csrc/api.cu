@@ -258,19 +258,40 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   p.halo = 0;
   if (use_halo() && allow_persistent && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC &&
       d.stride == 1 && d.num_taps == 9 && d.lower_h == -1 && d.lower_w == -1 && d.Ho == d.H && d.Wo == d.W &&
-      d.block_k == 64 && (d.C - d.a_c0) % 64 == 0 && d.W >= 16 && d.W + 2 <= 128 && 2 * p.acc_cols <= 512) {
+      d.block_k == 64 && (d.C - d.a_c0) % 64 == 0 && d.W >= 8 && d.H >= 4 && 2 * p.acc_cols <= 512) {
     bool taps_ok = true;
     for (int t = 0; t < 9; ++t) taps_ok = taps_ok && (d.tap_off[t] >> 8) <= 2 && (d.tap_off[t] & 0xFF) <= 2;
-    const int pw = static_cast<int>(d.W) + 2;
-    int th = 128 / pw;
-    if (th > d.H) th = static_cast<int>(d.H);
+    // Strip geometry: a tile is th rows x (pw - 2) columns of one image, pw * th <= 128 accumulator rows. Pick the
+    // patch width that wastes the fewest accumulator rows, weighing in the bytes of the patch it has to fetch.
+    int pw = 0, th = 0, strips = 0, tiles_y = 0;
+    {
+      long best_tiles = 0;
+      const int max_pw = d.W + 2 < 128 ? static_cast<int>(d.W) + 2 : 128;
+      for (int cand = 6; cand <= max_pw; ++cand) {
+        const int sw = cand - 2;
+        int c_th = 128 / cand;
+        if (c_th > d.H) c_th = static_cast<int>(d.H);
+        if (c_th < 1) continue;
+        const int c_strips = static_cast<int>((d.W + sw - 1) / sw);
+        const int c_ty = static_cast<int>((d.H + c_th - 1) / c_th);
+        // cost ~ tiles x (accumulator rows + 0.15 x patch positions): tile count first, patch traffic second
+        const long n_tiles = static_cast<long>(c_strips) * c_ty * (20 * 128 + 3 * (c_th + 2) * cand);
+        if (pw == 0 || n_tiles <= best_tiles) {
+          best_tiles = n_tiles;
+          pw = cand;
+          th = c_th;
+          strips = c_strips;
+          tiles_y = c_ty;
+        }
+      }
+    }
     const uint32_t b_bytes = static_cast<uint32_t>(d.block_n) * 64 * 2;
     const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
     const uint32_t patch_tx = static_cast<uint32_t>((th + 2) * pw * 128);
     const uint32_t patch_alloc = (static_cast<uint32_t>((128 + 2 * pw + 2) * 128) + 1023u) & ~1023u;
     const size_t budget = 227 * 1024 - 1024 - 13312 - 1024;
     if (taps_ok && th >= 1 && b_res % 1024 == 0 && b_res + 2 * static_cast<size_t>(patch_alloc) <= budget) {
-      const int tiles_per_img = static_cast<int>((d.H + th - 1) / th);
+      const int tiles_per_img = strips * tiles_y;
       const int tiles = tiles_per_img * static_cast<int>(d.N);
       const int n_ctas = 148 / L->tiles_n > 0 ? 148 / L->tiles_n : 1;
       int st = static_cast<int>((budget - b_res) / patch_alloc);
@@ -290,6 +311,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
       p.halo_th = th;
       p.halo_pw = pw;
       p.halo_tiles_per_img = tiles_per_img;
+      p.halo_strips = strips;
       p.halo_H = static_cast<int>(d.H);
       p.halo_W = static_cast<int>(d.W);
       p.persistent = tiles < n_ctas ? tiles : n_ctas;

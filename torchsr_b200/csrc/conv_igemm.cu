@@ -168,19 +168,22 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
     if (PERS && p.halo) {
       // one tiled load per 64-channel chunk: the (halo_th + 2) x halo_pw input patch of this tile, origin (-1, -1)
       const int n_img = tile_m / p.halo_tiles_per_img;
-      const int hrow0 = (tile_m - n_img * p.halo_tiles_per_img) * p.halo_th - 1;
+      const int t_img = tile_m - n_img * p.halo_tiles_per_img;
+      const int t_y = t_img / p.halo_strips;
+      const int hrow0 = t_y * p.halo_th - 1;
+      const int wcol0 = (t_img - t_y * p.halo_strips) * (p.halo_pw - 2) - 1;
       for (int kc = 0; kc < kc_per_tap; ++kc) {
         if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
         const uint32_t full = bar_full + 8 * s;
-        if (elect_one()) {
-          if (p.debug & 4) {
+        if (FAST ? leader : elect_one()) {
+          if (!FAST && (p.debug & 4)) {
             mbar_arrive(full);      // attribution run: no activation traffic, the MMAs read whatever the stage holds
           } else {
             mbar_arrive_expect_tx(full, p.a_bytes);
-            tma_load_tile_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, -1, hrow0, n_img);
+            tma_load_tile_4d(dst, &p.tmA, full, p.a_c0 + kc * block_k, wcol0, hrow0, n_img);
           }
         }
-        __syncwarp();
+        if (!FAST) __syncwarp();
         dst += stage_bytes;
         if (++s == stages) {
           s = 0;
@@ -344,6 +347,35 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as) * p.acc_cols;
     uint32_t acc = 0, boff = 0;
+    if (PERS && FAST && p.halo) {
+      // Lean halo loop: per 64-channel chunk nine 4-step UMMA groups (one per tap) read nine shifted windows of the
+      // patch; window and weight-tile offsets are loop invariants.
+      const uint32_t kcpt = static_cast<uint32_t>(p.kc_per_tap);
+      const uint64_t a_desc0 = (static_cast<uint64_t>(a_hi) << 32) | a_lo0;
+      const uint64_t b_desc0 = (static_cast<uint64_t>(b_hi) << 32) | b_lo0;
+      for (uint32_t kc = 0; kc < kcpt; ++kc) {
+        if (!mbar_wait(bar_full + 8 * s, ph, p.epi.err, 2)) return;
+        tc_fence_after();
+        if (leader) {
+          const uint64_t ad = a_desc0 + static_cast<uint32_t>(s) * stage16;
+          const uint64_t bd = b_desc0 + kc * b16;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t off = p.tap_off[t];
+            const uint32_t win16 = ((off >> 8) * static_cast<uint32_t>(p.halo_pw) + (off & 0xFF)) * 8u;  // rows * 128 B / 16
+            umma_bf16_x4(d_tmem, ad + win16, bd + static_cast<uint32_t>(t) * kcpt * b16, idesc, t == 0 ? acc : 1u);
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        acc = 1;
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      if (leader) umma_commit(bar_acc_full + 8 * as);
+      continue;
+    }
     if (PERS && p.halo) {
       // per 64-channel chunk (one ring stage = one patch): nine taps = nine operand windows into the same patch
       const int kc_per_tap = p.kc_per_tap;
@@ -569,10 +601,13 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       if (PERS && p.halo) {
         // accumulator row -> (output row of the tile, position incl. the two discarded halo positions)
         n = tile_m / p.halo_tiles_per_img;
+        const int t_img = tile_m - n * p.halo_tiles_per_img;
+        const int t_y = t_img / p.halo_strips;
         const int orow = row / p.halo_pw;
-        wo = row - orow * p.halo_pw;
-        ho = (tile_m - n * p.halo_tiles_per_img) * p.halo_th + orow;
-        valid = wo < p.halo_W && orow < p.halo_th && ho < p.halo_H;
+        const int pos = row - orow * p.halo_pw;
+        wo = (t_img - t_y * p.halo_strips) * (p.halo_pw - 2) + pos;
+        ho = t_y * p.halo_th + orow;
+        valid = pos < p.halo_pw - 2 && wo < p.halo_W && orow < p.halo_th && ho < p.halo_H;
         m = (n * p.halo_H + ho) * p.halo_W + wo;
       } else {
         const int hw = p.Ho * p.Wo;

@@ -90,10 +90,13 @@ struct ConvParams {
   // (zero-filled outside the image) and the nine taps are nine UMMA operands that start (dy*halo_pw + dx) rows into
   // that patch - instead of nine im2col loads of 128 separate 128-byte rows each. Outputs at the two halo positions of
   // every row are computed and discarded. tmA then holds the tiled map.
+  // The image is cut into vertical strips of halo_sw = halo_pw - 2 output columns, so any image width works and the
+  // patch stays small: a tile is halo_th rows of one strip, tiles of an image are numbered strip-fastest.
   int halo;              // 0 / 1
-  int halo_th, halo_pw;  // output rows per tile, positions per row
+  int halo_th, halo_pw;  // output rows per tile, patch positions per row (strip width + 2)
   int halo_tiles_per_img;
   int halo_H, halo_W;    // image size (output == input size)
+  int halo_strips;       // strips per image row: ceil(W / (halo_pw - 2))
   int w_static;    // the B operand is not written by any kernel of the enclosing stream segment (real weights)
   int debug;       // attribution experiments only (TSR_CONV_DEBUG bits, tools/trace_conv.py), 0 in production: 1 = the
                    // epilogue skips the accumulator read-out and the stores, 2 = it computes but does not store,

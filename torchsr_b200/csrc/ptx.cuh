@@ -131,6 +131,21 @@ __device__ __forceinline__ void umma_bf16_x4_commit(uint32_t tmem_d, uint64_t ad
         "l"(adesc + 4), "l"(bdesc + 4), "l"(adesc + 6), "l"(bdesc + 6)
       : "memory");
 }
+// Same four steps without the commit (halo mode issues nine of these per stage, one per filter tap).
+__device__ __forceinline__ void umma_bf16_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %4, %4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %5, %6, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %7, %8, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %9, %10, %3, t;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "l"(adesc + 2), "l"(bdesc + 2),
+        "l"(adesc + 4), "l"(bdesc + 4), "l"(adesc + 6), "l"(bdesc + 6)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
