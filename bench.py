@@ -188,7 +188,7 @@ CONV_IGEMM_GFLOP_PER_CROP_VGG = 21.50
 
 
 def conv_kernel_roofline(trainer, lr_d, hr_d, batch, pk, vgg_ours):
-    """The dominant kernel (conv_igemm_kernel: ~49 % of the step's launch time with its persistent / grouped variants, profiles/r01c_ncu_launches_step.csv)
+    """The dominant kernel (conv_igemm_kernel with its persistent / grouped variants: the largest share of the step's launch time, profiles/r01d_ncu_launches_step.csv)
     over ALL of its launches in one training step: every distinct conv / GEMM descriptor of the programs a step
     executes is replayed 20x back to back (CUDA events on the launching stream) and weighted by how often the step
     runs it; achieved = algorithmic FLOPs of those launches / summed launch time."""
@@ -351,14 +351,18 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["sustained"], "unit": "TFLOP/s",
-                     "frac": ach / pk["sustained"], "traffic": None,
+                     "frac": ach / pk["sustained"],
+                     # dram__bytes_read + dram__bytes_write of one captured launch of the dominant kernel (persistent
+                     # 3x3 64->256 conv at 48x48, B=16: profiles/r01d_ncu_full_conv_summary.csv, ID 0); its operands are
+                     # 4.7 MB of activations + 0.3 MB of weights read, the 18.9 MB output stays in the 126 MB L2
+                     "traffic": 5.12e6,
                      "what": "whole step: crops/s x 21.73 GFLOP/crop (G+D algorithmic minimum, SURVEY 8d) per GPU vs the "
                              f"{pk['source']} sustained bf16 peak; with the VGG19 FLOPs (+21.50/crop) "
                              f"the step sustains {value * (GFLOP_PER_CROP_GD + GFLOP_PER_CROP_VGG) / 1e3 / world:.1f} TFLOP/s",
                      "dominant_kernel": dom, "trunk_conv_only": kern,
-                     "ncu": "profiles/r01c_ncu_full_conv_igemm_summary.csv, r01c_ncu_full_conv_persistent_summary.csv (dram "
-                            "bytes, tensor-pipe activity, L2->SM bytes per launch), r01c_ncu_launches_step.csv (every "
-                            "launch of one step)"},
+                     "ncu": "profiles/r01d_ncu_full_conv_summary.csv (dram bytes, tensor-pipe activity, L2->SM bytes per "
+                            "launch; r01c_* hold the captures before the lean main loops), r01d_ncu_launches_step.csv "
+                            "(every launch of one step), r01d_conv_attribution.md (what bounds the kernel)"},
     }
     if not args.no_cpu_baseline and world == 1:
         cps, spstep, threads = cpu_port_crops_per_sec(args.batch, 3, 1, not args.no_vgg)

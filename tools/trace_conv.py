@@ -98,11 +98,11 @@ def main():
                 row.append(time_it(shape))
             os.environ["TSR_CONV_DEBUG"] = "0"
             if os.environ.get("TRACE_CONV_QUICK"):
-                print(f"{name} bn={shape[5]:3d} halo={halo}: {row[0]:7.2f} us ({gflop / row[0]:6.1f} TF/s)")
+                print(f"{name} bn={shape[5]:3d} halo={halo}: {row[0]:7.2f} us ({gflop / row[0] * 1e3:6.1f} TF/s)")
                 continue
             tr = trace_it(shape)
             chunks = " ".join(f"[{int(a)}->{int(b)}]" for a, b in tr["chunks"])
-            print(f"{name} bn={shape[5]:3d} halo={halo}: {row[0]:7.2f} us ({gflop / row[0] * 1e-3 * 1e3:6.1f} TF/s) | no-store "
+            print(f"{name} bn={shape[5]:3d} halo={halo}: {row[0]:7.2f} us ({gflop / row[0] * 1e3:6.1f} TF/s) | no-store "
                   f"{row[1]:7.2f} | no-epi {row[2]:7.2f} | no-epi,no-TMA {row[3]:7.2f} | no-epi,no-MMA {row[4]:7.2f} | "
                   f"sync only {row[5]:7.2f} | ctas {tr['ctas']} setup {int(tr['setup'])} "
                   f"acc_full {int(tr['acc_full'])} chunks(ld->st) {chunks} epi_done {int(tr['epi_done'])} exit {int(tr['exit'])}")
