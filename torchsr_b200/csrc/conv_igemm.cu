@@ -6,7 +6,12 @@
 // 128-pixel x block_k-channel box per (tap, channel chunk), halo pixels zero-filled by the TMA unit.
 // B (packed weights, [tap][Cout][Cin] bf16, K-major) is fetched by tiled TMA. Both land in 128B/64B/32B
 // swizzled shared memory and feed tcgen05.mma (M=128, N=block_n, K=16) with the fp32 accumulator in TMEM.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue (tcgen05.ld).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue (tcgen05.ld; two warps
+// per TMEM lane quadrant split the 16-column chunks).
+// Instantiations: conv_body<A_MODE, PERS, FAST>. PERS = persistent weight-stationary CTAs (large-M im2col convs), FAST =
+// lean producer / MMA loops for 64-channel K chunks without trace stamps or attribution hooks - the production path of
+// every 3x3 / 9x9 conv whose input has a multiple of 64 channels (profiles/r01d_conv_attribution.md explains why the
+// instruction count of those two single-warp loops sets the K-iteration rate).
 // The same kernel serves forward convs, stride-1 data gradients (flipped/transposed weight pack),
 // stride-2 data gradients (one launch per output parity class) and the Linear layers (a_mode 1/2, split-K).
 //
