@@ -132,3 +132,26 @@ def test_bucket_slices_cover_flat_gradient_once():
         assert all(hi - lo <= cap for lo, hi in sl)
         if early:
             assert sl[0][0] == early      # the tail (produced first in backward) is sent first
+
+
+def test_image_folder_pipeline_shapes_and_split(tmp_path):
+    """The minimal loader behind `torchsr train` (reference torchsr/dataset.py:55-136,279): 90/10 split, HR crops of the
+    model's crop size with /4 bicubic LR inputs in [0, 1], (LR, bicubic, HR) triples for evaluation."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from torchsr_b200.dataset import initialize_datasets
+    rng = np.random.default_rng(0)
+    for i in range(20):
+        Image.fromarray(rng.integers(0, 255, (100 + i, 130, 3), dtype=np.uint8)).save(tmp_path / f"im{i:02d}.png")
+    tl, el, n_train, n_test = initialize_datasets(str(tmp_path), 4, 96, dataset_multiplier=2, workers=0, seed=3)
+    assert (n_train, n_test) == (36, 2)
+    lr, hr = next(iter(tl))
+    assert lr.shape == (4, 3, 24, 24) and hr.shape == (4, 3, 96, 96) and lr.dtype == torch.float32
+    assert 0.0 <= float(lr.min()) and float(hr.max()) <= 1.0
+    assert len(tl) == 9                     # drop_last: 36 crops / 4
+    low, bic, high = next(iter(el))
+    assert low.shape == (2, 3, 24, 24) and bic.shape == (2, 3, 96, 96) and high.shape == (2, 3, 96, 96)
+    import pytest
+    with pytest.raises(RuntimeError):
+        initialize_datasets(str(tmp_path / "missing"), 4, 96, workers=0)
