@@ -5,7 +5,9 @@
 For each of the four networks: synthetic weights (synth.py) are loaded into the reference module, one training-mode
 forward + backward is run for a synthetic input and upstream gradient, and the fixture stores the input, the output,
 the BatchNorm buffers after the forward, the parameter shapes and a digest of every parameter gradient (L2 norm and
-the first 4 values). A fifth fixture records one full SRGANTrainer._gan_loop step (post-step parameter digests).
+the first 4 values). Step fixtures: one full SRGANTrainer._gan_loop step, one full ESRGANTrainer._gan_loop step
+(relativistic GAN, 23 RRDB blocks) and two PSNR-phase (pretrain) steps of each trainer - post-step parameter digests
+(and losses for the pretrain steps). `--steps-only` regenerates just the ESRGAN / pretrain step fixtures.
 """
 import json
 import os
