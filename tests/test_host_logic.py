@@ -95,7 +95,9 @@ from torchsr_b200.srgan.discriminator import Discriminator
 from torchsr_b200.esrgan.discriminator import Discriminator as ED
 from torchsr_b200.esrgan.generator import Generator as EG
 from torchsr_b200.srgan.residual import ResidualBlock, SubpixelConvolutionLayer
-for mod, shape, need_x in [(Generator(), (2, 3, 24, 24), False), (Discriminator(), (2, 3, 96, 96), True),
+from torchsr_b200.esrgan.residual import ResidualDenseBlock, ResidualInResidualDenseBlock
+for mod, shape, need_x in [(ResidualDenseBlock(), (2, 64, 8, 8), True), (ResidualInResidualDenseBlock(), (1, 64, 8, 8), True),
+                           (Generator(), (2, 3, 24, 24), False), (Discriminator(), (2, 3, 96, 96), True),
                            (ED(), (1, 3, 128, 128), True), (EG(num_rrdb_blocks=2), (1, 3, 16, 16), False),
                            (ResidualBlock(), (2, 64, 8, 8), True), (SubpixelConvolutionLayer(), (2, 64, 8, 8), True)]:
     x = torch.rand(*shape, requires_grad=need_x)

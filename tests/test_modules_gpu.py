@@ -42,6 +42,43 @@ def test_subpixel_stage():
     assert r["out"] <= 1e-2 and r["grad_worst"] <= 5e-2 and r["dx"] <= 5e-2, (r, errs)
 
 
+def _branch_gain(module, gain):
+    """The reference init (kaiming_normal * 0.1) makes a dense block's residual branch ~3 % of its output, below one
+    bf16 ulp of the identity path; the parity tests scale the weights up so that the branch is what gets compared."""
+    with torch.no_grad():
+        for m in module.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                m.weight.mul_(gain)
+                m.bias.copy_(torch.randn(m.bias.shape) * 0.05)
+
+
+@pytest.mark.parametrize("kind", ["rdb", "rrdb"])
+def test_esrgan_dense_blocks_standalone_residual_branch(kind):
+    """ResidualDenseBlock / ResidualInResidualDenseBlock called on their own (reference esrgan/residual.py:81-86,
+    124-129), teacher-forced on a bf16-representable input. The block output is dominated by the identity path
+    (SURVEY.md section 4), so the RESIDUAL BRANCH (out - x) is what is compared, plus every parameter gradient."""
+    import module_checks as MC
+    from torchsr_b200.esrgan.residual import ResidualDenseBlock, ResidualInResidualDenseBlock
+    torch.manual_seed(11)
+    m = ResidualDenseBlock() if kind == "rdb" else ResidualInResidualDenseBlock()
+    _branch_gain(m, 10.0 if kind == "rdb" else 15.0)
+    x = torch.randn(2, 64, 16, 16).bfloat16().float()
+    fn = MC.O.esrgan_rdb if kind == "rdb" else MC.O.esrgan_rrdb
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    r, errs = MC.check_module(m, lambda s_, x_, tr, buf: fn({("p." + k): v for k, v in s_.items()}, "p", x_), x,
+                              input_grad=True)
+    with torch.no_grad():
+        y_gpu = m(x.cuda()).cpu()
+        y_ref = fn({("p." + k): v for k, v in sd.items()}, "p", x)
+    ident = 1.0 if kind == "rdb" else 1.2      # RRDB: out = 1.2 x + 0.04 (c5_1 + c5_2 + c5_3)
+    branch = MC.rel_l2(y_gpu - ident * x, y_ref - ident * x)
+    share = float((y_ref - ident * x).norm() / y_ref.norm())
+    print(kind, "branch", branch, "branch share of output", share, r)
+    assert share > 0.2, share
+    assert branch <= 2e-2, (branch, r)
+    assert r["grad_median"] <= 3e-2 and r["grad_worst"] <= 0.15 and r["dx"] <= 5e-2, (r, sorted(errs.items(), key=lambda kv: -kv[1])[:5])
+
+
 def test_srgan_generator_vs_oracle():
     MC, SG, SD, EG, ED = _mods()
     torch.manual_seed(3)

@@ -199,21 +199,24 @@ class _IdentityRec:
         self.w_t.view(C, C).copy_(torch.eye(C, dtype=BF16, device=plan.device))
 
 
-def define_standalone(m, plan: Plan, shape, stage_fn):
+def define_standalone(m, plan: Plan, shape, stage_fn, xin: Act = None, gy: Act = None):
     """A building block called on its own (e.g. ResidualBlock()(x)): NCHW fp32 <-> NHWC bf16 conversion kernels at
-    both ends, the block's stage in between."""
+    both ends, the block's stage in between. `xin` / `gy` override where the converted input / output gradient live
+    (channel slices of wider buffers for the ESRGAN dense blocks)."""
     B, C, H, W = shape
     if C % 16:
         raise RuntimeError(f"{type(m).__name__} needs a channel count that is a multiple of 16, got {C}")
-    xin = plan.act("in", B, H, W, C)
+    if xin is None:
+        xin = plan.act("in", B, H, W, C)
     y = stage_fn(xin)
-    gy = plan.act("gy", y.B, y.H, y.W, y.C)
+    if gy is None:
+        gy = plan.act("gy", y.B, y.H, y.W, y.C)
     if y.hook is not None:
         ident = _IdentityRec(plan, y.C)
         plan.tape.append(lambda bp, g, want_x, want_w: plan.conv_dgrad(bp, "hook", ident, g, y))
 
     def input_fn(x):
-        ops.run_now(ops.elt(L.E_NCHW2NHWC, p=[x, xin.t], i=[B, C, H, W, C, 0]))
+        ops.run_now(ops.elt(L.E_NCHW2NHWC, p=[x, xin.t], i=[B, C, H, W, xin.ld, xin.c0]))
 
     def output_fn():
         out = torch.empty(B, y.C, y.H, y.W, dtype=F32, device=plan.device)
@@ -221,7 +224,7 @@ def define_standalone(m, plan: Plan, shape, stage_fn):
         return out
 
     def ingest_fn(gout):
-        ops.run_now(ops.elt(L.E_NCHW2NHWC, p=[gout, gy.t], i=[B, y.C, y.H, y.W, y.C, 0]))
+        ops.run_now(ops.elt(L.E_NCHW2NHWC, p=[gout, gy.t], i=[B, y.C, y.H, y.W, gy.ld, gy.c0]))
         return gy
 
     def grad_input_fn():
@@ -368,13 +371,104 @@ def esrgan_generator_records(m) -> List[ConvRec]:
     recs = [ConvRec("conv1", m.conv1, "fullk", need_dgrad=False)]
     for b, blk in enumerate(m.blocks):
         for r in RDB_NAMES:
-            rdb = getattr(blk, r)
-            for k in range(1, 5):
-                recs.append(ConvRec(f"blocks.{b}.{r}.conv{k}.0", getattr(rdb, f"conv{k}")[0]))
-            recs.append(ConvRec(f"blocks.{b}.{r}.conv5", rdb.conv5))
+            recs += rdb_records(f"blocks.{b}.{r}.", getattr(blk, r))
     recs += [ConvRec("conv2", m.conv2), ConvRec("upsample1", m.upsample1), ConvRec("upsample2", m.upsample2),
              ConvRec("conv3.0", m.conv3[0]), ConvRec("conv4", m.conv4)]
     return recs
+
+
+RDB_GRAD_RING = 5   # ring of gradient buffers: an RRDB's incoming gradient must outlive its three RDB backward passes
+
+
+def rdb_records(prefix: str, rdb) -> List[ConvRec]:
+    """The five convs of one ResidualDenseBlock (conv1-4 are nn.Sequential(conv, LeakyReLU) -> '.0.', conv5 is bare)."""
+    recs = [ConvRec(f"{prefix}conv{k}.0", getattr(rdb, f"conv{k}")[0]) for k in range(1, 5)]
+    recs.append(ConvRec(f"{prefix}conv5", rdb.conv5))
+    return recs
+
+
+def rdb_chain(plan: Plan, fwd, R: Dict[str, ConvRec], names: List[str], B: int, H: int, W: int, rrdb: bool):
+    """A chain of ResidualDenseBlocks (torchsr/esrgan/residual.py:81-86), every three of them closed by the RRDB
+    residual when `rrdb` (:124-129). Zero-copy dense concatenation: RDB j owns the [B,H,W,192] NHWC buffer `cat{j}`;
+    conv_k reads the channel prefix [0, 64+32(k-1)) and writes its 32 channels right behind it, conv5 reads all 192
+    and writes (conv5+b)*0.2 + x into the first 64 channels of the NEXT buffer (for the third RDB of an RRDB the outer
+    `*0.2 + x` is folded into the same epilogue: (conv5+b)*0.04 + 0.2*x_rdb3 + x_rrdb). The caller fills
+    cat0[..., :64]; the chain's output is cat{len(names)}[..., :64]. Backward mirrors this with [B,H,W,192] gradient
+    buffers that the data-gradient convs accumulate into in place; the incoming gradient must live in a 192-wide
+    buffer too. `names[j]` is the record prefix of RDB j ('' or 'blocks.3.RDB2')."""
+    C, G, CT = 64, 32, 192
+    store = plan.grads
+    n_rdb = len(names)
+    assert not rrdb or n_rdb % 3 == 0
+
+    def cat_buf(j):
+        return plan.buf(f"cat{j}", B * H * W * CT, BF16)
+
+    def sl(t, c, c0=0):
+        return Act(t, B, H, W, c, ld=CT, c0=c0)
+
+    def gbuf(i):
+        return plan.buf(f"dcat{i % RDB_GRAD_RING}", B * H * W * CT, BF16)
+
+    def rn(name, leaf):
+        return f"{name}.{leaf}" if name else leaf
+
+    for j in range(n_rdb):
+        r = j % 3 if rrdb else 0
+        name = names[j]
+        cat, nxt = cat_buf(j), cat_buf(j + 1)
+        rk = [R[rn(name, f"conv{k}.0")] for k in range(1, 5)]
+        r5 = R[rn(name, "conv5")]
+        for k in range(1, 5):
+            plan.conv_fwd(fwd, rk[k - 1], sl(cat, C + G * (k - 1)), sl(cat, G, C + G * (k - 1)), act=L.ACT_LEAKY)
+        x_rdb = sl(cat, C)
+        if rrdb and r == 2:
+            x_rrdb = sl(cat_buf(j - 2), C)
+            plan.conv_fwd(fwd, r5, sl(cat, CT), sl(nxt, C), acc_scale=0.04, res=x_rdb, res_scale=0.2, res2=x_rrdb,
+                          res2_scale=1.0)
+        else:
+            plan.conv_fwd(fwd, r5, sl(cat, CT), sl(nxt, C), acc_scale=0.2, res=x_rdb)
+
+        def bwd(bp, g, want_x, want_w, j=j, r=r, name=name, cat=cat, rk=rk, r5=r5):
+            # g: gradient w.r.t. this RDB's output (first 64 channels of a 192-wide buffer). For the third RDB of an
+            # RRDB it is the RRDB-level gradient: the block output was 0.2 * rdb3_out + x_rrdb.
+            outer = 0.2 if (rrdb and r == 2) else 1.0
+            if rrdb and r == 2:
+                plan.slots[f"rrdb{j // 3}"] = g
+            dcat = gbuf(n_rdb - j)
+            d5 = plan.norm_act_bwd(bp, rn(name, "c5"), g, g, act=L.ACT_NONE, gscale=0.2 * outer,
+                                   bias_grad=store.grad_slice(r5.bias), want_w=want_w)
+            if want_w:
+                plan.conv_wgrad(bp, r5, sl(cat, CT), d5)
+            plan.conv_dgrad(bp, rn(name, "c5"), r5, d5, sl(cat, CT), out=sl(dcat, CT), res=sl(g.t, C), res_scale=outer,
+                            res_cols=C)
+            for k in range(4, 0, -1):
+                ck = C + G * (k - 1)
+                dk = plan.norm_act_bwd(bp, rn(name, f"c{k}"), sl(dcat, G, ck), sl(cat, G, ck), act=L.ACT_LEAKY,
+                                       bias_grad=store.grad_slice(rk[k - 1].bias), want_w=want_w)
+                if want_w:
+                    plan.conv_wgrad(bp, rk[k - 1], sl(cat, ck), dk)
+                last = rrdb and k == 1 and r == 0
+                plan.conv_dgrad(bp, rn(name, f"c{k}"), rk[k - 1], dk, sl(cat, ck), out=sl(dcat, ck), res=sl(dcat, ck),
+                                res2=sl(plan.slots[f"rrdb{j // 3}"].t, ck) if last else None)
+            return sl(dcat, C)
+
+        plan.tape.append(bwd)
+    return sl(cat_buf(n_rdb), C)
+
+
+def define_rdb_standalone(m, plan: Plan, shape, names: List[str], rrdb: bool):
+    """ResidualDenseBlock()(x) / ResidualInResidualDenseBlock()(x) on their own (torchsr/esrgan/residual.py:81-86,
+    124-129): layout conversion kernels around rdb_chain; input, output and their gradients live in 192-wide buffers
+    because the chain addresses them that way."""
+    B, C, H, W = shape
+    if C != 64:
+        raise RuntimeError(f"{type(m).__name__} on the B200 path is built for 64 channels (growth 32), got {C}")
+    R = _recs(plan)
+    CT = 192
+    xin = Act(plan.buf("cat0", B * H * W * CT, BF16), B, H, W, C, ld=CT)
+    gy = Act(plan.buf("gy192", B * H * W * CT, BF16), B, H, W, C, ld=CT)
+    define_standalone(m, plan, shape, lambda x: rdb_chain(plan, plan.fwd, R, names, B, H, W, rrdb), xin=xin, gy=gy)
 
 
 def define_esrgan_generator(m, plan: Plan, shape):
@@ -417,52 +511,11 @@ def define_esrgan_generator(m, plan: Plan, shape):
     plan.tape.append(bwd_conv1)
 
     # ---- 23 x 3 dense blocks
-    NG = 5   # ring of gradient buffers: an RRDB's incoming gradient must outlive its three RDB backward passes
+    names = [f"blocks.{b}.{r}" for b in range(n_rrdb) for r in RDB_NAMES]
+    rdb_chain(plan, fwd, R, names, B, H, W, rrdb=True)
 
     def gbuf(i):
-        return plan.buf(f"dcat{i % NG}", B * H * W * CT, BF16)
-
-    for j in range(n_rdb):
-        b, r = divmod(j, 3)
-        name = f"blocks.{b}.{RDB_NAMES[r]}"
-        cat, nxt = cat_buf(j), cat_buf(j + 1)
-        rk = [R[f"{name}.conv{k}.0"] for k in range(1, 5)]
-        r5 = R[f"{name}.conv5"]
-        for k in range(1, 5):
-            plan.conv_fwd(fwd, rk[k - 1], sl(cat, C + G * (k - 1)), sl(cat, G, C + G * (k - 1)), act=L.ACT_LEAKY)
-        x_rdb = sl(cat, C)
-        if r == 2:
-            x_rrdb = sl(cat_buf(j - 2), C)
-            plan.conv_fwd(fwd, r5, sl(cat, CT), sl(nxt, C), acc_scale=0.04, res=x_rdb, res_scale=0.2, res2=x_rrdb,
-                          res2_scale=1.0)
-        else:
-            plan.conv_fwd(fwd, r5, sl(cat, CT), sl(nxt, C), acc_scale=0.2, res=x_rdb)
-
-        def bwd(bp, g, want_x, want_w, j=j, r=r, name=name, cat=cat, rk=rk, r5=r5):
-            # g: gradient w.r.t. this RDB's output (first 64 channels of a 192-wide buffer). For the third RDB of an
-            # RRDB it is the RRDB-level gradient: the block output was 0.2 * rdb3_out + x_rrdb.
-            outer = 0.2 if r == 2 else 1.0
-            if r == 2:
-                plan.slots[f"rrdb{j // 3}"] = g
-            dcat = gbuf(n_rdb - j)
-            d5 = plan.norm_act_bwd(bp, name + ".c5", g, g, act=L.ACT_NONE, gscale=0.2 * outer,
-                                   bias_grad=store.grad_slice(r5.bias), want_w=want_w)
-            if want_w:
-                plan.conv_wgrad(bp, r5, sl(cat, CT), d5)
-            plan.conv_dgrad(bp, name + ".c5", r5, d5, sl(cat, CT), out=sl(dcat, CT), res=sl(g.t, C), res_scale=outer,
-                            res_cols=C)
-            for k in range(4, 0, -1):
-                ck = C + G * (k - 1)
-                dk = plan.norm_act_bwd(bp, f"{name}.c{k}", sl(dcat, G, ck), sl(cat, G, ck), act=L.ACT_LEAKY,
-                                       bias_grad=store.grad_slice(rk[k - 1].bias), want_w=want_w)
-                if want_w:
-                    plan.conv_wgrad(bp, rk[k - 1], sl(cat, ck), dk)
-                last = k == 1 and r == 0
-                plan.conv_dgrad(bp, f"{name}.c{k}", rk[k - 1], dk, sl(cat, ck), out=sl(dcat, ck), res=sl(dcat, ck),
-                                res2=sl(plan.slots[f"rrdb{j // 3}"].t, ck) if last else None)
-            return sl(dcat, C)
-
-        plan.tape.append(bwd)
+        return plan.buf(f"dcat{i % RDB_GRAD_RING}", B * H * W * CT, BF16)
 
     trunk = sl(cat_buf(n_rdb), C)
 
