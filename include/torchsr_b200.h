@@ -101,6 +101,25 @@ typedef struct tsr_conv_desc {
   int32_t* tile_counters;
   int32_t ws_ld, _pad1;
   int64_t* trace;           /* optional debug: per-CTA clock64 stamps [grid][40] (null in production) */
+  /* BatchNorm statistics groups (one discriminator pass over the real | fake batches, srgan/trainer.py:446-447): rows
+     [0, group_rows) are group 0, the rest group 1; 0 = one group. Multiple of 32. stats_partial / bnr_coef / bnf_coef
+     then hold one block per group. */
+  int32_t group_rows;
+  /* fused BatchNorm forward (nn.BatchNorm2d after the conv, srgan/residual.py:65,68, discriminator.py:36-60):
+     bnf_mode 1 = training (batch statistics, grid barrier inside the launch: needs stats_partial, bnf_counter and a
+     co-resident grid - tsr_conv_bnf_capacity), 2 = eval (running statistics). out receives act(BN(acc)) + res,
+     out_preact (optional) the raw bf16 conv output for backward. */
+  int32_t bnf_mode;
+  uint32_t* bnf_counter;    /* [cout_pad / block_n] arrival counters, zero at launch */
+  const float* bnf_gamma;   /* [bnf_c] */
+  const float* bnf_beta;
+  float* bnf_rm;            /* running_mean, updated in training mode (may be null) */
+  float* bnf_rv;
+  int64_t* bnf_nbt;         /* num_batches_tracked, += number of groups */
+  float* bnf_coef;          /* out, training mode: [groups][4][bnf_c] scale, shift, mean, invstd */
+  int64_t bnf_count;        /* rows per statistics group */
+  int32_t bnf_c, _pad2;
+  float bnf_eps, bnf_momentum;
 } tsr_conv_desc_t;
 
 typedef struct tsr_wgrad_desc {
@@ -159,7 +178,9 @@ enum tsr_elt_kind {
   TSR_E_MAXPOOL2_BWD = 25,
   TSR_E_CAST = 26,
   TSR_E_ADAM = 27,
-  TSR_E_CHANSUM_NCHW = 28
+  TSR_E_CHANSUM_NCHW = 28,
+  TSR_E_GAN_LOSS = 29,   /* BCE / BCE-with-logits / relativistic-average GAN criteria, value + gradient, one launch */
+  TSR_E_AXPBY_F32 = 30   /* out = a * (*scalar) * x + b * y on fp32 vectors */
 };
 
 /* weight pack / grad unpack index maps (TSR_E_PACK_W / TSR_E_UNPACK_G table entries) */
@@ -215,6 +236,9 @@ const char* tsr_last_error(void);
 int tsr_version(void);
 
 int tsr_conv(const tsr_conv_desc_t* d, void* stream);
+/* number of CTAs of this conv's launch and how many the device can hold at once for its kernel / shared-memory
+   footprint; the fused training BatchNorm (bnf_mode 1) requires ctas <= capacity. Returns 0 or a negative error. */
+int tsr_conv_bnf_capacity(const tsr_conv_desc_t* d, int* ctas, int* capacity);
 int tsr_wgrad(const tsr_wgrad_desc_t* d, void* stream);
 int tsr_elt(const tsr_elt_desc_t* d, void* stream);
 

@@ -139,10 +139,7 @@ def check_conv_fwd(B=2, H=24, W=24, Cin=64, Cout=64, k=3, stride=1, block_n=None
         out = torch.full((B, 2 * Ho, 2 * Wo, c4), float("nan"), device=DEV,
                          dtype=torch.float32 if out_f32 else torch.bfloat16)
         os_n, os_h, os_w = 4 * Ho * Wo * c4, 2 * Wo * c4, c4
-        bias_dev = None
-        if bias:
-            rows = torch.arange(Cout)
-            bias_dev = b[4 * (rows % c4) + rows // c4].contiguous().to(DEV)
+        bias_dev = b.to(DEV) if bias else None     # the epilogue indexes the OIHW-order bias through the shuffle map
     else:
         out = torch.full((B, Ho, Wo, Cout), float("nan"), device=DEV,
                          dtype=torch.float32 if out_f32 else torch.bfloat16)

@@ -113,6 +113,27 @@ for mod, shape, need_x in [(ResidualDenseBlock(), (2, 64, 8, 8), True), (Residua
     assert len(plans) == 2, plans.keys()
     for key, pool in plans.items():
         assert len(pool) == 1 and not pool[0].busy
+# one discriminator pass over (real | fake) with BatchNorm statistics per half, fused and two-launch BatchNorm paths
+from torchsr_b200 import engine, losses
+for fuse in (True, False):
+    engine.FUSE_BN_FWD = fuse
+    for D, n, size in ((Discriminator(), 8, 96), (ED(), 2, 128), (Discriminator(), 3, 96)):
+        a, b = torch.rand(n, 3, size, size), torch.rand(n, 3, size, size, requires_grad=True)
+        pa, pb = D.forward_pair(a, b)
+        assert pa.shape == (n, 1) and pb.shape == (n, 1)
+        losses.bce(pa, 1.0, pb, 0.0).backward()
+        assert all(p.grad is not None for p in D.parameters()) and b.grad.shape == b.shape
+        paired = [k for k in D._tsr["plans"] if len(k) == 3]
+        assert (len(paired) == 1) == (n != 3), (n, D._tsr["plans"].keys())      # 3 x 36 rows per half: falls back
+engine.FUSE_BN_FWD = True
+x = torch.rand(4, 3, 8, 8, requires_grad=True)
+for fn in (lambda: losses.mse(x, torch.rand(4, 3, 8, 8)), lambda: losses.l1(x, torch.rand(4, 3, 8, 8), scale=0.01),
+           lambda: losses.total(losses.relativistic_d(x[:, :1, 0, 0], x[:, 1:2, 0, 0]),
+                                losses.relativistic_g(x[:, :1, 0, 0], x[:, 1:2, 0, 0].detach(), scale=0.005))):
+    out = fn()
+    assert out.dim() == 0
+    out.backward(torch.ones(()))
+    assert x.grad.shape == x.shape
 print("DRY_OK")
 """
 
@@ -157,3 +178,30 @@ def test_image_folder_pipeline_shapes_and_split(tmp_path):
     import pytest
     with pytest.raises(RuntimeError):
         initialize_datasets(str(tmp_path / "missing"), 4, 96, workers=0)
+
+
+def test_trainer_resumes_at_checkpoint_epoch(tmp_path, monkeypatch):
+    """reference srgan/trainer.py:357-364, :483-499: a restarted job continues at checkpoint['epoch'] (it does not
+    repeat finished epochs), a GAN phase without its own checkpoint starts at 1 from the PSNR-phase weights."""
+    from argparse import Namespace
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("TORCHSR_VGG_WEIGHTS", "random")
+    from torchsr_b200.srgan.trainer import SRGANTrainer
+    args = Namespace(disable_amp=False, batch_size=2, epochs=8, pretrain_epochs=4, gan_checkpoint=None,
+                     psnr_checkpoint=None, skip_image_save=True, local_rank=-1, rank=-1, world_size=1)
+    tr = SRGANTrainer(torch.device("cpu"), args, [], [], 0, 0, False)
+    seen = []
+    monkeypatch.setattr(tr, "_test", lambda epoch, phase, step: seen.append((phase, epoch)))
+    marker = {k: torch.full_like(v, 0.5) if v.is_floating_point() else v for k, v in tr.generator.state_dict().items()}
+    torch.save({"epoch": 3, "phase": "srgan-psnr", "state": {"module." + k: v for k, v in marker.items()}},
+               "srgan-psnr-latest.pth")
+    tr._pretrain()
+    assert seen == [("srgan-psnr", 3), ("srgan-psnr", 4)], seen
+    assert float(tr.generator.conv3.weight.mean()) == 0.5          # weights restored (module. prefix stripped)
+    seen.clear()
+    tr._gan_train()                                                 # no GAN checkpoint: epoch 1, PSNR weights
+    assert [e for _, e in seen] == list(range(1, 9)), seen
+    torch.save({"epoch": 7, "phase": "srgan-gan", "state": marker}, "srgan-gan-latest.pth")
+    seen.clear()
+    tr._gan_train()
+    assert seen == [("srgan-gan", 7), ("srgan-gan", 8)], seen

@@ -21,7 +21,19 @@ def _mods():
     return MC, SG, SD, EG, ED
 
 
-def test_residual_block_stage():
+@pytest.fixture
+def bn_fuse(request, monkeypatch):
+    """Runs a test with the fused conv+BatchNorm launch (default) or with the two-launch path (conv, then bn_act)."""
+    from torchsr_b200 import engine
+    monkeypatch.setattr(engine, "FUSE_BN_FWD", bool(request.param))
+    return bool(request.param)
+
+
+BN_PATHS = pytest.mark.parametrize("bn_fuse", [True, False], indirect=True, ids=["bn-fused", "bn-two-launch"])
+
+
+@BN_PATHS
+def test_residual_block_stage(bn_fuse):
     import module_checks as MC
     from torchsr_b200.srgan.residual import ResidualBlock
     torch.manual_seed(1)
@@ -89,7 +101,8 @@ def test_srgan_generator_vs_oracle():
     assert r["grad_median"] <= 0.2, (r, sorted(errs.items(), key=lambda kv: -kv[1])[:5])
 
 
-def test_srgan_discriminator_vs_oracle():
+@BN_PATHS
+def test_srgan_discriminator_vs_oracle(bn_fuse):
     MC, SG, SD, EG, ED = _mods()
     torch.manual_seed(4)
     D = SD()
@@ -171,7 +184,175 @@ def test_discriminator_two_outstanding_forwards_and_frozen_pass():
     assert x.grad is not None and all(p.grad is None for p in D.parameters())
 
 
-def test_eval_mode_no_grad_and_large_image_psnr():
+def _pair_case(D_cls, n, size, fuse, monkeypatch, oracle_fn):
+    """forward_pair(a, b) against two separate calls of an identical module AND against the oracle's two calls."""
+    import module_checks as MC
+    from torchsr_b200 import engine
+    monkeypatch.setattr(engine, "FUSE_BN_FWD", fuse)
+    torch.manual_seed(21)
+    D1 = D_cls()
+    MC.randomize_bn(D1)
+    sd = {k: v.clone() for k, v in D1.state_dict().items()}
+    D2 = D_cls()
+    D2.load_state_dict(sd)
+    D1, D2 = D1.cuda().train(), D2.cuda().train()
+    a, b = torch.rand(n, 3, size, size), torch.rand(n, 3, size, size)
+    xa1, xb1 = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    xa2, xb2 = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    pa1, pb1 = D1.forward_pair(xa1, xb1)
+    assert any(len(k) == 3 for k in D1._tsr["plans"]), "the paired plan was not used"
+    (pa1.sum() + 2 * pb1.sum()).backward()
+    pa2, pb2 = D2(xa2), D2(xb2)
+    (pa2.sum() + 2 * pb2.sum()).backward()
+    torch.cuda.synchronize()
+    r = {"pa": MC.rel_l2(pa1, pa2), "pb": MC.rel_l2(pb1, pb2), "dxa": MC.rel_l2(xa1.grad, xa2.grad),
+         "dxb": MC.rel_l2(xb1.grad, xb2.grad)}
+    s1, s2 = D1.state_dict(), D2.state_dict()
+    for k in s1:
+        if "num_batches" in k:
+            assert int(s1[k]) == int(s2[k]) == 2, k
+        elif "running" in k:
+            r["buf"] = max(r.get("buf", 0.0), MC.rel_l2(s1[k], s2[k]))
+    g = sorted(MC.rel_l2(p1.grad, p2.grad) for p1, p2 in zip(D1.parameters(), D2.parameters()))
+    r["grad_median"], r["grad_worst"] = g[len(g) // 2], g[-1]
+    # and against the oracle (two calls, shared buffers dict -> two running-statistics updates, a first)
+    osd = MC.O.with_grad(sd)
+    buf = {}
+    ra, rb = oracle_fn(osd, a, True, buf), oracle_fn(osd, b, True, buf)
+    (ra.sum() + 2 * rb.sum()).backward()
+    r["oracle_pa"], r["oracle_pb"] = MC.rel_l2(pa1, ra), MC.rel_l2(pb1, rb)
+    for k, v in buf.items():
+        if "running" in k:
+            r["oracle_buf"] = max(r.get("oracle_buf", 0.0), MC.rel_l2(s1[k.lstrip(".")], v))
+    ref = {k: v.grad for k, v in osd.items() if v.requires_grad}
+    r["oracle_grad_worst"], r["oracle_grad_median"], _ = MC.grad_report(D1, ref)
+    print("forward_pair", D_cls.__module__, n, "fused" if fuse else "two-launch", r)
+    return r
+
+
+@pytest.mark.parametrize("fuse", [True, False], ids=["bn-fused", "bn-two-launch"])
+def test_forward_pair_equals_two_calls_srgan(fuse, monkeypatch):
+    """One discriminator pass over (real | fake) with BatchNorm statistics per half (srgan/trainer.py:446-447 semantics)
+    equals two separate calls: outputs, input gradients, parameter gradients, running statistics (two updates, real
+    first), num_batches_tracked += 2."""
+    MC, SG, SD, EG, ED = _mods()
+    r = _pair_case(SD, 8, 96, fuse, monkeypatch, MC.O.srgan_discriminator)
+    assert r["pa"] <= 5e-3 and r["pb"] <= 5e-3 and r["buf"] <= 1e-3, r
+    assert r["grad_median"] <= 3e-2 and r["dxa"] <= 0.1 and r["dxb"] <= 0.1, r
+    assert r["oracle_pa"] <= 1e-2 and r["oracle_pb"] <= 1e-2 and r["oracle_buf"] <= 1e-2 and r["oracle_grad_median"] <= 0.25, r
+
+
+@pytest.mark.parametrize("fuse", [True, False], ids=["bn-fused", "bn-two-launch"])
+def test_forward_pair_equals_two_calls_esrgan(fuse, monkeypatch):
+    MC, SG, SD, EG, ED = _mods()
+    r = _pair_case(ED, 4, 128, fuse, monkeypatch, MC.O.esrgan_discriminator)
+    assert r["pa"] <= 3e-2 and r["pb"] <= 3e-2 and r["buf"] <= 1e-3, r
+    assert r["grad_median"] <= 5e-2, r
+    assert r["oracle_pa"] <= 5e-2 and r["oracle_pb"] <= 5e-2 and r["oracle_buf"] <= 1e-2 and r["oracle_grad_median"] <= 0.3, r
+
+
+def test_forward_pair_falls_back_and_detaches_halves():
+    """Shapes whose halves do not split on 32-row boundaries (3 x 6 x 6 rows in the last layer) run as two calls;
+    grad_halves=(False, True) returns the first half detached (the relativistic generator step, esrgan/trainer.py:463)."""
+    MC, SG, SD, EG, ED = _mods()
+    torch.manual_seed(22)
+    D = SD().cuda().train()
+    a, b = torch.rand(3, 3, 96, 96, device="cuda"), torch.rand(3, 3, 96, 96, device="cuda", requires_grad=True)
+    pa, pb = D.forward_pair(a, b, grad_halves=(False, True))
+    assert not any(len(k) == 3 for k in D._tsr["plans"])
+    assert not pa.requires_grad and pb.requires_grad
+    D2 = ED().cuda().train()
+    a, b = torch.rand(4, 3, 128, 128, device="cuda"), torch.rand(4, 3, 128, 128, device="cuda", requires_grad=True)
+    pa, pb = D2.forward_pair(a, b, grad_halves=(False, True))
+    assert any(len(k) == 3 for k in D2._tsr["plans"])
+    assert not pa.requires_grad and pb.requires_grad
+    pb.sum().backward()
+    assert b.grad is not None and float(b.grad.abs().sum()) > 0
+
+
+def test_loss_kernels_match_torch():
+    """losses.* (loss_kernel / gan_loss_kernel / axpby_f32_kernel) against torch.nn.functional: values and gradients."""
+    import torch.nn.functional as F
+    from torchsr_b200 import losses
+    torch.manual_seed(23)
+    dev = "cuda"
+
+    def both(fn_ours, fn_ref, *shapes, prob=False):
+        xs = [torch.rand(s, device=dev) * 0.98 + 0.01 if prob else torch.randn(s, device=dev) for s in shapes]
+        a1 = [x.clone().requires_grad_(True) for x in xs]
+        a2 = [x.clone().requires_grad_(True) for x in xs]
+        up = torch.tensor(0.7, device=dev)
+        l1, l2 = fn_ours(*a1), fn_ref(*a2)
+        l1.backward(up)
+        l2.backward(up)
+        assert abs(float(l1) - float(l2)) <= 1e-5 * max(1.0, abs(float(l2))), (float(l1), float(l2))
+        for p, q in zip(a1, a2):
+            if q.grad is None:
+                assert p.grad is None
+            else:
+                assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7), (p.grad - q.grad).abs().max()
+
+    t = torch.rand(5, 3, 17, 13, device=dev)
+    both(lambda x: losses.mse(x, t), lambda x: F.mse_loss(x, t), (5, 3, 17, 13))
+    both(lambda x: losses.l1(x, t, scale=0.01), lambda x: 0.01 * F.l1_loss(x, t), (5, 3, 17, 13))
+    one = lambda x: torch.ones_like(x)  # noqa: E731
+    zero = lambda x: torch.zeros_like(x)  # noqa: E731
+    both(lambda p, q: losses.bce(p, 1.0, q, 0.0),
+         lambda p, q: F.binary_cross_entropy(p, one(p)) + F.binary_cross_entropy(q, zero(q)), (16, 1), (16, 1), prob=True)
+    both(lambda p: losses.bce(p, 1.0, scale=0.001), lambda p: 0.001 * F.binary_cross_entropy(p, one(p)), (7, 1), prob=True)
+    lab = (torch.rand(9, 1, device=dev) > 0.5).float()
+    both(lambda p: losses.BCELoss()(p, lab), lambda p: F.binary_cross_entropy(p, lab), (9, 1), prob=True)
+    both(lambda x: losses.BCEWithLogitsLoss()(x, lab), lambda x: F.binary_cross_entropy_with_logits(x, lab), (9, 1))
+    both(lambda r, f: losses.relativistic_d(r, f, scale=0.5),
+         lambda r, f: (F.binary_cross_entropy_with_logits(r - f.mean(), one(r)) +
+                       F.binary_cross_entropy_with_logits(f - r.mean(), zero(f))) / 2, (16, 1), (16, 1))
+    rconst = torch.randn(16, 1, device=dev)
+    both(lambda f: losses.relativistic_g(f, rconst, scale=0.005),
+         lambda f: 0.005 * F.binary_cross_entropy_with_logits(f - rconst.mean(), one(f)), (16, 1))
+    both(lambda x, y: losses.total(losses.mse(x, t), losses.l1(y, t), losses.mse(y, t, scale=2.0)),
+         lambda x, y: F.mse_loss(x, t) + F.l1_loss(y, t) + 2.0 * F.mse_loss(y, t), (5, 3, 17, 13), (5, 3, 17, 13))
+    # saturated probabilities: PyTorch clamps log at -100 and the gradient denominator at 1e-12
+    p = torch.tensor([[0.0], [1.0], [1e-30], [0.5]], device=dev)
+    both(lambda q: losses.bce(q * 0 + p, 1.0), lambda q: F.binary_cross_entropy(q * 0 + p, one(p)), (4, 1), prob=True)
+
+
+def test_graph_step_survives_an_eager_ragged_batch():
+    """FusedAdam's device table is referenced by the captured step graph; an eager step on another batch
+    shape (ragged last batch -> other gradient buffers) must not free or rewrite it. graph, ragged eager, graph again
+    must match an eager-only trainer."""
+    import os
+    from argparse import Namespace
+    os.environ.setdefault("TORCHSR_VGG_WEIGHTS", "random")
+    from torchsr_b200.srgan.trainer import SRGANTrainer
+
+    def make():
+        torch.manual_seed(31)
+        a = Namespace(disable_amp=False, batch_size=8, epochs=8, pretrain_epochs=1, gan_checkpoint=None,
+                      psnr_checkpoint=None, skip_image_save=True, local_rank=0, rank=-1, world_size=1)
+        return SRGANTrainer(torch.device("cuda"), a, [], [], 0, 0, False)
+
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.rand(n, 3, 24, 24, generator=g).cuda(), torch.rand(n, 3, 96, 96, generator=g).cuda())
+               for n in (8, 8, 5, 8, 8)]
+    t1, t2 = make(), make()
+    for i, (lr, hr) in enumerate(batches):
+        t1._train_step('gan', lr, hr, i)       # graph for full batches, eager for the ragged one
+        t2._gan_loop(lr, hr, i)                # eager only
+    torch.cuda.synchronize()
+    from torchsr_b200 import ops
+    ops.check_watchdog()
+    # Adam's first steps move every weight by ~lr * sign(g): atomics-order noise can flip the sign of a near-zero
+    # gradient, so single elements may differ by a few 1e-4; a corrupted table would give garbage everywhere
+    for mod1, mod2 in ((t1.generator, t2.generator), (t1.discriminator, t2.discriminator)):
+        for (k, p), q in zip(mod1.named_parameters(), mod2.parameters()):
+            assert torch.isfinite(p).all(), k
+            d = (p - q).abs()
+            assert float(d.max()) <= 1.5e-3, (k, float(d.max()))
+            assert float((d > 5e-5).float().mean()) <= 0.05, (k, float((d > 5e-5).float().mean()))
+
+
+@BN_PATHS
+def test_eval_mode_no_grad_and_large_image_psnr(bn_fuse):
     """Eval-mode inference on a non-square image: output PSNR against a target agrees with the oracle within 0.05 dB."""
     MC, SG, SD, EG, ED = _mods()
     torch.manual_seed(8)

@@ -16,7 +16,7 @@ ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_RELU = 0, 1, 2, 3
 (E_IM2ROW, E_GATHER_OUT, E_NCHW2NHWC, E_NHWC2NCHW, E_BN_FINALIZE, E_BN_EVAL_COEF, E_BN_ACT, E_BN_BWD_REDUCE,
  E_BN_BWD_FINALIZE, E_BN_BWD_APPLY, E_ACT_BWD, E_COLSUM_FINALIZE, E_SUM_FINALIZE, E_PACK_W, E_UNPACK_G,
  E_LINEAR_WGRAD, E_LOSS, E_ZERO, E_UPSAMPLE2X, E_UPSAMPLE2X_BWD, E_HEAD, E_HEAD_BWD, E_AXPBY, E_MAXPOOL2,
- E_MAXPOOL2_BWD, E_CAST, E_ADAM, E_CHANSUM_NCHW) = range(1, 29)
+ E_MAXPOOL2_BWD, E_CAST, E_ADAM, E_CHANSUM_NCHW, E_GAN_LOSS, E_AXPBY_F32) = range(1, 31)
 
 PK_FWD, PK_T, PK_ROWK, PK_ROWN, PK_ROWN_T, PK_FULLK, PK_LINEAR = range(7)
 
@@ -46,6 +46,11 @@ class ConvDesc(C.Structure):
         ("bnr_c", C.c_int32),
         ("ws", C.c_void_p), ("tile_counters", C.c_void_p), ("ws_ld", C.c_int32), ("_pad1", C.c_int32),
         ("trace", C.c_void_p),
+        ("group_rows", C.c_int32), ("bnf_mode", C.c_int32),
+        ("bnf_counter", C.c_void_p), ("bnf_gamma", C.c_void_p), ("bnf_beta", C.c_void_p), ("bnf_rm", C.c_void_p),
+        ("bnf_rv", C.c_void_p), ("bnf_nbt", C.c_void_p), ("bnf_coef", C.c_void_p),
+        ("bnf_count", C.c_int64), ("bnf_c", C.c_int32), ("_pad2", C.c_int32),
+        ("bnf_eps", C.c_float), ("bnf_momentum", C.c_float),
     ]
 
 
@@ -92,7 +97,7 @@ class AdamEntry(C.Structure):
 EXPORTS = [
     "tsr_init", "tsr_last_error", "tsr_version", "tsr_conv", "tsr_wgrad", "tsr_elt", "tsr_prog_create",
     "tsr_prog_destroy", "tsr_prog_add_conv", "tsr_prog_add_conv_group", "tsr_prog_add_wgrad", "tsr_prog_add_elt", "tsr_prog_size",
-    "tsr_prog_run", "tsr_launch_count", "tsr_check_watchdog",
+    "tsr_prog_run", "tsr_launch_count", "tsr_check_watchdog", "tsr_conv_bnf_capacity",
 ]
 
 _lib = None
@@ -127,6 +132,7 @@ def load():
     lib.tsr_prog_size.argtypes = [C.c_void_p]
     lib.tsr_prog_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.tsr_check_watchdog.argtypes = [C.c_void_p]
+    lib.tsr_conv_bnf_capacity.argtypes = [C.POINTER(ConvDesc), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = lib
     return lib
 

@@ -22,6 +22,7 @@ cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bo
 cudaError_t launch_conv_wgrad(const WgradParams& p, int gsets, int tiles_n, int splits, cudaStream_t stream, bool pdl);
 cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl);
 size_t conv_igemm_smem_bytes(const ConvParams& p);
+int conv_igemm_max_coresident(const ConvParams& p, int* per_sm);
 size_t conv_wgrad_smem_bytes(const WgradParams& p);
 }  // namespace tsr
 
@@ -162,6 +163,8 @@ int persistent_min_tiles_x10() {
 int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = true) {
   using namespace tsr;
   if (int e = ensure_init()) return e;
+  // the fused training BatchNorm keeps every tile's accumulator in TMEM across a grid barrier: one tile per CTA
+  if (d.bnf_mode == 1) allow_persistent = false;
   ConvParams& p = L->p;
   memset(&p, 0, sizeof(p));
   if (d.block_k != 16 && d.block_k != 32 && d.block_k != 64) return fail(-20, "block_k must be 16/32/64");
@@ -241,7 +244,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
     const int n_ctas = L->tiles_n > 0 ? (148 / L->tiles_n > 0 ? 148 / L->tiles_n : 1) : 148;
     const uint32_t a_bytes = kBlockM * d.block_k * 2, b_bytes = static_cast<uint32_t>(d.block_n) * d.block_k * 2;
     const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
-    const size_t budget = 227 * 1024 - 1024 - 13312 - 1024;
+    const size_t budget = 227 * 1024 - 1024 - kConvHeaderBytes - 1024;
     if (use_persistent() && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && allow_persistent &&
         b_res % 1024 == 0 && a_bytes % 1024 == 0 && b_res + 3 * static_cast<size_t>(a_bytes) <= budget &&
         10 * tiles_m >= persistent_min_tiles_x10() * n_ctas && 2 * p.acc_cols <= 512) {
@@ -289,7 +292,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
     const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
     const uint32_t patch_tx = static_cast<uint32_t>((th + 2) * pw * 128);
     const uint32_t patch_alloc = (static_cast<uint32_t>((128 + 2 * pw + 2) * 128) + 1023u) & ~1023u;
-    const size_t budget = 227 * 1024 - 1024 - 13312 - 1024;
+    const size_t budget = 227 * 1024 - 1024 - kConvHeaderBytes - 1024;
     if (taps_ok && th >= 1 && b_res % 1024 == 0 && b_res + 2 * static_cast<size_t>(patch_alloc) <= budget) {
       const int tiles_per_img = strips * tiles_y;
       const int tiles = tiles_per_img * static_cast<int>(d.N);
@@ -381,6 +384,32 @@ epilogue_params:
   e.bnr_prelu = d.bnr_prelu;
   e.bnr_act = d.bnr_act;
   e.bnr_c = d.bnr_c;
+  e.group_rows = d.group_rows;
+  e.bnf_mode = d.bnf_mode;
+  e.bnf_c = d.bnf_c;
+  e.bnf_counter = d.bnf_counter;
+  e.bnf_gamma = d.bnf_gamma;
+  e.bnf_beta = d.bnf_beta;
+  e.bnf_rm = d.bnf_rm;
+  e.bnf_rv = d.bnf_rv;
+  e.bnf_nbt = reinterpret_cast<long long*>(d.bnf_nbt);
+  e.bnf_coef = d.bnf_coef;
+  e.bnf_count = d.bnf_count;
+  e.bnf_eps = d.bnf_eps;
+  e.bnf_momentum = d.bnf_momentum;
+  if (e.group_rows < 0 || e.group_rows % 32) return fail(-20, "group_rows must be a non-negative multiple of 32");
+  if (e.group_rows > 0 && (d.a_mode != 0 || e.group_rows >= p.M_total)) return fail(-20, "group_rows needs an im2col conv and 0 < group_rows < M");
+  if (e.bnf_mode < 0 || e.bnf_mode > 2) return fail(-20, "bnf_mode must be 0, 1 or 2");
+  if (e.bnf_mode) {
+    if (d.a_mode != 0 || splits != 1 || d.out_mode != TSR_OUT_LINEAR || d.bias || d.bwd_z || d.bnr_x || d.res2 ||
+        d.acc_scale != 1.f)
+      return fail(-20, "fused BatchNorm forward needs an unsplit im2col conv with a linear store and no bias / bwd_z / bnr_x / res2 / acc_scale");
+    if (e.bnf_c < e.n_valid || !e.bnf_rm != !e.bnf_rv) return fail(-20, "fused BatchNorm forward: bad bnf_c or running statistics");
+    if (e.bnf_mode == 1 && (!e.stats_partial || !e.bnf_counter || e.bnf_count < 1 || p.persistent))
+      return fail(-20, "training-mode fused BatchNorm needs stats_partial, bnf_counter, bnf_count and one tile per CTA");
+    if (e.bnf_mode == 2 && (!e.bnf_rm || e.stats_partial || e.out_preact))
+      return fail(-20, "eval-mode fused BatchNorm needs running statistics and takes no stats_partial / out_preact");
+  }
   if (e.bnr_x && !e.stats_partial) return fail(-20, "the fused BatchNorm-backward reduction needs stats_partial");
   if (e.bnr_x && e.bnr_act == TSR_ACT_PRELU && !e.bnr_prelu) return fail(-20, "bnr PReLU needs the slope pointer");
   if (e.bnr_x && e.bwd_z) return fail(-20, "bnr_x and bwd_z are mutually exclusive");
@@ -649,6 +678,18 @@ int tsr_conv(const tsr_conv_desc_t* d, void* stream) {
   cudaError_t ce = tsr::launch_conv_igemm(L.p, L.tiles_n, L.splits, static_cast<cudaStream_t>(stream), false);
   if (ce != cudaSuccess) return fail(-40, "conv launch failed: %s", cudaGetErrorString(ce));
   g_launches++;
+  return 0;
+}
+
+int tsr_conv_bnf_capacity(const tsr_conv_desc_t* d, int* ctas, int* capacity) {
+  ConvLaunch L;
+  if (int e = build_conv(*d, &L)) return e;
+  const int tiles_m = (L.p.M_total + tsr::kBlockM - 1) / tsr::kBlockM;
+  if (ctas) *ctas = L.p.persistent ? L.p.persistent * L.tiles_n : tiles_m * L.tiles_n * L.splits;
+  int per_sm = 0;
+  const int cap = tsr::conv_igemm_max_coresident(L.p, &per_sm);
+  if (cap < 0) return fail(-46, "occupancy query failed");
+  if (capacity) *capacity = cap;
   return 0;
 }
 

@@ -25,9 +25,11 @@ namespace tsr {
 
 namespace {
 
-constexpr int kHeaderBytes = 13312;  // barriers + epilogue scratch, tiles start here (1024-aligned)
+constexpr int kHeaderBytes = kConvHeaderBytes;  // barriers + epilogue scratch, tiles start here (1024-aligned)
 constexpr int kScratchOff = 1024;    // float scratch[4 warps][256 cols][2]
-constexpr int kColVecOff = 9216 + 64; // float colvec[3][256]: bias, BatchNorm scale, shift of this CTA's columns
+constexpr int kQuadGroupOff = 9216 + 32;  // int qgrp[4]: BatchNorm statistics group of each TMEM lane quadrant's rows
+constexpr int kColVecOff = 9216 + 64; // float colvec: bias[256], then BatchNorm scale[groups][256], shift[groups][256]
+static_assert(kColVecOff + (1 + 2 * kMaxBnGroups) * 256 * 4 <= kHeaderBytes, "column vectors overflow the header");
 
 __device__ __forceinline__ void butterfly16(float (&v)[16], int lane, float& out) {
   // Sum each of the 16 per-lane values across the 32 lanes of the warp with 16 shuffles.
@@ -96,6 +98,31 @@ __device__ __forceinline__ void store_f32x16(void* base, long long off, const fl
   float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
 #pragma unroll
   for (int i = 0; i < 4; ++i) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// Grid-wide arrival barrier for the fused BatchNorm epilogues: `counter` is zero at launch, every CTA of the barrier's
+// scope arrives once. Called by ONE thread after a CTA-level barrier; the fence makes the CTA's earlier global
+// reductions (performed by other threads, ordered by that barrier) visible before the arrival, as cooperative-groups
+// grid.sync() does. The host only selects this path for grids whose CTAs are all co-resident; the spin is bounded by
+// the watchdog all the same (a timeout leaves a wrong tile and an error code, not a hung GPU).
+__device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* counter, unsigned int expected, int* err) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+  unsigned int seen;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+  if (seen < expected) {
+    const long long t0 = clock64();
+    do {
+      __nanosleep(20);
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (clock64() - t0 > TSR_WATCHDOG_CYCLES) {
+        if (err) atomicExch(err, 6);
+        return false;
+      }
+    } while (seen < expected);
+  }
+  __threadfence();
+  return true;
 }
 
 }  // namespace
@@ -578,21 +605,84 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
     const int ch_begin = half ? (chunks + 1) >> 1 : 0;
     const int ch_end = half ? chunks : (chunks + 1) >> 1;
     const int colbase = tile_n * p.block_n;
+    const int group_rows = e.group_rows;
+    const int n_groups = group_rows > 0 ? 2 : 1;
+    const int bnf = e.bnf_mode;
     // per-column vectors of this CTA's N tile -> shared memory, once (the chunk loop reads them as broadcasts)
     float* s_bias = reinterpret_cast<float*>(smem_gen + kColVecOff);
-    float* s_sc = s_bias + 256;
-    float* s_sh = s_sc + 256;
+    float* s_sc = s_bias + 256;                   // [groups][256]
+    float* s_sh = s_sc + kMaxBnGroups * 256;      // [groups][256]
+    int* s_qgrp = reinterpret_cast<int*>(smem_gen + kQuadGroupOff);
+    // Coefficients of the fused BatchNorm forward for this CTA's columns (every statistics group): training mode reads
+    // the completed column sums (after the grid barrier), eval mode the running statistics. The CTA with blockIdx.x == 0
+    // (first member of a grouped launch) publishes them for backward and updates the running statistics.
+    auto bnf_coefficients = [&](bool publish) {
+      const int et = threadIdx.x - 64;
+      if (et < p.block_n) {
+        const int c = colbase + et;
+        const bool cv = c < e.bnf_c;
+        const float gm = (cv && e.bnf_gamma) ? __ldg(e.bnf_gamma + c) : 1.f;
+        const float bt = (cv && e.bnf_beta) ? __ldg(e.bnf_beta + c) : 0.f;
+        float rm = 0.f, rv = 1.f;
+        if (cv && e.bnf_rm != nullptr) {
+          rm = e.bnf_rm[c];
+          rv = e.bnf_rv[c];
+        }
+        for (int g = 0; g < n_groups; ++g) {
+          float mean = rm, var = rv;
+          if (bnf == 1) {
+            const float inv_n = 1.f / static_cast<float>(e.bnf_count);
+            const float* sp = e.stats_partial + (static_cast<long long>(g) * e.stats_ld + c) * 2;
+            mean = cv ? __ldcg(sp) * inv_n : 0.f;
+            var = cv ? fmaxf(__ldcg(sp + 1) * inv_n - mean * mean, 0.f) : 1.f;
+          }
+          const float invstd = rsqrtf(var + e.bnf_eps);
+          const float sc = gm * invstd;
+          const float sh = bt - mean * sc;
+          s_sc[g * 256 + et] = sc;
+          s_sh[g * 256 + et] = sh;
+          if (publish && cv && bnf == 1) {
+            if (e.bnf_coef != nullptr) {
+              float* co = e.bnf_coef + static_cast<long long>(g) * 4 * e.bnf_c;
+              co[0 * e.bnf_c + c] = sc;
+              co[1 * e.bnf_c + c] = sh;
+              co[2 * e.bnf_c + c] = mean;
+              co[3 * e.bnf_c + c] = invstd;
+            }
+            const float n = static_cast<float>(e.bnf_count);
+            const float unbiased = e.bnf_count > 1 ? var * n / (n - 1.f) : var;
+            rm = (1.f - e.bnf_momentum) * rm + e.bnf_momentum * mean;
+            rv = (1.f - e.bnf_momentum) * rv + e.bnf_momentum * unbiased;
+          }
+        }
+        if (publish && cv && bnf == 1 && e.bnf_rm != nullptr) {
+          e.bnf_rm[c] = rm;
+          e.bnf_rv[c] = rv;
+        }
+      }
+      if (publish && bnf == 1 && e.bnf_nbt != nullptr && blockIdx.y == 0 && et == 0) *e.bnf_nbt += n_groups;
+      named_bar_sync(1, kConvThreads - 64);
+    };
     {
       const int et = threadIdx.x - 64;
       if (et < p.block_n) {
         const int c = colbase + et;
-        s_bias[et] = bias != nullptr ? __ldg(bias + c) : 0.f;
+        // PixelShuffle store: packed column c holds output channel 4*(c % shuf_c) + c / shuf_c; `bias` is the
+        // parameter itself (OIHW channel order)
+        const int bc = out_mode == OUT_SHUFFLE ? 4 * (c % shuf_c) + c / shuf_c : c;
+        s_bias[et] = bias != nullptr ? __ldg(bias + bc) : 0.f;
         const bool hc = bnr_x != nullptr && e.bnr_coef != nullptr && c < e.bnr_c;
-        s_sc[et] = hc ? __ldg(e.bnr_coef + c) : 1.f;
-        s_sh[et] = hc ? __ldg(e.bnr_coef + e.bnr_c + c) : 0.f;
+        if (bnf == 0) {
+          for (int g = 0; g < n_groups; ++g) {
+            const long long co = static_cast<long long>(g) * 4 * e.bnr_c + c;
+            s_sc[g * 256 + et] = hc ? __ldg(e.bnr_coef + co) : 1.f;
+            s_sh[g * 256 + et] = hc ? __ldg(e.bnr_coef + co + e.bnr_c) : 0.f;
+          }
+        }
       }
       named_bar_sync(1, kConvThreads - 64);
     }
+    if (bnf == 2) bnf_coefficients(false);
     int j = 0;
     for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++j) {
     const int m0 = tile_m * kBlockM;
@@ -633,6 +723,9 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       aux_base = static_cast<long long>(m) * e.aux_w + e.aux_ch_off;
     }
     float dalpha = 0.f;
+    // BatchNorm statistics group of this thread's row (all 32 rows of a warp share it: group_rows % 32 == 0)
+    const int grp = (group_rows > 0 && m >= group_rows) ? 1 : 0;
+    if (half == 0 && lane == 0) s_qgrp[q] = grp;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * p.acc_cols;
     // The auxiliary operands of the epilogue (residuals, activation-backward tensor, raw BatchNorm input) do not
     // depend on the accumulator: pull this thread's rows into L1 while the main loop runs, so that the dependent
@@ -648,6 +741,32 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         for (int b = 0; b < (c_hi - c_lo) * 2; b += 64) prefetch_l1(rowp + b);
       }
     }
+    // y = act(v * scale + shift) + res * res_scale for one 16-column chunk of this thread's row (fused BatchNorm forward)
+    auto bn_apply_store = [&](float (&v)[16], int ch, int col0) {
+      const float* sc = s_sc + grp * 256 + ch * 16;
+      const float* sh = s_sh + grp * 256 + ch * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = v[i] * sc[i] + sh[i];
+      if (act == ACT_PRELU || act == ACT_LEAKY) {
+        const float sl = act == ACT_PRELU ? alpha : leaky;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * sl;
+      } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (res != nullptr && col0 < e.res_cols) {
+        float z[16];
+        load_bf16x16(res, aux_base + col0, z);
+        const float rs = e.res_scale;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += z[i] * rs;
+      }
+      if (out_f32)
+        store_f32x16(out, out_base + col0, v);
+      else
+        store_bf16x16(out, out_base + col0, v);
+    };
     const bool ok = mbar_wait(bar_acc_full + 8 * as, (j >> 1) & 1, e.err, 3);
     tc_fence_after();
     if (trace && j == 0 && threadIdx.x == 64) trace[5] = clock64();
@@ -721,6 +840,10 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         }
         if (trace && threadIdx.x == 64 && ch < 4) trace[32 + 2 * ch] = clock64();
         const bool st = valid && col0 < n_valid && (FAST || !(p.debug & 2));
+        if (bnf == 2) {             // eval-mode BatchNorm folded into this pass: coefficients are known up front
+          if (st) bn_apply_store(v, ch, col0);
+          continue;
+        }
         if (bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 16);
 #pragma unroll
@@ -747,7 +870,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
             }
           }
         }
-        if (res != nullptr && st && col0 < e.res_cols) {
+        if (res != nullptr && st && col0 < e.res_cols && bnf == 0) {
           float z[16];
           load_bf16x16(res, aux_base + col0, z);
           const float rs = e.res_scale;
@@ -769,8 +892,8 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
             for (int i = 0; i < 16; ++i) xr[i] = 0.f;
           }
           if (bnr_act != ACT_NONE) {
-            const float* sc = s_sc + ch * 16;
-            const float* sh = s_sh + ch * 16;
+            const float* sc = s_sc + grp * 256 + ch * 16;
+            const float* sh = s_sh + grp * 256 + ch * 16;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float z = xr[i] * sc[i] + sh[i];
@@ -809,6 +932,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
             for (int i = 0; i < 16; ++i) atomicAdd(o + static_cast<long long>(col0 + i) * e.os_n + m, v[i]);
           } else {
             if (out_preact != nullptr) store_bf16x16(out_preact, off, v);
+            if (bnf != 0) continue;     // the normalised value is stored after the grid barrier (below)
             if (act == ACT_PRELU || act == ACT_LEAKY) {
               const float sl = act == ACT_PRELU ? alpha : leaky;
 #pragma unroll
@@ -827,9 +951,10 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       }
     }
     // every tcgen05.ld of this tile has completed (tmem_ld_wait above): hand the accumulator stage back to the MMA warp
+    // (the fused training BatchNorm reads the accumulator once more after the grid barrier and arrives there)
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+    if (bnf != 1 && lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
     // cross-warp reductions of the epilogue side products -> one red.global.add per column / per tile
     if (want_stats || e.dalpha_partial != nullptr) {
       if (e.dalpha_partial != nullptr) {
@@ -840,12 +965,25 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       named_bar_sync(1, kConvThreads - 64);
       const int t = threadIdx.x - 64;  // 0..255
       if (want_stats && finalize) {
-        // thread t -> (column t>>1, statistic t&1) for block_n <= 128; two passes for wider tiles
+        // thread t -> (column t>>1, statistic t&1) for block_n <= 128; two passes for wider tiles. The four lane
+        // quadrants' partial sums go to the statistics group their rows belong to (one group unless group_rows > 0).
         for (int idx = t; idx < p.block_n * 2; idx += kConvThreads - 64) {
           const int c = idx >> 1, w = idx & 1;
-          const float sum = scratch[(0 * 256 + c) * 2 + w] + scratch[(1 * 256 + c) * 2 + w] +
-                            scratch[(2 * 256 + c) * 2 + w] + scratch[(3 * 256 + c) * 2 + w];
-          atomicAdd(e.stats_partial + (colbase + c) * 2 + w, sum);
+          float sum0 = 0.f, sum1 = 0.f;
+          bool any0 = false, any1 = false;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const float pv = scratch[(qq * 256 + c) * 2 + w];
+            if (group_rows > 0 && s_qgrp[qq] != 0) {
+              sum1 += pv;
+              any1 = true;
+            } else {
+              sum0 += pv;
+              any0 = true;
+            }
+          }
+          if (any0) atomicAdd(e.stats_partial + (colbase + c) * 2 + w, sum0);
+          if (any1) atomicAdd(e.stats_partial + (static_cast<long long>(e.stats_ld) + colbase + c) * 2 + w, sum1);
         }
       }
       if (e.dalpha_partial != nullptr && t == 0 && finalize) {
@@ -856,6 +994,30 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       }
       // the scratch slots are reused by the next tile of a persistent CTA
       if (tile_m + static_cast<int>(gridDim.x) < tiles_m) named_bar_sync(1, kConvThreads - 64);
+    }
+    if (bnf == 1) {
+      // ---- fused training-mode BatchNorm: wait until every CTA of this N tile has added its column sums, derive the
+      // coefficients, then normalise + activate (+ residual) straight from the accumulator
+      named_bar_sync(1, kConvThreads - 64);
+      if (threadIdx.x == 64) grid_arrive_and_wait(e.bnf_counter + blockIdx.y, gridDim.x * gridDim.z, e.err);
+      named_bar_sync(1, kConvThreads - 64);
+      bnf_coefficients(blockIdx.x == 0 && blockIdx.z == 0);
+      tc_fence_after();
+      if (finalize) {
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int col0 = colbase + ch * 16;
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          if (valid && col0 < n_valid) bn_apply_store(v, ch, col0);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
     }
     if (trace && j == 0 && threadIdx.x == 64) trace[6] = clock64();
     if (!PERS) break;
@@ -898,6 +1060,19 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_group_kernel(const
 
 size_t conv_igemm_smem_bytes(const ConvParams& p) {
   return 1024 + kHeaderBytes + p.b_res_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
+}
+
+// CTAs of this conv's kernel instantiation that the device can hold at once (occupancy x SM count): the fused
+// training BatchNorm's grid barrier needs the whole grid resident. Returns -1 on a failed query.
+template <typename Kernel>
+static int max_coresident(Kernel kernel, size_t smem, int* per_sm) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
+  int n = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kConvThreads, smem) != cudaSuccess) return -1;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  if (per_sm) *per_sm = n;
+  return n * sms;
 }
 
 // One launch path for every instantiation: raises the dynamic shared-memory limit of `kernel` once, then launches.
@@ -949,6 +1124,17 @@ cudaError_t launch_conv_igemm(const ConvParams& p, int tiles_n, int splits, cuda
     return fast ? launch_mode<0, true>(p, grid, smem, stream, pdl) : launch_mode<0, false>(p, grid, smem, stream, pdl);
   if (p.a_mode == 1) return launch_mode<1, false>(p, grid, smem, stream, pdl);
   return launch_mode<2, false>(p, grid, smem, stream, pdl);
+}
+
+int conv_igemm_max_coresident(const ConvParams& p, int* per_sm) {
+  const size_t smem = conv_igemm_smem_bytes(p);
+  const bool fast = fast_ok(p);
+  if (p.persistent)
+    return fast ? max_coresident(conv_igemm_persistent_kernel<true>, smem, per_sm)
+                : max_coresident(conv_igemm_persistent_kernel<false>, smem, per_sm);
+  if (p.a_mode != 0) return -1;
+  return fast ? max_coresident(conv_igemm_kernel<0, true>, smem, per_sm)
+              : max_coresident(conv_igemm_kernel<0, false>, smem, per_sm);
 }
 
 }  // namespace tsr

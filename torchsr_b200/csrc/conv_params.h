@@ -9,6 +9,8 @@ constexpr int kMaxTaps = 81;      // 9x9
 constexpr int kBlockM = 128;      // UMMA M (TMEM lanes)
 constexpr int kConvThreads = 320; // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogue (2 per TMEM lane quadrant)
 constexpr int kWgradThreads = 192; // warp0 TMA, warp1 MMA/TMEM, warps 2..5 epilogue
+constexpr int kConvHeaderBytes = 15360;  // conv_igemm shared-memory header: barriers, epilogue scratch, column vectors
+constexpr int kMaxBnGroups = 2;    // BatchNorm statistics groups per launch (real | fake halves of a discriminator batch)
 
 enum OutMode : int {
   OUT_LINEAR = 0,     // off = n*os_n + ho*os_h + wo*os_w + col
@@ -57,10 +59,34 @@ struct EpiParams {
   int* tile_counters;    // [tiles_m * tiles_n], zero between launches
   int ws_ld;
   const void* bnr_x;     // bf16 raw conv output x of the BatchNorm being differentiated (aux addressing), or null
-  const float* bnr_coef; // [4][bnr_c]: scale, shift, mean, invstd (forward coefficients) or null
+  const float* bnr_coef; // [groups][4][bnr_c]: scale, shift, mean, invstd (forward coefficients) or null
   const float* bnr_prelu;
   int bnr_act;
   int bnr_c;
+  // BatchNorm statistics groups: the reference calls the discriminator separately on the real and on the fake batch, so
+  // each call normalises with its own batch statistics. Both batches run through one launch here; rows
+  // [0, group_rows) are group 0, the rest group 1 (group_rows = 0: one group). group_rows is a multiple of 32, so a
+  // warp's 32 accumulator rows always belong to one group. stats_partial is then [groups][stats_ld][2].
+  int group_rows;
+  // Fused training/eval BatchNorm forward (the conv feeds a BatchNorm): bnf_mode 1 = training - the epilogue accumulates
+  // the column sums as usual, all CTAs of the launch meet at a grid barrier (bnf_counter, one arrival counter per N
+  // tile, zero at launch; the host only selects this mode for grids that are co-resident), every CTA derives
+  // scale/shift of its columns from the completed sums and applies  y = act(acc*scale + shift) + res*res_scale
+  // straight from the TMEM accumulator; CTA 0 of each N tile publishes bnf_coef (scale, shift, mean, invstd per group)
+  // and updates the running statistics (group 0 first, then group 1: two sequential momentum updates, as two calls
+  // would). The raw accumulator is stored (bf16) to out_preact for backward. bnf_mode 2 = eval: scale/shift come from
+  // the running statistics, no barrier, no statistics, nothing published.
+  int bnf_mode;
+  int bnf_c;                 // channels of the BatchNorm (row length of the coefficient arrays)
+  unsigned int* bnf_counter; // [tiles_n]
+  const float* bnf_gamma;
+  const float* bnf_beta;
+  float* bnf_rm;
+  float* bnf_rv;
+  long long* bnf_nbt;
+  float* bnf_coef;           // [groups][4][bnf_c]
+  long long bnf_count;       // rows behind each group's statistics
+  float bnf_eps, bnf_momentum;
 };
 
 struct ConvParams {

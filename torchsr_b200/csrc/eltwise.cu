@@ -200,7 +200,10 @@ __global__ void nhwc2nchw_kernel(const bf16* __restrict__ x, float* __restrict__
 //   mode 2: eval-mode BatchNorm from running_mean / running_var
 // p0 = x bf16 [M][x_ld], p1 = stats, p2 = y bf16 [M][y_ld], p3 = res bf16 or null, p4 = prelu alpha or null, p5 = gamma,
 // p6 = beta, p7 = running_mean, p8 = running_var, p9 = num_batches_tracked (int64), p10 = coef_out fp32 [4][C] or null
-// i: 0 M, 1 C, 2 x_ld, 3 y_ld, 4 res_ld, 5 act, 6 x_off, 7 y_off, 8 res_off, 9 mode, 10 count (rows behind stats)
+// i: 0 M, 1 C, 2 x_ld, 3 y_ld, 4 res_ld, 5 act, 6 x_off, 7 y_off, 8 res_off, 9 mode, 10 count (rows behind each group's
+// stats), 11 group_rows (> 0: two statistics groups - rows [0, group_rows) and the rest, the real | fake halves of one
+// discriminator pass; stats is then [2][C][2], coef_out [2][4][C], the running statistics take two sequential updates
+// and num_batches_tracked += 2, exactly as two separate calls would)
 // f: 0 leaky slope, 1 res_scale, 2 x_scale, 3 eps, 4 momentum
 struct BnActArgs {
   const bf16* x;
@@ -214,7 +217,7 @@ struct BnActArgs {
   float* rv;
   long long* nbt;
   float* coef;
-  long long M, count;
+  long long M, count, group_rows;
   int C, x_ld, y_ld, res_ld, act, x_off, y_off, res_off, mode;
   float leaky, res_scale, x_scale, eps, momentum;
 };
@@ -229,45 +232,56 @@ __device__ __forceinline__ void lds8(const float* s, float (&v)[8]) {
 // The per-channel coefficients are derived ONCE per block into shared memory (one or two channels per thread);
 // the row loop then costs two 16-byte loads and one store per 8 channels. Two rows are in flight per thread.
 __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
-  __shared__ __align__(16) float s_sc[kMaxBnC], s_sh[kMaxBnC];
+  __shared__ __align__(16) float s_sc[2][kMaxBnC], s_sh[2][kMaxBnC];
   pdl_sync();
   const int C = a.C;
+  const int n_groups = (a.group_rows > 0 && a.mode == 1) ? 2 : 1;
   for (int c = threadIdx.x; c < C; c += 256) {
-    float sc = 1.f, sh = 0.f;
-    if (a.mode != 0) {
-      const float gm = a.gamma ? __ldg(a.gamma + c) : 1.f;
-      const float bt = a.beta ? __ldg(a.beta + c) : 0.f;
-      float mean, var;
-      if (a.mode == 1) {
-        const float inv_n = 1.f / static_cast<float>(a.count);
-        mean = a.stats[2 * c] * inv_n;
-        var = fmaxf(a.stats[2 * c + 1] * inv_n - mean * mean, 0.f);
-      } else {
-        mean = a.rm[c];
-        var = a.rv[c];
-      }
-      const float invstd = rsqrtf(var + a.eps);
-      sc = gm * invstd;
-      sh = bt - mean * sc;
-      if (blockIdx.x == 0) {
-        if (a.coef) {
-          a.coef[0 * C + c] = sc;
-          a.coef[1 * C + c] = sh;
-          a.coef[2 * C + c] = mean;
-          a.coef[3 * C + c] = invstd;
-        }
-        if (a.mode == 1 && a.rm) {
-          const float n = static_cast<float>(a.count);
-          const float unbiased = a.count > 1 ? var * n / (n - 1.f) : var;
-          a.rm[c] = (1.f - a.momentum) * a.rm[c] + a.momentum * mean;
-          a.rv[c] = (1.f - a.momentum) * a.rv[c] + a.momentum * unbiased;
-        }
-      }
+    const float gm = (a.mode != 0 && a.gamma) ? __ldg(a.gamma + c) : 1.f;
+    const float bt = (a.mode != 0 && a.beta) ? __ldg(a.beta + c) : 0.f;
+    float rm = 0.f, rv = 1.f;
+    if (a.mode != 0 && a.rm) {
+      rm = a.rm[c];
+      rv = a.rv[c];
     }
-    s_sc[c] = sc;
-    s_sh[c] = sh;
+    for (int g = 0; g < n_groups; ++g) {
+      float sc = 1.f, sh = 0.f;
+      if (a.mode != 0) {
+        float mean = rm, var = rv;
+        if (a.mode == 1) {
+          const float inv_n = 1.f / static_cast<float>(a.count);
+          const float* st = a.stats + static_cast<long long>(g) * 2 * C;
+          mean = st[2 * c] * inv_n;
+          var = fmaxf(st[2 * c + 1] * inv_n - mean * mean, 0.f);
+        }
+        const float invstd = rsqrtf(var + a.eps);
+        sc = gm * invstd;
+        sh = bt - mean * sc;
+        if (blockIdx.x == 0) {
+          if (a.coef) {
+            float* co = a.coef + static_cast<long long>(g) * 4 * C;
+            co[0 * C + c] = sc;
+            co[1 * C + c] = sh;
+            co[2 * C + c] = mean;
+            co[3 * C + c] = invstd;
+          }
+          if (a.mode == 1 && a.rm) {
+            const float n = static_cast<float>(a.count);
+            const float unbiased = a.count > 1 ? var * n / (n - 1.f) : var;
+            rm = (1.f - a.momentum) * rm + a.momentum * mean;
+            rv = (1.f - a.momentum) * rv + a.momentum * unbiased;
+          }
+        }
+      }
+      s_sc[g][c] = sc;
+      s_sh[g][c] = sh;
+    }
+    if (blockIdx.x == 0 && a.mode == 1 && a.rm) {
+      a.rm[c] = rm;
+      a.rv[c] = rv;
+    }
   }
-  if (a.mode == 1 && a.nbt && blockIdx.x == 0 && threadIdx.x == 0) *a.nbt += 1;
+  if (a.mode == 1 && a.nbt && blockIdx.x == 0 && threadIdx.x == 0) *a.nbt += n_groups;
   __syncthreads();
   const int groups = C >> 3;
   const long long total = a.M * groups;
@@ -275,15 +289,19 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
   const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * 256;
   const int g = static_cast<int>(idx0 % groups);  // constant per thread: the grid stride is a multiple of `groups`
-  float sc[8], sh[8];
-  lds8(s_sc + g * 8, sc);
-  lds8(s_sh + g * 8, sh);
+  const long long split = n_groups == 2 ? a.group_rows : a.M;   // rows >= split use the second coefficient set
+  float sc[8], sh[8], sc1[8], sh1[8];
+  lds8(s_sc[0] + g * 8, sc);
+  lds8(s_sh[0] + g * 8, sh);
+  lds8(s_sc[n_groups - 1] + g * 8, sc1);
+  lds8(s_sh[n_groups - 1] + g * 8, sh1);
   const bf16* xp = a.x + a.x_off + g * 8;
   const bf16* rp = a.res ? a.res + a.res_off + g * 8 : nullptr;
   bf16* yp = a.y + a.y_off + g * 8;
   for (long long idx = idx0; idx < total; idx += 2 * stride) {
     const long long m0 = idx / groups, m1 = (idx + stride) / groups;
     const bool two = idx + stride < total;
+    const bool hi0 = m0 >= split, hi1 = m1 >= split;
     float v0[8], v1[8], r0[8], r1[8];
     ld8(xp + m0 * a.x_ld, v0);
     if (two) ld8(xp + m1 * a.x_ld, v1);
@@ -293,8 +311,8 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      v0[j] = act_fwd(v0[j] * sc[j] + sh[j], a.act, slope) * a.x_scale;
-      v1[j] = act_fwd(v1[j] * sc[j] + sh[j], a.act, slope) * a.x_scale;
+      v0[j] = act_fwd(v0[j] * (hi0 ? sc1[j] : sc[j]) + (hi0 ? sh1[j] : sh[j]), a.act, slope) * a.x_scale;
+      v1[j] = act_fwd(v1[j] * (hi1 ? sc1[j] : sc[j]) + (hi1 ? sh1[j] : sh[j]), a.act, slope) * a.x_scale;
     }
     if (rp) {
 #pragma unroll
@@ -417,7 +435,7 @@ struct BnBwdApplyArgs {
   float* dbeta;
   float* dalpha;
   const float* dalpha_acc;
-  long long M;
+  long long M, group_rows;
   int C, act, g_ld, x_ld, dx_ld, has_bn, raw_sums, pre_act;
   float leaky, gscale;
 };
@@ -425,33 +443,44 @@ struct BnBwdApplyArgs {
 // i[7] raw_sums: sums[c][1] holds sum(dz * x) over the RAW conv output x (as accumulated by a data-gradient conv
 // epilogue, conv_igemm.cu "fused BatchNorm-backward reduction") instead of sum(dz * xhat);
 // i[8] pre_act: g already is dz (the activation derivative was applied by that epilogue).
+// i[9] group_rows (> 0, BatchNorm only): two statistics groups as in BN_ACT - coef is [2][4][C], sums [2][C][2], every
+// group's rows are normalised with that group's statistics and row count; dgamma / dbeta are the sums over both groups.
 // Per channel the whole backward collapses to dx = A*dz + Bx*x + Cc (derived once per block into shared memory).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs a) {
-  __shared__ __align__(16) float s_co[5][kMaxBnC];   // sc, sh, A, Bx, Cc
+  __shared__ __align__(16) float s_co[2][5][kMaxBnC];   // per group: sc, sh, A, Bx, Cc
   pdl_sync();
   const int C = a.C;
-  const float inv_m = 1.f / static_cast<float>(a.M);
+  const int n_groups = (a.group_rows > 0 && a.has_bn) ? 2 : 1;
   for (int c = threadIdx.x; c < C; c += 256) {
-    float sc = 1.f, sh = 0.f, mu = 0.f, is = 1.f;
-    if (a.has_bn) {
-      sc = a.coef[c];
-      sh = a.coef[C + c];
-      mu = a.coef[2 * C + c];
-      is = a.coef[3 * C + c];
+    float dbeta = 0.f, dgamma = 0.f;
+    for (int g = 0; g < n_groups; ++g) {
+      const long long rows = n_groups == 2 ? (g == 0 ? a.group_rows : a.M - a.group_rows) : a.M;
+      const float inv_m = 1.f / static_cast<float>(rows);
+      float sc = 1.f, sh = 0.f, mu = 0.f, is = 1.f;
+      if (a.has_bn) {
+        const float* co = a.coef + static_cast<long long>(g) * 4 * C;
+        sc = co[c];
+        sh = co[C + c];
+        mu = co[2 * C + c];
+        is = co[3 * C + c];
+      }
+      const float* sums = a.sums ? a.sums + static_cast<long long>(g) * 2 * C : nullptr;
+      const float s1 = sums ? sums[2 * c] : 0.f;
+      float s2 = sums ? sums[2 * c + 1] : 0.f;
+      if (a.raw_sums) s2 = is * (s2 - mu * s1);
+      const float A = (a.gamma ? __ldg(a.gamma + c) : 1.f) * is;
+      const float c2 = s1 * inv_m, c3 = s2 * inv_m;
+      s_co[g][0][c] = sc;
+      s_co[g][1][c] = sh;
+      s_co[g][2][c] = A;
+      s_co[g][3][c] = -A * c3 * is;
+      s_co[g][4][c] = -A * (c2 - mu * is * c3);
+      dbeta += s1;
+      dgamma += s2;
     }
-    const float s1 = a.sums ? a.sums[2 * c] : 0.f;
-    float s2 = a.sums ? a.sums[2 * c + 1] : 0.f;
-    if (a.raw_sums) s2 = is * (s2 - mu * s1);
-    const float A = (a.gamma ? __ldg(a.gamma + c) : 1.f) * is;
-    const float c2 = s1 * inv_m, c3 = s2 * inv_m;
-    s_co[0][c] = sc;
-    s_co[1][c] = sh;
-    s_co[2][c] = A;
-    s_co[3][c] = -A * c3 * is;
-    s_co[4][c] = -A * (c2 - mu * is * c3);
     if (blockIdx.x == 0) {
-      if (a.dbeta) a.dbeta[c] = s1;
-      if (a.dgamma) a.dgamma[c] = s2;
+      if (a.dbeta) a.dbeta[c] = dbeta;
+      if (a.dgamma) a.dgamma[c] = dgamma;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.dalpha) *a.dalpha = *a.dalpha_acc;
@@ -463,12 +492,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs 
   const long long idx0 = blockIdx.x * 256ll + threadIdx.x;
   const long long stride = static_cast<long long>(gridDim.x) * 256;
   const int gi = static_cast<int>(idx0 % groups);
-  float sc[8], sh[8], cA[8], cB[8], cC[8];
-  lds8(s_co[0] + gi * 8, sc);
-  lds8(s_co[1] + gi * 8, sh);
-  lds8(s_co[2] + gi * 8, cA);
-  lds8(s_co[3] + gi * 8, cB);
-  lds8(s_co[4] + gi * 8, cC);
+  const long long split = n_groups == 2 ? a.group_rows : a.M;
   const bf16* gp = a.g + gi * 8;
   const bf16* g2p = a.g2 ? a.g2 + gi * 8 : nullptr;
   const bf16* xp = a.x + gi * 8;
@@ -477,6 +501,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs 
   for (long long idx = idx0; idx < total; idx += 2 * stride) {
     const long long m0 = idx / groups, m1 = (idx + stride) / groups;
     const bool two = idx + stride < total;
+    const float (*c0)[kMaxBnC] = s_co[m0 >= split ? 1 : 0];
+    const float (*c1)[kMaxBnC] = s_co[(two && m1 >= split) ? 1 : 0];
     float g0[8], g1[8], x0[8], x1[8];
     ld8(gp + m0 * a.g_ld, g0);
     if (two) ld8(gp + m1 * a.g_ld, g1);
@@ -496,14 +522,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs 
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      const int c = gi * 8 + j;
       float d0 = g0[j] * a.gscale, d1 = g1[j] * a.gscale;
       if (mask) {
-        if (x0[j] * sc[j] + sh[j] <= 0.f) d0 *= slope;
-        if (x1[j] * sc[j] + sh[j] <= 0.f) d1 *= slope;
+        if (x0[j] * c0[0][c] + c0[1][c] <= 0.f) d0 *= slope;
+        if (x1[j] * c1[0][c] + c1[1][c] <= 0.f) d1 *= slope;
       }
       if (a.has_bn) {
-        d0 = cA[j] * d0 + cB[j] * x0[j] + cC[j];
-        d1 = cA[j] * d1 + cB[j] * x1[j] + cC[j];
+        d0 = c0[2][c] * d0 + c0[3][c] * x0[j] + c0[4][c];
+        d1 = c1[2][c] * d1 + c1[3][c] * x1[j] + c1[4][c];
       }
       g0[j] = d0;
       g1[j] = d1;
@@ -514,15 +541,17 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs 
 }
 
 // ---------------------------------------------------------------------------------------------- small finalizers
-// COLSUM_FINALIZE: p0 = partial [tiles][ld][2], p1 = out[C]; i: 0 tiles, 1 C, 2 ld, 3 which (0/1), 4 accumulate
+// COLSUM_FINALIZE: p0 = partial [tiles][ld][2], p1 = out[C]; i: 0 tiles, 1 C, 2 ld, 3 which (0/1), 4 accumulate,
+// 5 c4 (> 0: the columns are in PixelShuffle-packed order, column r belongs to channel 4*(r % c4) + r / c4)
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int tiles, int C,
-                                       int ld, int which, int accumulate) {
+                                       int ld, int which, int accumulate, int c4) {
   pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f;
   for (int t = 0; t < tiles; ++t) a += partial[(static_cast<long long>(t) * ld + c) * 2 + which];
-  out[c] = accumulate ? out[c] + a : a;
+  const int o = c4 > 0 ? 4 * (c % c4) + c / c4 : c;
+  out[o] = accumulate ? out[o] + a : a;
 }
 // SUM_FINALIZE: p0 = partial[n], p1 = out scalar; i: 0 n, 1 accumulate; f: 0 scale
 __global__ void sum_finalize_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int accumulate,
@@ -914,6 +943,114 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ a, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- adversarial losses
+// GAN_LOSS: the (relativistic) adversarial criteria of both trainers in ONE single-block launch - forward value and
+// the gradient w.r.t. the discriminator outputs (saved for backward), labels are constants (no label tensors):
+//   mode 0  nn.BCELoss on probabilities (srgan/trainer.py:164,446-448,456):
+//           L = mean_i bce(a_i, ya) [+ mean_j bce(b_j, yb)],  bce(p,y) = -(y*max(log p,-100) + (1-y)*max(log(1-p),-100)),
+//           d bce/dp = (p - y) / max((1-p)*p, 1e-12)   (ATen binary_cross_entropy_backward)
+//   mode 1  relativistic average GAN, discriminator side (esrgan/trainer.py:451-453):
+//           L = mean_i bcewl(a_i - mean(b), ya) + mean_j bcewl(b_j - mean(a), yb); gradients flow through both means
+//   mode 2  relativistic average GAN, generator side (esrgan/trainer.py:463-468): L = mean_i bcewl(a_i - mean(b), ya),
+//           b is a constant (computed under no_grad)
+//   bcewl(x,y) = max(x,0) - x*y + log1p(exp(-|x|)),  d/dx = sigmoid(x) - y
+// p0 = a fp32 [na], p1 = b fp32 [nb] or null, p2 = loss out (scalar), p3 = dL/da out [na], p4 = dL/db out [nb] or null,
+// p5 = optional per-element targets of a, fp32 [na] (the nn.BCELoss(input, target) form; null -> the constant ya)
+// i: 0 na, 1 nb, 2 mode; f: 0 ya, 1 yb, 2 scale (multiplies the loss and both gradients)
+__device__ __forceinline__ float block_sum_256(float v, float* sw) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += sw[w];
+  return t;
+}
+__device__ __forceinline__ float bce_prob(float p, float y) {
+  return -(y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(logf(1.f - p), -100.f));
+}
+__device__ __forceinline__ float bce_prob_grad(float p, float y) { return (p - y) / fmaxf((1.f - p) * p, 1e-12f); }
+__device__ __forceinline__ float bce_logit(float x, float y) { return fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float bce_logit_grad(float x, float y) { return 1.f / (1.f + expf(-x)) - y; }
+
+__global__ void __launch_bounds__(256) gan_loss_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                       float* __restrict__ loss, float* __restrict__ ga,
+                                                       float* __restrict__ gb, const float* __restrict__ ta,
+                                                       int na, int nb, int mode, float ya, float yb, float scale) {
+  pdl_sync();
+  __shared__ float sw[8];
+  const int t = threadIdx.x;
+  float ma = 0.f, mb = 0.f;
+  if (mode != 0) {
+    float sa = 0.f, sb = 0.f;
+    for (int i = t; i < na; i += 256) sa += a[i];
+    for (int j = t; j < nb; j += 256) sb += b[j];
+    ma = block_sum_256(sa, sw) / static_cast<float>(max(na, 1));
+    mb = block_sum_256(sb, sw) / static_cast<float>(max(nb, 1));
+  }
+  const bool b_term = b != nullptr && mode != 2;
+  const float inv_a = 1.f / static_cast<float>(max(na, 1)), inv_b = 1.f / static_cast<float>(max(nb, 1));
+  float la = 0.f, lb = 0.f, da = 0.f, db = 0.f;   // loss sums, sums of the per-element derivatives
+  for (int i = t; i < na; i += 256) {
+    const float x = a[i] - (mode != 0 ? mb : 0.f);
+    const float y = ta ? ta[i] : ya;
+    la += mode == 0 ? bce_prob(x, y) : bce_logit(x, y);
+    da += mode == 0 ? bce_prob_grad(x, y) : bce_logit_grad(x, y);
+  }
+  if (b_term) {
+    for (int j = t; j < nb; j += 256) {
+      const float x = b[j] - (mode != 0 ? ma : 0.f);
+      lb += mode == 0 ? bce_prob(x, yb) : bce_logit(x, yb);
+      db += mode == 0 ? bce_prob_grad(x, yb) : bce_logit_grad(x, yb);
+    }
+  }
+  la = block_sum_256(la, sw);
+  lb = block_sum_256(lb, sw);
+  da = block_sum_256(da, sw);
+  db = block_sum_256(db, sw);
+  if (t == 0) *loss = scale * (la * inv_a + (b_term ? lb * inv_b : 0.f));
+  // mode 1: a_i also enters every b-term through mean(a) (and vice versa): - (1/na) * mean_j bcewl'(b_j - mean a)
+  const float cross_a = (mode == 1 && b_term) ? db * inv_b * inv_a : 0.f;
+  const float cross_b = mode == 1 ? da * inv_a * inv_b : 0.f;
+  for (int i = t; i < na; i += 256) {
+    const float x = a[i] - (mode != 0 ? mb : 0.f);
+    const float y = ta ? ta[i] : ya;
+    const float d = mode == 0 ? bce_prob_grad(x, y) : bce_logit_grad(x, y);
+    ga[i] = scale * (d * inv_a - cross_a);
+  }
+  if (gb != nullptr && b_term) {
+    for (int j = t; j < nb; j += 256) {
+      const float x = b[j] - (mode != 0 ? ma : 0.f);
+      const float d = mode == 0 ? bce_prob_grad(x, yb) : bce_logit_grad(x, yb);
+      gb[j] = scale * (d * inv_b - cross_b);
+    }
+  }
+}
+
+// AXPBY_F32: out = a * s * x + b * y on fp32 vectors; s = *p3 when given (a device scalar: the upstream gradient of a
+// scalar loss, so that loss backward passes need no host round trip and no ATen multiply), else 1.
+// p0 = x, p1 = y or null, p2 = out (may alias x or y), p3 = device scalar or null; i: 0 n; f: 0 a, 1 b
+__global__ void __launch_bounds__(256) axpby_f32_kernel(const float* x, const float* y, float* out,
+                                                        const float* __restrict__ s, long long n, float a, float b) {
+  pdl_sync();
+  const float k = a * (s ? __ldg(s) : 1.f);
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                     (y ? reinterpret_cast<uintptr_t>(y) : 0)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * 256) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+    if (y) {
+      const float4 w = reinterpret_cast<const float4*>(y)[i];
+      v.x += b * w.x; v.y += b * w.y; v.z += b * w.z; v.w += b * w.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * 256ll + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * 256)
+    out[i] = k * x[i] + (y ? b * y[i] : 0.f);
+}
+
 // ---------------------------------------------------------------------------------------------- upsample (ESRGAN)
 // UPSAMPLE2X: p0 = x bf16 [B,H,W,ld_in], p1 = y bf16 [B,2H,2W,ld_out]; i: 0 B,1 H,2 W,3 C,4 ld_in,5 ld_out
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C,
@@ -1199,7 +1336,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       a.alpha = (const float*)p[4]; a.gamma = (const float*)p[5]; a.beta = (const float*)p[6]; a.rm = (float*)p[7];
       a.rv = (float*)p[8]; a.nbt = (long long*)p[9]; a.coef = (float*)p[10];
       a.M = i[0]; a.C = i[1]; a.x_ld = i[2]; a.y_ld = i[3]; a.res_ld = i[4]; a.act = i[5]; a.x_off = i[6];
-      a.y_off = i[7]; a.res_off = i[8]; a.mode = i[9]; a.count = i[10];
+      a.y_off = i[7]; a.res_off = i[8]; a.mode = i[9]; a.count = i[10]; a.group_rows = i[11];
       a.leaky = d.f[0]; a.res_scale = d.f[1]; a.x_scale = d.f[2]; a.eps = d.f[3]; a.momentum = d.f[4];
       if (a.C > kMaxBnC) return cudaErrorInvalidValue;
       ce = launch_k(bn_act_kernel, dim3(grid_for(i[0] * (i[1] / 8))), dim3(256), 0, st, pdl, a);
@@ -1223,7 +1360,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       a.alpha = (const float*)p[4]; a.dx = (bf16*)p[5]; a.g2 = (const bf16*)p[6]; a.gamma = (const float*)p[7];
       a.dgamma = (float*)p[8]; a.dbeta = (float*)p[9]; a.dalpha = (float*)p[10]; a.dalpha_acc = (const float*)p[11];
       a.M = i[0]; a.C = i[1]; a.act = i[2]; a.g_ld = i[3]; a.x_ld = i[4]; a.dx_ld = i[5]; a.has_bn = i[6];
-      a.raw_sums = i[7]; a.pre_act = i[8];
+      a.raw_sums = i[7]; a.pre_act = i[8]; a.group_rows = i[9];
       if (a.C > kMaxBnC) return cudaErrorInvalidValue;
       a.leaky = d.f[0];
       a.gscale = d.f[1] != 0.f ? d.f[1] : 1.f;
@@ -1232,7 +1369,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
     }
     case TSR_E_COLSUM_FINALIZE:
       ce = launch_k(colsum_finalize_kernel, dim3((i[1] + 127) / 128), dim3(128), 0, st, pdl, (const float*)p[0], (float*)p[1], i[0], i[1], i[2], i[3],
-                                                                i[4]);
+                                                                i[4], i[5]);
       break;
     case TSR_E_SUM_FINALIZE:
       ce = launch_k(sum_finalize_kernel, dim3(1), dim3(32), 0, st, pdl, (const float*)p[0], (float*)p[1], i[0], i[1], d.f[0]);
@@ -1297,6 +1434,14 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       break;
     case TSR_E_CAST:
       ce = launch_k(cast_kernel, dim3(grid_for(i[0])), dim3(256), 0, st, pdl, p[0], p[1], i[0], i[1]);
+      break;
+    case TSR_E_GAN_LOSS:
+      ce = launch_k(gan_loss_kernel, dim3(1), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (float*)p[2],
+                    (float*)p[3], (float*)p[4], (const float*)p[5], i[0], i[1], i[2], d.f[0], d.f[1], d.f[2]);
+      break;
+    case TSR_E_AXPBY_F32:
+      ce = launch_k(axpby_f32_kernel, dim3(grid_for((i[0] + 3) / 4)), dim3(256), 0, st, pdl, (const float*)p[0],
+                    (const float*)p[1], (float*)p[2], (const float*)p[3], i[0], d.f[0], d.f[1]);
       break;
     case TSR_E_CHANSUM_NCHW: {
       dim3 grid(static_cast<unsigned>(i[1]), static_cast<unsigned>(i[3]));

@@ -30,11 +30,20 @@ FUSE_BN_REDUCE = os.environ.get("TSR_FUSE_BN_REDUCE", "1") != "0"
 # (0): measured on B200 the last-CTA finalize (dependent L2 reads of the fp32 partial sums) costs more than the shorter
 # main loop saves for every layer of this workload (profiles/r01_splitk_experiment.md); the mode stays parity-tested.
 SPLIT_K_MIN_ITERS = int(os.environ.get("TSR_SPLITK_MIN_ITERS", "0"))
+# conv + BatchNorm (+ activation, + residual) in ONE launch: training mode crosses a grid barrier inside the conv kernel
+# (only for grids the device holds at once), eval mode folds the running statistics into the epilogue. "0" keeps the
+# two-launch path (conv with column sums, then bn_act_kernel) everywhere - both stay parity-tested.
+FUSE_BN_FWD = os.environ.get("TSR_BN_FUSE", "1") != "0"
 ZERO_ARENA_FLOATS = 64 * 1024
 
 
 def _round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
+
+
+class GroupSplitError(RuntimeError):
+    """A two-group (real | fake) BatchNorm pass was asked for a shape whose per-group row count is not a multiple of 32
+    in some layer; B200Module.forward_pair then falls back to two separate calls."""
 
 
 class Act:
@@ -129,7 +138,7 @@ class ConvRec:
             self.acc_rows, self.acc_taps, self.acc_cols = self.npad, k, self.cin
         else:
             raise ValueError(kind)
-        self.w_fwd = self.w_t = self.acc = self.bias_packed = None
+        self.w_fwd = self.w_t = self.acc = None
 
 
 class LinearRec:
@@ -181,7 +190,6 @@ class ParamStore:
 
     def _build_tables(self):
         pack = []
-        self.bias_perm: List[ConvRec] = []
         for r in self.convs:
             n_fwd = r.slots * r.cout_pad * r.cols
             r.w_fwd = self.w_arena[r._fwd_off:r._fwd_off + n_fwd]
@@ -199,9 +207,6 @@ class ParamStore:
                     r.w_t = self.w_arena[r._t_off:r._t_off + n_t]
                     pack.append(dict(src=r.weight, dst=r.w_t, mode=r.t_mode, cout=r.cout, cin=r.cin, kh=r.k, kw=r.k,
                                      rows_pad=r.t_rows, cols_pad=r.t_cols, shuffle=r.shuffle, count=n_t))
-            if r.shuffle and r.bias is not None:
-                r.bias_packed = torch.zeros(r.cout_pad, dtype=F32, device=self.device)
-                self.bias_perm.append(r)
         for r in self.linears:
             n = r.nout_pad * r.K
             r.w_fwd = self.w_arena[r._fwd_off:r._fwd_off + n]
@@ -218,8 +223,7 @@ class ParamStore:
         if special:
             self._sp_tab, n, blocks = ops.pack_table(special, self.device)
             self._pack_special_desc = ops.elt(L.E_PACK_W, p=[self._sp_tab], i=[n, blocks])
-        self._watched = [r.weight for r in self.convs] + [r.weight for r in self.linears] + \
-                        [r.bias for r in self.bias_perm]
+        self._watched = [r.weight for r in self.convs] + [r.weight for r in self.linears]
 
     def ensure_packed(self):
         """Re-packs the bf16 operand copies if any watched parameter changed since the last pack (one kernel)."""
@@ -235,9 +239,6 @@ class ParamStore:
         else:
             ops.run_now(self._pack_desc)
         self.opt_fresh = False
-        for r in self.bias_perm:   # PixelShuffle layers consume the bias in packed-column order
-            c4 = r.cout // 4
-            r.bias_packed.view(4, c4).copy_(r.bias.detach().view(c4, 4).t())
         self._version = ver
         self.dirty = False
 
@@ -268,7 +269,6 @@ class GradBuffers:
         st = self.store
         self.flat = torch.zeros(max(st.total, 4), dtype=F32, device=st.device)
         self.acc_arena = torch.zeros(st.acc_elems, dtype=F32, device=st.device)
-        self._bgp: Dict[str, torch.Tensor] = {}
         unpack = []
         for r in st.convs:
             n_acc = r.acc_rows * r.acc_taps * r.acc_cols
@@ -286,20 +286,17 @@ class GradBuffers:
         self._ensure()
         return self.acc_arena[r._acc_off:r._acc_off + r.acc_rows * r.acc_taps * r.acc_cols]
 
-    def bias_grad_packed(self, r: ConvRec) -> torch.Tensor:
-        self._ensure()
-        if r.name not in self._bgp:
-            self._bgp[r.name] = torch.zeros(r.cout_pad, dtype=F32, device=self.store.device)
-        return self._bgp[r.name]
-
 
 # ------------------------------------------------------------------------------------------------ plan
 class Plan:
     """One instance = the workspaces + recorded programs of one module call at one input shape and mode.
     A net definition fills it through the emit_* helpers; backward is emitted by replaying the tape in reverse."""
 
-    def __init__(self, store: ParamStore, B: int, H: int, W: int, training: bool):
+    def __init__(self, store: ParamStore, B: int, H: int, W: int, training: bool, groups: int = 1):
         self.store, self.B, self.H, self.W, self.training = store, B, H, W, training
+        # BatchNorm statistics groups: 2 = the batch is (real | fake), each half normalised with its own batch
+        # statistics as two separate calls of the module would (B200Module.forward_pair); only matters in training mode
+        self.groups = groups if training else 1
         self.device = store.device
         self.grads = GradBuffers(store)
         self.bufs: Dict[str, torch.Tensor] = {}
@@ -318,6 +315,8 @@ class Plan:
         self.fwd.add(ops.elt(L.E_ZERO, p=[self._zarena["fwd"]], i=[ZERO_ARENA_FLOATS * 4]))
         self.post_backward: List[Callable] = []
         self.input_fn = self.output_fn = self.ingest_fn = self.grad_input_fn = None
+        # optional two-tensor variants for forward_pair (default: concatenate / split around the single-tensor ones)
+        self.input_pair_fn = self.ingest_pair_fn = None
         self.last_g: Dict[tuple, Optional[Act]] = {}
 
     # ---- buffers
@@ -358,14 +357,15 @@ class Plan:
 
     def conv_fwd(self, prog, rec: ConvRec, x: Act, out: Act, *, stats=None, act=L.ACT_NONE, prelu=None, preact=None,
                  res: Optional[Act] = None, res2: Optional[Act] = None, res_scale=1.0, res2_scale=1.0, acc_scale=1.0,
-                 out_f32=False, shuffle_out=False, use_bias=True):
+                 out_f32=False, shuffle_out=False, use_bias=True, group_rows=0, bnf: Optional[dict] = None,
+                 dry_add=True):
         """Forward of a 'std' conv (any stride) into `out` (OUT_LINEAR or PixelShuffle store), with the fused epilogue
         v = (acc + bias) * acc_scale + res * res_scale + res2 * res2_scale, optional activation, optional statistics.
         `x` / `out` / `res` may be channel slices of wider NHWC buffers (ld, c0)."""
         geom = ops.fwd_geometry(x.H, x.W, rec.k, rec.k, rec.pad, rec.pad, rec.stride)
         bias = None
         if rec.bias is not None and use_bias:
-            bias = rec.bias_packed if rec.shuffle else rec.bias
+            bias = rec.bias      # PixelShuffle stores index it through the channel permutation inside the epilogue
         kw = dict(bias=bias, act=act, prelu=prelu, out_preact=preact, out_f32=out_f32, acc_scale=acc_scale,
                   out_ch_off=out.c0)
         if stats is not None:
@@ -376,11 +376,67 @@ class Plan:
                       res2=res2.t if res2 is not None else None, res2_scale=res2_scale)
         if shuffle_out:
             kw.update(out_mode=L.OUT_SHUFFLE, shuf_c=rec.cout // 4)
+        if group_rows:
+            kw.update(group_rows=group_rows)
+        if bnf is not None:
+            kw.update(bnf)
         tiles = self.pick_tiles(x.B * geom["Ho"] * geom["Wo"], rec.cout_pad, rec.block_n,
                                 len(geom["taps"]) * ((x.C) // ops.pick_block_k(x.C)))
         block_n = tiles.pop("block_n")
+        if not dry_add:     # descriptor only (the caller decides whether this variant is launched)
+            return ops.conv_desc(x=ops.ptr(x.t, x.c0) if x.c0 else x.t, N=x.B, H=x.H, W=x.W, C=x.C, x_ld=x.ld, geom=geom,
+                                 w=rec.w_fwd, cout_pad=rec.cout_pad, w_ld=rec.cols, n_slots=rec.slots, block_n=block_n,
+                                 out=out.t, os_n=out.strides()[0], os_h=out.strides()[1], os_w=out.strides()[2],
+                                 n_valid=rec.cout_pad, **kw, **tiles)
         return self.conv(prog, x, rec.w_fwd, rec.cols, rec.slots, geom, rec.cout_pad, block_n, out.t, out.strides(),
                          rec.cout_pad, **kw, **tiles)
+
+    def conv_bn_act(self, prog, name: str, rec: ConvRec, x: Act, y: Act, *, bn: nn.BatchNorm2d, act=L.ACT_NONE,
+                    alpha=None, res: Optional[Act] = None):
+        """y = act(BN(conv(x))) + res  (reference srgan/residual.py:86-91, generator.py:78, discriminator.py:33-61).
+        Returns (raw, coef): the bf16 raw conv output and the published (scale, shift, mean, invstd) per statistics group,
+        both needed by backward (None in eval mode).
+
+        One launch when possible: eval mode always (running statistics folded into the conv epilogue); training mode
+        when the conv's whole grid is co-resident, so that its CTAs can meet at a grid barrier between the column sums
+        and the normalisation (csrc/conv_igemm.cu). Otherwise conv (with column sums) + bn_act_kernel."""
+        assert rec.kind == "std" and rec.bias is None and rec.cout == rec.cout_pad
+        self.has_bn = True
+        C = rec.cout
+        geom = ops.fwd_geometry(x.H, x.W, rec.k, rec.k, rec.pad, rec.pad, rec.stride)
+        M = x.B * geom["Ho"] * geom["Wo"]
+        G = self.groups
+        group_rows = M // 2 if G == 2 else 0
+        if G == 2 and (M % 2 or group_rows % 32):
+            raise GroupSplitError("torchsr_b200: a two-group BatchNorm pass needs (rows per group) % 32 == 0 in every layer")
+        eps, mom = bn.eps, (bn.momentum if bn.momentum is not None else 0.1)
+        if not self.training:
+            if FUSE_BN_FWD:
+                self.conv_fwd(prog, rec, x, y, act=act, prelu=alpha, res=res, bnf=dict(
+                    bnf_mode=2, bnf_c=C, bnf_gamma=bn.weight, bnf_beta=bn.bias, bnf_rm=bn.running_mean,
+                    bnf_rv=bn.running_var, bnf_eps=eps, bnf_momentum=mom, bnf_count=M))
+            else:
+                raw = self.act(name + ".raw", y.B, y.H, y.W, C)
+                self.conv_fwd(prog, rec, x, raw)
+                self.bn_act(prog, name + ".bn", raw, y, bn=bn, act=act, alpha=alpha, res=res)
+            return None, None
+        raw = self.act(name + ".raw", y.B, y.H, y.W, C)
+        stats = self.zbuf("fwd", name + ".s", G * rec.cout_pad * 2)
+        coef = self.buf(name + ".bn.coef", G * 4 * C, F32)
+        if FUSE_BN_FWD:
+            ctr = self.zbuf("fwd", name + ".ctr", 16)
+            kw = dict(stats=stats, act=act, prelu=alpha, res=res, preact=raw.t, group_rows=group_rows, bnf=dict(
+                bnf_mode=1, bnf_c=C, bnf_counter=ctr, bnf_gamma=bn.weight, bnf_beta=bn.bias, bnf_rm=bn.running_mean,
+                bnf_rv=bn.running_var, bnf_nbt=bn.num_batches_tracked, bnf_coef=coef, bnf_eps=eps, bnf_momentum=mom,
+                bnf_count=M // G))
+            d = self.conv_fwd(prog, rec, x, y, dry_add=False, **kw)
+            if ops.conv_is_coresident(d):
+                prog.add(d)
+                return raw, coef
+        self.conv_fwd(prog, rec, x, raw, stats=stats, group_rows=group_rows)
+        self.bn_act(prog, name + ".bn", raw, y, bn=bn, stats=stats, act=act, alpha=alpha, res=res, coef=coef,
+                    group_rows=group_rows, count=M // G)
+        return raw, coef
 
     def pick_tiles(self, M: int, n_total: int, block_n: int, total_iters: int) -> dict:
         """Tile shape / split-K choice for a conv whose grid would leave most SMs idle. Deep layers (many K iterations,
@@ -411,24 +467,26 @@ class Plan:
 
     def bn_act(self, prog, name: str, x: Act, y: Act, *, bn: Optional[nn.BatchNorm2d] = None,
                stats: Optional[torch.Tensor] = None, act=L.ACT_NONE, alpha=None, res: Optional[Act] = None,
-               leaky=0.2, res_scale=1.0, x_scale=1.0):
+               leaky=0.2, res_scale=1.0, x_scale=1.0, coef: Optional[torch.Tensor] = None, group_rows=0, count=None):
         """y = act(BN(x)) + res in one pass. Training mode: the batch statistics come from the conv epilogue's column
         sums (`stats`); the same launch publishes (scale, shift, mean, invstd) for backward and updates running_mean /
         running_var / num_batches_tracked. Eval mode: running statistics. Returns the coefficient buffer (or None)."""
         C = x.C
-        coef = None
         if bn is None:
             mode, p_bn = 0, [None] * 6
             eps = mom = 0.0
+            coef = None
         else:
-            coef = self.buf(name + ".coef", 4 * C, F32)
+            if coef is None:
+                coef = self.buf(name + ".coef", 4 * C, F32)
             mode = 1 if self.training else 2
             p_bn = [bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, coef]
             eps, mom = bn.eps, (bn.momentum if bn.momentum is not None else 0.1)
         prog.add(ops.elt(L.E_BN_ACT, p=[x.t, stats if mode == 1 else None, y.t, res.t if res is not None else None,
                                         alpha] + p_bn,
                          i=[x.M, C, x.ld, y.ld, res.ld if res is not None else 0, act, x.c0, y.c0,
-                            res.c0 if res is not None else 0, mode, x.M],
+                            res.c0 if res is not None else 0, mode, count if count is not None else x.M,
+                            group_rows if mode == 1 else 0],
                          f=[leaky, res_scale, x_scale, eps, mom]))
         return coef
 
@@ -442,6 +500,9 @@ class Plan:
         M, C = x.M, x.C
         assert g.C == C and (g2 is None or (g2.ld == g.ld and g2.C == C))
         has_bn = 1 if bn is not None else 0
+        # statistics groups only matter for the BatchNorm terms: mean(dz), mean(dz * xhat) are per group
+        G = self.groups if has_bn else 1
+        group_rows = M // 2 if G == 2 else 0
         rpb = max(32, -(-M // (2 * NUM_SMS)))
         dx = self.act(name + ".dx", x.B, x.H, x.W, C)
         prelu = act == L.ACT_PRELU
@@ -453,7 +514,7 @@ class Plan:
         sums = dacc = None
         fused = 0
         if need_reduce:
-            sums = self.zbuf("bwd", name + ".sums", 2 * C)
+            sums = self.zbuf("bwd", name + ".sums", G * 2 * C)
             dacc = self.zbuf("bwd", name + ".dalpha", 1) if prelu else None
             # The data-gradient conv that produced g may still be held by the program (conv_dgrad defers it): fold
             # the column reductions into its epilogue instead of a separate pass over g and x. The conv then stores
@@ -461,7 +522,7 @@ class Plan:
             # (with act == NONE the stored value is unchanged, e.g. the skip gradient of a residual block).
             held = prog.take_deferred(g) if (FUSE_BN_REDUCE and g2 is None and gscale == 1.0 and leaky == 0.2) else None
             if held is not None and self._fuse_bn_reduce(held, x, coef if has_bn else None, act,
-                                                         alpha if prelu else None, sums, dacc):
+                                                         alpha if prelu else None, sums, dacc, G):
                 fused = 1
             if held is not None:
                 if len(held) > 1:
@@ -469,22 +530,31 @@ class Plan:
                 else:
                     prog.add(held[0])
             if not fused:
-                prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[gp, xp, coef, alpha if prelu else None, sums, dacc, g2p],
-                                 i=[M, C, act, rpb, g.ld, x.ld, has_bn], f=[leaky, gscale]))
+                for gi in range(G):       # one launch per statistics group (row range, coefficient and sum blocks)
+                    r0, rows = gi * group_rows, (group_rows if G == 2 else M)
+                    prog.add(ops.elt(L.E_BN_BWD_REDUCE,
+                                     p=[gp + r0 * g.ld * 2, xp + r0 * x.ld * 2,
+                                        ops.ptr(coef, gi * 4 * C) if has_bn else None, alpha if prelu else None,
+                                        ops.ptr(sums, gi * 2 * C), dacc, (g2p + r0 * g.ld * 2) if g2p else None],
+                                     i=[rows, C, act, rpb, g.ld, x.ld, has_bn], f=[leaky, gscale]))
         dgamma = store.grad_slice(bn.weight) if has_bn and want_w else None
         dbeta = (store.grad_slice(bn.bias) if has_bn else bias_grad) if want_w else None
         dalpha = store.grad_slice(alpha) if (prelu and want_w) else None
         prog.add(ops.elt(L.E_BN_BWD_APPLY, p=[gp, xp, coef, sums, alpha if prelu else None, dx.t, g2p,
                                               bn.weight if has_bn else None, dgamma, dbeta, dalpha, dacc],
-                         i=[M, C, act, g.ld, x.ld, C, has_bn, fused, fused], f=[leaky, gscale]))
+                         i=[M, C, act, g.ld, x.ld, C, has_bn, fused, fused, group_rows], f=[leaky, gscale]))
         return dx
 
     @staticmethod
-    def _fuse_bn_reduce(descs, x: Act, coef, act, alpha, sums, dacc) -> bool:
+    def _fuse_bn_reduce(descs, x: Act, coef, act, alpha, sums, dacc, groups: int = 1) -> bool:
         """Patches the held data-gradient conv descriptor(s) (one, or the four output-parity classes of a stride-2
         layer) so that their epilogues accumulate sum(dz), sum(dz*x) into `sums`. Returns False (descriptors left
-        untouched) when the epilogue's aux addressing is already bound to a tensor of a different geometry."""
+        untouched) when the epilogue's aux addressing is already bound to a tensor of a different geometry, or when a
+        two-group pass does not split the descriptor's rows on a 32-row boundary."""
         xs = x.strides()
+        for d in descs:
+            if groups == 2 and ((d.N * d.Ho * d.Wo) % 64 or d.N % 2):
+                return False
         for d in descs:
             cls = getattr(d, "_parity", None)
             want = xs if cls is None else (xs[0], 2 * xs[1], 2 * xs[2])
@@ -512,6 +582,7 @@ class Plan:
             d.stats_partial = ops.ptr(sums)
             d.stats_ld = x.C
             d.dalpha_partial = ops.ptr(dacc)
+            d.group_rows = (d.N * d.Ho * d.Wo) // 2 if groups == 2 else 0
         return True
 
     def conv_dgrad(self, prog, name: str, rec: ConvRec, dy: Act, x_like: Act, *, res: Optional[Act] = None,
@@ -575,14 +646,15 @@ class Plan:
                 prog.add_group(descs)
         return target
 
-    def colsum(self, prog, name: str, g: Act, out_vec: torch.Tensor):
-        """out_vec[c] = sum over rows of g[:, c] (bias gradients)."""
+    def colsum(self, prog, name: str, g: Act, out_vec: torch.Tensor, shuffle_c4: int = 0):
+        """out_vec[c] = sum over rows of g[:, c] (bias gradients); shuffle_c4 > 0: g's columns are in PixelShuffle-packed
+        order and out_vec is the parameter-order gradient (channel 4*(r % c4) + r / c4 for column r)."""
         M, C = g.M, g.C
         rpb = max(32, -(-M // (2 * NUM_SMS)))
         sums = self.zbuf("bwd", name + ".cs", 2 * C)
         prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, g.t, None, None, sums, None, None],
                          i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2]))
-        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0]))
+        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0, shuffle_c4]))
 
     def colsum_strided(self, prog, name: str, g: Act, out_vec: torch.Tensor):
         """colsum for a channel slice of a wider buffer."""
@@ -608,6 +680,16 @@ class Plan:
         self.fwd.run()
         return self.output_fn()
 
+    def run_forward_pair(self, a: torch.Tensor, b: torch.Tensor):
+        if self.input_pair_fn is not None:
+            self.input_pair_fn(a, b)
+        else:
+            self.input_fn(torch.cat([a, b]))
+        self.fwd.run()
+        out = self.output_fn()
+        h = out.shape[0] // 2
+        return out[:h].clone(), out[h:].clone()
+
     def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None, alias: bool = False,
                      defer_comm: bool = False, early_cb=None):
         """defer_comm: no all-reduce here and the plan's own flat buffer is returned - the caller sums the gradients of
@@ -617,7 +699,7 @@ class Plan:
         if not self.training and self.has_bn:
             raise NotImplementedError("torchsr_b200: backward through eval-mode BatchNorm is not implemented; call "
                                       ".train() for gradient computation (the reference trainers do)")
-        seed = self.ingest_fn(gout)
+        seed = self.ingest_pair_fn(*gout) if isinstance(gout, tuple) else self.ingest_fn(gout)
         prog = self.backward_program(want_x, want_w, seed)
         flat = None
         store = self.store
@@ -688,9 +770,10 @@ class _Lease:
     """Returns a plan to its pool when the autograd node that holds it dies (backward done or graph dropped).
     `pending` (optional) is the module's set of outstanding calls whose backward will produce weight gradients."""
 
-    def __init__(self, plan: Plan, pending: Optional[set] = None):
+    def __init__(self, plan: Plan, pending: Optional[set] = None, state: Optional[dict] = None):
         self.plan = plan
         self.pending = pending
+        self.state = state
         if pending is not None:
             pending.add(id(plan))
 
@@ -698,6 +781,9 @@ class _Lease:
         if self.plan is not None:
             if self.pending is not None:
                 self.pending.discard(id(self.plan))
+                # no outstanding call left: gradients parked by calls whose siblings never reached backward are stale
+                if not self.pending and self.state is not None:
+                    self.state.pop("parked", None)
             self.plan.busy = False
             self.plan = None
 
@@ -748,16 +834,21 @@ class B200Module(nn.Module):
             st["plans"] = {}
         return st["store"]
 
-    def _acquire(self, shape, training: bool) -> Plan:
+    def _acquire(self, shape, training: bool, groups: int = 1) -> Plan:
         store = self._store()
-        key = (tuple(shape), bool(training))
+        key = (tuple(shape), bool(training)) if groups == 1 else (tuple(shape), bool(training), groups)
         pool = self._tsr["plans"].setdefault(key, [])
         for pl in pool:
             if not pl.busy:
                 pl.busy = True
                 return pl
-        pl = Plan(store, shape[0], shape[2], shape[3], training)
-        self._define(pl, shape)
+        pl = Plan(store, shape[0], shape[2], shape[3], training, groups)
+        try:
+            self._define(pl, shape)
+        except GroupSplitError:
+            if not pool:
+                del self._tsr["plans"][key]
+            raise
         pl.busy = True
         pool.append(pl)
         return pl
@@ -775,6 +866,44 @@ class B200Module(nn.Module):
         return _PlanFn.apply(self, needs_graph, x, *store.params)
 
 
+    def forward_pair(self, a: torch.Tensor, b: torch.Tensor, grad_halves=(True, True)):
+        """(self(a), self(b)) - two calls of the module on two batches of one shape - executed as ONE pass of its kernels
+        over the concatenated batch, with the reference's two-call semantics kept exactly: in training mode every
+        BatchNorm normalises each half with that half's batch statistics, the running statistics take two momentum
+        updates (a's first, then b's) and num_batches_tracked += 2 (reference srgan/trainer.py:446-447,
+        esrgan/trainer.py:447-449,463-464: D(high_res) then D(super_res)). grad_halves[i] False returns that half
+        detached (its input then also gets no gradient). Falls back to two calls in eval mode and for shapes whose
+        per-half row counts do not split on 32-row boundaries."""
+        if a.shape != b.shape or a.dim() != 4:
+            raise RuntimeError(f"forward_pair needs two 4-D NCHW tensors of one shape, got {tuple(a.shape)} and {tuple(b.shape)}")
+        store = self._store()
+        unsupported = self._tsr.setdefault("pair_unsupported", set())
+        shape = (2 * a.shape[0],) + tuple(a.shape[1:])
+        key = (shape, self.training)
+        if self.training and key not in unsupported:
+            a2, b2 = a.contiguous().float(), b.contiguous().float()
+            if not grad_halves[0]:
+                a2 = a2.detach()
+            if not grad_halves[1]:
+                b2 = b2.detach()
+            needs_graph = torch.is_grad_enabled() and (a2.requires_grad or b2.requires_grad or
+                                                       any(p.requires_grad for p in store.params))
+            try:
+                pa, pb = _PairFn.apply(self, needs_graph, shape, a2, b2, *store.params)
+            except GroupSplitError:
+                unsupported.add(key)
+            else:
+                return (pa if grad_halves[0] else pa.detach()), (pb if grad_halves[1] else pb.detach())
+        outs = []
+        for t, g in ((a, grad_halves[0]), (b, grad_halves[1])):
+            if g:
+                outs.append(self(t))
+            else:
+                with torch.no_grad():
+                    outs.append(self(t))
+        return outs[0], outs[1]
+
+
 class _PlanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module: B200Module, needs_graph: bool, x: torch.Tensor, *params):
@@ -787,7 +916,7 @@ class _PlanFn(torch.autograd.Function):
         out = plan.run_forward(x)
         if needs_graph:
             wants_w = any(p.requires_grad for p in store.params)
-            ctx.lease = _Lease(plan, module._tsr.setdefault("pending", set()) if wants_w else None)
+            ctx.lease = _Lease(plan, module._tsr.setdefault("pending", set()) if wants_w else None, module._tsr)
             ctx.module = module
         else:
             plan.busy = False
@@ -795,19 +924,28 @@ class _PlanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout: torch.Tensor):
+        gx, grads = _PlanFn._run_backward(ctx, gout.contiguous().float(), ctx.needs_input_grad[2],
+                                          list(ctx.needs_input_grad[3:]))
+        return (None, None, gx, *grads)
+
+    @staticmethod
+    def _run_backward(ctx, gout, want_x: bool, want: List[bool]):
+        """Shared by the one- and two-batch autograd bindings; `gout` is a tensor or a pair (either may be None)."""
         lease = ctx.lease
         plan = lease.plan
         if plan is None:
             raise RuntimeError("torchsr_b200: backward through the same module call twice is not supported "
                                "(activations live in a pooled workspace)")
-        want_x = ctx.needs_input_grad[2]
-        want = list(ctx.needs_input_grad[3:])
         want_w = any(want)
         st = ctx.module._tsr
         ddp = st.get("ddp")
         merge = want_w and st.get("merge_pending_grads", False)
+        # Aliased gradients (views of the plan's flat buffer) are only handed out when autograd will ASSIGN them: with a
+        # .grad already present (gradient accumulation, zero_grad(set_to_none=False)) AccumulateGrad would add the
+        # buffer to a tensor that may alias it, so those cases get a private copy.
+        safe_alias = all(p.grad is None for p in plan.store.params)
         if not merge:
-            gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ddp, st.get("alias_grads", False))
+            gx, flat = plan.run_backward(gout, want_x, want_w, ddp, st.get("alias_grads", False) and safe_alias)
         else:
             # Several calls of the module feed one loss (D(real) and D(fake), trainer.py): every backward but the last
             # parks its flat gradient; the last one adds the parked ones to its own (one kernel per parked call and
@@ -830,14 +968,14 @@ class _PlanFn(torch.autograd.Function):
                     mine = plan.grads.flat
                     for p in parked:
                         cur.wait_event(p["ev_early"])
-                        mine[offset:].add_(p["flat"][offset:])
+                        _add_flat(mine[offset:], p["flat"][offset:])
                     if dist_on:
                         allreduce_async_flat(mine[offset:], ddp)
                     info["early_done"] = offset
 
             # single GPU: nothing to send early - the whole backward runs as one range (the classifier's weight
             # gradient then overlaps the convolutional backward on the side branch)
-            gx, flat = plan.run_backward(gout.contiguous().float(), want_x, want_w, ddp, True, defer_comm=True,
+            gx, flat = plan.run_backward(gout, want_x, want_w, ddp, True, defer_comm=True,
                                          early_cb=early_cb if dist_on else None)
             if others:
                 info["flat"] = flat
@@ -850,12 +988,53 @@ class _PlanFn(torch.autograd.Function):
                 for p in st.pop("parked", []):
                     cur.wait_event(p["ev_done"])
                     if head is None:
-                        flat.add_(p["flat"])
+                        _add_flat(flat, p["flat"])
                     else:
-                        flat[:head].add_(p["flat"][:head])
+                        _add_flat(flat[:head], p["flat"][:head])
                 if dist_on:
                     allreduce_async_flat(flat if head is None else flat[:head], ddp)
                     ddp.wait()
+                if not safe_alias:
+                    flat = flat.clone()
         grads = plan.store.grads_from_flat(flat, want) if (want_w and flat is not None) else [None] * len(want)
         lease.release()
-        return (None, None, gx, *grads)
+        return gx, grads
+
+
+def _add_flat(dst: torch.Tensor, src: torch.Tensor):
+    """dst += src on flat fp32 gradient slices (axpby_f32_kernel; offsets are multiples of 4 elements)."""
+    ops.run_now(ops.elt(L.E_AXPBY_F32, p=[dst, src, dst, None], i=[dst.numel()], f=[1.0, 1.0]))
+
+
+class _PairFn(torch.autograd.Function):
+    """Autograd binding of B200Module.forward_pair: one plan over the concatenated (a | b) batch, two outputs."""
+
+    @staticmethod
+    def forward(ctx, module: B200Module, needs_graph: bool, shape, a: torch.Tensor, b: torch.Tensor, *params):
+        plan = module._acquire(shape, module.training, groups=2)
+        store = plan.store
+        store.ensure_packed()
+        if module.training and module._tsr.get("ddp") is not None:
+            from .dist import sync_buffers
+            sync_buffers(module)
+        pa, pb = plan.run_forward_pair(a, b)
+        ctx.set_materialize_grads(False)
+        if needs_graph:
+            wants_w = any(p.requires_grad for p in store.params)
+            ctx.lease = _Lease(plan, module._tsr.setdefault("pending", set()) if wants_w else None, module._tsr)
+            ctx.module = module
+        else:
+            plan.busy = False
+        return pa, pb
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        fix = lambda g: g.contiguous().float() if g is not None else None  # noqa: E731
+        want_x = ctx.needs_input_grad[3] or ctx.needs_input_grad[4]
+        gx, grads = _PlanFn._run_backward(ctx, (fix(ga), fix(gb)), want_x, list(ctx.needs_input_grad[5:]))
+        gxa = gxb = None
+        if gx is not None:
+            h = gx.shape[0] // 2
+            gxa = gx[:h] if ctx.needs_input_grad[3] else None
+            gxb = gx[h:] if ctx.needs_input_grad[4] else None
+        return (None, None, None, gxa, gxb, *grads)

@@ -7,9 +7,10 @@ generator step (the reference runs it twice on unchanged weights, :462), the dis
 images for the generator step (its discarded weight gradients are not computed), and bf16 kernels replace fp16
 autocast + GradScaler."""
 import torch
-from torch import Tensor, nn
+from torch import Tensor
 
 from .. import dist as tdist
+from .. import losses
 from ..srgan.trainer import SRGANTrainer
 from .discriminator import Discriminator
 from .generator import Generator
@@ -28,9 +29,11 @@ class ESRGANTrainer(SRGANTrainer):
             tdist.attach(self.discriminator, broadcast_buffers=False)
 
     def _initialize_loss(self) -> None:
-        self.l1_loss = nn.L1Loss().to(self.device)
-        self.bce_loss = nn.BCEWithLogitsLoss().to(self.device)
+        # same attribute names as the reference (:163-165); the criteria run on this repo's reduction kernels
+        self.l1_loss = losses.L1Loss()
+        self.bce_loss = losses.BCEWithLogitsLoss()
         self.vgg_loss = VGGLoss().to(self.device)
+        self._one = torch.ones((), dtype=torch.float32, device=self.device)
 
     def _pretrain_step(self, low_res: Tensor, high_res: Tensor) -> Tensor:
         """reference :378-390: G forward, L1, backward, Adam."""
@@ -38,7 +41,7 @@ class ESRGANTrainer(SRGANTrainer):
         high_res = high_res.to(self.device, non_blocking=True)
         self.psnr_optimizer.zero_grad()
         loss = self.l1_loss(self.generator(low_res), high_res)
-        loss.backward()
+        loss.backward(self._one)
         self.psnr_optimizer.step()
         return loss.detach()
 
@@ -46,30 +49,26 @@ class ESRGANTrainer(SRGANTrainer):
         """reference :435-484 (relativistic average GAN)."""
         low_res = low_res.to(self.device, non_blocking=True)
         high_res = high_res.to(self.device, non_blocking=True)
-        batch_size = low_res.size(0)
-        real_label = torch.full((batch_size, 1), 1, dtype=low_res.dtype, device=self.device)
-        fake_label = torch.full((batch_size, 1), 0, dtype=low_res.dtype, device=self.device)
 
         self.disc_optimizer.zero_grad()
         super_res = self.generator(low_res)
-        real_output = self.discriminator(high_res)
-        fake_output = self.discriminator(super_res.detach())
-        disc_loss_real = self.bce_loss(real_output - torch.mean(fake_output), real_label)
-        disc_loss_fake = self.bce_loss(fake_output - torch.mean(real_output), fake_label)
-        disc_loss = (disc_loss_real + disc_loss_fake) / 2
-        disc_loss.backward()
+        # :447-449 two separate D calls (BatchNorm statistics per call, real first) -> one pass, statistics per half
+        real_output, fake_output = self.discriminator.forward_pair(high_res, super_res.detach())
+        # (BCEwL(real - mean(fake), 1) + BCEwL(fake - mean(real), 0)) / 2   (:451-453), one reduction launch
+        disc_loss = losses.relativistic_d(real_output, fake_output, scale=0.5)
+        disc_loss.backward(self._one)
         self.disc_optimizer.step()
 
         self.gen_optimizer.zero_grad()
         with tdist.frozen(self.discriminator):
-            with torch.no_grad():
-                real_output = self.discriminator(high_res)
-            fake_output = self.discriminator(super_res)
-        pixel_loss = self.l1_loss(super_res, high_res)
+            # :463-464 D(high_res.detach()) then D(super_res), updated D weights: one pass again; the real half only
+            # feeds a mean that is a constant of the generator step
+            real_output, fake_output = self.discriminator.forward_pair(high_res, super_res, grad_halves=(False, True))
+        pixel_loss = losses.l1(super_res, high_res, scale=0.01)
         content_loss = self.vgg_loss(super_res, high_res)
-        adversarial_loss = self.bce_loss(fake_output - torch.mean(real_output), real_label)
-        gen_loss = 0.01 * pixel_loss + 1 * content_loss + 0.005 * adversarial_loss
-        gen_loss.backward()
+        adversarial_loss = losses.relativistic_g(fake_output, real_output, scale=0.005)
+        gen_loss = losses.total(pixel_loss, content_loss, adversarial_loss)     # 0.01 L1 + 1 VGG + 0.005 adv (:466-469)
+        gen_loss.backward(self._one)
         self.gen_optimizer.step()
         self.generator.zero_grad()
         return gen_loss.detach()

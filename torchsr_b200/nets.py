@@ -40,20 +40,12 @@ def srgan_generator_records(m) -> List[ConvRec]:
 
 def residual_block_stage(plan: Plan, prog, name: str, blk, ra: ConvRec, rb: ConvRec, x: Act) -> Act:
     """conv-BN-PReLU-conv-BN + x (torchsr/srgan/residual.py:86-91)."""
-    B, H, W, C, M = x.B, x.H, x.W, x.C, x.M
-    tr = plan.training
-    plan.has_bn = True
-    raw1 = plan.act(name + ".raw1", B, H, W, C)
-    s1 = plan.stats_buf(name + ".s1", M, C) if tr else None
-    plan.conv_fwd(prog, ra, x, raw1, stats=s1)
-    a1 = plan.act(name + ".a1", B, H, W, C)
+    B, H, W, C = x.B, x.H, x.W, x.C
     alpha = blk.prelu.weight
-    coef1 = plan.bn_act(prog, name + ".bn1", raw1, a1, bn=blk.bn1, stats=s1, act=L.ACT_PRELU, alpha=alpha)
-    raw2 = plan.act(name + ".raw2", B, H, W, C)
-    s2 = plan.stats_buf(name + ".s2", M, C) if tr else None
-    plan.conv_fwd(prog, rb, a1, raw2, stats=s2)
+    a1 = plan.act(name + ".a1", B, H, W, C)
+    raw1, coef1 = plan.conv_bn_act(prog, name + ".c1", ra, x, a1, bn=blk.bn1, act=L.ACT_PRELU, alpha=alpha)
     y = plan.act(name + ".y", B, H, W, C)
-    coef2 = plan.bn_act(prog, name + ".bn2", raw2, y, bn=blk.bn2, stats=s2, act=L.ACT_NONE, res=x)
+    raw2, coef2 = plan.conv_bn_act(prog, name + ".c2", rb, a1, y, bn=blk.bn2, act=L.ACT_NONE, res=x)
 
     def bwd(bp, g, want_x, want_w):
         d2 = plan.norm_act_bwd(bp, name + ".bn2", g, raw2, coef=coef2, bn=blk.bn2, act=L.ACT_NONE, want_w=want_w)
@@ -86,16 +78,11 @@ def subpixel_stage(plan: Plan, prog, name: str, layer, rec: ConvRec, x: Act, con
         assert g is dconv, "the consumer of a sub-pixel stage must honour its gradient hook"
         if want_w:
             bp.add(ops.elt(L.E_SUM_FINALIZE, p=[dap, store.grad_slice(alpha)], i=[1, 0], f=[1.0]))
-            plan.colsum(bp, name + ".db", g, store.bias_grad_packed(rec))
+            plan.colsum(bp, name + ".db", g, store.grad_slice(rec.bias), shuffle_c4=rec.cout // 4)
             plan.conv_wgrad(bp, rec, x, g)
         return plan.conv_dgrad(bp, name, rec, g, x)
 
-    def unpermute_bias_grad():
-        c4 = rec.cout // 4
-        store.grad_slice(rec.bias).view(c4, 4).copy_(store.bias_grad_packed(rec).view(4, c4).t())
-
     plan.tape.append(bwd)
-    plan.post_backward.append(unpermute_bias_grad)
     return out
 
 
@@ -128,13 +115,9 @@ def define_srgan_generator(m, plan: Plan, shape):
         x = residual_block_stage(plan, fwd, f"blocks.{i}", blk, R[f"blocks.{i}.conv1"], R[f"blocks.{i}.conv2"], x)
 
     rc2, bn2 = R["conv2.0"], m.conv2[1]
-    plan.has_bn = True
     xt = x
-    raw = plan.act("conv2.raw", B, H, W, 64)
-    st = plan.stats_buf("conv2.s", raw.M, 64) if plan.training else None
-    plan.conv_fwd(fwd, rc2, xt, raw, stats=st)
     s = plan.act("trunk", B, H, W, 64)
-    coef = plan.bn_act(fwd, "conv2.bn", raw, s, bn=bn2, stats=st, act=L.ACT_NONE, res=c1)
+    raw, coef = plan.conv_bn_act(fwd, "conv2", rc2, xt, s, bn=bn2, act=L.ACT_NONE, res=c1)
 
     def bwd_conv2(bp, g, want_x, want_w):
         plan.slots["skip"] = g          # out = conv1 + conv2 (generator.py:79): the same gradient reaches conv1
@@ -283,11 +266,8 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
         rk, bn = R[f"features.{k}"], m.features[k + 1]
         Ho = (prev.H + 2 * rk.pad - rk.k) // rk.stride + 1
         Wo = (prev.W + 2 * rk.pad - rk.k) // rk.stride + 1
-        raw = plan.act(f"f{k}.raw", B, Ho, Wo, rk.cout)
-        st = plan.stats_buf(f"f{k}.s", raw.M, rk.cout_pad) if plan.training else None
-        plan.conv_fwd(fwd, rk, prev, raw, stats=st)
         a = plan.act(f"f{k}.act", B, Ho, Wo, rk.cout)
-        coef = plan.bn_act(fwd, f"f{k}.bn", raw, a, bn=bn, stats=st, act=L.ACT_LEAKY)
+        raw, coef = plan.conv_bn_act(fwd, f"f{k}", rk, prev, a, bn=bn, act=L.ACT_LEAKY)
 
         def bwd(bp, g, want_x, want_w, rk=rk, bn=bn, raw=raw, coef=coef, xin=prev, k=k):
             d = plan.norm_act_bwd(bp, f"f{k}", g, raw, coef=coef, bn=bn, act=L.ACT_LEAKY, want_w=want_w)
@@ -353,6 +333,24 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
     def ingest_fn(gout):
         gbuf[:B].copy_(gout.reshape(-1))
         return None
+
+    # forward_pair: the (real | fake) batches land in the two halves of the im2row buffer / of the output gradient
+    def input_pair_fn(xa, xb):
+        h = B // 2
+        for t, off in ((xa, 0), (xb, h)):
+            ops.run_now(ops.elt(L.E_IM2ROW, p=[t, ops.ptr(E0.t, off * H * W * r0.epad)],
+                                i=[h, 3, H, W, r0.k, r0.k, r0.pad, r0.pad, 1, r0.epad]))
+
+    def ingest_pair_fn(ga, gb):
+        h = B // 2
+        for g, off in ((ga, 0), (gb, h)):
+            if g is None:      # that half's output did not reach the loss
+                ops.run_now(ops.elt(L.E_ZERO, p=[ops.ptr(gbuf, off)], i=[h * 4]))
+            else:
+                gbuf[off:off + h].copy_(g.reshape(-1))
+        return None
+
+    plan.input_pair_fn, plan.ingest_pair_fn = input_pair_fn, ingest_pair_fn
 
     def grad_input_fn():
         dE0 = plan.cur_g

@@ -123,7 +123,9 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
               act=L.ACT_NONE, out_preact=None, res=None, bwd_z=None, bwd_act=L.ACT_NONE, aux=(0, 0, 0), aux_ch_off=0,
               dalpha_partial=None, stats_partial=None, stats_ld=0, acc_scale=1.0, leaky=0.2, shuf_c=64, res2=None,
               res_scale=1.0, res2_scale=1.0, res_cols=0, w_static=True, bnr_x=None, bnr_coef=None, bnr_prelu=None,
-              bnr_act=L.ACT_NONE, bnr_c=0, splits=1, ws=None, tile_counters=None, ws_ld=0) -> ConvDesc:
+              bnr_act=L.ACT_NONE, bnr_c=0, splits=1, ws=None, tile_counters=None, ws_ld=0, group_rows=0, bnf_mode=0,
+              bnf_c=0, bnf_counter=None, bnf_gamma=None, bnf_beta=None, bnf_rm=None, bnf_rv=None, bnf_nbt=None,
+              bnf_coef=None, bnf_count=0, bnf_eps=1e-5, bnf_momentum=0.1) -> ConvDesc:
     d = ConvDesc()
     d.x, d.w = ptr(x), ptr(w)
     d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
@@ -149,7 +151,23 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     d.res2, d.res_scale, d.res2_scale, d.res_cols = ptr(res2), res_scale, res2_scale, res_cols
     d.w_static = int(w_static)
     d.bnr_x, d.bnr_coef, d.bnr_prelu, d.bnr_act, d.bnr_c = ptr(bnr_x), ptr(bnr_coef), ptr(bnr_prelu), bnr_act, bnr_c
+    d.group_rows, d.bnf_mode, d.bnf_c, d.bnf_count = group_rows, bnf_mode, bnf_c, bnf_count
+    d.bnf_counter, d.bnf_gamma, d.bnf_beta = ptr(bnf_counter), ptr(bnf_gamma), ptr(bnf_beta)
+    d.bnf_rm, d.bnf_rv, d.bnf_nbt, d.bnf_coef = ptr(bnf_rm), ptr(bnf_rv), ptr(bnf_nbt), ptr(bnf_coef)
+    d.bnf_eps, d.bnf_momentum = bnf_eps, bnf_momentum
     return d
+
+
+def conv_is_coresident(d: ConvDesc) -> bool:
+    """True when every CTA of this conv's launch fits on the device at once (needed by the fused training-mode
+    BatchNorm, whose CTAs meet at a grid barrier). Dry mode (no device): 2 CTAs on each of 148 SMs."""
+    tiles = ((d.N * d.Ho * d.Wo + 127) // 128) * (d.cout_pad // d.block_n)
+    if DRY:
+        return tiles <= 2 * 148
+    lib = L.load()
+    ctas, cap = C.c_int(0), C.c_int(0)
+    L.check(lib.tsr_conv_bnf_capacity(C.byref(d), C.byref(ctas), C.byref(cap)))
+    return 0 < ctas.value <= cap.value
 
 
 def dgrad_s2_descs(*, dy, N, Hy, Wy, Cout, dy_ld, wt, Cin, cin_pad, block_n, out, Hx, Wx, out_ld, n_valid,
@@ -286,6 +304,26 @@ def validate_conv(d: ConvDesc):
             if d.bnr_c < d.n_valid:
                 raise ExtentError("bnr_c smaller than the stored column count")
             _need("conv bnr_coef", d.bnr_coef, 4 * d.bnr_c * 4)
+    groups = 2 if d.group_rows else 1
+    if d.group_rows and (d.group_rows % 32 or d.a_mode != 0 or not 0 < d.group_rows < d.N * d.Ho * d.Wo):
+        raise ExtentError("group_rows must be a multiple of 32 inside (0, M) of an im2col conv")
+    if groups == 2 and d.stats_partial:
+        _need("conv stats_partial (2 groups)", d.stats_partial, 2 * d.stats_ld * 2 * 4)
+    if groups == 2 and d.bnr_coef:
+        _need("conv bnr_coef (2 groups)", d.bnr_coef, 2 * 4 * d.bnr_c * 4)
+    if d.bnf_mode:
+        if d.bnf_mode not in (1, 2) or d.a_mode != 0 or d.bias or d.bwd_z or d.bnr_x or d.out_mode != L.OUT_LINEAR:
+            raise ExtentError("fused BatchNorm forward: unsupported epilogue combination")
+        if d.bnf_c < d.n_valid:
+            raise ExtentError("bnf_c smaller than the stored column count")
+        for nm, pp, nb in (("gamma", d.bnf_gamma, d.bnf_c * 4), ("beta", d.bnf_beta, d.bnf_c * 4),
+                           ("running_mean", d.bnf_rm, d.bnf_c * 4), ("running_var", d.bnf_rv, d.bnf_c * 4),
+                           ("num_batches_tracked", d.bnf_nbt, 8), ("coef", d.bnf_coef, groups * 4 * d.bnf_c * 4),
+                           ("counter", d.bnf_counter, (d.cout_pad // d.block_n) * 4)):
+            if pp:
+                _need("conv bnf " + nm, pp, nb)
+        if d.bnf_mode == 1 and not (d.stats_partial and d.bnf_counter and d.bnf_count > 0):
+            raise ExtentError("training-mode fused BatchNorm needs stats_partial, bnf_counter and bnf_count")
     if d.n_valid % 16 or d.n_valid > d.cout_pad:
         raise ExtentError("conv n_valid must be a multiple of 16 and <= cout_pad")
     for off in (d.out_ch_off, d.aux_ch_off):
@@ -328,9 +366,12 @@ def _elt_extents(d: EltDesc):
         M, C = i[0], i[1]
         if 256 % (C // 8) or C % 8:
             raise ExtentError("BN_ACT needs C/8 to divide 256")
-        return [(0, ((M - 1) * i[2] + i[6] + C) * 2), (1, 2 * C * 4), (2, ((M - 1) * i[3] + i[7] + C) * 2),
+        G = 2 if i[11] else 1
+        if i[11] and (i[11] % 8 or not 0 < i[11] < M):
+            raise ExtentError("BN_ACT group_rows must lie inside (0, M)")
+        return [(0, ((M - 1) * i[2] + i[6] + C) * 2), (1, G * 2 * C * 4), (2, ((M - 1) * i[3] + i[7] + C) * 2),
                 (3, ((M - 1) * i[4] + i[8] + C) * 2), (4, 4), (5, C * 4), (6, C * 4), (7, C * 4), (8, C * 4), (9, 8),
-                (10, 4 * C * 4)]
+                (10, G * 4 * C * 4)]
     if k == L.E_BN_BWD_REDUCE:
         M, C = i[0], i[1]
         return [(0, ((M - 1) * i[4] + C) * 2), (1, ((M - 1) * i[5] + C) * 2), (2, 4 * C * 4 if i[6] else 0), (3, 4),
@@ -339,8 +380,9 @@ def _elt_extents(d: EltDesc):
         M, C = i[0], i[1]
         if 256 % (C // 8) or C % 8:
             raise ExtentError("BN_BWD_APPLY needs C/8 to divide 256")
-        return [(0, ((M - 1) * i[3] + C) * 2), (1, ((M - 1) * i[4] + C) * 2), (2, 4 * C * 4 if i[6] else 0),
-                (3, C * 8), (4, 4), (5, ((M - 1) * i[5] + C) * 2), (6, ((M - 1) * i[3] + C) * 2), (7, C * 4),
+        G = 2 if (i[9] and i[6]) else 1
+        return [(0, ((M - 1) * i[3] + C) * 2), (1, ((M - 1) * i[4] + C) * 2), (2, G * 4 * C * 4 if i[6] else 0),
+                (3, G * C * 8), (4, 4), (5, ((M - 1) * i[5] + C) * 2), (6, ((M - 1) * i[3] + C) * 2), (7, C * 4),
                 (8, C * 4), (9, C * 4), (10, 4), (11, 4)]
     if k == L.E_COLSUM_FINALIZE:
         return [(0, i[0] * i[2] * 8), (1, i[1] * 4)]
@@ -375,6 +417,10 @@ def _elt_extents(d: EltDesc):
         return [(0, i[0] * (4 if i[1] == 0 else 2)), (1, i[0] * (2 if i[1] == 0 else 4))]
     if k == L.E_CHANSUM_NCHW:
         return [(0, i[0] * i[1] * i[2] * 4), (1, i[3] * i[1] * 8)]
+    if k == L.E_GAN_LOSS:
+        return [(0, i[0] * 4), (1, i[1] * 4), (2, 4), (3, i[0] * 4), (4, i[1] * 4), (5, i[0] * 4)]
+    if k == L.E_AXPBY_F32:
+        return [(0, i[0] * 4), (1, i[0] * 4), (2, i[0] * 4), (3, 4)]
     return []
 
 

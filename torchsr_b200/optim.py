@@ -21,20 +21,25 @@ class FusedAdam(torch.optim.Optimizer):
         if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or eps < 0.0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
-        self._tables: Dict[int, dict] = {}
+        self._tables: Dict[int, Dict[tuple, dict]] = {}     # group index -> {address-set key -> table}
 
     # ---- per-group device state
     def _group_state(self, gi: int, group) -> dict:
-        st = self._tables.get(gi)
+        """Device table (parameter / gradient / state / pack pointers) of one param group for the CURRENT set of
+        gradient addresses. One table per distinct address set is kept for the optimizer's lifetime: a captured CUDA
+        graph holds the table's device pointer in its Adam kernel node, so a table must never be freed or rewritten
+        when another batch shape (a ragged last batch run eagerly) brings other gradient buffers."""
+        variants = self._tables.setdefault(gi, {})
         params = [p for p in group["params"] if p.grad is not None]
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params) + \
             tuple(id(s) for s in self._stores_of(params))
-        if st is not None and st["key"] == key:
+        st = variants.get(key)
+        if st is not None:
             return st
         dev = params[0].device
         if dev.type != "cuda" and not ops.DRY:
             raise L.TorchSRB200Error("torchsr_b200.optim.FusedAdam runs only on CUDA parameters (no CPU fallback)")
-        old = st
+        old = next(iter(variants.values()), None)
         st = dict(key=key, params=params)
         # optimizer state lives in two flat arenas; self.state[p] exposes per-parameter views (state_dict compatible)
         if old is not None and [id(p) for p in old["params"]] == [id(p) for p in params]:
@@ -94,7 +99,7 @@ class FusedAdam(torch.optim.Optimizer):
         st["table"] = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
         st["table"].copy_(host, non_blocking=True)
         st["n"], st["blocks"], st["stores"] = len(params), blocks, stores
-        self._tables[gi] = st
+        variants[key] = st
         return st
 
     @staticmethod

@@ -6,15 +6,15 @@ ImageNet weights (`vgg19(pretrained=True)`); offline they come from the torch-hu
 TORCHSR_VGG_WEIGHTS, or - for benchmarks and parity runs, where only the arithmetic matters - from a seeded random
 initialisation (TORCHSR_VGG_WEIGHTS=random).
 
-On a CUDA device the feature extractor runs on this repo's kernels (nets.define_vgg: implicit-GEMM convs with the ReLU
-fused into the epilogue, NHWC bf16 activations, max-pool / ReLU backward kernels, data gradients only - the network is
-frozen); TORCHSR_VGG_IMPL=torch selects PyTorch/cuDNN under bf16 instead. On the CPU it is plain PyTorch fp32."""
+The feature extractor runs on this repo's kernels (nets.define_vgg: implicit-GEMM convs with the ReLU fused into the
+epilogue, NHWC bf16 activations, max-pool / ReLU backward kernels, data gradients only - the network is frozen) and the
+feature L1 on losses.l1. There is no PyTorch/cuDNN or CPU execution path: inputs on another device raise."""
 import os
 
 import torch
 from torch import Tensor, nn
 
-from .. import nets
+from .. import losses, nets
 from ..engine import B200Module, Plan
 
 
@@ -59,12 +59,8 @@ class VGGLoss(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         r = super()._apply(fn, *a, **kw)
-        self._bf16 = None
         object.__setattr__(self, "_b200", None)
         return r
-
-    def _use_b200(self, x: Tensor) -> bool:
-        return x.is_cuda and os.environ.get("TORCHSR_VGG_IMPL", "b200") != "torch"
 
     def _features_b200(self) -> VGGFeaturesB200:
         if getattr(self, "_b200", None) is None:
@@ -72,20 +68,8 @@ class VGGLoss(nn.Module):
             object.__setattr__(self, "_b200", VGGFeaturesB200(self.features))
         return self._b200
 
-    def _features_bf16(self):
-        """bf16 channels_last copy of the frozen feature extractor (made once; the weights never change)."""
-        if getattr(self, "_bf16", None) is None:
-            import copy
-            f = copy.deepcopy(self.features).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
-            object.__setattr__(self, "_bf16", f.eval())
-        return self._bf16
-
     def _extract(self, x: Tensor) -> Tensor:
-        if self._use_b200(x):
-            return self._features_b200()(x)
-        if x.is_cuda:
-            return self._features_bf16()(x.to(dtype=torch.bfloat16, memory_format=torch.channels_last)).float()
-        return self.features(x)
+        return self._features_b200()(x)      # raises TorchSRB200Error off a CUDA sm_100 device
 
     def target_features(self, target: Tensor) -> Tensor:
         """Features of the (constant) target image; lets a trainer compute them early, on another stream."""
@@ -93,7 +77,7 @@ class VGGLoss(nn.Module):
             return self._extract(target)
 
     def from_features(self, source: Tensor, target_features: Tensor) -> Tensor:
-        return torch.nn.functional.l1_loss(self._extract(source), target_features)
+        return losses.l1(self._extract(source), target_features)
 
     def forward(self, source: Tensor, target: Tensor) -> Tensor:
         return self.from_features(source, self.target_features(target))

@@ -17,9 +17,11 @@ from math import log10
 from typing import Optional
 
 import torch
-from torch import Tensor, nn, optim
+from torch import Tensor, optim
 
 from .. import dist as tdist
+from .. import losses
+from ..optim import FusedAdam
 from .discriminator import Discriminator
 from .generator import Generator
 from .loss import VGGLoss
@@ -57,7 +59,7 @@ class SRGANTrainer:
     def _configure_modules(self) -> None:
         """Trainer-owned execution settings of the drop-in modules: gradients are handed to autograd as views of the
         plan's flat buffer (no copy) - valid here because every backward is preceded by zero_grad() - and a second
-        CUDA stream carries the work that depends only on the real batch."""
+        CUDA stream carries the VGG content branch."""
         for m in (self.generator, self.discriminator):
             # gradients are handed to autograd as views of the plan's flat buffer (stable addresses, no copy); calls of
             # one module that feed one loss - D(real) and D(fake) - are summed by the last of their backward passes
@@ -65,9 +67,7 @@ class SRGANTrainer:
             m._tsr["alias_grads"] = True
             m._tsr["merge_pending_grads"] = True
         cuda = self.device.type == 'cuda'
-        # stream B shares the critical path (D(real)), stream V only carries the VGG content branch: lowest priority
         prio = lambda name, default: int(os.environ.get(name, default))  # noqa: E731
-        self._side = torch.cuda.Stream(device=self.device, priority=prio("TSR_PRIO_SIDE", -1)) if cuda else None
         self._vgg_stream = torch.cuda.Stream(device=self.device, priority=prio("TSR_PRIO_VGG", -1)) if cuda else None
         self._capture_stream = torch.cuda.Stream(device=self.device, priority=prio("TSR_PRIO_MAIN", -1)) if cuda else None
 
@@ -82,22 +82,18 @@ class SRGANTrainer:
             tdist.attach(self.discriminator, broadcast_buffers=False)
 
     def _initialize_loss(self) -> None:
-        self.mse_loss = nn.MSELoss().to(self.device)
-        self.bce_loss = nn.BCELoss().to(self.device)
+        # same attribute names as the reference (:163-165); the criteria run on this repo's reduction kernels
+        self.mse_loss = losses.MSELoss()
+        self.bce_loss = losses.BCELoss()
         self.vgg_loss = VGGLoss().to(self.device)
+        # upstream gradient of every scalar loss: passed explicitly so that backward() launches no fill kernel
+        self._one = torch.ones((), dtype=torch.float32, device=self.device)
 
     def _initialize_optimizers(self) -> None:
-        cuda = self.device.type == 'cuda'
         # Adam on this repo's kernels (optim.FusedAdam: one launch updates parameters, state and the packed bf16 weight
         # copies); tensor lr + device-side step counter so that a whole training step can be replayed as one CUDA graph
         # (graph_step) while StepLR keeps working (schedulers fill_() a tensor learning rate in place).
-        # TSR_OPTIM=torch selects torch.optim.Adam(fused=True, capturable=True) instead.
-        if cuda and os.environ.get("TSR_OPTIM", "b200") != "torch":
-            from ..optim import FusedAdam
-            mk = lambda params: FusedAdam(params, lr=torch.tensor(0.0001, device=self.device), betas=(0.9, 0.999))  # noqa: E731
-        else:
-            mk = lambda params: optim.Adam(params, lr=torch.tensor(0.0001, device=self.device) if cuda else 0.0001,  # noqa: E731
-                                           betas=(0.9, 0.999), fused=cuda, capturable=cuda)
+        mk = lambda params: FusedAdam(params, lr=torch.tensor(0.0001, device=self.device), betas=(0.9, 0.999))  # noqa: E731
         self.psnr_optimizer = mk(self.generator.parameters())
         self.disc_optimizer = mk(self.discriminator.parameters())
         self.gen_optimizer = mk(self.generator.parameters())
@@ -131,7 +127,7 @@ class SRGANTrainer:
         self.psnr_optimizer.zero_grad()
         super_res = self.generator(low_res)
         loss = self.mse_loss(super_res, high_res)
-        loss.backward()
+        loss.backward(self._one)
         self.psnr_optimizer.step()
         return loss.detach()
 
@@ -139,26 +135,15 @@ class SRGANTrainer:
         """One GAN step, statement for statement the reference's `_gan_loop` (:435-469)."""
         low_res = low_res.to(self.device, non_blocking=True)
         high_res = high_res.to(self.device, non_blocking=True)
-        batch_size = low_res.size(0)
-        real_label = torch.full((batch_size, 1), 1, dtype=low_res.dtype, device=self.device)
-        fake_label = torch.full((batch_size, 1), 0, dtype=low_res.dtype, device=self.device)
-
-        cur, side, vs = torch.cuda.current_stream(self.device), self._side, self._vgg_stream
+        cur, vs = torch.cuda.current_stream(self.device), self._vgg_stream
         split_vgg = hasattr(self.vgg_loss, 'from_features')
         self.discriminator.zero_grad()
-        # Three dependency chains, same arithmetic as the reference's sequential statements (:444-468):
-        #   stream A (current): G forward -> D(fake) -> discriminator step -> D(super_res) -> G backward -> Adam
-        #   stream B (side):    D(real) forward (and, in backward, its gradients); D(fake) still follows D(real), so
-        #                       the BatchNorm running statistics are updated in the reference's order
-        #   stream V: everything of the VGG content loss - target features, features of super_res and
-        #                       the gradient of the content loss w.r.t. super_res. None of it depends on the
-        #                       discriminator, so it fills idle SMs during the discriminator step instead of sitting
-        #                       on the critical path of the generator step.
-        side.wait_stream(cur)
+        # Two dependency chains, same arithmetic as the reference's sequential statements (:444-468):
+        #   stream A (current): G forward -> D(real | fake) -> discriminator step -> D(super_res) -> G backward -> Adam
+        #   stream V: everything of the VGG content loss - target features, features of super_res and the gradient of
+        #             the content loss w.r.t. super_res. None of it depends on the discriminator, so it fills idle SMs
+        #             during the discriminator step instead of sitting on the critical path of the generator step.
         vs.wait_stream(cur)
-        with torch.cuda.stream(side):
-            p_real = self.discriminator(high_res)
-            done_real = side.record_event()
         if split_vgg:
             with torch.cuda.stream(vs):
                 hr_feats = self.vgg_loss.target_features(high_res)
@@ -171,33 +156,32 @@ class SRGANTrainer:
                 # exactly what autograd does at the super_res node for gen_loss = content + 0.001 * adversarial
                 sr_leaf = super_res.detach().requires_grad_(True)
                 content_loss = self.vgg_loss.from_features(sr_leaf, hr_feats)
-                (g_content,) = torch.autograd.grad(content_loss, sr_leaf)
+                (g_content,) = torch.autograd.grad(content_loss, sr_leaf, grad_outputs=self._one)
                 content_loss = content_loss.detach()
                 done_content = vs.record_event()
-        cur.wait_event(done_real)
-        p_fake = self.discriminator(super_res.detach())
-        p_real.record_stream(cur)
-        disc_loss_real = self.bce_loss(p_real, real_label)
-        disc_loss_fake = self.bce_loss(p_fake, fake_label)
-        disc_loss = disc_loss_real + disc_loss_fake
-        disc_loss.backward()
-        cur.wait_stream(side)      # D(real)'s backward ran on stream B
+        # reference :446-447 calls D(high_res) and D(super_res.detach()) separately: separate BatchNorm batch statistics
+        # and two running-statistics updates, real first. forward_pair runs both batches through ONE pass of the
+        # discriminator's kernels with exactly those semantics (statistics per half, engine.py bn_groups).
+        p_real, p_fake = self.discriminator.forward_pair(high_res, super_res.detach())
+        # BCE(p_real, 1) + BCE(p_fake, 0) (:446-448) in one reduction launch, constant labels
+        disc_loss = losses.bce(p_real, 1.0, p_fake, 0.0)
+        disc_loss.backward(self._one)
         self.disc_optimizer.step()
 
         self.generator.zero_grad()
         with tdist.frozen(self.discriminator):
-            adversarial_loss = self.bce_loss(self.discriminator(super_res), real_label)
+            adversarial_loss = losses.bce(self.discriminator(super_res), 1.0, scale=0.001)     # 0.001 * BCE (:456-457)
         if split_vgg:
-            (g_adv,) = torch.autograd.grad(0.001 * adversarial_loss, super_res)
+            (g_adv,) = torch.autograd.grad(adversarial_loss, super_res, grad_outputs=self._one)
             cur.wait_event(done_content)
             g_content.record_stream(cur)
             content_loss.record_stream(cur)
-            super_res.backward(g_content + g_adv)
-            gen_loss = content_loss + 0.001 * adversarial_loss.detach()
+            super_res.backward(losses.add(g_content, g_adv))
+            gen_loss = losses.add(content_loss, adversarial_loss)
         else:
             content_loss = self.vgg_loss(super_res, high_res.detach())
-            gen_loss = content_loss + 0.001 * adversarial_loss
-            gen_loss.backward()
+            gen_loss = losses.total(content_loss, adversarial_loss)
+            gen_loss.backward(self._one)
         self.gen_optimizer.step()
         return gen_loss.detach()
 
@@ -270,21 +254,32 @@ class SRGANTrainer:
             return torch.load(path, map_location=self.device)
         return None
 
-    def _restore(self, *paths) -> bool:
+    def _restore(self, *paths) -> Optional[dict]:
+        """Loads the generator weights from the first checkpoint that exists and returns it (None if none does).
+        Accepts the trainer's {"epoch", "phase", "state"} payload and bare (optionally `module.`-prefixed) state dicts."""
         for p in paths:
             ck = self._load_checkpoint(p)
             if ck is not None:
                 state = ck["state"] if "state" in ck else ck
                 state = {k[len('module.'):] if k.startswith('module.') else k: v for k, v in state.items()}
                 self.generator.load_state_dict(state)
-                return True
-        return False
+                return ck if "state" in ck else {"state": state}
+        return None
+
+    def _check_device(self) -> None:
+        """Epoch boundary (already synchronised): raise if a kernel's pipeline watchdog fired during the epoch instead
+        of training on with a garbage tile (csrc/ptx.cuh mbar_wait)."""
+        if self.device.type == 'cuda':
+            from .. import ops
+            ops.check_watchdog()
 
     def _pretrain(self) -> None:
         self.best_psnr = -1.0
-        self._restore(self.psnr_checkpoint, f'{self.PREFIX}-psnr-latest.pth')
+        # reference :357-364: explicit --psnr-checkpoint, else <model>-psnr-latest.pth; training resumes at its epoch
+        ck = self._restore(self.psnr_checkpoint) if self.psnr_checkpoint else self._restore(f'{self.PREFIX}-psnr-latest.pth')
+        first = int(ck.get("epoch", 1)) if ck else 1
         step = 0
-        for epoch in range(1, self.pre_epochs + 1):
+        for epoch in range(first, self.pre_epochs + 1):
             self._log(f'Starting epoch {epoch} out of {self.pre_epochs}')
             t0 = time.time()
             seen = 0
@@ -294,15 +289,20 @@ class SRGANTrainer:
                 step += 1
             if self.device.type == 'cuda':
                 torch.cuda.synchronize()
+            self._check_device()
             self._log(f'Throughput: {round(seen * max(self.world_size, 1) / (time.time() - t0), 3)} images/sec')
             self._test(epoch, f'{self.PREFIX}-psnr', step)
 
     def _gan_train(self) -> None:
         self.best_psnr = -1.0
-        if not self._restore(self.gan_checkpoint, f'{self.PREFIX}-gan-latest.pth'):
+        # reference :483-499: a GAN checkpoint (explicit or <model>-gan-latest.pth) restores weights AND the epoch to
+        # resume at; without one the PSNR-phase weights seed the generator and the GAN phase starts at epoch 1
+        ck = self._restore(self.gan_checkpoint) if self.gan_checkpoint else self._restore(f'{self.PREFIX}-gan-latest.pth')
+        first = int(ck.get("epoch", 1)) if ck else 1
+        if ck is None:
             self._restore(f'{self.PREFIX}-psnr-latest.pth')
         step = 0
-        for epoch in range(1, self.epochs + 1):
+        for epoch in range(first, self.epochs + 1):
             self._log(f'Starting epoch {epoch} out of {self.epochs}')
             t0 = time.time()
             seen = 0
@@ -314,6 +314,7 @@ class SRGANTrainer:
             self.gen_scheduler.step()
             if self.device.type == 'cuda':
                 torch.cuda.synchronize()
+            self._check_device()
             self._log(f'Throughput: {round(seen * max(self.world_size, 1) / (time.time() - t0), 3)} images/sec')
             self._test(epoch, f'{self.PREFIX}-gan', step)
 
