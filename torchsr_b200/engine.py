@@ -954,7 +954,7 @@ class _PlanFn(torch.autograd.Function):
             # as soon as every call has produced it, so its transfer overlaps the convolutional backward.
             from .dist import allreduce_async_flat
             dist_on = ddp is not None and ddp.world > 1
-            cur = torch.cuda.current_stream(gout.device)
+            cur = torch.cuda.current_stream(plan.device)
             others = st["pending"] - {id(plan)}
             parked = st.setdefault("parked", [])
             info = {}
