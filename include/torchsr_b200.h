@@ -99,7 +99,9 @@ typedef struct tsr_conv_desc {
      one int per output tile, both all-zero between launches (the kernel leaves them zeroed) */
   float* ws;
   int32_t* tile_counters;
-  int32_t ws_ld, _pad1;
+  int32_t ws_ld;
+  int32_t side;             /* inside a program: 1 = this GEMM only feeds gradient outputs, run it on the weight-gradient
+                               side branch (as tsr_elt_desc_t.side) */
   int64_t* trace;           /* optional debug: per-CTA clock64 stamps [grid][40] (null in production) */
   /* BatchNorm statistics groups (one discriminator pass over the real | fake batches, srgan/trainer.py:446-447): rows
      [0, group_rows) are group 0, the rest group 1; 0 = one group. Multiple of 32. stats_partial / bnr_coef / bnf_coef
@@ -118,7 +120,10 @@ typedef struct tsr_conv_desc {
   int64_t* bnf_nbt;         /* num_batches_tracked, += number of groups */
   float* bnf_coef;          /* out, training mode: [groups][4][bnf_c] scale, shift, mean, invstd */
   int64_t bnf_count;        /* rows per statistics group */
-  int32_t bnf_c, _pad2;
+  int32_t bnf_c;
+  int32_t w_chunk_rows;     /* a_mode 1/2 only, > 0: w is stored as K chunks of 64 columns, chunk j = rows
+                               [j*w_chunk_rows, (j+1)*w_chunk_rows) of a [chunks*w_chunk_rows][64] matrix (w_ld = 64): the
+                               layout an all-gather of per-rank [rows][64] factor blocks produces */
   float bnf_eps, bnf_momentum;
 } tsr_conv_desc_t;
 
@@ -180,7 +185,8 @@ enum tsr_elt_kind {
   TSR_E_ADAM = 27,
   TSR_E_CHANSUM_NCHW = 28,
   TSR_E_GAN_LOSS = 29,   /* BCE / BCE-with-logits / relativistic-average GAN criteria, value + gradient, one launch */
-  TSR_E_AXPBY_F32 = 30   /* out = a * (*scalar) * x + b * y on fp32 vectors */
+  TSR_E_AXPBY_F32 = 30,  /* out = a * (*scalar) * x + b * y on fp32 vectors */
+  TSR_E_FEAT_T = 31      /* NHWC bf16 features -> chunked transposed [(c,h,w)][batch] bf16 factor of the Linear wgrad GEMM */
 };
 
 /* weight pack / grad unpack index maps (TSR_E_PACK_W / TSR_E_UNPACK_G table entries) */

@@ -16,7 +16,7 @@ ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_RELU = 0, 1, 2, 3
 (E_IM2ROW, E_GATHER_OUT, E_NCHW2NHWC, E_NHWC2NCHW, E_BN_FINALIZE, E_BN_EVAL_COEF, E_BN_ACT, E_BN_BWD_REDUCE,
  E_BN_BWD_FINALIZE, E_BN_BWD_APPLY, E_ACT_BWD, E_COLSUM_FINALIZE, E_SUM_FINALIZE, E_PACK_W, E_UNPACK_G,
  E_LINEAR_WGRAD, E_LOSS, E_ZERO, E_UPSAMPLE2X, E_UPSAMPLE2X_BWD, E_HEAD, E_HEAD_BWD, E_AXPBY, E_MAXPOOL2,
- E_MAXPOOL2_BWD, E_CAST, E_ADAM, E_CHANSUM_NCHW, E_GAN_LOSS, E_AXPBY_F32) = range(1, 31)
+ E_MAXPOOL2_BWD, E_CAST, E_ADAM, E_CHANSUM_NCHW, E_GAN_LOSS, E_AXPBY_F32, E_FEAT_T) = range(1, 32)
 
 PK_FWD, PK_T, PK_ROWK, PK_ROWN, PK_ROWN_T, PK_FULLK, PK_LINEAR = range(7)
 
@@ -44,12 +44,12 @@ class ConvDesc(C.Structure):
         ("w_static", C.c_int32),
         ("bnr_x", C.c_void_p), ("bnr_coef", C.c_void_p), ("bnr_prelu", C.c_void_p), ("bnr_act", C.c_int32),
         ("bnr_c", C.c_int32),
-        ("ws", C.c_void_p), ("tile_counters", C.c_void_p), ("ws_ld", C.c_int32), ("_pad1", C.c_int32),
+        ("ws", C.c_void_p), ("tile_counters", C.c_void_p), ("ws_ld", C.c_int32), ("side", C.c_int32),
         ("trace", C.c_void_p),
         ("group_rows", C.c_int32), ("bnf_mode", C.c_int32),
         ("bnf_counter", C.c_void_p), ("bnf_gamma", C.c_void_p), ("bnf_beta", C.c_void_p), ("bnf_rm", C.c_void_p),
         ("bnf_rv", C.c_void_p), ("bnf_nbt", C.c_void_p), ("bnf_coef", C.c_void_p),
-        ("bnf_count", C.c_int64), ("bnf_c", C.c_int32), ("_pad2", C.c_int32),
+        ("bnf_count", C.c_int64), ("bnf_c", C.c_int32), ("w_chunk_rows", C.c_int32),
         ("bnf_eps", C.c_float), ("bnf_momentum", C.c_float),
     ]
 

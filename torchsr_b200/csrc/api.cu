@@ -201,7 +201,10 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   } else {
     return fail(-20, "bad a_mode");
   }
+  if (d.w_chunk_rows > 0 && (d.a_mode == 0 || d.block_k != 64 || d.w_ld != 64 || d.w_chunk_rows < d.cout_pad))
+    return fail(-20, "w_chunk_rows needs a_mode 1/2, block_k 64, w_ld 64 and w_chunk_rows >= cout_pad");
   if (int e = encode_2d(&p.tmB, d.w, d.w_rows, d.w_ld, d.w_ld, d.block_k, d.block_n)) return e;
+  p.b_chunk_rows = d.w_chunk_rows;
   p.stride = d.stride;
   p.lower_h = d.lower_h;
   p.lower_w = d.lower_w;
@@ -510,6 +513,7 @@ struct tsr_prog {
   enum Kind { CONV, WGRAD, ELT, CONV_GROUP };
   struct Op {
     Kind kind;
+    int side = 0;         // CONV: run on the weight-gradient side branch
     ConvLaunch conv;
     WgradLaunch wg;
     tsr_elt_desc_t elt;
@@ -544,6 +548,10 @@ constexpr int kSideStreams = 2;
 struct SideBranch {
   cudaStream_t s[kSideStreams] = {nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[kSideStreams] = {nullptr, nullptr};
+  // lowest-priority branch for bulk side work (elt.side == 2: the Linear weight gradient, thousands of small blocks):
+  // its pending blocks only take the SM slots the main chain's kernels leave free
+  cudaStream_t low = nullptr;
+  cudaEvent_t join_low = nullptr;
 };
 std::map<cudaStream_t, SideBranch> g_side;
 std::mutex g_side_mu;   // not g_mu: tsr_prog_run holds g_mu while it captures a range
@@ -572,6 +580,9 @@ SideBranch* side_for(cudaStream_t st) {
       return nullptr;
   }
   if (cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaStreamCreateWithPriority(&b.low, cudaStreamNonBlocking, lo) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b.join_low, cudaEventDisableTiming) != cudaSuccess)
+    return nullptr;
   return &(g_side[st] = b);
 }
 
@@ -600,9 +611,17 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
     if (!sb) return fail(-45, "side stream setup failed");
   }
   bool used[kSideStreams] = {false, false};
+  bool used_low = false, prev_low = false;
   int next_side = 0;
   bool chain = false;   // previous op on `st` was one of our kernels
   auto join = [&]() -> cudaError_t {
+    if (used_low) {
+      used_low = false;
+      chain = false;
+      cudaError_t e = cudaEventRecord(sb->join_low, sb->low);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, sb->join_low, 0);
+      if (e != cudaSuccess) return e;
+    }
     for (int k = 0; k < kSideStreams; ++k) {
       if (!used[k]) continue;
       used[k] = false;
@@ -617,7 +636,21 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
   for (int i = first; i < last; ++i) {
     const tsr_prog::Op& op = p->ops[i];
     cudaError_t ce;
-    const bool side_elt = side && op.kind == tsr_prog::ELT && op.elt.side != 0;
+    const bool side_conv = side && op.kind == tsr_prog::CONV && op.side != 0;
+    const bool side_elt = (side && op.kind == tsr_prog::ELT && op.elt.side != 0) || side_conv;
+    if (side_elt && !side_conv && op.elt.side == 2) {
+      ce = cudaSuccess;
+      if (!prev_low) {
+        ce = cudaEventRecord(sb->fork, st);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sb->low, sb->fork, 0);
+      }
+      if (ce == cudaSuccess) ce = tsr::launch_elt(op.elt, sb->low, false);
+      used_low = prev_low = true;
+      prev_side_elt = false;
+      if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
+      continue;
+    }
+    prev_low = false;
     if ((op.kind == tsr_prog::WGRAD && side) || side_elt) {
       int k = next_side;
       if (side_elt && prev_side_elt) {
@@ -629,8 +662,9 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
         if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sb->s[k], sb->fork, 0);
       }
       if (ce == cudaSuccess)
-        ce = side_elt ? tsr::launch_elt(op.elt, sb->s[k], false)
-                      : tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, sb->s[k], false);
+        ce = side_conv ? tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, sb->s[k], false)
+             : side_elt ? tsr::launch_elt(op.elt, sb->s[k], false)
+                        : tsr::launch_conv_wgrad(op.wg.p, op.wg.gsets, op.wg.tiles_n, op.wg.splits, sb->s[k], false);
       used[k] = true;
       prev_side_elt = side_elt;
       if (ce != cudaSuccess) return fail(-42, "program op %d failed to launch: %s", i, cudaGetErrorString(ce));
@@ -720,6 +754,7 @@ int tsr_prog_size(const tsr_prog_t* p) { return static_cast<int>(p->ops.size());
 int tsr_prog_add_conv(tsr_prog_t* p, const tsr_conv_desc_t* d) {
   tsr_prog::Op op;
   op.kind = tsr_prog::CONV;
+  op.side = d->side;
   if (int e = build_conv(*d, &op.conv)) return e;
   p->ops.push_back(op);
   return static_cast<int>(p->ops.size()) - 1;

@@ -106,14 +106,13 @@ __device__ __forceinline__ void store_f32x16(void* base, long long off, const fl
 // grid.sync() does. The host only selects this path for grids whose CTAs are all co-resident; the spin is bounded by
 // the watchdog all the same (a timeout leaves a wrong tile and an error code, not a hung GPU).
 __device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* counter, unsigned int expected, int* err) {
-  __threadfence();
-  atomicAdd(counter, 1u);
+  // release: orders this CTA's earlier reductions (made visible to this thread by the CTA barrier) before the arrival
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
   unsigned int seen;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
   if (seen < expected) {
     const long long t0 = clock64();
     do {
-      __nanosleep(20);
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
       if (clock64() - t0 > TSR_WATCHDOG_CYCLES) {
         if (err) atomicExch(err, 6);
@@ -121,7 +120,6 @@ __device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* counter, unsi
       }
     } while (seen < expected);
   }
-  __threadfence();
   return true;
 }
 
@@ -181,9 +179,9 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
           ktap = it / kc_per_tap;
           kkc = it - ktap * kc_per_tap;
         }
-        const int brow = (A_MODE == 0 ? p.tap_wrow[ktap] * p.b_rows_per_tap : 0) + b_row0;
+        const int brow = (A_MODE == 0 ? p.tap_wrow[ktap] * p.b_rows_per_tap : kkc * p.b_chunk_rows) + b_row0;
         mbar_arrive_expect_tx(bar_full + 8 * j, tx);
-        tma_load_2d(d, &p.tmB, bar_full + 8 * j, kkc * block_k, brow);
+        tma_load_2d(d, &p.tmB, bar_full + 8 * j, (A_MODE != 0 && p.b_chunk_rows) ? 0 : kkc * block_k, brow);
         d += stage_bytes;
       }
     }
@@ -316,7 +314,8 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
         if (elect_one()) {
           if (arm) mbar_arrive_expect_tx(full, tx);
           tma_load_2d(dst, &p.tmA, full, kc * block_k, m0);
-          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, p.b_chunk_rows ? 0 : kc * block_k,
+                                  kc * p.b_chunk_rows + b_row0);
         }
         ++kc;
       } else {
@@ -325,7 +324,8 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
           if (arm) mbar_arrive_expect_tx(full, tx);
           tma_load_2d(dst, &p.tmA, full, m0, kc * block_k);
           tma_load_2d(dst + block_k * 128, &p.tmA, full, m0 + 64, kc * block_k);
-          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, kc * block_k, b_row0);
+          if (load_b) tma_load_2d(dst + a_bytes, &p.tmB, full, p.b_chunk_rows ? 0 : kc * block_k,
+                                  kc * p.b_chunk_rows + b_row0);
         }
         ++kc;
       }
@@ -931,8 +931,8 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
 #pragma unroll
             for (int i = 0; i < 16; ++i) atomicAdd(o + static_cast<long long>(col0 + i) * e.os_n + m, v[i]);
           } else {
+            if (bnf != 0) continue;     // raw and normalised values are stored after the grid barrier (below)
             if (out_preact != nullptr) store_bf16x16(out_preact, off, v);
-            if (bnf != 0) continue;     // the normalised value is stored after the grid barrier (below)
             if (act == ACT_PRELU || act == ACT_LEAKY) {
               const float sl = act == ACT_PRELU ? alpha : leaky;
 #pragma unroll
@@ -1012,7 +1012,10 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          if (valid && col0 < n_valid) bn_apply_store(v, ch, col0);
+          if (valid && col0 < n_valid) {
+            if (out_preact != nullptr) store_bf16x16(out_preact, out_base + col0, v);   // raw conv output for backward
+            bn_apply_store(v, ch, col0);
+          }
         }
       }
       tc_fence_before();

@@ -104,6 +104,8 @@ struct ConvParams {
   int a_mode;      // 0: im2col NHWC; 1: 2D tiled, K-major rows; 2: 2D tiled, MN-major (A given as [K][M])
   int a_c0;        // first input channel
   int b_rows_per_tap;
+  int b_chunk_rows;     // a_mode 1/2, > 0: K chunk j of the B operand starts at row j*b_chunk_rows, column 0 (chunked
+                        // [chunks*rows][64] layout, see tsr_conv_desc_t.w_chunk_rows)
   int iters_per_split;  // K iterations handled per blockIdx.z
   int stages;
   int tmem_cols;

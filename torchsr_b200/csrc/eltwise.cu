@@ -1126,17 +1126,18 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ pre
 }
 // HEAD_BWD: p0 = gout fp32 [B] (grad wrt head output), p1 = out fp32 [B] (saved output), p2 = h1 fp32 [B][N1],
 // p3 = w2 [N1], p4 = dpre1 fp32 [B][N1] out, p5 = dpre1 bf16 [Bpad][N1] out (rows >= B zero-filled by caller),
-// p6 = dw2 [N1] out, p7 = db2 [1] out
+// p6 = dw2 [N1] out, p7 = db2 [1] out, p8 = db1 [N1] out or null (bias gradient of the first Linear: column sums of dpre1)
 // i: 0 B, 1 N1, 2 sigmoid, 3 row stride of dpre1_bf in elements (0 = N1); f: 0 leaky.
 // One block per 256 features; loops over batch.
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ out,
                                                        const float* __restrict__ h1, const float* __restrict__ w2,
                                                        float* __restrict__ dpre1, bf16* __restrict__ dpre1_bf,
-                                                       float* __restrict__ dw2, float* __restrict__ db2, int B, int N1,
-                                                       int sigmoid, int ld_bf, float leaky) {
+                                                       float* __restrict__ dw2, float* __restrict__ db2,
+                                                       float* __restrict__ db1, int B, int N1, int sigmoid, int ld_bf,
+                                                       float leaky) {
   pdl_sync();
   const int k = blockIdx.x * 256 + threadIdx.x;
-  float dw = 0.f, dbs = 0.f;
+  float dw = 0.f, dbs = 0.f, d1 = 0.f;
   for (int b = 0; b < B; ++b) {
     float dl = gout[b];
     if (sigmoid) {
@@ -1151,10 +1152,33 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       if (h <= 0.f) d *= leaky;
       dpre1[static_cast<long long>(b) * N1 + k] = d;
       if (dpre1_bf) dpre1_bf[static_cast<long long>(b) * ld_bf + k] = __float2bfloat16(d);
+      d1 += d;
     }
   }
   if (k < N1) dw2[k] = dw;
+  if (k < N1 && db1) db1[k] = d1;
   if (k == 0) db2[0] = dbs;
+}
+
+// FEAT_T: the flattened feature map in the Linear weight's column order, transposed and cut into 64-row batch chunks -
+// the K-major B operand of the Linear weight-gradient GEMM  dW[n][k] = sum_b dpre[b][n] * X[b][k]  (tcgen05, conv_igemm.cu):
+//   XT[chunk][k][j] = X[chunk*64 + j][k],  k = c*HW + hw (torch.flatten of NCHW, discriminator.py:86), zero for b >= B.
+// A chunk is one K block of the GEMM; an all-gather of every rank's chunks simply appends K blocks (dist.py).
+// p0 = act bf16 NHWC [B][HW][ld] (+off), p1 = XT bf16 [chunks][C*HW][64]; i: 0 B, 1 C, 2 HW, 3 ld, 4 off
+__global__ void __launch_bounds__(256) feat_t_kernel(const bf16* __restrict__ act, bf16* __restrict__ xt, int B, int C,
+                                                     int HW, int ld, int off) {
+  pdl_sync();
+  const int chunks = (B + 63) / 64;
+  const long long total = static_cast<long long>(chunks) * C * HW * 64;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
+    const int j = static_cast<int>(idx & 63);
+    const long long r = idx >> 6;
+    const int k = static_cast<int>(r % (static_cast<long long>(C) * HW));
+    const int chunk = static_cast<int>(r / (static_cast<long long>(C) * HW));
+    const int b = chunk * 64 + j;
+    const int c = k / HW, hw = k - c * HW;
+    xt[idx] = b < B ? act[(static_cast<long long>(b) * HW + hw) * ld + off + c] : __float2bfloat16(0.f);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- misc
@@ -1417,7 +1441,8 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
     case TSR_E_HEAD_BWD:
       ce = launch_k(head_bwd_kernel, dim3((i[1] + 255) / 256), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (const float*)p[2],
                                                          (const float*)p[3], (float*)p[4], (bf16*)p[5], (float*)p[6],
-                                                         (float*)p[7], i[0], i[1], i[2], i[3] > 0 ? i[3] : i[1], d.f[0]);
+                                                         (float*)p[7], (float*)p[8], i[0], i[1], i[2],
+                                                         i[3] > 0 ? i[3] : i[1], d.f[0]);
       break;
     case TSR_E_AXPBY:
       ce = launch_k(axpby_kernel, dim3(grid_for(i[0] / 8)), dim3(256), 0, st, pdl, (const bf16*)p[0], (const bf16*)p[1], (bf16*)p[2], i[0], d.f[0],
@@ -1434,6 +1459,10 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       break;
     case TSR_E_CAST:
       ce = launch_k(cast_kernel, dim3(grid_for(i[0])), dim3(256), 0, st, pdl, p[0], p[1], i[0], i[1]);
+      break;
+    case TSR_E_FEAT_T:
+      ce = launch_k(feat_t_kernel, dim3(grid_for(((i[0] + 63) / 64) * i[1] * i[2] * 64)), dim3(256), 0, st, pdl,
+                    (const bf16*)p[0], (bf16*)p[1], i[0], i[1], i[2], i[3], i[4]);
       break;
     case TSR_E_GAN_LOSS:
       ce = launch_k(gan_loss_kernel, dim3(1), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (float*)p[2],

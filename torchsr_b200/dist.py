@@ -3,9 +3,10 @@
 Replaces the DistributedDataParallel wrappers of the reference (torchsr/srgan/trainer.py:143-157, torchsr.py:257-258):
   * attach(): parameters (and buffers) are broadcast from rank 0 once - mandatory, ranks are seeded differently
     (torchsr.py:152-153);
-  * every backward of an attached module all-reduces its flat fp32 gradient in buckets, each launched asynchronously
-    as soon as the backward launch list has produced it, so the transfer of the discriminator's 75 MB classifier
-    gradient (produced first) overlaps the whole convolutional backward;
+  * every backward of an attached module averages its flat fp32 gradient over the ranks with bucketed NCCL all-reduces,
+    except the discriminator's 75 MB classifier weight gradient: that one is an outer product over the batch, so the
+    ranks all-gather its two small bf16 factors at the head of backward (the transfer overlaps the convolutional
+    backward) and each forms the averaged product itself with one tensor-core GEMM (engine.Plan.run_backward);
   * BatchNorm statistics stay local to each rank (the reference uses no SyncBatchNorm); with broadcast_buffers=True
     rank 0's running statistics are re-broadcast before each training forward, as DDP does for the generator.
 """
@@ -32,6 +33,13 @@ class DataParallelState:
             self.pending.append((dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
         else:   # gloo has no AVG
             self.pending.append((dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True), t))
+
+    def allgather_async(self, out: torch.Tensor, t: torch.Tensor):
+        """out[r * t.numel():(r + 1) * t.numel()] = rank r's t, asynchronously w.r.t. the current stream."""
+        if self.world == 1:
+            out.copy_(t)
+            return
+        self.pending.append((dist.all_gather_into_tensor(out, t, group=self.group, async_op=True), None))
 
     def wait(self):
         for work, t in self.pending:

@@ -179,6 +179,9 @@ class ParamStore:
         self._version = None
         self.dirty = True
         self.opt_fresh = False
+        # set by optim.FusedAdam(late_numel=...): the event after which the weights behind the forward program's
+        # "late_weights" mark (the big Linear layer) are valid
+        self.late_event = None
         self._build_tables()
         _LIVE_STORES.add(self)
         _install_optimizer_hook()
@@ -675,9 +678,20 @@ class Plan:
         prog.add(d)
 
     # ---- execution (set by the net definition: input_fn, output_fn, ingest_fn, grad_input_fn, post_backward)
+    def _run_fwd_program(self):
+        ev, mark = self.store.late_event, self.fwd.marks.get("late_weights")
+        if ev is not None and mark is not None:
+            self.fwd.run(0, mark)
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self.fwd.run(mark, -1)
+        else:
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+            self.fwd.run()
+
     def run_forward(self, x: torch.Tensor) -> torch.Tensor:
         self.input_fn(x)
-        self.fwd.run()
+        self._run_fwd_program()
         return self.output_fn()
 
     def run_forward_pair(self, a: torch.Tensor, b: torch.Tensor):
@@ -685,56 +699,59 @@ class Plan:
             self.input_pair_fn(a, b)
         else:
             self.input_fn(torch.cat([a, b]))
-        self.fwd.run()
+        self._run_fwd_program()
         out = self.output_fn()
         h = out.shape[0] // 2
         return out[:h].clone(), out[h:].clone()
 
-    def run_backward(self, gout: torch.Tensor, want_x: bool, want_w: bool, ddp=None, alias: bool = False,
-                     defer_comm: bool = False, early_cb=None):
-        """defer_comm: no all-reduce here and the plan's own flat buffer is returned - the caller sums the gradients of
-        several outstanding calls of the module first (see _PlanFn.backward, 'merge_pending_grads'). early_cb(offset)
-        is called once the tail [offset, total) of the flat gradient is final (the classifier of a discriminator,
-        produced by the first launches of backward), so that the caller can start its exchange early."""
+    def run_backward(self, gout, want_x: bool, want_w: bool, ddp=None, alias: bool = False, defer_comm: bool = False):
+        """Runs the backward launch list and, for a data-parallel module, the gradient exchange.
+
+        defer_comm (single GPU only): the plan's own flat buffer is returned and the caller sums the gradients of
+        several outstanding calls of the module first (see _PlanFn._run_backward, 'merge_pending_grads').
+
+        Data parallel (reference */trainer.py:143-157: DDP all-reduces every gradient): the flat fp32 gradient is averaged
+        in place with bucketed NCCL all-reduces - except the weight of a discriminator's first Linear layer (75 MB for
+        SRGAN, 80 % of the module): it is an outer product over the batch, so the ranks all-gather its two bf16 factors
+        (dpre1 [b][n], features^T in 64-row chunks; ~2.5 MB per rank) as soon as the head of backward has produced them,
+        the transfer overlaps the convolutional backward, and every rank forms  mean_r(A_r^T X_r)  itself with one GEMM
+        over the gathered K chunks."""
         if not self.training and self.has_bn:
             raise NotImplementedError("torchsr_b200: backward through eval-mode BatchNorm is not implemented; call "
                                       ".train() for gradient computation (the reference trainers do)")
         seed = self.ingest_pair_fn(*gout) if isinstance(gout, tuple) else self.ingest_fn(gout)
-        prog = self.backward_program(want_x, want_w, seed)
+        dist_on = want_w and ddp is not None and ddp.world > 1
+        prog = self.backward_program(want_x, want_w, seed, dist=dist_on)
         flat = None
-        store = self.store
         gb = self.grads
-        early = prog.marks.get("early_grads")
-        if want_w and ddp is not None and ddp.world > 1 and not defer_comm:
-            # bucketed all-reduce launched from inside backward: the tail of the flat gradient (the classifier of a
-            # discriminator) is complete after the first few launches and travels while the conv stack runs
-            from .dist import bucket_slices
-            flat = torch.empty_like(gb.flat)
-            early_from = self.early_from if early is not None else None
-            buckets = bucket_slices(store.total, early_from)
-            done = 0
-            if early is not None:
-                prog.run(0, early)
-                done = early
-                for lo, hi in buckets:
-                    if lo >= early_from:
-                        flat[lo:hi].copy_(gb.flat[lo:hi])
-                        ddp.allreduce_async(flat[lo:hi])
-            prog.run(done, -1)
-            for fn in self.post_backward:
-                fn()
-            for lo, hi in buckets:
-                if early is None or lo < early_from:
-                    flat[lo:hi].copy_(gb.flat[lo:hi])
-                    ddp.allreduce_async(flat[lo:hi])
-            ddp.wait()
-        else:
-            if want_w and early is not None and early_cb is not None:
-                prog.run(0, early)
-                early_cb(self.early_from)
-                prog.run(early, -1)
+        if dist_on:
+            assert not defer_comm
+            mark = prog.marks.get("factors")
+            if mark is not None:
+                prog.run(0, mark)
+                fa = self._factor_buffers(ddp.world)
+                ddp.allgather_async(fa["a_all"], self.factors["a"])
+                ddp.allgather_async(fa["xt_all"], self.factors["xt"])
+                prog.run(mark, -1)
             else:
                 prog.run()
+            for fn in self.post_backward:
+                fn()
+            lin_lo = lin_hi = None
+            if mark is not None:
+                w = self.factors["lin"].weight
+                lin_lo = self.store.offsets[id(w)]
+                lin_hi = lin_lo + _round_up(w.numel(), 4)
+            from .dist import bucket_slices
+            for lo, hi in ((0, self.store.total),) if mark is None else ((0, lin_lo), (lin_hi, self.store.total)):
+                for b0, b1 in bucket_slices(hi - lo, None):
+                    ddp.allreduce_async(gb.flat[lo + b0:lo + b1])
+            ddp.wait()          # the current stream waits for the gathers and the all-reduces
+            if mark is not None:
+                ops.run_now(fa["gemm"])
+            flat = gb.flat if alias else gb.flat.clone()
+        else:
+            prog.run()
             if want_w:
                 for fn in self.post_backward:
                     fn()
@@ -744,10 +761,25 @@ class Plan:
         gx = self.grad_input_fn() if want_x else None
         return gx, flat
 
+    def _factor_buffers(self, world: int) -> dict:
+        """Gathered-factor buffers and the GEMM over them (built once per plan and world size)."""
+        fa = getattr(self, "_factor_cache", None)
+        if fa is None or fa["world"] != world:
+            from .nets import linear_wgrad_gemm
+            f = self.factors
+            a_all = self.buf(f"factors.a_all.{world}", world * f["a"].numel(), BF16)
+            xt_all = self.buf(f"factors.xt_all.{world}", world * f["xt"].numel(), BF16)
+            fa = dict(world=world, a_all=a_all, xt_all=xt_all,
+                      gemm=linear_wgrad_gemm(self, a_all, xt_all, world * f["rows"], 1.0 / world))
+            fa["gemm"].side = 0
+            self._factor_cache = fa
+        return fa
+
     # ---- programs
-    def backward_program(self, want_x: bool, want_w: bool, seed: Act) -> "ops.Program":
-        key = (want_x, want_w)
+    def backward_program(self, want_x: bool, want_w: bool, seed: Act, dist: bool = False) -> "ops.Program":
+        key = (want_x, want_w, dist)
         if key not in self.bwd:
+            self._building_dist = dist      # read by the net definition's tape entries (nets.bwd_head)
             prog = ops.Program()
             prog.add(ops.elt(L.E_ZERO, p=[self._zarena["bwd"]], i=[ZERO_ARENA_FLOATS * 4]))
             if want_w:
@@ -939,61 +971,34 @@ class _PlanFn(torch.autograd.Function):
         want_w = any(want)
         st = ctx.module._tsr
         ddp = st.get("ddp")
-        merge = want_w and st.get("merge_pending_grads", False)
+        dist_on = want_w and ddp is not None and ddp.world > 1
         # Aliased gradients (views of the plan's flat buffer) are only handed out when autograd will ASSIGN them: with a
-        # .grad already present (gradient accumulation, zero_grad(set_to_none=False)) AccumulateGrad would add the
-        # buffer to a tensor that may alias it, so those cases get a private copy.
+        # .grad already present (gradient accumulation, zero_grad(set_to_none=False), a second call of the module
+        # feeding the same loss) AccumulateGrad would add the buffer to a tensor that may alias it: private copy then.
         safe_alias = all(p.grad is None for p in plan.store.params)
+        merge = want_w and st.get("merge_pending_grads", False) and not dist_on
         if not merge:
-            gx, flat = plan.run_backward(gout, want_x, want_w, ddp, st.get("alias_grads", False) and safe_alias)
+            # data parallel: every backward exchanges its own gradient (averaging is linear, autograd sums the calls)
+            others = st.get("pending", set()) - {id(plan)} if want_w else set()
+            gx, flat = plan.run_backward(gout, want_x, want_w, ddp,
+                                         st.get("alias_grads", False) and safe_alias and not others)
         else:
-            # Several calls of the module feed one loss (D(real) and D(fake), trainer.py): every backward but the last
-            # parks its flat gradient; the last one adds the parked ones to its own (one kernel per parked call and
-            # slice), all-reduces the sum once and returns it - the others return no parameter gradients, which
-            # autograd treats as zero. The tail of the flat gradient that is final early (early_cb) is summed and sent
-            # as soon as every call has produced it, so its transfer overlaps the convolutional backward.
-            from .dist import allreduce_async_flat
-            dist_on = ddp is not None and ddp.world > 1
+            # Several calls of the module feed one loss (D(real) and D(fake) as two calls): every backward but the last
+            # parks its flat gradient; the last one adds the parked ones to its own (one kernel per parked call) and
+            # returns the sum - the others return no parameter gradients, which autograd treats as zero.
             cur = torch.cuda.current_stream(plan.device)
             others = st["pending"] - {id(plan)}
             parked = st.setdefault("parked", [])
-            info = {}
-
-            def early_cb(offset):
-                info["offset"] = offset
-                if others:
-                    info["ev_early"] = torch.cuda.Event()
-                    info["ev_early"].record(cur)
-                elif all(p.get("offset") == offset for p in parked):
-                    mine = plan.grads.flat
-                    for p in parked:
-                        cur.wait_event(p["ev_early"])
-                        _add_flat(mine[offset:], p["flat"][offset:])
-                    if dist_on:
-                        allreduce_async_flat(mine[offset:], ddp)
-                    info["early_done"] = offset
-
-            # single GPU: nothing to send early - the whole backward runs as one range (the classifier's weight
-            # gradient then overlaps the convolutional backward on the side branch)
-            gx, flat = plan.run_backward(gout, want_x, want_w, ddp, True, defer_comm=True,
-                                         early_cb=early_cb if dist_on else None)
+            gx, flat = plan.run_backward(gout, want_x, want_w, None, True, defer_comm=True)
             if others:
-                info["flat"] = flat
-                info["ev_done"] = torch.cuda.Event()
-                info["ev_done"].record(cur)
-                parked.append(info)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                parked.append(dict(flat=flat, ev_done=ev))
                 flat = None
             else:
-                head = info.get("early_done")      # [head, total) was already summed (and sent)
                 for p in st.pop("parked", []):
                     cur.wait_event(p["ev_done"])
-                    if head is None:
-                        _add_flat(flat, p["flat"])
-                    else:
-                        _add_flat(flat[:head], p["flat"][:head])
-                if dist_on:
-                    allreduce_async_flat(flat if head is None else flat[:head], ddp)
-                    ddp.wait()
+                    _add_flat(flat, p["flat"])
                 if not safe_alias:
                     flat = flat.clone()
         grads = plan.store.grads_from_flat(flat, want) if (want_w and flat is not None) else [None] * len(want)

@@ -70,5 +70,6 @@ class ESRGANTrainer(SRGANTrainer):
         gen_loss = losses.total(pixel_loss, content_loss, adversarial_loss)     # 0.01 L1 + 1 VGG + 0.005 adv (:466-469)
         gen_loss.backward(self._one)
         self.gen_optimizer.step()
+        self.disc_optimizer.join()
         self.generator.zero_grad()
         return gen_loss.detach()

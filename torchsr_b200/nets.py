@@ -232,6 +232,15 @@ def discriminator_linears(m, image_size: int):
     return [LinearRec("classifier.0", m.classifier[0], 512, fm, fm)]
 
 
+def linear_wgrad_gemm(plan: Plan, a: torch.Tensor, xt: torch.Tensor, k_rows: int, scale: float):
+    """Descriptor of dW = scale * A^T . X over `k_rows` batch rows (a multiple of 64; the gathered factors of all ranks
+    in the data-parallel case), written into the flat gradient slice of the module's first Linear weight."""
+    l1 = plan.store.linears[0]
+    return ops.gemm_desc(a=a, M=l1.nout, K=k_rows, a_ld=l1.nout_pad, a_mn_major=True, w=xt, n_rows=l1.K, block_n=128,
+                         out=plan.grads.grad_slice(l1.weight), out_ld=l1.K, n_valid=l1.K, out_f32=True, acc_scale=scale,
+                         w_chunked=True, side=True)
+
+
 def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
     """3x3 conv + LeakyReLU, then (conv, BN, LeakyReLU) stages with strides from the module, flatten, Linear,
     LeakyReLU, Linear (+ Sigmoid for SRGAN)."""
@@ -288,6 +297,7 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
     tiles_n = l1.nout_pad // 128
     k_iters = K // 64
     splits = max(1, min(k_iters, (2 * 148) // tiles_n))
+    fwd.mark("late_weights")       # first launch that reads the classifier weight (optim.FusedAdam late launch)
     fwd.add(ops.gemm_desc(a=prev.t, M=B, K=K, a_ld=K, w=l1.w_fwd, n_rows=l1.nout_pad, block_n=128, out=pre1t, out_ld=B,
                           n_valid=l1.nout_pad, splits=splits, atomic_t=True, w_static=True))
     out_b = plan.buf("out", B, F32)
@@ -297,27 +307,38 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
     flat_act = prev
 
     def bwd_head(bp, g, want_x, want_w):
+        Bp64 = _round_up(B, 64)
+        chunks = Bp64 // 64
         dpre1 = plan.buf("dpre1", B * N1, F32)
-        dpre1_bf = plan.buf("dpre1_bf", Bpad * l1.nout_pad, BF16, zero=True)
+        dpre1_bf = plan.buf("dpre1_bf", Bp64 * l1.nout_pad, BF16, zero=True)   # rows >= B stay zero (GEMM K padding)
         dw2 = store.grad_slice(lin2.weight) if want_w else plan.buf("dw2.scratch", N1, F32)
         db2 = store.grad_slice(lin2.bias) if want_w else plan.buf("db2.scratch", 4, F32)
-        bp.add(ops.elt(L.E_HEAD_BWD, p=[gbuf, out_b, h1, lin2.weight, dpre1, dpre1_bf, dw2, db2],
+        db1 = store.grad_slice(l1.bias) if want_w else None
+        bp.add(ops.elt(L.E_HEAD_BWD, p=[gbuf, out_b, h1, lin2.weight, dpre1, dpre1_bf, dw2, db2, db1],
                        i=[B, N1, int(sigmoid), l1.nout_pad], f=[0.2]))
-        if want_w:
-            xchw = plan.buf("flat_chw", B * K, F32)     # features in the parameter's (c,h,w) column order
-            # both only feed gradient outputs: they run on the weight-gradient side branch (joined at the range end)
-            bp.add(ops.elt(L.E_NHWC2NCHW, p=[flat_act.t, xchw], i=[B, l1.C, l1.Hf, l1.Wf, flat_act.ld, flat_act.c0, 0],
-                           side=True))
-            bp.add(ops.elt(L.E_LINEAR_WGRAD, p=[dpre1, xchw, store.grad_slice(l1.weight), store.grad_slice(l1.bias)],
-                           i=[B, N1, K], side=True))
-            bp.mark("early_grads")     # everything from classifier.0.weight to the end of the flat gradient is final
-            plan.early_from = plan.store.offsets[id(l1.weight)]
         dflat32 = plan.buf("dflat32", Bpad * K, F32)
         bp.add(ops.elt(L.E_ZERO, p=[dflat32], i=[Bpad * K * 4]))
         bn_ = next(b for b in (128, 64, 32, 16) if Bpad % b == 0)
         # dX^T[(h,w,c)][b] = sum_n Wp[n][(h,w,c)] * dpre1[b][n]: the packed weight is the MN-major A operand as stored
         bp.add(ops.gemm_desc(a=l1.w_fwd, M=K, K=l1.nout_pad, a_ld=K, a_mn_major=True, w=dpre1_bf, n_rows=Bpad,
                              block_n=bn_, out=dflat32, out_ld=K, n_valid=Bpad, atomic_t=True))
+        if want_w:
+            # Weight gradient of the first Linear (75 MB for SRGAN) as a tensor-core GEMM over the batch:
+            #   dW[n][k] = sum_b dpre1[b][n] * X[b][k],  k in the parameter's (c,h,w) column order
+            # A = dpre1 (bf16, [batch][n], MN-major as stored), B = the transposed features cut into 64-row batch
+            # chunks (feat_t_kernel), fp32 result stored straight into the flat gradient. Both launches only feed
+            # gradient outputs: they run on the weight-gradient side branch, emitted AFTER the data-gradient GEMM above
+            # so that its CTAs (critical path) are resident first.
+            # Data parallel (engine.Plan.run_backward): instead of all-reducing the 75 MB product, every rank gathers the
+            # two bf16 factors of all ranks (appending K chunks) and forms the averaged gradient itself.
+            xt = plan.buf("feat_t", chunks * K * 64, BF16)
+            bp.add(ops.elt(L.E_FEAT_T, p=[flat_act.t, xt], i=[B, l1.C, l1.Hf * l1.Wf, flat_act.ld, flat_act.c0],
+                           side=True))
+            plan.factors = dict(a=dpre1_bf, xt=xt, rows=Bp64, chunks=chunks, lin=l1, K=K)
+            if getattr(plan, "_building_dist", False):
+                bp.mark("factors")         # both factors are final here; the GEMM runs over the gathered ones
+            else:
+                bp.add(linear_wgrad_gemm(plan, dpre1_bf, xt, Bp64, 1.0))
         dflat = plan.act("dflat", B, flat_act.H, flat_act.W, flat_act.C)
         bp.add(ops.elt(L.E_CAST, p=[dflat32, dflat.t], i=[B * K, 0]))
         return dflat

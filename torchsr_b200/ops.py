@@ -194,8 +194,11 @@ def dgrad_s2_descs(*, dy, N, Hy, Wy, Cout, dy_ld, wt, Cin, cin_pad, block_n, out
 
 
 def gemm_desc(*, a, M, K, a_ld, a_mn_major=False, w, n_rows, block_n, out, out_ld, n_valid, splits=1, bias=None,
-              act=L.ACT_NONE, atomic_t=False, out_f32=True, acc_scale=1.0, leaky=0.2, w_static=False) -> ConvDesc:
-    """D[M, n] = sum_k A[m,k] * Wt[n,k].  atomic_t: fp32 atomics into out[n*out_ld + m] (split-K)."""
+              act=L.ACT_NONE, atomic_t=False, out_f32=True, acc_scale=1.0, leaky=0.2, w_static=False, w_chunked=False,
+              side=False) -> ConvDesc:
+    """D[M, n] = sum_k A[m,k] * Wt[n,k].  atomic_t: fp32 atomics into out[n*out_ld + m] (split-K).
+    w_chunked: Wt is stored as K/64 chunks [chunk][n_rows][64] (see tsr_conv_desc_t.w_chunk_rows); side: run on the
+    weight-gradient side branch of a program."""
     d = ConvDesc()
     d.x, d.w = ptr(a), ptr(w)
     d.a_mode = 2 if a_mn_major else 1
@@ -206,6 +209,10 @@ def gemm_desc(*, a, M, K, a_ld, a_mn_major=False, w, n_rows, block_n, out, out_l
     d.block_n = block_n
     d.cout_pad = n_rows
     d.w_rows, d.w_ld = n_rows, K
+    if w_chunked:
+        assert K % 64 == 0
+        d.w_rows, d.w_ld, d.w_chunk_rows = (K // 64) * n_rows, 64, n_rows
+    d.side = int(side)
     d.splits = splits
     d.out, d.bias = ptr(out), ptr(bias)
     d.out_mode = L.OUT_GEMM_T_ATOMIC if atomic_t else L.OUT_LINEAR
@@ -237,7 +244,8 @@ def wgrad_desc(*, x, N, H, W, C, x_ld, geom, dy, dy_ld, dy_c, out, cout_valid, b
     return d
 
 
-def elt(kind: int, p: Iterable = (), i: Iterable = (), f: Iterable = (), side: bool = False) -> EltDesc:
+def elt(kind: int, p: Iterable = (), i: Iterable = (), f: Iterable = (), side=False) -> EltDesc:
+    """side: False = main chain; True / 1 = weight-gradient side branch; 2 = lowest-priority bulk side branch."""
     d = EltDesc()
     d.kind = kind
     d.side = int(side)
@@ -405,7 +413,7 @@ def _elt_extents(d: EltDesc):
         B, N1 = i[0], i[1]
         ld = i[3] if i[3] > 0 else N1
         return [(0, B * 4), (1, B * 4), (2, B * N1 * 4), (3, N1 * 4), (4, B * N1 * 4), (5, ((B - 1) * ld + N1) * 2),
-                (6, N1 * 4), (7, 4)]
+                (6, N1 * 4), (7, 4), (8, N1 * 4)]
     if k in (L.E_MAXPOOL2, L.E_MAXPOOL2_BWD):
         big, small = i[0] * i[1] * i[2] * i[3] * 2, i[0] * (i[1] // 2) * (i[2] // 2) * i[3] * 2
         if i[1] % 2 or i[2] % 2 or i[3] % 8:
@@ -417,6 +425,9 @@ def _elt_extents(d: EltDesc):
         return [(0, i[0] * (4 if i[1] == 0 else 2)), (1, i[0] * (2 if i[1] == 0 else 4))]
     if k == L.E_CHANSUM_NCHW:
         return [(0, i[0] * i[1] * i[2] * 4), (1, i[3] * i[1] * 8)]
+    if k == L.E_FEAT_T:
+        chunks = (i[0] + 63) // 64
+        return [(0, ((i[0] * i[2] - 1) * i[3] + i[4] + i[1]) * 2), (1, chunks * i[1] * i[2] * 64 * 2)]
     if k == L.E_GAN_LOSS:
         return [(0, i[0] * 4), (1, i[1] * 4), (2, 4), (3, i[0] * 4), (4, i[1] * 4), (5, i[0] * 4)]
     if k == L.E_AXPBY_F32:

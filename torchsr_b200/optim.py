@@ -5,6 +5,7 @@ adam_pack_kernel), replacing torch's multi-tensor Adam launches plus the separat
 Same update rule, defaults and param_group keys as torch.optim.Adam (reference torchsr/srgan/trainer.py:171-185:
 lr 1e-4, betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad), so lr schedulers (StepLR) work unchanged; a tensor
 learning rate and the device-side step counter make a step capturable in a CUDA graph. There is no CPU path."""
+import ctypes as C
 from typing import Dict, List
 
 import torch
@@ -17,11 +18,21 @@ ADAM_TILES = 4     # kAdamTiles in csrc/eltwise.cu
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    """late_numel > 0: Linear weights of at least that many elements (the discriminator's 18.9 M-element classifier
+    weight: 80 % of its parameters) are updated by a SECOND launch on a side stream. The layers that read them sit at
+    the end of the network, so the next forward of the module starts on the freshly updated conv weights while the big
+    update is still streaming through HBM; the module's forward waits for it right before the first launch that reads
+    those weights (engine.Plan.run_forward, mark "late_weights"). The caller must call join() before anything else
+    touches those parameters (the trainers do, at the end of every step)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, late_numel: int = 0):
         if not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or eps < 0.0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._tables: Dict[int, Dict[tuple, dict]] = {}     # group index -> {address-set key -> table}
+        self.late_numel = late_numel
+        self._late_stream = None
+        self._late_pending: List = []                       # (event, stores) of late launches not yet joined
 
     # ---- per-group device state
     def _group_state(self, gi: int, group) -> dict:
@@ -54,15 +65,27 @@ class FusedAdam(torch.optim.Optimizer):
                       counter=torch.zeros(1, dtype=torch.int32, device=dev), offs=offs)
             for p, o in zip(params, offs):
                 s = self.state[p]
-                s["step"] = st["step"]
+                s["step"] = st["step"]      # (late-launched parameters count the same steps in st["step_late"])
                 s["exp_avg"] = st["m"][o:o + p.numel()].view(p.shape)
                 s["exp_avg_sq"] = st["v"][o:o + p.numel()].view(p.shape)
-        # table
+        # table(s): main launch + optional late launch (big Linear weights, see the class docstring)
         recs = self._recs_of(params)
+        is_late = []
+        for p in params:
+            rec, _ = recs.get(id(p), (None, None))
+            is_late.append(self.late_numel > 0 and isinstance(rec, engine.LinearRec) and rec.Hf * rec.Wf <= 64 and
+                           rec.w_fwd is not None and p.numel() >= self.late_numel)
+        order = [k for k in range(len(params)) if not is_late[k]] + [k for k in range(len(params)) if is_late[k]]
+        n_main = sum(1 for f in is_late if not f)
         arr = (L.AdamEntry * len(params))()
         blocks = 0
+        main_blocks = 0
         stores = set()
-        for k, (p, o) in enumerate(zip(params, st["offs"])):
+        late_stores = set()
+        for k, src in enumerate(order):
+            p, o = params[src], st["offs"][src]
+            if k == n_main:
+                main_blocks, blocks = blocks, 0        # the late table counts its blocks from zero
             e = arr[k]
             if not p.is_contiguous() or not p.grad.is_contiguous() or p.dtype != torch.float32:
                 raise L.TorchSRB200Error("FusedAdam needs contiguous fp32 parameters and gradients")
@@ -86,6 +109,8 @@ class FusedAdam(torch.optim.Optimizer):
                 e.dst_fwd = ops.ptr(rec.w_fwd)
                 blocks += rec.nout * (((rec.C + 31) // 32 + ADAM_TILES - 1) // ADAM_TILES)
                 stores.add(store)
+                if k >= n_main:
+                    late_stores.add(store)
             else:
                 e.mode = L.AD_PLAIN
                 blocks += (p.numel() + 1023) // 1024
@@ -98,7 +123,15 @@ class FusedAdam(torch.optim.Optimizer):
         st["table_host"] = host
         st["table"] = torch.empty(host.numel(), dtype=torch.uint8, device=dev)
         st["table"].copy_(host, non_blocking=True)
-        st["n"], st["blocks"], st["stores"] = len(params), blocks, stores
+        if n_main == len(params):
+            main_blocks, blocks = blocks, 0
+        st["n"], st["blocks"], st["stores"] = n_main, main_blocks, stores
+        st["n_late"], st["blocks_late"], st["late_stores"] = len(params) - n_main, blocks, late_stores
+        st["late_offset"] = n_main * C.sizeof(L.AdamEntry)
+        if st["n_late"] and "step_late" not in st:
+            src = old if (old is not None and "step_late" in old) else None
+            st["step_late"] = src["step_late"] if src else st["step"].clone()
+            st["counter_late"] = src["counter_late"] if src else torch.zeros(1, dtype=torch.int32, device=dev)
         variants[key] = st
         return st
 
@@ -131,8 +164,33 @@ class FusedAdam(torch.optim.Optimizer):
             lr = group["lr"]
             lr_t = lr if (isinstance(lr, torch.Tensor) and lr.is_cuda) else None
             b1, b2 = group["betas"]
-            ops.run_now(ops.elt(L.E_ADAM, p=[st["table"], lr_t, st["step"], st["counter"]], i=[st["n"], st["blocks"]],
-                                f=[0.0 if lr_t is not None else float(lr), b1, b2, group["eps"], 1.0 - b1, 1.0 - b2]))
+            f = [0.0 if lr_t is not None else float(lr), b1, b2, group["eps"], 1.0 - b1, 1.0 - b2]
+            if st["n"]:
+                ops.run_now(ops.elt(L.E_ADAM, p=[st["table"], lr_t, st["step"], st["counter"]], i=[st["n"], st["blocks"]],
+                                    f=f))
+            if st["n_late"]:
+                dev = st["table"].device
+                cur = torch.cuda.current_stream(dev)
+                if self._late_stream is None:
+                    self._late_stream = torch.cuda.Stream(device=dev)
+                side = self._late_stream
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.run_now(ops.elt(L.E_ADAM, p=[ops.ptr(st["table"], st["late_offset"]), lr_t, st["step_late"],
+                                                     st["counter_late"]], i=[st["n_late"], st["blocks_late"]], f=f))
+                    ev = side.record_event()
+                for store in st["late_stores"]:
+                    store.late_event = ev
+                self._late_pending.append((ev, st["late_stores"]))
             for store in st["stores"]:
                 store.opt_fresh = True     # its 'std' conv / Linear packs were just rewritten by the kernel
         return loss
+
+    def join(self):
+        """Makes the current stream wait for the late launches of step() and forgets them."""
+        for ev, stores in self._late_pending:
+            torch.cuda.current_stream().wait_event(ev)
+            for store in stores:
+                if store.late_event is ev:
+                    store.late_event = None
+        self._late_pending.clear()

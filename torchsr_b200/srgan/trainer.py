@@ -93,9 +93,11 @@ class SRGANTrainer:
         # Adam on this repo's kernels (optim.FusedAdam: one launch updates parameters, state and the packed bf16 weight
         # copies); tensor lr + device-side step counter so that a whole training step can be replayed as one CUDA graph
         # (graph_step) while StepLR keeps working (schedulers fill_() a tensor learning rate in place).
-        mk = lambda params: FusedAdam(params, lr=torch.tensor(0.0001, device=self.device), betas=(0.9, 0.999))  # noqa: E731
+        mk = lambda params, **kw: FusedAdam(params, lr=torch.tensor(0.0001, device=self.device), betas=(0.9, 0.999), **kw)  # noqa: E731
         self.psnr_optimizer = mk(self.generator.parameters())
-        self.disc_optimizer = mk(self.discriminator.parameters())
+        # the classifier weight (80 % of the discriminator's parameters) is updated by a second launch on a side stream:
+        # D(super_res) of the generator step starts on the updated conv weights meanwhile (joined at the end of the step)
+        self.disc_optimizer = mk(self.discriminator.parameters(), late_numel=1 << 20)
         self.gen_optimizer = mk(self.generator.parameters())
         step = max(1, self.epochs // 8)   # reference :188 divides by zero for --epochs < 8
         self.disc_scheduler = optim.lr_scheduler.StepLR(self.disc_optimizer, step_size=step, gamma=0.6)
@@ -183,6 +185,7 @@ class SRGANTrainer:
             gen_loss = losses.total(content_loss, adversarial_loss)
             gen_loss.backward(self._one)
         self.gen_optimizer.step()
+        self.disc_optimizer.join()
         return gen_loss.detach()
 
     # ------------------------------------------------------------------ whole-step CUDA graph
