@@ -566,8 +566,12 @@ def gpu_eager_baseline(batch, steps=10):
 
 def dp_parity(trainer, lr_d, hr_d):
     """Data-parallel correctness (reference */trainer.py:143-157 DDP semantics, BatchNorm local): the gradient every rank
-    holds after the in-backward exchange must equal the mean over ranks of the gradients each rank computes alone on
-    its own shard. Returns the max over both modules and all ranks of the rel-L2 difference."""
+    holds after the in-backward exchange (bucketed all-reduce; factor all-gather + local GEMM for the classifier weight)
+    must equal the mean over ranks of the gradients the ranks computed on their own shards. Both sides come from the
+    SAME backward execution (engine.Plan.capture_local snapshots the pre-exchange gradient): two separate executions of
+    this bf16 network differ by ~1e-1 in the discriminator's gradient through atomics-order noise alone (rounding flips
+    of near-zero pre-activations), which would mask the exchange error being measured. Returns the max over both
+    modules and all ranks of the rel-L2 difference."""
     import torch
     import torch.distributed as dist
     from torchsr_b200 import losses
@@ -577,6 +581,11 @@ def dp_parity(trainer, lr_d, hr_d):
 
     def flat_grads(module):
         return torch.cat([p.grad.detach().reshape(-1).float() for p in module.parameters()])
+
+    def unpad(module, flat):
+        """engine's flat gradient pads every parameter to a multiple of 4 elements: back to the dense order."""
+        st = module._tsr["store"]
+        return torch.cat([flat[st.offsets[id(p)]:st.offsets[id(p)] + p.numel()] for p in st.params])
 
     def d_loss():
         with torch.no_grad():
@@ -588,17 +597,21 @@ def dp_parity(trainer, lr_d, hr_d):
         return losses.mse(trainer.generator(lr_d), hr_d)
 
     for module, loss_fn in ((trainer.discriminator, d_loss), (trainer.generator, g_loss)):
-        ddp = module._tsr.get("ddp")
-        module._tsr["ddp"] = None                       # this rank alone, on its own shard
+        cap = []
         module.zero_grad()
-        loss_fn().backward(one)
-        local = flat_grads(module).clone()
+        loss = loss_fn()
+        for pool in module._tsr["plans"].values():
+            for plan in pool:
+                plan.capture_local = cap
+        loss.backward(one)
+        for pool in module._tsr["plans"].values():
+            for plan in pool:
+                plan.capture_local = None
+        assert len(cap) == 1, len(cap)
+        local = unpad(module, cap[0])
         gathered = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
         expect = torch.stack(gathered).mean(0)
-        module._tsr["ddp"] = ddp                        # the product path: exchange inside backward
-        module.zero_grad()
-        loss_fn().backward(one)
         got = flat_grads(module)
         err = ((got - expect).double().norm() / expect.double().norm().clamp_min(1e-30)).reshape(1).float()
         dist.all_reduce(err, op=dist.ReduceOp.MAX)

@@ -1,9 +1,10 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 30 --warmup 5 --only none > gpurun_out/bench_r2e.json 2> gpurun_out/bench_r2e.err; tail -c 300 gpurun_out/bench_r2e.err
+nvidia-smi -L | head -3
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 tools/dp_check.py 16 2>&1 | tail -15
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29712 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_r2f_n2.json 2> gpurun_out/bench_r2f_n2.err; tail -c 600 gpurun_out/bench_r2f_n2.err
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench_r2e.json').read().strip().splitlines()[-1])
-for k in ('value','ms_per_step','e2e','launches_per_step'):
-    print(k, json.dumps(d.get(k))[:700])
+d=json.loads(open('gpurun_out/bench_r2f_n2.json').read().strip().splitlines()[-1])
+for k in ('value','ms_per_step','e2e','launches_per_step','dp_parity','b64'):
+    print(k, json.dumps(d.get(k))[:600])
 PY
-TIMELINE=gpurun_out/timeline_r2e.csv TOP=3 timeout 200 python tools/profile_step.py 16 2>&1 | tail -4 | cut -c1-160

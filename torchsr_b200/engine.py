@@ -742,6 +742,18 @@ class Plan:
                 w = self.factors["lin"].weight
                 lin_lo = self.store.offsets[id(w)]
                 lin_hi = lin_lo + _round_up(w.numel(), 4)
+            cap = getattr(self, "capture_local", None)
+            if cap is not None:
+                # checker hook (tools/dp_check.py, bench.py dp_parity): this rank's own gradient of THIS backward
+                # execution, before the exchange (the Linear weight slice from the local factors)
+                snap = gb.flat.clone()
+                if mark is not None:
+                    from .nets import linear_wgrad_gemm
+                    f = self.factors
+                    d = linear_wgrad_gemm(self, f["a"], f["xt"], f["rows"], 1.0, out=snap[lin_lo:lin_lo + w.numel()])
+                    d.side = 0
+                    ops.run_now(d)
+                cap.append(snap)
             from .dist import bucket_slices
             for lo, hi in ((0, self.store.total),) if mark is None else ((0, lin_lo), (lin_hi, self.store.total)):
                 for b0, b1 in bucket_slices(hi - lo, None):

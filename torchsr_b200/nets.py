@@ -232,13 +232,13 @@ def discriminator_linears(m, image_size: int):
     return [LinearRec("classifier.0", m.classifier[0], 512, fm, fm)]
 
 
-def linear_wgrad_gemm(plan: Plan, a: torch.Tensor, xt: torch.Tensor, k_rows: int, scale: float):
+def linear_wgrad_gemm(plan: Plan, a: torch.Tensor, xt: torch.Tensor, k_rows: int, scale: float, out=None):
     """Descriptor of dW = scale * A^T . X over `k_rows` batch rows (a multiple of 64; the gathered factors of all ranks
-    in the data-parallel case), written into the flat gradient slice of the module's first Linear weight."""
+    in the data-parallel case), written into the flat gradient slice of the module's first Linear weight (or `out`)."""
     l1 = plan.store.linears[0]
     return ops.gemm_desc(a=a, M=l1.nout, K=k_rows, a_ld=l1.nout_pad, a_mn_major=True, w=xt, n_rows=l1.K, block_n=128,
-                         out=plan.grads.grad_slice(l1.weight), out_ld=l1.K, n_valid=l1.K, out_f32=True, acc_scale=scale,
-                         w_chunked=True, side=True)
+                         out=out if out is not None else plan.grads.grad_slice(l1.weight), out_ld=l1.K, n_valid=l1.K,
+                         out_f32=True, acc_scale=scale, w_chunked=True, side=True)
 
 
 def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
