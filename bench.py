@@ -633,8 +633,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     distributed = world > 1
     if distributed:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from torchsr_b200.dist import init_process_group as tdist_init
+        tdist_init(local)
     from torchsr_b200 import _lib as L
     from torchsr_b200 import ops
     from torchsr_b200.srgan.trainer import SRGANTrainer

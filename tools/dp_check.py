@@ -18,8 +18,8 @@ import torch.distributed as dist  # noqa: E402
 def main():
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from torchsr_b200.dist import init_process_group as tdist_init
+    tdist_init(local)
     sys.path.insert(0, ROOT)
     import bench
     from torchsr_b200 import ops

@@ -17,9 +17,16 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     novgg = len(sys.argv) > 2 and sys.argv[2] == "novgg"
     torch.manual_seed(0)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:       # torchrun: data-parallel timeline of rank 0
+        import torch.distributed as dist
+        from torchsr_b200.dist import init_process_group as tdist_init
+        tdist_init(local)
     targs = Namespace(disable_amp=False, batch_size=B, epochs=8, pretrain_epochs=1, gan_checkpoint=None,
-                      psnr_checkpoint=None, skip_image_save=True, local_rank=0, rank=-1, world_size=1)
-    tr = SRGANTrainer(torch.device("cuda"), targs, [], [], 0, 0, False)
+                      psnr_checkpoint=None, skip_image_save=True, local_rank=local, rank=rank if world > 1 else -1,
+                      world_size=world)
+    tr = SRGANTrainer(torch.device("cuda"), targs, [], [], 0, 0, world > 1)
     if novgg:
         tr.vgg_loss = lambda a, b: torch.nn.functional.mse_loss(a, b)
     lr, hr = torch.rand(B, 3, 24, 24, device="cuda"), torch.rand(B, 3, 96, 96, device="cuda")
@@ -32,6 +39,8 @@ def main():
         for s in range(steps):
             step_fn(lr, hr, s)
         torch.cuda.synchronize()
+    if rank != 0:
+        return
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     agg = {}
     t0, t1, busy = None, None, 0.0
@@ -89,3 +98,7 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        os._exit(0)

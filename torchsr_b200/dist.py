@@ -17,12 +17,29 @@ import torch
 import torch.distributed as dist
 
 
+def init_process_group(local_rank: int):
+    """dist.init_process_group('nccl') as the reference does (torchsr.py:257-258), with NCCL's kernels on HIGH-priority
+    streams. The compute graph of a training step keeps every SM slot occupied (programmatic dependent launch stages the
+    next kernel's CTAs while the current one drains) on high-priority streams of its own; default-priority NCCL kernels
+    then only start in the gaps - measured: the gradient all-reduces issued in the middle of the discriminator backward
+    ran after its end. High priority lets their few CTAs in as soon as any slot frees."""
+    import os
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    opts = None
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    except Exception:  # noqa: BLE001
+        opts = None
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+
+
 class DataParallelState:
     def __init__(self, group=None, broadcast_buffers: bool = True):
         self.group = group
         self.world = dist.get_world_size(group)
         self.broadcast_buffers = broadcast_buffers
         self.pending: List = []
+        self.gathers: List = []
 
     def allreduce_async(self, t: torch.Tensor):
         """Average `t` over the ranks, asynchronously w.r.t. the current stream."""
@@ -39,9 +56,15 @@ class DataParallelState:
         if self.world == 1:
             out.copy_(t)
             return
-        self.pending.append((dist.all_gather_into_tensor(out, t, group=self.group, async_op=True), None))
+        self.gathers.append(dist.all_gather_into_tensor(out, t, group=self.group, async_op=True))
+
+    def wait_gathers(self):
+        for work in self.gathers:
+            work.wait()
+        self.gathers.clear()
 
     def wait(self):
+        self.wait_gathers()
         for work, t in self.pending:
             work.wait()
             if t is not None:
@@ -91,12 +114,7 @@ def attach(module, group=None, broadcast_buffers: bool = True) -> DataParallelSt
     return state
 
 
-def sync_buffers(module):
-    """DDP's broadcast_buffers=True behaviour: rank 0's buffers win before a training forward. The buffers are
-    coalesced per dtype into one flat tensor (one broadcast per dtype instead of one per buffer), as DDP does."""
-    state = module._tsr.get("ddp")
-    if state is None or not state.broadcast_buffers or state.world == 1:
-        return
+def _broadcast_buffers(module, state):
     with torch.no_grad():
         groups = {}
         for b in module.buffers():
@@ -105,6 +123,52 @@ def sync_buffers(module):
             flat = torch.cat([b.reshape(-1) for b in bufs])
             dist.broadcast(flat, src=0, group=state.group)
             torch._foreach_copy_(bufs, [c.view(b.shape) for b, c in zip(bufs, flat.split([b.numel() for b in bufs]))])
+
+
+def sync_buffers(module):
+    """DDP's broadcast_buffers=True behaviour: rank 0's buffers win before a training forward. The buffers are
+    coalesced per dtype into one flat tensor (one broadcast per dtype instead of one per buffer), as DDP does.
+    When the previous training forward already published rank 0's buffers (publish_buffers, off the critical path)
+    nothing has changed them since and the broadcast is skipped."""
+    state = module._tsr.get("ddp")
+    if state is None or not state.broadcast_buffers or state.world == 1:
+        return
+    ev = getattr(state, "buffers_event", None)
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)      # (already joined by join_buffers in the trainers: a no-op)
+        state.buffers_event = None
+    if getattr(state, "buffers_fresh", False):
+        state.buffers_fresh = False
+        return
+    _broadcast_buffers(module, state)
+
+
+def publish_buffers(module):
+    """Right after a training forward (the only thing that changes BatchNorm buffers) rank 0's buffers are broadcast on a
+    side stream, so the next forward finds them in place instead of paying two broadcasts at its head. Same values
+    as DDP's pre-forward broadcast: nothing modifies the buffers in between. join_buffers() (or the next forward) makes
+    the consumer stream wait."""
+    state = module._tsr.get("ddp")
+    if state is None or not state.broadcast_buffers or state.world == 1 or not torch.cuda.is_available():
+        return
+    cur = torch.cuda.current_stream()
+    side = getattr(state, "buffers_stream", None)
+    if side is None:
+        side = state.buffers_stream = torch.cuda.Stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        _broadcast_buffers(module, state)
+        state.buffers_event = side.record_event()
+    state.buffers_fresh = True
+
+
+def join_buffers(module):
+    """The current stream waits for publish_buffers (end of a training step; required inside CUDA-graph capture)."""
+    state = module._tsr.get("ddp")
+    ev = getattr(state, "buffers_event", None) if state is not None else None
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+        state.buffers_event = None
 
 
 @contextlib.contextmanager

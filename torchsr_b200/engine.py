@@ -272,13 +272,21 @@ class GradBuffers:
         st = self.store
         self.flat = torch.zeros(max(st.total, 4), dtype=F32, device=st.device)
         self.acc_arena = torch.zeros(st.acc_elems, dtype=F32, device=st.device)
+        self.unpack_desc = None      # (set below; unpack_for() calls _ensure() again while it is being built)
+        self._tabs = []
+        self.unpack_desc = self.unpack_for(st.convs)
+
+    def unpack_for(self, convs: List[ConvRec]):
+        """One-launch descriptor that unpacks the weight-gradient accumulators of `convs` into the flat gradient."""
+        self._ensure()
         unpack = []
-        for r in st.convs:
+        for r in convs:
             n_acc = r.acc_rows * r.acc_taps * r.acc_cols
             unpack.append(dict(src=self.acc(r), dst=self.grad_slice(r.weight), mode=r.fwd_mode, cout=r.cout, cin=r.cin,
                                kh=r.k, kw=r.k, rows_pad=r.acc_rows, cols_pad=r.acc_cols, shuffle=r.shuffle, count=n_acc))
-        self._tab, n, blocks = ops.pack_table(unpack, st.device)
-        self.unpack_desc = ops.elt(L.E_UNPACK_G, p=[self._tab], i=[n, blocks])
+        tab, n, blocks = ops.pack_table(unpack, self.store.device)
+        self._tabs.append(tab)
+        return ops.elt(L.E_UNPACK_G, p=[tab], i=[n, blocks])
 
     def grad_slice(self, p: torch.Tensor) -> torch.Tensor:
         self._ensure()
@@ -677,6 +685,18 @@ class Plan:
                            dy_c=dy.C, out=self.grads.acc(rec), cout_valid=rec.acc_rows, block_n=block_n, x_c0=x.c0, dy_c0=dy.c0)
         prog.add(d)
 
+    def early_unpack(self, prog, convs: List[ConvRec], first_param: torch.Tensor, end_param: torch.Tensor):
+        """Data-parallel programs only: the weight gradients of `convs` (the deep layers, produced first in backward)
+        are unpacked NOW and the flat-gradient slice [offset(first_param), offset(end_param)) - those conv weights and
+        the BatchNorm parameters between them - is marked final ("early_grads"), so that its all-reduce overlaps the
+        rest of backward (run_backward). The unpack launch joins the weight-gradient side branch."""
+        if not getattr(self, "_building_dist", False):
+            return
+        prog.add(self.grads.unpack_for(convs))
+        prog.mark("early_grads")
+        self.early_slice = (self.store.offsets[id(first_param)], self.store.offsets[id(end_param)])
+        self._early_unpacked = {r.name for r in convs}
+
     # ---- execution (set by the net definition: input_fn, output_fn, ingest_fn, grad_input_fn, post_backward)
     def _run_fwd_program(self):
         ev, mark = self.store.late_event, self.fwd.marks.get("late_weights")
@@ -727,14 +747,28 @@ class Plan:
         if dist_on:
             assert not defer_comm
             mark = prog.marks.get("factors")
+            early = prog.marks.get("early_grads")
+            from .dist import bucket_slices
+            pos = 0
             if mark is not None:
                 prog.run(0, mark)
+                pos = mark
                 fa = self._factor_buffers(ddp.world)
                 ddp.allgather_async(fa["a_all"], self.factors["a"])
                 ddp.allgather_async(fa["xt_all"], self.factors["xt"])
-                prog.run(mark, -1)
-            else:
-                prog.run()
+            sent = []         # [lo, hi) slices of the flat gradient already handed to NCCL
+            cap = getattr(self, "capture_local", None)
+            early_snap = None
+            if early is not None:
+                prog.run(pos, early - pos)
+                pos = early
+                lo, hi = self.early_slice
+                if cap is not None:
+                    early_snap = (lo, hi, gb.flat[lo:hi].clone())     # before the in-place reduction starts
+                for b0, b1 in bucket_slices(hi - lo, None):
+                    ddp.allreduce_async(gb.flat[lo + b0:lo + b1])
+                sent.append((lo, hi))
+            prog.run(pos, -1)
             for fn in self.post_backward:
                 fn()
             lin_lo = lin_hi = None
@@ -742,11 +776,14 @@ class Plan:
                 w = self.factors["lin"].weight
                 lin_lo = self.store.offsets[id(w)]
                 lin_hi = lin_lo + _round_up(w.numel(), 4)
-            cap = getattr(self, "capture_local", None)
+                sent.append((lin_lo, lin_hi))      # formed locally from the gathered factors, never all-reduced
             if cap is not None:
                 # checker hook (tools/dp_check.py, bench.py dp_parity): this rank's own gradient of THIS backward
-                # execution, before the exchange (the Linear weight slice from the local factors)
+                # execution, before the exchange (the Linear weight slice from the local factors; the early slice was
+                # copied before its in-place reduction started)
                 snap = gb.flat.clone()
+                if early_snap is not None:
+                    snap[early_snap[0]:early_snap[1]].copy_(early_snap[2])
                 if mark is not None:
                     from .nets import linear_wgrad_gemm
                     f = self.factors
@@ -754,13 +791,16 @@ class Plan:
                     d.side = 0
                     ops.run_now(d)
                 cap.append(snap)
-            from .dist import bucket_slices
-            for lo, hi in ((0, self.store.total),) if mark is None else ((0, lin_lo), (lin_hi, self.store.total)):
-                for b0, b1 in bucket_slices(hi - lo, None):
-                    ddp.allreduce_async(gb.flat[lo + b0:lo + b1])
-            ddp.wait()          # the current stream waits for the gathers and the all-reduces
+            cur = 0
+            for lo, hi in sorted(sent) + [(self.store.total, self.store.total)]:
+                if lo > cur:
+                    for b0, b1 in bucket_slices(lo - cur, None):
+                        ddp.allreduce_async(gb.flat[cur + b0:cur + b1])
+                cur = max(cur, hi)
             if mark is not None:
-                ops.run_now(fa["gemm"])
+                ddp.wait_gathers()      # the current stream waits for the gathered factors ...
+                ops.run_now(fa["gemm"])  # ... and forms the averaged product while the last all-reduces are in flight
+            ddp.wait()
             flat = gb.flat if alias else gb.flat.clone()
         else:
             prog.run()
@@ -803,7 +843,12 @@ class Plan:
                 g = fn(prog, g, want_x, want_w)
             self.last_g[key] = g
             if want_w:
-                prog.add(self.grads.unpack_desc)
+                done = getattr(self, "_early_unpacked", None)
+                if done:
+                    prog.add(self.grads.unpack_for([r for r in self.store.convs if r.name not in done]))
+                else:
+                    prog.add(self.grads.unpack_desc)
+            self._early_unpacked = None
             prog.flush()
             self.bwd[key] = prog
         self.cur_g = self.last_g[key]
@@ -958,6 +1003,9 @@ class _PlanFn(torch.autograd.Function):
             from .dist import sync_buffers
             sync_buffers(module)
         out = plan.run_forward(x)
+        if module.training and module._tsr.get("ddp") is not None and plan.has_bn:
+            from .dist import publish_buffers
+            publish_buffers(module)
         if needs_graph:
             wants_w = any(p.requires_grad for p in store.params)
             ctx.lease = _Lease(plan, module._tsr.setdefault("pending", set()) if wants_w else None, module._tsr)

@@ -43,6 +43,7 @@ class ESRGANTrainer(SRGANTrainer):
         loss = self.l1_loss(self.generator(low_res), high_res)
         loss.backward(self._one)
         self.psnr_optimizer.step()
+        tdist.join_buffers(self.generator)
         return loss.detach()
 
     def _gan_loop(self, low_res: Tensor, high_res: Tensor, step: int) -> Tensor:
@@ -71,5 +72,6 @@ class ESRGANTrainer(SRGANTrainer):
         gen_loss.backward(self._one)
         self.gen_optimizer.step()
         self.disc_optimizer.join()
+        tdist.join_buffers(self.generator)
         self.generator.zero_grad()
         return gen_loss.detach()

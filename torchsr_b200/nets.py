@@ -271,6 +271,8 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
 
     prev = f0
     plan.has_bn = True
+    l1 = plan.store.linears[0]
+    early_k = conv_idx[-3]
     for k in conv_idx[1:]:
         rk, bn = R[f"features.{k}"], m.features[k + 1]
         Ho = (prev.H + 2 * rk.pad - rk.k) // rk.stride + 1
@@ -280,6 +282,12 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
 
         def bwd(bp, g, want_x, want_w, rk=rk, bn=bn, raw=raw, coef=coef, xin=prev, k=k):
             d = plan.norm_act_bwd(bp, f"f{k}", g, raw, coef=coef, bn=bn, act=L.ACT_LEAKY, want_w=want_w)
+            if want_w and k == conv_idx[-4]:
+                # data parallel: the three deepest convs hold 88 % of the conv parameters and their weight gradients
+                # were launched at least one stage ago - unpack and all-reduce that slice now (engine.Plan.early_unpack;
+                # emitted before this stage's own weight-gradient launch: the unpack joins the side branch)
+                plan.early_unpack(bp, [R[f"features.{j}"] for j in conv_idx if j >= early_k],
+                                  R[f"features.{early_k}"].weight, l1.weight)
             if want_w:
                 plan.conv_wgrad(bp, rk, xin, d)
             return plan.conv_dgrad(bp, f"f{k}", rk, d, xin)

@@ -131,6 +131,7 @@ class SRGANTrainer:
         loss = self.mse_loss(super_res, high_res)
         loss.backward(self._one)
         self.psnr_optimizer.step()
+        tdist.join_buffers(self.generator)
         return loss.detach()
 
     def _gan_loop(self, low_res: Tensor, high_res: Tensor, step: int) -> Tensor:
@@ -186,6 +187,7 @@ class SRGANTrainer:
             gen_loss.backward(self._one)
         self.gen_optimizer.step()
         self.disc_optimizer.join()
+        tdist.join_buffers(self.generator)
         return gen_loss.detach()
 
     # ------------------------------------------------------------------ whole-step CUDA graph

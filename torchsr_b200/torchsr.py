@@ -72,8 +72,8 @@ def main(argv=None) -> None:
     trainer_class, crop_size = select_trainer_model(args)
     torch.cuda.set_device(args.local_rank)
     if args.distributed:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group(backend='nccl')
+        from .dist import init_process_group
+        init_process_group(args.local_rank)       # reference torchsr.py:257-258 (NCCL); high-priority NCCL streams
     from .dataset import initialize_datasets
     train_loader, test_loader, train_len, test_len = initialize_datasets(
         args.train_dir, args.batch_size, crop_size, args.dataset_multiplier, args.data_workers, args.distributed,
