@@ -125,6 +125,17 @@ typedef struct tsr_conv_desc {
                                [j*w_chunk_rows, (j+1)*w_chunk_rows) of a [chunks*w_chunk_rows][64] matrix (w_ld = 64): the
                                layout an all-gather of per-rank [rows][64] factor blocks produces */
   float bnf_eps, bnf_momentum;
+  /* fused BatchNorm backward apply on top of bnr_x (nn.BatchNorm2d backward, autograd of srgan/residual.py:65,68,
+     discriminator.py:36-60): the launch stores dx = A*dz + Bx*x + Cc instead of dz and publishes dgamma / dbeta /
+     dalpha; needs a co-resident grid (tsr_conv_bnf_capacity), bnf_counter and bnr_coef. */
+  int32_t bnr_apply, _pad3;
+  void* bnr_dx;             /* bf16 BatchNorm input gradient, addressed with the out strides; `out` still receives dz when
+                               bnr_act is NONE (dz is then the incoming gradient, which a skip path may still read) */
+  const float* bnr_gamma;
+  float* bnr_dgamma;
+  float* bnr_dbeta;
+  float* bnr_dalpha;
+  int64_t bnr_count;
 } tsr_conv_desc_t;
 
 typedef struct tsr_wgrad_desc {
@@ -216,7 +227,9 @@ typedef struct tsr_pack_entry {
 enum tsr_adam_mode {
   TSR_AD_PLAIN = 0,   /* update only (1-D parameters, convs whose packs the pack kernel still makes)       */
   TSR_AD_CONV = 1,    /* OIHW conv weight: + dst_fwd[(t*rows_fwd + co')*cols_fwd + ci], dst_t[(t*rows_t + ci)*cols_t + co'] */
-  TSR_AD_LINEAR = 2   /* Linear weight [n][c*HW+hw]: + dst_fwd[n*K + hw*C + c] (NHWC column order)          */
+  TSR_AD_LINEAR = 2,  /* Linear weight [n][c*HW+hw]: + dst_fwd[n*K + hw*C + c] (NHWC column order)          */
+  TSR_AD_CONV_TILE = 3 /* as CONV for 3x3 weights with cin % 32 == 0, cout % 16 == 0, no PixelShuffle permutation:
+                          one block = 16 x 32 x 9 tile, coalesced float4 state traffic, packs staged through smem */
 };
 typedef struct tsr_adam_entry {
   float* p;           /* parameter (fp32, updated in place) */

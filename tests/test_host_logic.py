@@ -116,7 +116,7 @@ for mod, shape, need_x in [(ResidualDenseBlock(), (2, 64, 8, 8), True), (Residua
 # one discriminator pass over (real | fake) with BatchNorm statistics per half, fused and two-launch BatchNorm paths
 from torchsr_b200 import engine, losses
 for fuse in (True, False):
-    engine.FUSE_BN_FWD = fuse
+    engine.FUSE_BN_FWD = engine.FUSE_BN_BWD = fuse
     for D, n, size in ((Discriminator(), 8, 96), (ED(), 2, 128), (Discriminator(), 3, 96)):
         a, b = torch.rand(n, 3, size, size), torch.rand(n, 3, size, size, requires_grad=True)
         pa, pb = D.forward_pair(a, b)
@@ -125,7 +125,7 @@ for fuse in (True, False):
         assert all(p.grad is not None for p in D.parameters()) and b.grad.shape == b.shape
         paired = [k for k in D._tsr["plans"] if len(k) == 3]
         assert (len(paired) == 1) == (n != 3), (n, D._tsr["plans"].keys())      # 3 x 36 rows per half: falls back
-engine.FUSE_BN_FWD = True
+engine.FUSE_BN_FWD = engine.FUSE_BN_BWD = True
 x = torch.rand(4, 3, 8, 8, requires_grad=True)
 for fn in (lambda: losses.mse(x, torch.rand(4, 3, 8, 8)), lambda: losses.l1(x, torch.rand(4, 3, 8, 8), scale=0.01),
            lambda: losses.total(losses.relativistic_d(x[:, :1, 0, 0], x[:, 1:2, 0, 0]),

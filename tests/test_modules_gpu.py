@@ -26,6 +26,7 @@ def bn_fuse(request, monkeypatch):
     """Runs a test with the fused conv+BatchNorm launch (default) or with the two-launch path (conv, then bn_act)."""
     from torchsr_b200 import engine
     monkeypatch.setattr(engine, "FUSE_BN_FWD", bool(request.param))
+    monkeypatch.setattr(engine, "FUSE_BN_BWD", bool(request.param))
     return bool(request.param)
 
 
@@ -186,11 +187,69 @@ def test_discriminator_two_outstanding_forwards_and_frozen_pass():
     assert x.grad is not None and all(p.grad is None for p in D.parameters())
 
 
+def _stage_assert(rep, label):
+    print(label, "stagewise summary (max error, tolerance, checks):", rep.summary())
+    bad = rep.failures()
+    assert not bad, (label, len(bad), "of", len(rep.rows), "worst", rep.worst(), bad[:6])
+
+
+@BN_PATHS
+def test_srgan_generator_every_stage_teacher_forced(bn_fuse):
+    """All 33 conv + BatchNorm stages of the 16-block generator, each checked against fp32 math on the tensors the CUDA
+    path stored around it: raw conv output, batch statistics, stage output, BatchNorm input gradient, data gradient and
+    EVERY parameter gradient (conv weights, gamma, beta, PReLU slopes) to a few 1e-3 (tests/stagewise_checks.py)."""
+    import module_checks as MC
+    import stagewise_checks as SC
+    MC_, SG, SD, EG, ED = _mods()
+    torch.manual_seed(41)
+    G = SG()
+    MC.randomize_bn(G)
+    G = G.cuda().train()
+    x = torch.rand(4, 3, 24, 24, device="cuda")
+    gout = torch.randn(4, 3, 96, 96, device="cuda")
+    rep = SC.srgan_generator_stagewise(G, x, gout)
+    assert len(rep.rows) > 33 * 8
+    _stage_assert(rep, "srgan generator " + ("fused" if bn_fuse else "two-launch"))
+
+
+@BN_PATHS
+@pytest.mark.parametrize("pair", [False, True], ids=["one-call", "paired-call"])
+def test_srgan_discriminator_every_stage_teacher_forced(bn_fuse, pair):
+    """The seven conv + BatchNorm + LeakyReLU stages of the discriminator, forward and backward, for one call and for
+    one paired (real | fake) call with per-half batch statistics: statistics, outputs, gradients, parameter gradients."""
+    import module_checks as MC
+    import stagewise_checks as SC
+    from torchsr_b200.srgan.discriminator import CONV_IDX
+    MC_, SG, SD, EG, ED = _mods()
+    torch.manual_seed(42)
+    D = SD()
+    MC.randomize_bn(D)
+    D = D.cuda().train()
+    xs = [torch.rand(8, 3, 96, 96, device="cuda") for _ in range(2 if pair else 1)]
+    rep = SC.discriminator_stagewise(D, CONV_IDX, xs, pair)
+    _stage_assert(rep, "srgan discriminator " + ("pair " if pair else "") + ("fused" if bn_fuse else "two-launch"))
+
+
+def test_esrgan_discriminator_every_stage_teacher_forced_paired():
+    import module_checks as MC
+    import stagewise_checks as SC
+    from torchsr_b200.esrgan.discriminator import CONV_IDX
+    MC_, SG, SD, EG, ED = _mods()
+    torch.manual_seed(43)
+    D = ED()
+    MC.randomize_bn(D)
+    D = D.cuda().train()
+    xs = [torch.rand(4, 3, 128, 128, device="cuda") for _ in range(2)]
+    rep = SC.discriminator_stagewise(D, CONV_IDX, xs, True)
+    _stage_assert(rep, "esrgan discriminator pair")
+
+
 def _pair_case(D_cls, n, size, fuse, monkeypatch, oracle_fn):
     """forward_pair(a, b) against two separate calls of an identical module AND against the oracle's two calls."""
     import module_checks as MC
     from torchsr_b200 import engine
     monkeypatch.setattr(engine, "FUSE_BN_FWD", fuse)
+    monkeypatch.setattr(engine, "FUSE_BN_BWD", fuse)
     torch.manual_seed(21)
     D1 = D_cls()
     MC.randomize_bn(D1)

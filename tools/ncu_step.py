@@ -1,5 +1,6 @@
-"""Target for ncu (--profile-from-start off): three warm-up training steps, then ONE eager SRGAN `_gan_loop` at the
-bench configuration between cudaProfilerStart/Stop, so the launch list holds exactly one step of this repo's kernels."""
+"""One eager SRGAN GAN step between cudaProfilerStart/Stop (for `ncu --profile-from-start off`): every kernel of the step
+is launched individually through the library (TSR_GRAPHS=0 set by the caller keeps the per-program CUDA graphs off), so
+an ncu launch list maps one line to one kernel of the step. Usage: python tools/ncu_step.py [batch] [steps_profiled]"""
 import os
 import sys
 from argparse import Namespace
@@ -14,6 +15,7 @@ from torchsr_b200.srgan.trainer import SRGANTrainer  # noqa: E402
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     torch.manual_seed(0)
     targs = Namespace(disable_amp=False, batch_size=B, epochs=8, pretrain_epochs=1, gan_checkpoint=None,
                       psnr_checkpoint=None, skip_image_save=True, local_rank=0, rank=-1, world_size=1)
@@ -22,11 +24,12 @@ def main():
     for s in range(3):
         tr._gan_loop(lr, hr, s)
     torch.cuda.synchronize()
-    torch.cuda.profiler.start()
-    loss = tr._gan_loop(lr, hr, 3)
+    torch.cuda.cudart().cudaProfilerStart()
+    for s in range(n):
+        loss = tr._gan_loop(lr, hr, s)
     torch.cuda.synchronize()
-    torch.cuda.profiler.stop()
-    print("loss", float(loss))
+    torch.cuda.cudart().cudaProfilerStop()
+    print("ncu_step done, loss", float(loss))
 
 
 if __name__ == "__main__":

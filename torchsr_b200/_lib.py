@@ -51,6 +51,9 @@ class ConvDesc(C.Structure):
         ("bnf_rv", C.c_void_p), ("bnf_nbt", C.c_void_p), ("bnf_coef", C.c_void_p),
         ("bnf_count", C.c_int64), ("bnf_c", C.c_int32), ("w_chunk_rows", C.c_int32),
         ("bnf_eps", C.c_float), ("bnf_momentum", C.c_float),
+        ("bnr_apply", C.c_int32), ("_pad3", C.c_int32), ("bnr_dx", C.c_void_p),
+        ("bnr_gamma", C.c_void_p), ("bnr_dgamma", C.c_void_p), ("bnr_dbeta", C.c_void_p), ("bnr_dalpha", C.c_void_p),
+        ("bnr_count", C.c_int64),
     ]
 
 
@@ -81,7 +84,7 @@ class PackEntry(C.Structure):
     ]
 
 
-AD_PLAIN, AD_CONV, AD_LINEAR = 0, 1, 2
+AD_PLAIN, AD_CONV, AD_LINEAR, AD_CONV_TILE = 0, 1, 2, 3
 
 
 class AdamEntry(C.Structure):

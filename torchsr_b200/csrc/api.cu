@@ -164,7 +164,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   using namespace tsr;
   if (int e = ensure_init()) return e;
   // the fused training BatchNorm keeps every tile's accumulator in TMEM across a grid barrier: one tile per CTA
-  if (d.bnf_mode == 1) allow_persistent = false;
+  if (d.bnf_mode == 1 || d.bnr_apply) allow_persistent = false;
   ConvParams& p = L->p;
   memset(&p, 0, sizeof(p));
   if (d.block_k != 16 && d.block_k != 32 && d.block_k != 64) return fail(-20, "block_k must be 16/32/64");
@@ -413,6 +413,17 @@ epilogue_params:
     if (e.bnf_mode == 2 && (!e.bnf_rm || e.stats_partial || e.out_preact))
       return fail(-20, "eval-mode fused BatchNorm needs running statistics and takes no stats_partial / out_preact");
   }
+  e.bnr_apply = d.bnr_apply;
+  e.bnr_dx = d.bnr_dx;
+  e.bnr_gamma = d.bnr_gamma;
+  e.bnr_dgamma = d.bnr_dgamma;
+  e.bnr_dbeta = d.bnr_dbeta;
+  e.bnr_dalpha = d.bnr_dalpha;
+  e.bnr_count = d.bnr_count;
+  if (e.bnr_apply && (!e.bnr_x || !e.bnr_dx || !e.bnr_coef || !e.bnr_gamma || !e.bnf_counter || e.bnr_count < 1 || splits != 1 ||
+                      p.persistent || d.out_f32 || d.out_mode != TSR_OUT_LINEAR || e.bnf_mode))
+    return fail(-20, "fused BatchNorm-backward apply needs bnr_x, bnr_coef, bnr_gamma, bnf_counter, bnr_count, a linear "
+                     "bf16 store and one tile per CTA");
   if (e.bnr_x && !e.stats_partial) return fail(-20, "the fused BatchNorm-backward reduction needs stats_partial");
   if (e.bnr_x && e.bnr_act == TSR_ACT_PRELU && !e.bnr_prelu) return fail(-20, "bnr PReLU needs the slope pointer");
   if (e.bnr_x && e.bwd_z) return fail(-20, "bnr_x and bwd_z are mutually exclusive");
@@ -768,6 +779,10 @@ int tsr_prog_add_conv_group(tsr_prog_t* p, const tsr_conv_desc_t* descs, int n) 
     ConvLaunch L;
     if (int e = build_conv(descs[k], &L, false)) return e;
     if (L.p.a_mode != 0 || L.splits != 1) return fail(-20, "conv group members must be unsplit im2col convs");
+    if ((descs[k].bnr_apply != 0) != (descs[0].bnr_apply != 0) ||
+        (descs[k].bnr_apply && k > 0 && (L.p.M_total != grp.g.p[0].M_total || L.tiles_n != grp.g.tiles_n[0])))
+      return fail(-20, "a conv group with the fused BatchNorm-backward apply needs members of one tile grid (its grid "
+                       "barrier counts every CTA of the launch)");
     grp.g.p[k] = L.p;
     grp.g.tiles_n[k] = L.tiles_n;
   }

@@ -608,6 +608,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
     const int group_rows = e.group_rows;
     const int n_groups = group_rows > 0 ? 2 : 1;
     const int bnf = e.bnf_mode;
+    const bool bnr_apply = e.bnr_apply != 0;
     // per-column vectors of this CTA's N tile -> shared memory, once (the chunk loop reads them as broadcasts)
     float* s_bias = reinterpret_cast<float*>(smem_gen + kColVecOff);
     float* s_sc = s_bias + 256;                   // [groups][256]
@@ -920,6 +921,17 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
             scratch[(q * 256 + c) * 2 + 1] = s2;
           }
         }
+        if (bnr_apply) {
+          // fused BatchNorm-backward apply: park dz in the accumulator (warp-collective, every lane) - dx is formed from
+          // it after the grid barrier below
+          uint32_t pz[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pz[i] = __float_as_uint(st ? v[i] : 0.f);
+          tmem_st16(taddr + ch * 16, pz);
+          // with an activation nothing else reads dz; without one dz == the incoming gradient, which a residual
+          // block's skip path still needs: it is stored to `out` as usual, dx goes to bnr_dx
+          if (bnr_act != ACT_NONE) continue;
+        }
         if (st) {
           long long off = out_base + col0;
           if (out_mode == OUT_SHUFFLE) {
@@ -951,10 +963,12 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       }
     }
     // every tcgen05.ld of this tile has completed (tmem_ld_wait above): hand the accumulator stage back to the MMA warp
-    // (the fused training BatchNorm reads the accumulator once more after the grid barrier and arrives there)
+    // (the fused training BatchNorm / BatchNorm-backward apply read the accumulator once more after the grid barrier and
+    // arrive there)
+    if (bnr_apply) tmem_st_wait();
     tc_fence_before();
     __syncwarp();
-    if (bnf != 1 && lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+    if (bnf != 1 && !bnr_apply && lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
     // cross-warp reductions of the epilogue side products -> one red.global.add per column / per tile
     if (want_stats || e.dalpha_partial != nullptr) {
       if (e.dalpha_partial != nullptr) {
@@ -1015,6 +1029,74 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           if (valid && col0 < n_valid) {
             if (out_preact != nullptr) store_bf16x16(out_preact, out_base + col0, v);   // raw conv output for backward
             bn_apply_store(v, ch, col0);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+    }
+    if (bnr_apply) {
+      // ---- fused BatchNorm-backward apply: every CTA of this N tile has added sum(dz), sum(dz*x) of its rows
+      named_bar_sync(1, kConvThreads - 64);
+      if (threadIdx.x == 64) grid_arrive_and_wait(e.bnf_counter + blockIdx.y, gridDim.x * gridDim.z, e.err);
+      named_bar_sync(1, kConvThreads - 64);
+      float* cA = scratch;                 // [groups][256] each; the reduction scratch is free now
+      float* cB = scratch + kMaxBnGroups * 256;
+      float* cC = scratch + 2 * kMaxBnGroups * 256;
+      {
+        const int et = threadIdx.x - 64;
+        const bool publish = blockIdx.x == 0 && blockIdx.z == 0;
+        if (et < p.block_n) {
+          const int c = colbase + et;
+          const bool cv = c < e.bnr_c;
+          const float gm = cv ? __ldg(e.bnr_gamma + c) : 0.f;
+          const float inv_m = 1.f / static_cast<float>(e.bnr_count);
+          float dbeta = 0.f, dgamma = 0.f;
+          for (int g = 0; g < n_groups; ++g) {
+            float A = 0.f, Bx = 0.f, Cc = 0.f;
+            if (cv) {
+              const float* co = e.bnr_coef + static_cast<long long>(g) * 4 * e.bnr_c;
+              const float mu = __ldg(co + 2 * e.bnr_c + c), is = __ldg(co + 3 * e.bnr_c + c);
+              const float* sp = e.stats_partial + (static_cast<long long>(g) * e.stats_ld + c) * 2;
+              const float s1 = __ldcg(sp);
+              const float s2 = is * (__ldcg(sp + 1) - mu * s1);      // sum(dz * xhat) from sum(dz * x)
+              const float c2 = s1 * inv_m, c3 = s2 * inv_m;
+              A = gm * is;
+              Bx = -A * c3 * is;
+              Cc = -A * (c2 - mu * is * c3);
+              dbeta += s1;
+              dgamma += s2;
+            }
+            cA[g * 256 + et] = A;
+            cB[g * 256 + et] = Bx;
+            cC[g * 256 + et] = Cc;
+          }
+          if (publish && cv) {
+            if (e.bnr_dbeta != nullptr) e.bnr_dbeta[c] = dbeta;
+            if (e.bnr_dgamma != nullptr) e.bnr_dgamma[c] = dgamma;
+          }
+        }
+        if (publish && blockIdx.y == 0 && et == 0 && e.bnr_dalpha != nullptr && e.dalpha_partial != nullptr)
+          *e.bnr_dalpha = __ldcg(e.dalpha_partial);
+      }
+      named_bar_sync(1, kConvThreads - 64);
+      tc_fence_after();
+      if (finalize) {
+        for (int ch = ch_begin; ch < ch_end; ++ch) {
+          const int col0 = colbase + ch * 16;
+          uint32_t r[16];
+          tmem_ld16(taddr + ch * 16, r);
+          tmem_ld_wait();
+          if (valid && col0 < n_valid) {
+            float xr[16], dx[16];
+            load_bf16x16(bnr_x, aux_base + col0, xr);
+            const float* a = cA + grp * 256 + ch * 16;
+            const float* b = cB + grp * 256 + ch * 16;
+            const float* c = cC + grp * 256 + ch * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dx[i] = a[i] * __uint_as_float(r[i]) + b[i] * xr[i] + c[i];
+            store_bf16x16(e.bnr_dx, out_base + col0, dx);
           }
         }
       }

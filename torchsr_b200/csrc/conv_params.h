@@ -87,6 +87,20 @@ struct EpiParams {
   float* bnf_coef;           // [groups][4][bnf_c]
   long long bnf_count;       // rows behind each group's statistics
   float bnf_eps, bnf_momentum;
+  // Fused BatchNorm backward APPLY on top of the fused reduction (bnr_x above; data-gradient convs of co-resident
+  // grids): dz is parked in the TMEM accumulator instead of being stored, the CTAs meet at the grid barrier
+  // (bnf_counter) once every column sum is complete, and each CTA turns its tile into the BatchNorm input gradient
+  //   dx = A*dz + Bx*x + Cc,  A = gamma*invstd, Bx = -A*invstd*mean(dz*xhat), Cc = -A*(mean(dz) - mean*invstd*mean(dz*xhat))
+  // (per statistics group) and stores only dx. The first CTA of each N tile publishes dgamma = sum(dz*xhat),
+  // dbeta = sum(dz) (summed over the groups) and the PReLU slope gradient - what bn_bwd_apply_kernel did in a second
+  // launch plus one HBM round trip of dz.
+  int bnr_apply;
+  void* bnr_dx;              // bf16 dx output, addressed like `out` (same strides / channel offset)
+  const float* bnr_gamma;    // [bnr_c]
+  float* bnr_dgamma;         // [bnr_c] or null
+  float* bnr_dbeta;          // [bnr_c] or null
+  float* bnr_dalpha;         // scalar out (= *dalpha_partial) or null
+  long long bnr_count;       // rows per statistics group
 };
 
 struct ConvParams {

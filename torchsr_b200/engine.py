@@ -34,6 +34,9 @@ SPLIT_K_MIN_ITERS = int(os.environ.get("TSR_SPLITK_MIN_ITERS", "0"))
 # (only for grids the device holds at once), eval mode folds the running statistics into the epilogue. "0" keeps the
 # two-launch path (conv with column sums, then bn_act_kernel) everywhere - both stay parity-tested.
 FUSE_BN_FWD = os.environ.get("TSR_BN_FUSE", "1") != "0"
+# the same for backward: dx = A*dz + B*x + C formed in the epilogue of the data-gradient conv that produced dz (after a
+# grid barrier on the column sums) instead of a bn_bwd_apply_kernel launch; "0" keeps the separate launch
+FUSE_BN_BWD = os.environ.get("TSR_BN_BWD_FUSE", "1") != "0"
 ZERO_ARENA_FLOATS = 64 * 1024
 
 
@@ -535,6 +538,12 @@ class Plan:
             if held is not None and self._fuse_bn_reduce(held, x, coef if has_bn else None, act,
                                                          alpha if prelu else None, sums, dacc, G):
                 fused = 1
+                if has_bn and FUSE_BN_BWD and self._fuse_bn_apply(held, name, g, x, dx, bn, act, alpha, want_w, G):
+                    if len(held) > 1:
+                        prog.add_group(held)
+                    else:
+                        prog.add(held[0])
+                    return dx
             if held is not None:
                 if len(held) > 1:
                     prog.add_group(held)
@@ -555,6 +564,47 @@ class Plan:
                                               bn.weight if has_bn else None, dgamma, dbeta, dalpha, dacc],
                          i=[M, C, act, g.ld, x.ld, C, has_bn, fused, fused, group_rows], f=[leaky, gscale]))
         return dx
+
+    def _fuse_bn_apply(self, descs, name: str, g: Act, x: Act, dx: Act, bn, act, alpha, want_w: bool, groups: int) -> bool:
+        """On top of _fuse_bn_reduce: the held data-gradient conv(s) also form dx = A*dz + Bx*x + Cc after a grid barrier
+        and publish dgamma / dbeta / dalpha - no bn_bwd_apply launch, no HBM round trip of dz. Needs every CTA of the
+        launch co-resident (one launch = one conv, or the four parity classes of a stride-2 layer) and a dense target
+        with the geometry of dx. Returns False with the descriptors left as _fuse_bn_reduce made them."""
+        C = x.C
+        if g.ld != C or g.c0 != 0 or g.C != C or dx.ld != C:
+            return False
+        store = self.grads
+        ctr = self.zbuf("bwd", name + ".ctr", 16)
+        M = x.M
+        for d in descs:
+            d.bnr_apply = 1
+            d.bnr_dx = ops.ptr(dx.t)
+            if getattr(d, "_parity", None) is not None:
+                rh, rw = d._parity          # same scatter as `out`: (rh, rw) offset into the fine grid
+                d.bnr_dx = ops.ptr(dx.t) + ((rh * x.W + rw) * dx.ld) * 2
+            d.bnr_gamma = ops.ptr(bn.weight)
+            d.bnr_dgamma = ops.ptr(store.grad_slice(bn.weight)) if want_w else 0
+            d.bnr_dbeta = ops.ptr(store.grad_slice(bn.bias)) if want_w else 0
+            d.bnr_dalpha = ops.ptr(store.grad_slice(alpha)) if (want_w and act == L.ACT_PRELU) else 0
+            d.bnr_count = M // groups
+            d.bnf_counter = ops.ptr(ctr)
+        ok = True
+        total = 0
+        for d in descs:
+            tiles = ((d.N * d.Ho * d.Wo + 127) // 128) * (d.cout_pad // d.block_n)
+            total += tiles
+        if len({(d.N * d.Ho * d.Wo, d.cout_pad // d.block_n) for d in descs}) != 1:
+            ok = False
+        elif ops.DRY:
+            ok = total <= 2 * 148
+        else:
+            ok = ops.conv_coresident_capacity(descs[0]) >= total
+        if not ok:
+            for d in descs:
+                d.bnr_apply = 0
+                d.bnr_dx = d.bnr_gamma = d.bnr_dgamma = d.bnr_dbeta = d.bnr_dalpha = d.bnf_counter = 0
+                d.bnr_count = 0
+        return ok
 
     @staticmethod
     def _fuse_bn_reduce(descs, x: Act, coef, act, alpha, sums, dacc, groups: int = 1) -> bool:

@@ -158,6 +158,14 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     return d
 
 
+def conv_coresident_capacity(d: ConvDesc) -> int:
+    """CTAs of this conv's kernel instantiation / shared-memory footprint the device holds at once."""
+    lib = L.load()
+    ctas, cap = C.c_int(0), C.c_int(0)
+    L.check(lib.tsr_conv_bnf_capacity(C.byref(d), C.byref(ctas), C.byref(cap)))
+    return cap.value
+
+
 def conv_is_coresident(d: ConvDesc) -> bool:
     """True when every CTA of this conv's launch fits on the device at once (needed by the fused training-mode
     BatchNorm, whose CTAs meet at a grid barrier). Dry mode (no device): 2 CTAs on each of 148 SMs."""
@@ -305,6 +313,16 @@ def validate_conv(d: ConvDesc):
             raise ExtentError("split-K conv needs ws / tile_counters and ws_ld >= cout_pad (multiple of 4)")
         _need("conv ws", d.ws, d.N * d.Ho * d.Wo * d.ws_ld * 4)
         _need("conv tile_counters", d.tile_counters, tiles * 4)
+    if d.bnr_apply:
+        if not (d.bnr_x and d.bnr_dx and d.bnr_coef and d.bnr_gamma and d.bnf_counter and d.bnr_count > 0) or d.out_f32:
+            raise ExtentError("fused BatchNorm-backward apply: incomplete descriptor")
+        last = (d.N - 1) * d.os_n + (d.Ho - 1) * d.os_h + (d.Wo - 1) * d.os_w
+        _need("conv bnr_dx", d.bnr_dx, (last + d.out_ch_off + d.n_valid) * 2)
+        for nm, pp, nb in (("gamma", d.bnr_gamma, d.bnr_c * 4), ("dgamma", d.bnr_dgamma, d.bnr_c * 4),
+                           ("dbeta", d.bnr_dbeta, d.bnr_c * 4), ("dalpha", d.bnr_dalpha, 4),
+                           ("counter", d.bnf_counter, (d.cout_pad // d.block_n) * 4)):
+            if pp:
+                _need("conv bnr " + nm, pp, nb)
     if d.bnr_x:
         if not d.stats_partial or d.bwd_z or d.out_mode != L.OUT_LINEAR:
             raise ExtentError("bnr_x needs stats_partial, no bwd_z hook and a linear store")

@@ -101,7 +101,11 @@ class FusedAdam(torch.optim.Optimizer):
                 if rec.need_dgrad:
                     e.dst_t, e.rows_t, e.cols_t = ops.ptr(rec.w_t), rec.t_rows, rec.t_cols
                 e.shuffle = int(rec.shuffle)
-                blocks += (rec.cout * rec.cin + 255) // 256
+                if rec.k == 3 and rec.cin % 32 == 0 and rec.cout % 16 == 0 and not rec.shuffle:
+                    e.mode = L.AD_CONV_TILE
+                    blocks += (rec.cout // 16) * (rec.cin // 32)
+                else:
+                    blocks += (rec.cout * rec.cin + 255) // 256
                 stores.add(store)
             elif isinstance(rec, engine.LinearRec) and rec.Hf * rec.Wf <= 64 and rec.w_fwd is not None:
                 e.mode = L.AD_LINEAR
