@@ -361,11 +361,18 @@ def hbm_kernels(counts, trainer, pk):
         for _ in range(2):
             opt.step()
             opt.join()
+        torch.cuda.synchronize()
+        # replayed as a CUDA graph, like inside graph_step: the eager call's host work (table lookup) would dominate
+        # the smaller kernel; the late launch (big Linear weight, side stream) is part of the step
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            opt.step()
+            opt.join()
+        graph.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            opt.step()
-            opt.join()      # the late launch (big Linear weight, side stream) is part of the step
+            graph.replay()
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 5
@@ -377,7 +384,8 @@ def hbm_kernels(counts, trainer, pk):
 
 def traffic_from_profiles():
     """dram__bytes_read + dram__bytes_write per launch of the dominant kernel, read from the newest committed ncu
-    `--set full` summary (profiles/r*_ncu_full_conv*summary.csv, first data row); None if there is none."""
+    `--set full` summary of the conv kernel (profiles/r*_ncu_full_conv*summary.csv, `ncu --page raw --csv` export: a
+    header row, a units row, one row per captured launch; the first launch is used); (None, None) if there is none."""
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_conv*summary.csv")))
     if not files:
         return None, None
@@ -385,12 +393,13 @@ def traffic_from_profiles():
     path = files[-1]
     try:
         rows = list(csv.reader(open(path)))
-        hdr, units = rows[0], rows[1]
+        hdr, units, row = rows[0], rows[1], rows[2]
         ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        row = rows[2]
         total = float(row[ri]) * scale.get(units[ri], 1.0) + float(row[wi]) * scale.get(units[wi], 1.0)
-        return total, os.path.relpath(path, ROOT) + " (kernel ID 0: " + row[1][:60] + ", grid " + row[3] + ")"
+        name = row[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        grid = row[hdr.index("Grid Size")] if "Grid Size" in hdr else "?"
+        return total, os.path.relpath(path, ROOT) + " (first captured launch: " + name[:60] + ", grid " + grid + ")"
     except Exception:  # noqa: BLE001
         return None, None
 

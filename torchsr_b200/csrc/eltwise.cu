@@ -75,6 +75,38 @@ __global__ void im2row_kernel(const float* __restrict__ x, bf16* __restrict__ E,
   }
 }
 
+// The same mapping with compile-time filter constants (the SRGAN generator's 9x9 3-channel input layer sits at the very
+// head of the step's critical path): the per-element divisions of the generic kernel become multiplies.
+template <int KH, int KW, int C>
+__global__ void __launch_bounds__(256) im2row_ct_kernel(const float* __restrict__ x, bf16* __restrict__ E, int B, int H, int W,
+                                                        int ph, int pw, int sign, int Epad) {
+  pdl_sync();
+  const int groups = Epad / 8;
+  const long long total = static_cast<long long>(B) * H * W * groups;
+  const long long hw = static_cast<long long>(H) * W;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * 256) {
+    const int g = static_cast<int>(idx % groups);
+    const long long pix = idx / groups;
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const long long n = pix / hw;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = g * 8 + j;
+      float val = 0.f;
+      if (col < KH * KW * C) {
+        const int c = col % C, t = col / C;
+        const int kw = t % KW, kh = t / KW;
+        const int hh = h + sign * (kh - ph), ww = w + sign * (kw - pw);
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + (n * C + c) * hw + static_cast<long long>(hh) * W + ww);
+      }
+      v[j] = val;
+    }
+    st8(E + pix * Epad + g * 8, v);
+  }
+}
+
 // Fast path for the 3-channel 3x3 first layers of the discriminators and VGG: one thread per pixel gathers its 27 taps
 // once and writes the whole 64-byte row; the generic kernel above spends most of its time on per-element index
 // arithmetic.
@@ -298,31 +330,38 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
   const bf16* xp = a.x + a.x_off + g * 8;
   const bf16* rp = a.res ? a.res + a.res_off + g * 8 : nullptr;
   bf16* yp = a.y + a.y_off + g * 8;
-  for (long long idx = idx0; idx < total; idx += 2 * stride) {
-    const long long m0 = idx / groups, m1 = (idx + stride) / groups;
-    const bool two = idx + stride < total;
-    const bool hi0 = m0 >= split, hi1 = m1 >= split;
-    float v0[8], v1[8], r0[8], r1[8];
-    ld8(xp + m0 * a.x_ld, v0);
-    if (two) ld8(xp + m1 * a.x_ld, v1);
-    if (rp) {
-      ld8(rp + m0 * a.res_ld, r0);
-      if (two) ld8(rp + m1 * a.res_ld, r1);
+  // four rows in flight per thread: every load of the iteration is issued before the first dependent instruction
+  // (one row per iteration left the kernel latency-bound at ~1.1 TB/s, profiles/r02_ncu_full_bn_act_summary.csv)
+  constexpr int R = 4;
+  for (long long idx = idx0; idx < total; idx += R * stride) {
+    long long m[R];
+    bool on[R];
+    float v[R][8], r[R][8];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      on[k] = idx + k * stride < total;
+      m[k] = (idx + k * stride) / groups;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v0[j] = act_fwd(v0[j] * (hi0 ? sc1[j] : sc[j]) + (hi0 ? sh1[j] : sh[j]), a.act, slope) * a.x_scale;
-      v1[j] = act_fwd(v1[j] * (hi1 ? sc1[j] : sc[j]) + (hi1 ? sh1[j] : sh[j]), a.act, slope) * a.x_scale;
-    }
+    for (int k = 0; k < R; ++k)
+      if (on[k]) ld8(xp + m[k] * a.x_ld, v[k]);
     if (rp) {
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (on[k]) ld8(rp + m[k] * a.res_ld, r[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (!on[k]) continue;
+      const bool hi = m[k] >= split;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v0[j] += r0[j] * a.res_scale;
-        v1[j] += r1[j] * a.res_scale;
+        float t = act_fwd(v[k][j] * (hi ? sc1[j] : sc[j]) + (hi ? sh1[j] : sh[j]), a.act, slope) * a.x_scale;
+        if (rp) t += r[k][j] * a.res_scale;
+        v[k][j] = t;
       }
+      st8(yp + m[k] * a.y_ld, v[k]);
     }
-    st8(yp + m0 * a.y_ld, v0);
-    if (two) st8(yp + m1 * a.y_ld, v1);
   }
 }
 
@@ -498,45 +537,54 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyArgs 
   const bf16* xp = a.x + gi * 8;
   bf16* op = a.dx + gi * 8;
   const bool need_x = a.has_bn || mask;
-  for (long long idx = idx0; idx < total; idx += 2 * stride) {
-    const long long m0 = idx / groups, m1 = (idx + stride) / groups;
-    const bool two = idx + stride < total;
-    const float (*c0)[kMaxBnC] = s_co[m0 >= split ? 1 : 0];
-    const float (*c1)[kMaxBnC] = s_co[(two && m1 >= split) ? 1 : 0];
-    float g0[8], g1[8], x0[8], x1[8];
-    ld8(gp + m0 * a.g_ld, g0);
-    if (two) ld8(gp + m1 * a.g_ld, g1);
+  // four rows in flight per thread, all global loads of an iteration issued before the math (see bn_act_kernel)
+  constexpr int R = 4;
+  for (long long idx = idx0; idx < total; idx += R * stride) {
+    long long m[R];
+    bool on[R];
+    float gv[R][8], xv[R][8];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      on[k] = idx + k * stride < total;
+      m[k] = (idx + k * stride) / groups;
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      if (on[k]) ld8(gp + m[k] * a.g_ld, gv[k]);
     if (need_x) {
-      ld8(xp + m0 * a.x_ld, x0);
-      if (two) ld8(xp + m1 * a.x_ld, x1);
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if (on[k]) ld8(xp + m[k] * a.x_ld, xv[k]);
     }
     if (g2p) {
-      float t0[8], t1[8];
-      ld8(g2p + m0 * a.g_ld, t0);
-      if (two) ld8(g2p + m1 * a.g_ld, t1);
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (!on[k]) continue;
+        float t[8];
+        ld8(g2p + m[k] * a.g_ld, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[k][j] += t[j];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (!on[k]) continue;
+      const float (*cs)[kMaxBnC] = s_co[m[k] >= split ? 1 : 0];
+      float sc[8], sh[8], cA[8], cB[8], cC[8];
+      lds8(cs[0] + gi * 8, sc);
+      lds8(cs[1] + gi * 8, sh);
+      lds8(cs[2] + gi * 8, cA);
+      lds8(cs[3] + gi * 8, cB);
+      lds8(cs[4] + gi * 8, cC);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        g0[j] += t0[j];
-        g1[j] += t1[j];
+        float d = gv[k][j] * a.gscale;
+        if (mask && xv[k][j] * sc[j] + sh[j] <= 0.f) d *= slope;
+        if (a.has_bn) d = cA[j] * d + cB[j] * xv[k][j] + cC[j];
+        gv[k][j] = d;
       }
+      st8(op + m[k] * a.dx_ld, gv[k]);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = gi * 8 + j;
-      float d0 = g0[j] * a.gscale, d1 = g1[j] * a.gscale;
-      if (mask) {
-        if (x0[j] * c0[0][c] + c0[1][c] <= 0.f) d0 *= slope;
-        if (x1[j] * c1[0][c] + c1[1][c] <= 0.f) d1 *= slope;
-      }
-      if (a.has_bn) {
-        d0 = c0[2][c] * d0 + c0[3][c] * x0[j] + c0[4][c];
-        d1 = c1[2][c] * d1 + c1[3][c] * x1[j] + c1[4][c];
-      }
-      g0[j] = d0;
-      g1[j] = d1;
-    }
-    st8(op + m0 * a.dx_ld, g0);
-    if (two) st8(op + m1 * a.dx_ld, g1);
   }
 }
 
@@ -1390,6 +1438,11 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
                       (const float*)p[0], (bf16*)p[1], i[0], i[2], i[3], i[6], i[7], i[8]);
         break;
       }
+      if (i[1] == 3 && i[4] == 9 && i[5] == 9) {                      // 9x9 3-channel input layer of the SRGAN generator
+        ce = launch_k(im2row_ct_kernel<9, 9, 3>, dim3(grid_for(i[0] * i[2] * i[3] * (i[9] / 8))), dim3(256), 0, st, pdl,
+                      (const float*)p[0], (bf16*)p[1], i[0], i[2], i[3], i[6], i[7], i[8], i[9]);
+        break;
+      }
       ce = launch_k(im2row_kernel, dim3(grid_for(i[0] * i[2] * i[3] * (i[9] / 8))), dim3(256), 0, st, pdl, 
           (const float*)p[0], (bf16*)p[1], i[0], i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8], i[9]);
       break;
@@ -1415,7 +1468,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       a.y_off = i[7]; a.res_off = i[8]; a.mode = i[9]; a.count = i[10]; a.group_rows = i[11];
       a.leaky = d.f[0]; a.res_scale = d.f[1]; a.x_scale = d.f[2]; a.eps = d.f[3]; a.momentum = d.f[4];
       if (a.C > kMaxBnC) return cudaErrorInvalidValue;
-      ce = launch_k(bn_act_kernel, dim3(grid_for(i[0] * (i[1] / 8))), dim3(256), 0, st, pdl, a);
+      ce = launch_k(bn_act_kernel, dim3(grid_for((i[0] * (i[1] / 8) + 3) / 4, 256, 148 * 8)), dim3(256), 0, st, pdl, a);
       break;
     }
     case TSR_E_BN_BWD_REDUCE: {
@@ -1440,7 +1493,7 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       if (a.C > kMaxBnC) return cudaErrorInvalidValue;
       a.leaky = d.f[0];
       a.gscale = d.f[1] != 0.f ? d.f[1] : 1.f;
-      ce = launch_k(bn_bwd_apply_kernel, dim3(grid_for(i[0] * (i[1] / 8))), dim3(256), 0, st, pdl, a);
+      ce = launch_k(bn_bwd_apply_kernel, dim3(grid_for((i[0] * (i[1] / 8) + 3) / 4, 256, 148 * 8)), dim3(256), 0, st, pdl, a);
       break;
     }
     case TSR_E_COLSUM_FINALIZE:
