@@ -124,6 +124,21 @@ def test_esrgan_generator_vs_oracle():
     assert r["grad_median"] <= 0.1, (r, sorted(errs.items(), key=lambda kv: -kv[1])[:5])
 
 
+def test_esrgan_generator_23_rrdb_vs_oracle():
+    """The full-depth generator (23 RRDB = 345 dense-block convs) against the oracle, as a module: output and every
+    parameter gradient (module parity had only been run at 2-3 blocks)."""
+    MC, SG, SD, EG, ED = _mods()
+    torch.manual_seed(15)
+    G = EG()
+    assert len(G.blocks) == 23
+    r, errs = MC.check_module(G, lambda sd, x, tr, buf: MC.O.esrgan_generator(sd, x), torch.rand(1, 3, 16, 16))
+    print("esrgan generator, 23 RRDB:", r, sorted(errs.items(), key=lambda kv: -kv[1])[:3])
+    assert r["out"] <= 2e-2, r
+    # measured: median 0.114, worst 0.208 (bias of a 32-channel dense conv deep in the trunk) - 345 LeakyReLU masks from
+    # bf16 pre-activations between the loss and the first block; the 3-block module sits at <= 0.1
+    assert r["grad_median"] <= 0.15 and r["grad_worst"] <= 0.4, (r, sorted(errs.items(), key=lambda kv: -kv[1])[:5])
+
+
 def test_esrgan_discriminator_vs_oracle():
     MC, SG, SD, EG, ED = _mods()
     torch.manual_seed(6)

@@ -791,7 +791,8 @@ class Plan:
                                       ".train() for gradient computation (the reference trainers do)")
         seed = self.ingest_pair_fn(*gout) if isinstance(gout, tuple) else self.ingest_fn(gout)
         dist_on = want_w and ddp is not None and ddp.world > 1
-        prog = self.backward_program(want_x, want_w, seed, dist=dist_on)
+        inline = getattr(self, "inline_adam", None) if (want_w and not dist_on) else None
+        prog = self.backward_program(want_x, want_w, seed, dist=dist_on, inline=inline)
         flat = None
         gb = self.grads
         if dist_on:
@@ -854,6 +855,8 @@ class Plan:
             flat = gb.flat if alias else gb.flat.clone()
         else:
             prog.run()
+            if inline is not None and prog.marks.get("inline_adam") is not None:
+                inline.mark_late_done()
             if want_w:
                 for fn in self.post_backward:
                     fn()
@@ -878,10 +881,11 @@ class Plan:
         return fa
 
     # ---- programs
-    def backward_program(self, want_x: bool, want_w: bool, seed: Act, dist: bool = False) -> "ops.Program":
-        key = (want_x, want_w, dist)
+    def backward_program(self, want_x: bool, want_w: bool, seed: Act, dist: bool = False, inline=None) -> "ops.Program":
+        key = (want_x, want_w, dist, id(inline) if inline is not None else 0)
         if key not in self.bwd:
             self._building_dist = dist      # read by the net definition's tape entries (nets.bwd_head)
+            self._building_inline = inline  # optimizer whose late parameters are updated inside this program
             prog = ops.Program()
             prog.add(ops.elt(L.E_ZERO, p=[self._zarena["bwd"]], i=[ZERO_ARENA_FLOATS * 4]))
             if want_w:
@@ -1087,6 +1091,7 @@ class _PlanFn(torch.autograd.Function):
         # feeding the same loss) AccumulateGrad would add the buffer to a tensor that may alias it: private copy then.
         safe_alias = all(p.grad is None for p in plan.store.params)
         merge = want_w and st.get("merge_pending_grads", False) and not dist_on
+        plan.inline_adam = st.get("inline_adam") if (st.get("alias_grads", False) and safe_alias) else None
         if not merge:
             # data parallel: every backward exchanges its own gradient (averaging is linear, autograd sums the calls)
             others = st.get("pending", set()) - {id(plan)} if want_w else set()

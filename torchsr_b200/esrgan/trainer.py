@@ -57,7 +57,8 @@ class ESRGANTrainer(SRGANTrainer):
         real_output, fake_output = self.discriminator.forward_pair(high_res, super_res.detach())
         # (BCEwL(real - mean(fake), 1) + BCEwL(fake - mean(real), 0)) / 2   (:451-453), one reduction launch
         disc_loss = losses.relativistic_d(real_output, fake_output, scale=0.5)
-        disc_loss.backward(self._one)
+        with self.disc_optimizer.late_in_backward(self.discriminator):
+            disc_loss.backward(self._one)
         self.disc_optimizer.step()
 
         self.gen_optimizer.zero_grad()

@@ -347,6 +347,13 @@ def define_discriminator(m, plan: Plan, shape, conv_idx, sigmoid: bool):
                 bp.mark("factors")         # both factors are final here; the GEMM runs over the gathered ones
             else:
                 bp.add(linear_wgrad_gemm(plan, dpre1_bf, xt, Bp64, 1.0))
+                opt = getattr(plan, "_building_inline", None)
+                adam = opt.late_desc_for(plan) if opt is not None else None
+                if adam is not None:
+                    # optim.FusedAdam.late_in_backward: the classifier weight is updated right behind the GEMM that
+                    # produced its gradient, on the same side branch (nothing later in this backward reads the weight)
+                    bp.add(adam)
+                    bp.mark("inline_adam")
         dflat = plan.act("dflat", B, flat_act.H, flat_act.W, flat_act.C)
         bp.add(ops.elt(L.E_CAST, p=[dflat32, dflat.t], i=[B * K, 0]))
         return dflat

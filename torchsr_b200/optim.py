@@ -33,6 +33,8 @@ class FusedAdam(torch.optim.Optimizer):
         self.late_numel = late_numel
         self._late_stream = None
         self._late_pending: List = []                       # (event, stores) of late launches not yet joined
+        self._inline_tables: Dict[int, dict] = {}           # id(plan) -> in-backward table of the late parameters
+        self._late_done_in_backward = False
 
     # ---- per-group device state
     def _group_state(self, gi: int, group) -> dict:
@@ -132,6 +134,7 @@ class FusedAdam(torch.optim.Optimizer):
         st["n"], st["blocks"], st["stores"] = n_main, main_blocks, stores
         st["n_late"], st["blocks_late"], st["late_stores"] = len(params) - n_main, blocks, late_stores
         st["late_offset"] = n_main * C.sizeof(L.AdamEntry)
+        st["params_late"] = [params[k] for k in order[n_main:]]
         if st["n_late"] and "step_late" not in st:
             src = old if (old is not None and "step_late" in old) else None
             st["step_late"] = src["step_late"] if src else st["step"].clone()
@@ -172,7 +175,9 @@ class FusedAdam(torch.optim.Optimizer):
             if st["n"]:
                 ops.run_now(ops.elt(L.E_ADAM, p=[st["table"], lr_t, st["step"], st["counter"]], i=[st["n"], st["blocks"]],
                                     f=f))
-            if st["n_late"]:
+            if st["n_late"] and self._late_done_in_backward:
+                self._late_done_in_backward = False          # already applied inside this step's backward
+            elif st["n_late"]:
                 dev = st["table"].device
                 cur = torch.cuda.current_stream(dev)
                 if self._late_stream is None:
@@ -189,6 +194,56 @@ class FusedAdam(torch.optim.Optimizer):
             for store in st["stores"]:
                 store.opt_fresh = True     # its 'std' conv / Linear packs were just rewritten by the kernel
         return loss
+
+    # ---- late parameters updated from inside the module's backward launch list
+    def late_in_backward(self, module):
+        """Context for ONE backward of `module` that is followed by step(): the late parameters (see the class
+        docstring) are updated by a launch placed inside the backward launch list, right behind the GEMM that produces
+        their gradient - for the discriminator that is the head of backward, so the 75 MB classifier update streams
+        through HBM under the convolutional backward instead of after it. step() then only updates the rest. Same
+        arithmetic, same step count; active once a regular step() has created the optimizer state."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            ok = bool(self._tables) and module._tsr.get("ddp") is None
+            if ok:
+                module._tsr["inline_adam"] = self
+            try:
+                yield
+            finally:
+                module._tsr.pop("inline_adam", None)
+        return ctx()
+
+    def late_desc_for(self, plan):
+        """The launch descriptor of the in-backward update for `plan` (its gradients are slices of the plan's flat
+        buffer, engine alias mode), or None when this optimizer has no late parameters."""
+        ent = self._inline_tables.get(id(plan))
+        if ent is None:
+            st = next((v for g in self._tables.values() for v in g.values() if v.get("n_late")), None)
+            if st is None:
+                return None
+            n = st["n_late"]
+            raw = bytes(st["table_host"].numpy().tobytes())[st["late_offset"]:st["late_offset"] + n * C.sizeof(L.AdamEntry)]
+            arr = (L.AdamEntry * n).from_buffer_copy(raw)
+            late_params = st["params_late"]
+            for e, p in zip(arr, late_params):
+                e.g = ops.ptr(plan.grads.grad_slice(p))
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+            tab = torch.empty(host.numel(), dtype=torch.uint8, device=st["table"].device)
+            tab.copy_(host, non_blocking=True)
+            group = self.param_groups[0]
+            lr = group["lr"]
+            lr_t = lr if (isinstance(lr, torch.Tensor) and lr.is_cuda) else None
+            b1, b2 = group["betas"]
+            desc = ops.elt(L.E_ADAM, p=[tab, lr_t, st["step_late"], st["counter_late"]], i=[n, st["blocks_late"]],
+                           f=[0.0 if lr_t is not None else float(lr), b1, b2, group["eps"], 1.0 - b1, 1.0 - b2], side=True)
+            ent = self._inline_tables[id(plan)] = dict(desc=desc, tab=tab, host=host, stores=st["late_stores"])
+        return ent["desc"]
+
+    def mark_late_done(self):
+        """Called by the module's backward after it ran the in-backward update (engine.Plan.run_backward)."""
+        self._late_done_in_backward = True
 
     def join(self):
         """Makes the current stream wait for the late launches of step() and forgets them."""

@@ -168,7 +168,8 @@ class SRGANTrainer:
         p_real, p_fake = self.discriminator.forward_pair(high_res, super_res.detach())
         # BCE(p_real, 1) + BCE(p_fake, 0) (:446-448) in one reduction launch, constant labels
         disc_loss = losses.bce(p_real, 1.0, p_fake, 0.0)
-        disc_loss.backward(self._one)
+        with self.disc_optimizer.late_in_backward(self.discriminator):
+            disc_loss.backward(self._one)
         self.disc_optimizer.step()
 
         self.generator.zero_grad()
