@@ -197,6 +197,7 @@ enum tsr_elt_kind {
   TSR_E_CHANSUM_NCHW = 28,
   TSR_E_GAN_LOSS = 29,   /* BCE / BCE-with-logits / relativistic-average GAN criteria, value + gradient, one launch */
   TSR_E_AXPBY_F32 = 30,  /* out = a * (*scalar) * x + b * y on fp32 vectors */
+  TSR_E_CROP_LR = 32,    /* batched RandomCrop + flips + Pillow-exact bicubic /4 (dataset.py:86-99,118-121) on uint8 images in HBM */
   TSR_E_FEAT_T = 31      /* NHWC bf16 features -> chunked transposed [(c,h,w)][batch] bf16 factor of the Linear wgrad GEMM */
 };
 

@@ -1,11 +1,10 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -rA --timeout=600 2>&1 > gpurun_out/pytest_r2l.log; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_r2l.log | tail -20; grep -E "stagewise summary|23 RRDB" gpurun_out/pytest_r2l.log | cut -c1-700
-timeout 600 python bench.py --steps 30 --warmup 5 --only esrgan > gpurun_out/bench_r2l.json 2> gpurun_out/bench_r2l.err; tail -c 300 gpurun_out/bench_r2l.err
-python - <<'PY'
+for h in 0 1; do
+TSR_CONV_HALO=$h timeout 600 python bench.py --steps 30 --warmup 5 --only b64,inference > gpurun_out/bench_halo$h.json 2> gpurun_out/bench_halo$h.err; tail -c 300 gpurun_out/bench_halo$h.err
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_r2l.json').read().strip().splitlines()[-1])
-for k in ('value','ms_per_step','e2e','launches_per_step'):
-    print(k, json.dumps(d.get(k))[:300])
-print('esrgan', d['esrgan'].get('value'), d['esrgan'].get('ms_per_step'))
+d=json.loads(open('gpurun_out/bench_halo$h.json').read().strip().splitlines()[-1])
+print('HALO=$h', 'value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'b64', round(d['b64']['value'],1), 'inference', round(d['inference']['value'],1))
 PY
-TIMELINE=gpurun_out/timeline_r2l.csv TOP=2 timeout 200 python tools/profile_step.py 16 2>&1 | tail -3 | cut -c1-160
+done
+TSR_CONV_HALO=1 timeout 900 python -m pytest tests -m gpu -q --timeout=600 -k "oracle or stage or golden or psnr" 2>&1 | tail -3

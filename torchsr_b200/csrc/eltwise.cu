@@ -1281,6 +1281,69 @@ __global__ void __launch_bounds__(256) feat_t_kernel(const bf16* __restrict__ ac
   }
 }
 
+// ---------------------------------------------------------------------------------------------- input pipeline
+// CROP_LR: the reference's per-sample training transform (torchsr/dataset.py:86-99,118-121) for a whole batch in one
+// launch, on pre-decoded uint8 images resident in HBM: RandomCrop + horizontal / vertical flip -> HR crop (ToTensor:
+// u8 / 255), then ToPILImage -> Resize(crop/4, BICUBIC) -> ToTensor for the LR input. The resize is Pillow's
+// ImagingResample for 8-bit images restated bit for bit (src/libImaging/Resample.c: separable, antialiased - support
+// 2 * scale, 17 taps at /4 -, integer coefficients with 22 fractional bits, horizontal pass first, every pass rounded
+// and clamped to uint8): kk / bounds are the coefficient tables of precompute_coeffs + normalize_coeffs_8bpc, built on
+// the host (gpu_data.pil_bicubic_tables).
+// p0 = pool u8 (images HWC, RGB), p1 = params int64 [B][6] (byte offset of the image, image width in pixels, x0, y0,
+// flip_h, flip_v), p2 = kk int32 [out][ksize], p3 = bounds int32 [out][2] (first tap, tap count), p4 = hr fp32
+// [B][3][crop][crop], p5 = lr fp32 [B][3][out][out]; i: 0 B, 1 crop (<= 128), 2 out, 3 ksize. One block per crop.
+__global__ void __launch_bounds__(256) crop_lr_kernel(const uint8_t* __restrict__ pool, const long long* __restrict__ params,
+                                                      const int* __restrict__ kk, const int* __restrict__ bounds,
+                                                      float* __restrict__ hr, float* __restrict__ lr, int crop, int out,
+                                                      int ksize) {
+  pdl_sync();
+  __shared__ uint8_t tmp[128 * 32 * 3];     // horizontally resampled crop [crop][out][3]
+  const long long* pr = params + 6ll * blockIdx.x;
+  const uint8_t* img = pool + pr[0];
+  const int W = static_cast<int>(pr[1]), x0 = static_cast<int>(pr[2]), y0 = static_cast<int>(pr[3]);
+  const bool fh = pr[4] != 0, fv = pr[5] != 0;
+  auto src = [&](int y, int x) {   // first byte of crop pixel (y, x) in the pool
+    const int sy = y0 + (fv ? crop - 1 - y : y), sx = x0 + (fh ? crop - 1 - x : x);
+    return img + (static_cast<long long>(sy) * W + sx) * 3;
+  };
+  float* hr_b = hr + static_cast<long long>(blockIdx.x) * 3 * crop * crop;
+  for (int i = threadIdx.x; i < crop * crop; i += 256) {
+    const int y = i / crop, x = i - y * crop;
+    const uint8_t* s = src(y, x);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) hr_b[(c * crop + y) * crop + x] = static_cast<float>(s[c]) / 255.f;
+  }
+  // horizontal pass: (y, xx) -> 3 channels
+  for (int i = threadIdx.x; i < crop * out; i += 256) {
+    const int y = i / out, xx = i - y * out;
+    const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
+    const int* k = kk + xx * ksize;
+    int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+    for (int t = 0; t < n; ++t) {
+      const uint8_t* s = src(y, xmin + t);
+      const int w = k[t];
+      a0 += s[0] * w;
+      a1 += s[1] * w;
+      a2 += s[2] * w;
+    }
+    uint8_t* d = tmp + (y * out + xx) * 3;
+    d[0] = static_cast<uint8_t>(min(max(a0 >> 22, 0), 255));
+    d[1] = static_cast<uint8_t>(min(max(a1 >> 22, 0), 255));
+    d[2] = static_cast<uint8_t>(min(max(a2 >> 22, 0), 255));
+  }
+  __syncthreads();
+  float* lr_b = lr + static_cast<long long>(blockIdx.x) * 3 * out * out;
+  for (int i = threadIdx.x; i < out * out * 3; i += 256) {
+    const int c = i % 3, p = i / 3;
+    const int yy = p / out, xx = p - yy * out;
+    const int ymin = bounds[2 * yy], n = bounds[2 * yy + 1];
+    const int* k = kk + yy * ksize;
+    int a = 1 << 21;
+    for (int t = 0; t < n; ++t) a += tmp[((ymin + t) * out + xx) * 3 + c] * k[t];
+    lr_b[(c * out + yy) * out + xx] = static_cast<float>(min(max(a >> 22, 0), 255)) / 255.f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- misc
 // AXPBY (bf16): p0 = x, p1 = y or null, p2 = out; i: 0 n (multiple of 8); f: 0 a, 1 b;  out = a*x + b*y
 __global__ void axpby_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, bf16* __restrict__ out,
@@ -1564,6 +1627,11 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       break;
     case TSR_E_CAST:
       ce = launch_k(cast_kernel, dim3(grid_for(i[0])), dim3(256), 0, st, pdl, p[0], p[1], i[0], i[1]);
+      break;
+    case TSR_E_CROP_LR:
+      if (i[1] > 128 || i[2] > 32 || i[1] % 4 || i[2] * 4 != i[1]) return cudaErrorInvalidValue;
+      ce = launch_k(crop_lr_kernel, dim3(static_cast<unsigned>(i[0])), dim3(256), 0, st, pdl, (const uint8_t*)p[0],
+                    (const long long*)p[1], (const int*)p[2], (const int*)p[3], (float*)p[4], (float*)p[5], i[1], i[2], i[3]);
       break;
     case TSR_E_FEAT_T:
       ce = launch_k(feat_t_kernel, dim3(grid_for(((i[0] + 63) / 64) * i[1] * i[2] * 64)), dim3(256), 0, st, pdl,

@@ -1,6 +1,10 @@
-"""Minimal image-folder input pipeline for the CLI (the reference's torchsr/dataset.py:55-428 is a CPU-side PIL
-pipeline and out of scope for the hot path; this keeps `torchsr train` usable end to end):
-90/10 train/test split, random HR crops + flips, bicubic /4 low-resolution inputs, DistributedSampler when needed."""
+"""Image-folder input pipeline behind `torchsr train` (reference torchsr/dataset.py:55-428): 90/10 train/test split,
+random HR crops + flips, bicubic /4 low-resolution inputs, one shard per rank.
+
+Training batches come from the GPU pipeline (gpu_data.py: images decoded once into HBM, crop + flips + Pillow-exact
+bicubic in one launch per batch) whenever the trainer runs on a CUDA device; TORCHSR_GPU_DATA=0 selects the reference's
+scheme instead (PIL in DataLoader workers, one image decode per crop). The small evaluation split always uses the
+DataLoader path."""
 import os
 import random
 from typing import Tuple
@@ -62,7 +66,8 @@ class TestData(Dataset):
 
 
 def initialize_datasets(train_dir: str, batch_size: int, crop_size: int, dataset_multiplier: int = 1, workers: int = 16,
-                        distributed: bool = False, seed: int = 0) -> Tuple[DataLoader, DataLoader, int, int]:
+                        distributed: bool = False, seed: int = 0, device=None, rank: int = 0,
+                        world_size: int = 1) -> Tuple[DataLoader, DataLoader, int, int]:
     files = _files(train_dir)
     if not files:
         raise RuntimeError(f'no images found under {train_dir}')
@@ -71,9 +76,22 @@ def initialize_datasets(train_dir: str, batch_size: int, crop_size: int, dataset
     n_test = max(1, len(files) // 10)
     test_files, train_files = files[:n_test], files[n_test:] or files
     train, test = TrainData(train_files, crop_size, dataset_multiplier), TestData(test_files, crop_size)
-    ts = DistributedSampler(train, seed=seed) if distributed else None
     es = DistributedSampler(test, seed=seed, shuffle=False) if distributed else None
-    tl = DataLoader(train, batch_size=batch_size, shuffle=ts is None, sampler=ts, num_workers=workers, pin_memory=True,
-                    drop_last=True)
+    use_gpu = device is not None and torch.device(device).type == 'cuda' and os.environ.get('TORCHSR_GPU_DATA', '1') != '0'
+    if use_gpu:
+        from .gpu_data import GpuTrainLoader, ImagePool
+        pool = ImagePool.from_files(train_files, torch.device(device))
+        small = [f for f, (h, w) in zip(train_files, pool.shapes) if h < crop_size or w < crop_size]
+        if small:      # the CPU path upsizes such images; keep them out of the pool instead of failing the run
+            keep = [f for f in train_files if f not in set(small)]
+            if not keep:
+                raise RuntimeError(f'every image under {train_dir} is smaller than the {crop_size}x{crop_size} crop')
+            pool = ImagePool.from_files(keep, torch.device(device))
+        tl = GpuTrainLoader(pool, crop_size, batch_size, dataset_multiplier, seed=seed, rank=rank if distributed else 0,
+                            world_size=world_size if distributed else 1)
+    else:
+        ts = DistributedSampler(train, seed=seed) if distributed else None
+        tl = DataLoader(train, batch_size=batch_size, shuffle=ts is None, sampler=ts, num_workers=workers,
+                        pin_memory=True, drop_last=True)
     el = DataLoader(test, batch_size=batch_size, shuffle=False, sampler=es, num_workers=workers, pin_memory=True)
     return tl, el, len(train), len(test)

@@ -443,6 +443,9 @@ def _elt_extents(d: EltDesc):
         return [(0, i[0] * (4 if i[1] == 0 else 2)), (1, i[0] * (2 if i[1] == 0 else 4))]
     if k == L.E_CHANSUM_NCHW:
         return [(0, i[0] * i[1] * i[2] * 4), (1, i[3] * i[1] * 8)]
+    if k == L.E_CROP_LR:
+        return [(1, i[0] * 6 * 8), (2, i[2] * i[3] * 4), (3, i[2] * 2 * 4), (4, i[0] * 3 * i[1] * i[1] * 4),
+                (5, i[0] * 3 * i[2] * i[2] * 4)]
     if k == L.E_FEAT_T:
         chunks = (i[0] + 63) // 64
         return [(0, ((i[0] * i[2] - 1) * i[3] + i[4] + i[1]) * 2), (1, chunks * i[1] * i[2] * 64 * 2)]

@@ -77,7 +77,7 @@ def main(argv=None) -> None:
     from .dataset import initialize_datasets
     train_loader, test_loader, train_len, test_len = initialize_datasets(
         args.train_dir, args.batch_size, crop_size, args.dataset_multiplier, args.data_workers, args.distributed,
-        args.seed)
+        args.seed, device=device, rank=max(args.rank, 0), world_size=max(args.world_size, 1))
     trainer = trainer_class(device, args, train_loader, test_loader, train_len, test_len, args.distributed)
     trainer.train()
     if args.distributed:
