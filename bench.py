@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-vgg", action="store_true", help="MSE content loss instead of VGG (NOT the headline config)")
     ap.add_argument("--eager", action="store_true", help="call _gan_loop eagerly instead of trainer.graph_step")
     ap.add_argument("--only", default="", help="comma list restricting the extra blocks: b64,inference,esrgan,hbm,"
-                                               "eager_baseline,cpu,roofline,dp_parity (default: all)")
+                                               "eager_baseline,data_pipeline,cpu,roofline,dp_parity (default: all)")
     return ap.parse_args()
 
 
@@ -459,6 +459,29 @@ def inference_block(pk, steps=10):
     return out
 
 
+def data_pipeline_block(batch=16, steps=50):
+    """training batches from the GPU input pipeline (gpu_data.py: RandomCrop + flips + Pillow-exact
+    bicubic /4 on uint8 images resident in HBM, one launch per batch) - crops/s including the host-side index draw."""
+    import torch
+    from torchsr_b200 import gpu_data as GD
+    g = torch.Generator().manual_seed(0)
+    pool = GD.ImagePool([torch.randint(0, 256, (512, 512, 3), dtype=torch.uint8, generator=g) for _ in range(64)], "cuda")
+    loader = GD.GpuTrainLoader(pool, 96, batch, multiplier=-(-steps * batch // 64) + 1, seed=1)
+    it = iter(loader)
+    for _ in range(3):
+        next(it)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        lr, hr = next(it)
+        n += lr.shape[0]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"workload": "GpuTrainLoader: batch %d of 96x96 crops from 64 synthetic 512x512 uint8 images in HBM" % batch,
+            "value": n / dt, "unit": "crops/s", "ms_per_batch": dt / steps * 1e3}
+
+
 def esrgan_block(pk, batch=16, steps=8):
     """BASELINE configs[3] shape on one GPU: ESRGAN (23 RRDB) generator + 10-conv discriminator + VGG loss, 128x128 HR
     crops; one step = ESRGANTrainer._gan_loop through graph_step."""
@@ -789,6 +812,7 @@ def run_b200(args):
         del trainer
         torch.cuda.empty_cache()
         for name, fn in (("inference", lambda: inference_block(pk)), ("esrgan", lambda: esrgan_block(pk)),
+                         ("data_pipeline", lambda: data_pipeline_block(args.batch)),
                          ("gpu_eager_baseline", lambda: gpu_eager_baseline(args.batch))):
             key = {"gpu_eager_baseline": "eager_baseline"}.get(name, name)
             if not want(args, key):

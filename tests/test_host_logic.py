@@ -205,3 +205,14 @@ def test_trainer_resumes_at_checkpoint_epoch(tmp_path, monkeypatch):
     seen.clear()
     tr._gan_train()
     assert seen == [("srgan-gan", 7), ("srgan-gan", 8)], seen
+
+
+def test_install_as_torchsr_gives_reference_import_paths():
+    """`import torchsr...` (the name the reference installs under, setup.py:39-41) served by the drop-in package."""
+    code = ("import sys; sys.path.insert(0, %r); import torchsr_b200; torchsr_b200.install_as_torchsr(); "
+            "from torchsr.srgan.generator import Generator; from torchsr.esrgan.residual import ResidualDenseBlock; "
+            "from torchsr.models import select_trainer_model, CROP_SIZE; from torchsr.torchsr import main; "
+            "import torchsr_b200.srgan.generator as g; assert Generator is g.Generator and CROP_SIZE['srgan'] == 96; "
+            "print('ALIAS_OK')") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "ALIAS_OK" in out.stdout, out.stdout + out.stderr[-2000:]

@@ -1,10 +1,11 @@
 mkdir -p gpurun_out
-for h in 0 1; do
-TSR_CONV_HALO=$h timeout 600 python bench.py --steps 30 --warmup 5 --only b64,inference > gpurun_out/bench_halo$h.json 2> gpurun_out/bench_halo$h.err; tail -c 300 gpurun_out/bench_halo$h.err
-python - <<PY
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 2>&1 > gpurun_out/pytest_r2m.log; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_r2m.log | tail -20
+timeout 900 python bench.py --steps 30 --warmup 5 > gpurun_out/bench_r2m.json 2> gpurun_out/bench_r2m.err; tail -c 300 gpurun_out/bench_r2m.err
+python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/bench_halo$h.json').read().strip().splitlines()[-1])
-print('HALO=$h', 'value', round(d['value'],1), 'ms', round(d['ms_per_step'],4), 'b64', round(d['b64']['value'],1), 'inference', round(d['inference']['value'],1))
+d=json.loads(open('gpurun_out/bench_r2m.json').read().strip().splitlines()[-1])
+for k in ('value','ms_per_step','e2e','launches_per_step','data_pipeline'):
+    print(k, json.dumps(d.get(k))[:400])
+print('b64', d['b64']['value'], 'inference', d['inference']['value'], 'esrgan', d['esrgan']['value'])
+print(json.dumps(d['gpu_eager_baseline'])[:600])
 PY
-done
-TSR_CONV_HALO=1 timeout 900 python -m pytest tests -m gpu -q --timeout=600 -k "oracle or stage or golden or psnr" 2>&1 | tail -3
