@@ -582,6 +582,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
                      it_end - it_begin, tiles_m, trace);
   } else {
     pdl_sync();   // the epilogue reads residuals / statistics buffers written by earlier kernels of the stream
+    if (trace && threadIdx.x == 64) trace[2] = clock64();
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the 16-column chunks.
     const EpiParams& e = p.epi;
@@ -768,6 +769,172 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       else
         store_bf16x16(out, out_base + col0, v);
     };
+    // ---- lean path of the fused training-mode BatchNorm (one tile per CTA, at most two 16-column chunks per warp: the
+    // generator trunk and every narrow layer). The generic epilogue below re-reads its parameter block from the constant
+    // bank inside every chunk and walks through every fusion option; tools/trace_fused.py measured ~1.0 us for each of
+    // its two passes over ONE chunk, ~0.5 us to derive the coefficients and ~1.4 us around the grid barrier. Here every
+    // invariant is in a register before the accumulator is ready, the BatchNorm parameters and the residual rows are
+    // fetched while the main loop runs, and the accumulator stays in registers across the barrier.
+    const int nch = ch_end - ch_begin;
+    if (!PERS && bnf == 1 && nch <= 2 && nsplits == 1 && out_mode == OUT_LINEAR && !out_f32) {
+      const int et = threadIdx.x - 64;
+      const bool publish = blockIdx.x == 0 && blockIdx.z == 0;
+      const bool col_thread = et < p.block_n;
+      const int cc = colbase + et;
+      const bool cv = col_thread && cc < e.bnf_c;
+      float gm = 1.f, bt = 0.f, rm = 0.f, rv = 1.f;
+      if (cv) {
+        if (e.bnf_gamma) gm = __ldg(e.bnf_gamma + cc);
+        if (e.bnf_beta) bt = __ldg(e.bnf_beta + cc);
+        if (publish && e.bnf_rm != nullptr) {
+          rm = e.bnf_rm[cc];
+          rv = e.bnf_rv[cc];
+        }
+      }
+      const float inv_n = 1.f / static_cast<float>(e.bnf_count), eps = e.bnf_eps, mom = e.bnf_momentum;
+      const float cnt = static_cast<float>(e.bnf_count);
+      float* const stats_g = e.stats_partial;
+      const int stats_ld = e.stats_ld;
+      unsigned int* const ctr = e.bnf_counter + blockIdx.y;
+      const unsigned int expected = gridDim.x * gridDim.z;
+      float* const coef_g = e.bnf_coef;
+      const int bnf_c = e.bnf_c;
+      const float rs = e.res_scale;
+      const int res_cols = e.res_cols;
+      const float sl = act == ACT_PRELU ? alpha : (act == ACT_LEAKY ? leaky : 0.f);
+      // residual rows of this thread's chunks -> registers, now
+      uint4 rq[2][2];
+      bool has_r[2] = {false, false};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int col0 = colbase + (ch_begin + k) * 16;
+        has_r[k] = k < nch && res != nullptr && valid && col0 < n_valid && col0 < res_cols;
+        if (has_r[k]) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + aux_base + col0);
+          rq[k][0] = __ldg(rp);
+          rq[k][1] = __ldg(rp + 1);
+        }
+      }
+      const bool okl = mbar_wait(bar_acc_full + 8 * as, (j >> 1) & 1, e.err, 3);
+      tc_fence_after();
+      if (trace && threadIdx.x == 64) trace[5] = clock64();
+      uint32_t r0[16], r1[16];
+      tmem_ld16(taddr + ch_begin * 16, r0);
+      if (nch == 2) tmem_ld16(taddr + (ch_begin + 1) * 16, r1);
+      tmem_ld_wait();
+      float v[2][16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[0][i] = (valid && okl) ? __uint_as_float(r0[i]) : 0.f;
+        v[1][i] = (valid && okl && nch == 2) ? __uint_as_float(r1[i]) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k < nch) {
+          float sq[16], s1, s2;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sq[i] = v[k][i] * v[k][i];
+          butterfly16(v[k], lane, s1);
+          butterfly16(sq, lane, s2);
+          if ((lane & 1) == 0) {
+            const int c = (ch_begin + k) * 16 + butterfly_col(lane);
+            scratch[(q * 256 + c) * 2 + 0] = s1;
+            scratch[(q * 256 + c) * 2 + 1] = s2;
+          }
+        }
+      }
+      if (trace && threadIdx.x == 64) trace[17] = clock64();
+      named_bar_sync(1, kConvThreads - 64);
+      for (int idx = et; idx < p.block_n * 2; idx += kConvThreads - 64) {
+        const int c = idx >> 1, w = idx & 1;
+        float sum0 = 0.f, sum1 = 0.f;
+        bool any0 = false, any1 = false;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float pv = scratch[(qq * 256 + c) * 2 + w];
+          if (group_rows > 0 && s_qgrp[qq] != 0) {
+            sum1 += pv;
+            any1 = true;
+          } else {
+            sum0 += pv;
+            any0 = true;
+          }
+        }
+        if (any0) atomicAdd(stats_g + (colbase + c) * 2 + w, sum0);
+        if (any1) atomicAdd(stats_g + (static_cast<long long>(stats_ld) + colbase + c) * 2 + w, sum1);
+      }
+      if (trace && threadIdx.x == 64) trace[18] = clock64();
+      named_bar_sync(1, kConvThreads - 64);
+      if (threadIdx.x == 64) grid_arrive_and_wait(ctr, expected, e.err);
+      named_bar_sync(1, kConvThreads - 64);
+      if (trace && threadIdx.x == 64) trace[19] = clock64();
+      if (col_thread) {
+        for (int g = 0; g < n_groups; ++g) {
+          const float* sp = stats_g + (static_cast<long long>(g) * stats_ld + cc) * 2;
+          const float mean = cv ? __ldcg(sp) * inv_n : 0.f;
+          const float var = cv ? fmaxf(__ldcg(sp + 1) * inv_n - mean * mean, 0.f) : 1.f;
+          const float invstd = rsqrtf(var + eps);
+          const float sc = gm * invstd;
+          const float sh = bt - mean * sc;
+          s_sc[g * 256 + et] = sc;
+          s_sh[g * 256 + et] = sh;
+          if (publish && cv) {
+            if (coef_g != nullptr) {
+              float* co = coef_g + static_cast<long long>(g) * 4 * bnf_c;
+              co[0 * bnf_c + cc] = sc;
+              co[1 * bnf_c + cc] = sh;
+              co[2 * bnf_c + cc] = mean;
+              co[3 * bnf_c + cc] = invstd;
+            }
+            const float unbiased = cnt > 1.f ? var * cnt / (cnt - 1.f) : var;
+            rm = (1.f - mom) * rm + mom * mean;
+            rv = (1.f - mom) * rv + mom * unbiased;
+          }
+        }
+        if (publish && cv && e.bnf_rm != nullptr) {
+          e.bnf_rm[cc] = rm;
+          e.bnf_rv[cc] = rv;
+        }
+      }
+      if (publish && e.bnf_nbt != nullptr && blockIdx.y == 0 && et == 0) *e.bnf_nbt += n_groups;
+      named_bar_sync(1, kConvThreads - 64);
+      if (trace && threadIdx.x == 64) trace[20] = clock64();
+      if (okl && valid) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int ch = ch_begin + k;
+          const int col0 = colbase + ch * 16;
+          if (k < nch && col0 < n_valid) {
+            if (out_preact != nullptr) store_bf16x16(out_preact, out_base + col0, v[k]);   // raw conv output for backward
+            const float* sc = s_sc + grp * 256 + ch * 16;
+            const float* sh = s_sh + grp * 256 + ch * 16;
+            float y[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float z = v[k][i] * sc[i] + sh[i];
+              y[i] = (act == ACT_NONE || z > 0.f) ? z : z * sl;
+            }
+            if (has_r[k]) {
+              float z[16];
+              unpack_bf16x2(rq[k][0].x, z[0], z[1]);
+              unpack_bf16x2(rq[k][0].y, z[2], z[3]);
+              unpack_bf16x2(rq[k][0].z, z[4], z[5]);
+              unpack_bf16x2(rq[k][0].w, z[6], z[7]);
+              unpack_bf16x2(rq[k][1].x, z[8], z[9]);
+              unpack_bf16x2(rq[k][1].y, z[10], z[11]);
+              unpack_bf16x2(rq[k][1].z, z[12], z[13]);
+              unpack_bf16x2(rq[k][1].w, z[14], z[15]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y[i] += z[i] * rs;
+            }
+            store_bf16x16(out, out_base + col0, y);
+          }
+        }
+      }
+      if (trace && threadIdx.x == 64) trace[21] = clock64();
+      if (trace && threadIdx.x == 64) trace[6] = clock64();
+      break;
+    }
     const bool ok = mbar_wait(bar_acc_full + 8 * as, (j >> 1) & 1, e.err, 3);
     tc_fence_after();
     if (trace && j == 0 && threadIdx.x == 64) trace[5] = clock64();
@@ -962,6 +1129,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         if (trace && threadIdx.x == 64 && ch < 4) trace[33 + 2 * ch] = clock64();
       }
     }
+    if (trace && j == 0 && threadIdx.x == 64) trace[17] = clock64();
     // every tcgen05.ld of this tile has completed (tmem_ld_wait above): hand the accumulator stage back to the MMA warp
     // (the fused training BatchNorm / BatchNorm-backward apply read the accumulator once more after the grid barrier and
     // arrive there)
@@ -1009,13 +1177,16 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       // the scratch slots are reused by the next tile of a persistent CTA
       if (tile_m + static_cast<int>(gridDim.x) < tiles_m) named_bar_sync(1, kConvThreads - 64);
     }
+    if (trace && j == 0 && threadIdx.x == 64) trace[18] = clock64();
     if (bnf == 1) {
       // ---- fused training-mode BatchNorm: wait until every CTA of this N tile has added its column sums, derive the
       // coefficients, then normalise + activate (+ residual) straight from the accumulator
       named_bar_sync(1, kConvThreads - 64);
       if (threadIdx.x == 64) grid_arrive_and_wait(e.bnf_counter + blockIdx.y, gridDim.x * gridDim.z, e.err);
       named_bar_sync(1, kConvThreads - 64);
+      if (trace && j == 0 && threadIdx.x == 64) trace[19] = clock64();
       bnf_coefficients(blockIdx.x == 0 && blockIdx.z == 0);
+      if (trace && j == 0 && threadIdx.x == 64) trace[20] = clock64();
       tc_fence_after();
       if (finalize) {
         for (int ch = ch_begin; ch < ch_end; ++ch) {
@@ -1032,6 +1203,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           }
         }
       }
+      if (trace && j == 0 && threadIdx.x == 64) trace[21] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);

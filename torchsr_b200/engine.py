@@ -37,6 +37,8 @@ FUSE_BN_FWD = os.environ.get("TSR_BN_FUSE", "1") != "0"
 # the same for backward: dx = A*dz + B*x + C formed in the epilogue of the data-gradient conv that produced dz (after a
 # grid barrier on the column sums) instead of a bn_bwd_apply_kernel launch; "0" keeps the separate launch
 FUSE_BN_BWD = os.environ.get("TSR_BN_BWD_FUSE", "1") != "0"
+# pick_block_n halves the N tile while the grid stays at or below this many CTAs (x2)
+HALVE_BELOW_CTAS = int(os.environ.get("TSR_HALVE_BELOW_CTAS", str(NUM_SMS + 20)))
 ZERO_ARENA_FLOATS = 64 * 1024
 
 
@@ -472,7 +474,7 @@ class Plan:
         """Halve the N tile while the grid cannot cover the SMs: these layers are bound by per-SM L2->smem bandwidth
         and per-CTA latency, so more, narrower CTAs win even though the A tile is then fetched once per N tile."""
         tiles_m = (M + 127) // 128
-        while block_n >= 64 and block_n % 32 == 0 and tiles_m * (n_total // block_n) * 2 <= NUM_SMS + 20:
+        while block_n >= 64 and block_n % 32 == 0 and tiles_m * (n_total // block_n) * 2 <= HALVE_BELOW_CTAS:
             block_n //= 2
         return block_n
 
