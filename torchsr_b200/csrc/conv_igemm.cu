@@ -935,6 +935,192 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       if (trace && threadIdx.x == 64) trace[6] = clock64();
       break;
     }
+    // ---- lean path of the fused BatchNorm-backward reduce + apply (same idea as the forward lean path above): dz and
+    // the BatchNorm input x stay in registers across the grid barrier, every invariant is hoisted, x / residual rows and
+    // the per-column parameters are fetched while the main loop runs. One chunk per warp (block_n <= 32: the generator
+    // trunk) - two chunks of dz and x would not fit the 96-register budget of two CTAs per SM.
+    if (!PERS && bnr_apply && nch == 1 && nsplits == 1 && out_mode == OUT_LINEAR && !out_f32 && bnr_x != nullptr &&
+        e.bwd_z == nullptr && e.bias == nullptr && acc_scale == 1.f && e.res2 == nullptr) {
+      const int et = threadIdx.x - 64;
+      const bool publish = blockIdx.x == 0 && blockIdx.z == 0;
+      const bool col_thread = et < p.block_n;
+      const int cc = colbase + et;
+      const bool cv = col_thread && cc < e.bnr_c;
+      const int bc = e.bnr_c;
+      float gm = 0.f, mu[kMaxBnGroups] = {0.f, 0.f}, is[kMaxBnGroups] = {1.f, 1.f};
+      if (cv) {
+        gm = __ldg(e.bnr_gamma + cc);
+        for (int g = 0; g < n_groups; ++g) {
+          mu[g] = __ldg(e.bnr_coef + (static_cast<long long>(g) * 4 + 2) * bc + cc);
+          is[g] = __ldg(e.bnr_coef + (static_cast<long long>(g) * 4 + 3) * bc + cc);
+        }
+      }
+      const float inv_m = 1.f / static_cast<float>(e.bnr_count);
+      float* const stats_g = e.stats_partial;
+      const int stats_ld = e.stats_ld;
+      unsigned int* const ctr = e.bnf_counter + blockIdx.y;
+      const unsigned int expected = gridDim.x * gridDim.z;
+      const float rs = e.res_scale;
+      const int res_cols = e.res_cols;
+      float* const dalpha_g = e.dalpha_partial;
+      void* const dx_out = e.bnr_dx;
+      uint4 xq[1][2], rq[1][2];
+      bool has_c[1] = {false}, has_r[1] = {false};
+#pragma unroll
+      for (int k = 0; k < 1; ++k) {
+        const int col0 = colbase + (ch_begin + k) * 16;
+        has_c[k] = k < nch && valid && col0 < n_valid;
+        has_r[k] = has_c[k] && res != nullptr && col0 < res_cols;
+        if (has_c[k]) {
+          const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(bnr_x) + aux_base + col0);
+          xq[k][0] = __ldg(xp);
+          xq[k][1] = __ldg(xp + 1);
+        }
+        if (has_r[k]) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + aux_base + col0);
+          rq[k][0] = __ldg(rp);
+          rq[k][1] = __ldg(rp + 1);
+        }
+      }
+      const bool okl = mbar_wait(bar_acc_full + 8 * as, (j >> 1) & 1, e.err, 3);
+      tc_fence_after();
+      uint32_t r0[16];
+      tmem_ld16(taddr + ch_begin * 16, r0);
+      tmem_ld_wait();
+      float dz[1][16], xr[1][16];
+      auto unpack16 = [](const uint4 (&q)[2], float (&z)[16]) {
+        unpack_bf16x2(q[0].x, z[0], z[1]);
+        unpack_bf16x2(q[0].y, z[2], z[3]);
+        unpack_bf16x2(q[0].z, z[4], z[5]);
+        unpack_bf16x2(q[0].w, z[6], z[7]);
+        unpack_bf16x2(q[1].x, z[8], z[9]);
+        unpack_bf16x2(q[1].y, z[10], z[11]);
+        unpack_bf16x2(q[1].z, z[12], z[13]);
+        unpack_bf16x2(q[1].w, z[14], z[15]);
+      };
+#pragma unroll
+      for (int k = 0; k < 1; ++k) {
+        if (k < nch) {
+          const int ch = ch_begin + k;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            dz[k][i] = (has_c[k] && okl) ? __uint_as_float(r0[i]) : 0.f;
+            xr[k][i] = 0.f;
+          }
+          if (has_r[k]) {
+            float z[16];
+            unpack16(rq[k], z);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dz[k][i] += z[i] * rs;
+          }
+          if (has_c[k]) unpack16(xq[k], xr[k]);
+          if (bnr_act != ACT_NONE) {
+            const float* sc = s_sc + grp * 256 + ch * 16;
+            const float* sh = s_sh + grp * 256 + ch * 16;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float z = xr[k][i] * sc[i] + sh[i];
+              if (z <= 0.f) {
+                dalpha += dz[k][i] * z;
+                dz[k][i] *= bnr_slope;
+              }
+            }
+          }
+          float sq[16], s1, s2;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sq[i] = dz[k][i] * xr[k][i];
+          float t16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t16[i] = dz[k][i];
+          butterfly16(t16, lane, s1);
+          butterfly16(sq, lane, s2);
+          if ((lane & 1) == 0) {
+            const int c = ch * 16 + butterfly_col(lane);
+            scratch[(q * 256 + c) * 2 + 0] = s1;
+            scratch[(q * 256 + c) * 2 + 1] = s2;
+          }
+          // without an activation dz is the incoming gradient itself, which a residual block's skip path still reads
+          if (bnr_act == ACT_NONE && has_c[k]) store_bf16x16(out, out_base + colbase + ch * 16, dz[k]);
+        }
+      }
+      if (dalpha_g != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dalpha += __shfl_xor_sync(0xffffffffu, dalpha, o);
+        if (lane == 0) scratch[4 * 256 * 2 + (warp - 2)] = dalpha;
+      }
+      named_bar_sync(1, kConvThreads - 64);
+      for (int idx = et; idx < p.block_n * 2; idx += kConvThreads - 64) {
+        const int c = idx >> 1, w = idx & 1;
+        float sum0 = 0.f, sum1 = 0.f;
+        bool any0 = false, any1 = false;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float pv = scratch[(qq * 256 + c) * 2 + w];
+          if (group_rows > 0 && s_qgrp[qq] != 0) {
+            sum1 += pv;
+            any1 = true;
+          } else {
+            sum0 += pv;
+            any0 = true;
+          }
+        }
+        if (any0) atomicAdd(stats_g + (colbase + c) * 2 + w, sum0);
+        if (any1) atomicAdd(stats_g + (static_cast<long long>(stats_ld) + colbase + c) * 2 + w, sum1);
+      }
+      if (dalpha_g != nullptr && et == 0) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += scratch[4 * 256 * 2 + w];
+        atomicAdd(dalpha_g, tot);
+      }
+      named_bar_sync(1, kConvThreads - 64);
+      if (threadIdx.x == 64) grid_arrive_and_wait(ctr, expected, e.err);
+      named_bar_sync(1, kConvThreads - 64);
+      float* cA = scratch;
+      float* cB = scratch + kMaxBnGroups * 256;
+      float* cC = scratch + 2 * kMaxBnGroups * 256;
+      if (col_thread) {
+        float dbeta = 0.f, dgamma = 0.f;
+        for (int g = 0; g < n_groups; ++g) {
+          float A = 0.f, Bx = 0.f, Cc = 0.f;
+          if (cv) {
+            const float* sp = stats_g + (static_cast<long long>(g) * stats_ld + cc) * 2;
+            const float s1 = __ldcg(sp);
+            const float s2 = is[g] * (__ldcg(sp + 1) - mu[g] * s1);
+            const float c2 = s1 * inv_m, c3 = s2 * inv_m;
+            A = gm * is[g];
+            Bx = -A * c3 * is[g];
+            Cc = -A * (c2 - mu[g] * is[g] * c3);
+            dbeta += s1;
+            dgamma += s2;
+          }
+          cA[g * 256 + et] = A;
+          cB[g * 256 + et] = Bx;
+          cC[g * 256 + et] = Cc;
+        }
+        if (publish && cv) {
+          if (e.bnr_dbeta != nullptr) e.bnr_dbeta[cc] = dbeta;
+          if (e.bnr_dgamma != nullptr) e.bnr_dgamma[cc] = dgamma;
+        }
+      }
+      if (publish && blockIdx.y == 0 && et == 0 && e.bnr_dalpha != nullptr && dalpha_g != nullptr)
+        *e.bnr_dalpha = __ldcg(dalpha_g);
+      named_bar_sync(1, kConvThreads - 64);
+#pragma unroll
+      for (int k = 0; k < 1; ++k) {
+        if (k < nch && has_c[k] && okl) {
+          const int ch = ch_begin + k;
+          const float* a = cA + grp * 256 + ch * 16;
+          const float* b = cB + grp * 256 + ch * 16;
+          const float* c = cC + grp * 256 + ch * 16;
+          float dx[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dx[i] = a[i] * dz[k][i] + b[i] * xr[k][i] + c[i];
+          store_bf16x16(dx_out, out_base + colbase + ch * 16, dx);
+        }
+      }
+      break;
+    }
     const bool ok = mbar_wait(bar_acc_full + 8 * as, (j >> 1) & 1, e.err, 3);
     tc_fence_after();
     if (trace && j == 0 && threadIdx.x == 64) trace[5] = clock64();
