@@ -1,5 +1,8 @@
-timeout 200 python tools/bench_programs.py 16 2>&1 | tail -5 | cut -c1-100
-timeout 900 python -m pytest tests -m gpu -q --timeout=600 -k "stage or oracle or golden or pair or residual or gan_step" 2>&1 | tail -3
-timeout 600 python bench.py --steps 30 --warmup 5 --only b64 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value', d['value'], 'ms', d['ms_per_step'], 'b64', d['b64']['value'], 'launches', d['launches_per_step'])"
+mkdir -p gpurun_out
+export TSR_GRAPHS=0
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/r02c_ncu_launches_infer.csv python tools/ncu_infer.py > gpurun_out/ncu_infer.log 2>&1; tail -1 gpurun_out/ncu_infer.log
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/r02c_ncu_launches_step_b64.csv python tools/ncu_step.py 64 > gpurun_out/ncu_b64.log 2>&1; tail -1 gpurun_out/ncu_b64.log
+unset TSR_GRAPHS
+TIMELINE=gpurun_out/timeline_b64_r2n.csv TOP=14 timeout 300 python tools/profile_step.py 64 2>&1 | tail -18 | cut -c1-170
