@@ -39,6 +39,7 @@ extern "C" {
 #define TSR_OUT_SHUFFLE 1
 #define TSR_OUT_UNSHUFFLE 2
 #define TSR_OUT_GEMM_T_ATOMIC 3
+#define TSR_OUT_GATHER_W 4      /* horizontal tap sum into fp32 NCHW with atomics, see gather_* below */
 /* activations */
 #define TSR_ACT_NONE 0
 #define TSR_ACT_PRELU 1
@@ -136,6 +137,13 @@ typedef struct tsr_conv_desc {
   float* bnr_dbeta;
   float* bnr_dalpha;
   int64_t bnr_count;
+  /* TSR_OUT_GATHER_W (the 9x9 Cout=3 output conv of both generators, srgan/generator.py:58, row-decomposed): accumulator
+     column kw*gather_c + c holds the partial product of horizontal tap kw for output channel c; the epilogue sums the
+     gather_k horizontally shifted columns inside its tile and adds them to out (fp32 NCHW [N][gather_c][Ho][Wo], zero
+     at launch):  out[n][c][h][w] += sum_kw acc[(n, h, w + kw - gather_pad)][kw*gather_c + c]  (+ gather_bias[c], once).
+     One N tile (block_n == cout_pad >= gather_k*gather_c), no split-K; the out strides are not used. */
+  const float* gather_bias;
+  int32_t gather_k, gather_pad, gather_c, _pad4;
 } tsr_conv_desc_t;
 
 typedef struct tsr_wgrad_desc {

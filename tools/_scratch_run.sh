@@ -1,8 +1,6 @@
 mkdir -p gpurun_out
-export TSR_GRAPHS=0
-timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-    --log-file gpurun_out/r02c_ncu_launches_infer.csv python tools/ncu_infer.py > gpurun_out/ncu_infer.log 2>&1; tail -1 gpurun_out/ncu_infer.log
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-    --log-file gpurun_out/r02c_ncu_launches_step_b64.csv python tools/ncu_step.py 64 > gpurun_out/ncu_b64.log 2>&1; tail -1 gpurun_out/ncu_b64.log
-unset TSR_GRAPHS
-TIMELINE=gpurun_out/timeline_b64_r2n.csv TOP=14 timeout 300 python tools/profile_step.py 64 2>&1 | tail -18 | cut -c1-170
+timeout 900 python -m pytest tests -m gpu -q --timeout=600 -x -k "generator or golden or eval_mode or c1_fixture or subpixel or residual_block or kernel" 2>&1 | tail -4
+echo "--- default"; TSR_CONV_VERBOSE=1 timeout 300 python tools/bench_infer.py 2> gpurun_out/verbose_infer.log | tail -2; sort gpurun_out/verbose_infer.log | uniq -c | sort -rn | head -12
+echo "--- HALO=0 (staged, im2col tiles)"; TSR_CONV_HALO=0 timeout 300 python tools/bench_infer.py 2>&1 | tail -1
+echo "--- STAGED=0"; TSR_CONV_STAGED=0 timeout 300 python tools/bench_infer.py 2>&1 | tail -1
+timeout 300 python tools/profile_infer.py > gpurun_out/profile_infer.log 2>&1; tail -48 gpurun_out/profile_infer.log | cut -c1-110

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtorchsr_b200.so")
 
 MAX_TAPS = 81
-OUT_LINEAR, OUT_SHUFFLE, OUT_UNSHUFFLE, OUT_GEMM_T_ATOMIC = 0, 1, 2, 3
+OUT_LINEAR, OUT_SHUFFLE, OUT_UNSHUFFLE, OUT_GEMM_T_ATOMIC, OUT_GATHER_W = 0, 1, 2, 3, 4
 ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_RELU = 0, 1, 2, 3
 
 (E_IM2ROW, E_GATHER_OUT, E_NCHW2NHWC, E_NHWC2NCHW, E_BN_FINALIZE, E_BN_EVAL_COEF, E_BN_ACT, E_BN_BWD_REDUCE,
@@ -54,6 +54,8 @@ class ConvDesc(C.Structure):
         ("bnr_apply", C.c_int32), ("_pad3", C.c_int32), ("bnr_dx", C.c_void_p),
         ("bnr_gamma", C.c_void_p), ("bnr_dgamma", C.c_void_p), ("bnr_dbeta", C.c_void_p), ("bnr_dalpha", C.c_void_p),
         ("bnr_count", C.c_int64),
+        ("gather_bias", C.c_void_p), ("gather_k", C.c_int32), ("gather_pad", C.c_int32), ("gather_c", C.c_int32),
+        ("_pad4", C.c_int32),
     ]
 
 

@@ -141,12 +141,19 @@ bool use_persistent() {
   return g_use_persistent == 1;
 }
 
-// Halo mode is correct (parity-tested) but off by default: with the main loop this cheap the large-M convs turn out to
-// be bound by their epilogue (tcgen05.ld + scattered 32-byte stores per tile), so it does not pay yet
-// (profiles/r01c_halo_mode.md). TSR_CONV_HALO=1 enables it; read at descriptor-build time so tests can switch it.
-bool use_halo() {
+// Halo mode (one patch per tile instead of nine im2col boxes: 1.4-1.75x instead of 9x re-read of the activations) only
+// pays once the epilogue is cheaper than the main loop, i.e. together with the staged epilogue (conv_params.h): by
+// default it is on exactly for the launches that get the staged epilogue. TSR_CONV_HALO=1 forces it for every eligible
+// conv, TSR_CONV_HALO=0 switches it off; TSR_CONV_STAGED=0 switches the staged epilogue off. Read at descriptor-build
+// time so tests can switch them.
+int halo_setting() {   // -1 default, 0 off, 1 forced
   const char* e = getenv("TSR_CONV_HALO");
-  return e && e[0] == '1' && use_persistent();
+  if (!e || !e[0]) return -1;
+  return e[0] == '1' ? 1 : 0;
+}
+bool use_staged() {
+  const char* e = getenv("TSR_CONV_STAGED");
+  return !(e && e[0] == '0') && use_persistent();
 }
 
 // persistent mode needs at least this many M tiles per CTA (x10); TSR_PERSIST_MIN_TILES_X10 overrides
@@ -218,6 +225,17 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
     const char* dbg = getenv("TSR_CONV_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  // Staged epilogue (conv_params.h): plain bf16 linear / PixelShuffle stores of 64-column tiles from a persistent FAST
+  // kernel. Decided here because its staging buffers come out of the shared-memory budget of the operand ring.
+  const bool out_lin = d.out_mode == TSR_OUT_LINEAR, out_shuf = d.out_mode == TSR_OUT_SHUFFLE;
+  const bool out_dense = d.os_h == d.Wo * d.os_w && d.os_n == d.Ho * d.os_h;
+  const bool want_staged =
+      use_staged() && allow_persistent && d.a_mode == 0 && d.block_k == 64 && d.block_n == 64 && d.splits <= 1 &&
+      (out_lin || (out_shuf && d.shuf_c == 64 && d.cout_pad == 256)) && !d.out_f32 && !d.out_preact && !d.bwd_z && !d.bnr_x &&
+      !d.stats_partial && !d.dalpha_partial && !d.res2 && d.bnf_mode != 1 && !d.bnr_apply && !d.trace && p.debug == 0 &&
+      d.group_rows == 0 && d.os_w % 8 == 0 && d.os_h % 8 == 0 && d.os_n % 8 == 0 && d.out_ch_off % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(d.out) % 16 == 0 && d.n_valid % 8 == 0;
+  const size_t smem_reserve = want_staged ? 2 * 16384 : 0;
   p.b_rows_per_tap = d.cout_pad;
   memcpy(p.tap_off, d.tap_off, sizeof(p.tap_off));
   memcpy(p.tap_wrow, d.tap_wrow, sizeof(p.tap_wrow));
@@ -247,7 +265,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
     const int n_ctas = L->tiles_n > 0 ? (148 / L->tiles_n > 0 ? 148 / L->tiles_n : 1) : 148;
     const uint32_t a_bytes = kBlockM * d.block_k * 2, b_bytes = static_cast<uint32_t>(d.block_n) * d.block_k * 2;
     const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
-    const size_t budget = 227 * 1024 - 1024 - kConvHeaderBytes - 1024;
+    const size_t budget = 227 * 1024 - 1024 - kConvHeaderBytes - 1024 - smem_reserve;
     if (use_persistent() && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && allow_persistent &&
         b_res % 1024 == 0 && a_bytes % 1024 == 0 && b_res + 3 * static_cast<size_t>(a_bytes) <= budget &&
         10 * tiles_m >= persistent_min_tiles_x10() * n_ctas && 2 * p.acc_cols <= 512) {
@@ -262,7 +280,8 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   }
   // Halo mode on top of the persistent kernel (see conv_params.h): 3x3 / stride 1 / "same" convs on 64-channel chunks.
   p.halo = 0;
-  if (use_halo() && allow_persistent && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC &&
+  const int halo_env = halo_setting();
+  if ((halo_env == 1 || (halo_env < 0 && want_staged)) && use_persistent() && allow_persistent && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC &&
       d.stride == 1 && d.num_taps == 9 && d.lower_h == -1 && d.lower_w == -1 && d.Ho == d.H && d.Wo == d.W &&
       d.block_k == 64 && (d.C - d.a_c0) % 64 == 0 && d.W >= 8 && d.H >= 4 && 2 * p.acc_cols <= 512) {
     bool taps_ok = true;
@@ -295,7 +314,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
     const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
     const uint32_t patch_tx = static_cast<uint32_t>((th + 2) * pw * 128);
     const uint32_t patch_alloc = (static_cast<uint32_t>((128 + 2 * pw + 2) * 128) + 1023u) & ~1023u;
-    const size_t budget = 227 * 1024 - 1024 - kConvHeaderBytes - 1024;
+    const size_t budget = 227 * 1024 - 1024 - kConvHeaderBytes - 1024 - smem_reserve;
     if (taps_ok && th >= 1 && b_res % 1024 == 0 && b_res + 2 * static_cast<size_t>(patch_alloc) <= budget) {
       const int tiles_per_img = strips * tiles_y;
       const int tiles = tiles_per_img * static_cast<int>(d.N);
@@ -420,6 +439,50 @@ epilogue_params:
   e.bnr_dbeta = d.bnr_dbeta;
   e.bnr_dalpha = d.bnr_dalpha;
   e.bnr_count = d.bnr_count;
+  e.gather_bias = d.gather_bias;
+  e.gather_k = d.gather_k;
+  e.gather_pad = d.gather_pad;
+  e.gather_c = d.gather_c;
+  p.staged = 0;
+  p.extra_bytes = 0;
+  if (d.out_mode == TSR_OUT_GATHER_W) {
+    if (d.a_mode != 0 || splits != 1 || L->tiles_n != 1 || !d.out_f32 || d.gather_k < 1 || d.gather_c < 1 ||
+        d.gather_k * d.gather_c > d.block_n || d.gather_pad < 0 || d.gather_pad >= d.gather_k || d.out_preact || d.bias ||
+        d.res || d.bwd_z || d.bnr_x || d.stats_partial || d.bnf_mode || p.halo)
+      return fail(-20, "OUT_GATHER_W needs an unsplit im2col conv with one N tile, an fp32 NCHW output and a plain epilogue");
+    if (d.gather_k != 9 || d.gather_c != 3 || d.gather_pad != 4 || d.block_n != 32)
+      return fail(-20, "OUT_GATHER_W is implemented for the 9-tap, 3-channel, 32-column case (conv_igemm.cu:gather9x3)");
+  }
+  if (want_staged && p.persistent && (p.halo || (out_lin && out_dense))) {
+    // output map(s): the staging buffer is one {64 channels x 128 pixels} (im2col tiles) or {64 x (pw-2) x th} (halo
+    // tiles) box in the 128B swizzle; columns >= n_valid and pixels outside the tensor are clipped by the TMA unit
+    const char* obase = reinterpret_cast<const char*>(d.out) + static_cast<int64_t>(d.out_ch_off) * 2;
+    if (!p.halo) {
+      if (int e2 = encode_2d(&p.tmO[0], obase, p.M_total, d.n_valid, d.os_w, 64, kBlockM)) return e2;
+    } else {
+      const int n_maps = out_shuf ? 4 : 1;
+      for (int b = 0; b < n_maps; ++b) {
+        const int64_t mul = out_shuf ? 2 : 1;
+        const char* base = obase + ((b >> 1) * d.os_h + (b & 1) * d.os_w) * 2 * (out_shuf ? 1 : 0);
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(out_shuf ? 64 : d.n_valid), static_cast<cuuint64_t>(d.W),
+                              static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.N)};
+        cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.os_w * mul) * 2, static_cast<cuuint64_t>(d.os_h * mul) * 2,
+                                 static_cast<cuuint64_t>(d.os_n) * 2};
+        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.halo_pw - 2), static_cast<cuuint32_t>(p.halo_th), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_encode_tiled(&p.tmO[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides,
+                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(-12, "cuTensorMapEncodeTiled (staged output) failed (%d)", (int)r);
+      }
+    }
+    p.staged = 1;
+    p.extra_bytes = 2 * 16384;
+  }
+  if (const char* v = getenv("TSR_CONV_VERBOSE"); v && v[0] == '1' && d.a_mode == 0)
+    fprintf(stderr, "[tsr] conv M=%d C=%lld taps=%d block_n=%d tiles_n=%d persistent=%d halo=%d (th=%d pw=%d) staged=%d stages=%d "
+            "stage_bytes=%u b_res=%u extra=%u out_mode=%d\n", p.M_total, (long long)d.C, p.num_taps, d.block_n, L->tiles_n,
+            p.persistent, p.halo, p.halo_th, p.halo_pw, p.staged, p.stages, p.stage_bytes, p.b_res_bytes, p.extra_bytes, d.out_mode);
   if (e.bnr_apply && (!e.bnr_x || !e.bnr_dx || !e.bnr_coef || !e.bnr_gamma || !e.bnf_counter || e.bnr_count < 1 || splits != 1 ||
                       p.persistent || d.out_f32 || d.out_mode != TSR_OUT_LINEAR || e.bnf_mode))
     return fail(-20, "fused BatchNorm-backward apply needs bnr_x, bnr_coef, bnr_gamma, bnf_counter, bnr_count, a linear "

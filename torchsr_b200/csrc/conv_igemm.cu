@@ -100,6 +100,62 @@ __device__ __forceinline__ void store_f32x16(void* base, long long off, const fl
   for (int i = 0; i < 4; ++i) p[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// OUT_GATHER_W for the generators' 9x9 Cout=3 output conv (EpiParams::gather_*), one 16-column chunk of a warp's 32
+// accumulator rows (= 32 consecutive pixels, lane = pixel): column col = kw*3 + c is horizontal tap kw of channel c, and
+//   out[pixel][c] = sum_kw acc[pixel + kw - 4][kw*3 + c].
+// Lane L collects the taps that the warp's own rows hold for its pixel with one shuffle per column; lanes 0..7 then do
+// the same for the 4 + 4 pixels just outside the warp's range (their remaining taps come from the neighbouring warp /
+// tile, which adds them the same way). Every partial sum goes to the zero-initialised fp32 NCHW output with one atomic
+// per channel: no shared memory, no barrier, and the 64-byte fp32 rows never travel to HBM.
+template <int CH>
+__device__ __forceinline__ void gather9x3(const float (&v)[16], int lane, bool valid, int wo, long long own, int m_first,
+                                          int M_total, int Ho, int Wo, float* __restrict__ out,
+                                          const float* __restrict__ bias) {
+  constexpr int K = 9, GC = 3, PAD = 4;
+  const long long cs = static_cast<long long>(Ho) * Wo;
+  // pixels outside the warp's rows: lanes 0..3 -> m_first - 4 .. - 1, lanes 4..7 -> m_first + 32 .. + 35
+  const int P = lane < 4 ? lane - 4 : 28 + lane;
+  const long long mo = static_cast<long long>(m_first) + P;
+  const bool ext = lane < 8 && mo >= 0 && mo < M_total;
+  int rowid = 0, wcol = 0;
+  if (ext) {
+    rowid = static_cast<int>(mo / Wo);
+    wcol = static_cast<int>(mo - static_cast<long long>(rowid) * Wo);
+  }
+  float a0[GC] = {0.f, 0.f, 0.f}, a1[GC] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int col = CH * 16 + i;
+    if (col < K * GC) {
+      const int kw = col / GC, c = col % GC;
+      const int src0 = lane + kw - PAD;
+      const float t0 = __shfl_sync(0xffffffffu, v[i], src0 & 31);
+      const int ws0 = wo + kw - PAD;
+      if (src0 >= 0 && src0 < 32 && ws0 >= 0 && ws0 < Wo) a0[c] += t0;
+      const int src1 = P + kw - PAD;
+      const float t1 = __shfl_sync(0xffffffffu, v[i], src1 & 31);
+      const int ws1 = wcol + kw - PAD;
+      if (ext && src1 >= 0 && src1 < 32 && ws1 >= 0 && ws1 < Wo) a1[c] += t1;
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      atomicAdd(out + own + c * cs, a0[c] + ((CH == 0 && bias != nullptr) ? __ldg(bias + c) : 0.f));
+    }
+  }
+  if (ext) {
+    const int nn = rowid / Ho, hh = rowid - nn * Ho;
+    const long long o = ((static_cast<long long>(nn) * GC) * Ho + hh) * Wo + wcol;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) atomicAdd(out + o + c * cs, a1[c]);
+  }
+}
+
 // Grid-wide arrival barrier for the fused BatchNorm epilogues: `counter` is zero at launch, every CTA of the barrier's
 // scope arrives once. Called by ONE thread after a CTA-level barrier; the fence makes the CTA's earlier global
 // reductions (performed by other threads, ordered by that barrier) visible before the arrival, as cooperative-groups
@@ -685,8 +741,133 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       named_bar_sync(1, kConvThreads - 64);
     }
     if (bnf == 2) bnf_coefficients(false);
+    // shared memory behind the operand ring: staging buffers of the staged epilogue / the OUT_GATHER_W tile
+    const uint32_t extra = ring + static_cast<uint32_t>(p.stages) * p.stage_bytes;
+    bool staged_done = false;
+    if constexpr (PERS && FAST) {
+      if (p.staged) {
+        // ---- staged epilogue (conv_params.h): 64-column N tile, this warp owns 32 rows x 32 columns of it. One
+        // tcgen05.ld + one wait per tile, the TMEM stage goes back to the MMA warp before any arithmetic, the bf16 tile
+        // leaves through a 128B-swizzled staging buffer and ONE bulk tensor store per tile.
+        staged_done = true;
+        const int sw = p.halo ? p.halo_pw - 2 : 0;
+        const bool has_bias = bias != nullptr;
+        const float rs = e.res_scale;
+        const float sl = act == ACT_PRELU ? alpha : (act == ACT_LEAKY ? leaky : 0.f);
+        const int c_lo = half * 32;
+        const long long aux_n = e.aux_n, aux_h = e.aux_h, aux_w = e.aux_w;
+        const int aux_c = e.aux_ch_off + colbase + c_lo;
+        const bool res_cols_ok = res != nullptr && colbase + c_lo < e.res_cols;
+        const int row = q * 32 + lane;
+        const bool shuf = out_mode == OUT_SHUFFLE;
+        int jj = 0;
+        for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++jj) {
+          const int as = jj & 1;
+          int n, ho, wo, crow = row, w0 = 0, h0 = 0;
+          bool valid;
+          if (p.halo) {
+            n = tile_m / p.halo_tiles_per_img;
+            const int t_img = tile_m - n * p.halo_tiles_per_img;
+            const int t_y = t_img / p.halo_strips;
+            const int orow = row / p.halo_pw;
+            const int pos = row - orow * p.halo_pw;
+            w0 = (t_img - t_y * p.halo_strips) * sw;
+            h0 = t_y * p.halo_th;
+            wo = w0 + pos;
+            ho = h0 + orow;
+            valid = pos < sw && wo < p.halo_W && orow < p.halo_th && ho < p.halo_H;
+            crow = orow * sw + pos;       // the two discarded positions of every patch row are squeezed out
+          } else {
+            const int m = tile_m * kBlockM + row;
+            valid = m < p.M_total;
+            const int hw = p.Ho * p.Wo;
+            n = m / hw;
+            const int rem = m - n * hw;
+            ho = rem / p.Wo;
+            wo = rem - ho * p.Wo;
+          }
+          // the residual row does not depend on the accumulator: fetch it before waiting for the main loop
+          uint4 rq[4];
+          const bool has_res = res_cols_ok && valid;
+          if (has_res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + n * aux_n +
+                                                             ho * aux_h + wo * aux_w + aux_c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rq[k] = __ldg(rp + k);
+          }
+          mbar_wait(bar_acc_full + 8 * as, (jj >> 1) & 1, e.err, 3);
+          tc_fence_after();
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as) * p.acc_cols + c_lo, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);   // the MMA warp may start tile j+2 now
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
+            float z0 = 0.f, z1 = 0.f;
+            if (has_res) {
+              const uint4 qq = rq[i >> 3];
+              const uint32_t w = ((i >> 1) & 3) == 0 ? qq.x : (((i >> 1) & 3) == 1 ? qq.y : (((i >> 1) & 3) == 2 ? qq.z : qq.w));
+              unpack_bf16x2(w, z0, z1);
+            }
+            if (bnf == 2) {        // y = act(BN(acc)) + res
+              x0 = x0 * s_sc[c_lo + i] + s_sh[c_lo + i];
+              x1 = x1 * s_sc[c_lo + i + 1] + s_sh[c_lo + i + 1];
+              if (act == ACT_RELU) {
+                x0 = fmaxf(x0, 0.f);
+                x1 = fmaxf(x1, 0.f);
+              } else if (act != ACT_NONE) {
+                x0 = x0 > 0.f ? x0 : x0 * sl;
+                x1 = x1 > 0.f ? x1 : x1 * sl;
+              }
+              x0 += z0 * rs;
+              x1 += z1 * rs;
+            } else {               // y = act((acc + bias) * acc_scale + res)
+              if (has_bias) {
+                x0 += s_bias[c_lo + i];
+                x1 += s_bias[c_lo + i + 1];
+              }
+              x0 = x0 * acc_scale + z0 * rs;
+              x1 = x1 * acc_scale + z1 * rs;
+              if (act == ACT_RELU) {
+                x0 = fmaxf(x0, 0.f);
+                x1 = fmaxf(x1, 0.f);
+              } else if (act != ACT_NONE) {
+                x0 = x0 > 0.f ? x0 : x0 * sl;
+                x1 = x1 > 0.f ? x1 : x1 * sl;
+              }
+            }
+            pk[i >> 1] = pack_bf16x2(x0, x1);
+          }
+          const uint32_t sbuf = extra + static_cast<uint32_t>(jj & 1) * 16384u;
+          if (valid) {
+            const uint32_t rowaddr = sbuf + static_cast<uint32_t>(crow) * 128u;
+            const uint32_t sx = static_cast<uint32_t>(crow) & 7u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              sts128(rowaddr + (((static_cast<uint32_t>(half) * 4u + k) ^ sx) << 4), pk[4 * k], pk[4 * k + 1], pk[4 * k + 2],
+                     pk[4 * k + 3]);
+          }
+          fence_proxy_async_smem();
+          // the store of tile j-1 (other buffer) must have left shared memory before any warp starts tile j+1
+          if (threadIdx.x == 64) bulk_wait_group_read0();
+          named_bar_sync(1, kConvThreads - 64);
+          if (threadIdx.x == 64) {
+            if (p.halo)
+              tma_store_4d(&p.tmO[shuf ? tile_n : 0], sbuf, shuf ? 0 : colbase, w0, h0, n);
+            else
+              tma_store_2d(&p.tmO[0], sbuf, colbase, tile_m * kBlockM);
+            bulk_commit_group();
+          }
+        }
+        if (threadIdx.x == 64) bulk_wait_group0();
+      }
+    }
     int j = 0;
-    for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++j) {
+    for (int tile_m = blockIdx.x; !staged_done && tile_m < tiles_m; tile_m += gridDim.x, ++j) {
     const int m0 = tile_m * kBlockM;
     const int as = j & 1;          // accumulator stage of this tile
     const int row = q * 32 + lane;
@@ -1193,6 +1374,18 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           }
         }
         if (trace && threadIdx.x == 64 && ch < 4) trace[32 + 2 * ch] = clock64();
+        if (out_mode == OUT_GATHER_W) {
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          }
+          const long long own = ((static_cast<long long>(n) * 3) * p.Ho + ho) * p.Wo + wo;
+          if (ch == 0)
+            gather9x3<0>(v, lane, valid, wo, own, m0 + q * 32, p.M_total, p.Ho, p.Wo, reinterpret_cast<float*>(out), e.gather_bias);
+          else
+            gather9x3<1>(v, lane, valid, wo, own, m0 + q * 32, p.M_total, p.Ho, p.Wo, reinterpret_cast<float*>(out), e.gather_bias);
+          continue;
+        }
         const bool st = valid && col0 < n_valid && (FAST || !(p.debug & 2));
         if (bnf == 2) {             // eval-mode BatchNorm folded into this pass: coefficients are known up front
           if (st) bn_apply_store(v, ch, col0);
@@ -1502,7 +1695,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_igemm_group_kernel(const
 }
 
 size_t conv_igemm_smem_bytes(const ConvParams& p) {
-  return 1024 + kHeaderBytes + p.b_res_bytes + static_cast<size_t>(p.stages) * p.stage_bytes;
+  return 1024 + kHeaderBytes + p.b_res_bytes + static_cast<size_t>(p.stages) * p.stage_bytes + p.extra_bytes;
 }
 
 // CTAs of this conv's kernel instantiation that the device can hold at once (occupancy x SM count): the fused

@@ -16,7 +16,8 @@ enum OutMode : int {
   OUT_LINEAR = 0,     // off = n*os_n + ho*os_h + wo*os_w + col
   OUT_SHUFFLE = 1,    // PixelShuffle(2) store: column block (i,j) of 64 -> pixel (2ho+i, 2wo+j)
   OUT_UNSHUFFLE = 2,  // inverse: fine pixel (ho,wo) -> coarse pixel (ho/2,wo/2), column block ((ho&1)*2+(wo&1))
-  OUT_GEMM_T_ATOMIC = 3  // split-K GEMM: atomicAdd(out[col*ld + row], v) in fp32
+  OUT_GEMM_T_ATOMIC = 3, // split-K GEMM: atomicAdd(out[col*ld + row], v) in fp32
+  OUT_GATHER_W = 4       // horizontal K-tap sum of the accumulator columns into fp32 NCHW (see EpiParams::gather_*)
 };
 enum Act : int { ACT_NONE = 0, ACT_PRELU = 1, ACT_LEAKY = 2, ACT_RELU = 3 };
 
@@ -101,11 +102,20 @@ struct EpiParams {
   float* bnr_dbeta;          // [bnr_c] or null
   float* bnr_dalpha;         // scalar out (= *dalpha_partial) or null
   long long bnr_count;       // rows per statistics group
+  // OUT_GATHER_W (row-decomposed K x K conv with a handful of output channels, e.g. the generators' 9x9 64->3 output
+  // conv): accumulator column kw*gather_c + c is the partial product of horizontal tap kw for channel c. The tile goes
+  // through shared memory (fp32, odd row stride), each output position of the tile's span sums its gather_k shifted
+  // columns and adds the result to out[n][c][h][w] (fp32 NCHW, zero at launch) with one atomic: positions whose taps
+  // straddle two tiles receive two adds (commutative, so the result does not depend on the order); the tile that owns
+  // the position adds the bias. Replaces a [M][block_n] fp32 round trip through HBM plus a gather kernel.
+  const float* gather_bias;
+  int gather_k, gather_pad, gather_c;
 };
 
 struct ConvParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmO[4];   // staged epilogue: output map(s), one per PixelShuffle sub-pixel block (linear stores use [0])
   EpiParams epi;
   int M_total;     // rows of the implicit GEMM (N*Ho*Wo traversal positions)
   int Ho, Wo;      // traversal grid (per image)
@@ -139,6 +149,13 @@ struct ConvParams {
   int halo_tiles_per_img;
   int halo_H, halo_W;    // image size (output == input size)
   int halo_strips;       // strips per image row: ceil(W / (halo_pw - 2))
+  // Staged epilogue (persistent FAST kernels, bf16 linear / PixelShuffle stores, 64-column N tiles): every epilogue warp
+  // reads its whole share of the accumulator with one tcgen05.ld + wait, hands the TMEM stage back at once, and writes
+  // the finished bf16 tile into a 128B-swizzled shared-memory buffer (double-buffered); one thread stores it with
+  // cp.async.bulk.tensor (tmO) - full 128-byte lines instead of 32 half-sector stores per warp instruction. Halo tiles
+  // are compacted (the two discarded positions per patch row are skipped), so the box is th x (pw-2) pixels.
+  int staged;
+  uint32_t extra_bytes;  // shared memory behind the operand ring: staging buffers (staged) or the OUT_GATHER_W tile
   int w_static;    // the B operand is not written by any kernel of the enclosing stream segment (real weights)
   int debug;       // attribution experiments only (TSR_CONV_DEBUG bits, tools/trace_conv.py), 0 in production: 1 = the
                    // epilogue skips the accumulator read-out and the stores, 2 = it computes but does not store,

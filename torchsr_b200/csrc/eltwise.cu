@@ -107,6 +107,65 @@ __global__ void __launch_bounds__(256) im2row_ct_kernel(const float* __restrict_
   }
 }
 
+// Shared-memory tiled variant for large images (x4 inference: the 512x512 input of the 9x9 layer expands to 134 MB of
+// rows): a block stages the (TH+KH-1) x (TW+KW-1) x C input patch of a TH x TW pixel tile once, then every thread
+// assembles 16-byte row pieces from shared memory - the row writes are the only HBM traffic left (the per-element
+// __ldg gathers of the kernel above ran at a fifth of the write bandwidth).
+template <int KH, int KW, int C>
+__global__ void __launch_bounds__(256) im2row_tiled_kernel(const float* __restrict__ x, bf16* __restrict__ E, int B, int H,
+                                                           int W, int ph, int pw, int sign, int Epad) {
+  constexpr int TH = 4, TW = 32, PH = TH + KH - 1, PW = TW + KW - 1;
+  __shared__ float patch[C][PH][PW + 1];
+  pdl_sync();
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+  const long long n_tiles = static_cast<long long>(B) * tiles_h * tiles_w;
+  const int lo_h = sign > 0 ? -ph : -(KH - 1 - ph), lo_w = sign > 0 ? -pw : -(KW - 1 - pw);
+  const int groups = Epad / 8;     // <= 64: a lane owns column group `lane` and, for wide rows, `lane + 32`
+  const long long hw = static_cast<long long>(H) * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int off[8], off2[8];             // patch offsets of the lane's columns relative to the pixel's patch origin, -1 = padding
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    for (int k = 0; k < 2; ++k) {
+      const int col = (lane + 32 * k) * 8 + j;
+      int o = -1;
+      if (col < KH * KW * C) {
+        const int c = col % C, tt = col / C;
+        const int kw = tt % KW, kh = tt / KW;
+        o = (c * PH + sign * (kh - ph) - lo_h) * (PW + 1) + sign * (kw - pw) - lo_w;
+      }
+      if (k == 0) off[j] = o; else off2[j] = o;
+    }
+  }
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tw = static_cast<int>(t % tiles_w);
+    const int th = static_cast<int>((t / tiles_w) % tiles_h);
+    const long long n = t / (static_cast<long long>(tiles_w) * tiles_h);
+    const int h0 = th * TH, w0 = tw * TW;
+    __syncthreads();   // readers of the previous tile
+    for (int i = threadIdx.x; i < C * PH * PW; i += 256) {
+      const int pwi = i % PW, phi = (i / PW) % PH, c = i / (PW * PH);
+      const int hh = h0 + lo_h + phi, ww = w0 + lo_w + pwi;
+      patch[c][phi][pwi] =
+          (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(x + (n * C + c) * hw + static_cast<long long>(hh) * W + ww) : 0.f;
+    }
+    __syncthreads();
+    // lane = column group (loop invariant: the eight (channel, tap) sources of its columns), warp = pixel slot
+    for (int pl = warp; pl < TH * TW; pl += 8) {
+      const int wl = pl % TW, hl = pl / TW;
+      const int h = h0 + hl, w = w0 + wl;
+      if (h >= H || w >= W) continue;
+      const float* base = &patch[0][hl][wl];
+      for (int g = lane; g < groups; g += 32) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (g == lane ? off[j] : off2[j]) >= 0 ? base[g == lane ? off[j] : off2[j]] : 0.f;
+        st8(E + ((n * H + h) * W + w) * Epad + g * 8, v);
+      }
+    }
+  }
+}
+
 // Fast path for the 3-channel 3x3 first layers of the discriminators and VGG: one thread per pixel gathers its 27 taps
 // once and writes the whole 64-byte row; the generic kernel above spends most of its time on per-element index
 // arithmetic.
@@ -1499,6 +1558,12 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
       if (i[9] == 32 && i[1] == 3 && i[4] == 1 && i[5] == 9) {      // row expansion of dOut for the 9x9 Cout=3 conv
         ce = launch_k(im2row_small_kernel<1, 9, 3>, dim3(grid_for(i[0] * i[2] * i[3])), dim3(256), 0, st, pdl,
                       (const float*)p[0], (bf16*)p[1], i[0], i[2], i[3], i[6], i[7], i[8]);
+        break;
+      }
+      if (i[1] == 3 && i[4] == 9 && i[5] == 9 && i[0] * i[2] * i[3] >= 65536 && i[9] <= 512) {   // the same layer on large images
+        const long long n_tiles = i[0] * ((i[2] + 3) / 4) * ((i[3] + 31) / 32);
+        ce = launch_k(im2row_tiled_kernel<9, 9, 3>, dim3(static_cast<unsigned>(n_tiles < 148 * 16 ? n_tiles : 148 * 16)), dim3(256),
+                      0, st, pdl, (const float*)p[0], (bf16*)p[1], i[0], i[2], i[3], i[6], i[7], i[8], i[9]);
         break;
       }
       if (i[1] == 3 && i[4] == 9 && i[5] == 9) {                      // 9x9 3-channel input layer of the SRGAN generator

@@ -34,6 +34,8 @@ SPLIT_K_MIN_ITERS = int(os.environ.get("TSR_SPLITK_MIN_ITERS", "0"))
 # (only for grids the device holds at once), eval mode folds the running statistics into the epilogue. "0" keeps the
 # two-launch path (conv with column sums, then bn_act_kernel) everywhere - both stay parity-tested.
 FUSE_BN_FWD = os.environ.get("TSR_BN_FUSE", "1") != "0"
+# 64-column N tiles for the convs the staged epilogue serves (see Plan.conv_fwd); TSR_CONV_STAGED=0 also disables it in C
+STAGED_N64 = os.environ.get("TSR_CONV_STAGED", "1") != "0" and os.environ.get("TSR_CONV_PERSISTENT", "1") != "0"
 # the same for backward: dx = A*dz + B*x + C formed in the epilogue of the data-gradient conv that produced dz (after a
 # grid barrier on the column sums) instead of a bn_bwd_apply_kernel launch; "0" keeps the separate launch
 FUSE_BN_BWD = os.environ.get("TSR_BN_BWD_FUSE", "1") != "0"
@@ -308,8 +310,12 @@ class Plan:
     """One instance = the workspaces + recorded programs of one module call at one input shape and mode.
     A net definition fills it through the emit_* helpers; backward is emitted by replaying the tape in reverse."""
 
-    def __init__(self, store: ParamStore, B: int, H: int, W: int, training: bool, groups: int = 1):
+    def __init__(self, store: ParamStore, B: int, H: int, W: int, training: bool, groups: int = 1,
+                 infer_only: bool = False):
         self.store, self.B, self.H, self.W, self.training = store, B, H, W, training
+        # eval-mode call that autograd will never walk back through (no_grad / nothing requires grad): the stages skip
+        # the pre-activation copies they would keep for backward (x4 inference: 0.7 GB of stores per 2048x2048 image)
+        self.infer_only = infer_only and not training
         # BatchNorm statistics groups: 2 = the batch is (real | fake), each half normalised with its own batch
         # statistics as two separate calls of the module would (B200Module.forward_pair); only matters in training mode
         self.groups = groups if training else 1
@@ -399,6 +405,16 @@ class Plan:
         tiles = self.pick_tiles(x.B * geom["Ho"] * geom["Wo"], rec.cout_pad, rec.block_n,
                                 len(geom["taps"]) * ((x.C) // ops.pick_block_k(x.C)))
         block_n = tiles.pop("block_n")
+        # 3x3 / stride-1 convs on 64 input channels with a plain bf16 store and many M tiles per SM run the persistent
+        # halo kernel with the staged (TMA-store) epilogue, which is built for 64-column N tiles (csrc/conv_params.h):
+        # the activations are then re-read once per N tile, but from a patch that is fetched ~1.5x instead of 9x
+        if (STAGED_N64 and rec.k == 3 and rec.stride == 1 and rec.pad == 1 and x.C == 64 and block_n > 64
+                and rec.cout_pad % 64 == 0 and "splits" not in tiles and stats is None and preact is None and res2 is None
+                and not out_f32 and (bnf is None or bnf.get("bnf_mode") == 2)
+                and (not shuffle_out or (rec.cout == 256 and rec.cout_pad == 256))):
+            tiles_m = (x.B * geom["Ho"] * geom["Wo"] + 127) // 128
+            if tiles_m >= 2 * max(1, NUM_SMS // (rec.cout_pad // 64)):
+                block_n = 64
         if not dry_add:     # descriptor only (the caller decides whether this variant is launched)
             return ops.conv_desc(x=ops.ptr(x.t, x.c0) if x.c0 else x.t, N=x.B, H=x.H, W=x.W, C=x.C, x_ld=x.ld, geom=geom,
                                  w=rec.w_fwd, cout_pad=rec.cout_pad, w_ld=rec.cols, n_slots=rec.slots, block_n=block_n,
@@ -979,15 +995,18 @@ class B200Module(nn.Module):
             st["plans"] = {}
         return st["store"]
 
-    def _acquire(self, shape, training: bool, groups: int = 1) -> Plan:
+    def _acquire(self, shape, training: bool, groups: int = 1, infer_only: bool = False) -> Plan:
         store = self._store()
+        infer_only = bool(infer_only) and not training and groups == 1
         key = (tuple(shape), bool(training)) if groups == 1 else (tuple(shape), bool(training), groups)
+        if infer_only:
+            key = key + ("infer",)
         pool = self._tsr["plans"].setdefault(key, [])
         for pl in pool:
             if not pl.busy:
                 pl.busy = True
                 return pl
-        pl = Plan(store, shape[0], shape[2], shape[3], training, groups)
+        pl = Plan(store, shape[0], shape[2], shape[3], training, groups, infer_only)
         try:
             self._define(pl, shape)
         except GroupSplitError:
@@ -1052,7 +1071,7 @@ class B200Module(nn.Module):
 class _PlanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module: B200Module, needs_graph: bool, x: torch.Tensor, *params):
-        plan = module._acquire(x.shape, module.training)
+        plan = module._acquire(x.shape, module.training, infer_only=not needs_graph)
         store = plan.store
         store.ensure_packed()
         if module.training and module._tsr.get("ddp") is not None:

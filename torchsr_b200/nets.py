@@ -67,10 +67,11 @@ def subpixel_stage(plan: Plan, prog, name: str, layer, rec: ConvRec, x: Act, con
     B, H, W, C = x.B, x.H, x.W, rec.cout // 4
     store = plan.grads
     out = plan.act(name + ".out", B, 2 * H, 2 * W, C)
-    pre = plan.act(name + ".pre", B, 2 * H, 2 * W, C)
+    pre = out if plan.infer_only else plan.act(name + ".pre", B, 2 * H, 2 * W, C)
     alpha = layer.prelu.weight
-    plan.conv_fwd(prog, rec, x, out, act=L.ACT_PRELU, prelu=alpha, preact=pre.t, shuffle_out=True)
-    dconv = plan.act(name + ".dconv", B, H, W, rec.cout)
+    plan.conv_fwd(prog, rec, x, out, act=L.ACT_PRELU, prelu=alpha, preact=None if plan.infer_only else pre.t,
+                  shuffle_out=True)
+    dconv = None if plan.infer_only else plan.act(name + ".dconv", B, H, W, rec.cout)
     dap = plan.zbuf("bwd", name + ".dalpha", 1)     # accumulated by the consumer's dgrad epilogue (one red per CTA)
     out.hook = dict(bwd_z=pre, bwd_act=L.ACT_PRELU, prelu=alpha, unshuffle_to=dconv, dalpha_partial=dap)
 
@@ -96,10 +97,10 @@ def define_srgan_generator(m, plan: Plan, shape):
     alpha1 = m.conv1[1].weight
     E1 = plan.act("E1", B, H, W, r1.epad)
     c1 = plan.act("c1", B, H, W, 64)
-    c1_pre = plan.act("c1.pre", B, H, W, 64)
+    c1_pre = c1 if plan.infer_only else plan.act("c1.pre", B, H, W, 64)
     g1 = _geom1(H, W)
     plan.conv(fwd, E1, r1.w_fwd, r1.cols, 1, g1, r1.cout_pad, r1.block_n, c1.t, c1.strides(), r1.cout_pad, bias=r1.bias,
-              act=L.ACT_PRELU, prelu=alpha1, out_preact=c1_pre.t)
+              act=L.ACT_PRELU, prelu=alpha1, out_preact=None if plan.infer_only else c1_pre.t)
 
     def bwd_conv1(bp, g, want_x, want_w):
         if want_w:
@@ -134,10 +135,16 @@ def define_srgan_generator(m, plan: Plan, shape):
 
     r3 = R["conv3"]
     Hf, Wf = u.H, u.W
-    T = plan.act("T", B, Hf, Wf, r3.npad, F32)
+    # 9x9 64->3 output conv (srgan/generator.py:58), row-decomposed: the GEMM runs over the 9 vertical taps with
+    # N' = 9 horizontal taps x 3 channels (27 -> 32 columns); its epilogue sums the horizontally shifted columns inside
+    # the tile and adds them (+ bias) into the zero-initialised fp32 NCHW result (OUT_GATHER_W) - no [M][32] fp32 round
+    # trip through HBM, no gather kernel.
+    Y = plan.buf("Y", B * r3.cout * Hf * Wf, F32)
+    fwd.add(ops.elt(L.E_ZERO, p=[Y], i=[Y.numel() * 4]))
     geom3 = ops.fwd_geometry(Hf, Wf, r3.k, 1, r3.pad, 0, 1)
-    plan.conv(fwd, u, r3.w_fwd, r3.cols, r3.k, geom3, r3.npad, r3.npad, T.t, T.strides(), r3.npad, out_f32=True)
-    E3 = plan.act("E3", B, Hf, Wf, r3.npad)
+    plan.conv(fwd, u, r3.w_fwd, r3.cols, r3.k, geom3, r3.npad, r3.npad, Y, (0, 0, 0), r3.npad,
+              gather=dict(k=r3.k, pad=r3.pad, c=r3.cout, bias=r3.bias))
+    E3 = None if plan.infer_only else plan.act("E3", B, Hf, Wf, r3.npad)
     cs = plan.buf("conv3.cs", CHANSUM_SPLITS * r3.cout * 2, F32)
     u_last = u
 
@@ -145,8 +152,9 @@ def define_srgan_generator(m, plan: Plan, shape):
         ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E1.t], i=[B, 3, H, W, r1.k, r1.k, r1.pad, r1.pad, 1, r1.epad]))
 
     def output_fn():
+        # a fresh tensor per call (the plan's buffer is overwritten by the next forward): one device-to-device copy
         out = torch.empty(B, r3.cout, Hf, Wf, dtype=F32, device=plan.device)
-        ops.run_now(ops.elt(L.E_GATHER_OUT, p=[T.t, out, r3.bias], i=[B, r3.cout, Hf, Wf, 1, r3.k, 0, r3.pad, 1, r3.npad, 0]))
+        out.view(-1).copy_(Y)
         return out
 
     def ingest_fn(gout):

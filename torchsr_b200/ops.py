@@ -125,7 +125,7 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
               res_scale=1.0, res2_scale=1.0, res_cols=0, w_static=True, bnr_x=None, bnr_coef=None, bnr_prelu=None,
               bnr_act=L.ACT_NONE, bnr_c=0, splits=1, ws=None, tile_counters=None, ws_ld=0, group_rows=0, bnf_mode=0,
               bnf_c=0, bnf_counter=None, bnf_gamma=None, bnf_beta=None, bnf_rm=None, bnf_rv=None, bnf_nbt=None,
-              bnf_coef=None, bnf_count=0, bnf_eps=1e-5, bnf_momentum=0.1) -> ConvDesc:
+              bnf_coef=None, bnf_count=0, bnf_eps=1e-5, bnf_momentum=0.1, gather=None) -> ConvDesc:
     d = ConvDesc()
     d.x, d.w = ptr(x), ptr(w)
     d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
@@ -155,6 +155,9 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     d.bnf_counter, d.bnf_gamma, d.bnf_beta = ptr(bnf_counter), ptr(bnf_gamma), ptr(bnf_beta)
     d.bnf_rm, d.bnf_rv, d.bnf_nbt, d.bnf_coef = ptr(bnf_rm), ptr(bnf_rv), ptr(bnf_nbt), ptr(bnf_coef)
     d.bnf_eps, d.bnf_momentum = bnf_eps, bnf_momentum
+    if gather is not None:      # dict(k, pad, c, bias): OUT_GATHER_W, `out` is the zero-initialised fp32 NCHW result
+        d.out_mode, d.out_f32 = L.OUT_GATHER_W, 1
+        d.gather_k, d.gather_pad, d.gather_c, d.gather_bias = gather["k"], gather["pad"], gather["c"], ptr(gather.get("bias"))
     return d
 
 
@@ -282,7 +285,16 @@ def validate_conv(d: ConvDesc):
             span = d.n_valid
         else:
             span = d.n_valid
-        _need("conv out", d.out, (last + d.out_ch_off + span) * esz)
+        if d.out_mode == L.OUT_GATHER_W:
+            if (d.gather_k < 1 or d.gather_c < 1 or d.gather_k * d.gather_c > d.block_n or d.block_n != d.cout_pad
+                    or not 0 <= d.gather_pad < d.gather_k or d.splits > 1 or not d.out_f32 or d.out_preact or d.bias
+                    or d.res or d.bwd_z or d.bnr_x or d.stats_partial or d.bnf_mode):
+                raise ExtentError("OUT_GATHER_W: one N tile holding gather_k*gather_c columns, fp32 output, plain epilogue")
+            _need("conv gather out", d.out, d.N * d.gather_c * d.Ho * d.Wo * 4)
+            if d.gather_bias:
+                _need("conv gather bias", d.gather_bias, d.gather_c * 4)
+        else:
+            _need("conv out", d.out, (last + d.out_ch_off + span) * esz)
         if d.out_preact:
             _need("conv out_preact", d.out_preact, (last + d.out_ch_off + span) * 2)
         rc = min(d.n_valid, d.res_cols) if d.res_cols > 0 else d.n_valid
@@ -355,7 +367,7 @@ def validate_conv(d: ConvDesc):
     for off in (d.out_ch_off, d.aux_ch_off):
         if off % 8:
             raise ExtentError("channel offsets must be multiples of 8 (16-byte vector accesses)")
-    if d.out_mode != L.OUT_GEMM_T_ATOMIC:
+    if d.out_mode not in (L.OUT_GEMM_T_ATOMIC, L.OUT_GATHER_W):
         q = 4 if d.out_f32 else 8
         for st in ((d.os_n, d.os_h, d.os_w) if d.a_mode == 0 else (d.os_w,)):
             if st % q:
