@@ -462,6 +462,42 @@ def test_eval_mode_no_grad_and_large_image_psnr(bn_fuse):
     assert not any(p.busy for pool in G._tsr["plans"].values() for p in pool)
 
 
+def test_large_image_inference_staged_halo_paths_match_oracle_and_generic_kernels(monkeypatch):
+    """A 160x192 image is large enough for the persistent kernels: trunk convs run the halo-patch main loop with the
+    staged (bulk tensor store) epilogue, the sub-pixel convs its PixelShuffle variant, the 9x9 output conv sums its
+    horizontal taps in the epilogue. Checked against the oracle and against the generic kernels (both switches off)."""
+    MC, SG, SD, EG, ED = _mods()
+    torch.manual_seed(21)
+    G = SG()
+    MC.randomize_bn(G)
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    x = torch.rand(1, 3, 160, 192)
+    with torch.no_grad():
+        ref = MC.O.srgan_generator(sd, x, False)
+        y_new = G.cuda().eval()(x.cuda()).cpu()
+        monkeypatch.setenv("TSR_CONV_STAGED", "0")
+        monkeypatch.setenv("TSR_CONV_HALO", "0")
+        G2 = SG()
+        G2.load_state_dict(sd)
+        y_old = G2.cuda().eval()(x.cuda()).cpu()
+    assert y_new.shape == (1, 3, 640, 768)
+    assert MC.rel_l2(y_new, ref) <= 3e-2, MC.rel_l2(y_new, ref)
+    # same bf16 store points, same fp32 accumulation per tile: only the tile shapes differ
+    assert MC.rel_l2(y_new, y_old) <= 2e-3, MC.rel_l2(y_new, y_old)
+
+
+def test_upscale_pipelined_equals_sequential_upscale():
+    from torchsr_b200.test import upscale, upscale_pipelined
+    MC, SG, SD, EG, ED = _mods()
+    torch.manual_seed(22)
+    G = SG().cuda()
+    xs = [torch.rand(1, 3, 24, 32).pin_memory() for _ in range(5)]
+    ys = [torch.empty(1, 3, 96, 128).pin_memory() for _ in range(5)]
+    upscale_pipelined(G, xs, ys)
+    for x, y in zip(xs, ys):
+        assert torch.equal(y, upscale(G, x.cuda()).cpu())
+
+
 def test_gan_step_matches_oracle_step():
     """One SRGANTrainer._gan_loop on the B200 against the oracle port of the reference step: same losses (MSE content
     loss stands in for VGG, which is executed by PyTorch on both sides) and the same direction of the Adam update."""

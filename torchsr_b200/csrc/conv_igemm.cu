@@ -760,40 +760,60 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         const bool res_cols_ok = res != nullptr && colbase + c_lo < e.res_cols;
         const int row = q * 32 + lane;
         const bool shuf = out_mode == OUT_SHUFFLE;
-        int jj = 0;
-        for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++jj) {
-          const int as = jj & 1;
-          int n, ho, wo, crow = row, w0 = 0, h0 = 0;
+        // tile -> (image, output pixel of this thread's accumulator row, its row in the staging buffer, box origin)
+        struct TileGeom {
+          int n, ho, wo, crow, w0, h0;
           bool valid;
+        };
+        auto tile_geom = [&](int tile_m) {
+          TileGeom g;
+          g.crow = row;
+          g.w0 = g.h0 = 0;
           if (p.halo) {
-            n = tile_m / p.halo_tiles_per_img;
-            const int t_img = tile_m - n * p.halo_tiles_per_img;
+            g.n = tile_m / p.halo_tiles_per_img;
+            const int t_img = tile_m - g.n * p.halo_tiles_per_img;
             const int t_y = t_img / p.halo_strips;
             const int orow = row / p.halo_pw;
             const int pos = row - orow * p.halo_pw;
-            w0 = (t_img - t_y * p.halo_strips) * sw;
-            h0 = t_y * p.halo_th;
-            wo = w0 + pos;
-            ho = h0 + orow;
-            valid = pos < sw && wo < p.halo_W && orow < p.halo_th && ho < p.halo_H;
-            crow = orow * sw + pos;       // the two discarded positions of every patch row are squeezed out
+            g.w0 = (t_img - t_y * p.halo_strips) * sw;
+            g.h0 = t_y * p.halo_th;
+            g.wo = g.w0 + pos;
+            g.ho = g.h0 + orow;
+            g.valid = pos < sw && g.wo < p.halo_W && orow < p.halo_th && g.ho < p.halo_H;
+            g.crow = orow * sw + pos;       // the two discarded positions of every patch row are squeezed out
           } else {
             const int m = tile_m * kBlockM + row;
-            valid = m < p.M_total;
+            g.valid = m < p.M_total;
             const int hw = p.Ho * p.Wo;
-            n = m / hw;
-            const int rem = m - n * hw;
-            ho = rem / p.Wo;
-            wo = rem - ho * p.Wo;
+            g.n = m / hw;
+            const int rem = m - g.n * hw;
+            g.ho = rem / p.Wo;
+            g.wo = rem - g.ho * p.Wo;
           }
-          // the residual row does not depend on the accumulator: fetch it before waiting for the main loop
-          uint4 rq[4];
-          const bool has_res = res_cols_ok && valid;
-          if (has_res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + n * aux_n +
-                                                             ho * aux_h + wo * aux_w + aux_c);
+          return g;
+        };
+        // the residual row does not depend on the accumulator: it is fetched one whole tile ahead (registers), so its
+        // L2 round trip never sits between two tiles of this warp
+        auto load_res = [&](const TileGeom& g, uint4 (&rq)[4]) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(res) + g.n * aux_n +
+                                                           g.ho * aux_h + g.wo * aux_w + aux_c);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rq[k] = __ldg(rp + k);
+          for (int k = 0; k < 4; ++k) rq[k] = __ldg(rp + k);
+        };
+        TileGeom tg = tile_geom(blockIdx.x);
+        uint4 rq[4], rq_next[4];
+        if (res_cols_ok && tg.valid && static_cast<int>(blockIdx.x) < tiles_m) load_res(tg, rq);
+        int jj = 0;
+        for (int tile_m = blockIdx.x; tile_m < tiles_m; tile_m += gridDim.x, ++jj) {
+          const int as = jj & 1;
+          const int n = tg.n, crow = tg.crow, w0 = tg.w0, h0 = tg.h0;
+          const bool valid = tg.valid;
+          const bool has_res = res_cols_ok && valid;
+          const int tile_next = tile_m + static_cast<int>(gridDim.x);
+          TileGeom tg_next = tg;
+          if (tile_next < tiles_m) {
+            tg_next = tile_geom(tile_next);
+            if (res_cols_ok && tg_next.valid) load_res(tg_next, rq_next);
           }
           mbar_wait(bar_acc_full + 8 * as, (jj >> 1) & 1, e.err, 3);
           tc_fence_after();
@@ -862,6 +882,9 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
               tma_store_2d(&p.tmO[0], sbuf, colbase, tile_m * kBlockM);
             bulk_commit_group();
           }
+          tg = tg_next;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rq[k] = rq_next[k];
         }
         if (threadIdx.x == 64) bulk_wait_group0();
       }

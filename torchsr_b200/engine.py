@@ -35,7 +35,8 @@ SPLIT_K_MIN_ITERS = int(os.environ.get("TSR_SPLITK_MIN_ITERS", "0"))
 # two-launch path (conv with column sums, then bn_act_kernel) everywhere - both stay parity-tested.
 FUSE_BN_FWD = os.environ.get("TSR_BN_FUSE", "1") != "0"
 # 64-column N tiles for the convs the staged epilogue serves (see Plan.conv_fwd); TSR_CONV_STAGED=0 also disables it in C
-STAGED_N64 = os.environ.get("TSR_CONV_STAGED", "1") != "0" and os.environ.get("TSR_CONV_PERSISTENT", "1") != "0"
+def _staged_n64() -> bool:     # read per plan build, like the C side reads its switches per descriptor
+    return os.environ.get("TSR_CONV_STAGED", "1") != "0" and os.environ.get("TSR_CONV_PERSISTENT", "1") != "0"
 # the same for backward: dx = A*dz + B*x + C formed in the epilogue of the data-gradient conv that produced dz (after a
 # grid barrier on the column sums) instead of a bn_bwd_apply_kernel launch; "0" keeps the separate launch
 FUSE_BN_BWD = os.environ.get("TSR_BN_BWD_FUSE", "1") != "0"
@@ -408,7 +409,7 @@ class Plan:
         # 3x3 / stride-1 convs on 64 input channels with a plain bf16 store and many M tiles per SM run the persistent
         # halo kernel with the staged (TMA-store) epilogue, which is built for 64-column N tiles (csrc/conv_params.h):
         # the activations are then re-read once per N tile, but from a patch that is fetched ~1.5x instead of 9x
-        if (STAGED_N64 and rec.k == 3 and rec.stride == 1 and rec.pad == 1 and x.C == 64 and block_n > 64
+        if (_staged_n64() and rec.k == 3 and rec.stride == 1 and rec.pad == 1 and x.C == 64 and block_n > 64
                 and rec.cout_pad % 64 == 0 and "splits" not in tiles and stats is None and preact is None and res2 is None
                 and not out_f32 and (bnf is None or bnf.get("bnf_mode") == 2)
                 and (not shuffle_out or (rec.cout == 256 and rec.cout_pad == 256))):

@@ -23,6 +23,30 @@ def upscale(generator, low_res: torch.Tensor, train_mode: bool = False) -> torch
         return generator(low_res)
 
 
+def upscale_pipelined(generator, inputs, outputs, train_mode: bool = False) -> None:
+    """Throughput path for a folder / stream of images (the loop of `_test`, */trainer.py:282-286, over many images):
+    `inputs` are host tensors [B,3,H,W] (pinned for real overlap), `outputs` pre-allocated host tensors [B,3,4H,4W].
+    The host->device copy of image i+1 and the device->host copy of image i-1 run on their own streams while image i
+    is being computed; every image still takes the same three steps in order. Returns once all outputs are on the host."""
+    dev = next(generator.parameters()).device
+    cur = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    generator.train(train_mode)
+    with torch.no_grad():
+        for x_h, y_h in zip(inputs, outputs):
+            with torch.cuda.stream(s_in):
+                x = x_h.to(dev, non_blocking=True)
+            cur.wait_stream(s_in)
+            x.record_stream(cur)
+            y = generator(x)
+            s_out.wait_stream(cur)
+            with torch.cuda.stream(s_out):
+                y_h.copy_(y, non_blocking=True)
+            y.record_stream(s_out)
+    cur.wait_stream(s_out)
+    s_out.synchronize()
+
+
 def test(args: Namespace, model_class, device) -> str:
     from PIL import Image
     from torchvision import utils
