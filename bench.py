@@ -455,6 +455,15 @@ def inference_block(pk, steps=10):
         e1.record()
         torch.cuda.synchronize()
         ms_e2e_serial = e0.elapsed_time(e1) / steps
+        # the same loop delivering the 8-bit image the reference's test() writes (save_image quantisation on the device)
+        y8 = [torch.empty(y_h.shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        upscale_pipelined(G, [x_h] * 2, y8)
+        torch.cuda.synchronize()
+        e0.record()
+        upscale_pipelined(G, [x_h] * steps, [y8[i & 1] for i in range(steps)])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e_u8 = e0.elapsed_time(e1) / steps
     mpx = b * (4 * size) ** 2 / 1e6
     tf = GFLOP_PER_MPX_INFER * mpx / ms
     out = {"workload": "SRGAN generator x4 inference (BASELINE configs[4]): batch %d of synthetic %dx%d LR -> %dx%d, eval "
@@ -463,7 +472,11 @@ def inference_block(pk, steps=10):
            "e2e": {"value": mpx / (ms_e2e * 1e-3), "unit": "output Mpx/s", "ms_per_image": ms_e2e / b,
                    "h2d_bytes_per_step": x_h.numel() * 4, "d2h_bytes_per_step": y_h.numel() * 4,
                    "api": "torchsr_b200.test.upscale_pipelined (copies of neighbouring images overlap the compute)",
-                   "serial_ms_per_image": ms_e2e_serial / b},
+                   "serial_ms_per_image": ms_e2e_serial / b,
+                   "uint8_output": {"value": mpx / (ms_e2e_u8 * 1e-3), "ms_per_image": ms_e2e_u8 / b,
+                                    "d2h_bytes_per_step": y_h.numel(),
+                                    "what": "same API with uint8 host outputs: the 8-bit image of torchvision.utils."
+                                            "save_image (reference test.py:62), quantised on the device"}},
            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["sustained"], "unit": "TFLOP/s",
                         "frac": tf / pk["sustained"], "gflop_per_output_mpx": GFLOP_PER_MPX_INFER},
            "peak_memory_gib": torch.cuda.max_memory_allocated() / 2 ** 30}

@@ -496,6 +496,10 @@ def test_upscale_pipelined_equals_sequential_upscale():
     upscale_pipelined(G, xs, ys)
     for x, y in zip(xs, ys):
         assert torch.equal(y, upscale(G, x.cuda()).cpu())
+    y8 = [torch.empty(1, 3, 96, 128, dtype=torch.uint8).pin_memory() for _ in range(5)]
+    upscale_pipelined(G, xs, y8)
+    for y, q in zip(ys, y8):        # torchvision.utils.save_image's quantisation
+        assert torch.equal(q, y.clone().mul_(255).add_(0.5).clamp_(0, 255).to(torch.uint8))
 
 
 def test_gan_step_matches_oracle_step():

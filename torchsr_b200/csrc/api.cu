@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -529,48 +530,80 @@ int build_wgrad(const tsr_wgrad_desc_t& d, WgradLaunch* L) {
   p.err = g_watchdog;
   memcpy(p.tap_off, d.tap_off, sizeof(p.tap_off));
   const int total_groups = (p.total_blocks + p.blocks_per_m - 1) / p.blocks_per_m;
-  int gpc = 512 / d.block_n;  // groups whose accumulators fit the 512 TMEM columns
-  if (gpc > total_groups) gpc = total_groups;
-  {
-    // fewer groups per CTA = more CTAs (each re-reads the dY tile): shrink until the grid can cover the 148 SMs
-    const int tiles_n0 = static_cast<int>((d.cout_valid + d.block_n - 1) / d.block_n);
-    const int iters64 = (p.M_total + 63) / 64;
-    const int max_splits0 = iters64 / 4 > 0 ? iters64 / 4 : 1;
-    while (gpc > 1 && ((total_groups + gpc - 1) / gpc) * tiles_n0 * max_splits0 < 148) gpc = (gpc + 1) / 2;
-  }
-  // choose pixels per stage / groups per CTA so that at least 2 stages fit in ~200 KB
-  int pix = 64;
+  L->tiles_n = static_cast<int>((d.cout_valid + d.block_n - 1) / d.block_n);
+  // Grid shape = (groups per CTA, pixels per stage, K splits), one CTA per SM (the accumulators may take the whole
+  // TMEM). Every candidate is scored with a small cost model fitted to tools/microbench_wgrad.py on B200
+  // (profiles/r02c_wgrad_grid.md) and the cheapest wins:
+  //   pipeline stage: 300 clk + stage bytes / 36 B/clk  (the im2col boxes arrive at the per-SM L2 -> SM rate; the
+  //                   UMMAs of the stage hide behind them), x1.5 when fewer than 3 stages fit in shared memory
+  //   CTA:            3000 clk (setup, first TMA round trip, drain) + stages + tile bytes / 30 (fp32 vector atomics)
+  //   launch:         max(1, CTAs / 148) rounds of that (short CTAs backfill, so fractional rounds), plus the total
+  //                   atomic volume at ~12 KB/clk of L2 reduction throughput.
+  // TSR_WGRAD_GPC / TSR_WGRAD_SPLITS / TSR_WGRAD_PIX pin a choice (tools/microbench_wgrad.py).
   auto stage_bytes = [&](int g, int px) {
     return static_cast<size_t>(((g * p.blocks_per_m * px * d.chan_block * 2 + (d.block_n / d.dy_block) * px * d.dy_block * 2) +
                                 1023) & ~1023);
   };
-  while (gpc > 1 && stage_bytes(gpc, pix) * 2 > 200 * 1024) --gpc;
-  if (stage_bytes(gpc, pix) * 3 > 200 * 1024) pix = 32;
-  if (stage_bytes(gpc, pix) * 2 > 200 * 1024) return fail(-32, "wgrad tile does not fit shared memory");
+  const size_t smem_cap = 200 * 1024;
+  int gpc = 1, pix = 64, splits = 1;
+  {
+    const int env_gpc = getenv("TSR_WGRAD_GPC") ? atoi(getenv("TSR_WGRAD_GPC")) : 0;
+    const int env_pix = getenv("TSR_WGRAD_PIX") ? atoi(getenv("TSR_WGRAD_PIX")) : 0;
+    const int env_splits = getenv("TSR_WGRAD_SPLITS") ? atoi(getenv("TSR_WGRAD_SPLITS")) : 0;
+    const int max_gpc = std::min(512 / d.block_n, total_groups);
+    double best = 1e30;
+    for (int px = 64; px >= 32; px -= 32) {
+      if (env_pix > 0 && px != env_pix) continue;
+      const int iters_total = (p.M_total + px - 1) / px;
+      for (int g = 1; g <= max_gpc; ++g) {
+        if (env_gpc > 0 && g != env_gpc) continue;
+        if (stage_bytes(g, px) * 2 > smem_cap) continue;
+        const int gsets = (total_groups + g - 1) / g;
+        const int base = gsets * L->tiles_n;
+        int st_fit = 6;
+        while (st_fit > 2 && stage_bytes(g, px) * st_fit > smem_cap) --st_fit;
+        const double it_clk = (300.0 + static_cast<double>(stage_bytes(g, px)) / 36.0) * (st_fit < 3 ? 1.5 : 1.0);
+        const double tile_bytes = static_cast<double>(g) * 128 * d.block_n * 4;
+        int last_ipc = -1;
+        for (int sp = 1; sp <= iters_total; ++sp) {
+          if (d.splits > 0 && sp != d.splits) continue;
+          if (env_splits > 0 && sp != env_splits) continue;
+          const int ipc = (iters_total + sp - 1) / sp;     // pipeline iterations per CTA
+          if (ipc == last_ipc) continue;                   // same work per CTA with more CTAs: never better
+          last_ipc = ipc;
+          const int sp_eff = (iters_total + ipc - 1) / ipc;
+          const long ctas = static_cast<long>(base) * sp_eff;
+          const double rounds = std::max(1.0, static_cast<double>(ctas) / 148.0);
+          const double cost = rounds * (3000.0 + ipc * it_clk + tile_bytes / 30.0) + ctas * tile_bytes / 12000.0;
+          if (cost < best) {
+            best = cost;
+            gpc = g;
+            pix = px;
+            splits = sp_eff;
+          }
+        }
+      }
+    }
+    if (best >= 1e30) return fail(-32, "wgrad tile does not fit shared memory");
+  }
   p.groups_per_cta = gpc;
   p.pix_per_stage = pix;
   int stages = 6;
-  while (stages > 2 && stage_bytes(gpc, pix) * stages > 200 * 1024) --stages;
+  while (stages > 2 && stage_bytes(gpc, pix) * stages > smem_cap) --stages;
   p.tmem_cols = pow2_cols(gpc * d.block_n);
   if (p.tmem_cols > 512) return fail(-32, "wgrad accumulators exceed TMEM");
   L->gsets = (total_groups + gpc - 1) / gpc;
-  L->tiles_n = static_cast<int>((d.cout_valid + d.block_n - 1) / d.block_n);
   const int total_stage_iters = (p.M_total + pix - 1) / pix;
-  int splits = d.splits;
-  if (splits <= 0) {
-    // aim for ~2 CTAs per SM overall, at least 4 pipeline iterations per CTA
-    const int base = L->gsets * L->tiles_n;
-    splits = (296 + base - 1) / base;
-    const int max_splits = total_stage_iters / 4 > 0 ? total_stage_iters / 4 : 1;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-  }
   if (splits > total_stage_iters) splits = total_stage_iters;
   p.stages_per_cta = (total_stage_iters + splits - 1) / splits;
   splits = (total_stage_iters + p.stages_per_cta - 1) / p.stages_per_cta;
   L->splits = splits;
   if (stages > p.stages_per_cta) stages = p.stages_per_cta;
   p.stages = stages;
+  if (const char* v = getenv("TSR_CONV_VERBOSE"); v && v[0] == '1')
+    fprintf(stderr, "[tsr] wgrad M=%d C=%d taps=%d N=%d block_n=%d: gpc=%d gsets=%d tiles_n=%d splits=%d pix=%d stages=%d/%d\n",
+            p.M_total, p.cin_pad, p.num_taps, d.cout_valid, d.block_n, gpc, L->gsets, L->tiles_n, splits, pix, stages,
+            p.stages_per_cta);
   if (int e = encode_im2col(&p.tmX, reinterpret_cast<const char*>(d.x) + static_cast<int64_t>(d.x_c0) * 2, d.N, d.H, d.W,
                             p.cin_pad, d.x_ld, d.lower_h, d.lower_w, d.upper_h, d.upper_w, d.stride, d.chan_block, pix))
     return e;

@@ -107,26 +107,17 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 // OUT_GATHER_W for the generators' 9x9 Cout=3 output conv (EpiParams::gather_*), one 16-column chunk of a warp's 32
 // accumulator rows (= 32 consecutive pixels, lane = pixel): column col = kw*3 + c is horizontal tap kw of channel c, and
 //   out[pixel][c] = sum_kw acc[pixel + kw - 4][kw*3 + c].
-// Lane L collects the taps that the warp's own rows hold for its pixel with one shuffle per column; lanes 0..7 then do
-// the same for the 4 + 4 pixels just outside the warp's range (their remaining taps come from the neighbouring warp /
-// tile, which adds them the same way). Every partial sum goes to the zero-initialised fp32 NCHW output with one atomic
-// per channel: no shared memory, no barrier, and the 64-byte fp32 rows never travel to HBM.
+// Lane L collects the taps that the warp's own rows hold for its pixel with one shuffle per column (a0); lanes 0..7 do
+// the same for the 4 + 4 pixels just outside the warp's range (a1) - their remaining taps come from the neighbouring
+// warp / tile, which adds them the same way. The caller sums the partials of the two column chunks and adds them to the
+// zero-initialised fp32 NCHW output: at most two atomic adds ever meet on one element, so the result does not depend on
+// their order. No shared-memory tile, no CTA barrier, and the 64-byte fp32 rows never travel to HBM.
 template <int CH>
-__device__ __forceinline__ void gather9x3(const float (&v)[16], int lane, bool valid, int wo, long long own, int m_first,
-                                          int M_total, int Ho, int Wo, float* __restrict__ out,
-                                          const float* __restrict__ bias) {
+__device__ __forceinline__ void gather9x3(const float (&v)[16], int lane, int wo, int P, bool ext, int wcol, int Wo,
+                                          float (&a0)[3], float (&a1)[3]) {
   constexpr int K = 9, GC = 3, PAD = 4;
-  const long long cs = static_cast<long long>(Ho) * Wo;
-  // pixels outside the warp's rows: lanes 0..3 -> m_first - 4 .. - 1, lanes 4..7 -> m_first + 32 .. + 35
-  const int P = lane < 4 ? lane - 4 : 28 + lane;
-  const long long mo = static_cast<long long>(m_first) + P;
-  const bool ext = lane < 8 && mo >= 0 && mo < M_total;
-  int rowid = 0, wcol = 0;
-  if (ext) {
-    rowid = static_cast<int>(mo / Wo);
-    wcol = static_cast<int>(mo - static_cast<long long>(rowid) * Wo);
-  }
-  float a0[GC] = {0.f, 0.f, 0.f}, a1[GC] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < GC; ++c) a0[c] = a1[c] = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int col = CH * 16 + i;
@@ -141,18 +132,6 @@ __device__ __forceinline__ void gather9x3(const float (&v)[16], int lane, bool v
       const int ws1 = wcol + kw - PAD;
       if (ext && src1 >= 0 && src1 < 32 && ws1 >= 0 && ws1 < Wo) a1[c] += t1;
     }
-  }
-  if (valid) {
-#pragma unroll
-    for (int c = 0; c < GC; ++c) {
-      atomicAdd(out + own + c * cs, a0[c] + ((CH == 0 && bias != nullptr) ? __ldg(bias + c) : 0.f));
-    }
-  }
-  if (ext) {
-    const int nn = rowid / Ho, hh = rowid - nn * Ho;
-    const long long o = ((static_cast<long long>(nn) * GC) * Ho + hh) * Wo + wcol;
-#pragma unroll
-    for (int c = 0; c < GC; ++c) atomicAdd(out + o + c * cs, a1[c]);
   }
 }
 
@@ -1402,11 +1381,47 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = 0.f;
           }
-          const long long own = ((static_cast<long long>(n) * 3) * p.Ho + ho) * p.Wo + wo;
+          // pixels just outside the warp's rows: lanes 0..3 -> first - 4 .. - 1, lanes 4..7 -> first + 32 .. + 35
+          const int P = lane < 4 ? lane - 4 : 28 + lane;
+          const long long mo = static_cast<long long>(m0) + q * 32 + P;
+          const bool ext = lane < 8 && mo >= 0 && mo < p.M_total;
+          int rowid = 0, wcol = 0;
+          if (ext) {
+            rowid = static_cast<int>(mo / p.Wo);
+            wcol = static_cast<int>(mo - static_cast<long long>(rowid) * p.Wo);
+          }
+          float a0[3], a1[3];
           if (ch == 0)
-            gather9x3<0>(v, lane, valid, wo, own, m0 + q * 32, p.M_total, p.Ho, p.Wo, reinterpret_cast<float*>(out), e.gather_bias);
+            gather9x3<0>(v, lane, wo, P, ext, wcol, p.Wo, a0, a1);
           else
-            gather9x3<1>(v, lane, valid, wo, own, m0 + q * 32, p.M_total, p.Ho, p.Wo, reinterpret_cast<float*>(out), e.gather_bias);
+            gather9x3<1>(v, lane, wo, P, ext, wcol, p.Wo, a0, a1);
+          // the two warps of a lane quadrant hold the two column chunks of the same rows: the upper half hands its
+          // partial sums over through shared memory (double-buffered across the tiles of a persistent CTA)
+          float* pbuf = scratch + ((j & 1) * kBlockM + row) * 6;
+          if (half == 1) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              pbuf[c] = a0[c];
+              pbuf[3 + c] = a1[c];
+            }
+            named_bar_sync(2 + q, 64);
+          } else {
+            named_bar_sync(2 + q, 64);
+            float* const o = reinterpret_cast<float*>(out);
+            const long long cs = static_cast<long long>(p.Ho) * p.Wo;
+            if (valid) {
+              const long long own = ((static_cast<long long>(n) * 3) * p.Ho + ho) * p.Wo + wo;
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                atomicAdd(o + own + c * cs, a0[c] + pbuf[c] + (e.gather_bias != nullptr ? __ldg(e.gather_bias + c) : 0.f));
+            }
+            if (ext) {
+              const int nn = rowid / p.Ho, hh = rowid - nn * p.Ho;
+              const long long oe = ((static_cast<long long>(nn) * 3) * p.Ho + hh) * p.Wo + wcol;
+#pragma unroll
+              for (int c = 0; c < 3; ++c) atomicAdd(o + oe + c * cs, a1[c] + pbuf[3 + c]);
+            }
+          }
           continue;
         }
         const bool st = valid && col0 < n_valid && (FAST || !(p.debug & 2));

@@ -23,11 +23,19 @@ def upscale(generator, low_res: torch.Tensor, train_mode: bool = False) -> torch
         return generator(low_res)
 
 
+def to_uint8_image(img: torch.Tensor) -> torch.Tensor:
+    """[0,1] float image -> 8-bit, with the arithmetic of torchvision.utils.save_image (the reference's last step,
+    test.py:62): mul(255).add_(0.5).clamp_(0, 255).to(uint8). In place on `img`, which must be a temporary."""
+    return img.mul_(255.0).add_(0.5).clamp_(0.0, 255.0).to(torch.uint8)
+
+
 def upscale_pipelined(generator, inputs, outputs, train_mode: bool = False) -> None:
     """Throughput path for a folder / stream of images (the loop of `_test`, */trainer.py:282-286, over many images):
     `inputs` are host tensors [B,3,H,W] (pinned for real overlap), `outputs` pre-allocated host tensors [B,3,4H,4W].
     The host->device copy of image i+1 and the device->host copy of image i-1 run on their own streams while image i
-    is being computed; every image still takes the same three steps in order. Returns once all outputs are on the host."""
+    is being computed; every image still takes the same three steps in order. Returns once all outputs are on the host.
+    uint8 `outputs` receive the 8-bit image `torchvision.utils.save_image` would write (quantised on the device, a
+    quarter of the bytes over PCIe); float outputs receive the raw generator output."""
     dev = next(generator.parameters()).device
     cur = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -39,6 +47,8 @@ def upscale_pipelined(generator, inputs, outputs, train_mode: bool = False) -> N
             cur.wait_stream(s_in)
             x.record_stream(cur)
             y = generator(x)
+            if y_h.dtype == torch.uint8:
+                y = to_uint8_image(y)
             s_out.wait_stream(cur)
             with torch.cuda.stream(s_out):
                 y_h.copy_(y, non_blocking=True)
