@@ -46,6 +46,25 @@ def test_residual_block_stage(bn_fuse):
     assert r["grad_median"] <= 3e-2 and r["dx"] <= 5e-2, (r, errs)
 
 
+def test_residual_block_stage_two_ctas_per_sm_grid_barrier():
+    """Batch 64 of 24x24: 288 output tiles, i.e. more CTAs than SMs. The fused conv + BatchNorm launches (forward, and
+    the backward apply) then rely on two CTAs per SM being resident together at the grid barrier (the host counts the
+    resources itself: the runtime's occupancy calculator reports 1 for every tcgen05 kernel, tools/occ_probe)."""
+    import module_checks as MC
+    from torchsr_b200 import ops
+    from torchsr_b200.srgan.residual import ResidualBlock
+    torch.manual_seed(3)
+    m = ResidualBlock()
+    MC.randomize_bn(m)
+    launches0 = ops.launch_count() if hasattr(ops, "launch_count") else None
+    r, errs = MC.check_module(m, lambda sd, x, tr, buf: MC.O.srgan_residual_block(
+        {("." + k): v for k, v in sd.items()}, "", x, tr, buf), torch.randn(64, 64, 24, 24), input_grad=True)
+    assert r["out"] <= 1e-2 and r["bn_buffers"] <= 1e-2, r
+    assert r["grad_median"] <= 3e-2 and r["dx"] <= 5e-2, (r, errs)
+    ops.check_watchdog()
+    del launches0
+
+
 def test_subpixel_stage():
     import module_checks as MC
     from torchsr_b200.srgan.residual import SubpixelConvolutionLayer

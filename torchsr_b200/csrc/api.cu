@@ -256,6 +256,13 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   while (stages > 2 && static_cast<size_t>(stages) * stage_bytes > 96 * 1024) --stages;
   if (static_cast<size_t>(stages) * stage_bytes > 200 * 1024) return fail(-22, "tile does not fit shared memory");
   if (stages > p.iters_per_split) stages = p.iters_per_split < 1 ? 1 : p.iters_per_split;
+  // Launches whose CTAs meet at a grid barrier (fused BatchNorm forward / backward apply) must be co-resident: grids
+  // of more than one CTA per SM keep their ring small enough for two CTAs per SM (<= 96 KB each, conv_igemm.cu)
+  if ((d.bnf_mode == 1 || d.bnr_apply) && d.a_mode == 0) {
+    const long tiles = static_cast<long>((p.M_total + kBlockM - 1) / kBlockM) * L->tiles_n;
+    if (tiles > 148)
+      while (stages > 2 && 1024 + kConvHeaderBytes + static_cast<size_t>(stages) * stage_bytes > 96 * 1024) --stages;
+  }
   // Persistent weight-stationary mode: many M tiles per CTA, the weights of the N tile resident in shared memory
   // (they are re-fetched by every CTA otherwise: half of the L2->SM traffic of the large-M layers), two accumulator
   // stages. Chosen when the resident weights fit and every CTA gets at least two tiles.
@@ -550,10 +557,13 @@ int build_wgrad(const tsr_wgrad_desc_t& d, WgradLaunch* L) {
     const int env_gpc = getenv("TSR_WGRAD_GPC") ? atoi(getenv("TSR_WGRAD_GPC")) : 0;
     const int env_pix = getenv("TSR_WGRAD_PIX") ? atoi(getenv("TSR_WGRAD_PIX")) : 0;
     const int env_splits = getenv("TSR_WGRAD_SPLITS") ? atoi(getenv("TSR_WGRAD_SPLITS")) : 0;
-    const int max_gpc = std::min(512 / d.block_n, total_groups);
+    // measured: more than 3 groups per CTA never wins (two-stage rings, long atomics tail), and 32-pixel stages only
+    // pay their doubled per-stage overhead when a 64-pixel stage does not fit at all
+    const int max_gpc = std::min(env_gpc > 0 ? 8 : 3, std::min(512 / d.block_n, total_groups));
     double best = 1e30;
     for (int px = 64; px >= 32; px -= 32) {
       if (env_pix > 0 && px != env_pix) continue;
+      if (env_pix <= 0 && px == 32 && best < 1e30) break;
       const int iters_total = (p.M_total + px - 1) / px;
       for (int g = 1; g <= max_gpc; ++g) {
         if (env_gpc > 0 && g != env_gpc) continue;
@@ -831,6 +841,10 @@ int tsr_conv_bnf_capacity(const tsr_conv_desc_t* d, int* ctas, int* capacity) {
   const int cap = tsr::conv_igemm_max_coresident(L.p, &per_sm);
   if (cap < 0) return fail(-46, "occupancy query failed");
   if (capacity) *capacity = cap;
+  if (const char* v = getenv("TSR_CONV_VERBOSE"); v && v[0] == '1')
+    fprintf(stderr, "[tsr] co-residency M=%d block_n=%d: %d CTAs, capacity %d (%d per SM, %zu B shared memory per CTA)\n",
+            L.p.M_total, L.p.block_n, L.p.persistent ? L.p.persistent * L.tiles_n : tiles_m * L.tiles_n * L.splits, cap, per_sm,
+            tsr::conv_igemm_smem_bytes(L.p));
   return 0;
 }
 

@@ -17,6 +17,9 @@
 //
 // Reference behaviour being replaced: every nn.Conv2d / nn.Linear call on the SRGAN/ESRGAN path
 // (torchsr/srgan/generator.py:38-58, residual.py:27,64,67, discriminator.py:31-69 and the esrgan twins).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "conv_params.h"
 #include "launch.h"
 #include "ptx.cuh"
@@ -1398,15 +1401,22 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           // the two warps of a lane quadrant hold the two column chunks of the same rows: the upper half hands its
           // partial sums over through shared memory (double-buffered across the tiles of a persistent CTA)
           float* pbuf = scratch + ((j & 1) * kBlockM + row) * 6;
+          // (barrier ids spelled out: a run-time id makes ptxas reserve all 16 hardware barriers for the CTA)
+          auto pair_sync = [&]() {
+            if (q == 0) named_bar_sync(2, 64);
+            else if (q == 1) named_bar_sync(3, 64);
+            else if (q == 2) named_bar_sync(4, 64);
+            else named_bar_sync(5, 64);
+          };
           if (half == 1) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               pbuf[c] = a0[c];
               pbuf[3 + c] = a1[c];
             }
-            named_bar_sync(2 + q, 64);
+            pair_sync();
           } else {
-            named_bar_sync(2 + q, 64);
+            pair_sync();
             float* const o = reinterpret_cast<float*>(out);
             const long long cs = static_cast<long long>(p.Ho) * p.Wo;
             if (valid) {
@@ -1739,13 +1749,65 @@ size_t conv_igemm_smem_bytes(const ConvParams& p) {
 // CTAs of this conv's kernel instantiation that the device can hold at once (occupancy x SM count): the fused
 // training BatchNorm's grid barrier needs the whole grid resident. Returns -1 on a failed query.
 template <typename Kernel>
-static int max_coresident(Kernel kernel, size_t smem, int* per_sm) {
+static int max_coresident(Kernel kernel, size_t smem, int tmem_cols, int* per_sm) {
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -1;
   int n = 0, dev = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kConvThreads, smem) != cudaSuccess) return -1;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  {
+    // The runtime's occupancy calculator answers 1 block per SM for ANY kernel that contains tcgen05.alloc, whatever its
+    // block size or shared memory (tools/occ_probe: a 12-register kernel with 32 KB gets 1), while the hardware does
+    // place two such CTAs on an SM when it is otherwise empty (same probe: 296 CTAs holding 64 TMEM columns and 96 KB
+    // each all meet at a device-wide counter). TSR_OCCUPANCY=own counts the resources here instead (registers per warp
+    // in units of 256 over the four register files, shared memory + the per-block reservation against 200 KB, threads,
+    // TMEM columns) and so lets 149..296-CTA grids use the grid-barrier epilogues. It is OPT-IN and not safe in general:
+    // inside the whole-step CUDA graph, where other branches keep SMs busy, the second CTA of some SMs never becomes
+    // resident while the first spins at the barrier (watchdog code 6 at B=64; profiles/r02c_two_ctas_per_sm.md).
+    cudaFuncAttributes fa;
+    int regs_sm = 0, resv = 0, thr_sm = 0;
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess &&
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&resv, cudaDevAttrReservedSharedMemoryPerBlock, dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev) == cudaSuccess) {
+      const int warps = kConvThreads / 32;
+      const int regs_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+      const int by_regs = (regs_sm / 4 / regs_warp) * 4 / warps;
+      const int by_smem = static_cast<int>((200 * 1024) / (smem + fa.sharedSizeBytes + resv));
+      const int by_thr = thr_sm / kConvThreads;
+      const int by_tmem = tmem_cols > 0 ? 512 / tmem_cols : 1;
+      const int own = std::min(std::min(by_regs, by_tmem), std::min(by_smem, by_thr));
+      const char* t = getenv("TSR_OCCUPANCY");
+      if (own > n && t && t[0] == 'o') n = own;
+    }
+  }
   if (per_sm) *per_sm = n;
+  if (const char* v = getenv("TSR_CONV_VERBOSE"); v && v[0] == '2') {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kernel);
+    int smem_sm = 0, regs_sm = 0, resv = 0, blocks_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&resv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+    cudaDeviceGetAttribute(&blocks_sm, cudaDevAttrMaxBlocksPerMultiprocessor, dev);
+    int n2[4] = {0, 0, 0, 0};
+    const size_t probe[4] = {32768, 65536, 98304, 112 * 1024};
+    for (int i = 0; i < 4; ++i) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n2[i], kernel, kConvThreads, probe[i]);
+    size_t avail2 = 0, avail1 = 0;
+    cudaOccupancyAvailableDynamicSMemPerBlock(&avail2, kernel, 2, kConvThreads);
+    cudaOccupancyAvailableDynamicSMemPerBlock(&avail1, kernel, 1, kConvThreads);
+    int n256 = 0, n128 = 0, nflag = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n256, kernel, 256, 32768);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n128, kernel, 128, 32768);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(&nflag, kernel, kConvThreads, 32768, cudaOccupancyDisableCachingOverride);
+    fprintf(stderr, "[tsr] occupancy probes: dyn smem available for 2 blocks/SM %zu, for 1 %zu; blocks at 256 thr %d, 128 thr %d, "
+            "flags %d; maxThreadsPerBlock %d binaryVersion %d\n", avail2, avail1, n256, n128, nflag, fa.maxThreadsPerBlock,
+            fa.binaryVersion);
+    fprintf(stderr, "[tsr] occupancy: regs %d static smem %zu local %zu maxdyn %d | SM: smem %d regs %d reserved/block %d "
+            "blocks %d | blocks/SM at 32K %d 64K %d 96K %d 112K %d, at %zu B: %d\n", fa.numRegs, fa.sharedSizeBytes,
+            fa.localSizeBytes, fa.maxDynamicSharedSizeBytes, smem_sm, regs_sm, resv, blocks_sm, n2[0], n2[1], n2[2], n2[3],
+            smem, n);
+  }
   return n * sms;
 }
 
@@ -1804,11 +1866,11 @@ int conv_igemm_max_coresident(const ConvParams& p, int* per_sm) {
   const size_t smem = conv_igemm_smem_bytes(p);
   const bool fast = fast_ok(p);
   if (p.persistent)
-    return fast ? max_coresident(conv_igemm_persistent_kernel<true>, smem, per_sm)
-                : max_coresident(conv_igemm_persistent_kernel<false>, smem, per_sm);
+    return fast ? max_coresident(conv_igemm_persistent_kernel<true>, smem, p.tmem_cols, per_sm)
+                : max_coresident(conv_igemm_persistent_kernel<false>, smem, p.tmem_cols, per_sm);
   if (p.a_mode != 0) return -1;
-  return fast ? max_coresident(conv_igemm_kernel<0, true>, smem, per_sm)
-              : max_coresident(conv_igemm_kernel<0, false>, smem, per_sm);
+  return fast ? max_coresident(conv_igemm_kernel<0, true>, smem, p.tmem_cols, per_sm)
+              : max_coresident(conv_igemm_kernel<0, false>, smem, p.tmem_cols, per_sm);
 }
 
 }  // namespace tsr
