@@ -46,10 +46,13 @@ def test_residual_block_stage(bn_fuse):
     assert r["grad_median"] <= 3e-2 and r["dx"] <= 5e-2, (r, errs)
 
 
-def test_residual_block_stage_two_ctas_per_sm_grid_barrier():
-    """Batch 64 of 24x24: 288 output tiles, i.e. more CTAs than SMs. The fused conv + BatchNorm launches (forward, and
-    the backward apply) then rely on two CTAs per SM being resident together at the grid barrier (the host counts the
-    resources itself: the runtime's occupancy calculator reports 1 for every tcgen05 kernel, tools/occ_probe)."""
+@pytest.mark.parametrize("occupancy", ["api", "own"])
+def test_residual_block_stage_batch64_more_tiles_than_sms(occupancy, monkeypatch):
+    """Batch 64 of 24x24: 288 output tiles, i.e. more CTAs than SMs. With the runtime's occupancy answer (1 CTA per SM for
+    every tcgen05 kernel) the stage takes the two-launch BatchNorm path; with TSR_OCCUPANCY=own (opt-in, host-side
+    resource count, profiles/r02c_two_ctas_per_sm.md) the fused launches rely on two CTAs per SM being resident together
+    at the grid barrier - fine for a module run on its own, which is what this test does."""
+    monkeypatch.setenv("TSR_OCCUPANCY", occupancy)
     import module_checks as MC
     from torchsr_b200 import ops
     from torchsr_b200.srgan.residual import ResidualBlock
