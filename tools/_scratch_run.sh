@@ -1,11 +1,7 @@
-echo "A carveout=max, api occupancy"; timeout 200 python bench.py --only none --steps 20 --warmup 5 2>/dev/null | python -c "
+run() { timeout 400 python bench.py --only b64 --steps 20 --warmup 5 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"
-echo "B carveout=default, api occupancy"; TSR_CARVEOUT=default timeout 200 python bench.py --only none --steps 20 --warmup 5 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"
-export TSR_OCCUPANCY=own
-echo "C carveout=max, own occupancy b16"; timeout 200 python bench.py --only none --steps 20 --warmup 5 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])"
-echo "D graph_step b64 own occupancy"; TOP=2 timeout 150 python tools/profile_step.py 64 2>&1 | tail -3 | cut -c1-200
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', 'b16', round(d['value']), d['ms_per_step'], 'b64', round(d['b64']['value']), d['b64']['ms_per_step'])"; }
+run default
+TSR_RING_KB=190 run ring190
+TSR_PERSIST_MIN_TILES_X10=12 run persist1.2
+TSR_RING_KB=190 TSR_PERSIST_MIN_TILES_X10=12 run both

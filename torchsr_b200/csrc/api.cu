@@ -252,8 +252,14 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   p.acc_cols = pow2_cols(d.block_n);
   p.tmem_cols = p.acc_cols;
   uint32_t stage_bytes = ((kBlockM * d.block_k * 2 + d.block_n * d.block_k * 2) + 1023u) & ~1023u;
-  int stages = 6;
-  while (stages > 2 && static_cast<size_t>(stages) * stage_bytes > 96 * 1024) --stages;
+  // ring budget of the one-tile kernels (KB; TSR_RING_KB overrides): 96 KB leaves room for a second CTA on the SM
+  static const int ring_kb = [] {
+    const char* e = getenv("TSR_RING_KB");
+    const int v = e ? atoi(e) : 96;
+    return v < 48 ? 48 : (v > 200 ? 200 : v);
+  }();
+  int stages = ring_kb > 96 ? 8 : 6;     // the barrier block holds eight stages
+  while (stages > 2 && static_cast<size_t>(stages) * stage_bytes > static_cast<size_t>(ring_kb) * 1024) --stages;
   if (static_cast<size_t>(stages) * stage_bytes > 200 * 1024) return fail(-22, "tile does not fit shared memory");
   if (stages > p.iters_per_split) stages = p.iters_per_split < 1 ? 1 : p.iters_per_split;
   // Launches whose CTAs meet at a grid barrier (fused BatchNorm forward / backward apply) must be co-resident: grids
