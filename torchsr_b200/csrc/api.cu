@@ -231,7 +231,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   const bool out_lin = d.out_mode == TSR_OUT_LINEAR, out_shuf = d.out_mode == TSR_OUT_SHUFFLE;
   const bool out_dense = d.os_h == d.Wo * d.os_w && d.os_n == d.Ho * d.os_h;
   const bool want_staged =
-      use_staged() && allow_persistent && d.a_mode == 0 && d.block_k == 64 && d.block_n == 64 && d.splits <= 1 &&
+      use_staged() && allow_persistent && d.a_mode == 0 && (d.block_k == 64 || d.block_k == 32) && d.block_n == 64 && d.splits <= 1 &&
       (out_lin || (out_shuf && d.shuf_c == 64 && d.cout_pad == 256)) && !d.out_f32 && !d.out_preact && !d.bwd_z && !d.bnr_x &&
       !d.stats_partial && !d.dalpha_partial && !d.res2 && d.bnf_mode != 1 && !d.bnr_apply && !d.trace && p.debug == 0 &&
       d.group_rows == 0 && d.os_w % 8 == 0 && d.os_h % 8 == 0 && d.os_n % 8 == 0 && d.out_ch_off % 8 == 0 &&

@@ -726,7 +726,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
     // shared memory behind the operand ring: staging buffers of the staged epilogue / the OUT_GATHER_W tile
     const uint32_t extra = ring + static_cast<uint32_t>(p.stages) * p.stage_bytes;
     bool staged_done = false;
-    if constexpr (PERS && FAST) {
+    if constexpr (PERS) {   // (both instantiations: the 3-channel first layers run the K=32 non-FAST main loop)
       if (p.staged) {
         // ---- staged epilogue (conv_params.h): 64-column N tile, this warp owns 32 rows x 32 columns of it. One
         // tcgen05.ld + one wait per tile, the TMEM stage goes back to the MMA warp before any arithmetic, the bf16 tile
