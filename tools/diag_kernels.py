@@ -16,6 +16,19 @@ import eltwise_checks as E  # noqa: E402
 import kernel_checks as K  # noqa: E402
 from torchsr_b200 import _lib as L  # noqa: E402
 
+def _env(name, value, fn):
+    """Runs fn() with an environment switch set (the C side reads its switches when a descriptor is built)."""
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+
+
 CHECKS = [
     ("layout", lambda: E.check_layout()),
     ("im2row_3x3", lambda: E.check_im2row()),
@@ -52,6 +65,14 @@ CHECKS = [
     ("conv3x3_c16", lambda: K.check_conv_fwd(Cin=16, Cout=64)),
     ("conv3x3_128_256", lambda: K.check_conv_fwd(Cin=128, Cout=256, H=12, W=12)),
     ("conv3x3_512", lambda: K.check_conv_fwd(Cin=512, Cout=512, H=6, W=6)),
+    # activation multicast across clusters of two N tiles (tiles_n even, M % 128 == 0, >= 18 K iterations)
+    ("conv3x3_cluster_128_256", lambda: _env("TSR_CONV_CLUSTER", "1", lambda: K.check_conv_fwd(Cin=128, Cout=256, H=16, W=16))),
+    ("conv3x3_cluster_256_512_epi", lambda: _env("TSR_CONV_CLUSTER", "1", lambda: K.check_conv_fwd(
+        B=4, Cin=256, Cout=512, H=8, W=8, bias=True, act=L.ACT_LEAKY, stats=True))),
+    ("conv3x3_cluster_s2", lambda: _env("TSR_CONV_CLUSTER", "1", lambda: K.check_conv_fwd(
+        Cin=128, Cout=256, H=32, W=32, stride=2, stats=True))),
+    ("conv3x3_cluster_n64_res", lambda: _env("TSR_CONV_CLUSTER", "1", lambda: K.check_conv_fwd(
+        B=8, Cin=128, Cout=128, H=16, W=16, block_n=64, residual=True, repeat=3))),
     ("conv3x3_splitk", lambda: K.check_conv_fwd(Cin=256, Cout=256, H=12, W=12, splits=6, bias=True, act=L.ACT_LEAKY,
                                                 stats=True, repeat=2)),
     ("conv3x3_splitk_odd", lambda: K.check_conv_fwd(B=3, H=13, W=10, Cin=128, Cout=64, splits=4, residual=True,

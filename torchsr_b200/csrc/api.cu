@@ -168,7 +168,15 @@ int persistent_min_tiles_x10() {
   return v;
 }
 
-int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = true) {
+// Activation multicast across clusters of two N tiles: parity-tested, but measured neutral (x0.94 - x1.04 on the VGG /
+// discriminator layers with 128-512 input channels, tools/microbench_cluster.py: those launches already run at
+// 0.9-1.2 PFLOP/s and are not bound by their L2 -> SM traffic), so it is opt-in: TSR_CONV_CLUSTER=1.
+bool use_cluster() {
+  const char* e = getenv("TSR_CONV_CLUSTER");
+  return e && e[0] == '1';
+}
+
+int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = true, bool allow_cluster = true) {
   using namespace tsr;
   if (int e = ensure_init()) return e;
   // the fused training BatchNorm keeps every tile's accumulator in TMEM across a grid barrier: one tile per CTA
@@ -493,10 +501,22 @@ epilogue_params:
     p.staged = 1;
     p.extra_bytes = 2 * 16384;
   }
+  // Activation multicast across clusters of two N tiles (conv_params.h): one-tile FAST kernels whose K loop is long
+  // enough to be bound by the per-SM L2 -> SM traffic (at least 18 K iterations: 128 input channels), plain epilogues.
+  p.cluster_n = 1;
+  if (use_cluster() && allow_cluster && !p.persistent && d.a_mode == 0 && d.block_k == 64 && !d.trace && p.debug == 0 &&
+      splits == 1 && L->tiles_n % 2 == 0 && p.M_total % kBlockM == 0 && d.bnf_mode != 1 && !d.bnr_apply &&
+      total_iters >= 18) {
+    if (int e2 = encode_im2col(&p.tmA2, d.x, d.N, d.H, d.W, d.C, d.x_ld, d.lower_h, d.lower_w, d.upper_h, d.upper_w,
+                               d.stride, d.block_k, 64))
+      return e2;
+    p.cluster_n = 2;
+  }
   if (const char* v = getenv("TSR_CONV_VERBOSE"); v && v[0] == '1' && d.a_mode == 0)
     fprintf(stderr, "[tsr] conv M=%d C=%lld taps=%d block_n=%d tiles_n=%d persistent=%d halo=%d (th=%d pw=%d) staged=%d stages=%d "
-            "stage_bytes=%u b_res=%u extra=%u out_mode=%d\n", p.M_total, (long long)d.C, p.num_taps, d.block_n, L->tiles_n,
-            p.persistent, p.halo, p.halo_th, p.halo_pw, p.staged, p.stages, p.stage_bytes, p.b_res_bytes, p.extra_bytes, d.out_mode);
+            "stage_bytes=%u b_res=%u extra=%u out_mode=%d cluster=%d\n", p.M_total, (long long)d.C, p.num_taps, d.block_n, L->tiles_n,
+            p.persistent, p.halo, p.halo_th, p.halo_pw, p.staged, p.stages, p.stage_bytes, p.b_res_bytes, p.extra_bytes, d.out_mode,
+            p.cluster_n);
   if (e.bnr_apply && (!e.bnr_x || !e.bnr_dx || !e.bnr_coef || !e.bnr_gamma || !e.bnf_counter || e.bnr_count < 1 || splits != 1 ||
                       p.persistent || d.out_f32 || d.out_mode != TSR_OUT_LINEAR || e.bnf_mode))
     return fail(-20, "fused BatchNorm-backward apply needs bnr_x, bnr_coef, bnr_gamma, bnf_counter, bnr_count, a linear "
@@ -893,7 +913,7 @@ int tsr_prog_add_conv_group(tsr_prog_t* p, const tsr_conv_desc_t* descs, int n) 
   grp.n = n;
   for (int k = 0; k < n; ++k) {
     ConvLaunch L;
-    if (int e = build_conv(descs[k], &L, false)) return e;
+    if (int e = build_conv(descs[k], &L, false, false)) return e;
     if (L.p.a_mode != 0 || L.splits != 1) return fail(-20, "conv group members must be unsplit im2col convs");
     if ((descs[k].bnr_apply != 0) != (descs[0].bnr_apply != 0) ||
         (descs[k].bnr_apply && k > 0 && (L.p.M_total != grp.g.p[0].M_total || L.tiles_n != grp.g.tiles_n[0])))

@@ -177,7 +177,7 @@ __device__ __forceinline__ bool grid_arrive_and_wait(unsigned int* counter, unsi
 template <int A_MODE, bool PERS, bool FAST>
 __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_b,
                                               uint32_t b_res, uint32_t ring, int tile_n, int it_begin, int it_end,
-                                              int tiles_m, long long* trace) {
+                                              int tiles_m, long long* trace, int mc_rank) {
   constexpr bool pers = PERS;
   const int stages = p.stages;
   const uint32_t stage_bytes = p.stage_bytes, a_bytes = p.a_bytes, b_bytes = p.b_bytes;
@@ -261,7 +261,8 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
       }
       continue;
     }
-    const int m0 = tile_m * kBlockM;
+    // activation multicast (ConvParams::cluster_n): this CTA fetches the 64 pixels [m0 + 64 * rank, + 64) of the box
+    const int m0 = tile_m * kBlockM + (mc_rank >= 0 ? 64 * mc_rank : 0);
     int w0 = 0, h0 = 0, n0 = 0;
     if (A_MODE == 0) {
       const int hw = p.Ho * p.Wo;
@@ -287,6 +288,7 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
       const uint32_t sbytes = in_reg(stage_bytes), txr = in_reg(tx), abytes = in_reg(a_bytes);
       const uint32_t b_tap_rows = in_reg(static_cast<uint32_t>(p.b_rows_per_tap));
       const int c_first = static_cast<int>(in_reg(static_cast<uint32_t>(p.a_c0)));
+      const uint32_t mc_half = mc_rank > 0 ? (abytes >> 1) : 0u;
       int n_pre = first_tile ? pre : 0;
       uint32_t ukc = static_cast<uint32_t>(kc);
       int cA = c_first + kc * 64, cB = kc * 64;
@@ -297,7 +299,10 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
         if (!mbar_wait(empty, ph, p.epi.err, 1)) return;
         if (leader) {
           if (PERS || n_pre <= 0) mbar_arrive_expect_tx(full, txr);
-          tma_load_im2col_4d(dst, &p.tmA, full, cA, w0, h0, n0, offs & 0xFF, offs >> 8);
+          if (!PERS && mc_rank >= 0)
+            tma_load_im2col_4d_mc(dst + mc_half, &p.tmA2, full, cA, w0, h0, n0, offs & 0xFF, offs >> 8, 3);
+          else
+            tma_load_im2col_4d(dst, &p.tmA, full, cA, w0, h0, n0, offs & 0xFF, offs >> 8);
           if (!PERS && n_pre <= 0) tma_load_2d(dst + abytes, &p.tmB, full, cB, brow);
         }
         --n_pre;
@@ -385,7 +390,7 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
 template <int A_MODE, bool PERS, bool FAST>
 __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full, uint32_t bar_empty, uint32_t bar_acc_full,
                                          uint32_t bar_acc_empty, uint32_t bar_b, uint32_t b_res, uint32_t ring,
-                                         uint32_t tmem_base, int n_iters, int tiles_m, long long* trace) {
+                                         uint32_t tmem_base, int n_iters, int tiles_m, long long* trace, bool mc) {
   constexpr bool pers = PERS;
   const int stages = p.stages;
   const uint32_t ksteps = p.ksteps, idesc = p.idesc;
@@ -498,7 +503,12 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
       for (int it = 0; it < n_iters; ++it) {
         if (!mbar_wait(full, ph, p.epi.err, 2)) return;
         tc_fence_after();
-        if (leader) umma_bf16_x4_commit(d_tmem, ad, bd, idesc_r, acc, empty);
+        if (leader) {
+          if (!PERS && mc)
+            umma_bf16_x4_commit_mc(d_tmem, ad, bd, idesc_r, acc, empty, 3);   // frees the stage in both CTAs of the pair
+          else
+            umma_bf16_x4_commit(d_tmem, ad, bd, idesc_r, acc, empty);
+        }
         acc = 1;
         ad += st16;
         bd += pers ? b16r : st16;
@@ -587,13 +597,14 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
   const int it_begin = zsplit * p.iters_per_split;
   const int it_end = min(total_iters, it_begin + p.iters_per_split);
 
+  const bool mc = !PERS && FAST && A_MODE == 0 && p.cluster_n == 2;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(mc ? &p.tmA2 : &p.tmA);
     tma_prefetch_desc(&p.tmB);
     const int stages = p.stages;
     for (int s = 0; s < stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, mc ? 2 : 1);   // multicast stages are released by both CTAs' MMA warps
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_acc_full + 8 * a, 1);
@@ -611,13 +622,16 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   if (trace && threadIdx.x == 0) trace[1] = clock64();
+  // the peer CTA multicasts into this CTA's ring and arrives on its barriers: both must have initialised them first
+  if (mc) cluster_sync_all();
 
   if (warp == 0) {
-    producer_role<A_MODE, PERS, FAST>(p, bar_full, bar_empty, bar_b, b_res, ring, tile_n, it_begin, it_end, tiles_m, trace);  // pdl_sync() inside
+    producer_role<A_MODE, PERS, FAST>(p, bar_full, bar_empty, bar_b, b_res, ring, tile_n, it_begin, it_end, tiles_m, trace,
+                                      mc ? static_cast<int>(cluster_ctarank()) : -1);  // pdl_sync() inside
   } else if (warp == 1) {
     pdl_sync();
     mma_role<A_MODE, PERS, FAST>(p, bar_full, bar_empty, bar_acc_full, bar_acc_empty, bar_b, b_res, ring, tmem_base,
-                     it_end - it_begin, tiles_m, trace);
+                     it_end - it_begin, tiles_m, trace, mc);
   } else {
     pdl_sync();   // the epilogue reads residuals / statistics buffers written by earlier kernels of the stream
     if (trace && threadIdx.x == 64) trace[2] = clock64();
@@ -1710,6 +1724,8 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
 
   tc_fence_before();
   __syncthreads();
+  // the peer's last multicast commits still arrive on this CTA's barriers: leave together
+  if (mc) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -1814,20 +1830,21 @@ static int max_coresident(Kernel kernel, size_t smem, int tmem_cols, int* per_sm
 // One launch path for every instantiation: raises the dynamic shared-memory limit of `kernel` once, then launches.
 template <typename Kernel, typename Params>
 static cudaError_t launch_conv_kernel(Kernel kernel, bool* attr_set, dim3 grid, size_t smem, cudaStream_t stream, bool pdl,
-                                      const Params& params) {
+                                      const Params& params, int cluster_y = 1) {
   if (!*attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     *attr_set = true;
   }
-  cudaError_t e = launch_k(kernel, grid, dim3(kConvThreads), smem, stream, pdl, params);
+  cudaError_t e = launch_kc(kernel, grid, dim3(kConvThreads), smem, stream, pdl, cluster_y, params);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 template <int A_MODE, bool FAST>
 static cudaError_t launch_mode(const ConvParams& p, dim3 grid, size_t smem, cudaStream_t stream, bool pdl) {
   static bool attr_set = false;
-  return launch_conv_kernel(conv_igemm_kernel<A_MODE, FAST>, &attr_set, grid, smem, stream, pdl, p);
+  return launch_conv_kernel(conv_igemm_kernel<A_MODE, FAST>, &attr_set, grid, smem, stream, pdl, p,
+                            (A_MODE == 0 && FAST && p.cluster_n == 2) ? 2 : 1);
 }
 
 cudaError_t launch_conv_group(const ConvGroup& g, int n, cudaStream_t stream, bool pdl) {

@@ -115,6 +115,7 @@ struct EpiParams {
 struct ConvParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmA2;     // cluster_n == 2: im2col map with 64-pixel boxes (each CTA of the pair fetches half of the A box)
   CUtensorMap tmO[4];   // staged epilogue: output map(s), one per PixelShuffle sub-pixel block (linear stores use [0])
   EpiParams epi;
   int M_total;     // rows of the implicit GEMM (N*Ho*Wo traversal positions)
@@ -156,6 +157,12 @@ struct ConvParams {
   // are compacted (the two discarded positions per patch row are skipped), so the box is th x (pw-2) pixels.
   int staged;
   uint32_t extra_bytes;  // shared memory behind the operand ring: staging buffers (staged) or the OUT_GATHER_W tile
+  // Activation multicast (one-tile FAST kernels, tiles_n even, M a multiple of 128): the launch runs clusters of two
+  // CTAs along N - same M tile, neighbouring N tiles. Both need the same 128-pixel x 64-channel activation box per K
+  // iteration: each fetches 64 pixels of it and multicasts them into both CTAs' ring stage, so the per-CTA L2 -> SM
+  // traffic of an iteration drops from A + B to A/2 + B (the deep layers are bound by exactly that traffic). A stage is
+  // recycled when both CTAs' MMA warps have consumed it (multicast tcgen05.commit onto both `empty` barriers).
+  int cluster_n;   // 1 or 2
   int w_static;    // the B operand is not written by any kernel of the enclosing stream segment (real weights)
   int debug;       // attribution experiments only (TSR_CONV_DEBUG bits, tools/trace_conv.py), 0 in production: 1 = the
                    // epilogue skips the accumulator read-out and the stores, 2 = it computes but does not store,

@@ -108,6 +108,30 @@ __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async
 // ... have completed (their global writes are performed)
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ------------------------------------------------------------------ thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// Cluster-wide barrier (every thread of every CTA of the cluster executes both halves).
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// im2col load whose box lands at the same shared-memory offset of every CTA in `cta_mask` and signals the mbarrier at
+// the same offset in each of them (TMA multicast): the CTAs of a cluster that compute different N tiles of the same M
+// tile fetch the activation box once per cluster instead of once per CTA.
+__device__ __forceinline__ void tma_load_im2col_4d_mc(uint32_t dst, const void* map, uint32_t bar, int c, int w, int h,
+                                                      int n, uint16_t off_w, uint16_t off_h, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+      "[%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w),
+      "h"(off_h), "h"(cta_mask)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
@@ -148,6 +172,23 @@ __device__ __forceinline__ void umma_bf16_x4_commit(uint32_t tmem_d, uint64_t ad
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(bar), "l"(adesc + 2), "l"(bdesc + 2),
         "l"(adesc + 4), "l"(bdesc + 4), "l"(adesc + 6), "l"(bdesc + 6)
+      : "memory");
+}
+// The same with the commit arriving on the barrier at this offset in EVERY CTA of `cta_mask`: a ring stage that was
+// filled by multicast loads may only be refilled once all receiving CTAs have consumed it.
+__device__ __forceinline__ void umma_bf16_x4_commit_mc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                       uint32_t accumulate, uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %4, %4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %6, %7, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %8, %9, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %10, %11, %3, t;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %12;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(bar), "l"(adesc + 2), "l"(bdesc + 2),
+        "l"(adesc + 4), "l"(bdesc + 4), "l"(adesc + 6), "l"(bdesc + 6), "h"(cta_mask)
       : "memory");
 }
 // Same four steps without the commit (halo mode issues nine of these per stage, one per filter tap).
