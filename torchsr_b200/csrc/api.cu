@@ -300,29 +300,37 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
       stages = st;
     }
   }
-  // Halo mode on top of the persistent kernel (see conv_params.h): 3x3 / stride 1 / "same" convs on 64-channel chunks.
+  // Halo mode on top of the persistent kernel (see conv_params.h): stride-1 "same" convs with nine taps on 64-channel
+  // chunks - 3x3 (offsets up to (2, 2)) and the 9x1 tap column of the row-decomposed 9x9 output conv (offsets (kh, 0)).
   p.halo = 0;
   const int halo_env = halo_setting();
-  if ((halo_env == 1 || (halo_env < 0 && want_staged)) && use_persistent() && allow_persistent && d.a_mode == 0 && splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC &&
-      d.stride == 1 && d.num_taps == 9 && d.lower_h == -1 && d.lower_w == -1 && d.Ho == d.H && d.Wo == d.W &&
+  const bool gather_w = d.out_mode == TSR_OUT_GATHER_W;
+  int eh = 0, ew = 0;    // extent of the tap offsets
+  for (int t = 0; t < d.num_taps && t < kMaxTaps; ++t) {
+    eh = std::max(eh, static_cast<int>(d.tap_off[t] >> 8));
+    ew = std::max(ew, static_cast<int>(d.tap_off[t] & 0xFF));
+  }
+  if ((halo_env == 1 || (halo_env < 0 && (want_staged || gather_w))) && use_persistent() && allow_persistent && d.a_mode == 0 &&
+      splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && d.stride == 1 && d.num_taps == 9 && d.Ho == d.H && d.Wo == d.W &&
+      ((eh == 2 && ew == 2 && d.lower_h == -1 && d.lower_w == -1) || (eh == 8 && ew == 0 && d.lower_h == -4 && d.lower_w == 0)) &&
       d.block_k == 64 && (d.C - d.a_c0) % 64 == 0 && d.W >= 8 && d.H >= 4 && 2 * p.acc_cols <= 512) {
     bool taps_ok = true;
-    for (int t = 0; t < 9; ++t) taps_ok = taps_ok && (d.tap_off[t] >> 8) <= 2 && (d.tap_off[t] & 0xFF) <= 2;
-    // Strip geometry: a tile is th rows x (pw - 2) columns of one image, pw * th <= 128 accumulator rows. Pick the
-    // patch width that wastes the fewest accumulator rows, weighing in the bytes of the patch it has to fetch.
+    // Strip geometry: a tile is th rows x (pw - ew) columns of one image, pw * th <= 128 accumulator rows. Pick the
+    // patch width that wastes the fewest accumulator rows, weighing in the bytes of the patch it has to fetch. The
+    // OUT_GATHER_W epilogue needs every warp's 32 accumulator rows to be 32 consecutive pixels: pw a multiple of 32.
     int pw = 0, th = 0, strips = 0, tiles_y = 0;
     {
       long best_tiles = 0;
-      const int max_pw = d.W + 2 < 128 ? static_cast<int>(d.W) + 2 : 128;
-      for (int cand = 6; cand <= max_pw; ++cand) {
-        const int sw = cand - 2;
+      const int max_pw = d.W + ew < 128 ? static_cast<int>(d.W) + ew : 128;
+      for (int cand = gather_w ? 32 : 6; cand <= (gather_w ? 128 : max_pw); cand += gather_w ? 32 : 1) {
+        const int sw = cand - ew;
         int c_th = 128 / cand;
         if (c_th > d.H) c_th = static_cast<int>(d.H);
-        if (c_th < 1) continue;
+        if (c_th < 1 || sw < 1) continue;
         const int c_strips = static_cast<int>((d.W + sw - 1) / sw);
         const int c_ty = static_cast<int>((d.H + c_th - 1) / c_th);
         // cost ~ tiles x (accumulator rows + 0.15 x patch positions): tile count first, patch traffic second
-        const long n_tiles = static_cast<long>(c_strips) * c_ty * (20 * 128 + 3 * (c_th + 2) * cand);
+        const long n_tiles = static_cast<long>(c_strips) * c_ty * (20 * 128 + 3 * (c_th + eh) * cand);
         if (pw == 0 || n_tiles <= best_tiles) {
           best_tiles = n_tiles;
           pw = cand;
@@ -332,10 +340,12 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
         }
       }
     }
+    if (pw == 0) taps_ok = false;
     const uint32_t b_bytes = static_cast<uint32_t>(d.block_n) * 64 * 2;
     const size_t b_res = static_cast<size_t>(total_iters) * b_bytes;
-    const uint32_t patch_tx = static_cast<uint32_t>((th + 2) * pw * 128);
-    const uint32_t patch_alloc = (static_cast<uint32_t>((128 + 2 * pw + 2) * 128) + 1023u) & ~1023u;
+    const uint32_t patch_tx = static_cast<uint32_t>((th + eh) * pw * 128);
+    // the last tap's 128-row operand window starts eh * pw + ew rows into the stage
+    const uint32_t patch_alloc = (static_cast<uint32_t>((128 + eh * pw + ew) * 128) + 1023u) & ~1023u;
     const size_t budget = 227 * 1024 - 1024 - kConvHeaderBytes - 1024 - smem_reserve;
     if (taps_ok && th >= 1 && b_res % 1024 == 0 && b_res + 2 * static_cast<size_t>(patch_alloc) <= budget) {
       const int tiles_per_img = strips * tiles_y;
@@ -348,7 +358,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
                             static_cast<cuuint64_t>(d.N)};
       cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.x_ld) * 2, static_cast<cuuint64_t>(d.x_ld) * 2 * d.W,
                                static_cast<cuuint64_t>(d.x_ld) * 2 * d.W * d.H};
-      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pw), static_cast<cuuint32_t>(th + 2), 1};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(pw), static_cast<cuuint32_t>(th + eh), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = g_encode_tiled(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.x), dims, strides, box,
                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -357,6 +367,9 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
       p.halo = 1;
       p.halo_th = th;
       p.halo_pw = pw;
+      p.halo_sw = pw - ew;
+      p.halo_lo_h = d.lower_h;
+      p.halo_lo_w = d.lower_w;
       p.halo_tiles_per_img = tiles_per_img;
       p.halo_strips = strips;
       p.halo_H = static_cast<int>(d.H);
@@ -470,7 +483,7 @@ epilogue_params:
   if (d.out_mode == TSR_OUT_GATHER_W) {
     if (d.a_mode != 0 || splits != 1 || L->tiles_n != 1 || !d.out_f32 || d.gather_k < 1 || d.gather_c < 1 ||
         d.gather_k * d.gather_c > d.block_n || d.gather_pad < 0 || d.gather_pad >= d.gather_k || d.out_preact || d.bias ||
-        d.res || d.bwd_z || d.bnr_x || d.stats_partial || d.bnf_mode || p.halo)
+        d.res || d.bwd_z || d.bnr_x || d.stats_partial || d.bnf_mode || (p.halo && p.halo_pw % 32))
       return fail(-20, "OUT_GATHER_W needs an unsplit im2col conv with one N tile, an fp32 NCHW output and a plain epilogue");
     if (d.gather_k != 9 || d.gather_c != 3 || d.gather_pad != 4 || d.block_n != 32)
       return fail(-20, "OUT_GATHER_W is implemented for the 9-tap, 3-channel, 32-column case (conv_igemm.cu:gather9x3)");
@@ -490,7 +503,7 @@ epilogue_params:
                               static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.N)};
         cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.os_w * mul) * 2, static_cast<cuuint64_t>(d.os_h * mul) * 2,
                                  static_cast<cuuint64_t>(d.os_n) * 2};
-        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.halo_pw - 2), static_cast<cuuint32_t>(p.halo_th), 1};
+        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.halo_sw), static_cast<cuuint32_t>(p.halo_th), 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = g_encode_tiled(&p.tmO[b], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides,
                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -238,8 +238,8 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
       const int n_img = tile_m / p.halo_tiles_per_img;
       const int t_img = tile_m - n_img * p.halo_tiles_per_img;
       const int t_y = t_img / p.halo_strips;
-      const int hrow0 = t_y * p.halo_th - 1;
-      const int wcol0 = (t_img - t_y * p.halo_strips) * (p.halo_pw - 2) - 1;
+      const int hrow0 = t_y * p.halo_th + p.halo_lo_h;
+      const int wcol0 = (t_img - t_y * p.halo_strips) * p.halo_sw + p.halo_lo_w;
       for (int kc = 0; kc < kc_per_tap; ++kc) {
         if (!mbar_wait(bar_empty + 8 * s, ph, p.epi.err, 1)) return;
         const uint32_t full = bar_full + 8 * s;
@@ -746,7 +746,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         // tcgen05.ld + one wait per tile, the TMEM stage goes back to the MMA warp before any arithmetic, the bf16 tile
         // leaves through a 128B-swizzled staging buffer and ONE bulk tensor store per tile.
         staged_done = true;
-        const int sw = p.halo ? p.halo_pw - 2 : 0;
+        const int sw = p.halo ? p.halo_sw : 0;
         const bool has_bias = bias != nullptr;
         const float rs = e.res_scale;
         const float sl = act == ACT_PRELU ? alpha : (act == ACT_LEAKY ? leaky : 0.f);
@@ -902,9 +902,9 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         const int t_y = t_img / p.halo_strips;
         const int orow = row / p.halo_pw;
         const int pos = row - orow * p.halo_pw;
-        wo = (t_img - t_y * p.halo_strips) * (p.halo_pw - 2) + pos;
+        wo = (t_img - t_y * p.halo_strips) * p.halo_sw + pos;
         ho = t_y * p.halo_th + orow;
-        valid = pos < p.halo_pw - 2 && wo < p.halo_W && orow < p.halo_th && ho < p.halo_H;
+        valid = pos < p.halo_sw && wo < p.halo_W && orow < p.halo_th && ho < p.halo_H;
         m = (n * p.halo_H + ho) * p.halo_W + wo;
       } else {
         const int hw = p.Ho * p.Wo;
@@ -1400,7 +1400,9 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           }
           // pixels just outside the warp's rows: lanes 0..3 -> first - 4 .. - 1, lanes 4..7 -> first + 32 .. + 35
           const int P = lane < 4 ? lane - 4 : 28 + lane;
-          const long long mo = static_cast<long long>(m0) + q * 32 + P;
+          // (m - lane = linear index of the warp's first pixel: the warp's 32 rows are 32 consecutive pixels of one
+          // image row, in im2col tiles and - patch width a multiple of 32 - in halo tiles alike)
+          const long long mo = static_cast<long long>(m) - lane + P;
           const bool ext = lane < 8 && mo >= 0 && mo < p.M_total;
           int rowid = 0, wcol = 0;
           if (ext) {

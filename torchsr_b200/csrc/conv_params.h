@@ -149,7 +149,11 @@ struct ConvParams {
   int halo_th, halo_pw;  // output rows per tile, patch positions per row (strip width + 2)
   int halo_tiles_per_img;
   int halo_H, halo_W;    // image size (output == input size)
-  int halo_strips;       // strips per image row: ceil(W / (halo_pw - 2))
+  int halo_strips;       // strips per image row: ceil(W / halo_sw)
+  // generalised geometry (the 9 x 1 tap column of the row-decomposed 9x9 output conv uses the same machinery): the
+  // patch is (halo_th + halo_eh) rows x halo_pw positions with origin (row0 + halo_lo_h, col0 + halo_lo_w), a tile
+  // keeps halo_sw = halo_pw - halo_ew positions per row; 3x3: eh = ew = 2, lo = -1; 9x1: eh = 8, ew = 0, lo = (-4, 0)
+  int halo_sw, halo_lo_h, halo_lo_w;
   // Staged epilogue (persistent FAST kernels, bf16 linear / PixelShuffle stores, 64-column N tiles): every epilogue warp
   // reads its whole share of the accumulator with one tcgen05.ld + wait, hands the TMEM stage back at once, and writes
   // the finished bf16 tile into a 128B-swizzled shared-memory buffer (double-buffered); one thread stores it with
