@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtorchsr_b200.so")
+LIB_PATH = os.environ.get("TSR_LIB_PATH") or os.path.join(_HERE, "lib", "libtorchsr_b200.so")   # override: A/B of two builds
 
 MAX_TAPS = 81
 OUT_LINEAR, OUT_SHUFFLE, OUT_UNSHUFFLE, OUT_GEMM_T_ATOMIC, OUT_GATHER_W = 0, 1, 2, 3, 4
