@@ -144,6 +144,13 @@ typedef struct tsr_conv_desc {
      One N tile (block_n == cout_pad >= gather_k*gather_c), no split-K; the out strides are not used. */
   const float* gather_bias;
   int32_t gather_k, gather_pad, gather_c, _pad4;
+  /* Nearest-neighbour x2 upsampling of the result (F.interpolate(scale_factor=2) in front of the ESRGAN upsample convs,
+     esrgan/generator.py:73,76) folded into the producer's store: besides `out`, every output pixel (ho, wo) is written
+     to the four positions (2ho + i, 2wo + j) of out_rep2x (bf16, strides in elements of the fine grid). Linear bf16
+     stores of im2col convs only. */
+  void* out_rep2x;
+  int64_t rep_n, rep_h, rep_w;
+  int32_t rep_ch_off, _pad5;
 } tsr_conv_desc_t;
 
 typedef struct tsr_wgrad_desc {

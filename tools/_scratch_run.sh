@@ -1,5 +1,4 @@
-for i in 1 2; do
-echo "prev"; TSR_LIB_PATH=$PWD/torchsr_b200/lib/lib_prev.so timeout 300 python tools/bench_infer.py 2>&1 | tail -1 | cut -c60-140
-echo "new";  timeout 300 python tools/bench_infer.py 2>&1 | tail -1 | cut -c60-140
-done
-nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_throttle_reasons.active --format=csv
+timeout 1200 python -m pytest tests -m gpu -q --timeout=600 -x -k "esrgan or dense" 2>&1 | tail -3
+timeout 600 python bench.py --only esrgan --steps 10 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('esrgan', d['esrgan']['value'], d['esrgan']['ms_per_step'])"

@@ -242,6 +242,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
       use_staged() && allow_persistent && d.a_mode == 0 && (d.block_k == 64 || d.block_k == 32) && d.block_n == 64 && d.splits <= 1 &&
       (out_lin || (out_shuf && d.shuf_c == 64 && d.cout_pad == 256)) && !d.out_f32 && !d.out_preact && !d.bwd_z && !d.bnr_x &&
       !d.stats_partial && !d.dalpha_partial && !d.res2 && d.bnf_mode != 1 && !d.bnr_apply && !d.trace && p.debug == 0 &&
+      !d.out_rep2x &&
       d.group_rows == 0 && d.os_w % 8 == 0 && d.os_h % 8 == 0 && d.os_n % 8 == 0 && d.out_ch_off % 8 == 0 &&
       reinterpret_cast<uintptr_t>(d.out) % 16 == 0 && d.n_valid % 8 == 0;
   const size_t smem_reserve = want_staged ? 2 * 16384 : 0;
@@ -474,6 +475,14 @@ epilogue_params:
   e.bnr_dbeta = d.bnr_dbeta;
   e.bnr_dalpha = d.bnr_dalpha;
   e.bnr_count = d.bnr_count;
+  e.out_rep2x = d.out_rep2x;
+  e.rep_n = d.rep_n;
+  e.rep_h = d.rep_h;
+  e.rep_w = d.rep_w;
+  e.rep_ch_off = d.rep_ch_off;
+  if (d.out_rep2x && (d.a_mode != 0 || d.out_mode != TSR_OUT_LINEAR || d.out_f32 || d.bnf_mode || d.bnr_apply || splits != 1 ||
+                      d.rep_ch_off % 8 || d.rep_n % 8 || d.rep_h % 8 || d.rep_w % 8))
+    return fail(-20, "out_rep2x needs an unsplit im2col conv with a linear bf16 store, no fused BatchNorm and 16-byte aligned strides");
   e.gather_bias = d.gather_bias;
   e.gather_k = d.gather_k;
   e.gather_pad = d.gather_pad;

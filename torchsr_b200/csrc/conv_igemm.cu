@@ -1567,6 +1567,14 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
               store_f32x16(out, off, v);
             else
               store_bf16x16(out, off, v);
+            if (A_MODE == 0 && e.out_rep2x != nullptr) {
+              // nearest x2 of the result (EpiParams::out_rep2x): the same 16 values to the 2 x 2 fine-grid positions
+              const long long rb = n * e.rep_n + (2 * ho) * e.rep_h + (2 * wo) * e.rep_w + e.rep_ch_off + col0;
+              store_bf16x16(e.out_rep2x, rb, v);
+              store_bf16x16(e.out_rep2x, rb + e.rep_w, v);
+              store_bf16x16(e.out_rep2x, rb + e.rep_h, v);
+              store_bf16x16(e.out_rep2x, rb + e.rep_h + e.rep_w, v);
+            }
           }
         }
         if (trace && threadIdx.x == 64 && ch < 4) trace[33 + 2 * ch] = clock64();

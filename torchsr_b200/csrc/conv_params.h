@@ -110,6 +110,10 @@ struct EpiParams {
   // the position adds the bias. Replaces a [M][block_n] fp32 round trip through HBM plus a gather kernel.
   const float* gather_bias;
   int gather_k, gather_pad, gather_c;
+  // nearest x2 of the result folded into the store: pixel (ho, wo) also goes to (2ho + i, 2wo + j) of out_rep2x
+  void* out_rep2x;
+  long long rep_n, rep_h, rep_w;
+  int rep_ch_off;
 };
 
 struct ConvParams {

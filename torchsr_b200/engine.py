@@ -381,7 +381,7 @@ class Plan:
     def conv_fwd(self, prog, rec: ConvRec, x: Act, out: Act, *, stats=None, act=L.ACT_NONE, prelu=None, preact=None,
                  res: Optional[Act] = None, res2: Optional[Act] = None, res_scale=1.0, res2_scale=1.0, acc_scale=1.0,
                  out_f32=False, shuffle_out=False, use_bias=True, group_rows=0, bnf: Optional[dict] = None,
-                 dry_add=True):
+                 dry_add=True, rep2x: Optional[Act] = None):
         """Forward of a 'std' conv (any stride) into `out` (OUT_LINEAR or PixelShuffle store), with the fused epilogue
         v = (acc + bias) * acc_scale + res * res_scale + res2 * res2_scale, optional activation, optional statistics.
         `x` / `out` / `res` may be channel slices of wider NHWC buffers (ld, c0)."""
@@ -403,6 +403,9 @@ class Plan:
             kw.update(group_rows=group_rows)
         if bnf is not None:
             kw.update(bnf)
+        if rep2x is not None:       # nearest x2 of the result written by the same epilogue (esrgan/generator.py:73,76)
+            assert rep2x.H == 2 * geom["Ho"] and rep2x.W == 2 * geom["Wo"] and not shuffle_out
+            kw.update(rep2x=dict(t=rep2x.t, strides=rep2x.strides(), ch_off=rep2x.c0))
         tiles = self.pick_tiles(x.B * geom["Ho"] * geom["Wo"], rec.cout_pad, rec.block_n,
                                 len(geom["taps"]) * ((x.C) // ops.pick_block_k(x.C)))
         block_n = tiles.pop("block_n")

@@ -564,7 +564,12 @@ def define_esrgan_generator(m, plan: Plan, shape):
     # ---- conv2 + skip, two nearest-x2 upsample stages, conv3 + LeakyReLU, conv4
     r2 = R["conv2"]
     s = plan.act("trunk", B, H, W, C)
-    plan.conv_fwd(fwd, r2, trunk, s, res=c1)
+    # F.interpolate(scale_factor=2) in front of upsample1 / upsample2 (esrgan/generator.py:73,76) is folded into the
+    # PRODUCER's store: conv2 and upsample1 write every output pixel to the 2 x 2 positions of the next conv's input as
+    # well (out_rep2x) - no upsample kernel, no extra read of the low-resolution tensor
+    ups_in = {"upsample1": plan.act("upsample1.in", B, 2 * H, 2 * W, C),
+              "upsample2": plan.act("upsample2.in", B, 4 * H, 4 * W, C)}
+    plan.conv_fwd(fwd, r2, trunk, s, res=c1, rep2x=ups_in["upsample1"])
 
     def bwd_conv2(bp, g, want_x, want_w):
         # g: gradient w.r.t. s = conv1 + conv2(trunk), living in a 192-wide buffer; it also reaches conv1
@@ -579,10 +584,9 @@ def define_esrgan_generator(m, plan: Plan, shape):
     prev, h, w = s, H, W
     for name in ("upsample1", "upsample2"):
         rec = R[name]
-        up = plan.act(name + ".in", B, 2 * h, 2 * w, C)
-        fwd.add(ops.elt(L.E_UPSAMPLE2X, p=[prev.t, up.t], i=[B, h, w, C, prev.ld, C]))
+        up = ups_in[name]
         out = plan.act(name + ".out", B, 2 * h, 2 * w, C)
-        plan.conv_fwd(fwd, rec, up, out, act=L.ACT_LEAKY)
+        plan.conv_fwd(fwd, rec, up, out, act=L.ACT_LEAKY, rep2x=ups_in["upsample2"] if name == "upsample1" else None)
         first = name == "upsample1"
 
         def bwd_up(bp, g, want_x, want_w, rec=rec, up=up, out=out, h=h, w=w, name=name, first=first):

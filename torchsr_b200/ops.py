@@ -125,7 +125,7 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
               res_scale=1.0, res2_scale=1.0, res_cols=0, w_static=True, bnr_x=None, bnr_coef=None, bnr_prelu=None,
               bnr_act=L.ACT_NONE, bnr_c=0, splits=1, ws=None, tile_counters=None, ws_ld=0, group_rows=0, bnf_mode=0,
               bnf_c=0, bnf_counter=None, bnf_gamma=None, bnf_beta=None, bnf_rm=None, bnf_rv=None, bnf_nbt=None,
-              bnf_coef=None, bnf_count=0, bnf_eps=1e-5, bnf_momentum=0.1, gather=None) -> ConvDesc:
+              bnf_coef=None, bnf_count=0, bnf_eps=1e-5, bnf_momentum=0.1, gather=None, rep2x=None) -> ConvDesc:
     d = ConvDesc()
     d.x, d.w = ptr(x), ptr(w)
     d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
@@ -155,6 +155,10 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     d.bnf_counter, d.bnf_gamma, d.bnf_beta = ptr(bnf_counter), ptr(bnf_gamma), ptr(bnf_beta)
     d.bnf_rm, d.bnf_rv, d.bnf_nbt, d.bnf_coef = ptr(bnf_rm), ptr(bnf_rv), ptr(bnf_nbt), ptr(bnf_coef)
     d.bnf_eps, d.bnf_momentum = bnf_eps, bnf_momentum
+    if rep2x is not None:       # dict(t, strides (n, h, w) of the x2 grid, ch_off): nearest x2 copy of the result
+        d.out_rep2x = ptr(rep2x["t"])
+        d.rep_n, d.rep_h, d.rep_w = rep2x["strides"]
+        d.rep_ch_off = rep2x.get("ch_off", 0)
     if gather is not None:      # dict(k, pad, c, bias): OUT_GATHER_W, `out` is the zero-initialised fp32 NCHW result
         d.out_mode, d.out_f32 = L.OUT_GATHER_W, 1
         d.gather_k, d.gather_pad, d.gather_c, d.gather_bias = gather["k"], gather["pad"], gather["c"], ptr(gather.get("bias"))
@@ -297,6 +301,11 @@ def validate_conv(d: ConvDesc):
             _need("conv out", d.out, (last + d.out_ch_off + span) * esz)
         if d.out_preact:
             _need("conv out_preact", d.out_preact, (last + d.out_ch_off + span) * 2)
+        if d.out_rep2x:
+            if d.out_mode != L.OUT_LINEAR or d.out_f32 or d.bnf_mode or d.bnr_apply or d.splits > 1:
+                raise ExtentError("out_rep2x: linear bf16 store of an unsplit conv without fused BatchNorm only")
+            rep_last = (d.N - 1) * d.rep_n + (2 * d.Ho - 1) * d.rep_h + (2 * d.Wo - 1) * d.rep_w
+            _need("conv out_rep2x", d.out_rep2x, (rep_last + d.rep_ch_off + d.n_valid) * 2)
         rc = min(d.n_valid, d.res_cols) if d.res_cols > 0 else d.n_valid
         for name, p, cols in (("res", d.res, rc), ("res2", d.res2, rc), ("bwd_z", d.bwd_z, d.n_valid),
                               ("bnr_x", d.bnr_x, d.n_valid)):
