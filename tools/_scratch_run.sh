@@ -1,4 +1,5 @@
-timeout 1200 python -m pytest tests -m gpu -q --timeout=600 -x -k "esrgan or dense" 2>&1 | tail -3
-timeout 600 python bench.py --only esrgan --steps 10 --warmup 3 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('esrgan', d['esrgan']['value'], d['esrgan']['ms_per_step'])"
+TSR_LIB_PATH=$PWD/torchsr_b200/lib/lib_prev.so timeout 120 python tools/microbench_epilogue.py 2>&1 | tail -1
+timeout 120 python tools/microbench_epilogue.py 2>&1 | tail -1
+TSR_LIB_PATH=$PWD/torchsr_b200/lib/lib_prev.so timeout 300 python tools/bench_infer.py 2>&1 | tail -1 | cut -c60-140
+timeout 300 python tools/bench_infer.py 2>&1 | tail -1 | cut -c60-140
+timeout 900 python -m pytest tests -m gpu -q --timeout=600 -x -k "generator or golden or eval_mode or c1_fixture or large_image or kernel or vgg or discriminator" 2>&1 | tail -2

@@ -19,6 +19,7 @@
 // (torchsr/srgan/generator.py:38-58, residual.py:27,64,67, discriminator.py:31-69 and the esrgan twins).
 #include <algorithm>
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 #include "conv_params.h"
 #include "launch.h"
@@ -820,43 +821,73 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);   // the MMA warp may start tile j+2 now
           uint32_t pk[16];
+          // The arithmetic of the 32 columns, instantiated per (eval-BatchNorm | plain, activation kind, residual): with
+          // the mode tests inside the element loop the section cost 1 500 - 2 900 clk per tile (tools/
+          // microbench_epilogue.py: skipping it halved the launch) - uniform, but evaluated and branched on per element
+          // by two warps per scheduler with nothing to hide the latency behind.
+          auto math = [&](auto bn_c, auto act_c, auto res_c) {
+            constexpr bool BN = decltype(bn_c)::value;
+            constexpr int ACT = decltype(act_c)::value;      // 0 none, 1 slope (PReLU / LeakyReLU), 2 ReLU
+            constexpr bool RES = decltype(res_c)::value;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
-            float z0 = 0.f, z1 = 0.f;
+            for (int i4 = 0; i4 < 8; ++i4) {
+              float x[4], z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) x[k] = __uint_as_float(r[4 * i4 + k]);
+              if (RES) {
+                const uint4 qq = rq[i4 >> 1];
+                unpack_bf16x2((i4 & 1) ? qq.z : qq.x, z[0], z[1]);
+                unpack_bf16x2((i4 & 1) ? qq.w : qq.y, z[2], z[3]);
+              }
+              if (BN) {        // y = act(BN(acc)) + res
+                const float4 sc4 = *reinterpret_cast<const float4*>(s_sc + c_lo + 4 * i4);
+                const float4 sh4 = *reinterpret_cast<const float4*>(s_sh + c_lo + 4 * i4);
+                x[0] = x[0] * sc4.x + sh4.x;
+                x[1] = x[1] * sc4.y + sh4.y;
+                x[2] = x[2] * sc4.z + sh4.z;
+                x[3] = x[3] * sc4.w + sh4.w;
+              } else {         // y = act((acc + bias) * acc_scale + res)
+                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c_lo + 4 * i4);   // zeros without a bias
+                x[0] = (x[0] + b4.x) * acc_scale;
+                x[1] = (x[1] + b4.y) * acc_scale;
+                x[2] = (x[2] + b4.z) * acc_scale;
+                x[3] = (x[3] + b4.w) * acc_scale;
+                if (RES) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) x[k] += z[k] * rs;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (ACT == 2) x[k] = fmaxf(x[k], 0.f);
+                if (ACT == 1) x[k] = x[k] > 0.f ? x[k] : x[k] * sl;
+              }
+              if (BN && RES) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] += z[k] * rs;
+              }
+              pk[2 * i4] = pack_bf16x2(x[0], x[1]);
+              pk[2 * i4 + 1] = pack_bf16x2(x[2], x[3]);
+            }
+          };
+          using T = std::true_type;
+          using F = std::false_type;
+          using A0 = std::integral_constant<int, 0>;
+          using A1 = std::integral_constant<int, 1>;
+          using A2 = std::integral_constant<int, 2>;
+          const int act_kind = act == ACT_NONE ? 0 : (act == ACT_RELU ? 2 : 1);
+          if (bnf == 2) {
             if (has_res) {
-              const uint4 qq = rq[i >> 3];
-              const uint32_t w = ((i >> 1) & 3) == 0 ? qq.x : (((i >> 1) & 3) == 1 ? qq.y : (((i >> 1) & 3) == 2 ? qq.z : qq.w));
-              unpack_bf16x2(w, z0, z1);
+              if (act_kind == 0) math(T{}, A0{}, T{}); else if (act_kind == 1) math(T{}, A1{}, T{}); else math(T{}, A2{}, T{});
+            } else {
+              if (act_kind == 0) math(T{}, A0{}, F{}); else if (act_kind == 1) math(T{}, A1{}, F{}); else math(T{}, A2{}, F{});
             }
-            if (bnf == 2) {        // y = act(BN(acc)) + res
-              x0 = x0 * s_sc[c_lo + i] + s_sh[c_lo + i];
-              x1 = x1 * s_sc[c_lo + i + 1] + s_sh[c_lo + i + 1];
-              if (act == ACT_RELU) {
-                x0 = fmaxf(x0, 0.f);
-                x1 = fmaxf(x1, 0.f);
-              } else if (act != ACT_NONE) {
-                x0 = x0 > 0.f ? x0 : x0 * sl;
-                x1 = x1 > 0.f ? x1 : x1 * sl;
-              }
-              x0 += z0 * rs;
-              x1 += z1 * rs;
-            } else {               // y = act((acc + bias) * acc_scale + res)
-              if (has_bias) {
-                x0 += s_bias[c_lo + i];
-                x1 += s_bias[c_lo + i + 1];
-              }
-              x0 = x0 * acc_scale + z0 * rs;
-              x1 = x1 * acc_scale + z1 * rs;
-              if (act == ACT_RELU) {
-                x0 = fmaxf(x0, 0.f);
-                x1 = fmaxf(x1, 0.f);
-              } else if (act != ACT_NONE) {
-                x0 = x0 > 0.f ? x0 : x0 * sl;
-                x1 = x1 > 0.f ? x1 : x1 * sl;
-              }
+          } else {
+            if (has_res) {
+              if (act_kind == 0) math(F{}, A0{}, T{}); else if (act_kind == 1) math(F{}, A1{}, T{}); else math(F{}, A2{}, T{});
+            } else {
+              if (act_kind == 0) math(F{}, A0{}, F{}); else if (act_kind == 1) math(F{}, A1{}, F{}); else math(F{}, A2{}, F{});
             }
-            pk[i >> 1] = pack_bf16x2(x0, x1);
           }
           const uint32_t sbuf = extra + static_cast<uint32_t>(jj & 1) * 16384u;
           if (valid) {
