@@ -503,9 +503,13 @@ def test_large_image_inference_staged_halo_paths_match_oracle_and_generic_kernel
         G2.load_state_dict(sd)
         y_old = G2.cuda().eval()(x.cuda()).cpu()
     assert y_new.shape == (1, 3, 640, 768)
-    assert MC.rel_l2(y_new, ref) <= 3e-2, MC.rel_l2(y_new, ref)
-    # same bf16 store points, same fp32 accumulation per tile: only the tile shapes differ
-    assert MC.rel_l2(y_new, y_old) <= 2e-3, MC.rel_l2(y_new, y_old)
+    e_new, e_old, d = MC.rel_l2(y_new, ref), MC.rel_l2(y_old, ref), MC.rel_l2(y_new, y_old)
+    print("large-image inference vs oracle: staged/halo/in-place", e_new, "generic kernels", e_old, "between them", d)
+    assert e_new <= 3e-2 and e_old <= 3e-2, (e_new, e_old)
+    # same bf16 store points and fp32 accumulation per tile, except that the in-place residual blocks of the inference
+    # plan add their tile to the block input in global memory (bulk reduce store): the tile is rounded to bf16 before
+    # the add, the generic path adds in fp32 and rounds once - one extra 2^-9 rounding of the branch per block
+    assert d <= 1e-2 and e_new <= 1.25 * e_old + 2e-3, (e_new, e_old, d)
 
 
 def test_upscale_pipelined_equals_sequential_upscale():

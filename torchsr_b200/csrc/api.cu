@@ -522,6 +522,17 @@ epilogue_params:
     }
     p.staged = 1;
     p.extra_bytes = 2 * 16384;
+    // in-place residual (res aliases out element for element, added last with scale 1): the bulk store adds
+    const bool res_inplace = d.res && out_lin && d.act == TSR_ACT_NONE && d.res_scale == 1.f &&
+                             reinterpret_cast<const char*>(d.res) + static_cast<int64_t>(d.aux_ch_off) * 2 ==
+                                 reinterpret_cast<const char*>(d.out) + static_cast<int64_t>(d.out_ch_off) * 2 &&
+                             d.aux_n == d.os_n && d.aux_h == d.os_h && d.aux_w == d.os_w &&
+                             (d.res_cols <= 0 || d.res_cols >= d.n_valid) && d.n_valid % 64 == 0;
+    static const bool reduce_on = [] {
+      const char* e = getenv("TSR_RES_REDUCE");
+      return !(e && e[0] == '0');
+    }();
+    p.res_reduce = (res_inplace && reduce_on) ? 1 : 0;
   }
   // Activation multicast across clusters of two N tiles (conv_params.h): one-tile FAST kernels whose K loop is long
   // enough to be bound by the per-SM L2 -> SM traffic (at least 18 K iterations: 128 input channels), plain epilogues.

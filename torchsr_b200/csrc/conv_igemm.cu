@@ -754,7 +754,8 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
         const int c_lo = half * 32;
         const long long aux_n = e.aux_n, aux_h = e.aux_h, aux_w = e.aux_w;
         const int aux_c = e.aux_ch_off + colbase + c_lo;
-        const bool res_cols_ok = res != nullptr && colbase + c_lo < e.res_cols;
+        const bool res_reduce = p.res_reduce != 0;     // the bulk store adds the tile to the residual already in `out`
+        const bool res_cols_ok = res != nullptr && !res_reduce && colbase + c_lo < e.res_cols;
         const int row = q * 32 + lane;
         const bool shuf = out_mode == OUT_SHUFFLE;
         // tile -> (image, output pixel of this thread's accumulator row, its row in the staging buffer, box origin)
@@ -903,10 +904,16 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           if (threadIdx.x == 64) bulk_wait_group_read0();
           named_bar_sync(1, kConvThreads - 64);
           if (threadIdx.x == 64) {
-            if (p.halo)
+            if (res_reduce) {
+              if (p.halo)
+                tma_reduce_add_4d(&p.tmO[0], sbuf, colbase, w0, h0, n);
+              else
+                tma_reduce_add_2d(&p.tmO[0], sbuf, colbase, tile_m * kBlockM);
+            } else if (p.halo) {
               tma_store_4d(&p.tmO[shuf ? tile_n : 0], sbuf, shuf ? 0 : colbase, w0, h0, n);
-            else
+            } else {
               tma_store_2d(&p.tmO[0], sbuf, colbase, tile_m * kBlockM);
+            }
             bulk_commit_group();
           }
           tg = tg_next;

@@ -164,6 +164,9 @@ struct ConvParams {
   // cp.async.bulk.tensor (tmO) - full 128-byte lines instead of 32 half-sector stores per warp instruction. Halo tiles
   // are compacted (the two discarded positions per patch row are skipped), so the box is th x (pw-2) pixels.
   int staged;
+  int res_reduce;        // staged epilogue, residual == output buffer (y = x + f(..) written in place, res_scale 1, no
+                         // activation after the add): the tile is ADDED to global memory by the bulk store
+                         // (cp.reduce.async.bulk.tensor .add) instead of loading x into registers first
   uint32_t extra_bytes;  // shared memory behind the operand ring: staging buffers (staged) or the OUT_GATHER_W tile
   // Activation multicast (one-tile FAST kernels, tiles_n even, M a multiple of 128): the launch runs clusters of two
   // CTAs along N - same M tile, neighbouring N tiles. Both need the same 128-pixel x 64-channel activation box per K

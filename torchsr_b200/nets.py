@@ -38,13 +38,15 @@ def srgan_generator_records(m) -> List[ConvRec]:
     return recs
 
 
-def residual_block_stage(plan: Plan, prog, name: str, blk, ra: ConvRec, rb: ConvRec, x: Act) -> Act:
-    """conv-BN-PReLU-conv-BN + x (torchsr/srgan/residual.py:86-91)."""
+def residual_block_stage(plan: Plan, prog, name: str, blk, ra: ConvRec, rb: ConvRec, x: Act, inplace: bool = False) -> Act:
+    """conv-BN-PReLU-conv-BN + x (torchsr/srgan/residual.py:86-91). `inplace` (inference-only plans, when nothing else
+    reads x afterwards): the block's output replaces x in its buffer - the second conv's epilogue then adds its tile to
+    global memory with a reducing bulk store instead of loading x (ConvParams::res_reduce)."""
     B, H, W, C = x.B, x.H, x.W, x.C
     alpha = blk.prelu.weight
     a1 = plan.act(name + ".a1", B, H, W, C)
     raw1, coef1 = plan.conv_bn_act(prog, name + ".c1", ra, x, a1, bn=blk.bn1, act=L.ACT_PRELU, alpha=alpha)
-    y = plan.act(name + ".y", B, H, W, C)
+    y = x if (inplace and plan.infer_only) else plan.act(name + ".y", B, H, W, C)
     raw2, coef2 = plan.conv_bn_act(prog, name + ".c2", rb, a1, y, bn=blk.bn2, act=L.ACT_NONE, res=x)
 
     def bwd(bp, g, want_x, want_w):
@@ -113,11 +115,13 @@ def define_srgan_generator(m, plan: Plan, shape):
 
     x = c1
     for i, blk in enumerate(m.blocks):
-        x = residual_block_stage(plan, fwd, f"blocks.{i}", blk, R[f"blocks.{i}.conv1"], R[f"blocks.{i}.conv2"], x)
+        # block 0 reads c1, which the skip connection behind the trunk needs again: every later block may work in place
+        x = residual_block_stage(plan, fwd, f"blocks.{i}", blk, R[f"blocks.{i}.conv1"], R[f"blocks.{i}.conv2"], x,
+                                 inplace=i >= 1)
 
     rc2, bn2 = R["conv2.0"], m.conv2[1]
     xt = x
-    s = plan.act("trunk", B, H, W, 64)
+    s = c1 if plan.infer_only else plan.act("trunk", B, H, W, 64)     # inference: added into c1 in place (see the blocks)
     raw, coef = plan.conv_bn_act(fwd, "conv2", rc2, xt, s, bn=bn2, act=L.ACT_NONE, res=c1)
 
     def bwd_conv2(bp, g, want_x, want_w):
