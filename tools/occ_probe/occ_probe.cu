@@ -1,5 +1,5 @@
 // Which feature of a kernel makes cudaOccupancyMaxActiveBlocksPerMultiprocessor answer 1 block per SM on B200?
-// nvcc -gencode arch=compute_100a,code=sm_100a -o occ_probe occ_probe.cu && ./occ_probe
+// nvcc -gencode arch=compute_100a,code=sm_100a -o occ_probe occ_probe.cu && ./occ_probe   (the binary is not tracked)
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
