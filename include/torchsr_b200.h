@@ -143,14 +143,19 @@ typedef struct tsr_conv_desc {
      at launch):  out[n][c][h][w] += sum_kw acc[(n, h, w + kw - gather_pad)][kw*gather_c + c]  (+ gather_bias[c], once).
      One N tile (block_n == cout_pad >= gather_k*gather_c), no split-K; the out strides are not used. */
   const float* gather_bias;
-  int32_t gather_k, gather_pad, gather_c, _pad4;
+  int32_t gather_k, gather_pad, gather_c;
+  int32_t gather_rows;      /* 0 / 1: one output row per GEMM row. 2: the GEMM row (n, y2, x) produces the TWO output rows
+                               2*y2 and 2*y2 + 1 (columns r*32 + kw*gather_c + c, ten vertical taps, traversal stride 2
+                               along H): out is [N][gather_c][2*Ho][Wo], block_n = 64 */
   /* Nearest-neighbour x2 upsampling of the result (F.interpolate(scale_factor=2) in front of the ESRGAN upsample convs,
      esrgan/generator.py:73,76) folded into the producer's store: besides `out`, every output pixel (ho, wo) is written
      to the four positions (2ho + i, 2wo + j) of out_rep2x (bf16, strides in elements of the fine grid). Linear bf16
      stores of im2col convs only. */
   void* out_rep2x;
   int64_t rep_n, rep_h, rep_w;
-  int32_t rep_ch_off, _pad5;
+  int32_t rep_ch_off;
+  int32_t stride_w;         /* a_mode 0: traversal stride along W when it differs from `stride` (then the stride along H);
+                               0 = same */
 } tsr_conv_desc_t;
 
 typedef struct tsr_wgrad_desc {

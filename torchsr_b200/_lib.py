@@ -55,9 +55,9 @@ class ConvDesc(C.Structure):
         ("bnr_gamma", C.c_void_p), ("bnr_dgamma", C.c_void_p), ("bnr_dbeta", C.c_void_p), ("bnr_dalpha", C.c_void_p),
         ("bnr_count", C.c_int64),
         ("gather_bias", C.c_void_p), ("gather_k", C.c_int32), ("gather_pad", C.c_int32), ("gather_c", C.c_int32),
-        ("_pad4", C.c_int32),
+        ("gather_rows", C.c_int32),
         ("out_rep2x", C.c_void_p), ("rep_n", C.c_int64), ("rep_h", C.c_int64), ("rep_w", C.c_int64),
-        ("rep_ch_off", C.c_int32), ("_pad5", C.c_int32),
+        ("rep_ch_off", C.c_int32), ("stride_w", C.c_int32),
     ]
 
 

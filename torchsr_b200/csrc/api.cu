@@ -93,14 +93,14 @@ int encode_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int6
 
 // NHWC bf16 tensor, im2col mode: box = {chan, pixels}
 int encode_im2col(CUtensorMap* m, const void* base, int64_t N, int64_t H, int64_t W, int64_t C, int64_t ld, int lower_h,
-                  int lower_w, int upper_h, int upper_w, int stride, int chan, int pixels) {
+                  int lower_w, int upper_h, int upper_w, int stride, int chan, int pixels, int stride_w = 0) {
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                         static_cast<cuuint64_t>(N)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * W,
                            static_cast<cuuint64_t>(ld) * 2 * W * H};
   int lower[2] = {lower_w, lower_h};
   int upper[2] = {upper_w, upper_h};
-  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w > 0 ? stride_w : stride), static_cast<cuuint32_t>(stride), 1};
   CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
                                upper, static_cast<cuuint32_t>(chan), static_cast<cuuint32_t>(pixels), estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(chan * 2),
@@ -189,13 +189,14 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   if (d.num_taps < 1 || d.num_taps > kMaxTaps) return fail(-20, "num_taps out of range");
   if (d.a_mode == 0) {
     if (d.C % d.block_k) return fail(-20, "C (%lld) must be a multiple of block_k (%d)", (long long)d.C, d.block_k);
-    const int64_t wo = (d.W + d.upper_w - d.lower_w - 1) / d.stride + 1;
+    const int stride_w = d.stride_w > 0 ? d.stride_w : d.stride;
+    const int64_t wo = (d.W + d.upper_w - d.lower_w - 1) / stride_w + 1;
     const int64_t ho = (d.H + d.upper_h - d.lower_h - 1) / d.stride + 1;
     if (wo != d.Wo || ho != d.Ho)
       return fail(-21, "traversal grid mismatch: corners give %lldx%lld, descriptor says %lldx%lld", (long long)ho,
                   (long long)wo, (long long)d.Ho, (long long)d.Wo);
     if (int e = encode_im2col(&p.tmA, d.x, d.N, d.H, d.W, d.C, d.x_ld, d.lower_h, d.lower_w, d.upper_h, d.upper_w,
-                              d.stride, d.block_k, kBlockM))
+                              d.stride, d.block_k, kBlockM, stride_w))
       return e;
     p.M_total = static_cast<int>(d.N * d.Ho * d.Wo);
     p.kc_per_tap = static_cast<int>((d.C - d.a_c0) / d.block_k);
@@ -222,6 +223,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
   if (int e = encode_2d(&p.tmB, d.w, d.w_rows, d.w_ld, d.w_ld, d.block_k, d.block_n)) return e;
   p.b_chunk_rows = d.w_chunk_rows;
   p.stride = d.stride;
+  p.stride_w = d.stride_w > 0 ? d.stride_w : d.stride;
   p.lower_h = d.lower_h;
   p.lower_w = d.lower_w;
   p.num_taps = d.a_mode == 0 ? d.num_taps : 1;
@@ -312,7 +314,7 @@ int build_conv(const tsr_conv_desc_t& d, ConvLaunch* L, bool allow_persistent = 
     ew = std::max(ew, static_cast<int>(d.tap_off[t] & 0xFF));
   }
   if ((halo_env == 1 || (halo_env < 0 && (want_staged || gather_w))) && use_persistent() && allow_persistent && d.a_mode == 0 &&
-      splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && d.stride == 1 && d.num_taps == 9 && d.Ho == d.H && d.Wo == d.W &&
+      splits == 1 && d.out_mode != TSR_OUT_GEMM_T_ATOMIC && d.stride == 1 && p.stride_w == 1 && d.num_taps == 9 && d.Ho == d.H && d.Wo == d.W &&
       ((eh == 2 && ew == 2 && d.lower_h == -1 && d.lower_w == -1) || (eh == 8 && ew == 0 && d.lower_h == -4 && d.lower_w == 0)) &&
       d.block_k == 64 && (d.C - d.a_c0) % 64 == 0 && d.W >= 8 && d.H >= 4 && 2 * p.acc_cols <= 512) {
     bool taps_ok = true;
@@ -487,6 +489,7 @@ epilogue_params:
   e.gather_k = d.gather_k;
   e.gather_pad = d.gather_pad;
   e.gather_c = d.gather_c;
+  e.gather_rows = d.gather_rows == 2 ? 2 : 1;
   p.staged = 0;
   p.extra_bytes = 0;
   if (d.out_mode == TSR_OUT_GATHER_W) {
@@ -494,8 +497,11 @@ epilogue_params:
         d.gather_k * d.gather_c > d.block_n || d.gather_pad < 0 || d.gather_pad >= d.gather_k || d.out_preact || d.bias ||
         d.res || d.bwd_z || d.bnr_x || d.stats_partial || d.bnf_mode || (p.halo && p.halo_pw % 32))
       return fail(-20, "OUT_GATHER_W needs an unsplit im2col conv with one N tile, an fp32 NCHW output and a plain epilogue");
-    if (d.gather_k != 9 || d.gather_c != 3 || d.gather_pad != 4 || d.block_n != 32)
-      return fail(-20, "OUT_GATHER_W is implemented for the 9-tap, 3-channel, 32-column case (conv_igemm.cu:gather9x3)");
+    const int g_rows = d.gather_rows == 2 ? 2 : 1;
+    if (d.gather_k != 9 || d.gather_c != 3 || d.gather_pad != 4 || d.block_n != 32 * g_rows)
+      return fail(-20, "OUT_GATHER_W is implemented for 9 taps x 3 channels in 32 columns per output row (conv_igemm.cu:gather9x3)");
+    if (g_rows == 2 && (d.stride != 2 || p.stride_w != 1 || p.halo))
+      return fail(-20, "OUT_GATHER_W with two output rows per GEMM row traverses H with stride 2 (im2col tiles)");
   }
   if (want_staged && p.persistent && (p.halo || (out_lin && out_dense))) {
     // output map(s): the staging buffer is one {64 channels x 128 pixels} (im2col tiles) or {64 x (pw-2) x th} (halo
@@ -541,7 +547,7 @@ epilogue_params:
       splits == 1 && L->tiles_n % 2 == 0 && p.M_total % kBlockM == 0 && d.bnf_mode != 1 && !d.bnr_apply &&
       total_iters >= 18) {
     if (int e2 = encode_im2col(&p.tmA2, d.x, d.N, d.H, d.W, d.C, d.x_ld, d.lower_h, d.lower_w, d.upper_h, d.upper_w,
-                               d.stride, d.block_k, 64))
+                               d.stride, d.block_k, 64, p.stride_w))
       return e2;
     p.cluster_n = 2;
   }

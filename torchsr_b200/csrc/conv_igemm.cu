@@ -272,7 +272,7 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
       const int ho = rem / p.Wo;
       const int wo = rem - ho * p.Wo;
       h0 = ho * p.stride + p.lower_h;
-      w0 = wo * p.stride + p.lower_w;
+      w0 = wo * p.stride_w + p.lower_w;
     }
     int tap = 0, kc = it_begin;
     if (A_MODE == 0) {
@@ -963,6 +963,7 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       aux_base = static_cast<long long>(m) * e.aux_w + e.aux_ch_off;
     }
     float dalpha = 0.f;
+    float g2a0[3] = {0.f, 0.f, 0.f}, g2a1[3] = {0.f, 0.f, 0.f};     // OUT_GATHER_W, two output rows per GEMM row
     // BatchNorm statistics group of this thread's row (all 32 rows of a warp share it: group_rows % 32 == 0)
     const int grp = (group_rows > 0 && m >= group_rows) ? 1 : 0;
     if (half == 0 && lane == 0) s_qgrp[q] = grp;
@@ -1448,10 +1449,39 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
             wcol = static_cast<int>(mo - static_cast<long long>(rowid) * p.Wo);
           }
           float a0[3], a1[3];
-          if (ch == 0)
+          const int cl = e.gather_rows == 2 ? ((ch - ch_begin) & 1) : ch;     // chunk inside the 32 columns of an output row
+          if (cl == 0)
             gather9x3<0>(v, lane, wo, P, ext, wcol, p.Wo, a0, a1);
           else
             gather9x3<1>(v, lane, wo, P, ext, wcol, p.Wo, a0, a1);
+          float* const o = reinterpret_cast<float*>(out);
+          if (e.gather_rows == 2) {
+            // two output rows per GEMM row: this warp holds BOTH column chunks of output row 2*ho + half; the first
+            // chunk's partial sums wait in registers for the second
+            if (cl == 0) {
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                g2a0[c] = a0[c];
+                g2a1[c] = a1[c];
+              }
+            } else {
+              const int Hout = 2 * p.Ho;
+              const long long cs = static_cast<long long>(Hout) * p.Wo;
+              if (valid) {
+                const long long own = ((static_cast<long long>(n) * 3) * Hout + 2 * ho + half) * p.Wo + wo;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                  atomicAdd(o + own + c * cs, a0[c] + g2a0[c] + (e.gather_bias != nullptr ? __ldg(e.gather_bias + c) : 0.f));
+              }
+              if (ext) {
+                const int nn = rowid / p.Ho, hh = rowid - nn * p.Ho;
+                const long long oe = ((static_cast<long long>(nn) * 3) * Hout + 2 * hh + half) * p.Wo + wcol;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) atomicAdd(o + oe + c * cs, a1[c] + g2a1[c]);
+              }
+            }
+            continue;
+          }
           // the two warps of a lane quadrant hold the two column chunks of the same rows: the upper half hands its
           // partial sums over through shared memory (double-buffered across the tiles of a persistent CTA)
           float* pbuf = scratch + ((j & 1) * kBlockM + row) * 6;
@@ -1471,7 +1501,6 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
             pair_sync();
           } else {
             pair_sync();
-            float* const o = reinterpret_cast<float*>(out);
             const long long cs = static_cast<long long>(p.Ho) * p.Wo;
             if (valid) {
               const long long own = ((static_cast<long long>(n) * 3) * p.Ho + ho) * p.Wo + wo;

@@ -110,6 +110,8 @@ struct EpiParams {
   // the position adds the bias. Replaces a [M][block_n] fp32 round trip through HBM plus a gather kernel.
   const float* gather_bias;
   int gather_k, gather_pad, gather_c;
+  int gather_rows;   // 2: every GEMM row (n, y2, x) holds the taps of the two output rows 2*y2 + r, r = column / 32 (ten
+                     // vertical taps, traversal stride 2 along H, N = 64): twice the columns per fetched activation tile
   // nearest x2 of the result folded into the store: pixel (ho, wo) also goes to (2ho + i, 2wo + j) of out_rep2x
   void* out_rep2x;
   long long rep_n, rep_h, rep_w;
@@ -124,7 +126,8 @@ struct ConvParams {
   EpiParams epi;
   int M_total;     // rows of the implicit GEMM (N*Ho*Wo traversal positions)
   int Ho, Wo;      // traversal grid (per image)
-  int stride;      // traversal stride in input pixels
+  int stride;      // traversal stride in input pixels (along H)
+  int stride_w;    // ... along W (== stride unless the descriptor says otherwise)
   int lower_h, lower_w;
   int num_taps;
   int kc_per_tap;  // K chunks (of block_k) per tap

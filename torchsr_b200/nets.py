@@ -146,8 +146,29 @@ def define_srgan_generator(m, plan: Plan, shape):
     Y = plan.buf("Y", B * r3.cout * Hf * Wf, F32)
     fwd.add(ops.elt(L.E_ZERO, p=[Y], i=[Y.numel() * 4]))
     geom3 = ops.fwd_geometry(Hf, Wf, r3.k, 1, r3.pad, 0, 1)
-    plan.conv(fwd, u, r3.w_fwd, r3.cols, r3.k, geom3, r3.npad, r3.npad, Y, (0, 0, 0), r3.npad,
-              gather=dict(k=r3.k, pad=r3.pad, c=r3.cout, bias=r3.bias))
+    if plan.infer_only and r3.k == 9 and r3.cout == 3 and r3.cin == 64 and Hf % 2 == 0:
+        # Inference plans: TWO output rows per GEMM row. The GEMM row (n, y2, x) reads input rows 2*y2 - 4 .. 2*y2 + 5 (ten
+        # vertical taps, traversal stride 2 along H) against N = 2 x 32 columns (r, kw, c): output row 2*y2 + r uses tap
+        # kh' with the weights of kh = kh' - r. Twice the columns per fetched activation tile: an N = 64 UMMA reads 6 KB of
+        # operands for twice the work of the 5 KB an N = 32 UMMA reads (the launch is bound by exactly that).
+        w2 = plan.buf("conv3.w2", 10 * 64 * 64, BF16)
+
+        def pack_w2():
+            wk = r3.weight.detach().permute(2, 3, 0, 1).reshape(9, 27, 64)      # [kh][kw*3 + c][ci]
+            t = torch.zeros(10, 2, 32, 64, dtype=F32, device=plan.device)
+            t[0:9, 0, :27] = wk
+            t[1:10, 1, :27] = wk
+            w2.view(10, 64, 64).copy_(t.view(10, 64, 64))
+
+        pack_w2()
+        plan.store.extra_packers.append(pack_w2)
+        geom2 = dict(lower_h=-r3.pad, lower_w=0, upper_h=-(r3.pad + 1), upper_w=0, Ho=Hf // 2, Wo=Wf, stride=2, stride_w=1,
+                     taps=[(kh, 0, kh) for kh in range(10)])
+        plan.conv(fwd, u, w2, 64, 10, geom2, 64, 64, Y, (0, 0, 0), 64,
+                  gather=dict(k=r3.k, pad=r3.pad, c=r3.cout, bias=r3.bias, rows=2))
+    else:
+        plan.conv(fwd, u, r3.w_fwd, r3.cols, r3.k, geom3, r3.npad, r3.npad, Y, (0, 0, 0), r3.npad,
+                  gather=dict(k=r3.k, pad=r3.pad, c=r3.cout, bias=r3.bias))
     E3 = None if plan.infer_only else plan.act("E3", B, Hf, Wf, r3.npad)
     cs = plan.buf("conv3.cs", CHANSUM_SPLITS * r3.cout * 2, F32)
     u_last = u

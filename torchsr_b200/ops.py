@@ -125,13 +125,15 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
               res_scale=1.0, res2_scale=1.0, res_cols=0, w_static=True, bnr_x=None, bnr_coef=None, bnr_prelu=None,
               bnr_act=L.ACT_NONE, bnr_c=0, splits=1, ws=None, tile_counters=None, ws_ld=0, group_rows=0, bnf_mode=0,
               bnf_c=0, bnf_counter=None, bnf_gamma=None, bnf_beta=None, bnf_rm=None, bnf_rv=None, bnf_nbt=None,
-              bnf_coef=None, bnf_count=0, bnf_eps=1e-5, bnf_momentum=0.1, gather=None, rep2x=None) -> ConvDesc:
+              bnf_coef=None, bnf_count=0, bnf_eps=1e-5, bnf_momentum=0.1, gather=None, rep2x=None,
+              stride_w=0) -> ConvDesc:
     d = ConvDesc()
     d.x, d.w = ptr(x), ptr(w)
     d.N, d.H, d.W, d.C, d.x_ld = N, H, W, C, x_ld
     d.Ho, d.Wo = geom["Ho"], geom["Wo"]
     d.a_mode = 0
     d.stride = geom["stride"]
+    d.stride_w = geom.get("stride_w", stride_w)
     d.lower_h, d.lower_w, d.upper_h, d.upper_w = geom["lower_h"], geom["lower_w"], geom["upper_h"], geom["upper_w"]
     _set_taps(d, geom["taps"])
     d.block_k = block_k or pick_block_k(C - a_c0)
@@ -162,6 +164,7 @@ def conv_desc(*, x, N, H, W, C, x_ld, geom, w, cout_pad, w_ld, n_slots, block_n,
     if gather is not None:      # dict(k, pad, c, bias): OUT_GATHER_W, `out` is the zero-initialised fp32 NCHW result
         d.out_mode, d.out_f32 = L.OUT_GATHER_W, 1
         d.gather_k, d.gather_pad, d.gather_c, d.gather_bias = gather["k"], gather["pad"], gather["c"], ptr(gather.get("bias"))
+        d.gather_rows = gather.get("rows", 1)
     return d
 
 
@@ -290,11 +293,12 @@ def validate_conv(d: ConvDesc):
         else:
             span = d.n_valid
         if d.out_mode == L.OUT_GATHER_W:
-            if (d.gather_k < 1 or d.gather_c < 1 or d.gather_k * d.gather_c > d.block_n or d.block_n != d.cout_pad
+            g_rows = 2 if d.gather_rows == 2 else 1
+            if (d.gather_k < 1 or d.gather_c < 1 or g_rows * 32 != d.block_n or d.block_n != d.cout_pad
                     or not 0 <= d.gather_pad < d.gather_k or d.splits > 1 or not d.out_f32 or d.out_preact or d.bias
                     or d.res or d.bwd_z or d.bnr_x or d.stats_partial or d.bnf_mode):
                 raise ExtentError("OUT_GATHER_W: one N tile holding gather_k*gather_c columns, fp32 output, plain epilogue")
-            _need("conv gather out", d.out, d.N * d.gather_c * d.Ho * d.Wo * 4)
+            _need("conv gather out", d.out, d.N * d.gather_c * g_rows * d.Ho * d.Wo * 4)
             if d.gather_bias:
                 _need("conv gather bias", d.gather_bias, d.gather_c * 4)
         else:
