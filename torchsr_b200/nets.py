@@ -97,12 +97,31 @@ def define_srgan_generator(m, plan: Plan, shape):
     store, fwd = plan.grads, plan.fwd
     r1 = R["conv1.0"]
     alpha1 = m.conv1[1].weight
-    E1 = plan.act("E1", B, H, W, r1.epad)
+    E1 = None if (plan.infer_only and r1.k == 9 and r1.cin == 3 and r1.cout == 64) else plan.act("E1", B, H, W, r1.epad)
     c1 = plan.act("c1", B, H, W, 64)
     c1_pre = c1 if plan.infer_only else plan.act("c1.pre", B, H, W, 64)
     g1 = _geom1(H, W)
-    plan.conv(fwd, E1, r1.w_fwd, r1.cols, 1, g1, r1.cout_pad, r1.block_n, c1.t, c1.strides(), r1.cout_pad, bias=r1.bias,
-              act=L.ACT_PRELU, prelu=alpha1, out_preact=None if plan.infer_only else c1_pre.t)
+    rowk = plan.infer_only and r1.k == 9 and r1.cin == 3 and r1.cout == 64
+    if rowk:
+        # Inference plans: the 9x9 3-channel input layer row-decomposed like the output layer - the im2row kernel expands
+        # only the nine HORIZONTAL taps (27 -> 32 columns, 64 bytes per pixel instead of the 512 of the full 243-column
+        # expansion: 17 MB instead of 134 MB per 512x512 image), the nine vertical taps are im2col taps of the conv
+        E1r = plan.act("E1r", B, H, W, 32)
+        w1r = plan.buf("conv1.w_rowk", 9 * 64 * 32, BF16)
+
+        def pack_w1r():
+            wk = r1.weight.detach().permute(2, 0, 3, 1).reshape(9, 64, 27)      # [kh][co][kw*3 + c]
+            t = torch.zeros(9, 64, 32, dtype=F32, device=plan.device)
+            t[:, :, :27] = wk
+            w1r.view(9, 64, 32).copy_(t)
+
+        pack_w1r()
+        plan.store.extra_packers.append(pack_w1r)
+        g1r = ops.fwd_geometry(H, W, r1.k, 1, r1.pad, 0, 1)
+        plan.conv(fwd, E1r, w1r, 32, 9, g1r, 64, 64, c1.t, c1.strides(), 64, bias=r1.bias, act=L.ACT_PRELU, prelu=alpha1)
+    else:
+        plan.conv(fwd, E1, r1.w_fwd, r1.cols, 1, g1, r1.cout_pad, r1.block_n, c1.t, c1.strides(), r1.cout_pad, bias=r1.bias,
+                  act=L.ACT_PRELU, prelu=alpha1, out_preact=None if plan.infer_only else c1_pre.t)
 
     def bwd_conv1(bp, g, want_x, want_w):
         if want_w:
@@ -174,7 +193,10 @@ def define_srgan_generator(m, plan: Plan, shape):
     u_last = u
 
     def input_fn(x_nchw):
-        ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E1.t], i=[B, 3, H, W, r1.k, r1.k, r1.pad, r1.pad, 1, r1.epad]))
+        if rowk:
+            ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E1r.t], i=[B, 3, H, W, 1, r1.k, 0, r1.pad, 1, 32]))
+        else:
+            ops.run_now(ops.elt(L.E_IM2ROW, p=[x_nchw, E1.t], i=[B, 3, H, W, r1.k, r1.k, r1.pad, r1.pad, 1, r1.epad]))
 
     def output_fn():
         # a fresh tensor per call (the plan's buffer is overwritten by the next forward): one device-to-device copy
