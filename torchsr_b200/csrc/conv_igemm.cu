@@ -292,7 +292,10 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
       const uint32_t mc_half = mc_rank > 0 ? (abytes >> 1) : 0u;
       int n_pre = first_tile ? pre : 0;
       uint32_t ukc = static_cast<uint32_t>(kc);
-      int cA = c_first + kc * 64, cB = kc * 64;
+      // 64 channels per K chunk; the persistent instantiation also runs 32 (the one-tile kernel stays at 64: it is at its
+      // 96-register budget)
+      const int bk = PERS ? static_cast<int>(in_reg(static_cast<uint32_t>(block_k))) : 64;
+      int cA = c_first + kc * bk, cB = kc * bk;
       uint32_t offs = p.tap_off[tap];
       int brow = static_cast<int>(p.tap_wrow[tap] * b_tap_rows) + b_row0;
       uint32_t full = bar_full + 8 * s, empty = bar_empty + 8 * s;
@@ -307,8 +310,8 @@ __device__ __forceinline__ void producer_role(const ConvParams& p, uint32_t bar_
           if (!PERS && n_pre <= 0) tma_load_2d(dst + abytes, &p.tmB, full, cB, brow);
         }
         --n_pre;
-        cA += 64;
-        cB += 64;
+        cA += bk;
+        cB += bk;
         if (++ukc == kcpt) {
           ukc = 0;
           cA = c_first;
@@ -497,6 +500,7 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
       // and barrier addresses of the next stage are advanced before its wait, loop invariants are pinned in registers.
       const uint32_t nst = in_reg(static_cast<uint32_t>(stages)), st16 = in_reg(stage16), b16r = in_reg(b16);
       const uint32_t idesc_r = in_reg(idesc);
+      const bool k4 = PERS ? in_reg(ksteps) == 4u : true;
       const uint64_t a_desc0 = (static_cast<uint64_t>(a_hi) << 32) | a_lo0;
       const uint64_t b_desc0 = (static_cast<uint64_t>(b_hi) << 32) | b_lo0;
       uint64_t ad = a_desc0 + soff, bd = pers ? b_desc0 : b_desc0 + soff;
@@ -507,8 +511,10 @@ __device__ __forceinline__ void mma_role(const ConvParams& p, uint32_t bar_full,
         if (leader) {
           if (!PERS && mc)
             umma_bf16_x4_commit_mc(d_tmem, ad, bd, idesc_r, acc, empty, 3);   // frees the stage in both CTAs of the pair
-          else
+          else if (k4)
             umma_bf16_x4_commit(d_tmem, ad, bd, idesc_r, acc, empty);
+          else
+            umma_bf16_x2_commit(d_tmem, ad, bd, idesc_r, acc, empty);         // 32-element K chunks
         }
         acc = 1;
         ad += st16;
@@ -963,7 +969,6 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
       aux_base = static_cast<long long>(m) * e.aux_w + e.aux_ch_off;
     }
     float dalpha = 0.f;
-    float g2a0[3] = {0.f, 0.f, 0.f}, g2a1[3] = {0.f, 0.f, 0.f};     // OUT_GATHER_W, two output rows per GEMM row
     // BatchNorm statistics group of this thread's row (all 32 rows of a warp share it: group_rows % 32 == 0)
     const int grp = (group_rows > 0 && m >= group_rows) ? 1 : 0;
     if (half == 0 && lane == 0) s_qgrp[q] = grp;
@@ -1458,13 +1463,22 @@ __device__ __forceinline__ void conv_body(const ConvParams& p, const int zsplit,
           if (e.gather_rows == 2) {
             // two output rows per GEMM row: this warp holds BOTH column chunks of output row 2*ho + half; the first
             // chunk's partial sums wait in registers for the second
+            // (parked in this thread's own slot of the reduction scratch rather than in registers: six registers live
+            // across the chunk loop made the one-tile instantiation spill)
+            float* const park = scratch + (half * kBlockM + row) * 6;
             if (cl == 0) {
 #pragma unroll
               for (int c = 0; c < 3; ++c) {
-                g2a0[c] = a0[c];
-                g2a1[c] = a1[c];
+                park[c] = a0[c];
+                park[3 + c] = a1[c];
               }
             } else {
+              float g2a0[3], g2a1[3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                g2a0[c] = park[c];
+                g2a1[c] = park[3 + c];
+              }
               const int Hout = 2 * p.Ho;
               const long long cs = static_cast<long long>(Hout) * p.Wo;
               if (valid) {
@@ -1821,9 +1835,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_persistent_kernel(
   conv_body<0, true, FAST>(p, 0, 1);
 }
 
-// FAST instantiations need 64-channel K chunks and run without trace stamps / attribution hooks.
+// FAST instantiations need 64-channel K chunks (the persistent one also takes 32) and run without trace stamps /
+// attribution hooks.
 static bool fast_ok(const ConvParams& p) {
-  return p.a_mode == 0 && p.block_k == 64 && p.epi.trace == nullptr && p.debug == 0;
+  return p.a_mode == 0 && (p.block_k == 64 || (p.block_k == 32 && p.persistent)) && p.epi.trace == nullptr && p.debug == 0;
 }
 
 // Up to four independent im2col convs of the same tile grid in ONE launch (blockIdx.z selects the member): the four

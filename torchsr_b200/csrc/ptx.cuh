@@ -186,6 +186,20 @@ __device__ __forceinline__ void umma_bf16_x4_commit(uint32_t tmem_d, uint64_t ad
         "l"(adesc + 4), "l"(bdesc + 4), "l"(adesc + 6), "l"(bdesc + 6)
       : "memory");
 }
+// Two K=16 steps + commit: 32-element K chunks (64-byte swizzled rows), e.g. the 27 -> 32 column row expansions of the
+// 9x9 layers.
+__device__ __forceinline__ void umma_bf16_x2_commit(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate, uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %4, %4;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %6, %7, %3, t;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(bar), "l"(adesc + 2), "l"(bdesc + 2)
+      : "memory");
+}
 // The same with the commit arriving on the barrier at this offset in EVERY CTA of `cta_mask`: a ring stage that was
 // filled by multicast loads may only be refilled once all receiving CTAs have consumed it.
 __device__ __forceinline__ void umma_bf16_x4_commit_mc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
