@@ -218,6 +218,9 @@ enum tsr_elt_kind {
   TSR_E_GAN_LOSS = 29,   /* BCE / BCE-with-logits / relativistic-average GAN criteria, value + gradient, one launch */
   TSR_E_AXPBY_F32 = 30,  /* out = a * (*scalar) * x + b * y on fp32 vectors */
   TSR_E_CROP_LR = 32,    /* batched RandomCrop + flips + Pillow-exact bicubic /4 (dataset.py:86-99,118-121) on uint8 images in HBM */
+  TSR_E_PACK_GATHER = 33, /* dst[i] (bf16) = idx[i] >= 0 ? src[idx[i]] (fp32) : 0; p: src, idx (int32), dst; i: 0 n. Operand
+                             layouts that only one plan uses, re-derived from the fp32 parameter inside that plan's own
+                             launch list (always current, also under CUDA-graph replays of optimizer steps) */
   TSR_E_FEAT_T = 31      /* NHWC bf16 features -> chunked transposed [(c,h,w)][batch] bf16 factor of the Linear wgrad GEMM */
 };
 

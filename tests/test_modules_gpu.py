@@ -514,6 +514,35 @@ def test_large_image_inference_staged_halo_paths_match_oracle_and_generic_kernel
     assert d <= 1e-2 and e_new <= 1.25 * e_old + 2e-3, (e_new, e_old, d)
 
 
+def test_inference_plan_packs_follow_the_weights():
+    """The inference plans keep their own packs of the two 9x9 layers (row-decomposed input conv, two output rows per GEMM
+    row in the output conv), derived from the fp32 parameters by a kernel of the plan's own launch list: a changed
+    weight must show in the very next eval forward, also when it changed on the device only (no version bump)."""
+    MC, SG, SD, EG, ED = _mods()
+    torch.manual_seed(23)
+    G = SG().cuda().eval()
+    x = torch.rand(1, 3, 40, 48, device="cuda")
+
+    def fresh():
+        H = SG().cuda().eval()
+        H.load_state_dict(G.state_dict())
+        with torch.no_grad():
+            return H(x)
+
+    with torch.no_grad():
+        y0 = G(x)
+        assert MC.rel_l2(y0, fresh()) <= 1e-6
+        G.conv3.weight.mul_(0.5)                       # version bump
+        y1 = G(x)
+        assert MC.rel_l2(y1, fresh()) <= 1e-6 and MC.rel_l2(y1, y0) > 1e-2
+        G.conv3.weight.data.view(-1)[:].mul_(2.0)      # in place on the device through .data: no version bump
+        G.conv1[0].weight.data.mul_(0.5)
+        y2 = G(x)
+        assert MC.rel_l2(y2, fresh()) <= 1e-6 and MC.rel_l2(y2, y1) > 1e-2
+        ref = MC.O.srgan_generator({k: v.detach().cpu() for k, v in G.state_dict().items()}, x.cpu(), False)
+    assert MC.rel_l2(y2.cpu(), ref) <= 3e-2
+
+
 def test_upscale_pipelined_equals_sequential_upscale():
     from torchsr_b200.test import upscale, upscale_pipelined
     MC, SG, SD, EG, ED = _mods()

@@ -16,7 +16,7 @@ ACT_NONE, ACT_PRELU, ACT_LEAKY, ACT_RELU = 0, 1, 2, 3
 (E_IM2ROW, E_GATHER_OUT, E_NCHW2NHWC, E_NHWC2NCHW, E_BN_FINALIZE, E_BN_EVAL_COEF, E_BN_ACT, E_BN_BWD_REDUCE,
  E_BN_BWD_FINALIZE, E_BN_BWD_APPLY, E_ACT_BWD, E_COLSUM_FINALIZE, E_SUM_FINALIZE, E_PACK_W, E_UNPACK_G,
  E_LINEAR_WGRAD, E_LOSS, E_ZERO, E_UPSAMPLE2X, E_UPSAMPLE2X_BWD, E_HEAD, E_HEAD_BWD, E_AXPBY, E_MAXPOOL2,
- E_MAXPOOL2_BWD, E_CAST, E_ADAM, E_CHANSUM_NCHW, E_GAN_LOSS, E_AXPBY_F32, E_FEAT_T, E_CROP_LR) = range(1, 33)
+ E_MAXPOOL2_BWD, E_CAST, E_ADAM, E_CHANSUM_NCHW, E_GAN_LOSS, E_AXPBY_F32, E_FEAT_T, E_CROP_LR, E_PACK_GATHER) = range(1, 34)
 
 PK_FWD, PK_T, PK_ROWK, PK_ROWN, PK_ROWN_T, PK_FULLK, PK_LINEAR = range(7)
 

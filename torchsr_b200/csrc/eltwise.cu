@@ -1490,6 +1490,17 @@ __global__ void maxpool2_bwd_kernel(const bf16* __restrict__ x, const bf16* __re
   }
 }
 // ZERO: p0 = dst (16-byte aligned); i: 0 bytes (multiple of 16)
+// PACK_GATHER: dst[i] = idx[i] >= 0 ? bf16(src[idx[i]]) : 0 (table-driven operand layouts of single plans)
+__global__ void pack_gather_kernel(const float* __restrict__ src, const int* __restrict__ idx, bf16* __restrict__ dst,
+                                   long long n) {
+  pdl_sync();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = __ldg(idx + i);
+    dst[i] = __float2bfloat16(k >= 0 ? __ldg(src + k) : 0.f);
+  }
+}
+
 __global__ void zero_kernel(uint4* __restrict__ dst, long long n16) {
   pdl_sync();
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -1651,6 +1662,10 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
     case TSR_E_LOSS:
       ce = launch_k(loss_kernel, dim3(static_cast<unsigned>(i[2])), dim3(256), 0, st, pdl, (const float*)p[0], (const float*)p[1], (float*)p[2],
                                                               (float*)p[3], i[0], i[1], d.f[0]);
+      break;
+    case TSR_E_PACK_GATHER:
+      ce = launch_k(pack_gather_kernel, dim3(grid_for(i[0])), dim3(256), 0, st, pdl, (const float*)p[0], (const int*)p[1],
+                    (bf16*)p[2], i[0]);
       break;
     case TSR_E_ZERO: {
       // a kernel (not a memset node): stays inside programmatic-launch chains and graph branches of kernel nodes

@@ -187,10 +187,7 @@ class ParamStore:
         self._version = None
         self.dirty = True
         self.opt_fresh = False
-        # extra operand layouts that only some plans use (e.g. the two-rows-per-GEMM-row pack of the 9x9 output conv in
-        # the inference plans): callables re-run after every re-pack; deferred while a CUDA graph is being captured
-        self.extra_packers = []
-        self._extra_stale = False
+
         # set by optim.FusedAdam(late_numel=...): the event after which the weights behind the forward program's
         # "late_weights" mark (the big Linear layer) are valid
         self.late_event = None
@@ -246,10 +243,6 @@ class ParamStore:
         for p in self._watched:
             ver += p._version
         if ver == self._version and not self.dirty:
-            if self._extra_stale and self.extra_packers and not torch.cuda.is_current_stream_capturing():
-                for f in self.extra_packers:
-                    f()
-                self._extra_stale = False
             return
         if ver == self._version and self.opt_fresh:
             # stepped by torchsr_b200.optim.FusedAdam only: it rewrote the 'std' conv and Linear packs itself
@@ -260,13 +253,6 @@ class ParamStore:
         self.opt_fresh = False
         self._version = ver
         self.dirty = False
-        if self.extra_packers:
-            if torch.cuda.is_current_stream_capturing():
-                self._extra_stale = True
-            else:
-                for f in self.extra_packers:
-                    f()
-                self._extra_stale = False
 
     def grads_from_flat(self, flat: torch.Tensor, want: List[bool]) -> List[Optional[torch.Tensor]]:
         out = []

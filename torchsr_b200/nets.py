@@ -108,15 +108,13 @@ def define_srgan_generator(m, plan: Plan, shape):
         # expansion: 17 MB instead of 134 MB per 512x512 image), the nine vertical taps are im2col taps of the conv
         E1r = plan.act("E1r", B, H, W, 32)
         w1r = plan.buf("conv1.w_rowk", 9 * 64 * 32, BF16)
-
-        def pack_w1r():
-            wk = r1.weight.detach().permute(2, 0, 3, 1).reshape(9, 64, 27)      # [kh][co][kw*3 + c]
-            t = torch.zeros(9, 64, 32, dtype=F32, device=plan.device)
-            t[:, :, :27] = wk
-            w1r.view(9, 64, 32).copy_(t)
-
-        pack_w1r()
-        plan.store.extra_packers.append(pack_w1r)
+        # [kh][co][kw*3 + c] <- W[co][c][kh][kw]; packed by the plan's own launch list (always the current weights)
+        src = torch.arange(64 * 3 * 9 * 9, dtype=torch.int32).view(64, 3, 9, 9).permute(2, 0, 3, 1).reshape(9, 64, 27)
+        idx1 = torch.full((9, 64, 32), -1, dtype=torch.int32)
+        idx1[:, :, :27] = src
+        idx1_d = plan.buf("conv1.w_rowk.idx", idx1.numel(), torch.int32)
+        idx1_d.copy_(idx1.view(-1))
+        fwd.add(ops.elt(L.E_PACK_GATHER, p=[r1.weight, idx1_d, w1r], i=[idx1.numel()]))
         g1r = ops.fwd_geometry(H, W, r1.k, 1, r1.pad, 0, 1)
         plan.conv(fwd, E1r, w1r, 32, 9, g1r, 64, 64, c1.t, c1.strides(), 64, bias=r1.bias, act=L.ACT_PRELU, prelu=alpha1)
     else:
@@ -171,16 +169,14 @@ def define_srgan_generator(m, plan: Plan, shape):
         # kh' with the weights of kh = kh' - r. Twice the columns per fetched activation tile: an N = 64 UMMA reads 6 KB of
         # operands for twice the work of the 5 KB an N = 32 UMMA reads (the launch is bound by exactly that).
         w2 = plan.buf("conv3.w2", 10 * 64 * 64, BF16)
-
-        def pack_w2():
-            wk = r3.weight.detach().permute(2, 3, 0, 1).reshape(9, 27, 64)      # [kh][kw*3 + c][ci]
-            t = torch.zeros(10, 2, 32, 64, dtype=F32, device=plan.device)
-            t[0:9, 0, :27] = wk
-            t[1:10, 1, :27] = wk
-            w2.view(10, 64, 64).copy_(t.view(10, 64, 64))
-
-        pack_w2()
-        plan.store.extra_packers.append(pack_w2)
+        # [kh'][r*32 + kw*3 + c][ci] <- W[c][ci][kh' - r][kw]; packed by the plan's own launch list
+        src = torch.arange(3 * 64 * 9 * 9, dtype=torch.int32).view(3, 64, 9, 9).permute(2, 3, 0, 1).reshape(9, 27, 64)
+        idx2 = torch.full((10, 2, 32, 64), -1, dtype=torch.int32)
+        idx2[0:9, 0, :27] = src
+        idx2[1:10, 1, :27] = src
+        idx2_d = plan.buf("conv3.w2.idx", idx2.numel(), torch.int32)
+        idx2_d.copy_(idx2.view(-1))
+        fwd.add(ops.elt(L.E_PACK_GATHER, p=[r3.weight, idx2_d, w2], i=[idx2.numel()]))
         geom2 = dict(lower_h=-r3.pad, lower_w=0, upper_h=-(r3.pad + 1), upper_w=0, Ho=Hf // 2, Wo=Wf, stride=2, stride_w=1,
                      taps=[(kh, 0, kh) for kh in range(10)])
         plan.conv(fwd, u, w2, 64, 10, geom2, 64, 64, Y, (0, 0, 0), 64,

@@ -445,6 +445,8 @@ def _elt_extents(d: EltDesc):
         return [(0, i[0] * 4), (1, i[0] * 4), (2, i[2] * 4), (3, i[0] * 4)]
     if k == L.E_ZERO:
         return [(0, i[0])]
+    if k == L.E_PACK_GATHER:
+        return [(1, i[0] * 4), (2, i[0] * 2)]
     if k == L.E_UPSAMPLE2X:
         return [(0, ((i[0] * i[1] * i[2] - 1) * i[4] + i[3]) * 2), (1, ((4 * i[0] * i[1] * i[2] - 1) * i[5] + i[3]) * 2)]
     if k == L.E_UPSAMPLE2X_BWD:
