@@ -116,7 +116,10 @@ def define_srgan_generator(m, plan: Plan, shape):
         idx1_d.copy_(idx1.view(-1))
         fwd.add(ops.elt(L.E_PACK_GATHER, p=[r1.weight, idx1_d, w1r], i=[idx1.numel()]))
         g1r = ops.fwd_geometry(H, W, r1.k, 1, r1.pad, 0, 1)
-        plan.conv(fwd, E1r, w1r, 32, 9, g1r, 64, 64, c1.t, c1.strides(), 64, bias=r1.bias, act=L.ACT_PRELU, prelu=alpha1)
+        # w_static=False: the pack is written by a kernel of this very launch list - the conv must not fetch weight tiles
+        # before its programmatic-launch wait
+        plan.conv(fwd, E1r, w1r, 32, 9, g1r, 64, 64, c1.t, c1.strides(), 64, bias=r1.bias, act=L.ACT_PRELU, prelu=alpha1,
+                  w_static=False)
     else:
         plan.conv(fwd, E1, r1.w_fwd, r1.cols, 1, g1, r1.cout_pad, r1.block_n, c1.t, c1.strides(), r1.cout_pad, bias=r1.bias,
                   act=L.ACT_PRELU, prelu=alpha1, out_preact=None if plan.infer_only else c1_pre.t)
@@ -179,7 +182,7 @@ def define_srgan_generator(m, plan: Plan, shape):
         fwd.add(ops.elt(L.E_PACK_GATHER, p=[r3.weight, idx2_d, w2], i=[idx2.numel()]))
         geom2 = dict(lower_h=-r3.pad, lower_w=0, upper_h=-(r3.pad + 1), upper_w=0, Ho=Hf // 2, Wo=Wf, stride=2, stride_w=1,
                      taps=[(kh, 0, kh) for kh in range(10)])
-        plan.conv(fwd, u, w2, 64, 10, geom2, 64, 64, Y, (0, 0, 0), 64,
+        plan.conv(fwd, u, w2, 64, 10, geom2, 64, 64, Y, (0, 0, 0), 64, w_static=False,
                   gather=dict(k=r3.k, pad=r3.pad, c=r3.cout, bias=r3.bias, rows=2))
     else:
         plan.conv(fwd, u, r3.w_fwd, r3.cols, r3.k, geom3, r3.npad, r3.npad, Y, (0, 0, 0), r3.npad,
