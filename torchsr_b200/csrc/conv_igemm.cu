@@ -14,13 +14,22 @@
 // instruction count of those two single-warp loops sets the K-iteration rate).
 // The same kernel serves forward convs, stride-1 data gradients (flipped/transposed weight pack),
 // stride-2 data gradients (one launch per output parity class) and the Linear layers (a_mode 1/2, split-K).
+// Epilogues (warps 2..9), selected per launch by the host (api.cu:build_conv, conv_params.h):
+//   * generic chunk loop: bias / scale / residuals / activation forward or backward / PixelShuffle permutations /
+//     BatchNorm column sums / nearest-x2 replication (out_rep2x) / OUT_GATHER_W (horizontal tap sums of the row-decomposed
+//     9x9 output conv, one or two output rows per GEMM row);
+//   * lean fused training BatchNorm forward and backward-apply paths (grid barrier, accumulator in registers);
+//   * staged epilogue of the persistent kernels (one tcgen05.ld per warp, TMEM stage returned at once, arithmetic
+//     instantiated per mode, 128B-swizzled staging buffer, cp.async.bulk.tensor store - or reducing store for in-place
+//     residual blocks), on im2col tiles or on halo patches (3x3, or the 9x1 tap column of the output conv).
+// Optional: activation multicast across clusters of two N tiles (TSR_CONV_CLUSTER=1, measured neutral).
 //
 // Reference behaviour being replaced: every nn.Conv2d / nn.Linear call on the SRGAN/ESRGAN path
 // (torchsr/srgan/generator.py:38-58, residual.py:27,64,67, discriminator.py:31-69 and the esrgan twins).
 #include <algorithm>
 #include <cstdio>
-#include <type_traits>
 #include <cstdlib>
+#include <type_traits>
 #include "conv_params.h"
 #include "launch.h"
 #include "ptx.cuh"
