@@ -1,2 +1,4 @@
-for i in 1 2 3; do timeout 600 python -m pytest tests -m gpu -q --timeout=600 -x -k "c1_fixture or large_image or inference_plan or eval_mode" 2>&1 | tail -1; done
-timeout 300 python tools/bench_infer.py 2>&1 | tail -1 | cut -c60-170
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 -x -k "generator or golden or gan_step or pretrain or stage or cli or packed" 2>&1 | tail -2
+timeout 600 python bench.py --only b64 --steps 20 --warmup 5 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('b16', round(d['value']), d['ms_per_step'], 'b64', round(d['b64']['value']), d['b64']['ms_per_step'])"

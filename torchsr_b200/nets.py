@@ -166,8 +166,8 @@ def define_srgan_generator(m, plan: Plan, shape):
     Y = plan.buf("Y", B * r3.cout * Hf * Wf, F32)
     fwd.add(ops.elt(L.E_ZERO, p=[Y], i=[Y.numel() * 4]))
     geom3 = ops.fwd_geometry(Hf, Wf, r3.k, 1, r3.pad, 0, 1)
-    if plan.infer_only and r3.k == 9 and r3.cout == 3 and r3.cin == 64 and Hf % 2 == 0:
-        # Inference plans: TWO output rows per GEMM row. The GEMM row (n, y2, x) reads input rows 2*y2 - 4 .. 2*y2 + 5 (ten
+    if r3.k == 9 and r3.cout == 3 and r3.cin == 64 and Hf % 2 == 0:
+        # TWO output rows per GEMM row (forward only; backward keeps the one-row packs). The GEMM row (n, y2, x) reads input rows 2*y2 - 4 .. 2*y2 + 5 (ten
         # vertical taps, traversal stride 2 along H) against N = 2 x 32 columns (r, kw, c): output row 2*y2 + r uses tap
         # kh' with the weights of kh = kh' - r. Twice the columns per fetched activation tile: an N = 64 UMMA reads 6 KB of
         # operands for twice the work of the 5 KB an N = 32 UMMA reads (the launch is bound by exactly that).
