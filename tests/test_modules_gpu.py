@@ -514,6 +514,23 @@ def test_large_image_inference_staged_halo_paths_match_oracle_and_generic_kernel
     assert d <= 1e-2 and e_new <= 1.25 * e_old + 2e-3, (e_new, e_old, d)
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 37, 53), (2, 3, 64, 100), (1, 3, 131, 259)], ids=lambda s: "x".join(map(str, s)))
+def test_inference_odd_image_sizes(shape):
+    """Eval-mode inference on sizes that divide nothing: partial halo strips / row tiles, accumulator tiles that straddle
+    image rows in the two-rows-per-GEMM-row output conv, M not a multiple of 128, batch of two images."""
+    MC, SG, SD, EG, ED = _mods()
+    torch.manual_seed(24)
+    G = SG()
+    MC.randomize_bn(G)
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    x = torch.rand(*shape)
+    with torch.no_grad():
+        ref = MC.O.srgan_generator(sd, x, False)
+        y = G.cuda().eval()(x.cuda()).cpu()
+    assert y.shape == ref.shape and torch.isfinite(y).all()
+    assert MC.rel_l2(y, ref) <= 3e-2, MC.rel_l2(y, ref)
+
+
 def test_inference_plan_packs_follow_the_weights():
     """The inference plans keep their own packs of the two 9x9 layers (row-decomposed input conv, two output rows per GEMM
     row in the output conv), derived from the fp32 parameters by a kernel of the plan's own launch list: a changed
