@@ -863,7 +863,17 @@ int launch_range(const tsr_prog* p, int first, int last, cudaStream_t st) {
         if (ce != cudaSuccess) return fail(-45, "join failed: %s", cudaGetErrorString(ce));
       }
       if (op.kind == tsr_prog::CONV) {
-        ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st, pdl_on && chain);
+        // experiment switch (profiles/r02c_two_ctas_per_sm.md): grid-barrier launches of more than one CTA per SM
+        // without the programmatic-launch attribute
+        static const bool big_barrier_pdl = [] {
+          const char* e = getenv("TSR_PDL_BIG_BARRIER");
+          return !(e && e[0] == '0');
+        }();
+        const tsr::ConvParams& cp = op.conv.p;
+        const bool big_barrier = (cp.epi.bnf_mode == 1 || cp.epi.bnr_apply) && !cp.persistent &&
+                                 static_cast<long>((cp.M_total + tsr::kBlockM - 1) / tsr::kBlockM) * op.conv.tiles_n > 148;
+        ce = tsr::launch_conv_igemm(op.conv.p, op.conv.tiles_n, op.conv.splits, st,
+                                    pdl_on && chain && (big_barrier_pdl || !big_barrier));
       } else if (op.kind == tsr_prog::CONV_GROUP) {
         ce = tsr::launch_conv_group(p->groups[op.group].g, p->groups[op.group].n, st, pdl_on && chain);
       } else {
