@@ -78,6 +78,48 @@ def test_extent_validation_rejects_out_of_bounds():
         ops.validate(e)
 
 
+def test_extent_validation_of_the_gather_and_replicating_stores():
+    """OUT_GATHER_W (one and two output rows per GEMM row) and out_rep2x descriptors: extents of the fp32 NCHW image /
+    the x2 tensor are checked, incomplete combinations are rejected."""
+    from torchsr_b200 import _lib as L
+    from torchsr_b200 import ops
+    B, H, W = 1, 8, 8
+    x = torch.zeros(B * H * W * 64, dtype=torch.bfloat16)
+    # two output rows per GEMM row: ten vertical taps, stride 2 along H, 64 columns
+    w2 = torch.zeros(10 * 64 * 64, dtype=torch.bfloat16)
+    geom2 = dict(lower_h=-4, lower_w=0, upper_h=-5, upper_w=0, Ho=H // 2, Wo=W, stride=2, stride_w=1,
+                 taps=[(k, 0, k) for k in range(10)])
+    img = torch.zeros(B * 3 * H * W)
+    d = ops.conv_desc(x=x, N=B, H=H, W=W, C=64, x_ld=64, geom=geom2, w=w2, cout_pad=64, w_ld=64, n_slots=10, block_n=64,
+                      out=img, os_n=0, os_h=0, os_w=0, n_valid=64, gather=dict(k=9, pad=4, c=3, bias=torch.zeros(3), rows=2))
+    assert d.out_mode == L.OUT_GATHER_W and d.gather_rows == 2 and d.stride == 2 and d.stride_w == 1
+    ops.validate(d)
+    d.out = ops.ptr(torch.zeros(B * 3 * H * W - 4))          # image too small
+    with pytest.raises(ops.ExtentError):
+        ops.validate(d)
+    # one row per GEMM row needs 32 columns
+    w1 = torch.zeros(9 * 32 * 64, dtype=torch.bfloat16)
+    geom1 = ops.fwd_geometry(H, W, 9, 1, 4, 0, 1)
+    d1 = ops.conv_desc(x=x, N=B, H=H, W=W, C=64, x_ld=64, geom=geom1, w=w1, cout_pad=32, w_ld=64, n_slots=9, block_n=32,
+                       out=img, os_n=0, os_h=0, os_w=0, n_valid=32, gather=dict(k=9, pad=4, c=3))
+    ops.validate(d1)
+    d1.gather_rows = 2
+    with pytest.raises(ops.ExtentError):
+        ops.validate(d1)
+    # nearest x2 replica of the result
+    w3 = torch.zeros(9 * 64 * 64, dtype=torch.bfloat16)
+    out = torch.zeros(B * H * W * 64, dtype=torch.bfloat16)
+    up = torch.zeros(B * 2 * H * 2 * W * 64, dtype=torch.bfloat16)
+    g3 = ops.fwd_geometry(H, W, 3, 3, 1, 1, 1)
+    d3 = ops.conv_desc(x=x, N=B, H=H, W=W, C=64, x_ld=64, geom=g3, w=w3, cout_pad=64, w_ld=64, n_slots=9, block_n=64, out=out,
+                       os_n=H * W * 64, os_h=W * 64, os_w=64, n_valid=64,
+                       rep2x=dict(t=up, strides=(4 * H * W * 64, 2 * W * 64, 64)))
+    ops.validate(d3)
+    d3.out_rep2x = ops.ptr(torch.zeros(B * 2 * H * 2 * W * 64 - 64, dtype=torch.bfloat16))
+    with pytest.raises(ops.ExtentError):
+        ops.validate(d3)
+
+
 def test_modules_fail_loudly_without_cuda():
     from torchsr_b200 import _lib as L
     from torchsr_b200.srgan.generator import Generator
