@@ -1,7 +1,10 @@
-export TSR_OCCUPANCY=own TSR_PDL_BIG_BARRIER=0
-TOP=2 timeout 100 python tools/profile_step.py 64 2>&1 | tail -3 | cut -c1-160 > gpurun_out/exp_bigbarrier.log; cat gpurun_out/exp_bigbarrier.log
-if grep -q "GPU span [0-9]\.[0-9]* ms" gpurun_out/exp_bigbarrier.log; then
-timeout 200 python bench.py --only b64 --steps 30 --warmup 5 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('own+nopdl-big: b16', round(d['value']), d['ms_per_step'], 'b64', round(d['b64']['value']), d['b64']['ms_per_step'], d['b64']['launches_per_step'])"
-fi
+# scratch command file for `gpurun -- bash tools/_scratch_run.sh` (overwritten per experiment)
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 2>&1 > gpurun_out/pytest_final.log; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/pytest_final.log | tail -5
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 200 gpurun_out/bench_final.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[-1])
+print('b16', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'b64', d['b64']['value'], 'infer', d['inference']['value'], d['inference']['e2e']['value'], 'esrgan', d['esrgan']['value'], 'launches', d['launches_per_step'], d['clocks'])
+"
