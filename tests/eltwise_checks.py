@@ -57,6 +57,26 @@ def check_gather_out(B=2, C=3, H=8, W=10, KW=9, seed=2):
     return {"out": rel_l2(out, ref)}
 
 
+def check_gather_out_3x3(B=3, H=19, W=45, sign=-1, seed=4):
+    """3x3 taps x 3 channels in fp32 rows of 32 columns (the tiled kernel): out[n,c,h,w] = bias[c] + sum over the taps of
+    T[n, h + sign*(kh-1), w + sign*(kw-1), (kh*3+kw)*3 + c]."""
+    g = torch.Generator().manual_seed(seed)
+    C, K = 3, 3
+    T = torch.randn(B, H, W, 32, generator=g)
+    bias = torch.randn(C, generator=g)
+    out = torch.full((B, C, H, W), float("nan"), device=DEV)
+    ops.run_now(ops.elt(L.E_GATHER_OUT, p=[T.to(DEV), out, bias.to(DEV)], i=[B, C, H, W, K, K, 1, 1, sign, 32, 0]))
+    sync_check()
+    ref = bias.view(1, C, 1, 1).repeat(B, 1, H, W)
+    Tp = torch.nn.functional.pad(T.permute(0, 3, 1, 2), (1, 1, 1, 1))      # [B, 32, H+2, W+2]
+    for kh in range(K):
+        for kw in range(K):
+            dh, dw = sign * (kh - 1), sign * (kw - 1)
+            t = kh * K + kw
+            ref += Tp[:, t * C:(t + 1) * C, 1 + dh:1 + dh + H, 1 + dw:1 + dw + W]
+    return {"out": rel_l2(out, ref)}
+
+
 def check_bn_train(M=1000, C=64, act=L.ACT_PRELU, residual=True, seed=3):
     """column sums (as the conv epilogue leaves them) -> fused BN_ACT, then BN_BWD_REDUCE + BN_BWD_APPLY, against
     autograd through F.batch_norm / prelu / leaky_relu."""

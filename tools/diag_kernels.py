@@ -35,6 +35,8 @@ CHECKS = [
     ("im2row_9x9", lambda: E.check_im2row(KH=9, KW=9)),
     ("im2row_row_bwd", lambda: E.check_im2row(KH=1, KW=9, sign=-1)),
     ("gather_out", lambda: E.check_gather_out()),
+    ("gather_out_3x3_tiled", lambda: E.check_gather_out_3x3()),
+    ("gather_out_3x3_tiled_fwd_sign", lambda: E.check_gather_out_3x3(B=1, H=8, W=32, sign=1)),
     ("bn_prelu_res", lambda: E.check_bn_train()),
     ("bn_leaky_c512", lambda: E.check_bn_train(M=600, C=512, act=L.ACT_LEAKY, residual=False)),
     ("bn_none", lambda: E.check_bn_train(M=333, C=64, act=L.ACT_NONE, residual=False)),

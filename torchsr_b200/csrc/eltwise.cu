@@ -240,6 +240,50 @@ __global__ void gather_out_kernel(const void* __restrict__ T, float* __restrict_
   }
 }
 
+// Tiled variant for the 3-channel 3x3 case with fp32 rows of 32 columns (gradient w.r.t. the discriminator's input in
+// the generator step: on the critical path between D's backward and G's backward): a block stages the rows of a
+// (TH + 2) x (TW + 2) pixel patch in shared memory with coalesced 128-byte reads, then every thread sums the nine taps
+// of one output element - the kernel above reads nine half-used sectors per output straight from L2.
+__global__ void __launch_bounds__(256) gather_out3x3_tiled_kernel(const float* __restrict__ T, float* __restrict__ out,
+                                                                  const float* __restrict__ bias, int B, int H, int W,
+                                                                  int sign) {
+  constexpr int TH = 8, TW = 32, PH = TH + 2, PW = TW + 2, C = 3, LD = 32, SLD = 28;   // 27 used columns, padded to 28
+  __shared__ float patch[PH * PW][SLD];
+  pdl_sync();
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+  const long long n_tiles = static_cast<long long>(B) * tiles_h * tiles_w;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tw = static_cast<int>(t % tiles_w);
+    const int th = static_cast<int>((t / tiles_w) % tiles_h);
+    const long long n = t / (static_cast<long long>(tiles_w) * tiles_h);
+    const int h0 = th * TH - 1, w0 = tw * TW - 1;
+    __syncthreads();
+    // 8 threads per pixel row fetch its 32 floats as float4 (28 kept)
+    for (int i = threadIdx.x; i < PH * PW * 8; i += 256) {
+      const int q = i & 7, pp = i >> 3;
+      const int ph_ = pp / PW, pw_ = pp - ph_ * PW;
+      const int hh = h0 + ph_, ww = w0 + pw_;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = __ldg(reinterpret_cast<const float4*>(T + ((n * H + hh) * W + ww) * LD) + q);
+      if (q < 7) *reinterpret_cast<float4*>(&patch[pp][4 * q]) = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * TH * TW; i += 256) {
+      const int wl = i % TW, hl = (i / TW) % TH, c = i / (TW * TH);
+      const int h = th * TH + hl, w = tw * TW + wl;
+      if (h >= H || w >= W) continue;
+      float acc = bias ? __ldg(bias + c) : 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          acc += patch[(hl + 1 + sign * (kh - 1)) * PW + wl + 1 + sign * (kw - 1)][(kh * 3 + kw) * C + c];
+      out[((n * C + c) * H + h) * W + w] = acc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- layout
 // NCHW2NHWC: p0 = x fp32 NCHW, p1 = y bf16 NHWC (pixel stride ld, channel offset off); i: 0 B,1 C,2 H,3 W,4 ld,5 off
 // channels are processed in groups of 8 (C%8==0)
@@ -1586,6 +1630,13 @@ cudaError_t launch_elt(const tsr_elt_desc_t& d, cudaStream_t st, bool pdl) {
           (const float*)p[0], (bf16*)p[1], i[0], i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8], i[9]);
       break;
     case TSR_E_GATHER_OUT:
+      if (i[1] == 3 && i[4] == 3 && i[5] == 3 && i[6] == 1 && i[7] == 1 && i[9] == 32 && i[10] == 0 &&
+          (reinterpret_cast<uintptr_t>(p[0]) & 15) == 0) {
+        const long long n_tiles = i[0] * ((i[2] + 7) / 8) * ((i[3] + 31) / 32);
+        ce = launch_k(gather_out3x3_tiled_kernel, dim3(static_cast<unsigned>(n_tiles < 148 * 8 ? n_tiles : 148 * 8)), dim3(256), 0,
+                      st, pdl, (const float*)p[0], (float*)p[1], (const float*)p[2], i[0], i[2], i[3], i[8]);
+        break;
+      }
       ce = launch_k(gather_out_kernel, dim3(grid_for(i[0] * i[1] * i[2] * i[3])), dim3(256), 0, st, pdl, p[0], (float*)p[1], (const float*)p[2], i[0],
                                                                           i[1], i[2], i[3], i[4], i[5], i[6], i[7], i[8],
                                                                           i[9], i[10]);
