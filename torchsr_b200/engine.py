@@ -736,9 +736,11 @@ class Plan:
         M, C = g.M, g.C
         rpb = max(32, -(-M // (2 * NUM_SMS)))
         sums = self.zbuf("bwd", name + ".cs", 2 * C)
+        # parameter gradients only: both launches ride the weight-gradient side branch (consecutive side ops share one
+        # branch, in order), off the critical path of backward
         prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[g.t, g.t, None, None, sums, None, None],
-                         i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2]))
-        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0, shuffle_c4]))
+                         i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2], side=True))
+        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0, shuffle_c4], side=True))
 
     def colsum_strided(self, prog, name: str, g: Act, out_vec: torch.Tensor):
         """colsum for a channel slice of a wider buffer."""
@@ -747,8 +749,8 @@ class Plan:
         sums = self.zbuf("bwd", name + ".cs", 2 * C)
         gp = ops.ptr(g.t, g.c0)
         prog.add(ops.elt(L.E_BN_BWD_REDUCE, p=[gp, gp, None, None, sums, None, None],
-                         i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2]))
-        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0]))
+                         i=[M, C, L.ACT_NONE, rpb, g.ld, g.ld, 0], f=[0.2], side=True))
+        prog.add(ops.elt(L.E_COLSUM_FINALIZE, p=[sums, out_vec], i=[1, C, C, 0, 0], side=True))
 
     def conv_wgrad(self, prog, rec: ConvRec, x: Act, dy: Act, geom: Optional[dict] = None):
         geom = geom or ops.fwd_geometry(x.H, x.W, rec.k, rec.k, rec.pad, rec.pad, rec.stride)
