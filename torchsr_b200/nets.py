@@ -80,7 +80,7 @@ def subpixel_stage(plan: Plan, prog, name: str, layer, rec: ConvRec, x: Act, con
     def bwd(bp, g, want_x, want_w):
         assert g is dconv, "the consumer of a sub-pixel stage must honour its gradient hook"
         if want_w:
-            bp.add(ops.elt(L.E_SUM_FINALIZE, p=[dap, store.grad_slice(alpha)], i=[1, 0], f=[1.0]))
+            bp.add(ops.elt(L.E_SUM_FINALIZE, p=[dap, store.grad_slice(alpha)], i=[1, 0], f=[1.0], side=True))   # parameter gradient only
             plan.colsum(bp, name + ".db", g, store.grad_slice(rec.bias), shuffle_c4=rec.cout // 4)
             plan.conv_wgrad(bp, rec, x, g)
         return plan.conv_dgrad(bp, name, rec, g, x)
@@ -211,7 +211,8 @@ def define_srgan_generator(m, plan: Plan, shape):
 
     def bwd_conv3(bp, g, want_x, want_w):
         if want_w:
-            bp.add(ops.elt(L.E_COLSUM_FINALIZE, p=[cs, store.grad_slice(r3.bias)], i=[CHANSUM_SPLITS, r3.cout, r3.cout, 0, 0]))
+            bp.add(ops.elt(L.E_COLSUM_FINALIZE, p=[cs, store.grad_slice(r3.bias)], i=[CHANSUM_SPLITS, r3.cout, r3.cout, 0, 0],
+                           side=True))
             plan.conv_wgrad(bp, r3, u_last, E3, geom=geom3)
         return plan.conv_dgrad(bp, "conv3", r3, E3, u_last)
 
@@ -672,7 +673,8 @@ def define_esrgan_generator(m, plan: Plan, shape):
 
     def bwd_conv4(bp, g, want_x, want_w):
         if want_w:
-            bp.add(ops.elt(L.E_COLSUM_FINALIZE, p=[cs, store.grad_slice(r4.bias)], i=[CHANSUM_SPLITS, r4.cout, r4.cout, 0, 0]))
+            bp.add(ops.elt(L.E_COLSUM_FINALIZE, p=[cs, store.grad_slice(r4.bias)], i=[CHANSUM_SPLITS, r4.cout, r4.cout, 0, 0],
+                           side=True))
             plan.conv_wgrad(bp, r4, u3, E4)
         return plan.conv_dgrad(bp, "conv4", r4, E4, u3)
 
