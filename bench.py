@@ -822,8 +822,9 @@ def run_b200(args):
                              f"{pk['source']} sustained bf16 peak; with the VGG19 FLOPs (+21.50/crop) "
                              f"the step sustains {value * (GFLOP_PER_CROP_GD + GFLOP_PER_CROP_VGG) / 1e3 / world:.1f} TFLOP/s",
                      "dominant_kernel": dom, "trunk_conv_only": kern,
-                     "ncu": "profiles/r02_* (launch list of one step, --set full summaries of the conv, weight-gradient, "
-                            "BatchNorm and Adam kernels); r01* = round 1"},
+                     "ncu": "profiles/r02d_* / r02g_ncu_launches_step.csv (launch list of one step of the final build, --set full "
+                            "summaries of the conv, weight-gradient, BatchNorm and Adam kernels), r02f_* (inference kernels); "
+                            "r02, r02b = earlier builds of round 2, r01* = round 1"},
     }
     if parity is not None:
         line["dp_parity"] = parity

@@ -1,3 +1,4 @@
-# scratch command file for `gpurun -- bash tools/_scratch_run.sh` (overwritten per experiment)
-timeout 1500 python -m pytest tests -m gpu -q --timeout=600 2>&1 | tail -3
-timeout 900 python bench.py
+mkdir -p gpurun_out
+export TSR_GRAPHS=0
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/r02g_ncu_launches_step.csv python tools/ncu_step.py 16 > gpurun_out/ncu_step_g.log 2>&1; tail -1 gpurun_out/ncu_step_g.log; wc -l gpurun_out/r02g_ncu_launches_step.csv
